@@ -1,0 +1,237 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE ITSELF (/root/reference) on small synthetic inputs.
+
+TEST INFRASTRUCTURE ONLY -- run in the build container (where /root/reference exists):
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz
+
+The reference's own classes are used unmodified through oracle/ref_shims.py:
+  core.collector.Collector                       (core/collector.py:20-367)
+  core.policy.ppo.PPOPolicy                      (core/policy/ppo.py:14-246)
+  core.state_tracker.StateTrackerTransformer     (core/state_tracker.py:128-250)  dropout=0
+  core.env.simulatedEnv.simulated_env.SimulatedEnv over KuaishouEnv / VirtualTB
+  tianshou DummyVectorEnv / VectorReplayBuffer / Net / Actor / Critic / ActorProb
+Only three things are instrumented, none of which changes arithmetic:
+  * users: python ``random`` is seeded so KuaishouEnv.__user_generator (kuaishouEnv.py:155-159) is replayable,
+    and the drawn users are recorded from the reset observations;
+  * Categorical.sample is replaced by its own algorithm made explicit, argmax(p / q), q ~ Exp(1) from the same
+    torch generator (bit-identical to torch.multinomial), so the noise q can be recorded;
+  * np.random is seeded before every policy.update so minibatch permutations (batch.py:733-744) are replayable.
+Every recorded array is what the reference computed; the oracle restatement (oracle/*.py) and the CUDA path are
+both tested against these files.
+"""
+import os
+import random
+import sys
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+
+ref_shims.install()
+
+import torch  # noqa: E402
+import pandas as pd  # noqa: E402
+import gym  # noqa: E402
+from sklearn.preprocessing import LabelEncoder  # noqa: E402
+
+from core.collector import Collector  # noqa: E402
+from core.policy.ppo import PPOPolicy  # noqa: E402
+from core.state_tracker import StateTrackerTransformer  # noqa: E402
+from core.inputs import get_dataset_columns  # noqa: E402
+from tianshou.data import VectorReplayBuffer  # noqa: E402
+from tianshou.env import DummyVectorEnv  # noqa: E402
+from tianshou.utils.net.common import Net  # noqa: E402
+from tianshou.utils.net.discrete import Actor, Critic  # noqa: E402
+
+from cirs_codes_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class Recorder:
+    def __init__(self):
+        self.turns = []  # per collect: list of dict per turn
+        self.cur = None
+
+    def new_collect(self):
+        self.turns.append([])
+
+    def turn(self):
+        self.turns[-1].append({})
+        return self.turns[-1][-1]
+
+
+def _sd(module, prefix):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def kuaishou_case(name, U=40, I=160, B=6, T=8, N=1, thr=0, d=16, nhead=4, tau=100.0, gamma_exposure=10.0,
+                  r_decay=1.0, version="v1", batch_size=16, repeat=2, iters=2, seed=7, use_ab=True):
+    tb = synth.kuaishou_tables(U, I, seed=seed)
+    list_feat = synth.cats_to_list_feat(tb["cats"])
+    dist = synth.jaccard_distance_matrix(tb["cats"])
+    lbe_user = LabelEncoder().fit(np.arange(U))
+    lbe_photo = LabelEncoder().fit(np.arange(I))
+    gym.register(id="KuaishouEnv-v0", entry_point="environments.KuaishouRec.env.kuaishouEnv:KuaishouEnv",
+                 kwargs=dict(mat=tb["mat"].astype(np.float64), lbe_user=lbe_user, lbe_photo=lbe_photo,
+                             num_leave_compute=N, leave_threshold=thr, max_turn=T, list_feat=list_feat,
+                             df_photo_env=None, df_dist_small=pd.DataFrame(dist)))
+    env = gym.make("KuaishouEnv-v0")
+    gym.register(id="SimulatedEnv-v0", entry_point="core.env.simulatedEnv.simulated_env:SimulatedEnv",
+                 kwargs=dict(user_model=torch.nn.Identity(), task_name="KuaishouEnv-v0", version=version, tau=tau,
+                             alpha_u=tb["alpha_u"].reshape(-1, 1) if use_ab else None,
+                             beta_i=tb["beta_i"].reshape(-1, 1) if use_ab else None,
+                             normed_mat=tb["normed_mat"].astype(np.float64),
+                             gamma_exposure=gamma_exposure, r_decay=r_decay))
+    train_envs = DummyVectorEnv([lambda: gym.make("SimulatedEnv-v0") for _ in range(B)])
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    train_envs.seed(seed)
+
+    cols = get_dataset_columns(d, envname="KuaishouEnv-v0", env=env)
+    tracker = StateTrackerTransformer(cols[0], cols[1], cols[2], dim_model=d, dim_state=20, dim_max_batch=B,
+                                      dataset="KuaishouEnv-v0", has_user_embedding=cols[3],
+                                      has_action_embedding=cols[4], has_feedback_embedding=cols[5],
+                                      nhead=nhead, d_hid=128, nlayers=2, dropout=0.0, device="cpu", seed=seed,
+                                      MAX_TURN=T)
+    # "trained-like" embeddings so the encoder is numerically non-trivial (init N(0,1e-4) makes tokens ~0)
+    with torch.no_grad():
+        for emb in tracker.embedding_dict.values():
+            emb.weight.normal_(0, 0.1)
+    net = Net(20, hidden_sizes=[64, 64], device="cpu")
+    actor = Actor(net, I, device="cpu")
+    critic = Critic(net, device="cpu")
+    for m in list(actor.modules()) + list(critic.modules()):
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.orthogonal_(m.weight)
+            torch.nn.init.zeros_(m.bias)
+    optim_RL = torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=1e-3)
+    optim_state = torch.optim.Adam(tracker.parameters(), lr=1e-3)
+    policy = PPOPolicy(actor, critic, [optim_RL, optim_state], torch.distributions.Categorical,
+                       discount_factor=0.95, max_grad_norm=0.5, eps_clip=0.2, vf_coef=0.25, ent_coef=0.0,
+                       reward_normalization=1, advantage_normalization=1, recompute_advantage=0, value_clip=1,
+                       gae_lambda=0.95, action_space=train_envs.action_space[0] if hasattr(
+                           train_envs, "action_space") else env.action_space,
+                       action_bound_method="", action_scaling=False)
+    rec = Recorder()
+
+    # --- instrumentation (recording only) ---
+    def sample_explicit(self, sample_shape=torch.Size()):
+        p = self.probs
+        q = torch.empty_like(p).exponential_(1)
+        rec.cur["q"] = q.numpy().copy()
+        rec.cur["probs"] = p.detach().numpy().copy()
+        return torch.argmax(p / q, dim=-1)
+
+    torch.distributions.Categorical.sample = sample_explicit
+    orig_forward = policy.forward
+
+    def fwd(batch, *a, **k):
+        if not policy.updating:
+            rec.cur = rec.turn()
+            rec.cur["state"] = batch.obs.detach().numpy().copy()
+        return orig_forward(batch, *a, **k)
+
+    policy.forward = fwd
+    orig_build = tracker.build_state
+
+    def build(**k):
+        out = orig_build(**k)
+        if k.get("obs") is not None:
+            rec.new_collect()
+            rec.reset_obs = np.asarray(k["obs"]).copy()
+            rec.s0 = out["obs"].detach().numpy().copy()
+        elif k.get("obs_next") is not None:
+            c = rec.cur
+            c["env_id"] = np.asarray(k["env_id"]).copy()
+            c["obs_next_raw"] = np.asarray(k["obs_next"]).copy()
+            c["rew"] = np.asarray(k["rew"], dtype=np.float64).copy()
+            c["done"] = np.asarray(k["done"]).copy()
+            c["state_next"] = out["obs_next"].detach().numpy().copy()
+        return out
+
+    collector = Collector(policy, train_envs, VectorReplayBuffer(B * (T + 2), B), preprocess_fn=build)
+
+    out = dict(cfg=np.array([U, I, B, T, N, thr, d, nhead, batch_size, repeat, iters, seed], dtype=np.int64),
+               cfg_f=np.array([tau, gamma_exposure, r_decay, 1.0 if version == "v1" else 2.0, float(use_ab)]),
+               **{k: v for k, v in tb.items()})
+    out.update(_sd(tracker, "init/tracker/"))
+    out.update(_sd(actor, "init/actor/"))
+    out.update(_sd(critic, "init/critic/"))
+
+    policy.train()
+    random.seed(seed + 1)
+    for it in range(iters):
+        res = collector.collect(n_episode=B)
+        buf = collector.buffer
+        turns = rec.turns[-1]
+        P = f"it{it}/"
+        out[P + "users"] = rec.reset_obs[:, 0].astype(np.int64)
+        out[P + "s0"] = rec.s0
+        out[P + "n_turns"] = np.array(len(turns))
+        for t, c in enumerate(turns):
+            for k, v in c.items():
+                out[P + f"turn{t}/{k}"] = v
+        idx = buf.sample_index(0)
+        out[P + "buf/index"] = idx
+        out[P + "buf/obs"] = buf.obs[idx].detach().numpy().copy()
+        out[P + "buf/obs_next"] = buf.obs_next[idx].detach().numpy().copy()
+        out[P + "buf/act"] = buf.act[idx].copy()
+        out[P + "buf/rew"] = buf.rew[idx].copy()
+        out[P + "buf/done"] = buf.done[idx].copy()
+        out[P + "buf/lengths"] = buf._lengths.copy()
+        out[P + "buf/sub_size"] = np.array(buf.buffers[0].maxsize)
+        for k in ("n/ep", "n/st", "rews", "lens", "idxs", "rew", "len", "rew_std", "len_std"):
+            out[P + "res/" + k.replace("/", "_")] = np.asarray(res[k])
+        # update with replayable minibatch permutations
+        useed = 1000 + it
+        np.random.seed(useed)
+        captured = {}
+        orig_process = policy.process_fn
+
+        def proc(batch, buffer, indice):
+            b = orig_process(batch, buffer, indice)
+            captured["v_s"] = b.v_s.numpy().copy()
+            captured["returns"] = b.returns.numpy().copy()
+            captured["adv"] = b.adv.numpy().copy()
+            captured["logp_old"] = b.logp_old.numpy().copy()
+            return b
+
+        policy.process_fn = proc
+        losses = policy.update(0, buf, batch_size=batch_size, repeat=repeat)
+        policy.process_fn = orig_process
+        out[P + "upd/seed"] = np.array(useed)
+        for k, v in captured.items():
+            out[P + "upd/" + k] = v
+        for k, v in losses.items():
+            out[P + "upd/" + k.replace("/", "_")] = np.array(v, dtype=np.float64)
+        out[P + "upd/ret_rms"] = np.array([policy.ret_rms.mean, policy.ret_rms.var, policy.ret_rms.count],
+                                          dtype=np.float64)
+        out.update(_sd(tracker, P + "after/tracker/"))
+        out.update(_sd(actor, P + "after/actor/"))
+        out.update(_sd(critic, P + "after/critic/"))
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB;",
+          "turns per collect:", [len(t) for t in rec.turns], "lens it0:", out["it0/res/lens"])
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    # reference defaults N=1, thr=0 (CIRS-RL-kuaishou.py:70-71): leave as soon as the action shares a category
+    kuaishou_case("kuaishou_N1", N=1, thr=0, T=8, seed=7, batch_size=7)
+    # BASELINE config 3 window: N=5 exercises the negative-slice quirk; r_decay<1 exercises repeat decay
+    kuaishou_case("kuaishou_N5", N=5, thr=1, T=10, B=5, d=32, seed=11, r_decay=0.9, batch_size=6)
+    # version v2 reward (r - e) with identity clip0, no alpha/beta
+    kuaishou_case("kuaishou_v2", N=3, thr=2, T=6, B=4, d=16, nhead=2, seed=13, version="v2", use_ab=False,
+                  gamma_exposure=0.05, tau=5.0, batch_size=5)
+
+
+if __name__ == "__main__":
+    main()
