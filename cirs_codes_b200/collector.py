@@ -1,0 +1,202 @@
+"""Collector: the rollout driver (core/collector.py:20-367, CIRS's fork of tianshou 0.4.2's Collector).
+
+Same constructor and ``collect`` result as the reference: ``Collector(policy, env, buffer, preprocess_fn,
+exploration_noise, remove_recommended_ids, force_length)``, ``collect(n_episode=...) -> {"n/ep", "n/st", "rews",
+"lens", "idxs", "rew", "len", "rew_std", "len_std"}``; the fork's behaviour is kept: everything is reset at the
+start of every collect (:201), the buffer is emptied (:113-121), finished environments are dropped from the ready
+set and never reset (:294-311), ``force_length`` overrides ``done`` (:253-258).
+
+Two execution paths with identical results:
+  * generic  -- the reference's loop, one call per component per turn through the numpy / Batch interfaces
+               (policy() -> env.step() -> preprocess_fn() -> buffer.add()); any duck-typed env / policy works;
+  * fused    -- when env, tracker, policy and buffer are this package's device-resident objects and
+               n_episode == env_num: per turn three kernel launches (actor sample -> env step -> tracker step)
+               on per-slot device arrays with an ``active`` mask; no host synchronisation inside the loop except
+               a non-blocking poll of "how many environments are still running"; trajectories are written by the
+               kernels straight into the replay buffer's env-major slots.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .data import Batch, VectorReplayBuffer
+from .env import KuaishouVectorEnv
+from .state_tracker import StateTrackerTransformer
+
+
+class Collector:
+    def __init__(self, policy, env, buffer=None, preprocess_fn=None, exploration_noise=False,
+                 remove_recommended_ids=False, force_length=0, fused=True):
+        self.policy, self.env = policy, env
+        self.env_num = len(env)
+        self.exploration_noise = exploration_noise
+        self.preprocess_fn = preprocess_fn
+        self.remove_recommended_ids = remove_recommended_ids
+        self.force_length = int(force_length)
+        self._action_space = getattr(env, "action_space", None)
+        if buffer is None:
+            buffer = VectorReplayBuffer(self.env_num * (getattr(env, "max_turn", 100) + 1), self.env_num)
+        assert buffer.buffer_num >= self.env_num
+        self.buffer = buffer
+        self.tracker = getattr(preprocess_fn, "__self__", None)
+        self.fused = bool(fused and isinstance(env, KuaishouVectorEnv)
+                          and isinstance(self.tracker, StateTrackerTransformer)
+                          and hasattr(policy, "sample_device") and isinstance(buffer, VectorReplayBuffer)
+                          and buffer.buffer_num == self.env_num and not remove_recommended_ids)
+        self.data = Batch()
+        self.reset_stat()
+
+    # ------------------------------------------------------------------ resets (collector.py:99-134)
+    def reset(self, users=None):
+        self.data = Batch(obs={}, act={}, rew={}, done={}, obs_next={}, info={}, policy={})
+        self.reset_env(users)
+        self.reset_buffer()
+        self.reset_stat()
+
+    def reset_stat(self):
+        self.collect_step, self.collect_episode, self.collect_time = 0, 0, 0.0
+
+    def reset_buffer(self, keep_statistics=False):
+        self.buffer.reset()
+
+    def reset_env(self, users=None):
+        if self.preprocess_fn:
+            self.preprocess_fn(dim_batch=self.env_num, reset=True)
+        obs = self.env.reset(users=users) if users is not None else self.env.reset()
+        self._reset_obs = obs
+        if self.preprocess_fn:
+            obs = self.preprocess_fn(obs=obs, env_id=np.arange(self.env_num)).get("obs", obs)
+        self.data.obs = obs
+
+    # ------------------------------------------------------------------ collect
+    def collect(self, n_step=None, n_episode=None, random=False, render=None, no_grad=True, users=None,
+                noise_fn=None):
+        """``users`` (ndarray [env_num]) injects the episode's users instead of drawing them; ``noise_fn(turn, n)``
+        supplies the Exp(1) race noise q[n, n_action] of the sampler (parity runs; generic path only)."""
+        assert not getattr(self.env, "is_async", False)
+        assert n_step is None and n_episode is not None and n_episode > 0, \
+            "CIRS collects whole episodes (n_episode == env_num, SURVEY §9 invariants)"
+        assert n_episode == self.env_num, "n_episode must equal the number of environments (collector.py:198-220)"
+        start = time.time()
+        if self.fused and not random and noise_fn is None:
+            res = self._collect_fused(users)
+        else:
+            res = self._collect_generic(n_episode, random, users, noise_fn)
+        self.collect_step += res["n/st"]
+        self.collect_episode += res["n/ep"]
+        self.collect_time += max(time.time() - start, 1e-9)
+        return res
+
+    @staticmethod
+    def _result(rews, lens, idxs):
+        if len(lens):
+            rm, rs, lm, ls = rews.mean(), rews.std(), lens.mean(), lens.std()
+        else:
+            rm = rs = lm = ls = 0
+        return {"n/ep": len(lens), "n/st": int(np.sum(lens)), "rews": rews, "lens": lens, "idxs": idxs, "rew": rm,
+                "len": lm, "rew_std": rs, "len_std": ls}
+
+    # ---- generic path: the reference's loop (collector.py:219-320)
+    def _collect_generic(self, n_episode, random, users, noise_fn):
+        ready = np.arange(min(self.env_num, n_episode))
+        self.reset(users)
+        if hasattr(self.buffer, "d_users") and np.issubdtype(np.asarray(self._reset_obs).dtype, np.integer):
+            self.buffer._alloc(self.data.obs.shape[-1])
+            self.buffer.d_users.copy_(torch.as_tensor(np.asarray(self._reset_obs).reshape(-1).astype(np.int32)))
+        step_count = episode_count = cnt_loop = 0
+        ep_rews, ep_lens, ep_idxs = [], [], []
+        while True:
+            assert len(self.data.obs) == len(ready)
+            if random:
+                act = np.array([self._action_space[i % len(self._action_space)].sample() for i in ready])
+                self.data.update(act=act)
+            else:
+                kw = {} if noise_fn is None else {"noise_q": noise_fn(cnt_loop, len(ready))}
+                result = self.policy(self.data, self.buffer, state=None,
+                                     remove_recommended_ids=self.remove_recommended_ids, **kw)
+                act = result.act
+                act = act.detach().cpu().numpy() if torch.is_tensor(act) else np.asarray(act)
+                if self.exploration_noise:
+                    act = self.policy.exploration_noise(act, self.data)
+                self.data.update(policy=result.get("policy", Batch()), act=act)
+            action_remap = self.policy.map_action(self.data.act)
+            obs_next, rew, done, info = self.env.step(action_remap, ready)
+            cnt_loop += 1
+            if self.force_length > 0:
+                done = np.full_like(done, cnt_loop >= self.force_length, dtype=bool)
+            self.data.update(obs_next=obs_next, rew=rew, done=done, info=info)
+            if self.preprocess_fn:
+                self.data.update(self.preprocess_fn(obs_next=self.data.obs_next, rew=self.data.rew,
+                                                    done=self.data.done, info=self.data.info,
+                                                    policy=self.data.policy, env_id=ready))
+            ptr, ep_rew, ep_len, ep_idx = self.buffer.add(self.data, buffer_ids=ready)
+            step_count += len(ready)
+            if np.any(done):
+                local = np.where(done)[0]
+                episode_count += len(local)
+                ep_lens.append(ep_len[local]); ep_rews.append(ep_rew[local]); ep_idxs.append(ep_idx[local])
+                surplus = len(ready) - (n_episode - episode_count)
+                if surplus > 0:
+                    mask = np.ones_like(ready, dtype=bool)
+                    mask[local[:surplus]] = False
+                    ready = ready[mask]
+                    self.data = Batch(obs=self.data.obs, obs_next=self.data.obs_next)[mask]
+            self.data.obs = self.data.obs_next
+            if episode_count >= n_episode:
+                break
+        if episode_count:
+            rews, lens, idxs = map(np.concatenate, (ep_rews, ep_lens, ep_idxs))
+        else:
+            rews, lens, idxs = np.array([]), np.array([], int), np.array([], int)
+        res = self._result(rews, lens, idxs)
+        res["n/st"] = step_count
+        return res
+
+    # ---- fused path
+    def _collect_fused(self, users):
+        env, trk, pol, buf, dev = self.env, self.tracker, self.policy, self.buffer, self.env.device
+        B, T = self.env_num, env.max_turn
+        buf._alloc(trk.dim_state)
+        L = buf.sub_size
+        assert L >= T or self.force_length > 0, "buffer_size must be >= env_num * max_turn (SURVEY §9 invariants)"
+        if not hasattr(self, "_f"):
+            z = lambda dt: torch.zeros(B, dtype=dt, device=dev)  # noqa: E731
+            self._f = dict(act=z(torch.int32), logp=z(torch.float32), value=z(torch.float32),
+                           cur=torch.zeros(B, trk.dim_state, dtype=torch.float32, device=dev),
+                           n_active=torch.zeros(1, dtype=torch.int32, device=dev),
+                           pin=torch.zeros(2 * T + 8, dtype=torch.int32).pin_memory(),
+                           ev=[torch.cuda.Event() for _ in range(2 * T + 8)])
+        f = self._f
+        users = env.draw_users(B) if users is None else np.asarray(users, dtype=np.int64).reshape(-1)
+        d_users = torch.from_numpy(users.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
+        self.data = Batch()
+        buf.reset()
+        trk.build_state(dim_batch=B, reset=True)
+        env.reset_device(d_users)                                   # sets active[:] = 1, turn = 0
+        buf.d_users.copy_(d_users)
+        buf.d_len.zero_()
+        trk.step_device(B, None, None, env.turn, 0, d_users, None, None, cur_state=f["cur"],
+                        traj=(L, buf.obs, buf.obs_next))            # user token -> s0 = obs[e, 0]
+        traj = (L, buf.d_act, buf.d_rew, buf.d_done)
+        max_steps = self.force_length if self.force_length > 0 else T
+        turns = 0
+        for t in range(max_steps):
+            pol.sample_device(B, f["cur"], trk.dim_state, f["act"], f["logp"], f["value"], active=env.active)
+            env.step_device(f["act"], env.rew, env.done, traj=traj, ep_len=buf.d_len, force_length=self.force_length)
+            trk.step_device(B, None, None, env.turn, t + 1, f["act"], None, env.rew, cur_state=f["cur"],
+                            traj=(L, buf.obs, buf.obs_next))
+            turns = t + 1
+            # non-blocking poll: number of environments still running after this turn
+            f["pin"][t:t + 1].copy_(env.active.sum(dtype=torch.int32).reshape(1), non_blocking=True)
+            f["ev"][t].record()
+            if t >= 2 and f["ev"][t - 2].query() and int(f["pin"][t - 2]) == 0:
+                break
+        lens = buf.d_len.cpu().numpy().astype(np.int64)             # the collect's D2H read (also a sync)
+        rews = env.cum_rew.cpu().numpy()
+        buf.set_from_device(lens)
+        order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
+        res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])
+        res["turns"] = turns
+        return res

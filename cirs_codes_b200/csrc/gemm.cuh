@@ -1,0 +1,167 @@
+// FP32 tile GEMM with functor operands -- the dense-contraction core shared by the actor head, the PPO backward
+// and the tracker's training pass.  C[M,N] (op)= sum_k A(m,k) * B(k,n).
+//
+// FP32 FFMA accumulation (not TF32/BF16 tensor-core MMA): the north-star parity bar is 1e-5 relative on
+// probabilities / losses, which single-pass TF32 (10-bit mantissa) cannot meet.
+//
+//   LA / LB : operand functors.  `float operator()(int m, int k) const` returns the element (bounds already
+//             checked by the tile loader);  `static constexpr bool INNER_IS_K` says which index is contiguous
+//             in memory, which selects the thread->element mapping of the tile loader so that global loads
+//             coalesce either way.
+//   EP      : epilogue functor  `void operator()(int m, int n, float acc) const`.
+// Tiles: BM x BN per CTA, BK per k-step, each thread TM x 4 outputs (TN fixed to 4 so every thread reads its
+// B fragment as one float4), (BM/TM) x (BN/4) threads.  blockIdx.z splits K (epilogue must then accumulate).
+#pragma once
+#include "common.cuh"
+
+namespace cirs {
+
+// ---- operand functors ---------------------------------------------------------------------------------
+// element (r, c) of a row-major matrix with optional row gather; used as A(m=r,k=c) [INNER_IS_K] ...
+struct RowMajorA {  // A(m,k) = p[row(m)*ld + k]
+  static constexpr bool INNER_IS_K = true;
+  const float* p; int64_t ld; const int32_t* row;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    return __ldg(p + (int64_t)(row ? row[m] : m) * ld + k);
+  }
+};
+struct ColMajorA {  // A(m,k) = p[row(k)*ld + m]   (the transpose of a row-major [K, M] matrix)
+  static constexpr bool INNER_IS_K = false;
+  const float* p; int64_t ld; const int32_t* row;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    return __ldg(p + (int64_t)(row ? row[k] : k) * ld + m);
+  }
+};
+struct RowMajorB {  // B(k,n) = p[row(k)*ld + n]
+  static constexpr bool INNER_IS_K = false;
+  const float* p; int64_t ld; const int32_t* row;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    return __ldg(p + (int64_t)(row ? row[k] : k) * ld + n);
+  }
+};
+struct ColMajorB {  // B(k,n) = p[n*ld + k]   (a row-major [N, K] matrix used transposed)
+  static constexpr bool INNER_IS_K = true;
+  const float* p; int64_t ld;
+  __device__ __forceinline__ float operator()(int k, int n) const { return __ldg(p + (int64_t)n * ld + k); }
+};
+
+// ---- epilogues ----------------------------------------------------------------------------------------
+struct StoreEp {  // C[row(m)*ld + n] = act(acc + bias[n]) * (mask ? mask[m*ldm+n] > 0 : 1)
+  float* c; int64_t ld; const float* bias; int relu; const int32_t* row; const float* mask; int64_t ldm;
+  __device__ __forceinline__ void operator()(int m, int n, float v) const {
+    if (bias) v += __ldg(bias + n);
+    if (relu) v = fmaxf(v, 0.f);
+    if (mask && !(mask[(int64_t)m * ldm + n] > 0.f)) v = 0.f;
+    c[(int64_t)(row ? row[m] : m) * ld + n] = v;
+  }
+};
+struct AtomicEp {  // C[m*ld + n] += acc   (split-K partial sums)
+  float* c; int64_t ld;
+  __device__ __forceinline__ void operator()(int m, int n, float v) const { atomicAdd(c + (int64_t)m * ld + n, v); }
+};
+
+// ---- kernel -------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int TM, class LA, class LB, class EP>
+__global__ void __launch_bounds__((BM / TM) * (BN / 4))
+gemm_kernel(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split, float* __restrict__ colsum) {
+  constexpr int TN = 4;
+  constexpr int NTX = BN / TN, NTY = BM / TM, NT = NTX * NTY;
+  constexpr int LDA_S = BM + 4, LDB_S = BN + 4;  // +4 keeps float4 alignment and staggers banks
+  __shared__ __align__(16) float As[BK][LDA_S];
+  __shared__ __align__(16) float Bs[BK][LDB_S];
+  static_assert(TM % 4 == 0, "TM must be a multiple of 4");
+  const int tid = threadIdx.x, tx = tid % NTX, ty = tid / NTX;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float csum = 0.f;  // column sum of B over this CTA's k-range (bias gradient), column n0 + tid % BN
+
+  for (int k0 = kb; k0 < ke; k0 += BK) {
+    // ---- stage A tile (BM x BK) as As[k][m]
+    if (LA::INNER_IS_K) {
+#pragma unroll 2
+      for (int i = tid; i < BM * BK; i += NT) {
+        const int kk = i % BK, mm = i / BK;
+        const int m = m0 + mm, k = k0 + kk;
+        As[kk][mm] = (m < M && k < ke) ? la(m, k) : 0.f;
+      }
+    } else {
+#pragma unroll 2
+      for (int i = tid; i < BM * BK; i += NT) {
+        const int mm = i % BM, kk = i / BM;
+        const int m = m0 + mm, k = k0 + kk;
+        As[kk][mm] = (m < M && k < ke) ? la(m, k) : 0.f;
+      }
+    }
+    // ---- stage B tile (BK x BN) as Bs[k][n]
+    if (LB::INNER_IS_K) {
+#pragma unroll 2
+      for (int i = tid; i < BN * BK; i += NT) {
+        const int kk = i % BK, nn = i / BK;
+        const int n = n0 + nn, k = k0 + kk;
+        Bs[kk][nn] = (n < N && k < ke) ? lb(k, n) : 0.f;
+      }
+    } else {
+#pragma unroll 2
+      for (int i = tid; i < BN * BK; i += NT) {
+        const int nn = i % BN, kk = i / BN;
+        const int n = n0 + nn, k = k0 + kk;
+        const float v = (n < N && k < ke) ? lb(k, n) : 0.f;
+        Bs[kk][nn] = v;
+        if (NT % BN == 0) csum += v;  // nn == tid % BN for every i when NT % BN == 0
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < N) ep(m, n, acc[i][j]);
+    }
+  }
+  if (colsum != nullptr && !LB::INNER_IS_K && NT % BN == 0 && blockIdx.y == 0) {
+    const int n = n0 + tid % BN;
+    if (n < N) atomicAdd(colsum + n, csum);
+  }
+}
+
+// Host launcher.  split_k: number of K partitions (epilogue must accumulate when > 1).
+template <int BM, int BN, int BK, int TM, class LA, class LB, class EP>
+inline void launch_gemm(LA la, LB lb, EP ep, int M, int N, int K, int split_k, float* colsum, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  if (split_k < 1) split_k = 1;
+  int kps = (K + split_k - 1) / split_k;
+  kps = ((kps + BK - 1) / BK) * BK;
+  split_k = (K + kps - 1) / kps;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
+  gemm_kernel<BM, BN, BK, TM, LA, LB, EP><<<grid, (BM / TM) * (BN / 4), 0, st>>>(la, lb, ep, M, N, K, kps, colsum);
+}
+
+}  // namespace cirs

@@ -1,0 +1,372 @@
+// K5: one PPO minibatch -- forward, losses and backward of the actor / critic heads (core/policy/ppo.py:181-220).
+//
+//   forward   trunk (20 -> 64 -> 64, ReLU) on the minibatch's observations, critic value, logits = h2 W3t + b3
+//             (FP32 tile GEMM, gemm.cuh), per-row softmax statistics, Categorical log_prob / entropy
+//             (log o clamp on the renormalised softmax), clipped surrogate, clipped value loss.
+//   backward  d logits is never materialised: the two GEMMs that consume it (dW3t = h2^T dl, dh2 = dl W3) rebuild
+//             each element from the stored logits and the row statistics while staging their operand tiles.
+//             The trunk backward runs on the same tile GEMM; d loss / d obs is scattered to the buffer slots of the
+//             minibatch (the upstream gradient of the tracker's training pass).
+// Tie semantics follow torch: min / max route half of the gradient to each argument when they are equal, clamp
+// passes the gradient on its closed interval.
+#include "gemm.cuh"
+#include "../../include/cirs_b200.h"
+
+namespace {
+using namespace cirs;
+constexpr int HID = CIRS_HIDDEN;
+
+struct Workspace {
+  float *h1, *h2, *value, *logits, *dh2, *dz2, *dz1, *rowm, *rinvz, *coef, *rowG, *dv, *terms;
+  int32_t* acta;
+};
+
+__host__ __device__ inline int64_t align64(int64_t x) { return (x + 63) & ~(int64_t)63; }
+
+Workspace carve(void* base, int64_t n, int64_t ldA) {
+  float* p = reinterpret_cast<float*>(base);
+  Workspace w;
+  auto take = [&](int64_t cnt) { float* r = p; p += align64(cnt); return r; };
+  w.h1 = take(n * HID); w.h2 = take(n * HID); w.value = take(n); w.logits = take(n * ldA);
+  w.dh2 = take(n * HID); w.dz2 = take(n * HID); w.dz1 = take(n * HID);
+  w.rowm = take(n); w.rinvz = take(n); w.coef = take(n); w.rowG = take(n); w.dv = take(n); w.terms = take(n * 4);
+  w.acta = reinterpret_cast<int32_t*>(take(n));
+  return w;
+}
+
+// ---- trunk forward on gathered observation rows: h1, h2 (row-major) and the critic value
+__global__ void __launch_bounds__(256)
+trunk_fwd_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, const float* __restrict__ obs,
+                 float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ value) {
+  constexpr int BM = 64, LD = BM + 1;
+  __shared__ float s_in[BM][33];
+  __shared__ float hT[HID][LD];
+  const int tid = threadIdx.x, r0 = blockIdx.x * BM, S = W.dim_state;
+  for (int i = tid; i < BM * S; i += 256) {
+    const int r = i / S, c = i % S;
+    s_in[r][c] = (r0 + r < n) ? obs[(int64_t)idx[r0 + r] * S + c] : 0.f;
+  }
+  __syncthreads();
+  const int row = tid % BM, cg = tid / BM;
+  const bool ok = r0 + row < n;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = __ldg(W.b1 + cg * 16 + j);
+  for (int k = 0; k < S; ++k) {
+    const float x = s_in[row][k];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, __ldg(W.w1t + (size_t)k * HID + cg * 16 + j), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float v = fmaxf(acc[j], 0.f);
+    hT[cg * 16 + j][row] = v;
+    if (ok) h1[(int64_t)(r0 + row) * HID + cg * 16 + j] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = __ldg(W.b2 + cg * 16 + j);
+  for (int k = 0; k < HID; ++k) {
+    const float x = hT[k][row];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, __ldg(W.w2t + (size_t)k * HID + cg * 16 + j), acc[j]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float v = fmaxf(acc[j], 0.f);
+    hT[cg * 16 + j][row] = v;
+    if (ok) h2[(int64_t)(r0 + row) * HID + cg * 16 + j] = v;
+  }
+  __syncthreads();
+  if (tid < BM && r0 + tid < n) {
+    float v = __ldg(W.bv);
+    for (int k = 0; k < HID; ++k) v = fmaf(hT[k][tid], __ldg(W.wv + k), v);
+    value[r0 + tid] = v;
+  }
+}
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int i = 0; i < nw; ++i) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];  // fixed order: deterministic
+  return r;
+}
+
+// ---- per-row softmax statistics, losses and d loss / d logp, d loss / d value   (one CTA per row)
+__global__ void __launch_bounds__(256)
+row_loss_kernel(int nA, int64_t ldA, cirs_ppo_config cfg, int n_global, const int32_t* __restrict__ idx,
+                const int32_t* __restrict__ act, const float* __restrict__ adv, const float* __restrict__ returns,
+                const float* __restrict__ v_old, const float* __restrict__ logp_old,
+                const double* __restrict__ adv_stat, Workspace ws) {
+  __shared__ float sh[8];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* L = ws.logits + (int64_t)r * ldA;
+  float mx = -INFINITY;
+  for (int c = tid; c < nA; c += 256) mx = fmaxf(mx, L[c]);
+  mx = block_reduce(mx, true, sh);
+  float z = 0.f;
+  for (int c = tid; c < nA; c += 256) z += expf(L[c] - mx);
+  z = block_reduce(z, false, sh);
+  const float invz = 1.0f / z;
+  // Categorical(probs = softmax): probs <- p / sum(p); logits = log(clamp(probs, eps, 1 - eps))
+  float ent = 0.f, pin = 0.f;
+  for (int c = tid; c < nA; c += 256) {
+    const float p = expf(L[c] - mx) * invz;
+    const bool inr = p >= CATEGORICAL_EPS && p <= 1.0f - CATEGORICAL_EPS;
+    const float pc = fminf(fmaxf(p, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS);
+    ent -= p * logf(pc);
+    if (inr) pin += p;
+  }
+  ent = block_reduce(ent, false, sh);
+  pin = block_reduce(pin, false, sh);
+  if (tid != 0) return;
+  const int slot = idx[r], a = act[slot];
+  const float pa = expf(L[a] - mx) * invz;
+  const bool inr_a = pa >= CATEGORICAL_EPS && pa <= 1.0f - CATEGORICAL_EPS;
+  const float logp = logf(fminf(fmaxf(pa, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS));
+  const float inv_n = 1.0f / (float)n_global;
+  // advantage normalisation with the minibatch's mean / unbiased std (ppo.py:185-186)
+  float A = adv[slot];
+  if (cfg.norm_adv) {
+    const double cnt = adv_stat[0], mean = adv_stat[1] / cnt;
+    const double var = (adv_stat[2] - cnt * mean * mean) / (cnt - 1.0);
+    A = (float)(((double)A - mean) / sqrt(fmax(var, 0.0)));
+  }
+  const float ratio = expf(logp - logp_old[slot]);                               // ppo.py:187
+  const float lo = 1.0f - cfg.eps_clip, hi = 1.0f + cfg.eps_clip;
+  const float surr1 = ratio * A, surr2 = fminf(fmaxf(ratio, lo), hi) * A;        // ppo.py:189-190
+  const float clip_i = -fminf(surr1, surr2);                                     // ppo.py:196
+  const float g1 = surr1 < surr2 ? 1.f : (surr1 == surr2 ? 0.5f : 0.f);
+  const float g2 = surr2 < surr1 ? 1.f : (surr1 == surr2 ? 0.5f : 0.f);
+  const bool in_clip = ratio >= lo && ratio <= hi;
+  const float dmin_dratio = g1 * A + (in_clip ? g2 * A : 0.f);
+  ws.coef[r] = inr_a ? -dmin_dratio * ratio * inv_n : 0.f;                       // d loss / d logp_r
+  // critic (ppo.py:199-207)
+  const float v = ws.value[r], vo = v_old[slot], R = returns[slot];
+  float vf_i, dvf;
+  if (cfg.value_clip) {
+    const float dvc = v - vo;
+    const float v_clip = vo + fminf(fmaxf(dvc, -cfg.eps_clip), cfg.eps_clip);
+    const float vf1 = (R - v) * (R - v), vf2 = (R - v_clip) * (R - v_clip);
+    vf_i = fmaxf(vf1, vf2);
+    const float w1 = vf1 > vf2 ? 1.f : (vf1 == vf2 ? 0.5f : 0.f);
+    const float w2 = vf2 > vf1 ? 1.f : (vf1 == vf2 ? 0.5f : 0.f);
+    const bool in_v = dvc >= -cfg.eps_clip && dvc <= cfg.eps_clip;
+    dvf = w1 * (-2.f * (R - v)) + (in_v ? w2 * (-2.f * (R - v_clip)) : 0.f);
+  } else {
+    vf_i = (R - v) * (R - v);
+    dvf = -2.f * (R - v);
+  }
+  ws.dv[r] = cfg.vf_coef * dvf * inv_n;
+  ws.rowm[r] = mx;
+  ws.rinvz[r] = invz;
+  ws.rowG[r] = ent - pin;   // sum_j g_j p_j with g_j = -(log clamp(p_j) + [p_j in range])
+  ws.acta[r] = a;
+  ws.terms[4 * r] = clip_i;
+  ws.terms[4 * r + 1] = vf_i;
+  ws.terms[4 * r + 2] = ent;
+}
+
+// ---- deterministic reduction of the per-row loss terms -> losses[4] = {loss, clip, vf, ent} / n_global
+__global__ void __launch_bounds__(1024)
+loss_reduce_kernel(int n, int n_global, cirs_ppo_config cfg, const float* __restrict__ terms, float* losses) {
+  __shared__ double sh[3][32];
+  double a = 0, b = 0, c = 0;
+  for (int r = threadIdx.x; r < n; r += 1024) {
+    a += terms[4 * r]; b += terms[4 * r + 1]; c += terms[4 * r + 2];
+  }
+  a = warp_sum_d(a); b = warp_sum_d(b); c = warp_sum_d(c);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = a; sh[1][w] = b; sh[2][w] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = b = c = 0;
+    for (int i = 0; i < 32; ++i) { a += sh[0][i]; b += sh[1][i]; c += sh[2][i]; }
+    a /= n_global; b /= n_global; c /= n_global;
+    losses[0] = (float)(a + cfg.vf_coef * b - cfg.ent_coef * c);   // ppo.py:211-212
+    losses[1] = (float)a; losses[2] = (float)b; losses[3] = (float)c;
+  }
+}
+
+// d loss / d logits[r][c], rebuilt on the fly:  coef_r (1[c == a_r] - p_rc)  +  ent_coef/n * p (log clamp(p) + inr + G_r)
+struct DlCore {
+  const float* logits; int64_t ld;
+  const float *rowm, *rinvz, *coef, *rowG;
+  const int32_t* acta;
+  float ecn;  // ent_coef / n_global
+  __device__ __forceinline__ float at(int r, int c) const {
+    const float p = expf(__ldg(logits + (int64_t)r * ld + c) - __ldg(rowm + r)) * __ldg(rinvz + r);
+    float v = __ldg(coef + r) * ((c == __ldg(acta + r) ? 1.f : 0.f) - p);
+    if (ecn != 0.f) {
+      const bool inr = p >= CATEGORICAL_EPS && p <= 1.0f - CATEGORICAL_EPS;
+      const float pc = fminf(fmaxf(p, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS);
+      v += ecn * p * (logf(pc) + (inr ? 1.f : 0.f) + __ldg(rowG + r));
+    }
+    return v;
+  }
+};
+struct DlA {  // A(m = row, k = column): contiguous along k
+  static constexpr bool INNER_IS_K = true;
+  DlCore d;
+  __device__ __forceinline__ float operator()(int m, int k) const { return d.at(m, k); }
+};
+struct DlB {  // B(k = row, n = column): contiguous along n
+  static constexpr bool INNER_IS_K = false;
+  DlCore d;
+  __device__ __forceinline__ float operator()(int k, int n) const { return d.at(k, n); }
+};
+
+// dz2 = (dh2 + dv * wv) * [h2 > 0]
+__global__ void dz2_kernel(int n, const float* __restrict__ dh2, const float* __restrict__ dv,
+                           const float* __restrict__ wv, const float* __restrict__ h2, float* __restrict__ dz2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * HID) return;
+  const int r = i / HID, c = i % HID;
+  dz2[i] = h2[i] > 0.f ? dh2[i] + dv[r] * __ldg(wv + c) : 0.f;
+}
+
+// critic.last gradients: g_wv[c] = sum_r dv[r] h2[r][c], g_bv = sum_r dv[r]   (single CTA, fixed order)
+__global__ void __launch_bounds__(256)
+critic_grad_kernel(int n, const float* __restrict__ dv, const float* __restrict__ h2, float* g_wv, float* g_bv) {
+  __shared__ float sh[4][HID + 1];
+  const int c = threadIdx.x % HID, part = threadIdx.x / HID;
+  float s = 0.f, sb = 0.f;
+  for (int r = part; r < n; r += 4) {
+    const float d = dv[r];
+    s = fmaf(d, h2[(int64_t)r * HID + c], s);
+    sb += d;
+  }
+  sh[part][c] = s;
+  if (c == 0) sh[part][HID] = sb;
+  __syncthreads();
+  if (part == 0) {
+    g_wv[c] = sh[0][c] + sh[1][c] + sh[2][c] + sh[3][c];
+    if (c == 0) g_bv[0] = sh[0][HID] + sh[1][HID] + sh[2][HID] + sh[3][HID];
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+adv_stats_kernel(const int32_t* __restrict__ mb_off, const int32_t* __restrict__ idx, const float* __restrict__ adv,
+                 double* __restrict__ stats) {
+  __shared__ double sh[2][32];
+  const int j = blockIdx.x, b = mb_off[j], e = mb_off[j + 1];
+  double s = 0, ss = 0;
+  for (int i = b + threadIdx.x; i < e; i += 1024) {
+    const double a = adv[idx[i]];
+    s += a; ss += a * a;
+  }
+  s = warp_sum_d(s); ss = warp_sum_d(ss);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s; sh[1][w] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = ss = 0;
+    for (int i = 0; i < 32; ++i) { s += sh[0][i]; ss += sh[1][i]; }
+    stats[3 * j] = (double)(e - b); stats[3 * j + 1] = s; stats[3 * j + 2] = ss;
+  }
+}
+
+int split_for(int tiles, int K, int bk) {
+  int s = (2 * 148 + tiles - 1) / tiles;
+  const int max_s = (K + 4 * bk - 1) / (4 * bk);
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
+}  // namespace
+
+extern "C" int64_t cirs_ppo_workspace_bytes(int32_t n_rows, int32_t n_action) {
+  const int64_t n = n_rows > 0 ? n_rows : 1, ldA = ((int64_t)n_action + 127) & ~127LL;
+  int64_t cnt = 5 * align64(n * HID) + align64(n * ldA) + 7 * align64(n) + align64(4 * n);
+  return cnt * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int cirs_adv_stats(int32_t n_mb, const int32_t* mb_off, const int32_t* idx, const float* adv,
+                              double* stats, void* stream) {
+  if (n_mb < 0 || !mb_off || !idx || !adv || !stats) {
+    cirs_set_error("cirs_adv_stats: null argument");
+    return CIRS_ERR_ARG;
+  }
+  if (n_mb == 0) return CIRS_OK;
+  adv_stats_kernel<<<n_mb, 1024, 0, (cudaStream_t)stream>>>(mb_off, idx, adv, stats);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+
+extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_policy_weights* grads,
+                                  const cirs_ppo_config* cfg, int32_t n, int32_t n_global, const int32_t* idx,
+                                  const float* obs, const int32_t* act, const float* adv, const float* returns,
+                                  const float* v_old, const float* logp_old, const double* adv_stat, float* d_obs,
+                                  float* losses, void* workspace, void* stream) {
+  if (!w || !grads || !cfg || !idx || !obs || !act || !adv || !returns || !v_old || !logp_old || !losses ||
+      !workspace || n < 0 || n_global < n || (cfg->norm_adv && !adv_stat)) {
+    cirs_set_error("cirs_ppo_minibatch: bad argument");
+    return CIRS_ERR_ARG;
+  }
+  if (w->dim_state > 32 || !grads->flat) {
+    cirs_set_error("cirs_ppo_minibatch: dim_state > 32 or grads->flat missing");
+    return CIRS_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nA = w->n_action, S = w->dim_state;
+  const int64_t ldA = w->ld_action;
+  cudaMemsetAsync(grads->flat, 0, sizeof(float) * grads->n_flat, st);
+  if (n == 0) {
+    cudaMemsetAsync(losses, 0, 4 * sizeof(float), st);
+    return CIRS_OK;
+  }
+  Workspace ws = carve(workspace, n, ldA);
+
+  // ---- forward
+  trunk_fwd_kernel<<<(n + 63) / 64, 256, 0, st>>>(*w, n, idx, obs, ws.h1, ws.h2, ws.value);
+  CIRS_CHECK_LAUNCH();
+  launch_gemm<64, 128, 16, 8>(RowMajorA{ws.h2, HID, nullptr}, RowMajorB{w->w3t, ldA, nullptr},
+                              StoreEp{ws.logits, ldA, w->b3, 0, nullptr, nullptr, 0}, n, nA, HID, 1, nullptr, st);
+  CIRS_CHECK_LAUNCH();
+  row_loss_kernel<<<n, 256, 0, st>>>(nA, ldA, *cfg, n_global, idx, act, adv, returns, v_old, logp_old, adv_stat,
+                                     ws);
+  CIRS_CHECK_LAUNCH();
+  loss_reduce_kernel<<<1, 1024, 0, st>>>(n, n_global, *cfg, ws.terms, losses);
+  CIRS_CHECK_LAUNCH();
+
+  // ---- backward through the actor head
+  DlCore dl{ws.logits, ldA, ws.rowm, ws.rinvz, ws.coef, ws.rowG, ws.acta, cfg->ent_coef / (float)n_global};
+  // dW3t[k][c] = sum_r h2[r][k] dl[r][c];  db3[c] = sum_r dl[r][c]      (M = 64, N = nA, K = n; split over rows)
+  launch_gemm<64, 128, 16, 8>(ColMajorA{ws.h2, HID, nullptr}, DlB{dl}, AtomicEp{grads->w3t, ldA}, HID, nA, n,
+                              split_for((nA + 127) / 128, n, 16), grads->b3, st);
+  CIRS_CHECK_LAUNCH();
+  // dh2[r][k] = sum_c dl[r][c] W3t[k][c]                                  (M = n, N = 64, K = nA; split over columns)
+  cudaMemsetAsync(ws.dh2, 0, sizeof(float) * (size_t)n * HID, st);
+  launch_gemm<64, 64, 16, 4>(DlA{dl}, ColMajorB{w->w3t, ldA}, AtomicEp{ws.dh2, HID}, n, HID, nA,
+                             split_for((n + 63) / 64, nA, 16), nullptr, st);
+  CIRS_CHECK_LAUNCH();
+  // ---- critic head + trunk
+  critic_grad_kernel<<<1, 256, 0, st>>>(n, ws.dv, ws.h2, grads->wv, grads->bv);
+  CIRS_CHECK_LAUNCH();
+  dz2_kernel<<<(n * HID + 255) / 256, 256, 0, st>>>(n, ws.dh2, ws.dv, w->wv, ws.h2, ws.dz2);
+  CIRS_CHECK_LAUNCH();
+  // dW2t[k][c] = sum_r h1[r][k] dz2[r][c], db2
+  launch_gemm<64, 64, 16, 4>(ColMajorA{ws.h1, HID, nullptr}, RowMajorB{ws.dz2, HID, nullptr},
+                             AtomicEp{grads->w2t, HID}, HID, HID, n, split_for(1, n, 16), grads->b2, st);
+  CIRS_CHECK_LAUNCH();
+  // dz1[r][k] = (sum_c dz2[r][c] W2t[k][c]) * [h1 > 0]
+  launch_gemm<64, 64, 16, 4>(RowMajorA{ws.dz2, HID, nullptr}, ColMajorB{w->w2t, HID},
+                             StoreEp{ws.dz1, HID, nullptr, 0, nullptr, ws.h1, HID}, n, HID, HID, 1, nullptr, st);
+  CIRS_CHECK_LAUNCH();
+  // dW1t[s][c] = sum_r obs[idx[r]][s] dz1[r][c], db1
+  launch_gemm<64, 64, 16, 4>(ColMajorA{obs, S, idx}, RowMajorB{ws.dz1, HID, nullptr}, AtomicEp{grads->w1t, HID}, S,
+                             HID, n, split_for(1, n, 16), grads->b1, st);
+  CIRS_CHECK_LAUNCH();
+  // d_obs[idx[r]][s] = sum_c dz1[r][c] W1t[s][c]
+  if (d_obs) {
+    launch_gemm<64, 64, 16, 4>(RowMajorA{ws.dz1, HID, nullptr}, ColMajorB{w->w1t, HID},
+                               StoreEp{d_obs, S, nullptr, 0, idx, nullptr, 0}, n, S, HID, 1, nullptr, st);
+    CIRS_CHECK_LAUNCH();
+  }
+  return CIRS_OK;
+}

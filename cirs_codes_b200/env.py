@@ -1,0 +1,177 @@
+"""Vectorised KuaishouEnv / SimulatedEnv: B environments stepped by ONE kernel launch (csrc/env_kuaishou.cu).
+
+Host-side mirror of the reference's vector-env interface (SURVEY §8b "Vector env"):
+  tianshou/env/venvs.py:153-252        BaseVectorEnv.reset(id) / step(action, id) / seed / __len__ / is_async
+  environments/KuaishouRec/env/kuaishouEnv.py:30-235   KuaishouEnv (reward = mat[u, a], category-overlap exit)
+  core/env/simulatedEnv/simulated_env.py:17-193        SimulatedEnv (reward = normed_mat / (1 + exposure))
+The reference holds one Python object per environment and loops over them (venvs.py:212-220); here the state of
+all environments lives in device arrays (user, turn, hist[B, T], cum_rew) and ``step`` is a single launch.
+``reset`` / ``step`` keep the numpy-in / numpy-out contract; ``reset_device`` / ``step_device`` are the
+zero-copy entry points used by the fused Collector.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Discrete:
+    """gym.spaces.Discrete stand-in (gym is not a dependency)."""
+
+    def __init__(self, n, seed=None):
+        self.n, self.shape, self.dtype = int(n), (), np.int64
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self):
+        return int(self._rng.integers(0, self.n))
+
+    def seed(self, seed=None):
+        self._rng = np.random.default_rng(seed)
+
+    def contains(self, x):
+        return 0 <= int(x) < self.n
+
+
+def cats_to_mask(cats):
+    """list_feat (list of lists of category ids 1..31, kuaishouEnv.py:92-96) or int array [I, <=4] zero padded ->
+    uint32 bitmask per item."""
+    if isinstance(cats, (list, tuple)):
+        m = np.zeros(len(cats), dtype=np.uint32)
+        for i, row in enumerate(cats):
+            for c in row:
+                if c > 0:
+                    m[i] |= np.uint32(1) << np.uint32(c)
+        return m
+    cats = np.asarray(cats)
+    assert cats.max() <= 31 and cats.min() >= 0, "category ids must be in 1..31 (0 = padding)"
+    m = np.zeros(cats.shape[0], dtype=np.uint32)
+    for k in range(cats.shape[1]):
+        c = cats[:, k].astype(np.uint32)
+        m |= np.where(c > 0, np.uint32(1) << c, np.uint32(0)).astype(np.uint32)
+    return m
+
+
+class KuaishouVectorEnv:
+    """``simulated=True``  -> SimulatedEnv over KuaishouEnv (training env, CIRS-RL-kuaishou.py:187-210)
+    ``simulated=False`` -> raw KuaishouEnv (test envs, CIRS-RL-kuaishou.py:214-221)."""
+
+    is_async = False
+
+    def __init__(self, env_num, mat, list_feat, *, normed_mat=None, alpha_u=None, beta_i=None, df_dist_small=None,
+                 simulated=True, max_turn=30, num_leave_compute=1, leave_threshold=0, tau=100.0,
+                 gamma_exposure=10.0, r_decay=1.0, version="v1", track_seen=False, device="cuda", seed=None):
+        _lib.require_cuda()
+        _lib.load()
+        self.device = torch.device(device)
+        self.env_num, self.max_turn = int(env_num), int(max_turn)
+        dev = self.device
+
+        def f32(x):
+            return None if x is None else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+
+        self.mat = None if mat is None else (mat if torch.is_tensor(mat) else f32(mat))
+        self.normed_mat = normed_mat if torch.is_tensor(normed_mat) else f32(normed_mat)
+        ref = self.mat if self.mat is not None else self.normed_mat
+        self.n_user, self.n_item = int(ref.shape[0]), int(ref.shape[1])
+        self.simulated = bool(simulated)
+        if self.simulated:
+            assert self.normed_mat is not None, "SimulatedEnv needs normed_mat (simulated_env.py:100)"
+        else:
+            assert self.mat is not None
+        self.cat_mask = torch.from_numpy(cats_to_mask(list_feat).view(np.int32)).to(dev)
+        assert self.cat_mask.numel() == self.n_item
+        self.alpha_u = None if alpha_u is None else f32(np.asarray(alpha_u).reshape(-1))
+        self.beta_i = None if beta_i is None else f32(np.asarray(beta_i).reshape(-1))
+        self.dist = None if df_dist_small is None else f32(np.asarray(df_dist_small))
+        B, T = self.env_num, self.max_turn
+        self.user = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.turn = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.hist = torch.zeros(B, T, dtype=torch.int32, device=dev)
+        self.cum_rew = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.active = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self.seen = torch.zeros(B, (self.n_item + 31) // 32, dtype=torch.int32, device=dev) if track_seen else None
+        self.rew = torch.zeros(B, dtype=torch.float32, device=dev)     # last step's outputs, per env slot
+        self.done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self.cfg = dict(num_leave_compute=int(num_leave_compute), leave_threshold=float(leave_threshold),
+                        tau=float(tau), gamma_exposure=float(gamma_exposure), r_decay=float(r_decay),
+                        version=1 if version == "v1" else 2)
+        s = _lib.KuaishouEnvStruct()
+        s.n_env, s.max_turn, s.num_leave_compute = B, T, int(num_leave_compute)
+        s.n_user, s.n_item, s.simulated, s.version = self.n_user, self.n_item, int(self.simulated), self.cfg["version"]
+        s.leave_threshold, s.tau = float(leave_threshold), float(tau)
+        s.gamma_exposure, s.r_decay = float(gamma_exposure), float(r_decay)
+        s.normed_mat, s.mat, s.cat_mask = _lib.ptr(self.normed_mat), _lib.ptr(self.mat), _lib.ptr(self.cat_mask)
+        s.alpha_u, s.beta_i, s.dist = _lib.ptr(self.alpha_u), _lib.ptr(self.beta_i), _lib.ptr(self.dist)
+        s.user, s.turn, s.hist = _lib.ptr(self.user), _lib.ptr(self.turn), _lib.ptr(self.hist)
+        s.cum_rew, s.seen = _lib.ptr(self.cum_rew), _lib.ptr(self.seen)
+        self._struct = s
+        self.action_space = [Discrete(self.n_item, None if seed is None else seed + i) for i in range(min(B, 8))]
+        self._rng = np.random.default_rng(seed)
+
+    # ------------------------------------------------------------------ gym / tianshou surface
+    def __len__(self):
+        return self.env_num
+
+    def seed(self, seed=None):
+        self._rng = np.random.default_rng(seed if not isinstance(seed, (list, tuple)) else seed[0])
+        return [seed] * self.env_num
+
+    def render(self, **kwargs):
+        return None
+
+    def close(self):
+        return None
+
+    def draw_users(self, n):
+        """kuaishouEnv.py:155-159 draws random.randint(0, U-1) per environment; here one vectorised draw."""
+        return self._rng.integers(0, self.n_user, size=n, dtype=np.int64)
+
+    def _ids(self, id):
+        if id is None:
+            return np.arange(self.env_num, dtype=np.int64)
+        return np.atleast_1d(np.asarray(id, dtype=np.int64))
+
+    def reset(self, id=None, users=None):
+        """venvs.py:153-173 -> obs ndarray [len(id), 1] (the user id, kuaishouEnv.py:147-153)."""
+        ids = self._ids(id)
+        users = self.draw_users(len(ids)) if users is None else np.asarray(users, dtype=np.int64).reshape(-1)
+        d_ids = torch.as_tensor(ids.astype(np.int32), device=self.device)
+        d_users = torch.as_tensor(users.astype(np.int32), device=self.device)
+        self.reset_device(d_users, d_ids)
+        return users.reshape(-1, 1).copy()
+
+    def step(self, action, id=None):
+        """venvs.py:175-252 -> (obs_next [n,1] int64, rew float64 [n], done bool [n], info).  One launch."""
+        ids = self._ids(id)
+        act = np.asarray(action).reshape(len(ids), -1)[:, 0].astype(np.int32)
+        d_ids = torch.as_tensor(ids.astype(np.int32), device=self.device)
+        d_act = torch.as_tensor(act, device=self.device)
+        rew = torch.empty(len(ids), dtype=torch.float32, device=self.device)
+        done = torch.empty(len(ids), dtype=torch.uint8, device=self.device)
+        self.step_device(d_act, rew, done, env_id=d_ids, use_active=False)
+        rew_h, done_h = rew.cpu().numpy().astype(np.float64), done.cpu().numpy().astype(bool)
+        info = {"env_id": ids}
+        cum = self.cum_rew[torch.as_tensor(ids, device=self.device)].cpu().numpy()
+        if self.simulated:
+            turn = self.turn[torch.as_tensor(ids, device=self.device)].cpu().numpy()
+            info["CTR"] = cum / np.maximum(turn, 1) / 10.0                     # simulated_env.py:141
+        else:
+            info["cum_reward"] = cum                                           # kuaishouEnv.py:178
+        return act.astype(np.int64).reshape(-1, 1), rew_h, done_h, info
+
+    # ------------------------------------------------------------------ device entry points
+    def reset_device(self, d_users, d_ids=None):
+        n = d_users.numel()
+        _lib.call("cirs_kuaishou_reset", C.byref(self._struct), n, _lib.ptr(d_ids), _lib.ptr(d_users),
+                  _lib.ptr(self.active), _lib.stream())
+
+    def step_device(self, d_act, rew, done, env_id=None, use_active=True, traj=None, ep_len=None, force_length=0):
+        """traj = (L, traj_act, traj_rew, traj_done) device arrays of the replay buffer, or None."""
+        n = d_act.numel()
+        L, ta, tr, td = traj if traj is not None else (0, None, None, None)
+        _lib.call("cirs_kuaishou_step", C.byref(self._struct), n, _lib.ptr(env_id),
+                  _lib.ptr(self.active) if use_active else None, _lib.ptr(d_act), _lib.ptr(rew), _lib.ptr(done),
+                  int(L), _lib.ptr(ta), _lib.ptr(tr), _lib.ptr(td), _lib.ptr(ep_len), int(force_length),
+                  _lib.stream())

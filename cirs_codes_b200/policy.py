@@ -1,0 +1,311 @@
+"""PPOPolicy: actor / critic forward with fused sampling (K3), returns (K4), the PPO update (K5, K7) and the
+tracker's training pass (K6), behind the reference's policy interface.
+
+Host-side mirror of (SURVEY §8b "Policy"):
+  core/policy/ppo.py:14-246                         PPOPolicy.__init__ / process_fn / forward / learn
+  tianshou/policy/modelfree/a2c.py:11-148           A2CPolicy (_compute_returns)
+  tianshou/policy/modelfree/pg.py:10-139            PGPolicy (ret_rms, action scaling)
+  tianshou/policy/base.py:13-423                    BasePolicy.update / map_action / compute_episodic_return
+Same constructor keywords, same ``update(0, buffer, batch_size=, repeat=) -> {"loss": [...], ...}`` result.
+Only the discrete actor over the item catalogue (KuaishouEnv) is implemented on the device in this round.
+
+Multi-GPU: environments are sharded over ranks; each global minibatch is the union of the ranks' local minibatches.
+Gradients are summed with ONE all-reduce per minibatch (torch.distributed, NCCL over NVLink); the advantage
+moments of all minibatches of a repeat, the return moments and the losses are reduced once per repeat / update.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, params
+from .data import Batch
+
+
+def split_indices(n, size, perm):
+    """tianshou/data/batch.py:721-744 with merge_last=True."""
+    merge = n % size > 0
+    out = []
+    for i in range(0, n, size):
+        if merge and i + size + size >= n:
+            out.append(perm[i:])
+            break
+        out.append(perm[i:i + size])
+    return out
+
+
+class RunningMeanStd:
+    """Host view of the device-resident return statistics (tianshou/utils/statistics.py:66-95)."""
+
+    def __init__(self, dev):
+        self.t = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64, device=dev)
+
+    mean = property(lambda self: float(self.t[0]))
+    var = property(lambda self: float(self.t[1]))
+    count = property(lambda self: float(self.t[2]))
+
+
+class PPOPolicy:
+    def __init__(self, actor, critic, optim, dist_fn=None, eps_clip=0.2, dual_clip=None, value_clip=False,
+                 advantage_normalization=True, recompute_advantage=False, vf_coef=0.5, ent_coef=0.01,
+                 max_grad_norm=None, gae_lambda=0.95, max_batchsize=256, discount_factor=0.99,
+                 reward_normalization=False, action_scaling=True, action_bound_method="clip", action_space=None,
+                 lr_scheduler=None, deterministic_eval=False, state_tracker=None, device="cuda", seed=0,
+                 process_group=None, **kwargs):
+        _lib.require_cuda()
+        _lib.load()
+        assert dual_clip is None, "dual_clip is not used by CIRS (CIRS-RL-kuaishou.py:277-279)"
+        assert not recompute_advantage, "recompute_advantage is not used by CIRS (default 0)"
+        assert lr_scheduler is None
+        if not reward_normalization:
+            assert not value_clip, "value clip is available only when `reward_normalization` is True"  # ppo.py:87-89
+        self.device = torch.device(device)
+        self.actor, self.critic = actor, critic
+        self.optim = optim if isinstance(optim, (list, tuple)) else [optim]
+        self.dist_fn = dist_fn
+        self.training, self.updating = True, False
+        self.callbacks = []
+        self._gamma, self._lambda = float(discount_factor), float(gae_lambda)
+        self._rew_norm, self._batch = bool(reward_normalization), int(max_batchsize)
+        self._deterministic_eval = bool(deterministic_eval)
+        self.action_type = "discrete"
+        self.action_space = action_space
+        self.seed, self._calls = int(seed), 0
+        self.group = process_group
+
+        dim_state = actor.preprocess.input_dim
+        n_action = actor.output_dim
+        self.layout = params.policy_layout(dim_state, n_action)
+        self.dim_state, self.n_action = dim_state, n_action
+        sd = params.policy_sd_from_reference(actor.state_dict(), critic.state_dict())
+        self.flat = self.layout.pack(sd, self.device)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.opt_state = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.opt_scratch = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self._w = params.policy_struct(self.layout, self.flat)
+        self._g = params.policy_struct(self.layout, self.grad)
+
+        def hyper(opt):
+            g = opt.param_groups[0]
+            return float(g["lr"]), tuple(g.get("betas", (0.9, 0.999))), float(g.get("eps", 1e-8))
+
+        lr, betas, eps = hyper(self.optim[0])
+        self.cfg = _lib.PPOConfigStruct(float(eps_clip), float(vf_coef), float(ent_coef),
+                                        float(max_grad_norm) if max_grad_norm else 0.0, int(bool(value_clip)),
+                                        int(bool(advantage_normalization)), lr, betas[0], betas[1], eps)
+        self.state_tracker = state_tracker
+        self.cfg_tracker = None
+        if len(self.optim) > 1:
+            lr2, b2, e2 = hyper(self.optim[1])
+            self.cfg_tracker = _lib.PPOConfigStruct(0, 0, 0, 0.0, 0, 0, lr2, b2[0], b2[1], e2)
+            if self.state_tracker is None:
+                for p in self.optim[1].param_groups[0]["params"]:
+                    self.state_tracker = getattr(p, "_cirs_owner", self.state_tracker)
+        self.ret_rms = RunningMeanStd(self.device)
+        self._ws_actor = self._ws_ppo = None
+        self._ws_actor_rows = self._ws_ppo_rows = 0
+
+    # ------------------------------------------------------------------ module-like surface
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def to(self, *a, **k):
+        return self
+
+    def cpu(self):
+        return self
+
+    def state_dict(self):
+        """{"actor.<name>", "critic.<name>"} in the reference's naming (loads into tianshou's PPOPolicy)."""
+        a, c = params.policy_sd_to_reference(self.layout.unpack(self.flat))
+        out = {"actor." + k: v for k, v in a.items()}
+        out.update({"critic." + k: v for k, v in c.items()})
+        out["ret_rms"] = self.ret_rms.t.detach().cpu()
+        return out
+
+    def load_state_dict(self, sd, strict=True):
+        a = {k[len("actor."):]: v for k, v in sd.items() if k.startswith("actor.")}
+        c = {k[len("critic."):]: v for k, v in sd.items() if k.startswith("critic.")}
+        self.flat.copy_(self.layout.pack(params.policy_sd_from_reference(a, c), self.device))
+        if "ret_rms" in sd:
+            self.ret_rms.t.copy_(torch.as_tensor(sd["ret_rms"], dtype=torch.float64))
+
+    def map_action(self, act):
+        """policy/base.py:143-173: identity for a discrete action space (action_bound_method="")."""
+        if torch.is_tensor(act):
+            act = act.detach().cpu().numpy()
+        return act
+
+    def exploration_noise(self, act, batch):
+        return act
+
+    def set_collector(self, train_collector):
+        self.train_collector = train_collector
+
+    # ------------------------------------------------------------------ forward (K3)
+    def _actor_ws(self, n):
+        if n > self._ws_actor_rows:
+            need = _lib.load().cirs_actor_workspace_bytes(n, self.n_action)
+            self._ws_actor = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_actor_rows = n
+        return self._ws_actor
+
+    def sample_device(self, n_rows, state, state_stride, act, logp, value, env_id=None, active=None, noise_q=None,
+                      mode=None, seen=None):
+        """One fused trunk + head + softmax + sample launch (csrc/actor.cu)."""
+        if mode is None:
+            mode = 1 if (self._deterministic_eval and not self.training) else 0
+        self._calls += 1
+        _lib.call("cirs_actor_sample", C.byref(self._w), int(n_rows), _lib.ptr(env_id), _lib.ptr(active),
+                  _lib.ptr(state), int(state_stride), _lib.ptr(noise_q), self.seed, self._calls, int(mode),
+                  _lib.ptr(seen), _lib.ptr(act), _lib.ptr(logp), _lib.ptr(value), _lib.ptr(self._actor_ws(n_rows)),
+                  _lib.stream())
+
+    def forward(self, batch, buffer=None, remove_recommended_ids=False, state=None, noise_q=None, **kwargs):
+        """core/policy/ppo.py:111-163.  batch.obs: float32 CUDA tensor [n, dim_state].  Returns Batch(act, logp,
+        value, logits=None, state=None, dist=None): the [n, n_action] probabilities are never materialised."""
+        obs = batch.obs if not isinstance(batch, torch.Tensor) else batch
+        obs = torch.as_tensor(obs, dtype=torch.float32, device=self.device).contiguous()
+        n = obs.shape[0]
+        act = torch.empty(n, dtype=torch.int32, device=self.device)
+        logp = torch.empty(n, dtype=torch.float32, device=self.device)
+        value = torch.empty(n, dtype=torch.float32, device=self.device)
+        seen = None
+        if remove_recommended_ids and buffer is not None and len(buffer) > 0:
+            seen = self._seen_bitset(buffer, n)
+        if noise_q is not None:
+            noise_q = torch.as_tensor(noise_q, dtype=torch.float32, device=self.device).contiguous()
+        self.sample_device(n, obs, self.dim_state, act, logp, value, noise_q=noise_q, seen=seen)
+        return Batch(logits=None, act=act.long(), state=None, dist=None, logp=logp, value=value)
+
+    __call__ = forward
+
+    def _seen_bitset(self, buffer, n):
+        """get_recommended_ids (core/policy/utils.py:7-27) as a per-row bitset over the catalogue."""
+        last = buffer.last_index
+        indices = last[~buffer.done[last]]
+        words = (self.n_action + 31) // 32
+        bits = np.zeros((len(indices), words), dtype=np.uint32)
+        rows = np.arange(len(indices))
+        while len(indices):
+            acts = buffer.act[indices]
+            np.bitwise_or.at(bits, (rows, acts >> 5), (np.uint32(1) << (acts & 31).astype(np.uint32)))
+            prev = buffer.prev(indices)
+            if np.all(prev == indices):
+                break
+            indices = prev
+        assert bits.shape[0] == n, "remove_recommended_ids: ready set and unfinished episodes differ"
+        return torch.from_numpy(bits.view(np.int32)).to(self.device)
+
+    # ------------------------------------------------------------------ update
+    def _ppo_ws(self, n):
+        if n > self._ws_ppo_rows:
+            need = _lib.load().cirs_ppo_workspace_bytes(n, self.n_action)
+            self._ws_ppo = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_ppo_rows = n
+        return self._ws_ppo
+
+    def _world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_world_size(self.group)
+        return None, 1
+
+    def _allreduce(self, t):
+        dist, world = self._world()
+        if world > 1:
+            dist.all_reduce(t, group=self.group)
+
+    def process_fn(self, buffer, indices):
+        """core/policy/ppo.py:96-109 + a2c.py:80-109: critic values, GAE / returns, old log-probs -- all on the
+        device, results stay per buffer slot."""
+        n_slots, dev = buffer.maxsize, self.device
+        B, L = buffer.buffer_num, buffer.sub_size
+        if getattr(self, "_slot_n", 0) != n_slots:
+            self._slot_n = n_slots
+            z = lambda dt=torch.float32: torch.zeros(n_slots, dtype=dt, device=dev)  # noqa: E731
+            self.v_s, self.v_next, self.logp_old, self.returns, self.adv = z(), z(), z(), z(), z()
+            self.d_obs = torch.zeros(n_slots, self.dim_state, dtype=torch.float32, device=dev)
+            self._gae_scratch = torch.zeros(2 * B, dtype=torch.float64, device=dev)
+            self._moments = torch.zeros(3, dtype=torch.float64, device=dev)
+        n = indices.numel()
+        ws = self._ppo_ws(1)  # noqa: F841  (allocated lazily in learn)
+        aws = self._actor_ws(n)
+        st = _lib.stream()
+        _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
+                  _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(aws), st)
+        _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
+                  _lib.ptr(self.v_next), None, _lib.ptr(aws), st)
+        _lib.call("cirs_compute_returns", B, L, _lib.ptr(buffer.d_len), _lib.ptr(self.v_s), _lib.ptr(self.v_next),
+                  _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_done), self._gamma, self._lambda,
+                  _lib.ptr(self.ret_rms.t) if self._rew_norm else None, _lib.ptr(self._gae_scratch),
+                  _lib.ptr(self._moments) if self._rew_norm else None, _lib.ptr(self.returns), _lib.ptr(self.adv), st)
+        if self._rew_norm:
+            self._allreduce(self._moments)
+            _lib.call("cirs_rms_update", _lib.ptr(self.ret_rms.t), _lib.ptr(self._moments), st)
+
+    def update(self, sample_size, buffer, batch_size=None, repeat=1, perms=None, **kwargs):
+        """policy/base.py:219-244: sample(0) -> process_fn -> learn.  ``perms`` (list of one permutation of
+        range(n) per repeat) overrides np.random.permutation for replayable parity runs."""
+        if buffer is None or len(buffer) == 0:
+            return {}
+        assert sample_size == 0, "on-policy: the whole buffer is used (core/trainer/onpolicy.py:199)"
+        self.updating = True
+        buffer.sync_device()
+        idx_h = buffer.sample_index(0)
+        indices = torch.as_tensor(idx_h.astype(np.int32), device=self.device)
+        self.process_fn(buffer, indices)
+        result = self.learn(buffer, idx_h, indices, batch_size or len(idx_h), repeat, perms=perms)
+        self.updating = False
+        return result
+
+    def learn(self, buffer, idx_h, indices, batch_size, repeat, perms=None):
+        """core/policy/ppo.py:166-246."""
+        n, dev, st = len(idx_h), self.device, _lib.stream()
+        dist, world = self._world()
+        tracker = self.state_tracker if self.cfg_tracker is not None else None
+        chunks_per_repeat, losses_all = [], []
+        for step in range(repeat):
+            perm = np.asarray(perms[step]) if perms is not None else np.random.permutation(n)   # batch.py:736
+            chunks = split_indices(n, batch_size, perm)
+            chunks_per_repeat.append(chunks)
+            offs = np.zeros(len(chunks) + 1, dtype=np.int32)
+            offs[1:] = np.cumsum([len(c) for c in chunks])
+            d_slots = torch.as_tensor(idx_h[np.concatenate(chunks)].astype(np.int32), device=dev)
+            d_offs = torch.as_tensor(offs, device=dev)
+            stats = torch.zeros(len(chunks), 3, dtype=torch.float64, device=dev)
+            _lib.call("cirs_adv_stats", len(chunks), _lib.ptr(d_offs), _lib.ptr(d_slots), _lib.ptr(self.adv),
+                      _lib.ptr(stats), st)
+            self._allreduce(stats)
+            n_glob = stats[:, 0].round().to(torch.int64).cpu().numpy() if world > 1 else np.diff(offs)
+            losses = torch.zeros(len(chunks), 4, dtype=torch.float32, device=dev)
+            if tracker is not None:
+                self.d_obs.zero_()                                                   # optim_state.zero_grad(), :174
+            ws = self._ppo_ws(int(np.diff(offs).max()))
+            for j in range(len(chunks)):
+                b, e = int(offs[j]), int(offs[j + 1])
+                _lib.call("cirs_ppo_minibatch", C.byref(self._w), C.byref(self._g), C.byref(self.cfg), e - b,
+                          int(n_glob[j]), d_slots.data_ptr() + 4 * b, _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act),
+                          _lib.ptr(self.adv), _lib.ptr(self.returns), _lib.ptr(self.v_s), _lib.ptr(self.logp_old),
+                          stats.data_ptr() + 24 * j, _lib.ptr(self.d_obs) if tracker is not None else None,
+                          losses.data_ptr() + 16 * j, _lib.ptr(ws), st)
+                self._allreduce(self.grad)                                           # ONE collective per minibatch
+                _lib.call("cirs_clip_adam", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
+                          _lib.ptr(self.exp_avg_sq), self.layout.total, self.layout.n_trunk, C.byref(self.cfg),
+                          _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), st)
+            losses_all.append(losses)
+        if tracker is not None:
+            tracker.zero_grad()
+            tracker.backward_from_buffer(buffer, self.d_obs, buffer.d_users)
+            self._allreduce(tracker.grad)
+            tracker.optim_step(self.cfg_tracker)                                     # optim_state.step(), :235
+        losses = torch.cat(losses_all)
+        self._allreduce(losses)
+        lh = losses.cpu().numpy().astype(np.float64)                                 # the update's only D2H read
+        return {"loss": lh[:, 0].tolist(), "loss/clip": lh[:, 1].tolist(), "loss/vf": lh[:, 2].tolist(),
+                "loss/ent": lh[:, 3].tolist()}

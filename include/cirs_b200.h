@@ -1,0 +1,232 @@
+/* cirs_b200.h -- C ABI of libcirs_b200.so: the CIRS rollout + PPO-update hot path as sm_100a CUDA kernels.
+ *
+ * Drop-in boundary.  The reference is pure Python and has no FFI of its own; each entry
+ * point below replaces one Python-level operator of the reference's hot path (file:line given per function,
+ * paths relative to the reference root).  The reference-side binding a maintainer would add is a ctypes stub
+ * (INTEGRATION.md); this repo's own binding is cirs_codes_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _h;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no entry point synchronises;
+ *     re-entrant per device, one process per GPU; every entry point can be captured into a CUDA graph;
+ *   - return 0 on success, non-zero on error; cirs_last_error() returns a message for the calling thread;
+ *   - "rows" are the environments taking part in a call.  Row k refers to environment slot
+ *     e = env_id ? env_id[k] : k, and is skipped when `active` is given and active[e] == 0;
+ *   - a Linear(in -> out) is stored k-major: Wt[in][ldo], ldo = out rounded up to a multiple of 32 (padding
+ *     columns are zero and have zero gradient); biases are padded to ldo as well.
+ *     cirs_codes_b200/params.py converts from/to the reference's torch state_dict layout ([out][in]);
+ *   - the weight structs hold non-const pointers because the same struct type describes the parameters, their
+ *     gradients and the Adam moments (three parallel flat buffers with identical layout).
+ */
+#ifndef CIRS_B200_H
+#define CIRS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CIRS_ABI_VERSION 2
+#define CIRS_MAX_LAYERS 4
+#define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
+
+const char* cirs_last_error(void);
+int cirs_abi_version(void);
+
+/* ------------------------------------------------------------------ KuaishouEnv / SimulatedEnv ---------- */
+typedef struct {
+  int32_t n_env;    /* B: environment slots */
+  int32_t max_turn; /* T */
+  int32_t num_leave_compute; /* N  (kuaishouEnv.py:38) */
+  int32_t n_user, n_item;
+  int32_t simulated; /* 1: SimulatedEnv reward (normed_mat, exposure); 0: raw KuaishouEnv reward mat[u,a] */
+  int32_t version;   /* 1: r/(1+e)   2: r-e      (simulated_env.py:102-107) */
+  float leave_threshold, tau, gamma_exposure, r_decay;
+  /* read-only tables */
+  const float* normed_mat;  /* [n_user, n_item]  simulated_env.py:100 */
+  const float* mat;         /* [n_user, n_item]  kuaishouEnv.py:171 (may be NULL when simulated) */
+  const uint32_t* cat_mask; /* [n_item] bit c set <=> category c (1..31) in list_feat_small[item] */
+  const float* alpha_u;     /* [n_user] indexed by encoded user id, or NULL (simulated_env.py:157-164) */
+  const float* beta_i;      /* [n_item] indexed by encoded item id, or NULL */
+  const float* dist;        /* optional [n_item, n_item] df_dist_small; NULL -> 1/Jaccard(cat_mask) */
+  /* per-environment state */
+  int32_t* user;    /* [B] */
+  int32_t* turn;    /* [B] total_turn */
+  int32_t* hist;    /* [B, T] history_action / sequence_action */
+  double* cum_rew;  /* [B] */
+  uint32_t* seen;   /* optional [B, ceil(n_item/32)] bitset of items already recommended this episode */
+} cirs_kuaishou_env;
+
+/* reset(): kuaishouEnv.py:182-190 + simulated_env.py:59-72.  users[n] are injected by the caller (the
+ * reference draws random.randint, kuaishouEnv.py:155-159).  Clears turn / history / cum_rew / seen and,
+ * when given, sets active[e] = 1. */
+int cirs_kuaishou_reset(const cirs_kuaishou_env* env, int32_t n_rows, const int32_t* env_id,
+                        const int32_t* users, uint8_t* active, void* stream);
+
+/* step(): simulated_env.py:111-168 + kuaishouEnv.py:161-218 + util.py:21-54 for n_rows environments.
+ * act[n] -> rew[n] (f32), done[n] (u8); obs_next is the action itself (kuaishouEnv.py:147-153).
+ * When `active` is given it is updated in place: active[e] &= !done (collector.py:303-311 drops finished
+ * environments from the ready set).  Optional trajectory outputs (env-major, VectorReplayBuffer layout,
+ * vecbuf.py:26-30; L = traj_len slots per environment): traj_act / traj_rew / traj_done [B, L] written at
+ * [e, t]; ep_len[e] written on done.  force_length > 0 overrides done (collector.py:253-258). */
+int cirs_kuaishou_step(const cirs_kuaishou_env* env, int32_t n_rows, const int32_t* env_id, uint8_t* active,
+                       const int32_t* act, float* rew, uint8_t* done, int32_t traj_len, int32_t* traj_act,
+                       float* traj_rew, uint8_t* traj_done, int32_t* ep_len, int32_t force_length,
+                       void* stream);
+
+/* ------------------------------------------------------------------ StateTracker ------------------------ */
+typedef struct {
+  float *in_wt, *in_b;     /* self_attn.in_proj  Wt[d][ld3d], b[3d] */
+  float *out_wt, *out_b;   /* self_attn.out_proj Wt[d][ldd] */
+  float *l1_wt, *l1_b;     /* linear1 Wt[d][ldh] */
+  float *l2_wt, *l2_b;     /* linear2 Wt[d_hid][ldd] */
+  float *n1_w, *n1_b, *n2_w, *n2_b; /* LayerNorm, eps 1e-5 */
+} cirs_encoder_layer;
+
+typedef struct {
+  int32_t d, nhead, d_hid, nlayers, dim_state, max_len; /* max_len = MAX_TURN + 1 (state_tracker.py:144) */
+  int32_t d_user_in;   /* input width of ffn_user: d (embedding) or 88 (VirtualTaobao dense) */
+  int32_t d_item_in;   /* input width of the item part of fnn_gate: d, or 27 */
+  int32_t n_user, n_item; /* embedding table rows (0 when dense) */
+  float* emb_user; /* [n_user, d] or NULL when the user observation is dense (core/inputs.py:24-44) */
+  float* emb_item; /* [n_item, d] or NULL */
+  float *user_wt, *user_b; /* ffn_user  Wt[d_user_in][ldd] (state_tracker.py:146) */
+  float *gate_wt, *gate_b; /* fnn_gate  Wt[1 + d_item_in][ldd], row 0 multiplies the reward (:150) */
+  float* pe;               /* [max_len, d]  PositionalEncoding table (:255-279); not a parameter */
+  cirs_encoder_layer layer[CIRS_MAX_LAYERS];
+  float *dec_wt, *dec_b;   /* decoder Wt[d][ld_state] (:158) */
+  float* flat;             /* base of the flat parameter buffer (everything above except pe) */
+  int64_t n_flat;
+} cirs_tracker_weights;
+
+/* build_state(): state_tracker.py:188-250, dropout = 0, with a per-environment K/V cache instead of the
+ * reference's whole-prefix recompute (exact by causality).
+ *   pos[e] : sequence position to write (0 = user token, t >= 1 = action token of turn t-1); read per env slot
+ *   expect_pos : >= 0 -> rows whose pos[e] differs are skipped (the fused rollout passes the current turn so that
+ *            environments that finished earlier are skipped but those that finished THIS turn still get their
+ *            last obs_next, as in collector.py:261-269); -1 -> no filter
+ *   idx[n] : user id (pos 0) or item id (pos >= 1) when the corresponding embedding table is non-NULL
+ *   dense[n, d_*_in] : dense user / item features otherwise
+ *   rew[n] : reward of the transition (ignored at pos 0)
+ * kcache / vcache: [nlayers, B, max_len, d].
+ * Outputs (each optional): state_out[k * state_stride ..+dim_state) per row;  cur_state[e * dim_state ..] per
+ * environment slot;  traj_obs[(e*traj_len + p) * dim_state ..] when p < traj_len and
+ * traj_obs_next[(e*traj_len + p-1) * dim_state ..] when p >= 1 -- the replay buffer's obs / obs_next slots
+ * (tianshou/data/buffer/base.py:238-275, env-major vecbuf.py:26-30). */
+int cirs_tracker_step(const cirs_tracker_weights* w, int32_t n_env, int32_t n_rows, const int32_t* env_id,
+                      const uint8_t* active, const int32_t* pos, int32_t expect_pos, const int32_t* idx,
+                      const float* dense, const float* rew, float* kcache, float* vcache, float* state_out,
+                      int64_t state_stride, float* cur_state, int32_t traj_len, float* traj_obs,
+                      float* traj_obs_next, void* stream);
+
+/* Training pass of the tracker (replaces autograd through the observations stored in the replay buffer,
+ * core/policy/ppo.py:215 loss.backward(retain_graph=True) -> tianshou/data/batch.py:256-258):
+ * one full-sequence causal forward over every environment's token sequence followed by the backward pass,
+ * given d_obs = d loss / d obs for every stored observation (accumulated by cirs_ppo_minibatch over the last
+ * repeat).  Sequences: environment e has n_tok[e] = ep_len[e] observation positions 0..ep_len[e]-1
+ * (position 0 = user token, position p>=1 = action token of turn p-1, reward traj_rew[e, p-1]).
+ *   users[B], traj_act[B, L], traj_rew[B, L], ep_len[B]   the rollout record (L = traj_len)
+ *   d_obs[B*L, dim_state]                                  upstream gradient per buffer slot (e*L + p)
+ *   grads                                                  same layout as w; ACCUMULATED into (zero it first)
+ *   workspace / workspace_bytes                            cirs_tracker_train_workspace_bytes(...) bytes
+ * dense_user[B, d_user_in] / dense_item[B, L, d_item_in] replace users / traj_act when the tables are NULL. */
+int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_t n_env, int32_t traj_len);
+int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights* grads, int32_t n_env,
+                       int32_t traj_len, const int32_t* users, const int32_t* traj_act, const float* traj_rew,
+                       const int32_t* ep_len, const float* dense_user, const float* dense_item,
+                       const float* d_obs, float* obs_check, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------ policy / value heads ---------------- */
+typedef struct {
+  int32_t dim_state, n_action;
+  int32_t ld_action;  /* n_action rounded up to 128 */
+  float *w1t, *b1; /* Net layer 0: Wt[dim_state][64]  (utils/net/common.py:87-92) */
+  float *w2t, *b2; /* Net layer 1: Wt[64][64] */
+  float *w3t, *b3; /* Actor.last: Wt[64][ld_action]  (utils/net/discrete.py:56-67) */
+  float *wv, *bv;  /* Critic.last: [64], [1]          (discrete.py:109-114) */
+  float* flat;     /* base of the flat buffer that holds all of the above, trunk first */
+  int64_t n_flat;  /* floats in the flat buffer */
+  int64_t n_trunk; /* leading floats that belong to the shared trunk (w1t, b1, w2t, b2) */
+} cirs_policy_weights;
+
+/* policy.forward(): core/policy/ppo.py:111-163 for the discrete actor: softmax over the whole catalogue and
+ * Categorical.sample(), i.e. the exponential race argmax_j p_j / q_j, q ~ Exp(1), fused with the
+ * logits GEMM so the [n, n_action] probabilities are never written.
+ *   state   : row k reads state + (env_id ? k : e) * state_stride   (compact rows with env_id, per-slot without)
+ *   noise_q : [n_rows, n_action] Exp(1) draws supplied by the caller (parity tests) or NULL -> Philox(seed, offset)
+ *   mode    : 0 sample, 1 argmax (deterministic_eval)
+ *   seen    : optional [B, ceil(n_action/32)] bitset; set bits are removed from the distribution
+ *             (remove_recommended_ids, core/policy/utils.py:30-58)
+ * Outputs per row k: act (i32), logp = Categorical.log_prob(act) (f32), value = critic(s) (f32).
+ * workspace: cirs_actor_workspace_bytes(n_rows, n_action) bytes of device scratch. */
+int64_t cirs_actor_workspace_bytes(int32_t n_rows, int32_t n_action);
+int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_t* env_id, const uint8_t* active,
+                      const float* state, int64_t state_stride, const float* noise_q, uint64_t seed,
+                      uint64_t offset, int32_t mode, const uint32_t* seen, int32_t* act, float* logp,
+                      float* value, void* workspace, void* stream);
+
+/* Critic / log-prob evaluation without sampling: A2CPolicy._compute_returns' critic(obs) calls
+ * (tianshou/policy/modelfree/a2c.py:89-90) and PPOPolicy.process_fn's old log-prob (core/policy/ppo.py:104-108).
+ * obs[n_rows, dim_state] (row r reads obs + (row_idx ? row_idx[r] : r) * dim_state);  act may be NULL (value
+ * only).  value / logp are indexed like obs (by row_idx[r] when given). */
+int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, const int32_t* row_idx, const float* obs,
+                     const int32_t* act, float* value, float* logp, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ returns (GAE) ----------------------- */
+/* A2CPolicy._compute_returns (a2c.py:80-109) + BasePolicy.compute_episodic_return / _gae_return
+ * (tianshou/policy/base.py:272-313, 380-396) + RunningMeanStd.update (utils/statistics.py:80-95), float64
+ * arithmetic like the reference.  Buffer slots are env-major [B, L]; environment e holds n_slot[e] transitions.
+ *   v_s, v_next : critic outputs (normalised space) per slot;  rew, done per slot
+ *   ret_rms     : double[3] = {mean, var, count} on the device (reward_normalization = 1; read only here);
+ *                 NULL -> no normalisation
+ *   scratch     : double[2 * n_env] device scratch;  moments: double[3] = raw {sum, sumsq, count} of this call's
+ *                 unnormalised returns (NULL -> not computed).  Ranks all-reduce `moments` before merging.
+ *   out: returns[B*L] (normalised, f32), adv[B*L] (f32).  Slots t >= n_slot[e] are left untouched.
+ * An episode still running at its last stored slot ends the scan there (unfinished_index, base.py:308-309).
+ * cirs_rms_update merges the batch moments into ret_rms (RunningMeanStd.update, statistics.py:80-95). */
+int cirs_compute_returns(int32_t n_env, int32_t traj_len, const int32_t* n_slot, const float* v_s,
+                         const float* v_next, const float* rew, const uint8_t* done, double gamma,
+                         double gae_lambda, const double* ret_rms, double* scratch, double* moments,
+                         float* returns, float* adv, void* stream);
+int cirs_rms_update(double* ret_rms, const double* moments, void* stream);
+
+/* ------------------------------------------------------------------ PPO update -------------------------- */
+typedef struct {
+  float eps_clip, vf_coef, ent_coef, max_grad_norm; /* CIRS-RL-kuaishou.py:97-104 */
+  int32_t value_clip, norm_adv;                     /* ppo.py:185-186, 200-205 */
+  float lr, beta1, beta2, adam_eps;                 /* torch.optim.Adam defaults, lr 1e-3 */
+} cirs_ppo_config;
+
+/* Per-minibatch advantage statistics (ppo.py:185-186: mean and UNBIASED std over the minibatch), computed for
+ * n_mb minibatches at once: minibatch j = slots idx[mb_off[j] .. mb_off[j+1]).  stats[j] = {count, sum, sumsq}
+ * in float64 -- raw moments so that ranks can all-reduce them before use. */
+int cirs_adv_stats(int32_t n_mb, const int32_t* mb_off, const int32_t* idx, const float* adv, double* stats,
+                   void* stream);
+
+/* One PPO minibatch, forward + loss + backward (core/policy/ppo.py:181-220):
+ *   idx[n]  buffer slots of the minibatch;  obs[., dim_state], act, adv, returns, v_old, logp_old per slot
+ *   adv_stat  double[3] {count, sum, sumsq} of this (global) minibatch;  n_global = number of rows the losses
+ *             are averaged over (== n unless the minibatch is sharded over ranks)
+ *   grads   gradient buffer (same layout as w), OVERWRITTEN with d loss / d params (local partial sums)
+ *   d_obs   [., dim_state] d loss / d obs written at the minibatch's slots (the tracker's upstream gradient)
+ *   losses  float[4] {loss, clip, vf, ent}: local partial sums already divided by n_global
+ * workspace: cirs_ppo_workspace_bytes(n_max, n_action). */
+int64_t cirs_ppo_workspace_bytes(int32_t n_rows, int32_t n_action);
+int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_policy_weights* grads, const cirs_ppo_config* cfg,
+                       int32_t n, int32_t n_global, const int32_t* idx, const float* obs, const int32_t* act,
+                       const float* adv, const float* returns, const float* v_old, const float* logp_old,
+                       const double* adv_stat, float* d_obs, float* losses, void* workspace, void* stream);
+
+/* clip_grad_norm_ + Adam over a flat parameter buffer (ppo.py:221-226; torch.optim.Adam single-tensor CPU
+ * semantics).  The first n_dup elements belong to tensors that occur TWICE in the reference's parameter list
+ * (the trunk shared by actor and critic, CIRS-RL-kuaishou.py:245-258): they count twice in the
+ * norm, are scaled by coef^2, and receive two sequential Adam updates (step counter += 2).
+ *   state   int32[2] on the device: {steps taken by ordinary tensors, steps taken by duplicated tensors}
+ *   max_grad_norm <= 0 -> no clipping.   scratch: double[2] device scratch. */
+int cirs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t n_dup,
+                   const cirs_ppo_config* cfg, int32_t* state, double* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,150 @@
+"""CPU-side tests (no GPU needed): the C-ABI library loads and exports every symbol include/cirs_b200.h declares,
+the ctypes binding covers the header, and the host-side logic (parameter packing, replay-buffer index arithmetic,
+minibatch splitting, feature columns) behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "cirs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cirs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from cirs_codes_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cirs_b200.h but not exported"
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes and header disagree"
+    lib.cirs_abi_version.restype = ctypes.c_int
+    assert lib.cirs_abi_version() == _lib.ABI_VERSION
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import cirs_codes_b200 as cb
+    from cirs_codes_b200._lib import CirsError
+    with pytest.raises(CirsError):
+        cb.KuaishouVectorEnv(2, np.zeros((3, 4)), [[1]] * 4, normed_mat=np.zeros((3, 4)))
+
+
+def test_struct_sizes_match_c_layout():
+    """sizeof() of the ctypes mirrors against the sizes the C compiler reports (compiled on the fly with gcc)."""
+    import subprocess
+    import tempfile
+    from cirs_codes_b200 import _lib
+    prog = r'''
+#include <stdio.h>
+#include "cirs_b200.h"
+int main(void){printf("%zu %zu %zu %zu %zu\n", sizeof(cirs_kuaishou_env), sizeof(cirs_encoder_layer),
+  sizeof(cirs_tracker_weights), sizeof(cirs_policy_weights), sizeof(cirs_ppo_config)); return 0;}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o",
+                        os.path.join(d, "t")], check=True)
+        got = [int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(s) for s in (_lib.KuaishouEnvStruct, _lib.EncoderLayerStruct, _lib.TrackerWeightsStruct,
+                                       _lib.PolicyWeightsStruct, _lib.PPOConfigStruct)]
+    assert got == want
+
+
+def test_param_pack_roundtrip_policy_and_tracker():
+    from cirs_codes_b200 import params, net
+    torch.manual_seed(0)
+    n = net.Net(20, hidden_sizes=[64, 64])
+    a, c = net.Actor(n, 300), net.Critic(n)
+    L = params.policy_layout(20, 300)
+    flat = L.pack(params.policy_sd_from_reference(a.state_dict(), c.state_dict()), "cpu")
+    assert flat.numel() == L.total and L.segs["actor.last.weight"].ld == 384 and L.n_trunk % 32 == 0
+    a2, c2 = params.policy_sd_to_reference(L.unpack(flat))
+    for k, v in a.state_dict().items():
+        assert torch.equal(a2[k], v), k
+    for k, v in c.state_dict().items():
+        assert torch.equal(c2[k], v), k
+    # k-major storage: Wt[in][ld]
+    w = a.state_dict()["last.model.0.weight"]
+    seg = L.segs["actor.last.weight"]
+    view = flat[seg.offset:seg.offset + 64 * seg.ld].view(64, seg.ld)
+    assert torch.equal(view[:, :300], w.t()) and torch.all(view[:, 300:] == 0)
+    T = params.tracker_layout(32, 4, 128, 2, 20, 31, n_user=7, n_item=9)
+    enc = torch.nn.TransformerEncoder(torch.nn.TransformerEncoderLayer(32, 4, 128, 0.0), 2, enable_nested_tensor=False)
+    sd = {"transformer_encoder." + k: v for k, v in enc.state_dict().items()}
+    sd.update({"embedding_dict.feat_user.weight": torch.randn(7, 32), "embedding_dict.feat_item.weight": torch.randn(9, 32),
+               "ffn_user.weight": torch.randn(32, 32), "ffn_user.bias": torch.randn(32),
+               "fnn_gate.weight": torch.randn(32, 33), "fnn_gate.bias": torch.randn(32),
+               "decoder.weight": torch.randn(20, 32), "decoder.bias": torch.randn(20)})
+    back = T.unpack(T.pack(sd, "cpu"))
+    assert set(back) == set(sd)
+    for k in sd:
+        assert torch.equal(back[k], sd[k]), k
+    from oracle import nets
+    assert torch.allclose(params.positional_encoding(31, 27), nets.positional_encoding(31, 27))
+
+
+def test_replay_buffer_layout_and_index_arithmetic():
+    """VectorReplayBuffer slot layout and prev / next / unfinished_index (tianshou/test/base/test_buffer.py's
+    ReplayBufferManager cases restated for the env-major layout), on the host with device='cpu'."""
+    from cirs_codes_b200.data import Batch, VectorReplayBuffer
+    buf = VectorReplayBuffer(20, 4, device="cpu")           # 4 sub-buffers of 5 slots
+    assert buf.maxsize == 20 and buf.sub_size == 5
+    S = 3
+
+    def add(ids, done):
+        n = len(ids)
+        b = Batch(obs=torch.ones(n, S) * len(buf), obs_next=torch.ones(n, S), act=np.array(ids) + 10,
+                  rew=np.ones(n), done=np.array(done))
+        return buf.add(b, buffer_ids=np.array(ids))
+
+    ptr, ep_rew, ep_len, ep_idx = add([0, 1, 2, 3], [0, 0, 0, 0])
+    assert list(ptr) == [0, 5, 10, 15] and list(ep_len) == [0, 0, 0, 0]
+    ptr, ep_rew, ep_len, ep_idx = add([0, 1, 3], [0, 1, 0])
+    assert list(ptr) == [1, 6, 16] and list(ep_len) == [0, 2, 0] and list(ep_rew) == [0, 2, 0] and ep_idx[1] == 5
+    ptr, *_ = add([0, 3], [1, 0])
+    assert list(ptr) == [2, 17]
+    assert len(buf) == 9
+    assert list(buf.sample_index(0)) == [0, 1, 2, 5, 6, 10, 15, 16, 17]
+    assert list(buf.last_index) == [2, 6, 10, 17]
+    assert list(buf.unfinished_index()) == [10, 17]
+    assert list(buf.prev([0, 1, 2, 6, 10, 17])) == [0, 0, 1, 5, 10, 16]
+    assert list(buf.next([0, 1, 2, 5, 6, 10, 16, 17])) == [1, 2, 2, 6, 6, 10, 17, 17]
+    assert list(buf.act[[0, 5, 17]]) == [10, 11, 13] and buf.done[6] and not buf.done[5]
+    b, idx = buf.sample(0)
+    assert len(idx) == 9 and b.obs.shape == (9, S)
+    buf.reset()
+    assert len(buf) == 0
+
+
+def test_split_indices_matches_oracle():
+    from cirs_codes_b200.policy import split_indices
+    from oracle import ppo
+    for n, size in ((10, 3), (12, 4), (7, 16), (33, 8), (16, 16)):
+        perm = np.random.default_rng(n).permutation(n)
+        a, b = split_indices(n, size, perm), ppo.split_indices(n, size, perm)
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_feature_columns_surface():
+    import cirs_codes_b200 as cb
+
+    class E:
+        mat = np.zeros((7, 9))
+
+    u, a, f, hu, ha, hf = cb.get_dataset_columns(32, "KuaishouEnv-v0", E)
+    assert (u[0].vocabulary_size, a[0].vocabulary_size, u[0].embedding_dim) == (7, 9, 32) and not hu and not ha and hf
+    assert cb.compute_input_dim(a) == 32 and cb.build_input_features(u + f) == {"feat_user": (0, 1), "feat_feedback": (1, 2)}
+    u, a, f, hu, ha, hf = cb.get_dataset_columns(27, "VirtualTB-v0")
+    assert cb.compute_input_dim(u) == 88 and cb.compute_input_dim(a) == 27 and hu and ha
