@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the CIRS hot path (rollout + PPO update) on B200, and the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config configs1|configs2|small]
+
+One "step" = one training iteration of the reference's loop (core/trainer/onpolicy.py:156-201):
+``collector.collect(n_episode=B)`` followed by ``policy.update(0, buffer, batch_size, repeat=2)`` on synthetic
+KuaiRec-shaped tables.  An env-step is one (environment, turn) transition added to the buffer -- the
+reference's own ``train_speed`` unit (tianshou/trainer/utils.py:73).
+
+JSON line (rank 0):  value = env-steps/s with the step's inputs (users, minibatch permutations) already resident in
+HBM, timed with CUDA events; e2e = the same through the public API with HOST inputs (pinned H2D of users and
+permutations, D2H of lengths / rewards / losses inside the timed region); roofline = the dominant kernel of the
+step, its duration measured live with CUDA events on the launching stream (cirs_profile_*); cpu_baseline = the CPU
+oracle port on a bounded sample on this box's host cores.  Multi-GPU: environments are sharded over ranks (weak
+scaling: --gpus N runs N x B environments), one NCCL all-reduce of the policy gradient per PPO minibatch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (512 envs per GPU -> 4096 at 8 GPUs)
+    "configs1": dict(U=7176, I=10728, B=512, d=32, nhead=4, T=30, N=1, thr=0, batch_size=1024, repeat=2,
+                     name="configs[1]: KuaishouEnv 7176x10728 synthetic, 512 envs/GPU, emb_dim=32, max_turn=30, "
+                          "N=1 thr=0 (reference defaults), PPO batch 1024 x repeat 2"),
+    # BASELINE.json configs[2]
+    "configs2": dict(U=7176, I=10728, B=4096, d=64, nhead=4, T=30, N=5, thr=0, batch_size=4096, repeat=2,
+                     name="configs[2]: KuaishouEnv 7176x10728 synthetic, 4096 envs/GPU, emb_dim=64, window N=5, "
+                          "PPO batch 4096 x repeat 2"),
+    "small": dict(U=300, I=1000, B=64, d=32, nhead=4, T=12, N=1, thr=0, batch_size=128, repeat=2,
+                  name="small (debug)"),
+}
+REF = dict(tau=100.0, gamma_exposure=10.0, r_decay=1.0, version="v1", dim_state=20, lr=1e-3, gamma=0.95,
+           gae_lambda=0.95, eps_clip=0.2, vf_coef=0.25, ent_coef=0.0, max_grad_norm=0.5)  # CIRS-RL-kuaishou.py:64-110
+
+
+def tables(cfg, seed=2023):
+    from cirs_codes_b200 import synth
+    return synth.kuaishou_tables(cfg["U"], cfg["I"], seed=seed)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def oracle_objects(cfg, tb, B, seed):
+    import torch
+    from oracle import env as oenv, nets, ppo
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    d, S, I = cfg["d"], REF["dim_state"], cfg["I"]
+    env = oenv.KuaishouSimOracle(tb["mat"], tb["normed_mat"], tb["cats"], tb["alpha_u"], tb["beta_i"],
+                                 max_turn=cfg["T"], num_leave_compute=cfg["N"], leave_threshold=cfg["thr"],
+                                 tau=REF["tau"], gamma_exposure=REF["gamma_exposure"], r_decay=REF["r_decay"],
+                                 version=REF["version"])
+    P = {"embedding_dict.feat_user.weight": torch.randn(cfg["U"], d) * 1e-4,
+         "embedding_dict.feat_item.weight": torch.randn(I, d) * 1e-4}
+    enc = nn.TransformerEncoder(nn.TransformerEncoderLayer(d, cfg["nhead"], 128, 0.0), 2, enable_nested_tensor=False)
+    for name, mod in (("ffn_user", nn.Linear(d, d)), ("fnn_gate", nn.Linear(1 + d, d)), ("transformer_encoder", enc),
+                      ("decoder", nn.Linear(d, S))):
+        for k, v in mod.state_dict().items():
+            P[f"{name}.{k}"] = v.detach().clone()
+    P = {k: v.requires_grad_(True) for k, v in P.items()}
+    R = {}
+    for k, shape in (("preprocess.model.model.0", (64, S)), ("preprocess.model.model.2", (64, 64)),
+                     ("actor.last", (I, 64)), ("critic.last", (1, 64))):
+        w = torch.empty(*shape)
+        nn.init.orthogonal_(w)
+        R[k + ".weight"], R[k + ".bias"] = w, torch.zeros(shape[0])
+    tracker = nets.TrackerOracle(P, cfg["nhead"], cfg["T"])
+    return env, tracker, P, R, ppo.AdamDup(), ppo.AdamDup(), ppo.RunningMeanStd()
+
+
+def oracle_step(cfg, objs, users, rng):
+    import torch
+    from oracle import pipeline
+    env, tracker, P, R, opt_rl, opt_tr, rms = objs
+
+    def noise(turn, n, A):
+        return torch.empty(n, A).exponential_(1)
+
+    traj, res = pipeline.collect(env, tracker, R, users, noise=noise)
+    n = len(traj.act)
+    perms = [rng.permutation(n) for _ in range(cfg["repeat"])]
+    pipeline.update(traj, R, opt_rl, list(P.values()), opt_tr, rms, perms, cfg["batch_size"], gamma=REF["gamma"],
+                    gae_lambda=REF["gae_lambda"], eps_clip=REF["eps_clip"], vf_coef=REF["vf_coef"],
+                    ent_coef=REF["ent_coef"], max_grad_norm=REF["max_grad_norm"])
+    return res["n/st"]
+
+
+def cpu_arm(cfg, tb, B_sample, budget_s, max_steps, seed=0):
+    """Time the CPU oracle port (all host threads) on a bounded sample: B_sample environments of the same workload,
+    whole iterations until ``budget_s`` seconds or ``max_steps`` iterations."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    objs = oracle_objects(cfg, tb, B_sample, seed)
+    rng = np.random.default_rng(seed)
+    steps, t_total, it = 0, 0.0, 0
+    while it < max_steps and (t_total < budget_s or it == 0):
+        users = rng.integers(0, cfg["U"], size=B_sample)
+        t0 = time.perf_counter()
+        n = oracle_step(cfg, objs, users, rng)
+        dt = time.perf_counter() - t0
+        if it > 0 or max_steps == 1:       # first iteration is warm-up unless it is the only one
+            steps, t_total = steps + n, t_total + dt
+        it += 1
+    return dict(value=steps / max(t_total, 1e-9), unit="env-steps/s", cores=cores, kind="port",
+                sample=f"{B_sample} envs x {max(it - 1, 1)} iterations of the same workload (oracle/pipeline.py collect + "
+                       f"update, torch CPU {torch.get_num_threads()} threads), {t_total:.1f} s"), steps, t_total, it
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p, self.index = None, index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        out = self.p.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def k1_bytes(lens, N):
+    """Algorithmic HBM bytes of the env-step kernel over whole episodes (mask-recompute variant):
+    bytes(t) = 57 + 20 w(t, N) + 20 t."""
+    tot = 0
+    for n, c in zip(*np.unique(lens, return_counts=True)):
+        t = np.arange(int(n))
+        w = np.where(t == 0, 0, np.where(t < N, t - np.maximum(0, 2 * t - N), N))
+        tot += int(c) * int(np.sum(57 + 20 * w + 20 * t))
+    return tot
+
+
+def gpu_arm(args, cfg):
+    import torch
+    import cirs_codes_b200 as cb
+    from cirs_codes_b200 import _lib, parallel
+    rank, world = parallel.init_from_env("nccl")
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    dist = torch.distributed if world > 1 else None
+    tb = tables(cfg)
+    B, T = cfg["B"], cfg["T"]
+
+    class _E:
+        mat = np.zeros((cfg["U"], cfg["I"]), dtype=np.float32)
+
+    env = cb.KuaishouVectorEnv(B, tb["mat"], tb["cats"], normed_mat=tb["normed_mat"], alpha_u=tb["alpha_u"],
+                               beta_i=tb["beta_i"], simulated=True, max_turn=T, num_leave_compute=cfg["N"],
+                               leave_threshold=cfg["thr"], tau=REF["tau"], gamma_exposure=REF["gamma_exposure"],
+                               r_decay=REF["r_decay"], version=REF["version"], device=dev, seed=1000 + rank)
+    cols = cb.get_dataset_columns(cfg["d"], "KuaishouEnv-v0", _E)
+    trk = cb.StateTrackerTransformer(cols[0], cols[1], cols[2], dim_model=cfg["d"], dim_state=REF["dim_state"],
+                                     dim_max_batch=B, dataset="KuaishouEnv-v0", has_user_embedding=cols[3],
+                                     has_action_embedding=cols[4], has_feedback_embedding=cols[5], nhead=cfg["nhead"],
+                                     d_hid=128, nlayers=2, dropout=0.0, device=dev, seed=2023, MAX_TURN=T)
+    torch.manual_seed(2023)
+    net = cb.Net(REF["dim_state"], hidden_sizes=[64, 64])
+    actor, critic = cb.Actor(net, cfg["I"]), cb.Critic(net)
+    cb.orthogonal_init(actor, critic)
+    optim = [torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=REF["lr"]),
+             torch.optim.Adam(trk.parameters(), lr=REF["lr"])]
+    pol = cb.PPOPolicy(actor, critic, optim, torch.distributions.Categorical, discount_factor=REF["gamma"],
+                       max_grad_norm=REF["max_grad_norm"], eps_clip=REF["eps_clip"], vf_coef=REF["vf_coef"],
+                       ent_coef=REF["ent_coef"], reward_normalization=1, advantage_normalization=1,
+                       recompute_advantage=0, value_clip=1, gae_lambda=REF["gae_lambda"], action_bound_method="",
+                       action_scaling=False, device=dev, seed=77 + rank)
+    buf = cb.VectorReplayBuffer(B * T, B, device=dev)
+    col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state)
+    assert col.fused
+    lib = _lib.load()
+    rng = np.random.default_rng(5 + rank)
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def one_step(users, resident):
+        pol.perm_on_device = resident
+        res = col.collect(n_episode=B, users=users)
+        pol.update(0, buf, batch_size=cfg["batch_size"], repeat=cfg["repeat"])
+        return res
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(K, resident):
+        users_all = [rng.integers(0, cfg["U"], size=B) for _ in range(K)]
+        if resident:
+            users_all = [torch.as_tensor(u.astype(np.int32), device=dev) for u in users_all]
+        steps, h2d, d2h, lens_all, ms = 0, 0, 0, [], 0.0
+        barrier()
+        for k in range(K):
+            flush.fill_(float(k))                       # evict L2 between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            res = one_step(users_all[k], resident)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+            steps += res["n/st"]
+            lens_all.append(res["lens"])
+            h2d += col.h2d_bytes + pol.h2d_bytes
+            d2h += col.d2h_bytes + pol.d2h_bytes
+        barrier()
+        t = torch.tensor([ms, float(steps)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, steps = float(tm[0]), float(t[1])
+        return ms, steps, h2d / K, d2h / K, np.concatenate(lens_all)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(rng.integers(0, cfg["U"], size=B), False)
+    one_step(torch.as_tensor(rng.integers(0, cfg["U"], size=B).astype(np.int32), device=dev), True)
+    clocks = Clocks(dev.index or 0)
+    clocks.start()
+    l0 = lib.cirs_launch_count()
+    ms_res, steps_res, _, _, lens = timed(args.steps, True)
+    launches = lib.cirs_launch_count() - l0
+    ms_e2e, steps_e2e, h2d, d2h, _ = timed(args.steps, False)
+    clk = clocks.stop()
+
+    # ---- per-kernel durations, live, CUDA events on the launching stream (separate pass: events perturb the step)
+    kern, roof = {}, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        which = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
+        lib.cirs_profile_enable(1)
+        lens_p = []
+        n_prof = min(args.steps, 3)
+        for _ in range(n_prof):
+            lens_p.append(one_step(rng.integers(0, cfg["U"], size=B), False)["lens"])
+        rep = _lib.profile_report()
+        lib.cirs_profile_enable(0)
+        lens_p = np.concatenate(lens_p)
+        total_ms = sum(v[1] for v in rep.values())
+        n_tr = int(lens_p.sum())
+        A, S = cfg["I"], REF["dim_state"]
+        head_flops = 2.0 * (S * 64 + 64 * 64 + 64 * A)
+        algo = {  # algorithmic work over the profiled pass, per kernel (DESIGN.md "kernels")
+            "kuaishou_step_kernel": ("hbm", k1_bytes(lens_p, cfg["N"])),
+            "actor_head_kernel": ("tensor", head_flops * n_tr * (1 + 1) + 2.0 * (S * 64 + 64 * 64) * n_tr),
+            "head_logits_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
+            "head_dW3_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
+            "head_dh2_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
+            "row_loss_kernel": ("hbm", 4.0 * A * n_tr * cfg["repeat"]),
+        }
+        for name, (cnt, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+            kern[name] = {"launches": cnt, "ms": round(ms, 4), "share": round(ms / total_ms, 4)}
+            if name in algo:
+                bound, work = algo[name]
+                ach = work / (ms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
+                peak = hbm_peak if bound == "hbm" else tc_peak
+                kern[name].update(bound=bound, achieved=round(ach, 3), peak=peak, frac=round(ach / peak, 5),
+                                  unit="GB/s" if bound == "hbm" else "TFLOP/s")
+        top = next((k for k in kern if "bound" in kern[k]), None)
+        if top:
+            roof = {"kernel": top, "bound": kern[top]["bound"], "achieved": kern[top]["achieved"],
+                    "peak": kern[top]["peak"], "unit": kern[top]["unit"], "frac": kern[top]["frac"], "traffic": None,
+                    "peak_source": which, "share_of_step": kern[top]["share"],
+                    "note": "FP32 FFMA GEMM measured against the bf16 tensor peak" if kern[top]["bound"] == "tensor"
+                    else "algorithmic bytes 57+20w+20t per env-step"}
+    out = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, *_ = cpu_arm(cfg, tb, min(B, args.cpu_envs), args.cpu_seconds, 50)
+        out = {
+            "metric": "env-steps/sec (rollout+PPO update)", "value": steps_res / (ms_res * 1e-3), "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "envs_per_gpu": B, "global_envs": B * world,
+                       "mean_episode_len": float(np.mean(lens)), "env_steps_per_step": steps_res / args.steps,
+                       "parallelism": f"env-sharded dp{world}", "l2": "192 MB flush between timed iterations",
+                       "timing": "CUDA events per step, max over ranks"},
+            "e2e": {"value": steps_e2e / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+        }
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="configs1", choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
+    ap.add_argument("--cpu-envs", type=int, default=128)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.envs:
+        cfg["B"] = args.envs
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        tb = tables(cfg)
+        B = min(cfg["B"], args.cpu_envs)
+        cpu, steps, t_total, it = cpu_arm(cfg, tb, B, 1e9, args.warmup + args.steps if args.steps < 20 else 20)
+        v = cpu["value"]
+        cpu["value"] = v
+        print(json.dumps({
+            "impl": "reference", "metric": "env-steps/sec (rollout+PPO update)", "value": v, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(it - 1, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "sample_envs": B}, "cpu_baseline": cpu,
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    out = gpu_arm(args, cfg)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

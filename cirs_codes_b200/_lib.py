@@ -58,6 +58,9 @@ P = C.POINTER
 PROTOTYPES = {
     "cirs_last_error": (C.c_char_p, []),
     "cirs_abi_version": (i32, []),
+    "cirs_launch_count": (i64, []),
+    "cirs_profile_enable": (None, [i32]),
+    "cirs_profile_report": (i32, [C.c_char_p, i32]),
     "cirs_kuaishou_reset": (i32, [P(KuaishouEnvStruct), i32, fp, fp, fp, fp]),
     "cirs_kuaishou_step": (i32, [P(KuaishouEnvStruct), i32, fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, i32, fp]),
     "cirs_tracker_step": (i32, [P(TrackerWeightsStruct), i32, i32, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, i64,
@@ -122,6 +125,17 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise CirsError(f"{name} failed ({rc}): {lib.cirs_last_error().decode()}")
+
+
+def profile_report():
+    """{kernel name: (launches, total ms)} since profiling was enabled; clears the records."""
+    buf = C.create_string_buffer(1 << 16)
+    load().cirs_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def require_cuda():

@@ -46,6 +46,7 @@ class Collector:
                           and hasattr(policy, "sample_device") and isinstance(buffer, VectorReplayBuffer)
                           and buffer.buffer_num == self.env_num and not remove_recommended_ids)
         self.data = Batch()
+        self.h2d_bytes = self.d2h_bytes = 0   # host<->device traffic of the last fused collect()
         self.reset_stat()
 
     # ------------------------------------------------------------------ resets (collector.py:99-134)
@@ -102,7 +103,8 @@ class Collector:
     def _collect_generic(self, n_episode, random, users, noise_fn):
         ready = np.arange(min(self.env_num, n_episode))
         self.reset(users)
-        if hasattr(self.buffer, "d_users") and np.issubdtype(np.asarray(self._reset_obs).dtype, np.integer):
+        if isinstance(self.buffer, VectorReplayBuffer) and \
+                np.issubdtype(np.asarray(self._reset_obs).dtype, np.integer):
             self.buffer._alloc(self.data.obs.shape[-1])
             self.buffer.d_users.copy_(torch.as_tensor(np.asarray(self._reset_obs).reshape(-1).astype(np.int32)))
         step_count = episode_count = cnt_loop = 0
@@ -167,10 +169,17 @@ class Collector:
                            cur=torch.zeros(B, trk.dim_state, dtype=torch.float32, device=dev),
                            n_active=torch.zeros(1, dtype=torch.int32, device=dev),
                            pin=torch.zeros(2 * T + 8, dtype=torch.int32).pin_memory(),
+                           pin_users=torch.zeros(B, dtype=torch.int32).pin_memory(),
                            ev=[torch.cuda.Event() for _ in range(2 * T + 8)])
         f = self._f
-        users = env.draw_users(B) if users is None else np.asarray(users, dtype=np.int64).reshape(-1)
-        d_users = torch.from_numpy(users.astype(np.int32)).pin_memory().to(dev, non_blocking=True)
+        self.h2d_bytes = self.d2h_bytes = 0
+        if torch.is_tensor(users) and users.is_cuda:                # inputs already resident in HBM
+            d_users = users.to(torch.int32)
+        else:
+            users = env.draw_users(B) if users is None else np.asarray(users, dtype=np.int64).reshape(-1)
+            f["pin_users"].copy_(torch.from_numpy(users.astype(np.int32)))
+            d_users = f["pin_users"].to(dev, non_blocking=True)    # pinned host -> device
+            self.h2d_bytes += 4 * B
         self.data = Batch()
         buf.reset()
         trk.build_state(dim_batch=B, reset=True)
@@ -195,6 +204,7 @@ class Collector:
                 break
         lens = buf.d_len.cpu().numpy().astype(np.int64)             # the collect's D2H read (also a sync)
         rews = env.cum_rew.cpu().numpy()
+        self.d2h_bytes += 4 * B + 8 * B + 4 * turns
         buf.set_from_device(lens)
         order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
         res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])

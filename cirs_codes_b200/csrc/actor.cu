@@ -300,10 +300,10 @@ int run_head(HeadArgs& P, int32_t* act, float* logp, void* workspace, cudaStream
     cudaFuncSetAttribute(actor_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     attr_set = true;
   }
-  actor_head_kernel<<<grid, NT, SMEM_BYTES, st>>>(P);
+  CIRS_LAUNCH(actor_head_kernel, grid, NT, SMEM_BYTES, st, P);
   CIRS_CHECK_LAUNCH();
   if (act || logp) {
-    actor_combine_kernel<<<(P.n_rows + 127) / 128, 128, 0, st>>>(P, act, logp);
+    CIRS_LAUNCH(actor_combine_kernel, (P.n_rows + 127) / 128, 128, 0, st, P, act, logp);
     CIRS_CHECK_LAUNCH();
   }
   return CIRS_OK;

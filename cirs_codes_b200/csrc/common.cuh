@@ -18,6 +18,19 @@
   } while (0)
 
 void cirs_set_error(const char* msg);
+void cirs_note_launch(void);  // counts kernel launches issued by this library (bench.py's gpu_launches)
+// optional per-kernel timing with CUDA events on the launching stream (cirs_profile_enable, error.cu)
+bool cirs_profile_begin(const char* name, cudaStream_t st);
+void cirs_profile_end(cudaStream_t st);
+
+// every kernel launch of the library goes through this macro (grid, block, dynamic smem, stream, args...)
+#define CIRS_LAUNCH(kernel, grid, block, smem, stream, ...)       \
+  do {                                                            \
+    const bool prof__ = cirs_profile_begin(#kernel, (stream));    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+    cirs_note_launch();                                           \
+    if (prof__) cirs_profile_end((stream));                       \
+  } while (0)
 
 #define FULL_MASK 0xffffffffu
 #define CATEGORICAL_EPS 1.1920928955078125e-07f  // torch.finfo(float32).eps, Categorical clamp_probs

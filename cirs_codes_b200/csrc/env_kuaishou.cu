@@ -139,7 +139,7 @@ extern "C" int cirs_kuaishou_reset(const cirs_kuaishou_env* env, int32_t n_rows,
   }
   if (n_rows == 0) return CIRS_OK;
   const int grid = (n_rows + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  kuaishou_reset_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(*env, n_rows, env_id, users,
+  CIRS_LAUNCH(kuaishou_reset_kernel, grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream, *env, n_rows, env_id, users,
                                                                                    active);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
@@ -167,7 +167,7 @@ extern "C" int cirs_kuaishou_step(const cirs_kuaishou_env* env, int32_t n_rows, 
   }
   if (n_rows == 0) return CIRS_OK;
   const int grid = (n_rows + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  kuaishou_step_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+  CIRS_LAUNCH(kuaishou_step_kernel, grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream, 
       *env, n_rows, env_id, active, act, rew, done, traj_len, traj_act, traj_rew, traj_done, ep_len,
       force_length);
   CIRS_CHECK_LAUNCH();

@@ -91,11 +91,11 @@ extern "C" int cirs_compute_returns(int32_t n_env, int32_t traj_len, const int32
   }
   if (n_env == 0) return CIRS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  gae_kernel<<<(n_env + 127) / 128, 128, 0, st>>>(n_env, traj_len, n_slot, v_s, v_next, rew, done, gamma,
+  CIRS_LAUNCH(gae_kernel, (n_env + 127) / 128, 128, 0, st, n_env, traj_len, n_slot, v_s, v_next, rew, done, gamma,
                                                   gae_lambda, ret_rms, returns, adv, moments ? scratch : nullptr);
   CIRS_CHECK_LAUNCH();
   if (moments) {
-    moments_kernel<<<1, 1024, 0, st>>>(n_env, n_slot, scratch, moments);
+    CIRS_LAUNCH(moments_kernel, 1, 1024, 0, st, n_env, n_slot, scratch, moments);
     CIRS_CHECK_LAUNCH();
   }
   return CIRS_OK;
@@ -106,7 +106,7 @@ extern "C" int cirs_rms_update(double* ret_rms, const double* moments, void* str
     cirs_set_error("cirs_rms_update: null argument");
     return CIRS_ERR_ARG;
   }
-  rms_merge_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(moments, ret_rms);
+  CIRS_LAUNCH(rms_merge_kernel, 1, 1, 0, (cudaStream_t)stream, moments, ret_rms);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }

@@ -46,12 +46,14 @@ struct ColMajorB {  // B(k,n) = p[n*ld + k]   (a row-major [N, K] matrix used tr
 };
 
 // ---- epilogues ----------------------------------------------------------------------------------------
-struct StoreEp {  // C[row(m)*ld + n] = act(acc + bias[n]) * (mask ? mask[m*ldm+n] > 0 : 1)
+struct StoreEp {  // C[row(m)*ld + n] = act(acc + bias[n]) * (mask ? mask[m*ldm+n] > 0 : 1) + (res ? res[m*ldr+n] : 0)
   float* c; int64_t ld; const float* bias; int relu; const int32_t* row; const float* mask; int64_t ldm;
+  const float* res; int64_t ldr;
   __device__ __forceinline__ void operator()(int m, int n, float v) const {
     if (bias) v += __ldg(bias + n);
     if (relu) v = fmaxf(v, 0.f);
     if (mask && !(mask[(int64_t)m * ldm + n] > 0.f)) v = 0.f;
+    if (res) v += res[(int64_t)m * ldr + n];
     c[(int64_t)(row ? row[m] : m) * ld + n] = v;
   }
 };
@@ -154,14 +156,18 @@ gemm_kernel(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split, float* __
 
 // Host launcher.  split_k: number of K partitions (epilogue must accumulate when > 1).
 template <int BM, int BN, int BK, int TM, class LA, class LB, class EP>
-inline void launch_gemm(LA la, LB lb, EP ep, int M, int N, int K, int split_k, float* colsum, cudaStream_t st) {
+inline void launch_gemm(LA la, LB lb, EP ep, int M, int N, int K, int split_k, float* colsum, cudaStream_t st,
+                        const char* tag = "gemm") {
   if (M <= 0 || N <= 0 || K <= 0) return;
   if (split_k < 1) split_k = 1;
   int kps = (K + split_k - 1) / split_k;
   kps = ((kps + BK - 1) / BK) * BK;
   split_k = (K + kps - 1) / kps;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
+  const bool prof = cirs_profile_begin(tag, st);
   gemm_kernel<BM, BN, BK, TM, LA, LB, EP><<<grid, (BM / TM) * (BN / 4), 0, st>>>(la, lb, ep, M, N, K, kps, colsum);
+  cirs_note_launch();
+  if (prof) cirs_profile_end(st);
 }
 
 }  // namespace cirs

@@ -84,13 +84,13 @@ extern "C" int cirs_clip_adam(float* params, float* grads, float* exp_avg, float
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bump_kernel<<<1, 1, 0, st>>>(state, scratch);
+  CIRS_LAUNCH(bump_kernel, 1, 1, 0, st, state, scratch);
   CIRS_CHECK_LAUNCH();
   if (cfg->max_grad_norm > 0.f) {
-    sumsq_kernel<<<blocks, 256, 0, st>>>(grads, n, n_dup, scratch);
+    CIRS_LAUNCH(sumsq_kernel, blocks, 256, 0, st, grads, n, n_dup, scratch);
     CIRS_CHECK_LAUNCH();
   }
-  adam_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, n_dup, *cfg, state, scratch);
+  CIRS_LAUNCH(adam_kernel, blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, n_dup, *cfg, state, scratch);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }

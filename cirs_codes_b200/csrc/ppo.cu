@@ -293,7 +293,7 @@ extern "C" int cirs_adv_stats(int32_t n_mb, const int32_t* mb_off, const int32_t
     return CIRS_ERR_ARG;
   }
   if (n_mb == 0) return CIRS_OK;
-  adv_stats_kernel<<<n_mb, 1024, 0, (cudaStream_t)stream>>>(mb_off, idx, adv, stats);
+  CIRS_LAUNCH(adv_stats_kernel, n_mb, 1024, 0, (cudaStream_t)stream, mb_off, idx, adv, stats);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }
@@ -323,49 +323,49 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   Workspace ws = carve(workspace, n, ldA);
 
   // ---- forward
-  trunk_fwd_kernel<<<(n + 63) / 64, 256, 0, st>>>(*w, n, idx, obs, ws.h1, ws.h2, ws.value);
+  CIRS_LAUNCH(trunk_fwd_kernel, (n + 63) / 64, 256, 0, st, *w, n, idx, obs, ws.h1, ws.h2, ws.value);
   CIRS_CHECK_LAUNCH();
   launch_gemm<64, 128, 16, 8>(RowMajorA{ws.h2, HID, nullptr}, RowMajorB{w->w3t, ldA, nullptr},
-                              StoreEp{ws.logits, ldA, w->b3, 0, nullptr, nullptr, 0}, n, nA, HID, 1, nullptr, st);
+                              StoreEp{ws.logits, ldA, w->b3, 0, nullptr, nullptr, 0}, n, nA, HID, 1, nullptr, st, "head_logits_gemm");
   CIRS_CHECK_LAUNCH();
-  row_loss_kernel<<<n, 256, 0, st>>>(nA, ldA, *cfg, n_global, idx, act, adv, returns, v_old, logp_old, adv_stat,
+  CIRS_LAUNCH(row_loss_kernel, n, 256, 0, st, nA, ldA, *cfg, n_global, idx, act, adv, returns, v_old, logp_old, adv_stat,
                                      ws);
   CIRS_CHECK_LAUNCH();
-  loss_reduce_kernel<<<1, 1024, 0, st>>>(n, n_global, *cfg, ws.terms, losses);
+  CIRS_LAUNCH(loss_reduce_kernel, 1, 1024, 0, st, n, n_global, *cfg, ws.terms, losses);
   CIRS_CHECK_LAUNCH();
 
   // ---- backward through the actor head
   DlCore dl{ws.logits, ldA, ws.rowm, ws.rinvz, ws.coef, ws.rowG, ws.acta, cfg->ent_coef / (float)n_global};
   // dW3t[k][c] = sum_r h2[r][k] dl[r][c];  db3[c] = sum_r dl[r][c]      (M = 64, N = nA, K = n; split over rows)
   launch_gemm<64, 128, 16, 8>(ColMajorA{ws.h2, HID, nullptr}, DlB{dl}, AtomicEp{grads->w3t, ldA}, HID, nA, n,
-                              split_for((nA + 127) / 128, n, 16), grads->b3, st);
+                              split_for((nA + 127) / 128, n, 16), grads->b3, st, "head_dW3_gemm");
   CIRS_CHECK_LAUNCH();
   // dh2[r][k] = sum_c dl[r][c] W3t[k][c]                                  (M = n, N = 64, K = nA; split over columns)
   cudaMemsetAsync(ws.dh2, 0, sizeof(float) * (size_t)n * HID, st);
   launch_gemm<64, 64, 16, 4>(DlA{dl}, ColMajorB{w->w3t, ldA}, AtomicEp{ws.dh2, HID}, n, HID, nA,
-                             split_for((n + 63) / 64, nA, 16), nullptr, st);
+                             split_for((n + 63) / 64, nA, 16), nullptr, st, "head_dh2_gemm");
   CIRS_CHECK_LAUNCH();
   // ---- critic head + trunk
-  critic_grad_kernel<<<1, 256, 0, st>>>(n, ws.dv, ws.h2, grads->wv, grads->bv);
+  CIRS_LAUNCH(critic_grad_kernel, 1, 256, 0, st, n, ws.dv, ws.h2, grads->wv, grads->bv);
   CIRS_CHECK_LAUNCH();
-  dz2_kernel<<<(n * HID + 255) / 256, 256, 0, st>>>(n, ws.dh2, ws.dv, w->wv, ws.h2, ws.dz2);
+  CIRS_LAUNCH(dz2_kernel, (n * HID + 255) / 256, 256, 0, st, n, ws.dh2, ws.dv, w->wv, ws.h2, ws.dz2);
   CIRS_CHECK_LAUNCH();
   // dW2t[k][c] = sum_r h1[r][k] dz2[r][c], db2
   launch_gemm<64, 64, 16, 4>(ColMajorA{ws.h1, HID, nullptr}, RowMajorB{ws.dz2, HID, nullptr},
-                             AtomicEp{grads->w2t, HID}, HID, HID, n, split_for(1, n, 16), grads->b2, st);
+                             AtomicEp{grads->w2t, HID}, HID, HID, n, split_for(1, n, 16), grads->b2, st, "trunk_dW2_gemm");
   CIRS_CHECK_LAUNCH();
   // dz1[r][k] = (sum_c dz2[r][c] W2t[k][c]) * [h1 > 0]
   launch_gemm<64, 64, 16, 4>(RowMajorA{ws.dz2, HID, nullptr}, ColMajorB{w->w2t, HID},
-                             StoreEp{ws.dz1, HID, nullptr, 0, nullptr, ws.h1, HID}, n, HID, HID, 1, nullptr, st);
+                             StoreEp{ws.dz1, HID, nullptr, 0, nullptr, ws.h1, HID}, n, HID, HID, 1, nullptr, st, "trunk_dz1_gemm");
   CIRS_CHECK_LAUNCH();
   // dW1t[s][c] = sum_r obs[idx[r]][s] dz1[r][c], db1
   launch_gemm<64, 64, 16, 4>(ColMajorA{obs, S, idx}, RowMajorB{ws.dz1, HID, nullptr}, AtomicEp{grads->w1t, HID}, S,
-                             HID, n, split_for(1, n, 16), grads->b1, st);
+                             HID, n, split_for(1, n, 16), grads->b1, st, "trunk_dW1_gemm");
   CIRS_CHECK_LAUNCH();
   // d_obs[idx[r]][s] = sum_c dz1[r][c] W1t[s][c]
   if (d_obs) {
     launch_gemm<64, 64, 16, 4>(RowMajorA{ws.dz1, HID, nullptr}, ColMajorB{w->w1t, HID},
-                               StoreEp{d_obs, S, nullptr, 0, idx, nullptr, 0}, n, S, HID, 1, nullptr, st);
+                               StoreEp{d_obs, S, nullptr, 0, idx, nullptr, 0}, n, S, HID, 1, nullptr, st, "trunk_dobs_gemm");
     CIRS_CHECK_LAUNCH();
   }
   return CIRS_OK;

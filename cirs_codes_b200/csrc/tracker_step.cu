@@ -221,7 +221,7 @@ extern "C" int cirs_tracker_step(const cirs_tracker_weights* w, int32_t n_env, i
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(tracker_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = (n_rows + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  tracker_step_kernel<<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(
+  CIRS_LAUNCH(tracker_step_kernel, grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream, 
       *w, n_env, n_rows, env_id, active, pos, expect_pos, idx, dense, rew, kcache, vcache, state_out,
       state_stride, cur_state, traj_len, traj_obs, traj_obs_next, per_warp);
   CIRS_CHECK_LAUNCH();

@@ -1,10 +1,486 @@
-// K6 placeholder (replaced by the real training pass in the next commit).
-#include "common.cuh"
+// K6: training pass of the StateTracker -- one full-sequence causal forward over every environment's token
+// sequence and the backward pass, given d loss / d obs for every stored observation.
+//
+// Replaces autograd through the observations held in the replay buffer (core/policy/ppo.py:215
+// loss.backward(retain_graph=True) reaching core/state_tracker.py:170-250 through tianshou/data/batch.py:256-258).
+// The reference re-encodes the whole prefix at every step, so its graph holds T separate encoder passes per
+// environment; because the mask is causal, position p of ONE pass over the full sequence equals the last
+// position of the prefix-p pass, and the gradient of sum_p <d_obs[p], s_p> is the same.
+//
+// Layout: token (e, p) lives in row e*L + p -- the replay buffer's slot index -- of every [M, .] activation
+// matrix (M = n_env * L).  Rows with p >= ep_len[e] are padding: their token is zero, nothing valid attends to
+// them (causality) and their upstream gradient is zero, so they contribute nothing.
+// Linear layers, their input gradients and their weight gradients run on the FP32 tile GEMM (gemm.cuh); attention,
+// LayerNorm, the reward gate and the embedding scatter are small dedicated kernels.  All reductions that feed a
+// parameter gradient use float atomics at CTA granularity (order-dependent in the last bits only).
+#include "gemm.cuh"
 #include "../../include/cirs_b200.h"
-extern "C" int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights*, int32_t, int32_t) { return 256; }
-extern "C" int cirs_tracker_train(const cirs_tracker_weights*, const cirs_tracker_weights*, int32_t, int32_t,
-                                  const int32_t*, const int32_t*, const float*, const int32_t*, const float*,
-                                  const float*, const float*, float*, void*, int64_t, void*) {
-  cirs_set_error("cirs_tracker_train: not built yet");
-  return CIRS_ERR_ARG;
+
+namespace {
+using namespace cirs;
+
+__host__ __device__ inline int64_t al(int64_t x) { return (x + 63) & ~(int64_t)63; }
+inline int up32(int v) { return (v + 31) & ~31; }
+
+struct LayerBufs {
+  float *qkv, *o, *r1, *st1, *x1, *h, *r2, *st2, *x2;
+};
+struct Bufs {
+  float *u, *in, *g, *x0, *tok0, *da, *db, *dqkv, *dh, *dtmp, *din, *du, *dtok0;
+  LayerBufs layer[CIRS_MAX_LAYERS];
+  int64_t total;
+};
+
+Bufs carve(float* base, int64_t B, int64_t M, int d, int dhid, int nl, int d_user_in) {
+  Bufs b;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { float* r = base ? base + off : nullptr; off += al(n); return r; };
+  b.u = take(B * d_user_in); b.in = take(M * (1 + d)); b.g = take(M * d); b.x0 = take(M * d); b.tok0 = take(B * d);
+  b.da = take(M * d); b.db = take(M * d); b.dqkv = take(M * 3 * d); b.dh = take(M * dhid); b.dtmp = take(M * d);
+  b.din = take(M * (1 + d)); b.du = take(B * d_user_in); b.dtok0 = take(B * d);
+  for (int l = 0; l < nl; ++l) {
+    LayerBufs& y = b.layer[l];
+    y.qkv = take(M * 3 * d); y.o = take(M * d); y.r1 = take(M * d); y.st1 = take(M * 2); y.x1 = take(M * d);
+    y.h = take(M * dhid); y.r2 = take(M * d); y.st2 = take(M * 2); y.x2 = take(M * d);
+  }
+  b.total = off;
+  return b;
+}
+
+// ---- gather the token inputs: U[e] = user embedding / dense user;  IN[row] = [rew ; item embedding] for p >= 1
+__global__ void gather_inputs_kernel(cirs_tracker_weights W, int B, int L, const int32_t* __restrict__ users,
+                                     const int32_t* __restrict__ act, const float* __restrict__ rew,
+                                     const int32_t* __restrict__ ep_len, const float* __restrict__ dense_user,
+                                     const float* __restrict__ dense_item, float* __restrict__ U,
+                                     float* __restrict__ IN) {
+  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d, tid = threadIdx.x;
+  const int n = ep_len[e];
+  if (p == 0) {
+    const int du = W.d_user_in;
+    const float* src = W.emb_user ? W.emb_user + (size_t)users[e] * d : dense_user + (size_t)e * du;
+    for (int c = tid; c < du; c += blockDim.x) U[(size_t)e * du + c] = src[c];
+  }
+  float* out = IN + (size_t)row * (1 + d);
+  if (p >= 1 && p < n) {
+    const size_t prev = (size_t)e * L + p - 1;
+    const float* src = W.emb_item ? W.emb_item + (size_t)act[prev] * d : dense_item + prev * d;
+    if (tid == 0) out[0] = rew[prev];
+    for (int c = tid; c < d; c += blockDim.x) out[1 + c] = src[c];
+  } else {
+    for (int c = tid; c < 1 + d; c += blockDim.x) out[c] = 0.f;
+  }
+}
+
+// ---- tokens: x0 = sqrt(d) * tok + PE[p];  tok = ffn_user(u) at p = 0, sigmoid(Z) * a afterwards (Z -> G in place)
+__global__ void token_fwd_kernel(cirs_tracker_weights W, int L, const int32_t* __restrict__ ep_len,
+                                 const float* __restrict__ IN, const float* __restrict__ tok0, float* __restrict__ G,
+                                 float* __restrict__ X0) {
+  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d;
+  const bool valid = p < ep_len[e];
+  const float sq = sqrtf((float)d);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const size_t i = (size_t)row * d + c;
+    const float pe = p < W.max_len ? W.pe[(size_t)p * d + c] : 0.f;  // rows beyond max_len are always padding
+    float tok = 0.f, g = 0.f;
+    if (valid) {
+      if (p == 0) tok = tok0[(size_t)e * d + c];
+      else {
+        g = 1.f / (1.f + expf(-G[i]));
+        tok = g * IN[(size_t)row * (1 + d) + 1 + c];
+      }
+    }
+    G[i] = g;
+    X0[i] = tok * sq + pe;
+  }
+}
+
+// d tok = sqrt(d) * dX0;  p = 0 -> dTOK0[e];  p >= 1 -> dZ = dtok * a * g (1 - g),  DA = dtok * g
+__global__ void token_bwd_kernel(cirs_tracker_weights W, int L, const int32_t* __restrict__ ep_len,
+                                 const float* __restrict__ IN, const float* __restrict__ G,
+                                 const float* __restrict__ dX0, float* __restrict__ dTOK0, float* __restrict__ dZ,
+                                 float* __restrict__ DA) {
+  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d;
+  const bool valid = p < ep_len[e];
+  const float sq = sqrtf((float)d);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const size_t i = (size_t)row * d + c;
+    const float dt = valid ? dX0[i] * sq : 0.f;
+    float dz = 0.f, da = 0.f;
+    if (p == 0) dTOK0[(size_t)e * d + c] = dt;
+    else if (valid) {
+      const float g = G[i], a = IN[(size_t)row * (1 + d) + 1 + c];
+      dz = dt * a * g * (1.f - g);
+      da = dt * g;
+    }
+    dZ[i] = dz;
+    DA[i] = da;
+  }
+}
+
+// embedding gradients (dense nn.Embedding grads, scatter-add)
+__global__ void emb_scatter_kernel(cirs_tracker_weights W, cirs_tracker_weights Gr, int B, int L,
+                                   const int32_t* __restrict__ users, const int32_t* __restrict__ act,
+                                   const int32_t* __restrict__ ep_len, const float* __restrict__ dIN,
+                                   const float* __restrict__ DA, const float* __restrict__ dU) {
+  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d;
+  if (p == 0) {
+    if (Gr.emb_user)
+      for (int c = threadIdx.x; c < d; c += blockDim.x)
+        atomicAdd(Gr.emb_user + (size_t)users[e] * d + c, dU[(size_t)e * d + c]);
+  } else if (p < ep_len[e] && Gr.emb_item) {
+    const int item = act[(size_t)e * L + p - 1];
+    for (int c = threadIdx.x; c < d; c += blockDim.x)
+      atomicAdd(Gr.emb_item + (size_t)item * d + c, dIN[(size_t)row * (1 + d) + 1 + c] + DA[(size_t)row * d + c]);
+  }
+}
+
+// ---- LayerNorm (eps 1e-5, biased variance): one warp per row
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(int M, int d, const float* __restrict__ R, const float* __restrict__ w, const float* __restrict__ b,
+              float* __restrict__ X, float* __restrict__ ST) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* r = R + (size_t)row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s += r[c];
+  const float mu = warp_sum(s) / d;
+  float q = 0.f;
+  for (int c = lane; c < d; c += 32) { const float v = r[c] - mu; q += v * v; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / d + 1e-5f);
+  for (int c = lane; c < d; c += 32) X[(size_t)row * d + c] = (r[c] - mu) * rstd * __ldg(w + c) + __ldg(b + c);
+  if (lane == 0) { ST[2 * row] = mu; ST[2 * row + 1] = rstd; }
+}
+
+// dR = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), dxhat = dY * w;  gw += dY * xhat, gb += dY
+constexpr int LN_MAXC = 8;  // d <= 256
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(int M, int d, const float* __restrict__ dY, const float* __restrict__ R, const float* __restrict__ ST,
+              const float* __restrict__ w, float* __restrict__ dR, float* gw, float* gb) {
+  __shared__ float sw[8][256], sb[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float aw[LN_MAXC], ab[LN_MAXC];
+#pragma unroll
+  for (int k = 0; k < LN_MAXC; ++k) aw[k] = ab[k] = 0.f;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const float mu = ST[2 * row], rstd = ST[2 * row + 1];
+    const float* r = R + (size_t)row * d;
+    const float* dy = dY + (size_t)row * d;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < d) {
+        const float xh = (r[c] - mu) * rstd, dyc = dy[c], dxh = dyc * __ldg(w + c);
+        s1 += dxh; s2 += dxh * xh;
+        aw[k] += dyc * xh; ab[k] += dyc;
+      }
+    }
+    s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int k = 0; k < LN_MAXC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < d) {
+        const float xh = (r[c] - mu) * rstd, dxh = dy[c] * __ldg(w + c);
+        dR[(size_t)row * d + c] = rstd * (dxh - s1 - xh * s2);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LN_MAXC; ++k) { sw[warp][lane + 32 * k] = aw[k]; sb[warp][lane + 32 * k] = ab[k]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += 256) {
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < 8; ++k) { a += sw[k][c]; b += sb[k][c]; }
+    atomicAdd(gw + c, a);
+    atomicAdd(gb + c, b);
+  }
+}
+
+// ---- causal multi-head self-attention, one CTA per (environment, head)
+struct AttnSmem {
+  float *q, *k, *v, *dO, *mx, *iz, *dd, *pw, *sw;
+};
+__device__ __forceinline__ AttnSmem attn_carve(float* s, int Lmax, int dh, int nwarp) {
+  AttnSmem a;
+  const int ld = dh + 1;
+  a.q = s; a.k = a.q + Lmax * ld; a.v = a.k + Lmax * ld; a.dO = a.v + Lmax * ld;
+  a.mx = a.dO + Lmax * ld; a.iz = a.mx + Lmax; a.dd = a.iz + Lmax;
+  a.pw = a.dd + Lmax; a.sw = a.pw + nwarp * Lmax;
+  return a;
+}
+inline size_t attn_smem_bytes(int Lmax, int dh, int nwarp) {
+  return sizeof(float) * ((size_t)4 * Lmax * (dh + 1) + 3 * Lmax + 2 * nwarp * Lmax);
+}
+constexpr int ATT_WARPS = 4;
+
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_fwd_kernel(int L, int d, int nhead, const int32_t* __restrict__ ep_len, const float* __restrict__ QKV,
+                float* __restrict__ O) {
+  extern __shared__ float sm[];
+  const int e = blockIdx.x, h = blockIdx.y, dh = d / nhead, ld = dh + 1;
+  const int n = min(ep_len[e], L), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  AttnSmem S = attn_carve(sm, L, dh, ATT_WARPS);
+  for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+    const int p = i / dh, c = i % dh;
+    const float* src = QKV + ((size_t)e * L + p) * 3 * d + h * dh + c;
+    S.q[p * ld + c] = src[0]; S.k[p * ld + c] = src[d]; S.v[p * ld + c] = src[2 * d];
+  }
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)dh);
+  float* pw = S.pw + warp * L;
+  for (int i = warp; i < L; i += ATT_WARPS) {
+    float* out = O + ((size_t)e * L + i) * d + h * dh;
+    if (i >= n) {
+      for (int c = lane; c < dh; c += 32) out[c] = 0.f;
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j <= i; j += 32) {
+      float s = 0.f;
+      for (int c = 0; c < dh; ++c) s = fmaf(S.q[i * ld + c] * scale, S.k[j * ld + c], s);
+      pw[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j <= i; j += 32) { const float ex = expf(pw[j] - mx); pw[j] = ex; z += ex; }
+    z = warp_sum(z);
+    __syncwarp();
+    const float inv = 1.0f / z;
+    for (int c = lane; c < dh; c += 32) {
+      float a = 0.f;
+      for (int j = 0; j <= i; ++j) a = fmaf(pw[j] * inv, S.v[j * ld + c], a);
+      out[c] = a;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_bwd_kernel(int L, int d, int nhead, const int32_t* __restrict__ ep_len, const float* __restrict__ QKV,
+                const float* __restrict__ dOg, float* __restrict__ dQKV) {
+  extern __shared__ float sm[];
+  const int e = blockIdx.x, h = blockIdx.y, dh = d / nhead, ld = dh + 1;
+  const int n = min(ep_len[e], L), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  AttnSmem S = attn_carve(sm, L, dh, ATT_WARPS);
+  for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+    const int p = i / dh, c = i % dh;
+    const size_t row = (size_t)e * L + p;
+    const float* src = QKV + row * 3 * d + h * dh + c;
+    S.q[p * ld + c] = src[0]; S.k[p * ld + c] = src[d]; S.v[p * ld + c] = src[2 * d];
+    S.dO[p * ld + c] = dOg[row * d + h * dh + c];
+  }
+  // padding rows: zero gradient
+  for (int i = threadIdx.x; i < (L - n) * dh; i += blockDim.x) {
+    const int p = n + i / dh, c = i % dh;
+    float* dst = dQKV + ((size_t)e * L + p) * 3 * d + h * dh + c;
+    dst[0] = 0.f; dst[d] = 0.f; dst[2 * d] = 0.f;
+  }
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)dh);
+  float* pw = S.pw + warp * L;
+  float* sw = S.sw + warp * L;
+  // phase 1: per query i -- row statistics, D_i = sum_j p_ij dP_ij, dq_i
+  for (int i = warp; i < n; i += ATT_WARPS) {
+    float mx = -INFINITY;
+    for (int j = lane; j <= i; j += 32) {
+      float s = 0.f;
+      for (int c = 0; c < dh; ++c) s = fmaf(S.q[i * ld + c] * scale, S.k[j * ld + c], s);
+      pw[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j <= i; j += 32) { const float ex = expf(pw[j] - mx); pw[j] = ex; z += ex; }
+    z = warp_sum(z);
+    const float inv = 1.0f / z;
+    float dsum = 0.f;
+    for (int j = lane; j <= i; j += 32) {
+      float dp = 0.f;
+      for (int c = 0; c < dh; ++c) dp = fmaf(S.dO[i * ld + c], S.v[j * ld + c], dp);
+      const float p = pw[j] * inv;
+      pw[j] = p;
+      sw[j] = dp;
+      dsum = fmaf(p, dp, dsum);
+    }
+    dsum = warp_sum(dsum);
+    for (int j = lane; j <= i; j += 32) sw[j] = pw[j] * (sw[j] - dsum);   // dS_ij
+    if (lane == 0) { S.mx[i] = mx; S.iz[i] = inv; S.dd[i] = dsum; }
+    __syncwarp();
+    float* dq = dQKV + ((size_t)e * L + i) * 3 * d + h * dh;
+    for (int c = lane; c < dh; c += 32) {
+      float a = 0.f;
+      for (int j = 0; j <= i; ++j) a = fmaf(sw[j], S.k[j * ld + c], a);
+      dq[c] = a * scale;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // phase 2: per key j -- dk_j = scale * sum_{i>=j} dS_ij q_i,  dv_j = sum_{i>=j} p_ij dO_i
+  for (int j = warp; j < n; j += ATT_WARPS) {
+    for (int i = j + lane; i < n; i += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int c = 0; c < dh; ++c) {
+        s = fmaf(S.q[i * ld + c] * scale, S.k[j * ld + c], s);
+        dp = fmaf(S.dO[i * ld + c], S.v[j * ld + c], dp);
+      }
+      const float p = expf(s - S.mx[i]) * S.iz[i];
+      pw[i] = p;
+      sw[i] = p * (dp - S.dd[i]);
+    }
+    __syncwarp();
+    float* dk = dQKV + ((size_t)e * L + j) * 3 * d + d + h * dh;
+    for (int c = lane; c < dh; c += 32) {
+      float ak = 0.f, av = 0.f;
+      for (int i = j; i < n; ++i) {
+        ak = fmaf(sw[i], S.q[i * ld + c], ak);
+        av = fmaf(pw[i], S.dO[i * ld + c], av);
+      }
+      dk[c] = ak * scale;
+      dk[d + c] = av;
+    }
+    __syncwarp();
+  }
+}
+
+int splitk(int tiles, int K) {
+  int s = (2 * 148 + tiles - 1) / tiles;
+  const int max_s = (K + 63) / 64;
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
+// Y[M,N] = X[M,K] Wt[K][ldw] + b (+ relu) (+ res)
+void linear_fwd(const float* X, int ldx, const float* Wt, int ldw, const float* b, float* Y, int ldy, int M, int N,
+                int K, int relu, const float* res, int ldr, cudaStream_t st) {
+  launch_gemm<64, 64, 16, 4>(RowMajorA{X, ldx, nullptr}, RowMajorB{Wt, ldw, nullptr},
+                             StoreEp{Y, ldy, b, relu, nullptr, nullptr, 0, res, ldr}, M, N, K, 1, nullptr, st, "tracker_linear_fwd_gemm");
+}
+// dX[M,K] = dY[M,N] Wt^T (* mask) (+ res)
+void linear_bwd_x(const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int N, int K,
+                  const float* mask, int ldm, const float* res, int ldr, cudaStream_t st) {
+  launch_gemm<64, 64, 16, 4>(RowMajorA{dY, ldy, nullptr}, ColMajorB{Wt, ldw},
+                             StoreEp{dX, ldx, nullptr, 0, nullptr, mask, ldm, res, ldr}, M, K, N, 1, nullptr, st, "tracker_linear_dx_gemm");
+}
+// gWt[K][ldw] += X^T dY,  gb[N] += colsum(dY)
+void linear_bwd_w(const float* X, int ldx, const float* dY, int ldy, float* gWt, int ldw, float* gb, int M, int N,
+                  int K, cudaStream_t st) {
+  const int tiles = ((K + 63) / 64) * ((N + 63) / 64);
+  launch_gemm<64, 64, 16, 4>(ColMajorA{X, ldx, nullptr}, RowMajorB{dY, ldy, nullptr}, AtomicEp{gWt, ldw}, K, N, M,
+                             splitk(tiles, M), gb, st, "tracker_linear_dw_gemm");
+}
+
+}  // namespace
+
+extern "C" int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_t n_env,
+                                                      int32_t traj_len) {
+  if (!w) return 0;
+  const Bufs b = carve(nullptr, n_env, (int64_t)n_env * traj_len, w->d, w->d_hid, w->nlayers, w->d_user_in);
+  return b.total * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights* grads, int32_t n_env,
+                                  int32_t traj_len, const int32_t* users, const int32_t* traj_act,
+                                  const float* traj_rew, const int32_t* ep_len, const float* dense_user,
+                                  const float* dense_item, const float* d_obs, float* obs_check, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  if (!w || !grads || !traj_rew || !ep_len || !workspace || n_env < 0 || traj_len < 1) {
+    cirs_set_error("cirs_tracker_train: null argument");
+    return CIRS_ERR_ARG;
+  }
+  if ((w->emb_user && !users) || (!w->emb_user && !dense_user) || (w->emb_item && !traj_act) ||
+      (!w->emb_item && !dense_item)) {
+    cirs_set_error("cirs_tracker_train: token inputs missing (ids for embedding tables, dense features otherwise)");
+    return CIRS_ERR_ARG;
+  }
+  if (w->d % w->nhead != 0 || w->d > 32 * LN_MAXC || w->nlayers > CIRS_MAX_LAYERS || w->d_item_in != w->d ||
+      (w->emb_user && w->d_user_in != w->d)) {
+    cirs_set_error("cirs_tracker_train: unsupported shape");
+    return CIRS_ERR_ARG;
+  }
+  if (cirs_tracker_train_workspace_bytes(w, n_env, traj_len) > workspace_bytes) {
+    cirs_set_error("cirs_tracker_train: workspace too small");
+    return CIRS_ERR_ARG;
+  }
+  if (n_env == 0) return CIRS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = n_env, L = traj_len, M = B * L, d = w->d, dhid = w->d_hid, S = w->dim_state, nl = w->nlayers;
+  const int ldd = up32(d), ld3 = up32(3 * d), ldh = up32(dhid), lds = up32(S), dui = w->d_user_in;
+  const int nh = w->nhead, dh = d / nh;
+  Bufs b = carve(reinterpret_cast<float*>(workspace), B, M, d, dhid, nl, dui);
+  const size_t att_smem = attn_smem_bytes(L, dh, ATT_WARPS);
+  if (att_smem > 200 * 1024) {
+    cirs_set_error("cirs_tracker_train: sequence too long for the attention kernel's shared memory");
+    return CIRS_ERR_ARG;
+  }
+  if (att_smem > 48 * 1024) {
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem);
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem);
+  }
+  const cirs_tracker_weights& W = *w;
+  const cirs_tracker_weights& G = *grads;
+
+  // ================= forward
+  CIRS_LAUNCH(gather_inputs_kernel, M, 64, 0, st, W, B, L, users, traj_act, traj_rew, ep_len, dense_user, dense_item, b.u, b.in);
+  CIRS_CHECK_LAUNCH();
+  linear_fwd(b.u, dui, W.user_wt, ldd, W.user_b, b.tok0, d, B, d, dui, 0, nullptr, 0, st);           // ffn_user
+  linear_fwd(b.in, 1 + d, W.gate_wt, ldd, W.gate_b, b.g, d, M, d, 1 + d, 0, nullptr, 0, st);          // fnn_gate (pre-act)
+  CIRS_LAUNCH(token_fwd_kernel, M, 64, 0, st, W, L, ep_len, b.in, b.tok0, b.g, b.x0);
+  CIRS_CHECK_LAUNCH();
+  const float* x = b.x0;
+  for (int l = 0; l < nl; ++l) {
+    const cirs_encoder_layer& Y = W.layer[l];
+    LayerBufs& y = b.layer[l];
+    linear_fwd(x, d, Y.in_wt, ld3, Y.in_b, y.qkv, 3 * d, M, 3 * d, d, 0, nullptr, 0, st);
+    CIRS_LAUNCH(attn_fwd_kernel, dim3(B, nh), ATT_WARPS * 32, att_smem, st, L, d, nh, ep_len, y.qkv, y.o);
+    CIRS_CHECK_LAUNCH();
+    linear_fwd(y.o, d, Y.out_wt, ldd, Y.out_b, y.r1, d, M, d, d, 0, x, d, st);                         // r1 = x + attn
+    CIRS_LAUNCH(ln_fwd_kernel, (M + 7) / 8, 256, 0, st, M, d, y.r1, Y.n1_w, Y.n1_b, y.x1, y.st1);
+    CIRS_CHECK_LAUNCH();
+    linear_fwd(y.x1, d, Y.l1_wt, ldh, Y.l1_b, y.h, dhid, M, dhid, d, 1, nullptr, 0, st);
+    linear_fwd(y.h, dhid, Y.l2_wt, ldd, Y.l2_b, y.r2, d, M, d, dhid, 0, y.x1, d, st);                  // r2 = x1 + ffn
+    CIRS_LAUNCH(ln_fwd_kernel, (M + 7) / 8, 256, 0, st, M, d, y.r2, Y.n2_w, Y.n2_b, y.x2, y.st2);
+    CIRS_CHECK_LAUNCH();
+    x = y.x2;
+  }
+  if (obs_check) linear_fwd(x, d, W.dec_wt, lds, W.dec_b, obs_check, S, M, S, d, 0, nullptr, 0, st);
+  CIRS_CHECK_LAUNCH();
+  if (!d_obs) return CIRS_OK;
+
+  // ================= backward
+  const int ln_grid = min((M + 7) / 8, 148 * 4);
+  linear_bwd_w(x, d, d_obs, S, G.dec_wt, lds, G.dec_b, M, S, d, st);
+  linear_bwd_x(d_obs, S, W.dec_wt, lds, b.da, d, M, S, d, nullptr, 0, nullptr, 0, st);                 // da = dX_last
+  for (int l = nl - 1; l >= 0; --l) {
+    const cirs_encoder_layer& Y = W.layer[l];
+    const cirs_encoder_layer& Gy = G.layer[l];
+    LayerBufs& y = b.layer[l];
+    const float* xin = l == 0 ? b.x0 : b.layer[l - 1].x2;
+    CIRS_LAUNCH(ln_bwd_kernel, ln_grid, 256, 0, st, M, d, b.da, y.r2, y.st2, Y.n2_w, b.db, Gy.n2_w, Gy.n2_b);  // db = dR2
+    CIRS_CHECK_LAUNCH();
+    linear_bwd_w(y.h, dhid, b.db, d, Gy.l2_wt, ldd, Gy.l2_b, M, d, dhid, st);
+    linear_bwd_x(b.db, d, Y.l2_wt, ldd, b.dh, dhid, M, d, dhid, y.h, dhid, nullptr, 0, st);            // dh (relu mask)
+    linear_bwd_w(y.x1, d, b.dh, dhid, Gy.l1_wt, ldh, Gy.l1_b, M, dhid, d, st);
+    linear_bwd_x(b.dh, dhid, Y.l1_wt, ldh, b.da, d, M, dhid, d, nullptr, 0, b.db, d, st);              // da = dX1
+    CIRS_LAUNCH(ln_bwd_kernel, ln_grid, 256, 0, st, M, d, b.da, y.r1, y.st1, Y.n1_w, b.db, Gy.n1_w, Gy.n1_b);  // db = dR1
+    CIRS_CHECK_LAUNCH();
+    linear_bwd_w(y.o, d, b.db, d, Gy.out_wt, ldd, Gy.out_b, M, d, d, st);
+    linear_bwd_x(b.db, d, Y.out_wt, ldd, b.dtmp, d, M, d, d, nullptr, 0, nullptr, 0, st);              // dtmp = dO
+    CIRS_LAUNCH(attn_bwd_kernel, dim3(B, nh), ATT_WARPS * 32, att_smem, st, L, d, nh, ep_len, y.qkv, b.dtmp, b.dqkv);
+    CIRS_CHECK_LAUNCH();
+    linear_bwd_w(xin, d, b.dqkv, 3 * d, Gy.in_wt, ld3, Gy.in_b, M, 3 * d, d, st);
+    linear_bwd_x(b.dqkv, 3 * d, Y.in_wt, ld3, b.da, d, M, 3 * d, d, nullptr, 0, b.db, d, st);          // da = dX_in
+  }
+  // tokens: dZ -> dtmp, direct item gradient -> db
+  CIRS_LAUNCH(token_bwd_kernel, M, 64, 0, st, W, L, ep_len, b.in, b.g, b.da, b.dtok0, b.dtmp, b.db);
+  CIRS_CHECK_LAUNCH();
+  linear_bwd_w(b.in, 1 + d, b.dtmp, d, G.gate_wt, ldd, G.gate_b, M, d, 1 + d, st);
+  linear_bwd_w(b.u, dui, b.dtok0, d, G.user_wt, ldd, G.user_b, B, d, dui, st);
+  if (G.emb_item || G.emb_user) {
+    linear_bwd_x(b.dtmp, d, W.gate_wt, ldd, b.din, 1 + d, M, d, 1 + d, nullptr, 0, nullptr, 0, st);
+    linear_bwd_x(b.dtok0, d, W.user_wt, ldd, b.du, dui, B, d, dui, nullptr, 0, nullptr, 0, st);
+    CIRS_LAUNCH(emb_scatter_kernel, M, 64, 0, st, W, G, B, L, users, traj_act, ep_len, b.din, b.db, b.du);
+  }
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
 }

@@ -34,6 +34,11 @@ def split_indices(n, size, perm):
     return out
 
 
+def split_sizes(n, size):
+    """Chunk sizes of split_indices (they depend on n and size only)."""
+    return [len(c) for c in split_indices(n, size, np.arange(n))]
+
+
 class RunningMeanStd:
     """Host view of the device-resident return statistics (tianshou/utils/statistics.py:66-95)."""
 
@@ -51,7 +56,7 @@ class PPOPolicy:
                  max_grad_norm=None, gae_lambda=0.95, max_batchsize=256, discount_factor=0.99,
                  reward_normalization=False, action_scaling=True, action_bound_method="clip", action_space=None,
                  lr_scheduler=None, deterministic_eval=False, state_tracker=None, device="cuda", seed=0,
-                 process_group=None, **kwargs):
+                 process_group=None, perm_on_device=False, **kwargs):
         _lib.require_cuda()
         _lib.load()
         assert dual_clip is None, "dual_clip is not used by CIRS (CIRS-RL-kuaishou.py:277-279)"
@@ -72,6 +77,8 @@ class PPOPolicy:
         self.action_space = action_space
         self.seed, self._calls = int(seed), 0
         self.group = process_group
+        self.perm_on_device = bool(perm_on_device)   # minibatch permutations from torch.randperm on the device
+        self.h2d_bytes = self.d2h_bytes = 0          # host<->device traffic of the last update()
 
         dim_state = actor.preprocess.input_dim
         n_action = actor.output_dim
@@ -259,6 +266,7 @@ class PPOPolicy:
         buffer.sync_device()
         idx_h = buffer.sample_index(0)
         indices = torch.as_tensor(idx_h.astype(np.int32), device=self.device)
+        self.h2d_bytes, self.d2h_bytes = indices.numel() * 4, 0
         self.process_fn(buffer, indices)
         result = self.learn(buffer, idx_h, indices, batch_size or len(idx_h), repeat, perms=perms)
         self.updating = False
@@ -269,15 +277,22 @@ class PPOPolicy:
         n, dev, st = len(idx_h), self.device, _lib.stream()
         dist, world = self._world()
         tracker = self.state_tracker if self.cfg_tracker is not None else None
-        chunks_per_repeat, losses_all = [], []
+        losses_all = []
+        from .parallel import sharded_sizes
+        sizes = sharded_sizes(n, batch_size, dist if world > 1 else None, self.group, dev)
+        offs = np.zeros(len(sizes) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum(sizes)
+        d_offs = torch.as_tensor(offs, device=dev)
+        chunks = sizes
         for step in range(repeat):
-            perm = np.asarray(perms[step]) if perms is not None else np.random.permutation(n)   # batch.py:736
-            chunks = split_indices(n, batch_size, perm)
-            chunks_per_repeat.append(chunks)
-            offs = np.zeros(len(chunks) + 1, dtype=np.int32)
-            offs[1:] = np.cumsum([len(c) for c in chunks])
-            d_slots = torch.as_tensor(idx_h[np.concatenate(chunks)].astype(np.int32), device=dev)
-            d_offs = torch.as_tensor(offs, device=dev)
+            if perms is not None:
+                d_slots = torch.as_tensor(idx_h[np.asarray(perms[step])].astype(np.int32), device=dev)
+                self.h2d_bytes += 4 * n
+            elif self.perm_on_device:
+                d_slots = indices[torch.randperm(n, device=dev)]
+            else:
+                d_slots = torch.as_tensor(idx_h[np.random.permutation(n)].astype(np.int32), device=dev)  # batch.py:736
+                self.h2d_bytes += 4 * n
             stats = torch.zeros(len(chunks), 3, dtype=torch.float64, device=dev)
             _lib.call("cirs_adv_stats", len(chunks), _lib.ptr(d_offs), _lib.ptr(d_slots), _lib.ptr(self.adv),
                       _lib.ptr(stats), st)
@@ -307,5 +322,6 @@ class PPOPolicy:
         losses = torch.cat(losses_all)
         self._allreduce(losses)
         lh = losses.cpu().numpy().astype(np.float64)                                 # the update's only D2H read
+        self.d2h_bytes += losses.numel() * 4
         return {"loss": lh[:, 0].tolist(), "loss/clip": lh[:, 1].tolist(), "loss/vf": lh[:, 2].tolist(),
                 "loss/ent": lh[:, 3].tolist()}

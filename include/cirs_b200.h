@@ -31,6 +31,12 @@ extern "C" {
 
 const char* cirs_last_error(void);
 int cirs_abi_version(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py reports it as gpu_launches) */
+int64_t cirs_launch_count(void);
+/* Optional per-kernel timing: while enabled every launch is bracketed by CUDA events on its own stream.
+ * cirs_profile_report synchronises the device and writes "kernel_name count total_ms" lines into buf. */
+void cirs_profile_enable(int on);
+int cirs_profile_report(char* buf, int n);
 
 /* ------------------------------------------------------------------ KuaishouEnv / SimulatedEnv ---------- */
 typedef struct {

@@ -151,10 +151,13 @@ def _returns(v_s, v_next, rew, done, lens, L, gamma, lam, rms=None):
     ret, adv = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
     scratch = torch.zeros(2 * B, dtype=torch.float64, device="cuda")
     mom = torch.zeros(3, dtype=torch.float64, device="cuda")
-    _lib.call("cirs_compute_returns", B, L, _lib.ptr(_dev(lens, torch.int32)), _lib.ptr(_dev(v_s, torch.float32)),
-              _lib.ptr(_dev(v_next, torch.float32)), _lib.ptr(_dev(rew, torch.float32)),
-              _lib.ptr(_dev(done, torch.uint8)), gamma, lam, _lib.ptr(rms), _lib.ptr(scratch), _lib.ptr(mom),
+    # keep the device inputs alive until the call has been issued (a temporary would be freed and its block reused)
+    d_len, d_vs, d_vn = _dev(lens, torch.int32), _dev(v_s, torch.float32), _dev(v_next, torch.float32)
+    d_rew, d_done = _dev(rew, torch.float32), _dev(done, torch.uint8)
+    _lib.call("cirs_compute_returns", B, L, _lib.ptr(d_len), _lib.ptr(d_vs), _lib.ptr(d_vn), _lib.ptr(d_rew),
+              _lib.ptr(d_done), gamma, lam, _lib.ptr(rms), _lib.ptr(scratch), _lib.ptr(mom),
               _lib.ptr(ret), _lib.ptr(adv), _lib.stream())
+    torch.cuda.synchronize()
     if rms is not None:
         _lib.call("cirs_rms_update", _lib.ptr(rms), _lib.ptr(mom), _lib.stream())
     return ret.cpu().numpy(), adv.cpu().numpy()
