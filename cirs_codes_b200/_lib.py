@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcirs_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS = 4
 HIDDEN = 64
 
@@ -69,7 +69,7 @@ PROTOTYPES = {
     "cirs_tracker_train": (i32, [P(TrackerWeightsStruct), P(TrackerWeightsStruct), i32, i32, fp, fp, fp, fp, fp,
                                  fp, fp, fp, fp, i64, fp]),
     "cirs_actor_workspace_bytes": (i64, [i32, i32]),
-    "cirs_actor_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, i32, fp, fp, fp, fp,
+    "cirs_actor_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp, fp,
                                 fp, fp]),
     "cirs_policy_eval": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp, fp]),
     "cirs_compute_returns": (i32, [i32, i32, fp, fp, fp, fp, fp, f64, f64, fp, fp, fp, fp, fp, fp]),
@@ -78,6 +78,8 @@ PROTOTYPES = {
     "cirs_ppo_workspace_bytes": (i64, [i32, i32]),
     "cirs_ppo_minibatch": (i32, [P(PolicyWeightsStruct), P(PolicyWeightsStruct), P(PPOConfigStruct), i32, i32, fp,
                                  fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp]),
+    "cirs_ppo_learn": (i32, [P(PolicyWeightsStruct), P(PolicyWeightsStruct), fp, fp, P(PPOConfigStruct), i32, i32,
+                             fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp]),
     "cirs_clip_adam": (i32, [fp, fp, fp, fp, i64, i64, P(PPOConfigStruct), fp, fp, fp]),
 }
 

@@ -11,9 +11,11 @@ Two execution paths with identical results:
                (policy() -> env.step() -> preprocess_fn() -> buffer.add()); any duck-typed env / policy works;
   * fused    -- when env, tracker, policy and buffer are this package's device-resident objects and
                n_episode == env_num: per turn three kernel launches (actor sample -> env step -> tracker step)
-               on per-slot device arrays with an ``active`` mask; no host synchronisation inside the loop except
-               a non-blocking poll of "how many environments are still running"; trajectories are written by the
-               kernels straight into the replay buffer's env-major slots.
+               on per-slot device arrays with an ``active`` mask; trajectories are written by the kernels straight
+               into the replay buffer's env-major slots.  The whole rollout (reset, user token, max_turn turns) is
+               captured once into a CUDA graph and replayed with ONE launch per collect (the sampler's Philox
+               counter lives on the device); without graphs the host issues the turns and stops through a
+               non-blocking poll of "how many environments are still running".
 """
 import time
 
@@ -28,7 +30,7 @@ from .state_tracker import StateTrackerTransformer
 
 class Collector:
     def __init__(self, policy, env, buffer=None, preprocess_fn=None, exploration_noise=False,
-                 remove_recommended_ids=False, force_length=0, fused=True):
+                 remove_recommended_ids=False, force_length=0, fused=True, use_graph=True):
         self.policy, self.env = policy, env
         self.env_num = len(env)
         self.exploration_noise = exploration_noise
@@ -45,6 +47,7 @@ class Collector:
                           and isinstance(self.tracker, StateTrackerTransformer)
                           and hasattr(policy, "sample_device") and isinstance(buffer, VectorReplayBuffer)
                           and buffer.buffer_num == self.env_num and not remove_recommended_ids)
+        self.use_graph = bool(use_graph)      # replay the fused rollout from one captured CUDA graph
         self.data = Batch()
         self.h2d_bytes = self.d2h_bytes = 0   # host<->device traffic of the last fused collect()
         self.reset_stat()
@@ -157,56 +160,83 @@ class Collector:
         return res
 
     # ---- fused path
-    def _collect_fused(self, users):
-        env, trk, pol, buf, dev = self.env, self.tracker, self.policy, self.buffer, self.env.device
+    def _fused_state(self):
+        env, trk, pol, dev = self.env, self.tracker, self.policy, self.env.device
         B, T = self.env_num, env.max_turn
-        buf._alloc(trk.dim_state)
-        L = buf.sub_size
-        assert L >= T or self.force_length > 0, "buffer_size must be >= env_num * max_turn (SURVEY §9 invariants)"
         if not hasattr(self, "_f"):
             z = lambda dt: torch.zeros(B, dtype=dt, device=dev)  # noqa: E731
             self._f = dict(act=z(torch.int32), logp=z(torch.float32), value=z(torch.float32),
                            cur=torch.zeros(B, trk.dim_state, dtype=torch.float32, device=dev),
-                           n_active=torch.zeros(1, dtype=torch.int32, device=dev),
+                           d_users=z(torch.int32), rng=torch.zeros(1, dtype=torch.int64, device=dev),
+                           ws=pol.actor_workspace(B),
                            pin=torch.zeros(2 * T + 8, dtype=torch.int32).pin_memory(),
                            pin_users=torch.zeros(B, dtype=torch.int32).pin_memory(),
                            ev=[torch.cuda.Event() for _ in range(2 * T + 8)])
-        f = self._f
-        self.h2d_bytes = self.d2h_bytes = 0
-        if torch.is_tensor(users) and users.is_cuda:                # inputs already resident in HBM
-            d_users = users.to(torch.int32)
-        else:
-            users = env.draw_users(B) if users is None else np.asarray(users, dtype=np.int64).reshape(-1)
-            f["pin_users"].copy_(torch.from_numpy(users.astype(np.int32)))
-            d_users = f["pin_users"].to(dev, non_blocking=True)    # pinned host -> device
-            self.h2d_bytes += 4 * B
-        self.data = Batch()
-        buf.reset()
+            self._graph = None
+        return self._f
+
+    def _rollout_body(self, max_steps, poll):
+        """reset -> user token -> max_steps x (sample -> env step -> tracker step), all on per-slot device arrays.
+        With ``poll`` the host stops issuing turns once a non-blocking read says every episode has ended; without it
+        (CUDA-graph capture) all turns are issued and finished environments are skipped on the device."""
+        env, trk, pol, buf, f = self.env, self.tracker, self.policy, self.buffer, self._f
+        B, L = self.env_num, buf.sub_size
         trk.build_state(dim_batch=B, reset=True)
-        env.reset_device(d_users)                                   # sets active[:] = 1, turn = 0
-        buf.d_users.copy_(d_users)
+        env.reset_device(f["d_users"])                               # sets active[:] = 1, turn = 0
+        buf.d_users.copy_(f["d_users"])
         buf.d_len.zero_()
-        trk.step_device(B, None, None, env.turn, 0, d_users, None, None, cur_state=f["cur"],
-                        traj=(L, buf.obs, buf.obs_next))            # user token -> s0 = obs[e, 0]
+        trk.step_device(B, None, None, env.turn, 0, f["d_users"], None, None, cur_state=f["cur"],
+                        traj=(L, buf.obs, buf.obs_next))             # user token -> s0 = obs[e, 0]
         traj = (L, buf.d_act, buf.d_rew, buf.d_done)
-        max_steps = self.force_length if self.force_length > 0 else T
         turns = 0
         for t in range(max_steps):
-            pol.sample_device(B, f["cur"], trk.dim_state, f["act"], f["logp"], f["value"], active=env.active)
+            pol.sample_device(B, f["cur"], trk.dim_state, f["act"], f["logp"], f["value"], active=env.active,
+                              workspace=f["ws"], rng_counter=f["rng"])
             env.step_device(f["act"], env.rew, env.done, traj=traj, ep_len=buf.d_len, force_length=self.force_length)
             trk.step_device(B, None, None, env.turn, t + 1, f["act"], None, env.rew, cur_state=f["cur"],
                             traj=(L, buf.obs, buf.obs_next))
             turns = t + 1
-            # non-blocking poll: number of environments still running after this turn
-            f["pin"][t:t + 1].copy_(env.active.sum(dtype=torch.int32).reshape(1), non_blocking=True)
-            f["ev"][t].record()
-            if t >= 2 and f["ev"][t - 2].query() and int(f["pin"][t - 2]) == 0:
-                break
+            if poll:   # non-blocking: number of environments still running after this turn, read two turns later
+                f["pin"][t:t + 1].copy_(env.active.sum(dtype=torch.int32).reshape(1), non_blocking=True)
+                f["ev"][t].record()
+                if t >= 2 and f["ev"][t - 2].query() and int(f["pin"][t - 2]) == 0:
+                    break
+        return turns
+
+    def _collect_fused(self, users):
+        env, trk, buf, dev = self.env, self.tracker, self.buffer, self.env.device
+        B, T = self.env_num, env.max_turn
+        buf._alloc(trk.dim_state)
+        L = buf.sub_size
+        assert L >= T or self.force_length > 0, "buffer_size must be >= env_num * max_turn (SURVEY §9 invariants)"
+        f = self._fused_state()
+        self.h2d_bytes = self.d2h_bytes = 0
+        if torch.is_tensor(users) and users.is_cuda:                # inputs already resident in HBM
+            f["d_users"].copy_(users)
+        else:
+            users = env.draw_users(B) if users is None else np.asarray(users, dtype=np.int64).reshape(-1)
+            f["pin_users"].copy_(torch.from_numpy(users.astype(np.int32)))
+            f["d_users"].copy_(f["pin_users"], non_blocking=True)   # pinned host -> device
+            self.h2d_bytes += 4 * B
+        self.data = Batch()
+        buf.reset()
+        max_steps = self.force_length if self.force_length > 0 else T
+        if self.use_graph:
+            if self._graph is None:
+                self._rollout_body(max_steps, poll=False)           # eager warm-up (function attributes, allocations)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._rollout_body(max_steps, poll=False)
+                self._graph = g
+            self._graph.replay()                                     # the whole rollout: ONE graph launch
+        else:
+            self._rollout_body(max_steps, poll=True)
         lens = buf.d_len.cpu().numpy().astype(np.int64)             # the collect's D2H read (also a sync)
         rews = env.cum_rew.cpu().numpy()
-        self.d2h_bytes += 4 * B + 8 * B + 4 * turns
+        self.d2h_bytes += 4 * B + 8 * B
         buf.set_from_device(lens)
         order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
         res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])
-        res["turns"] = turns
+        res["turns"] = int(lens.max()) if len(lens) else 0
         return res

@@ -38,6 +38,7 @@ struct HeadArgs {
   int64_t state_stride;
   const float* noise_q;
   uint64_t seed, offset;
+  unsigned long long* rng_counter;  // optional device counter added to `offset` and bumped once per call
   int mode;
   const uint32_t* seen;
   const int32_t* act_in;  // MODE_EVAL: action per output index (may be NULL -> value only)
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(NT) actor_head_kernel(HeadArgs P) {
   const int n_tiles = (nA + BN - 1) / BN;
   const int t_beg = split * P.tiles_per_split, t_end = min(n_tiles, t_beg + P.tiles_per_split);
   const int seen_words = (nA + 31) >> 5;
+  const uint64_t offset = P.offset + (P.rng_counter ? (uint64_t)*P.rng_counter : 0ull);
 
   for (int t = t_beg; t < t_end; ++t) {
     const int n0 = t * BN;
@@ -200,8 +202,8 @@ __global__ void __launch_bounds__(NT) actor_head_kernel(HeadArgs P) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) g[j] = (nb + j < nA) ? -logf(q[j]) : 0.f;
           } else {
-            const uint4 rnd = philox4x32(make_uint4((uint32_t)rid[i], (uint32_t)(nb >> 2), (uint32_t)P.offset,
-                                                    (uint32_t)(P.offset >> 32)),
+            const uint4 rnd = philox4x32(make_uint4((uint32_t)rid[i], (uint32_t)(nb >> 2), (uint32_t)offset,
+                                                    (uint32_t)(offset >> 32)),
                                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
             g[0] = -logf(-logf(u01(rnd.x)) + 1e-30f);  // Gumbel = -log(q), q = -log(u) ~ Exp(1)
             g[1] = -logf(-logf(u01(rnd.y)) + 1e-30f);
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(NT) actor_head_kernel(HeadArgs P) {
 // merge the catalogue splits; Categorical.log_prob = log(clamp(p_a / sum p, eps, 1 - eps))  
 __global__ void actor_combine_kernel(HeadArgs P, int32_t* __restrict__ act, float* __restrict__ logp) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0 && P.rng_counter) *P.rng_counter += 1ull;  // the head kernel of this call has already read it
   if (k >= P.n_rows) return;
   const int id = P.gather ? P.gather[k] : k;
   if (P.active && !P.active[id]) return;
@@ -320,9 +323,9 @@ extern "C" int64_t cirs_actor_workspace_bytes(int32_t n_rows, int32_t n_action) 
 
 extern "C" int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_t* env_id,
                                  const uint8_t* active, const float* state, int64_t state_stride,
-                                 const float* noise_q, uint64_t seed, uint64_t offset, int32_t mode,
-                                 const uint32_t* seen, int32_t* act, float* logp, float* value, void* workspace,
-                                 void* stream) {
+                                 const float* noise_q, uint64_t seed, uint64_t offset, uint64_t* rng_counter,
+                                 int32_t mode, const uint32_t* seen, int32_t* act, float* logp, float* value,
+                                 void* workspace, void* stream) {
   if (!w || !state || !act || !workspace || n_rows < 0 || (mode != MODE_SAMPLE && mode != MODE_ARGMAX)) {
     cirs_set_error("cirs_actor_sample: bad argument");
     return CIRS_ERR_ARG;
@@ -331,7 +334,8 @@ extern "C" int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, c
   HeadArgs P{};
   P.W = *w; P.n_rows = n_rows; P.gather = env_id; P.state_by_k = env_id != nullptr; P.out_by_k = 1;
   P.active = active; P.state = state; P.state_stride = state_stride; P.noise_q = noise_q; P.seed = seed;
-  P.offset = offset; P.mode = mode; P.seen = seen; P.act_in = nullptr; P.value = value;
+  P.offset = offset; P.rng_counter = reinterpret_cast<unsigned long long*>(rng_counter); P.mode = mode; P.seen = seen;
+  P.act_in = nullptr; P.value = value;
   return run_head(P, act, logp, workspace, (cudaStream_t)stream);
 }
 

@@ -370,3 +370,40 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   }
   return CIRS_OK;
 }
+
+// The whole learn() loop of one update for a single process (core/policy/ppo.py:173-233): for every repeat, the
+// advantage statistics of all minibatches, then per minibatch forward / loss / backward / clip / Adam -- issued
+// back to back from C so that the host pays one call instead of ~20 launches' worth of interpreter overhead per
+// minibatch.  Multi-process runs use the per-minibatch entry points with an all-reduce in between.
+extern "C" int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grads, float* exp_avg,
+                              float* exp_avg_sq, const cirs_ppo_config* cfg, int32_t n_repeat, int32_t n_mb,
+                              const int32_t* mb_off_h, const int32_t* mb_off, const int32_t* slots, const float* obs,
+                              const int32_t* act, const float* adv, const float* returns, const float* v_old,
+                              const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats,
+                              float* losses, int32_t* opt_state, double* opt_scratch, void* workspace,
+                              void* stream) {
+  if (!w || !grads || !exp_avg || !exp_avg_sq || !cfg || !mb_off_h || !mb_off || !slots || !adv_stats || !losses ||
+      !opt_state || !opt_scratch || n_repeat < 0 || n_mb < 0) {
+    cirs_set_error("cirs_ppo_learn: bad argument");
+    return CIRS_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t n = mb_off_h[n_mb];
+  for (int r = 0; r < n_repeat; ++r) {
+    const int32_t* sl = slots + (int64_t)r * n;
+    double* stats = adv_stats + (int64_t)r * n_mb * 3;
+    int rc = cirs_adv_stats(n_mb, mb_off, sl, adv, stats, stream);
+    if (rc) return rc;
+    if (d_obs) cudaMemsetAsync(d_obs, 0, sizeof(float) * d_obs_floats, st);   // optim_state.zero_grad(), ppo.py:174
+    for (int j = 0; j < n_mb; ++j) {
+      const int b = mb_off_h[j], cnt = mb_off_h[j + 1] - b;
+      rc = cirs_ppo_minibatch(w, grads, cfg, cnt, cnt, sl + b, obs, act, adv, returns, v_old, logp_old,
+                              stats + 3 * j, d_obs, losses + 4 * ((int64_t)r * n_mb + j), workspace, stream);
+      if (rc) return rc;
+      rc = cirs_clip_adam(w->flat, grads->flat, exp_avg, exp_avg_sq, w->n_flat, w->n_trunk, cfg, opt_state,
+                          opt_scratch, stream);
+      if (rc) return rc;
+    }
+  }
+  return CIRS_OK;
+}

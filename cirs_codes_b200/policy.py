@@ -77,6 +77,7 @@ class PPOPolicy:
         self.action_space = action_space
         self.seed, self._calls = int(seed), 0
         self.group = process_group
+        self.c_loop = True   # single process: run the repeat x minibatch loop inside one C call (cirs_ppo_learn)
         self.perm_on_device = bool(perm_on_device)   # minibatch permutations from torch.randperm on the device
         self.h2d_bytes = self.d2h_bytes = 0          # host<->device traffic of the last update()
 
@@ -163,15 +164,23 @@ class PPOPolicy:
         return self._ws_actor
 
     def sample_device(self, n_rows, state, state_stride, act, logp, value, env_id=None, active=None, noise_q=None,
-                      mode=None, seen=None):
-        """One fused trunk + head + softmax + sample launch (csrc/actor.cu)."""
+                      mode=None, seen=None, workspace=None, rng_counter=None):
+        """One fused trunk + head + softmax + sample launch (csrc/actor.cu).  ``rng_counter`` (device int64[1]) makes
+        the Philox stream advance on the device, so the launch can be replayed from a CUDA graph."""
         if mode is None:
             mode = 1 if (self._deterministic_eval and not self.training) else 0
-        self._calls += 1
+        if rng_counter is None:
+            self._calls += 1
+        ws = workspace if workspace is not None else self._actor_ws(n_rows)
         _lib.call("cirs_actor_sample", C.byref(self._w), int(n_rows), _lib.ptr(env_id), _lib.ptr(active),
-                  _lib.ptr(state), int(state_stride), _lib.ptr(noise_q), self.seed, self._calls, int(mode),
-                  _lib.ptr(seen), _lib.ptr(act), _lib.ptr(logp), _lib.ptr(value), _lib.ptr(self._actor_ws(n_rows)),
-                  _lib.stream())
+                  _lib.ptr(state), int(state_stride), _lib.ptr(noise_q), self.seed,
+                  self._calls if rng_counter is None else (1 << 40), _lib.ptr(rng_counter), int(mode),
+                  _lib.ptr(seen), _lib.ptr(act), _lib.ptr(logp), _lib.ptr(value), _lib.ptr(ws), _lib.stream())
+
+    def actor_workspace(self, n_rows):
+        """A dedicated sampler workspace (the fused Collector keeps its own so that captured graphs stay valid)."""
+        need = _lib.load().cirs_actor_workspace_bytes(n_rows, self.n_action)
+        return torch.empty(need, dtype=torch.uint8, device=self.device)
 
     def forward(self, batch, buffer=None, remove_recommended_ids=False, state=None, noise_q=None, **kwargs):
         """core/policy/ppo.py:111-163.  batch.obs: float32 CUDA tensor [n, dim_state].  Returns Batch(act, logp,
@@ -283,37 +292,54 @@ class PPOPolicy:
         offs = np.zeros(len(sizes) + 1, dtype=np.int32)
         offs[1:] = np.cumsum(sizes)
         d_offs = torch.as_tensor(offs, device=dev)
-        chunks = sizes
-        for step in range(repeat):
+        n_mb = len(sizes)
+
+        def slots_for(step):
             if perms is not None:
-                d_slots = torch.as_tensor(idx_h[np.asarray(perms[step])].astype(np.int32), device=dev)
                 self.h2d_bytes += 4 * n
-            elif self.perm_on_device:
-                d_slots = indices[torch.randperm(n, device=dev)]
-            else:
-                d_slots = torch.as_tensor(idx_h[np.random.permutation(n)].astype(np.int32), device=dev)  # batch.py:736
-                self.h2d_bytes += 4 * n
-            stats = torch.zeros(len(chunks), 3, dtype=torch.float64, device=dev)
-            _lib.call("cirs_adv_stats", len(chunks), _lib.ptr(d_offs), _lib.ptr(d_slots), _lib.ptr(self.adv),
-                      _lib.ptr(stats), st)
-            self._allreduce(stats)
-            n_glob = stats[:, 0].round().to(torch.int64).cpu().numpy() if world > 1 else np.diff(offs)
-            losses = torch.zeros(len(chunks), 4, dtype=torch.float32, device=dev)
-            if tracker is not None:
-                self.d_obs.zero_()                                                   # optim_state.zero_grad(), :174
-            ws = self._ppo_ws(int(np.diff(offs).max()))
-            for j in range(len(chunks)):
-                b, e = int(offs[j]), int(offs[j + 1])
-                _lib.call("cirs_ppo_minibatch", C.byref(self._w), C.byref(self._g), C.byref(self.cfg), e - b,
-                          int(n_glob[j]), d_slots.data_ptr() + 4 * b, _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act),
-                          _lib.ptr(self.adv), _lib.ptr(self.returns), _lib.ptr(self.v_s), _lib.ptr(self.logp_old),
-                          stats.data_ptr() + 24 * j, _lib.ptr(self.d_obs) if tracker is not None else None,
-                          losses.data_ptr() + 16 * j, _lib.ptr(ws), st)
-                self._allreduce(self.grad)                                           # ONE collective per minibatch
-                _lib.call("cirs_clip_adam", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
-                          _lib.ptr(self.exp_avg_sq), self.layout.total, self.layout.n_trunk, C.byref(self.cfg),
-                          _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), st)
+                return torch.as_tensor(idx_h[np.asarray(perms[step])].astype(np.int32), device=dev)
+            if self.perm_on_device:
+                return indices[torch.randperm(n, device=dev)]
+            self.h2d_bytes += 4 * n
+            return torch.as_tensor(idx_h[np.random.permutation(n)].astype(np.int32), device=dev)   # batch.py:736
+
+        ws = self._ppo_ws(int(max(sizes)))
+        d_obs = self.d_obs if tracker is not None else None
+        if world == 1 and self.c_loop:
+            # single process: the whole repeat x minibatch loop is one C call (csrc/ppo.cu cirs_ppo_learn)
+            d_slots = torch.cat([slots_for(step) for step in range(repeat)])
+            stats = torch.zeros(repeat * n_mb, 3, dtype=torch.float64, device=dev)
+            losses = torch.zeros(repeat * n_mb, 4, dtype=torch.float32, device=dev)
+            _lib.call("cirs_ppo_learn", C.byref(self._w), C.byref(self._g), _lib.ptr(self.exp_avg),
+                      _lib.ptr(self.exp_avg_sq), C.byref(self.cfg), repeat, n_mb, offs.ctypes.data, _lib.ptr(d_offs),
+                      _lib.ptr(d_slots), _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act), _lib.ptr(self.adv),
+                      _lib.ptr(self.returns), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(stats),
+                      _lib.ptr(d_obs), d_obs.numel() if d_obs is not None else 0, _lib.ptr(losses),
+                      _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), _lib.ptr(ws), st)
             losses_all.append(losses)
+        else:
+            for step in range(repeat):
+                d_slots = slots_for(step)
+                stats = torch.zeros(n_mb, 3, dtype=torch.float64, device=dev)
+                _lib.call("cirs_adv_stats", n_mb, _lib.ptr(d_offs), _lib.ptr(d_slots), _lib.ptr(self.adv),
+                          _lib.ptr(stats), st)
+                self._allreduce(stats)
+                n_glob = stats[:, 0].round().to(torch.int64).cpu().numpy()
+                losses = torch.zeros(n_mb, 4, dtype=torch.float32, device=dev)
+                if tracker is not None:
+                    self.d_obs.zero_()                                               # optim_state.zero_grad(), :174
+                for j in range(n_mb):
+                    b, e = int(offs[j]), int(offs[j + 1])
+                    _lib.call("cirs_ppo_minibatch", C.byref(self._w), C.byref(self._g), C.byref(self.cfg), e - b,
+                              int(n_glob[j]), d_slots.data_ptr() + 4 * b, _lib.ptr(buffer.obs),
+                              _lib.ptr(buffer.d_act), _lib.ptr(self.adv), _lib.ptr(self.returns), _lib.ptr(self.v_s),
+                              _lib.ptr(self.logp_old), stats.data_ptr() + 24 * j, _lib.ptr(d_obs),
+                              losses.data_ptr() + 16 * j, _lib.ptr(ws), st)
+                    self._allreduce(self.grad)                                       # ONE collective per minibatch
+                    _lib.call("cirs_clip_adam", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
+                              _lib.ptr(self.exp_avg_sq), self.layout.total, self.layout.n_trunk, C.byref(self.cfg),
+                              _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), st)
+                losses_all.append(losses)
         if tracker is not None:
             tracker.zero_grad()
             tracker.backward_from_buffer(buffer, self.d_obs, buffer.d_users)

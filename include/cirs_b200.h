@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CIRS_ABI_VERSION 2
+#define CIRS_ABI_VERSION 3
 #define CIRS_MAX_LAYERS 4
 #define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
 
@@ -160,6 +160,8 @@ typedef struct {
  * logits GEMM so the [n, n_action] probabilities are never written.
  *   state   : row k reads state + (env_id ? k : e) * state_stride   (compact rows with env_id, per-slot without)
  *   noise_q : [n_rows, n_action] Exp(1) draws supplied by the caller (parity tests) or NULL -> Philox(seed, offset)
+ *   rng_counter : optional device uint64; the Philox offset becomes offset + *rng_counter and the call increments it,
+ *             so that a captured CUDA graph draws fresh noise at every replay
  *   mode    : 0 sample, 1 argmax (deterministic_eval)
  *   seen    : optional [B, ceil(n_action/32)] bitset; set bits are removed from the distribution
  *             (remove_recommended_ids, core/policy/utils.py:30-58)
@@ -168,8 +170,8 @@ typedef struct {
 int64_t cirs_actor_workspace_bytes(int32_t n_rows, int32_t n_action);
 int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_t* env_id, const uint8_t* active,
                       const float* state, int64_t state_stride, const float* noise_q, uint64_t seed,
-                      uint64_t offset, int32_t mode, const uint32_t* seen, int32_t* act, float* logp,
-                      float* value, void* workspace, void* stream);
+                      uint64_t offset, uint64_t* rng_counter, int32_t mode, const uint32_t* seen, int32_t* act,
+                      float* logp, float* value, void* workspace, void* stream);
 
 /* Critic / log-prob evaluation without sampling: A2CPolicy._compute_returns' critic(obs) calls
  * (tianshou/policy/modelfree/a2c.py:89-90) and PPOPolicy.process_fn's old log-prob (core/policy/ppo.py:104-108).
@@ -231,6 +233,19 @@ int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_policy_weights* 
  *   max_grad_norm <= 0 -> no clipping.   scratch: double[2] device scratch. */
 int cirs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t n_dup,
                    const cirs_ppo_config* cfg, int32_t* state, double* scratch, void* stream);
+
+/* The whole learn() loop of one update for a single process (core/policy/ppo.py:173-233): n_repeat passes over
+ * n_mb minibatches; slots[r * n + i] is the i-th buffer slot of repeat r's permutation (n = mb_off_h[n_mb]),
+ * minibatch j = entries mb_off_h[j] .. mb_off_h[j+1].  mb_off_h is a HOST array, mb_off its device copy.
+ * adv_stats: double[n_repeat * n_mb * 3] device scratch; losses: float[n_repeat * n_mb * 4] on the device.
+ * d_obs (optional, d_obs_floats elements) is zeroed at the start of every repeat and receives d loss / d obs.
+ * exp_avg / exp_avg_sq / opt_state / opt_scratch: Adam state as in cirs_clip_adam (n_dup = w->n_trunk). */
+int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grads, float* exp_avg,
+                   float* exp_avg_sq, const cirs_ppo_config* cfg, int32_t n_repeat, int32_t n_mb,
+                   const int32_t* mb_off_h, const int32_t* mb_off, const int32_t* slots, const float* obs,
+                   const int32_t* act, const float* adv, const float* returns, const float* v_old,
+                   const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats, float* losses,
+                   int32_t* opt_state, double* opt_scratch, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

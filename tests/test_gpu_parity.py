@@ -247,8 +247,9 @@ def test_generic_collect_vs_golden(H, name):
         assert np.array_equal(buf.prev(mid), mid - 1)
 
 
+@pytest.mark.parametrize("c_loop", [True, False])
 @pytest.mark.parametrize("name", G.KUAISHOU_CASES)
-def test_update_heads_vs_golden_and_oracle(H, name):
+def test_update_heads_vs_golden_and_oracle(H, name, c_loop):
     """policy.update on the replayed rollout with the reference's minibatch permutations.  The tracker is frozen here
     (its step comes after all minibatches, core/policy/ppo.py:235, so iteration-0 losses and actor / critic weights
     do not depend on it); tests/test_gpu_tracker_train.py covers the tracker."""
@@ -257,6 +258,7 @@ def test_update_heads_vs_golden_and_oracle(H, name):
     c = G.cfg(z)
     trk = H.make_tracker(z, c)
     pol = H.make_policy(z, c, None)
+    pol.c_loop = c_loop     # one C call for the whole loop / the per-minibatch entry points the multi-GPU path uses
     col, buf, res = _golden_collect(H, z, c, 0, trk, pol)
     n = len(buf)
     perms = G.perms(z, 0, n)
