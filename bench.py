@@ -168,16 +168,10 @@ def k1_bytes(lens, N):
     return tot
 
 
-def gpu_arm(args, cfg):
+def setup_workload(cfg, tb, dev, rank=0):
+    """Build env / tracker / policy / buffer / collector for a config through the public (reference-facing) API."""
     import torch
     import cirs_codes_b200 as cb
-    from cirs_codes_b200 import _lib, parallel
-    rank, world = parallel.init_from_env("nccl")
-    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-    torch.cuda.set_device(dev)
-    dist = torch.distributed if world > 1 else None
-    tb = tables(cfg)
     B, T = cfg["B"], cfg["T"]
 
     class _E:
@@ -206,6 +200,21 @@ def gpu_arm(args, cfg):
     buf = cb.VectorReplayBuffer(B * T, B, device=dev)
     col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state)
     assert col.fused
+    return env, trk, pol, buf, col
+
+
+def gpu_arm(args, cfg):
+    import torch
+    import cirs_codes_b200 as cb
+    from cirs_codes_b200 import _lib, parallel
+    rank, world = parallel.init_from_env("nccl")
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    dist = torch.distributed if world > 1 else None
+    tb = tables(cfg)
+    B, T = cfg["B"], cfg["T"]
+    env, trk, pol, buf, col = setup_workload(cfg, tb, dev, rank)
     lib = _lib.load()
     rng = np.random.default_rng(5 + rank)
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
@@ -249,11 +258,11 @@ def gpu_arm(args, cfg):
             ms, steps = float(tm[0]), float(t[1])
         return ms, steps, h2d / K, d2h / K, np.concatenate(lens_all)
 
+    clocks = Clocks(dev.index or 0)
+    clocks.start()                  # sampler runs through warm-up and both timed regions (nvidia-smi starts slowly)
     for _ in range(max(args.warmup, 3)):
         one_step(rng.integers(0, cfg["U"], size=B), False)
     one_step(torch.as_tensor(rng.integers(0, cfg["U"], size=B).astype(np.int32), device=dev), True)
-    clocks = Clocks(dev.index or 0)
-    clocks.start()
     l0 = lib.cirs_launch_count()
     ms_res, steps_res, _, _, lens = timed(args.steps, True)
     launches = lib.cirs_launch_count() - l0
@@ -271,6 +280,9 @@ def gpu_arm(args, cfg):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
+        col.use_graph = False          # per-kernel events need real launches, not a graph replay
+        for _ in range(2):
+            one_step(rng.integers(0, cfg["U"], size=B), False)
         lib.cirs_profile_enable(1)
         lens_p = []
         n_prof = min(args.steps, 3)

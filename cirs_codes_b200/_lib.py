@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcirs_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LAYERS = 4
 HIDDEN = 64
 
@@ -65,9 +65,9 @@ PROTOTYPES = {
     "cirs_kuaishou_step": (i32, [P(KuaishouEnvStruct), i32, fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, i32, fp]),
     "cirs_tracker_step": (i32, [P(TrackerWeightsStruct), i32, i32, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, i64,
                                 fp, i32, fp, fp, fp]),
-    "cirs_tracker_train_workspace_bytes": (i64, [P(TrackerWeightsStruct), i32, i32]),
+    "cirs_tracker_train_workspace_bytes": (i64, [P(TrackerWeightsStruct), i32, i64]),
     "cirs_tracker_train": (i32, [P(TrackerWeightsStruct), P(TrackerWeightsStruct), i32, i32, fp, fp, fp, fp, fp,
-                                 fp, fp, fp, fp, i64, fp]),
+                                 fp, i32, fp, fp, fp, fp, fp, i64, fp]),
     "cirs_actor_workspace_bytes": (i64, [i32, i32]),
     "cirs_actor_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp, fp,
                                 fp, fp]),

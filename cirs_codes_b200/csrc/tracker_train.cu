@@ -22,6 +22,17 @@ using namespace cirs;
 __host__ __device__ inline int64_t al(int64_t x) { return (x + 63) & ~(int64_t)63; }
 inline int up32(int v) { return (v + 31) & ~31; }
 
+// Row <-> (environment, position) mapping.  Padded: row == buffer slot e*L + p.  Compact (tok_slot given): row i holds
+// the token of buffer slot tok_slot[i]; slots are env-major sorted, so environment e owns rows env_off[e] ..
+// env_off[e] + ep_len[e) and only valid tokens exist.
+struct RowMap {
+  int L;
+  const int32_t* tok_slot;
+  const int32_t* env_off;
+  __device__ __forceinline__ int slot(int row) const { return tok_slot ? tok_slot[row] : row; }
+  __device__ __forceinline__ size_t base(int e) const { return env_off ? (size_t)env_off[e] : (size_t)e * L; }
+};
+
 struct LayerBufs {
   float *qkv, *o, *r1, *st1, *x1, *h, *r2, *st2, *x2;
 };
@@ -48,12 +59,12 @@ Bufs carve(float* base, int64_t B, int64_t M, int d, int dhid, int nl, int d_use
 }
 
 // ---- gather the token inputs: U[e] = user embedding / dense user;  IN[row] = [rew ; item embedding] for p >= 1
-__global__ void gather_inputs_kernel(cirs_tracker_weights W, int B, int L, const int32_t* __restrict__ users,
+__global__ void gather_inputs_kernel(cirs_tracker_weights W, int B, RowMap map, const int32_t* __restrict__ users,
                                      const int32_t* __restrict__ act, const float* __restrict__ rew,
                                      const int32_t* __restrict__ ep_len, const float* __restrict__ dense_user,
                                      const float* __restrict__ dense_item, float* __restrict__ U,
                                      float* __restrict__ IN) {
-  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d, tid = threadIdx.x;
+  const int row = blockIdx.x, L = map.L, slot = map.slot(row), e = slot / L, p = slot % L, d = W.d, tid = threadIdx.x;
   const int n = ep_len[e];
   if (p == 0) {
     const int du = W.d_user_in;
@@ -72,10 +83,10 @@ __global__ void gather_inputs_kernel(cirs_tracker_weights W, int B, int L, const
 }
 
 // ---- tokens: x0 = sqrt(d) * tok + PE[p];  tok = ffn_user(u) at p = 0, sigmoid(Z) * a afterwards (Z -> G in place)
-__global__ void token_fwd_kernel(cirs_tracker_weights W, int L, const int32_t* __restrict__ ep_len,
+__global__ void token_fwd_kernel(cirs_tracker_weights W, RowMap map, const int32_t* __restrict__ ep_len,
                                  const float* __restrict__ IN, const float* __restrict__ tok0, float* __restrict__ G,
                                  float* __restrict__ X0) {
-  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d;
+  const int row = blockIdx.x, L = map.L, slot = map.slot(row), e = slot / L, p = slot % L, d = W.d;
   const bool valid = p < ep_len[e];
   const float sq = sqrtf((float)d);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -95,11 +106,11 @@ __global__ void token_fwd_kernel(cirs_tracker_weights W, int L, const int32_t* _
 }
 
 // d tok = sqrt(d) * dX0;  p = 0 -> dTOK0[e];  p >= 1 -> dZ = dtok * a * g (1 - g),  DA = dtok * g
-__global__ void token_bwd_kernel(cirs_tracker_weights W, int L, const int32_t* __restrict__ ep_len,
+__global__ void token_bwd_kernel(cirs_tracker_weights W, RowMap map, const int32_t* __restrict__ ep_len,
                                  const float* __restrict__ IN, const float* __restrict__ G,
                                  const float* __restrict__ dX0, float* __restrict__ dTOK0, float* __restrict__ dZ,
                                  float* __restrict__ DA) {
-  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d;
+  const int row = blockIdx.x, L = map.L, slot = map.slot(row), e = slot / L, p = slot % L, d = W.d;
   const bool valid = p < ep_len[e];
   const float sq = sqrtf((float)d);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -118,11 +129,11 @@ __global__ void token_bwd_kernel(cirs_tracker_weights W, int L, const int32_t* _
 }
 
 // embedding gradients (dense nn.Embedding grads, scatter-add)
-__global__ void emb_scatter_kernel(cirs_tracker_weights W, cirs_tracker_weights Gr, int B, int L,
+__global__ void emb_scatter_kernel(cirs_tracker_weights W, cirs_tracker_weights Gr, int B, RowMap map,
                                    const int32_t* __restrict__ users, const int32_t* __restrict__ act,
                                    const int32_t* __restrict__ ep_len, const float* __restrict__ dIN,
                                    const float* __restrict__ DA, const float* __restrict__ dU) {
-  const int row = blockIdx.x, e = row / L, p = row % L, d = W.d;
+  const int row = blockIdx.x, L = map.L, slot = map.slot(row), e = slot / L, p = slot % L, d = W.d;
   if (p == 0) {
     if (Gr.emb_user)
       for (int c = threadIdx.x; c < d; c += blockDim.x)
@@ -214,22 +225,24 @@ inline size_t attn_smem_bytes(int Lmax, int dh, int nwarp) {
 constexpr int ATT_WARPS = 4;
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attn_fwd_kernel(int L, int d, int nhead, const int32_t* __restrict__ ep_len, const float* __restrict__ QKV,
+attn_fwd_kernel(RowMap map, int d, int nhead, const int32_t* __restrict__ ep_len, const float* __restrict__ QKV,
                 float* __restrict__ O) {
   extern __shared__ float sm[];
-  const int e = blockIdx.x, h = blockIdx.y, dh = d / nhead, ld = dh + 1;
+  const int e = blockIdx.x, h = blockIdx.y, dh = d / nhead, ld = dh + 1, L = map.L;
   const int n = min(ep_len[e], L), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t r0 = map.base(e);
+  const int n_rows = map.env_off ? n : L;   // rows this environment owns (padding rows exist only when padded)
   AttnSmem S = attn_carve(sm, L, dh, ATT_WARPS);
   for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
     const int p = i / dh, c = i % dh;
-    const float* src = QKV + ((size_t)e * L + p) * 3 * d + h * dh + c;
+    const float* src = QKV + (r0 + p) * 3 * d + h * dh + c;
     S.q[p * ld + c] = src[0]; S.k[p * ld + c] = src[d]; S.v[p * ld + c] = src[2 * d];
   }
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)dh);
   float* pw = S.pw + warp * L;
-  for (int i = warp; i < L; i += ATT_WARPS) {
-    float* out = O + ((size_t)e * L + i) * d + h * dh;
+  for (int i = warp; i < n_rows; i += ATT_WARPS) {
+    float* out = O + (r0 + i) * d + h * dh;
     if (i >= n) {
       for (int c = lane; c < dh; c += 32) out[c] = 0.f;
       continue;
@@ -257,23 +270,25 @@ attn_fwd_kernel(int L, int d, int nhead, const int32_t* __restrict__ ep_len, con
 }
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attn_bwd_kernel(int L, int d, int nhead, const int32_t* __restrict__ ep_len, const float* __restrict__ QKV,
+attn_bwd_kernel(RowMap map, int d, int nhead, const int32_t* __restrict__ ep_len, const float* __restrict__ QKV,
                 const float* __restrict__ dOg, float* __restrict__ dQKV) {
   extern __shared__ float sm[];
-  const int e = blockIdx.x, h = blockIdx.y, dh = d / nhead, ld = dh + 1;
+  const int e = blockIdx.x, h = blockIdx.y, dh = d / nhead, ld = dh + 1, L = map.L;
   const int n = min(ep_len[e], L), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t r0 = map.base(e);
+  const int n_rows = map.env_off ? n : L;   // rows this environment owns (padding rows exist only when padded)
   AttnSmem S = attn_carve(sm, L, dh, ATT_WARPS);
   for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
     const int p = i / dh, c = i % dh;
-    const size_t row = (size_t)e * L + p;
+    const size_t row = r0 + p;
     const float* src = QKV + row * 3 * d + h * dh + c;
     S.q[p * ld + c] = src[0]; S.k[p * ld + c] = src[d]; S.v[p * ld + c] = src[2 * d];
     S.dO[p * ld + c] = dOg[row * d + h * dh + c];
   }
   // padding rows: zero gradient
-  for (int i = threadIdx.x; i < (L - n) * dh; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (n_rows - n) * dh; i += blockDim.x) {
     const int p = n + i / dh, c = i % dh;
-    float* dst = dQKV + ((size_t)e * L + p) * 3 * d + h * dh + c;
+    float* dst = dQKV + (r0 + p) * 3 * d + h * dh + c;
     dst[0] = 0.f; dst[d] = 0.f; dst[2 * d] = 0.f;
   }
   __syncthreads();
@@ -307,7 +322,7 @@ attn_bwd_kernel(int L, int d, int nhead, const int32_t* __restrict__ ep_len, con
     for (int j = lane; j <= i; j += 32) sw[j] = pw[j] * (sw[j] - dsum);   // dS_ij
     if (lane == 0) { S.mx[i] = mx; S.iz[i] = inv; S.dd[i] = dsum; }
     __syncwarp();
-    float* dq = dQKV + ((size_t)e * L + i) * 3 * d + h * dh;
+    float* dq = dQKV + (r0 + i) * 3 * d + h * dh;
     for (int c = lane; c < dh; c += 32) {
       float a = 0.f;
       for (int j = 0; j <= i; ++j) a = fmaf(sw[j], S.k[j * ld + c], a);
@@ -329,7 +344,7 @@ attn_bwd_kernel(int L, int d, int nhead, const int32_t* __restrict__ ep_len, con
       sw[i] = p * (dp - S.dd[i]);
     }
     __syncwarp();
-    float* dk = dQKV + ((size_t)e * L + j) * 3 * d + d + h * dh;
+    float* dk = dQKV + (r0 + j) * 3 * d + d + h * dh;
     for (int c = lane; c < dh; c += 32) {
       float ak = 0.f, av = 0.f;
       for (int i = j; i < n; ++i) {
@@ -373,16 +388,17 @@ void linear_bwd_w(const float* X, int ldx, const float* dY, int ldy, float* gWt,
 }  // namespace
 
 extern "C" int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_t n_env,
-                                                      int32_t traj_len) {
+                                                      int64_t n_rows) {
   if (!w) return 0;
-  const Bufs b = carve(nullptr, n_env, (int64_t)n_env * traj_len, w->d, w->d_hid, w->nlayers, w->d_user_in);
+  const Bufs b = carve(nullptr, n_env, n_rows, w->d, w->d_hid, w->nlayers, w->d_user_in);
   return b.total * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights* grads, int32_t n_env,
                                   int32_t traj_len, const int32_t* users, const int32_t* traj_act,
                                   const float* traj_rew, const int32_t* ep_len, const float* dense_user,
-                                  const float* dense_item, const float* d_obs, float* obs_check, void* workspace,
+                                  const float* dense_item, int32_t n_tok, const int32_t* tok_slot,
+                                  const int32_t* env_off, const float* d_obs, float* obs_check, void* workspace,
                                   int64_t workspace_bytes, void* stream) {
   if (!w || !grads || !traj_rew || !ep_len || !workspace || n_env < 0 || traj_len < 1) {
     cirs_set_error("cirs_tracker_train: null argument");
@@ -398,13 +414,19 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
     cirs_set_error("cirs_tracker_train: unsupported shape");
     return CIRS_ERR_ARG;
   }
-  if (cirs_tracker_train_workspace_bytes(w, n_env, traj_len) > workspace_bytes) {
+  if ((tok_slot == nullptr) != (env_off == nullptr) || n_tok < 0) {
+    cirs_set_error("cirs_tracker_train: tok_slot and env_off must be given together");
+    return CIRS_ERR_ARG;
+  }
+  const int64_t n_rows = tok_slot ? (int64_t)n_tok : (int64_t)n_env * traj_len;
+  if (cirs_tracker_train_workspace_bytes(w, n_env, n_rows) > workspace_bytes) {
     cirs_set_error("cirs_tracker_train: workspace too small");
     return CIRS_ERR_ARG;
   }
-  if (n_env == 0) return CIRS_OK;
+  if (n_env == 0 || n_rows == 0) return CIRS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int B = n_env, L = traj_len, M = B * L, d = w->d, dhid = w->d_hid, S = w->dim_state, nl = w->nlayers;
+  const RowMap map{traj_len, tok_slot, env_off};
+  const int B = n_env, L = traj_len, M = (int)n_rows, d = w->d, dhid = w->d_hid, S = w->dim_state, nl = w->nlayers;
   const int ldd = up32(d), ld3 = up32(3 * d), ldh = up32(dhid), lds = up32(S), dui = w->d_user_in;
   const int nh = w->nhead, dh = d / nh;
   Bufs b = carve(reinterpret_cast<float*>(workspace), B, M, d, dhid, nl, dui);
@@ -421,18 +443,18 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
   const cirs_tracker_weights& G = *grads;
 
   // ================= forward
-  CIRS_LAUNCH(gather_inputs_kernel, M, 64, 0, st, W, B, L, users, traj_act, traj_rew, ep_len, dense_user, dense_item, b.u, b.in);
+  CIRS_LAUNCH(gather_inputs_kernel, M, 64, 0, st, W, B, map, users, traj_act, traj_rew, ep_len, dense_user, dense_item, b.u, b.in);
   CIRS_CHECK_LAUNCH();
   linear_fwd(b.u, dui, W.user_wt, ldd, W.user_b, b.tok0, d, B, d, dui, 0, nullptr, 0, st);           // ffn_user
   linear_fwd(b.in, 1 + d, W.gate_wt, ldd, W.gate_b, b.g, d, M, d, 1 + d, 0, nullptr, 0, st);          // fnn_gate (pre-act)
-  CIRS_LAUNCH(token_fwd_kernel, M, 64, 0, st, W, L, ep_len, b.in, b.tok0, b.g, b.x0);
+  CIRS_LAUNCH(token_fwd_kernel, M, 64, 0, st, W, map, ep_len, b.in, b.tok0, b.g, b.x0);
   CIRS_CHECK_LAUNCH();
   const float* x = b.x0;
   for (int l = 0; l < nl; ++l) {
     const cirs_encoder_layer& Y = W.layer[l];
     LayerBufs& y = b.layer[l];
     linear_fwd(x, d, Y.in_wt, ld3, Y.in_b, y.qkv, 3 * d, M, 3 * d, d, 0, nullptr, 0, st);
-    CIRS_LAUNCH(attn_fwd_kernel, dim3(B, nh), ATT_WARPS * 32, att_smem, st, L, d, nh, ep_len, y.qkv, y.o);
+    CIRS_LAUNCH(attn_fwd_kernel, dim3(B, nh), ATT_WARPS * 32, att_smem, st, map, d, nh, ep_len, y.qkv, y.o);
     CIRS_CHECK_LAUNCH();
     linear_fwd(y.o, d, Y.out_wt, ldd, Y.out_b, y.r1, d, M, d, d, 0, x, d, st);                         // r1 = x + attn
     CIRS_LAUNCH(ln_fwd_kernel, (M + 7) / 8, 256, 0, st, M, d, y.r1, Y.n1_w, Y.n1_b, y.x1, y.st1);
@@ -443,14 +465,21 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
     CIRS_CHECK_LAUNCH();
     x = y.x2;
   }
-  if (obs_check) linear_fwd(x, d, W.dec_wt, lds, W.dec_b, obs_check, S, M, S, d, 0, nullptr, 0, st);
+  if (obs_check)   // decoded states, scattered to their buffer slots
+    launch_gemm<64, 64, 16, 4>(RowMajorA{x, d, nullptr}, RowMajorB{W.dec_wt, lds, nullptr},
+                               StoreEp{obs_check, S, W.dec_b, 0, tok_slot, nullptr, 0, nullptr, 0}, M, S, d, 1, nullptr,
+                               st, "tracker_linear_fwd_gemm");
   CIRS_CHECK_LAUNCH();
   if (!d_obs) return CIRS_OK;
 
   // ================= backward
   const int ln_grid = min((M + 7) / 8, 148 * 4);
-  linear_bwd_w(x, d, d_obs, S, G.dec_wt, lds, G.dec_b, M, S, d, st);
-  linear_bwd_x(d_obs, S, W.dec_wt, lds, b.da, d, M, S, d, nullptr, 0, nullptr, 0, st);                 // da = dX_last
+  // decoder: d_obs rows are gathered from their buffer slots
+  launch_gemm<64, 64, 16, 4>(ColMajorA{x, d, nullptr}, RowMajorB{d_obs, S, tok_slot}, AtomicEp{G.dec_wt, lds}, d, S, M,
+                             splitk(1, M), G.dec_b, st, "tracker_linear_dw_gemm");
+  launch_gemm<64, 64, 16, 4>(RowMajorA{d_obs, S, tok_slot}, ColMajorB{W.dec_wt, lds},
+                             StoreEp{b.da, d, nullptr, 0, nullptr, nullptr, 0, nullptr, 0}, M, d, S, 1, nullptr, st,
+                             "tracker_linear_dx_gemm");                                               // da = dX_last
   for (int l = nl - 1; l >= 0; --l) {
     const cirs_encoder_layer& Y = W.layer[l];
     const cirs_encoder_layer& Gy = G.layer[l];
@@ -466,20 +495,20 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
     CIRS_CHECK_LAUNCH();
     linear_bwd_w(y.o, d, b.db, d, Gy.out_wt, ldd, Gy.out_b, M, d, d, st);
     linear_bwd_x(b.db, d, Y.out_wt, ldd, b.dtmp, d, M, d, d, nullptr, 0, nullptr, 0, st);              // dtmp = dO
-    CIRS_LAUNCH(attn_bwd_kernel, dim3(B, nh), ATT_WARPS * 32, att_smem, st, L, d, nh, ep_len, y.qkv, b.dtmp, b.dqkv);
+    CIRS_LAUNCH(attn_bwd_kernel, dim3(B, nh), ATT_WARPS * 32, att_smem, st, map, d, nh, ep_len, y.qkv, b.dtmp, b.dqkv);
     CIRS_CHECK_LAUNCH();
     linear_bwd_w(xin, d, b.dqkv, 3 * d, Gy.in_wt, ld3, Gy.in_b, M, 3 * d, d, st);
     linear_bwd_x(b.dqkv, 3 * d, Y.in_wt, ld3, b.da, d, M, 3 * d, d, nullptr, 0, b.db, d, st);          // da = dX_in
   }
   // tokens: dZ -> dtmp, direct item gradient -> db
-  CIRS_LAUNCH(token_bwd_kernel, M, 64, 0, st, W, L, ep_len, b.in, b.g, b.da, b.dtok0, b.dtmp, b.db);
+  CIRS_LAUNCH(token_bwd_kernel, M, 64, 0, st, W, map, ep_len, b.in, b.g, b.da, b.dtok0, b.dtmp, b.db);
   CIRS_CHECK_LAUNCH();
   linear_bwd_w(b.in, 1 + d, b.dtmp, d, G.gate_wt, ldd, G.gate_b, M, d, 1 + d, st);
   linear_bwd_w(b.u, dui, b.dtok0, d, G.user_wt, ldd, G.user_b, B, d, dui, st);
   if (G.emb_item || G.emb_user) {
     linear_bwd_x(b.dtmp, d, W.gate_wt, ldd, b.din, 1 + d, M, d, 1 + d, nullptr, 0, nullptr, 0, st);
     linear_bwd_x(b.dtok0, d, W.user_wt, ldd, b.du, dui, B, d, dui, nullptr, 0, nullptr, 0, st);
-    CIRS_LAUNCH(emb_scatter_kernel, M, 64, 0, st, W, G, B, L, users, traj_act, ep_len, b.din, b.db, b.du);
+    CIRS_LAUNCH(emb_scatter_kernel, M, 64, 0, st, W, G, B, map, users, traj_act, ep_len, b.din, b.db, b.du);
   }
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;

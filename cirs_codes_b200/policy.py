@@ -342,7 +342,7 @@ class PPOPolicy:
                 losses_all.append(losses)
         if tracker is not None:
             tracker.zero_grad()
-            tracker.backward_from_buffer(buffer, self.d_obs, buffer.d_users)
+            tracker.backward_from_buffer(buffer, self.d_obs, buffer.d_users, tok_slot=indices)
             self._allreduce(tracker.grad)
             tracker.optim_step(self.cfg_tracker)                                     # optim_state.step(), :235
         losses = torch.cat(losses_all)

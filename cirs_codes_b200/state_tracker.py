@@ -176,16 +176,32 @@ class StateTrackerTransformer:
     def zero_grad(self):
         self.grad.zero_()
 
-    def backward_from_buffer(self, buffer, d_obs, users, obs_check=None):
-        """Accumulate d loss / d tracker-params into self.grad given d_obs[B*L, S] (zero rows = no gradient)."""
+    def backward_from_buffer(self, buffer, d_obs, users, obs_check=None, compact=True, tok_slot=None):
+        """Accumulate d loss / d tracker-params into self.grad given d_obs[B*L, S] (zero rows = no gradient).
+        ``compact``: process only the stored transitions' tokens (rows = buffer.sample_index(0)) instead of all B*L
+        padded slots."""
         lib = _lib.load()
         B, L = buffer.buffer_num, buffer.sub_size
-        need = lib.cirs_tracker_train_workspace_bytes(C.byref(self._w), B, L)
+        env_off = None
+        n_tok = 0
+        if compact:
+            lens = buffer._lengths
+            off = np.zeros(B + 1, dtype=np.int32)
+            off[1:] = np.cumsum(lens)
+            n_tok = int(off[-1])
+            env_off = torch.as_tensor(off, device=self.device)
+            if tok_slot is None:
+                tok_slot = torch.as_tensor(buffer.sample_index(0).astype(np.int32), device=self.device)
+        else:
+            tok_slot = None
+        n_rows = n_tok if compact else B * L
+        need = lib.cirs_tracker_train_workspace_bytes(C.byref(self._w), B, n_rows)
         if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
         _lib.call("cirs_tracker_train", C.byref(self._w), C.byref(self._g), B, L, _lib.ptr(users),
-                  _lib.ptr(buffer.d_act), _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_len), None, None,
-                  _lib.ptr(d_obs), _lib.ptr(obs_check), _lib.ptr(self._ws), int(need), _lib.stream())
+                  _lib.ptr(buffer.d_act), _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_len), None, None, n_tok,
+                  _lib.ptr(tok_slot), _lib.ptr(env_off), _lib.ptr(d_obs), _lib.ptr(obs_check), _lib.ptr(self._ws),
+                  int(self._ws.numel()), _lib.stream())
 
     def optim_step(self, cfg_struct):
         """optim_state.step() (core/policy/ppo.py:235): plain Adam, no clipping."""

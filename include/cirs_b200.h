@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CIRS_ABI_VERSION 3
+#define CIRS_ABI_VERSION 4
 #define CIRS_MAX_LAYERS 4
 #define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
 
@@ -134,13 +134,17 @@ int cirs_tracker_step(const cirs_tracker_weights* w, int32_t n_env, int32_t n_ro
  *   d_obs[B*L, dim_state]                                  upstream gradient per buffer slot (e*L + p)
  *   grads                                                  same layout as w; ACCUMULATED into (zero it first)
  *   workspace / workspace_bytes                            cirs_tracker_train_workspace_bytes(...) bytes
- * dense_user[B, d_user_in] / dense_item[B, L, d_item_in] replace users / traj_act when the tables are NULL. */
-int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_t n_env, int32_t traj_len);
+ * dense_user[B, d_user_in] / dense_item[B, L, d_item_in] replace users / traj_act when the tables are NULL.
+ * Compact mode (tok_slot != NULL): only the n_tok valid tokens are processed.  tok_slot[i] = buffer slot of compact
+ * row i (env-major sorted, i.e. VectorReplayBuffer.sample_index(0)), env_off[e] = first compact row of environment e
+ * (exclusive prefix sum of ep_len, B + 1 entries).  Without it every [B*L] slot is a row and padding is masked.
+ * obs_check (optional, [B*L, dim_state]) receives the forward pass's decoded states at their buffer slots. */
+int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_t n_env, int64_t n_rows);
 int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights* grads, int32_t n_env,
                        int32_t traj_len, const int32_t* users, const int32_t* traj_act, const float* traj_rew,
-                       const int32_t* ep_len, const float* dense_user, const float* dense_item,
-                       const float* d_obs, float* obs_check, void* workspace, int64_t workspace_bytes,
-                       void* stream);
+                       const int32_t* ep_len, const float* dense_user, const float* dense_item, int32_t n_tok,
+                       const int32_t* tok_slot, const int32_t* env_off, const float* d_obs, float* obs_check,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ policy / value heads ---------------- */
 typedef struct {

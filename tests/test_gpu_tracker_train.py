@@ -25,8 +25,9 @@ def _replay(H, z, c, it, trk, pol):
     return buf, res
 
 
+@pytest.mark.parametrize("compact", [True, False])
 @pytest.mark.parametrize("name", G.KUAISHOU_CASES)
-def test_tracker_train_forward_and_grads_vs_autograd(H, name):
+def test_tracker_train_forward_and_grads_vs_autograd(H, name, compact):
     """One full-sequence pass: (a) its decoded states equal the states the rollout stored; (b) the parameter
     gradients for a random upstream d_obs equal torch autograd through the oracle's encoder."""
     from oracle import nets
@@ -45,7 +46,7 @@ def test_tracker_train_forward_and_grads_vs_autograd(H, name):
     d_dobs = torch.tensor(d_obs, device="cuda")
     check = torch.zeros(B * L, S, device="cuda")
     trk.zero_grad()
-    trk.backward_from_buffer(buf, d_dobs, buf.d_users, obs_check=check)
+    trk.backward_from_buffer(buf, d_dobs, buf.d_users, obs_check=check, compact=compact)
     torch.cuda.synchronize()
     idx = buf.sample_index(0)
     it = torch.as_tensor(idx, device="cuda")
