@@ -281,6 +281,7 @@ def gpu_arm(args, cfg):
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
         col.use_graph = False          # per-kernel events need real launches, not a graph replay
+        col.persistent = bool(args.profile_persistent)
         for _ in range(2):
             one_step(rng.integers(0, cfg["U"], size=B), False)
         lib.cirs_profile_enable(1)
@@ -296,6 +297,8 @@ def gpu_arm(args, cfg):
         A, S = cfg["I"], REF["dim_state"]
         head_flops = 2.0 * (S * 64 + 64 * 64 + 64 * A)
         algo = {  # algorithmic work over the profiled pass, per kernel (DESIGN.md "kernels")
+            # the persistent rollout kernel = K3 (head contraction) + K1 + K2 for every env-step of the collect
+            "rollout_kuaishou_kernel": ("tensor", head_flops * n_tr),
             "kuaishou_step_kernel": ("hbm", k1_bytes(lens_p, cfg["N"])),
             "actor_head_kernel": ("tensor", head_flops * n_tr * (1 + 1) + 2.0 * (S * 64 + 64 * 64) * n_tr),
             "head_logits_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
@@ -352,6 +355,9 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout", default="persistent", choices=["persistent", "graph", "eager"])
+    ap.add_argument("--profile-persistent", type=int, default=1,
+                    help="profile pass: 1 = persistent rollout kernel, 0 = per-turn kernels")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.envs:

@@ -72,6 +72,10 @@ PROTOTYPES = {
     "cirs_actor_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp, fp,
                                 fp, fp]),
     "cirs_policy_eval": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp, fp]),
+    "cirs_rollout_workspace_bytes": (i64, [i32, i32]),
+    "cirs_rollout_kuaishou": (i32, [P(KuaishouEnvStruct), P(TrackerWeightsStruct), P(PolicyWeightsStruct), fp, fp, fp,
+                                    fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, fp, fp, u64, fp, i32, i32, i32,
+                                    fp, fp]),
     "cirs_compute_returns": (i32, [i32, i32, fp, fp, fp, fp, fp, f64, f64, fp, fp, fp, fp, fp, fp]),
     "cirs_rms_update": (i32, [fp, fp, fp]),
     "cirs_adv_stats": (i32, [i32, fp, fp, fp, fp, fp]),

@@ -12,11 +12,14 @@ Two execution paths with identical results:
   * fused    -- when env, tracker, policy and buffer are this package's device-resident objects and
                n_episode == env_num: per turn three kernel launches (actor sample -> env step -> tracker step)
                on per-slot device arrays with an ``active`` mask; trajectories are written by the kernels straight
-               into the replay buffer's env-major slots.  The whole rollout (reset, user token, max_turn turns) is
-               captured once into a CUDA graph and replayed with ONE launch per collect (the sampler's Philox
-               counter lives on the device); without graphs the host issues the turns and stops through a
-               non-blocking poll of "how many environments are still running".
+               into the replay buffer's env-major slots.  Three launch strategies, same device code and results:
+               ``persistent`` (default) -- the whole rollout is ONE cooperative kernel with grid-wide barriers
+               between the phases of a turn, ending when a device counter says every episode is over;
+               ``use_graph`` -- reset, user token and max_turn turns captured once into a CUDA graph and replayed
+               (the sampler's Philox counter lives on the device); otherwise the host issues the turns and stops
+               through a non-blocking poll of "how many environments are still running".
 """
+import ctypes as C
 import time
 
 import numpy as np
@@ -30,7 +33,7 @@ from .state_tracker import StateTrackerTransformer
 
 class Collector:
     def __init__(self, policy, env, buffer=None, preprocess_fn=None, exploration_noise=False,
-                 remove_recommended_ids=False, force_length=0, fused=True, use_graph=True):
+                 remove_recommended_ids=False, force_length=0, fused=True, use_graph=True, persistent=True):
         self.policy, self.env = policy, env
         self.env_num = len(env)
         self.exploration_noise = exploration_noise
@@ -47,7 +50,8 @@ class Collector:
                           and isinstance(self.tracker, StateTrackerTransformer)
                           and hasattr(policy, "sample_device") and isinstance(buffer, VectorReplayBuffer)
                           and buffer.buffer_num == self.env_num and not remove_recommended_ids)
-        self.use_graph = bool(use_graph)      # replay the fused rollout from one captured CUDA graph
+        self.persistent = bool(persistent)    # fused rollout as ONE persistent cooperative kernel (csrc/rollout.cu)
+        self.use_graph = bool(use_graph)      # else: replay the per-turn kernels from one captured CUDA graph
         self.data = Batch()
         self.h2d_bytes = self.d2h_bytes = 0   # host<->device traffic of the last fused collect()
         self.reset_stat()
@@ -169,6 +173,8 @@ class Collector:
                            cur=torch.zeros(B, trk.dim_state, dtype=torch.float32, device=dev),
                            d_users=z(torch.int32), rng=torch.zeros(1, dtype=torch.int64, device=dev),
                            ws=pol.actor_workspace(B),
+                           ws_roll=torch.empty(_lib.load().cirs_rollout_workspace_bytes(B, pol.n_action),
+                                               dtype=torch.uint8, device=dev),
                            pin=torch.zeros(2 * T + 8, dtype=torch.int32).pin_memory(),
                            pin_users=torch.zeros(B, dtype=torch.int32).pin_memory(),
                            ev=[torch.cuda.Event() for _ in range(2 * T + 8)])
@@ -221,7 +227,19 @@ class Collector:
         self.data = Batch()
         buf.reset()
         max_steps = self.force_length if self.force_length > 0 else T
-        if self.use_graph:
+        if self.persistent:
+            # the whole rollout in ONE persistent cooperative kernel (csrc/rollout.cu)
+            pol = self.policy
+            mode = 1 if (pol._deterministic_eval and not pol.training) else 0
+            _lib.call("cirs_rollout_kuaishou", C.byref(env._struct), C.byref(trk._w), C.byref(pol._w),
+                      _lib.ptr(f["d_users"]), _lib.ptr(env.active), _lib.ptr(f["act"]), _lib.ptr(f["logp"]),
+                      _lib.ptr(f["value"]), _lib.ptr(f["cur"]), _lib.ptr(env.rew), _lib.ptr(env.done), L,
+                      _lib.ptr(buf.obs), _lib.ptr(buf.obs_next), _lib.ptr(buf.d_act), _lib.ptr(buf.d_rew),
+                      _lib.ptr(buf.d_done), _lib.ptr(buf.d_len), _lib.ptr(trk.kcache), _lib.ptr(trk.vcache),
+                      pol.seed, _lib.ptr(f["rng"]), mode, max_steps, self.force_length, _lib.ptr(f["ws_roll"]),
+                      _lib.stream())
+            buf.d_users.copy_(f["d_users"])
+        elif self.use_graph:
             if self._graph is None:
                 self._rollout_body(max_steps, poll=False)           # eager warm-up (function attributes, allocations)
                 torch.cuda.synchronize()

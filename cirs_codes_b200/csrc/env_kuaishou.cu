@@ -7,10 +7,10 @@
 // the windowed category-overlap exit test, (c) its vote in the repeat count.  Warp shuffles / ballots reduce.
 // Algorithmic HBM bytes per env-step:  57 + 20*w(t,N) + 8*t  (gathered-distance variant)
 // or 57 + 20*w + 20*t (distance recomputed from the category masks, the default).
-#include "common.cuh"
-#include "../../include/cirs_b200.h"
+#include "env_dev.cuh"
 
 namespace {
+using namespace cirs_env;
 
 constexpr int WARPS_PER_CTA = 4;
 
@@ -20,113 +20,22 @@ kuaishou_reset_kernel(cirs_kuaishou_env E, int n_rows, const int32_t* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * WARPS_PER_CTA + warp;
   if (k >= n_rows) return;
-  const int e = env_id ? env_id[k] : k;
-  if (lane == 0) {
-    E.user[e] = users[k];
-    E.turn[e] = 0;
-    E.cum_rew[e] = 0.0;
-    if (active) active[e] = 1;
-  }
-  for (int j = lane; j < E.max_turn; j += 32) E.hist[(size_t)e * E.max_turn + j] = 0;
-  if (E.seen) {
-    const int nw = (E.n_item + 31) >> 5;
-    for (int j = lane; j < nw; j += 32) E.seen[(size_t)e * nw + j] = 0u;
-  }
+  kuaishou_reset_warp(E, env_id ? env_id[k] : k, users[k], lane, active);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 kuaishou_step_kernel(cirs_kuaishou_env E, int n_rows, const int32_t* __restrict__ env_id,
                      uint8_t* __restrict__ active, const int32_t* __restrict__ act, float* __restrict__ rew,
                      uint8_t* __restrict__ done, int traj_len, int32_t* __restrict__ traj_act,
-                     float* __restrict__ traj_rew,
-                     uint8_t* __restrict__ traj_done, int32_t* __restrict__ ep_len, int force_length) {
+                     float* __restrict__ traj_rew, uint8_t* __restrict__ traj_done, int32_t* __restrict__ ep_len,
+                     int force_length) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * WARPS_PER_CTA + warp;
   if (k >= n_rows) return;
   const int e = env_id ? env_id[k] : k;
   if (active && !active[e]) return;
-
-  const int T = E.max_turn, N = E.num_leave_compute;
-  const int t = E.turn[e], u = E.user[e], a = act[k];
-  const uint32_t ma = __ldg(E.cat_mask + a);
-  const int32_t* hist = E.hist + (size_t)e * T;
-
-  // window of the exit test: seq[t-N : t] with Python's negative-slice wrap when t < N (kuaishouEnv.py:203)
-  int w_lo = t - N;
-  if (w_lo < 0) w_lo = max(0, 2 * t - N);
-
-  double expo = 0.0;   // exposure partial sum
-  int n_prev = 0;      // previous occurrences of a   (num_actions[a] - 1, simulated_env.py:129-132)
-  bool leave = false;
-  uint32_t bits = ma;  // categories of a still to be checked
-  for (int j0 = 0; j0 < t; j0 += 32) {
-    const int j = j0 + lane;
-    const bool valid = j < t;
-    int hj = 0;
-    uint32_t mj = 0u;
-    if (valid) {
-      hj = hist[j];
-      mj = __ldg(E.cat_mask + hj);
-    }
-    n_prev += __popc(__ballot_sync(FULL_MASK, valid && hj == a));
-    if (E.simulated && valid && E.tau > 0.f) {
-      float dist;
-      if (E.dist) {
-        dist = __ldg(E.dist + (size_t)a * E.n_item + hj);  // df_dist_small.iloc[a, hist], util.py:33-36
-      } else {
-        const int inter = __popc(ma & mj), uni = __popc(ma | mj);
-        dist = inter ? (float)uni / (float)inter : INFINITY;  // 1 / Jaccard, util.py:234-268
-      }
-      expo += (double)expf(-(float)(t - j) * dist / E.tau);  // util.py:45
-    }
-  }
-  // exit test: count_c over the window items for every category c of the action (kuaishouEnv.py:204-213).
-  // The window holds at most N items (usually inside one 32-slot chunk); its masks are L1 hits from pass one.
-  if (t > 0) {
-    while (bits) {
-      const int c = __ffs(bits) - 1;
-      bits &= bits - 1;
-      int cnt = 0;
-      for (int j0 = (w_lo & ~31); j0 < t; j0 += 32) {
-        const int j = j0 + lane;
-        bool hit = false;
-        if (j >= w_lo && j < t) hit = (__ldg(E.cat_mask + hist[j]) >> c) & 1u;
-        cnt += __popc(__ballot_sync(FULL_MASK, hit));
-      }
-      if ((float)cnt > E.leave_threshold) leave = true;
-    }
-  }
-  expo = warp_sum_d(expo);
-
-  if (lane == 0) {
-    bool d = leave || (t >= T - 1);  // kuaishouEnv.py:166-168
-    float r;
-    if (!E.simulated) {
-      r = __ldg(E.mat + (size_t)u * E.n_item + a);  // kuaishouEnv.py:171
-    } else {
-      double ex = (t == 0 || E.tau <= 0.f) ? 0.0 : expo;
-      if (E.alpha_u) ex = ex * (double)__ldg(E.alpha_u + u) * (double)__ldg(E.beta_i + a);
-      ex *= (double)E.gamma_exposure;
-      const double pr = (double)__ldg(E.normed_mat + (size_t)u * E.n_item + a);
-      double rr = (E.version == 1) ? pr / (1.0 + ex) : (pr - ex);  // clip0 is an identity, util.py:53-54
-      if (E.r_decay != 1.0f) rr *= pow((double)E.r_decay, (double)n_prev);
-      r = (float)rr;
-    }
-    if (force_length > 0) d = (t + 1 >= force_length);  // collector.py:253-258
-    if (t < T) E.hist[(size_t)e * T + t] = a;
-    E.turn[e] = t + 1;
-    E.cum_rew[e] += (double)r;
-    if (E.seen) E.seen[(size_t)e * ((E.n_item + 31) >> 5) + (a >> 5)] |= (1u << (a & 31));
-    rew[k] = r;
-    done[k] = d ? 1 : 0;
-    if (traj_act && t < traj_len) {
-      traj_act[(size_t)e * traj_len + t] = a;
-      traj_rew[(size_t)e * traj_len + t] = r;
-      traj_done[(size_t)e * traj_len + t] = d ? 1 : 0;
-    }
-    if (ep_len && d) ep_len[e] = t + 1;
-    if (active && d) active[e] = 0;
-  }
+  kuaishou_step_warp(E, e, k, act[k], lane, active, rew, done, traj_len, traj_act, traj_rew, traj_done, ep_len,
+                     force_length, nullptr);
 }
 
 }  // namespace

@@ -184,6 +184,22 @@ int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_
 int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, const int32_t* row_idx, const float* obs,
                      const int32_t* act, float* value, float* logp, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------ fused rollout ----------------------- */
+/* A whole Collector.collect(n_episode = B) (core/collector.py:147-367 with the fork's semantics: reset everything,
+ * no reset on done, finished environments dropped) in ONE persistent cooperative kernel: reset + user token, then
+ * per turn  actor head -> sample -> environment step -> tracker token -> replay-buffer slots, until every episode
+ * has ended or max_steps turns were played.  All arrays are per environment slot ([B] or [B, .]); traj_* are the
+ * replay buffer's env-major arrays (traj_len slots per environment); ep_len[e] = episode length.
+ * rng_counter: device uint64, advanced once per turn (Philox offset of the sampler).  mode: 0 sample, 1 argmax.
+ * Same device code as cirs_actor_sample / cirs_kuaishou_step / cirs_tracker_step (bit-identical results). */
+int64_t cirs_rollout_workspace_bytes(int32_t n_env, int32_t n_action);
+int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weights* tw, const cirs_policy_weights* pw,
+                          const int32_t* users, uint8_t* active, int32_t* act, float* logp, float* value,
+                          float* cur_state, float* rew, uint8_t* done, int32_t traj_len, float* traj_obs,
+                          float* traj_obs_next, int32_t* traj_act, float* traj_rew, uint8_t* traj_done,
+                          int32_t* ep_len, float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter,
+                          int32_t mode, int32_t max_steps, int32_t force_length, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------ returns (GAE) ----------------------- */
 /* A2CPolicy._compute_returns (a2c.py:80-109) + BasePolicy.compute_episodic_return / _gae_return
  * (tianshou/policy/base.py:272-313, 380-396) + RunningMeanStd.update (utils/statistics.py:80-95), float64

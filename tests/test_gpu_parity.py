@@ -347,12 +347,14 @@ def test_update_entropy_and_noclip_vs_oracle(H):
 
 
 def test_fused_collect_matches_generic(H):
-    """Device-resident fused rollout == the generic loop (argmax actions so that both are deterministic)."""
+    """Device-resident fused rollout (persistent kernel, CUDA graph, host-issued turns) == the generic loop (argmax
+    actions so that all are deterministic)."""
     import cirs_codes_b200 as cb
     z, c = H.synthetic_case(U=64, I=300, B=48, T=12, N=3, thr=1, d=32)
     users = np.random.default_rng(1).integers(0, c["U"], size=c["B"])
     outs = []
-    for fused in (True, False):
+    for fused, kw in ((True, dict(persistent=True)), (False, {}), (True, dict(persistent=False, use_graph=True)),
+                      (True, dict(persistent=False, use_graph=False))):
         env = H.make_env(z, c)
         trk = H.make_tracker(None, c)
         with torch.no_grad():
@@ -365,20 +367,24 @@ def test_fused_collect_matches_generic(H):
         pol = H.make_policy(None, c, None, deterministic_eval=True)
         pol.eval()
         buf = cb.VectorReplayBuffer(c["B"] * c["T"], c["B"])
-        col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state, fused=fused)
+        col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state, fused=fused, **kw)
         assert col.fused == fused
         res = col.collect(n_episode=c["B"], users=users)
+        if fused:   # a second collect on the same objects (graph replay / re-launch) must reproduce the first
+            res2 = col.collect(n_episode=c["B"], users=users)
+            assert np.array_equal(res["lens"], res2["lens"]) and np.allclose(res["rews"], res2["rews"])
         idx = buf.sample_index(0)
         it = torch.as_tensor(idx, device="cuda")
         outs.append(dict(res=res, lens=buf._lengths.copy(), act=buf.act[idx].copy(), rew=buf.rew[idx].copy(),
                          done=buf.done[idx].copy(), obs=buf.obs[it].cpu().numpy(),
                          obs_next=buf.obs_next[it].cpu().numpy()))
-    a, b = outs
-    assert np.array_equal(a["lens"], b["lens"]) and np.array_equal(a["act"], b["act"])
-    assert np.array_equal(a["done"], b["done"])
-    G.assert_close(a["rew"], b["rew"], 1e-6, what="rew")
-    G.assert_close(a["obs"], b["obs"], 1e-6, 1e-7, what="obs")
-    G.assert_close(a["obs_next"], b["obs_next"], 1e-6, 1e-7, what="obs_next")
-    assert a["res"]["n/st"] == b["res"]["n/st"] and np.array_equal(a["res"]["lens"], b["res"]["lens"])
-    G.assert_close(a["res"]["rews"], b["res"]["rews"], 1e-6, what="episode rewards")
-    assert a["lens"].min() >= 1 and a["lens"].max() <= c["T"]
+    b = outs[1]
+    for a in (outs[0], outs[2], outs[3]):
+        assert np.array_equal(a["lens"], b["lens"]) and np.array_equal(a["act"], b["act"])
+        assert np.array_equal(a["done"], b["done"])
+        G.assert_close(a["rew"], b["rew"], 1e-6, what="rew")
+        G.assert_close(a["obs"], b["obs"], 1e-6, 1e-7, what="obs")
+        G.assert_close(a["obs_next"], b["obs_next"], 1e-6, 1e-7, what="obs_next")
+        assert a["res"]["n/st"] == b["res"]["n/st"] and np.array_equal(a["res"]["lens"], b["res"]["lens"])
+        G.assert_close(a["res"]["rews"], b["res"]["rews"], 1e-6, what="episode rewards")
+        assert a["lens"].min() >= 1 and a["lens"].max() <= c["T"]
