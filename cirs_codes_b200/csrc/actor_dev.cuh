@@ -35,6 +35,7 @@ struct HeadArgs {
   int mode;
   const uint32_t* seen;
   const int32_t* act_in;  // MODE_EVAL: action per output index (may be NULL -> value only)
+  const float* h2_in;     // optional precomputed trunk output [id][64] (actor_trunk_warp): skips trunk and critic
   int tiles_per_split, n_split;
   Partial* part;          // [n_split, n_rows]
   float* value;
@@ -77,58 +78,70 @@ __device__ __forceinline__ void actor_head_body(const HeadArgs& P, int bx, int b
   __syncthreads();
   if (!s_any) return;
 
-  // ---- trunk: h1 = relu(W1 s + b1), h2 = relu(W2 h1 + b2)   (common.py:87-92)
-  for (int i = tid; i < BM * S; i += NT) {
-    const int r = i / S, c = i % S;
-    const int id = s_id[r];
-    float v = 0.f;
-    if (id >= 0) v = P.state[(int64_t)(P.state_by_k ? (r0 + r) : id) * P.state_stride + c];
-    s_in[r][c] = v;
-  }
-  __syncthreads();
-  {
-    const int row = tid % BM, cg = tid / BM;  // 4 column groups of 16
-    float acc[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = __ldg(P.W.b1 + cg * 16 + j);
-    for (int k = 0; k < S; ++k) {
-      const float x = s_in[row][k];
-      const float4* w = reinterpret_cast<const float4*>(P.W.w1t + (size_t)k * HID + cg * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 t = __ldg(w + j);
-        acc[4 * j] = fmaf(x, t.x, acc[4 * j]);
-        acc[4 * j + 1] = fmaf(x, t.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(x, t.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(x, t.w, acc[4 * j + 3]);
-      }
+  if (P.h2_in) {
+    // trunk already evaluated per row (persistent rollout): stage h2 k-major
+    for (int i = tid; i < BM * HID; i += NT) {
+      const int r = i / HID, k = i % HID;
+      const int id = s_id[r];
+      h2T[k][r] = id >= 0 ? P.h2_in[(size_t)id * HID + k] : 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) h1T[cg * 16 + j][row] = fmaxf(acc[j], 0.f);
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = __ldg(P.W.b2 + cg * 16 + j);
-    for (int k = 0; k < HID; ++k) {
-      const float x = h1T[k][row];
-      const float4* w = reinterpret_cast<const float4*>(P.W.w2t + (size_t)k * HID + cg * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 t = __ldg(w + j);
-        acc[4 * j] = fmaf(x, t.x, acc[4 * j]);
-        acc[4 * j + 1] = fmaf(x, t.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(x, t.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(x, t.w, acc[4 * j + 3]);
-      }
+  } else {
+    // ---- trunk: h1 = relu(W1 s + b1), h2 = relu(W2 h1 + b2)   (common.py:87-92)
+    for (int i = tid; i < BM * S; i += NT) {
+      const int r = i / S, c = i % S;
+      const int id = s_id[r];
+      float v = 0.f;
+      if (id >= 0) v = P.state[(int64_t)(P.state_by_k ? (r0 + r) : id) * P.state_stride + c];
+      s_in[r][c] = v;
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) h2T[cg * 16 + j][row] = fmaxf(acc[j], 0.f);
     __syncthreads();
-  }
-  // ---- critic: V = wv . h2 + bv   (discrete.py:109-114); written once (split 0)
-  if (split == 0 && P.value && tid < BM && s_id[tid] >= 0) {
-    float v = __ldg(P.W.bv);
-    for (int k = 0; k < HID; ++k) v = fmaf(h2T[k][tid], __ldg(P.W.wv + k), v);
-    P.value[P.out_by_k ? (r0 + tid) : s_id[tid]] = v;
+    {
+      const int row = tid % BM, cg = tid / BM;  // 4 column groups of 16
+      float acc[16];
+  #pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = __ldg(P.W.b1 + cg * 16 + j);
+#pragma unroll 4
+      for (int k = 0; k < S; ++k) {
+        const float x = s_in[row][k];
+        const float4* w = reinterpret_cast<const float4*>(P.W.w1t + (size_t)k * HID + cg * 16);
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = __ldg(w + j);
+          acc[4 * j] = fmaf(x, t.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(x, t.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(x, t.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(x, t.w, acc[4 * j + 3]);
+        }
+      }
+  #pragma unroll
+      for (int j = 0; j < 16; ++j) h1T[cg * 16 + j][row] = fmaxf(acc[j], 0.f);
+      __syncthreads();
+  #pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = __ldg(P.W.b2 + cg * 16 + j);
+#pragma unroll 4
+      for (int k = 0; k < HID; ++k) {
+        const float x = h1T[k][row];
+        const float4* w = reinterpret_cast<const float4*>(P.W.w2t + (size_t)k * HID + cg * 16);
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = __ldg(w + j);
+          acc[4 * j] = fmaf(x, t.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(x, t.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(x, t.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(x, t.w, acc[4 * j + 3]);
+        }
+      }
+  #pragma unroll
+      for (int j = 0; j < 16; ++j) h2T[cg * 16 + j][row] = fmaxf(acc[j], 0.f);
+      __syncthreads();
+    }
+    // ---- critic: V = wv . h2 + bv   (discrete.py:109-114); written once (split 0)
+    if (split == 0 && P.value && tid < BM && s_id[tid] >= 0) {
+      float v = __ldg(P.W.bv);
+      for (int k = 0; k < HID; ++k) v = fmaf(h2T[k][tid], __ldg(P.W.wv + k), v);
+      P.value[P.out_by_k ? (r0 + tid) : s_id[tid]] = v;
+    }
   }
   if (P.mode == MODE_EVAL && P.act_in == nullptr) return;  // value only
 
@@ -271,6 +284,77 @@ __device__ __forceinline__ int actor_combine_row(const HeadArgs& P, int k, int32
   return bi;
 }
 
+
+// Trunk + critic of ONE row by one warp, in exactly the operation order of the tile version above (bias first, k
+// ascending, fmaf), so both produce bit-identical h2.  s: the row's state (dim_state floats); sh: >= 160 floats of
+// this warp's shared memory; h2_out: 64 floats (global).
+__device__ __forceinline__ void actor_trunk_warp(const cirs_policy_weights& W, const float* __restrict__ s, int lane,
+                                                 float* sh, float* __restrict__ h2_out, float* __restrict__ value_out) {
+  const int S = W.dim_state;
+  float* sx = sh;         // [32]
+  float* h1 = sh + 32;    // [64]
+  float* h2 = sh + 96;    // [64]
+  if (lane < S) sx[lane] = s[lane];
+  __syncwarp();
+  float a0 = __ldg(W.b1 + lane), a1 = __ldg(W.b1 + lane + 32);
+#pragma unroll 4
+  for (int k = 0; k < S; ++k) {
+    const float x = sx[k];
+    a0 = fmaf(x, __ldg(W.w1t + (size_t)k * HID + lane), a0);
+    a1 = fmaf(x, __ldg(W.w1t + (size_t)k * HID + lane + 32), a1);
+  }
+  h1[lane] = fmaxf(a0, 0.f);
+  h1[lane + 32] = fmaxf(a1, 0.f);
+  __syncwarp();
+  a0 = __ldg(W.b2 + lane); a1 = __ldg(W.b2 + lane + 32);
+#pragma unroll 16
+  for (int k = 0; k < HID; ++k) {
+    const float x = h1[k];
+    a0 = fmaf(x, __ldg(W.w2t + (size_t)k * HID + lane), a0);
+    a1 = fmaf(x, __ldg(W.w2t + (size_t)k * HID + lane + 32), a1);
+  }
+  a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
+  h2[lane] = a0; h2[lane + 32] = a1;
+  h2_out[lane] = a0; h2_out[lane + 32] = a1;
+  __syncwarp();
+  if (lane == 0 && value_out) {
+    float v = __ldg(W.bv);
+    for (int k = 0; k < HID; ++k) v = fmaf(h2[k], __ldg(W.wv + k), v);
+    *value_out = v;
+  }
+  __syncwarp();
+}
+
+// warp-parallel merge of the catalogue splits of row k (all 32 lanes call it; every lane returns the action)
+__device__ __forceinline__ int actor_combine_warp(const HeadArgs& P, int k, int lane, int32_t* __restrict__ act,
+                                                  float* __restrict__ logp) {
+  const int id = P.gather ? P.gather[k] : k;
+  float m = -INFINITY, z = 0.f, bs = -INFINITY, bl = 0.f;
+  int bi = 0x7fffffff;
+  for (int s = lane; s < P.n_split; s += 32) {
+    const Partial p = P.part[(size_t)s * P.n_rows + k];
+    merge_ms(m, z, p.m, p.z);
+    merge_best(bs, bl, bi, p.best_s, p.best_l, p.best_i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(FULL_MASK, m, o), z2 = __shfl_xor_sync(FULL_MASK, z, o);
+    const float s2 = __shfl_xor_sync(FULL_MASK, bs, o), l2 = __shfl_xor_sync(FULL_MASK, bl, o);
+    const int i2 = __shfl_xor_sync(FULL_MASK, bi, o);
+    merge_ms(m, z, m2, z2);
+    merge_best(bs, bl, bi, s2, l2, i2);
+  }
+  if (lane == 0) {
+    const int o = P.out_by_k ? k : id;
+    if (act) act[o] = bi;
+    if (logp) {
+      float pa = expf(bl - m) / z;
+      pa = fminf(fmaxf(pa, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS);
+      logp[o] = (bs == -INFINITY) ? logf(CATEGORICAL_EPS) : logf(pa);
+    }
+  }
+  return bi;
+}
 
 inline int pick_split(int n_rows, int n_action, int target_ctas = 2 * 148) {
   const int row_tiles = (n_rows + BM - 1) / BM, n_tiles = (n_action + BN - 1) / BN;

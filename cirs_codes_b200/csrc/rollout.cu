@@ -25,6 +25,12 @@ namespace cg = cooperative_groups;
 namespace {
 using namespace cirs_actor;
 
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct RolloutArgs {
   cirs_kuaishou_env E;
   cirs_tracker_weights T;
@@ -44,64 +50,143 @@ struct RolloutArgs {
   int32_t* ep_len;
   float *kcache, *vcache;
   int* n_active;            // device counter of running environments
+  int* count;               // [2] length of the compact list of turn t (index t & 1)
+  int32_t* list;            // [2, B] environments still running at turn t
+  float* h2;                // [B, 64] trunk output of the current state of every environment
+  const float* w_lo;        // tracker weights (everything but the embedding tables): start and float count
+  int w_count;
+  int smem_w_off;           // float offset of the staged weights inside dynamic shared memory
+  long long* dbg;           // [1 + 3 * max_steps] turns played, then per turn {n_active, ns phase A, ns phase B}
   int scratch_per_warp;
 };
 
-__global__ void __launch_bounds__(NT, 2) rollout_kuaishou_kernel(RolloutArgs A) {
+// SMW: the tracker's weights are staged once in shared memory (they are re-read by every warp at every turn; from L2
+// each token is ~55 dependent round trips of ~0.6 us, from shared memory ~20x less)
+template <bool SMW>
+__global__ void __launch_bounds__(NT, SMW ? 1 : 2) rollout_kuaishou_kernel(RolloutArgs A) {
   extern __shared__ __align__(16) float smem_dyn[];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warps_per_cta = NT / 32;
   const int gwarp = blockIdx.x * warps_per_cta + warp, n_warps = gridDim.x * warps_per_cta;
-  const int B = A.n_env, S = A.T.dim_state;
+  const int B = A.n_env;
   float* scratch = smem_dyn + (size_t)warp * A.scratch_per_warp;
+  if (SMW) {
+    float* wsm = smem_dyn + A.smem_w_off;
+    for (int i = tid; i < A.w_count / 4; i += NT)
+      reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(A.w_lo) + i);
+    const ptrdiff_t shift = wsm - A.w_lo;   // rebase every weight pointer into the staged copy
+    A.T.user_wt += shift; A.T.user_b += shift; A.T.gate_wt += shift; A.T.gate_b += shift;
+    A.T.dec_wt += shift; A.T.dec_b += shift;
+    for (int l = 0; l < A.T.nlayers; ++l) {
+      cirs_encoder_layer& Y = A.T.layer[l];
+      Y.in_wt += shift; Y.in_b += shift; Y.out_wt += shift; Y.out_b += shift; Y.l1_wt += shift; Y.l1_b += shift;
+      Y.l2_wt += shift; Y.l2_b += shift; Y.n1_w += shift; Y.n1_b += shift; Y.n2_w += shift; Y.n2_b += shift;
+    }
+    __syncthreads();
+  }
 
-  // ---- reset + user token (position 0)
-  if (blockIdx.x == 0 && tid == 0) *A.n_active = B;
+  // ---- reset + user token (position 0); every environment starts in the compact list of turn 0
+  if (blockIdx.x == 0 && tid == 0) {
+    *A.n_active = B;
+    A.count[0] = B;
+    A.count[1] = 0;
+  }
   for (int e = gwarp; e < B; e += n_warps) {
     const int u = A.users[e];
     cirs_env::kuaishou_reset_warp(A.E, e, u, lane, A.active);
-    if (lane == 0) A.ep_len[e] = 0;
-    cirs_tracker::tracker_token_warp(A.T, B, e, e, 0, u, nullptr, 0.f, A.kcache, A.vcache, scratch, lane, nullptr, 0,
+    if (lane == 0) {
+      A.ep_len[e] = 0;
+      A.list[e] = e;
+    }
+    cirs_tracker::tracker_token_warp<SMW>(A.T, B, e, e, 0, u, nullptr, 0.f, A.kcache, A.vcache, scratch, lane, nullptr, 0,
                                      A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
+    __syncwarp();
+    actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, scratch, A.h2 + (size_t)e * HID,
+                     A.value + e);
   }
   __threadfence();
   grid.sync();
 
-  const int row_tiles = (B + BM - 1) / BM, n_items = row_tiles * A.H.n_split;
+  const int n_col_tiles = (A.H.W.n_action + BN - 1) / BN;
   for (int t = 0; t < A.max_steps; ++t) {
-    // ---- phase A: actor head partials
+    // the environments still running, as a compact row list built during the previous turn (order is arbitrary:
+    // every row's result is independent of its tile, and the Philox counter is keyed by the environment id)
+    const int n_act = *reinterpret_cast<volatile int*>(A.count + (t & 1));
+    if (n_act <= 0) break;
+    const bool timer = blockIdx.x == 0 && tid == 0;
+    long long t0 = 0, t1 = 0;
+    if (timer) t0 = gtime_ns();
+    HeadArgs H = A.H;
+    H.n_rows = n_act;
+    H.gather = A.list + (size_t)(t & 1) * B;
+    const int row_tiles = (n_act + BM - 1) / BM;
+    int n_split = gridDim.x / row_tiles;
+    n_split = n_split < 1 ? 1 : (n_split > n_col_tiles ? n_col_tiles : n_split);
+    H.tiles_per_split = (n_col_tiles + n_split - 1) / n_split;
+    H.n_split = (n_col_tiles + H.tiles_per_split - 1) / H.tiles_per_split;
+    // ---- phase A: actor head partials over the compact rows
+    const int n_items = row_tiles * H.n_split;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      actor_head_body(A.H, w % row_tiles, w / row_tiles, smem_dyn);
+      actor_head_body(H, w % row_tiles, w / row_tiles, smem_dyn);
       __syncthreads();
     }
     __threadfence();
     grid.sync();
-    // ---- phase B: one warp per environment
-    for (int e = gwarp; e < B; e += n_warps) {
-      if (!A.active[e]) continue;
-      int a = 0;
-      if (lane == 0) a = actor_combine_row(A.H, e, A.act, A.logp);
-      a = __shfl_sync(FULL_MASK, a, 0);
-      cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len, A.traj_act, A.traj_rew,
-                                   A.traj_done, A.ep_len, A.force_length, A.n_active);
+    if (timer) t1 = gtime_ns();
+    // ---- phase B: one warp per running environment
+    int32_t* list_next = A.list + (size_t)((t + 1) & 1) * B;
+    for (int k = gwarp; k < n_act; k += n_warps) {
+      const int e = H.gather[k];
+      const bool sub = timer && k == 0;   // sub-phase timers of the first environment of block 0 / warp 0
+      long long s0 = 0, s1 = 0, s2 = 0;
+      if (sub) s0 = gtime_ns();
+      const int a = actor_combine_warp(H, k, lane, A.act, A.logp);
+      if (sub) s1 = gtime_ns();
+      const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len, A.traj_act,
+                                                  A.traj_rew, A.traj_done, A.ep_len, A.force_length, A.n_active);
+      if (lane == 0 && !d) {
+        const int kn = atomicAdd(A.count + ((t + 1) & 1), 1);
+        list_next[kn] = e;
+      }
       __syncwarp();
+      if (sub) s2 = gtime_ns();
       const float r = A.rew[e];
-      cirs_tracker::tracker_token_warp(A.T, B, e, e, t + 1, a, nullptr, r, A.kcache, A.vcache, scratch, lane, nullptr,
+      cirs_tracker::tracker_token_warp<SMW>(A.T, B, e, e, t + 1, a, nullptr, r, A.kcache, A.vcache, scratch, lane, nullptr,
                                        0, A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
+      if (!d) {   // trunk + critic of the new state, consumed by the next turn's head phase
+        __syncwarp();
+        actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, scratch, A.h2 + (size_t)e * HID,
+                         A.value + e);
+      }
+      if (sub) {
+        long long* q = A.dbg + 1 + 3 * 512 + 3 * t;
+        q[0] = s1 - s0; q[1] = s2 - s1; q[2] = gtime_ns() - s2;
+      }
     }
-    if (blockIdx.x == 0 && tid == 0 && A.H.rng_counter) *A.H.rng_counter += 1ull;
+    if (blockIdx.x == 0 && tid == 0) {
+      A.count[t & 1] = 0;   // consumed; it becomes the append counter of turn t + 1's phase B
+      if (A.H.rng_counter) *A.H.rng_counter += 1ull;
+    }
     __threadfence();
     grid.sync();
-    if (*reinterpret_cast<volatile int*>(A.n_active) <= 0) break;
+    if (timer) {
+      A.dbg[0] = t + 1;
+      A.dbg[1 + 3 * t] = n_act;
+      A.dbg[2 + 3 * t] = t1 - t0;
+      A.dbg[3 + 3 * t] = gtime_ns() - t1;
+    }
   }
 }
 
 }  // namespace
 
-// workspace: head partials for (n_split + 1) * n_env rows + the running-environment counter
+// workspace: [counters 256 B][phase timers][list 2*B i32][h2 B*64 f32][head partials]
+constexpr int64_t DBG_BYTES = 8 * (1 + 6 * 512);   // phase timers of up to 512 turns
+static int64_t partial_capacity(int32_t n_env) { return ((int64_t)n_env + 64) * 96 + 64 * 1024; }
 extern "C" int64_t cirs_rollout_workspace_bytes(int32_t n_env, int32_t n_action) {
-  return cirs_actor_workspace_bytes(n_env, n_action) + (int64_t)sizeof(Partial) * 64 * (int64_t)n_env + 256;
+  (void)n_action;
+  return 256 + DBG_BYTES + (int64_t)sizeof(int32_t) * 2 * n_env + 64 + (int64_t)sizeof(float) * HID * n_env + 64 + (int64_t)sizeof(Partial) * partial_capacity(n_env);
 }
 
 extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weights* tw,
@@ -117,12 +202,11 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     return CIRS_ERR_ARG;
   }
   if (!tw->emb_user || !tw->emb_item || tw->d % tw->nhead != 0 || tw->nlayers > CIRS_MAX_LAYERS ||
-      tw->d_item_in != tw->d || tw->d_user_in != tw->d || max_steps + 1 > tw->max_len) {
+      tw->d_item_in != tw->d || tw->d_user_in != tw->d || max_steps + 1 > tw->max_len || max_steps > 512) {
     cirs_set_error("cirs_rollout_kuaishou: unsupported tracker shape (needs embedding tables, max_steps < max_len)");
     return CIRS_ERR_ARG;
   }
   if (env->n_env <= 0) return CIRS_OK;
-  static int max_ctas = 0, n_sm = 0;
   const int per_warp = cirs_tracker::tracker_scratch_floats(*tw);
   size_t smem = SMEM_BYTES;
   if ((size_t)per_warp * (NT / 32) * sizeof(float) > smem) smem = (size_t)per_warp * (NT / 32) * sizeof(float);
@@ -130,49 +214,72 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     cirs_set_error("cirs_rollout_kuaishou: shared memory budget exceeded");
     return CIRS_ERR_ARG;
   }
+  RolloutArgs A{};
+  // stage the tracker weights in shared memory when they fit next to the head's tiles (d = 32: 113 KB + 77 KB)
+  constexpr size_t SMEM_MAX = 224 * 1024;
+  const float* w_lo = tw->user_wt;
+  const int64_t w_count = tw->flat ? (tw->flat + tw->n_flat) - w_lo : 0;
+  bool smw = tw->flat != nullptr && w_count > 0 && (w_count % 4) == 0 && ((uintptr_t)w_lo % 16) == 0 &&
+             smem + (size_t)w_count * sizeof(float) <= SMEM_MAX && tw->dec_b >= w_lo && tw->dec_b < w_lo + w_count &&
+             tw->gate_wt >= w_lo;
+  for (int l = 0; smw && l < tw->nlayers; ++l)
+    smw = tw->layer[l].in_wt >= w_lo && tw->layer[l].n2_b < w_lo + w_count;
+  if (smw) {
+    A.w_lo = w_lo; A.w_count = (int)w_count; A.smem_w_off = (int)(smem / sizeof(float));
+    smem += (size_t)w_count * sizeof(float);
+  }
+  static int max_ctas_v[2] = {0, 0};
+  int& max_ctas = max_ctas_v[smw ? 1 : 0];
   if (!max_ctas) {
-    int dev = 0, per_sm = 0;
+    int dev = 0, per_sm = 0, n_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(rollout_kuaishou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel, NT, smem);
+    if (smw) {
+      cudaFuncSetAttribute(rollout_kuaishou_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true>, NT, smem);
+    } else {
+      cudaFuncSetAttribute(rollout_kuaishou_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<false>, NT, smem);
+    }
     if (per_sm < 1) {
       cirs_set_error("cirs_rollout_kuaishou: kernel does not fit on an SM");
       return CIRS_ERR_CUDA;
     }
     max_ctas = per_sm * n_sm;
   }
-  RolloutArgs A{};
   A.E = *env; A.T = *tw;
-  A.H.W = *pw; A.H.n_rows = env->n_env; A.H.gather = nullptr; A.H.state_by_k = 0; A.H.out_by_k = 1;
+  A.H.W = *pw; A.H.n_rows = env->n_env; A.H.gather = nullptr; A.H.state_by_k = 0; A.H.out_by_k = 0;
   A.H.active = active; A.H.state = cur_state; A.H.state_stride = tw->dim_state; A.H.noise_q = nullptr;
   A.H.seed = seed; A.H.offset = 1ull << 40; A.H.rng_counter = reinterpret_cast<unsigned long long*>(rng_counter);
   A.H.mode = mode; A.H.seen = nullptr; A.H.act_in = nullptr; A.H.value = value;
   int grid = max_ctas;
-  if (!plan_head(A.H, grid) || A.H.n_split > 64) {
+  if (!plan_head(A.H, grid)) {
     cirs_set_error("cirs_rollout_kuaishou: unsupported head shape");
     return CIRS_ERR_ARG;
   }
-  A.H.part = reinterpret_cast<Partial*>(workspace);
-  A.n_active = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) +
-                                      sizeof(Partial) * (size_t)(A.H.n_split + 1) * env->n_env);
-  A.n_active = reinterpret_cast<int*>(((uintptr_t)A.n_active + 63) & ~(uintptr_t)63);
+  // per turn: row_tiles * n_split <= grid work items of 64 rows each, n_split <= 84 column tiles
+  char* wsp = reinterpret_cast<char*>(workspace);
+  A.n_active = reinterpret_cast<int*>(wsp);
+  A.count = reinterpret_cast<int*>(wsp + 64);
+  A.dbg = reinterpret_cast<long long*>(wsp + 256);
+  A.list = reinterpret_cast<int32_t*>(wsp + 256 + DBG_BYTES);
+  A.h2 = reinterpret_cast<float*>(((uintptr_t)(A.list + 2 * (size_t)env->n_env) + 63) & ~(uintptr_t)63);
+  A.H.h2_in = A.h2;
+  A.H.part = reinterpret_cast<Partial*>(((uintptr_t)(A.h2 + (size_t)env->n_env * HID) + 63) & ~(uintptr_t)63);
+  if ((int64_t)(grid + 96) * BM > partial_capacity(env->n_env)) {
+    cirs_set_error("cirs_rollout_kuaishou: workspace too small for this grid");
+    return CIRS_ERR_ARG;
+  }
   A.n_env = env->n_env; A.max_steps = max_steps; A.force_length = force_length; A.traj_len = traj_len;
   A.users = users; A.active = active; A.act = act; A.logp = logp; A.value = value; A.cur_state = cur_state;
   A.rew = rew; A.done = done; A.traj_obs = traj_obs; A.traj_obs_next = traj_obs_next; A.traj_act = traj_act;
   A.traj_rew = traj_rew; A.traj_done = traj_done; A.ep_len = ep_len; A.kcache = kcache; A.vcache = vcache;
   A.scratch_per_warp = per_warp;
-  // no more CTAs than there is work for (warps for phase B, work items for phase A)
-  const int row_tiles = (env->n_env + BM - 1) / BM;
-  int need = row_tiles * A.H.n_split;
-  const int need_b = (env->n_env + NT / 32 - 1) / (NT / 32);
-  if (need_b > need) need = need_b;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
   void* params[] = {&A};
   const bool prof = cirs_profile_begin("rollout_kuaishou_kernel", (cudaStream_t)stream);
-  cudaError_t err = cudaLaunchCooperativeKernel((void*)rollout_kuaishou_kernel, dim3(grid), dim3(NT), params, smem,
-                                                (cudaStream_t)stream);
+  cudaError_t err = cudaLaunchCooperativeKernel(
+      smw ? (void*)rollout_kuaishou_kernel<true> : (void*)rollout_kuaishou_kernel<false>, dim3(grid), dim3(NT), params,
+      smem, (cudaStream_t)stream);
   cirs_note_launch();
   if (prof) cirs_profile_end((cudaStream_t)stream);
   if (err != cudaSuccess) {

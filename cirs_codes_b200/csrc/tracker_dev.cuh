@@ -8,40 +8,66 @@ namespace cirs_tracker {
 
 
 
-template <int NK>
-__device__ __forceinline__ void matvec_chunk(const float* __restrict__ wp, const float* __restrict__ x, int n_in,
-                                             int ldo, float (&acc)[4]) {
-#pragma unroll 4
-  for (int i = 0; i < n_in; ++i) {
-    const float xi = x[i];
-    const float* w = wp + (size_t)i * ldo;
-#pragma unroll
-    for (int k = 0; k < NK; ++k) acc[k] = fmaf(__ldg(w + 32 * k), xi, acc[k]);
-  }
+// weight loads: global memory through the read-only path, or plain loads when the caller staged the weights in
+// shared memory (persistent rollout kernel, when they fit)
+template <bool SM>
+__device__ __forceinline__ float ldw(const float* p) {
+  if (SM) return *p;
+  return __ldg(p);
+}
+
+template <bool SM>
+__device__ __forceinline__ float4 ldw4(const float* p) {
+  if (SM) return *reinterpret_cast<const float4*>(p);
+  return __ldg(reinterpret_cast<const float4*>(p));
 }
 
 // y[o] = act(b[o] + sum_i Wt[i][o] * x[i]) for o < n_out.  x, y in shared memory (y != x).
-// act: 0 identity, 1 relu, 2 sigmoid
+// act: 0 identity, 1 relu, 2 sigmoid.
+// Lane mapping: a chunk of up to 128 outputs is 32 "quads" of 4 consecutive outputs; with nq quads in the chunk the
+// warp forms G = 32 / P groups (P = nq rounded up to a power of two): lane (g, q) accumulates quad q over the
+// inputs i = g, g + G, ... with ONE 16-byte weight load per 4 FMAs, and the groups are summed with xor-shuffles.
+// This cuts the instruction count per token ~5x against one-output-per-lane scalar loads (the single resident warp
+// per scheduler is issue/latency bound, not bandwidth bound).
+template <bool SM>
 __device__ __forceinline__ void matvec(const float* __restrict__ Wt, const float* __restrict__ b, const float* x,
                                        int n_in, int n_out, int ldo, float* y, int lane, int act) {
   for (int o0 = 0; o0 < n_out; o0 += 128) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int nk = min(4, (ldo - o0) >> 5);
-    const float* wp = Wt + o0 + lane;
-    switch (nk) {
-      case 1: matvec_chunk<1>(wp, x, n_in, ldo, acc); break;
-      case 2: matvec_chunk<2>(wp, x, n_in, ldo, acc); break;
-      case 3: matvec_chunk<3>(wp, x, n_in, ldo, acc); break;
-      default: matvec_chunk<4>(wp, x, n_in, ldo, acc); break;
+    const int nq = min(32, (n_out - o0 + 3) >> 2);
+    const int P = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 16 ? 16 : 32;
+    const int G = 32 / P, q = lane & (P - 1), g = lane / P;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nq) {
+      const float* w = Wt + o0 + 4 * q + (size_t)g * ldo;
+      const int step = G * ldo;
+#pragma unroll 8
+      for (int i = g; i < n_in; i += G) {
+        const float xi = x[i];
+        const float4 w4 = ldw4<SM>(w);
+        acc.x = fmaf(w4.x, xi, acc.x);
+        acc.y = fmaf(w4.y, xi, acc.y);
+        acc.z = fmaf(w4.z, xi, acc.z);
+        acc.w = fmaf(w4.w, xi, acc.w);
+        w += step;
+      }
     }
+    for (int off = P; off < 32; off <<= 1) {
+      acc.x += __shfl_xor_sync(FULL_MASK, acc.x, off);
+      acc.y += __shfl_xor_sync(FULL_MASK, acc.y, off);
+      acc.z += __shfl_xor_sync(FULL_MASK, acc.z, off);
+      acc.w += __shfl_xor_sync(FULL_MASK, acc.w, off);
+    }
+    if (g == 0 && q < nq) {
+      const float v4[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int o = o0 + lane + 32 * k;
-      if (k < nk && o < n_out) {
-        float v = acc[k] + __ldg(b + o);
-        if (act == 1) v = fmaxf(v, 0.f);
-        else if (act == 2) v = 1.f / (1.f + expf(-v));
-        y[o] = v;
+      for (int j = 0; j < 4; ++j) {
+        const int o = o0 + 4 * q + j;
+        if (o < n_out) {
+          float v = v4[j] + ldw<SM>(b + o);
+          if (act == 1) v = fmaxf(v, 0.f);
+          else if (act == 2) v = 1.f / (1.f + expf(-v));
+          y[o] = v;
+        }
       }
     }
   }
@@ -49,6 +75,7 @@ __device__ __forceinline__ void matvec(const float* __restrict__ Wt, const float
 }
 
 // x <- LayerNorm(x + y) * w + b  over d elements held in shared memory (biased variance, eps 1e-5)
+template <bool SM>
 __device__ __forceinline__ void add_layernorm(float* x, const float* y, const float* __restrict__ w,
                                               const float* __restrict__ b, int d, int lane) {
   float s = 0.f;
@@ -64,7 +91,7 @@ __device__ __forceinline__ void add_layernorm(float* x, const float* y, const fl
     q += v * v;
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / d + 1e-5f);
-  for (int c = lane; c < d; c += 32) x[c] = (x[c] - mu) * rstd * __ldg(w + c) + __ldg(b + c);
+  for (int c = lane; c < d; c += 32) x[c] = (x[c] - mu) * rstd * ldw<SM>(w + c) + ldw<SM>(b + c);
   __syncwarp();
 }
 
@@ -79,6 +106,7 @@ __host__ __device__ inline int tracker_scratch_floats(const cirs_tracker_weights
 
 // One new token of environment slot e (sequence position p) by one warp.  ``x`` = this warp's scratch
 // (tracker_scratch_floats(W) floats of shared memory).  id: user / item id when the table exists, else src_dense.
+template <bool SM = false>
 __device__ __forceinline__ void tracker_token_warp(const cirs_tracker_weights& W, int n_env, int e, int k, int p,
                                                    int id, const float* __restrict__ src_dense, float rew_k,
                                                    float* __restrict__ kcache, float* __restrict__ vcache,
@@ -99,14 +127,14 @@ __device__ __forceinline__ void tracker_token_warp(const cirs_tracker_weights& W
     const float* src = W.emb_user ? W.emb_user + (size_t)id * d : src_dense;
     for (int c = lane; c < n_in; c += 32) y[c] = __ldg(src + c);
     __syncwarp();
-    matvec(W.user_wt, W.user_b, y, n_in, d, ldd, x, lane, 0);  // ffn_user, state_tracker.py:212
+    matvec<SM>(W.user_wt, W.user_b, y, n_in, d, ldd, x, lane, 0);  // ffn_user, state_tracker.py:212
   } else {
     const int n_in = W.d_item_in;  // == d (the gate multiplies the item vector elementwise)
     const float* src = W.emb_item ? W.emb_item + (size_t)id * d : src_dense;
     if (lane == 0) y[0] = rew_k;
     for (int c = lane; c < n_in; c += 32) y[1 + c] = __ldg(src + c);
     __syncwarp();
-    matvec(W.gate_wt, W.gate_b, y, 1 + n_in, d, ldd, x, lane, 2);  // g = sigmoid(W_g [r;a] + b_g), :239
+    matvec<SM>(W.gate_wt, W.gate_b, y, 1 + n_in, d, ldd, x, lane, 2);  // g = sigmoid(W_g [r;a] + b_g), :239
     for (int c = lane; c < d; c += 32) x[c] *= y[1 + c];            // a' = g * a, :240
     __syncwarp();
   }
@@ -117,59 +145,82 @@ __device__ __forceinline__ void tracker_token_warp(const cirs_tracker_weights& W
   const float scale = 1.0f / sqrtf((float)dh);
   for (int l = 0; l < W.nlayers; ++l) {
     const cirs_encoder_layer& L = W.layer[l];
-    matvec(L.in_wt, L.in_b, x, d, 3 * d, ld3, qkv, lane, 0);
+    matvec<SM>(L.in_wt, L.in_b, x, d, 3 * d, ld3, qkv, lane, 0);
     float* kc = kcache + ((size_t)l * n_env + e) * W.max_len * d;
     float* vc = vcache + ((size_t)l * n_env + e) * W.max_len * d;
     for (int c = lane; c < d; c += 32) {
       kc[(size_t)p * d + c] = qkv[d + c];
       vc[(size_t)p * d + c] = qkv[2 * d + c];
     }
-    // scores: lane j handles cached position j
-    for (int h = 0; h < nh; ++h) {
-      const float* q = qkv + h * dh;
-      float mx = -INFINITY;
-      for (int j0 = 0; j0 <= p; j0 += 32) {
-        const int j = j0 + lane;
-        float s = -INFINITY;
-        if (j <= p) {
-          const float* kr = (j == p) ? (qkv + d + h * dh) : (kc + (size_t)j * d + h * dh);
-          float a = 0.f;
-          for (int c = 0; c < dh; ++c) a = fmaf(q[c] * scale, kr[c], a);
-          s = a;
-          prob[h * W.max_len + j] = s;
+    // scores of ALL heads: lane j (chunks of 32) owns cached position j and reads that key row once; the loads of
+    // one row are independent, so they are issued as a batch (one L2 round trip per 32 positions)
+    const bool vec4 = ((d & 3) == 0) && ((dh & 3) == 0);
+    for (int j0 = 0; j0 <= p; j0 += 32) {
+      const int j = j0 + lane;
+      if (j <= p) {
+        const float* kr = (j == p) ? (qkv + d) : (kc + (size_t)j * d);
+        if (vec4) {
+#pragma unroll 4
+          for (int h = 0; h < nh; ++h) {
+            const float* q = qkv + h * dh;
+            const float4* k4 = reinterpret_cast<const float4*>(kr + h * dh);
+            float a = 0.f;
+#pragma unroll 4
+            for (int c4 = 0; c4 < (dh >> 2); ++c4) {
+              const float4 kv = k4[c4];
+              a = fmaf(q[4 * c4] * scale, kv.x, a);
+              a = fmaf(q[4 * c4 + 1] * scale, kv.y, a);
+              a = fmaf(q[4 * c4 + 2] * scale, kv.z, a);
+              a = fmaf(q[4 * c4 + 3] * scale, kv.w, a);
+            }
+            prob[h * W.max_len + j] = a;
+          }
+        } else {
+          for (int h = 0; h < nh; ++h) {
+            const float* q = qkv + h * dh;
+            float a = 0.f;
+#pragma unroll 4
+            for (int c = 0; c < dh; ++c) a = fmaf(q[c] * scale, kr[h * dh + c], a);
+            prob[h * W.max_len + j] = a;
+          }
         }
-        mx = fmaxf(mx, s);
       }
+    }
+    __syncwarp();
+    for (int h = 0; h < nh; ++h) {
+      float* ph = prob + h * W.max_len;
+      float mx = -INFINITY;
+      for (int j = lane; j <= p; j += 32) mx = fmaxf(mx, ph[j]);
       mx = warp_max(mx);
-      __syncwarp();
       float sum = 0.f;
       for (int j = lane; j <= p; j += 32) {
-        const float ex = expf(prob[h * W.max_len + j] - mx);
-        prob[h * W.max_len + j] = ex;
+        const float ex = expf(ph[j] - mx);
+        ph[j] = ex;
         sum += ex;
       }
       sum = warp_sum(sum);
       const float inv = 1.0f / sum;
-      for (int j = lane; j <= p; j += 32) prob[h * W.max_len + j] *= inv;
+      for (int j = lane; j <= p; j += 32) ph[j] *= inv;
     }
     __syncwarp();
-    // o[c] = sum_j prob[head(c)][j] * V[j][c]
+    // o[c] = sum_j prob[head(c)][j] * V[j][c]   (row j of V is one coalesced line; loads batched by the unroll)
     for (int c = lane; c < d; c += 32) {
       const float* pr = prob + (c / dh) * W.max_len;
       float a = 0.f;
+#pragma unroll 8
       for (int j = 0; j < p; ++j) a = fmaf(pr[j], vc[(size_t)j * d + c], a);
       a = fmaf(pr[p], qkv[2 * d + c], a);
       hid[c] = a;
     }
     __syncwarp();
-    matvec(L.out_wt, L.out_b, hid, d, d, ldd, y, lane, 0);
-    add_layernorm(x, y, L.n1_w, L.n1_b, d, lane);
-    matvec(L.l1_wt, L.l1_b, x, d, dhid, ldh, hid, lane, 1);
-    matvec(L.l2_wt, L.l2_b, hid, dhid, d, ldd, y, lane, 0);
-    add_layernorm(x, y, L.n2_w, L.n2_b, d, lane);
+    matvec<SM>(L.out_wt, L.out_b, hid, d, d, ldd, y, lane, 0);
+    add_layernorm<SM>(x, y, L.n1_w, L.n1_b, d, lane);
+    matvec<SM>(L.l1_wt, L.l1_b, x, d, dhid, ldh, hid, lane, 1);
+    matvec<SM>(L.l2_wt, L.l2_b, hid, dhid, d, ldd, y, lane, 0);
+    add_layernorm<SM>(x, y, L.n2_w, L.n2_b, d, lane);
   }
   // decoder -> state
-  matvec(W.dec_wt, W.dec_b, x, d, W.dim_state, lds, y, lane, 0);
+  matvec<SM>(W.dec_wt, W.dec_b, x, d, W.dim_state, lds, y, lane, 0);
   const int S = W.dim_state;
   for (int c = lane; c < S; c += 32) {
     const float v = y[c];

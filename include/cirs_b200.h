@@ -191,7 +191,9 @@ int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, const int32_t
  * has ended or max_steps turns were played.  All arrays are per environment slot ([B] or [B, .]); traj_* are the
  * replay buffer's env-major arrays (traj_len slots per environment); ep_len[e] = episode length.
  * rng_counter: device uint64, advanced once per turn (Philox offset of the sampler).  mode: 0 sample, 1 argmax.
- * Same device code as cirs_actor_sample / cirs_kuaishou_step / cirs_tracker_step (bit-identical results). */
+ * Same device code as cirs_actor_sample / cirs_kuaishou_step / cirs_tracker_step (bit-identical results).
+ * The workspace's bytes [256, 256 + 8 * (1 + 3 * 512)) hold int64 phase timers written by the kernel:
+ * turns played, then per turn {running environments, ns in the actor-head phase, ns in the per-environment phase}. */
 int64_t cirs_rollout_workspace_bytes(int32_t n_env, int32_t n_action);
 int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weights* tw, const cirs_policy_weights* pw,
                           const int32_t* users, uint8_t* active, int32_t* act, float* logp, float* value,

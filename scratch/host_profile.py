@@ -25,7 +25,7 @@ for _ in range(20):
     tc += t1 - t0; tu += t2 - t1
 print(f"collect {tc/20*1e3:.3f} ms  update {tu/20*1e3:.3f} ms  n/st {res['n/st']} turns {res['turns']}")
 # graph replay alone
-g = col._graph
+col.persistent=False; col.collect(n_episode=B, users=rng.integers(0, cfg["U"], size=B)); g = col._graph
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(20): g.replay()
 torch.cuda.synchronize(); print(f"graph replay alone {(time.perf_counter()-t0)/20*1e3:.3f} ms")
@@ -33,3 +33,17 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(20): step()
 torch.cuda.synchronize(); pr.disable()
 s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(35); print(s.getvalue()[:6000])
+# rollout variants
+import time
+for name, kw in (("persistent", dict(persistent=True)), ("graph", dict(persistent=False, use_graph=True)), ("eager", dict(persistent=False, use_graph=False))):
+    col.persistent, col.use_graph = kw.get("persistent", False), kw.get("use_graph", False)
+    for _ in range(3): col.collect(n_episode=B, users=rng.integers(0, cfg["U"], size=B))
+    torch.cuda.synchronize(); t0 = time.perf_counter(); st = 0; tr = 0
+    for _ in range(20):
+        r = col.collect(n_episode=B, users=rng.integers(0, cfg["U"], size=B)); st += r["n/st"]; tr += r["turns"]
+    torch.cuda.synchronize(); print(f"collect[{name}] {(time.perf_counter()-t0)/20*1e3:.3f} ms  mean steps {st/20:.0f} mean turns {tr/20:.1f}")
+col.persistent = True
+r = col.collect(n_episode=B, users=rng.integers(0, cfg["U"], size=B))
+dbg = col._f["ws_roll"][256:256 + 8 * (1 + 6 * 512)].view(torch.int64).cpu().numpy()
+nt = int(dbg[0]); print("persistent turns", nt, "lens max", r["turns"])
+for t in range(nt): print(f"  turn {t:2d} n_act {dbg[1+3*t]:5d}  phaseA {dbg[2+3*t]/1e3:7.1f} us  phaseB {dbg[3+3*t]/1e3:7.1f} us   env0: combine {dbg[1+1536+3*t]/1e3:5.1f} env {dbg[2+1536+3*t]/1e3:5.1f} tracker {dbg[3+1536+3*t]/1e3:5.1f}")
