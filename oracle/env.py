@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  The product package never imports this file.
-Parity pinned: against tests/golden/kuaishou_*.npz, which were produced by executing the reference itself
-(oracle/make_golden.py).
+Parity pinned: against tests/golden/kuaishou_*.npz and tests/golden/taobao_*.npz, which were produced by executing
+the reference itself (oracle/make_golden.py).
 
 Each env object holds B independent environments (the reference holds one per Python object and loops over
 them in DummyVectorEnv, tianshou/env/venvs.py:212-220); the arithmetic per environment follows the cited lines.

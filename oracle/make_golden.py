@@ -222,6 +222,198 @@ def kuaishou_case(name, U=40, I=160, B=6, T=8, N=1, thr=0, d=16, nhead=4, tau=10
           "turns per collect:", [len(t) for t in rec.turns], "lens it0:", out["it0/res/lens"])
 
 
+def _update_and_record(policy, buf, out, P, it, batch_size, repeat, modules):
+    """policy.update with replayable minibatch permutations; records process_fn's outputs, the losses, ret_rms and
+    every parameter after the update."""
+    useed = 1000 + it
+    np.random.seed(useed)
+    captured = {}
+    orig_process = policy.process_fn
+
+    def proc(batch, buffer, indice):
+        b = orig_process(batch, buffer, indice)
+        captured["v_s"] = b.v_s.numpy().copy()
+        captured["returns"] = b.returns.numpy().copy()
+        captured["adv"] = b.adv.numpy().copy()
+        captured["logp_old"] = b.logp_old.numpy().copy()
+        return b
+
+    policy.process_fn = proc
+    losses = policy.update(0, buf, batch_size=batch_size, repeat=repeat)
+    policy.process_fn = orig_process
+    out[P + "upd/seed"] = np.array(useed)
+    for k, v in captured.items():
+        out[P + "upd/" + k] = v
+    for k, v in losses.items():
+        out[P + "upd/" + k.replace("/", "_")] = np.array(v, dtype=np.float64)
+    out[P + "upd/ret_rms"] = np.array([policy.ret_rms.mean, policy.ret_rms.var, policy.ret_rms.count],
+                                      dtype=np.float64)
+    for name, mod in modules.items():
+        out.update(_sd(mod, P + f"after/{name}/"))
+
+
+def taobao_case(name, B=5, T=8, N=3, thr=5.2, tau=10.0, gamma_exposure=10.0, version="v1", batch_size=9, repeat=2,
+                iters=2, seed=17):
+    """SimulatedEnv over VirtualTB (CIRS-RL-taobao.py:152-246): dense user / item features, d_model = 27, nhead = 3,
+    ActorProb + Independent(Normal), action clip + scaling in map_action.  The Taobao user model is not shipped
+    (SURVEY §8c): UserModel_MMOE is random-initialised with the shapes of CIRS-UserModel-taobao.py:100-148 and given
+    'trained-like' weights so that the predicted reward varies over [0, 10]."""
+    import collections
+    from deepctr_torch.inputs import DenseFeat
+    from core.user_model_mmoe import UserModel_MMOE
+    from tianshou.utils.net.continuous import ActorProb, Critic as CriticC
+    from torch.distributions import Independent, Normal
+
+    x_columns = [DenseFeat("user_feat", 91), DenseFeat("feat_item", 27)]
+    y_columns = [DenseFeat("y", 1)]
+    tasks = collections.OrderedDict({f.name: "regression" for f in y_columns})
+    task_logit_dim = {f.name: f.dimension for f in y_columns}
+    um = UserModel_MMOE(x_columns, y_columns, len(tasks), tasks, task_logit_dim, dnn_hidden_units=(64, 64), seed=2022,
+                        device="cpu")
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n_, p_ in um.named_parameters():
+            if n_.startswith("dnn.linears") and n_.endswith("weight"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * (1.5 / p_.shape[1] ** 0.5))
+            elif n_.startswith("dnn.linears"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.1)
+            elif n_.startswith("mmoe_layer"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.3)
+            elif n_.startswith("tower_network"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.5)
+            elif n_.startswith("linear_model_task") and n_.endswith("weight"):
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.2)
+            elif n_.startswith("out."):
+                p_.fill_(3.0)
+    um.device = "cpu"
+    gym.register(id="VirtualTB-v0", entry_point="environments.VirtualTaobao.virtualTB.envs:VirtualTB",
+                 kwargs=dict(num_leave_compute=N, leave_threshold=thr, max_turn=T))
+    gym.register(id="SimulatedEnv-v0", entry_point="core.env.simulatedEnv.simulated_env:SimulatedEnv",
+                 kwargs=dict(user_model=um, task_name="VirtualTB-v0", version=version, tau=tau,
+                             gamma_exposure=gamma_exposure))
+    sim = gym.make("SimulatedEnv-v0")
+    train_envs = DummyVectorEnv([lambda: gym.make("SimulatedEnv-v0") for _ in range(B)])
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    train_envs.seed(seed)
+    d, nhead = 27, 3
+    cols = get_dataset_columns(d, envname="VirtualTB-v0")
+    tracker = StateTrackerTransformer(cols[0], cols[1], cols[2], dim_model=d, dim_state=20, dim_max_batch=B,
+                                      dataset="VirtualTB-v0", has_user_embedding=cols[3],
+                                      has_action_embedding=cols[4], has_feedback_embedding=cols[5], nhead=nhead,
+                                      d_hid=128, nlayers=2, dropout=0.0, device="cpu", seed=seed, MAX_TURN=T)
+    net = Net(20, hidden_sizes=[64, 64], device="cpu")
+    actor = ActorProb(net, sim.action_space.shape, max_action=sim.action_space.high[0], device="cpu")
+    critic = CriticC(net, device="cpu")
+    for m in list(actor.modules()) + list(critic.modules()):
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.orthogonal_(m.weight)
+            torch.nn.init.zeros_(m.bias)
+    with torch.no_grad():
+        actor.sigma_param.copy_(torch.randn(27, 1, generator=g) * 0.2 - 0.3)   # non-trivial sigma
+    optim_RL = torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=1e-3)
+    optim_state = torch.optim.Adam(tracker.parameters(), lr=1e-3)
+
+    def dist(*logits):
+        return Independent(Normal(*logits), 1)
+
+    policy = PPOPolicy(actor, critic, [optim_RL, optim_state], dist, discount_factor=0.95, max_grad_norm=0.5,
+                       eps_clip=0.2, vf_coef=0.25, ent_coef=0.0, reward_normalization=1, advantage_normalization=1,
+                       recompute_advantage=0, value_clip=1, gae_lambda=0.95, action_space=sim.action_space)
+    rec = Recorder()
+
+    # --- instrumentation (recording only): Normal.sample made explicit (torch.normal(mean, std) == N(0,1)*std+mean)
+    def sample_explicit(self, sample_shape=torch.Size()):
+        with torch.no_grad():
+            eps = torch.empty_like(self.loc).normal_()
+            rec.cur["eps"] = eps.numpy().copy()
+            rec.cur["mu"] = self.loc.detach().numpy().copy()
+            rec.cur["sigma"] = self.scale.detach().numpy().copy()
+            return eps * self.scale + self.loc
+
+    st0 = torch.get_rng_state()
+    probe = Normal(torch.linspace(-1, 1, 27).reshape(1, 27), torch.linspace(0.5, 1.5, 27).reshape(1, 27))
+    ref_draw = probe.sample()
+    torch.set_rng_state(st0)
+    rec.cur = {}
+    Normal.sample = sample_explicit
+    assert torch.equal(ref_draw, probe.sample()), "explicit Normal.sample differs from torch's"
+    torch.set_rng_state(st0)
+
+    orig_forward = policy.forward
+
+    def fwd(batch, *a, **k):
+        if not policy.updating:
+            rec.cur = rec.turn()
+            rec.cur["state"] = batch.obs.detach().numpy().copy()
+        else:
+            rec.cur = {}
+        return orig_forward(batch, *a, **k)
+
+    policy.forward = fwd
+    orig_build = tracker.build_state
+
+    def build(**k):
+        out = orig_build(**k)
+        if k.get("obs") is not None:
+            rec.new_collect()
+            rec.reset_obs = np.asarray(k["obs"]).copy()
+            rec.s0 = out["obs"].detach().numpy().copy()
+        elif k.get("obs_next") is not None:
+            c = rec.cur
+            c["env_id"] = np.asarray(k["env_id"]).copy()
+            c["obs_next_raw"] = np.asarray(k["obs_next"]).copy()
+            c["rew"] = np.asarray(k["rew"], dtype=np.float64).copy()
+            c["done"] = np.asarray(k["done"]).copy()
+            c["state_next"] = out["obs_next"].detach().numpy().copy()
+        return out
+
+    collector = Collector(policy, train_envs, VectorReplayBuffer(B * (T + 2), B), preprocess_fn=build)
+    out = dict(cfg=np.array([B, T, N, d, nhead, batch_size, repeat, iters, seed], dtype=np.int64),
+               cfg_f=np.array([thr, tau, gamma_exposure, 1.0 if version == "v1" else 2.0]),
+               action_low=np.asarray(sim.action_space.low), action_high=np.asarray(sim.action_space.high))
+    out.update(_sd(um, "usermodel/"))
+    out.update(_sd(tracker, "init/tracker/"))
+    out.update(_sd(actor, "init/actor/"))
+    out.update(_sd(critic, "init/critic/"))
+    # user-model known answers on random inputs (pins the MMOE restatement alone)
+    xs = torch.randn(16, 118, generator=g)
+    out["usermodel_x"] = xs.numpy().copy()
+    out["usermodel_y"] = um.forward(xs).detach().numpy().copy()
+
+    policy.train()
+    for it in range(iters):
+        res = collector.collect(n_episode=B)
+        buf = collector.buffer
+        turns = rec.turns[-1]
+        P = f"it{it}/"
+        out[P + "users"] = rec.reset_obs[:, :88].astype(np.float32)
+        out[P + "reset_obs"] = rec.reset_obs
+        out[P + "s0"] = rec.s0
+        out[P + "n_turns"] = np.array(len(turns))
+        for t, c in enumerate(turns):
+            for k, v in c.items():
+                out[P + f"turn{t}/{k}"] = v
+        idx = buf.sample_index(0)
+        out[P + "buf/index"] = idx
+        out[P + "buf/obs"] = buf.obs[idx].detach().numpy().copy()
+        out[P + "buf/obs_next"] = buf.obs_next[idx].detach().numpy().copy()
+        out[P + "buf/act"] = np.asarray(buf.act[idx]).copy()
+        out[P + "buf/rew"] = buf.rew[idx].copy()
+        out[P + "buf/done"] = buf.done[idx].copy()
+        out[P + "buf/lengths"] = buf._lengths.copy()
+        out[P + "buf/sub_size"] = np.array(buf.buffers[0].maxsize)
+        for k in ("n/ep", "n/st", "rews", "lens", "idxs", "rew", "len", "rew_std", "len_std"):
+            out[P + "res/" + k.replace("/", "_")] = np.asarray(res[k])
+        _update_and_record(policy, buf, out, P, it, batch_size, repeat,
+                           dict(tracker=tracker, actor=actor, critic=critic))
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB;",
+          "turns per collect:", [len(t) for t in rec.turns], "lens it0:", out["it0/res/lens"],
+          "rew range:", min(c["rew"].min() for c in rec.turns[-1]), max(c["rew"].max() for c in rec.turns[-1]))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     # reference defaults N=1, thr=0 (CIRS-RL-kuaishou.py:70-71): leave as soon as the action shares a category
@@ -233,5 +425,18 @@ def main():
                   gamma_exposure=0.05, tau=5.0, batch_size=5)
 
 
+def main_taobao():
+    os.makedirs(GOLD, exist_ok=True)
+    # CIRS-RL-taobao.py defaults (N=5, thr=3.0, tau=10, gamma_exposure=10) scaled to a short horizon; thr raised so
+    # that the Euclidean exit actually fires for N(mu, sigma) actions clipped to [-1, 1]^27
+    taobao_case("taobao_N3", B=6, T=8, N=3, thr=4.45, seed=17)
+
+
 if __name__ == "__main__":
-    main()
+    # the two families register different gym ids / patch different distributions: one process each
+    #   python -m oracle.make_golden            -> kuaishou_*.npz
+    #   python -m oracle.make_golden taobao     -> taobao_*.npz
+    if len(sys.argv) > 1 and sys.argv[1] == "taobao":
+        main_taobao()
+    else:
+        main()

@@ -174,3 +174,65 @@ def entropy(p):
 def sample_race(p, q):
     """Categorical.sample == torch.multinomial(p, 1, True) == argmax(p / q), q ~ Exp(1)."""
     return torch.argmax(torch.as_tensor(p) / torch.as_tensor(q), dim=-1)
+
+
+# ---------------------------------------------------------------- continuous actor (VirtualTaobao)
+def rl_params_continuous(actor_sd, critic_sd):
+    """ActorProb + Critic state dicts -> one dict (tianshou/utils/net/continuous.py:120-199, :60-110)."""
+    R = {k: v for k, v in actor_sd.items() if k.startswith("preprocess.")}
+    R["actor.mu.weight"], R["actor.mu.bias"] = actor_sd["mu.model.0.weight"], actor_sd["mu.model.0.bias"]
+    R["actor.sigma_param"] = actor_sd["sigma_param"]
+    R["critic.last.weight"], R["critic.last.bias"] = critic_sd["last.model.0.weight"], critic_sd["last.model.0.bias"]
+    return R
+
+
+def actor_mu_sigma(R, s, max_action=1.0):
+    """continuous.py:179-199: mu = max_action * tanh(W h + b); sigma = exp(sigma_param) broadcast over rows."""
+    mu = max_action * torch.tanh(trunk(R, s) @ R["actor.mu.weight"].T + R["actor.mu.bias"])
+    sigma = (R["actor.sigma_param"].view(1, -1) + torch.zeros_like(mu)).exp()
+    return mu, sigma
+
+
+def normal_log_prob(mu, sigma, act):
+    """Independent(Normal(mu, sigma), 1).log_prob (torch/distributions/normal.py log_prob, summed over the last dim)."""
+    act = torch.as_tensor(act, dtype=torch.float32)
+    var = sigma ** 2
+    return (-((act - mu) ** 2) / (2 * var) - sigma.log() - math.log(math.sqrt(2 * math.pi))).sum(-1)
+
+
+def normal_entropy(sigma):
+    """Independent(Normal).entropy: sum of 0.5 + 0.5 log(2 pi) + log sigma."""
+    return (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(sigma)).sum(-1)
+
+
+def sample_normal(mu, sigma, eps):
+    """Normal.sample == torch.normal(mu, sigma) == N(0,1) * sigma + mu (ATen normal_out_impl: mul_ then add_)."""
+    return torch.as_tensor(eps, dtype=torch.float32) * sigma + mu
+
+
+def map_action(act, low, high):
+    """tianshou/policy/base.py:143-173, action_bound_method="clip", action_scaling=True: float32 throughout, so the
+    scaling to [low, high] = [-1, 1] is NOT an exact identity (act + 1 rounds)."""
+    act = np.clip(np.asarray(act, dtype=np.float32), -1.0, 1.0)
+    low, high = np.asarray(low, dtype=np.float32), np.asarray(high, dtype=np.float32)
+    return low + (high - low) * (act + 1.0) / 2.0
+
+
+# ---------------------------------------------------------------- Taobao reward model
+def mmoe_forward(UM, x):
+    """UserModel_MMOE.forward (core/user_model_mmoe.py:144-220) for the Taobao columns: dense features only (no
+    sparse embeddings -> no FM term, :186), one regression task.  x[n,118] = [user 88, prev_r, 0, turn, item 27]
+    (simulated_env.py:79-80).  Linear part core/layers.py:67-70; DNN deepctr layers/core.py:120-134 (ReLU, no BN, no
+    dropout); MMOE layer core/layers.py:107-116 (experts reshaped [output_dim, num_experts], softmax gate);
+    tower Linear(8 -> 1, no bias); PredictionLayer 'regression' adds a bias (layers/core.py:155-161)."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    lin = x @ UM["linear_model_task.0.weight"]
+    h = torch.relu(x @ UM["dnn.linears.0.weight"].T + UM["dnn.linears.0.bias"])
+    h = torch.relu(h @ UM["dnn.linears.1.weight"].T + UM["dnn.linears.1.bias"])
+    n_exp = UM["mmoe_layer.gating_networks.0.weight"].shape[0]
+    e = (h @ UM["mmoe_layer.expert_network.weight"].T + UM["mmoe_layer.expert_network.bias"])
+    e = e.reshape(x.shape[0], -1, n_exp)
+    g = torch.softmax(h @ UM["mmoe_layer.gating_networks.0.weight"].T, dim=1).unsqueeze(-1)
+    m = torch.bmm(e, g).squeeze(-1)
+    dnn = m @ UM["tower_network.0.weight"].T
+    return (lin + dnn) + UM["out.0.bias"]

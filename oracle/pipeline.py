@@ -31,7 +31,7 @@ class Trajectory:
         return u
 
 
-def collect(env, tracker, R, users, *, actions=None, noise=None, force_length=0, record=None):
+def collect(env, tracker, R, users, *, actions=None, noise=None, force_length=0, record=None, action_space=None):
     """One Collector.collect(n_episode=B).  Actions come from, in order of preference: ``actions`` (teacher
     forcing: list per turn of arrays aligned with the ready set), ``noise`` (callable(turn, n, A) -> q, Exp(1)
     race noise) or argmax of the probabilities.  Returns (Trajectory, result-dict like collector.py:352-362)."""
@@ -43,16 +43,31 @@ def collect(env, tracker, R, users, *, actions=None, noise=None, force_length=0,
     per_env = [dict(obs=[], obs_next=[], act=[], rew=[], done=[]) for _ in range(B)]
     ep_rews, ep_lens, order = [], [], []
     turn = 0
+    continuous = "actor.sigma_param" in R
     while True:
-        with torch.no_grad():
-            p = nets.actor_probs(R, s.detach())
-        if actions is not None:
-            act = np.asarray(actions[turn]).reshape(-1)
-        elif noise is not None:
-            act = nets.sample_race(p, noise(turn, len(ready), p.shape[1])).numpy()
+        if continuous:
+            # ActorProb + Independent(Normal) (ppo.py:144-156); ``noise(turn, n, 27)`` -> N(0,1) draws; the buffer keeps
+            # the raw sample, the environment receives map_action(act) (collector.py:246-250, base.py:143-173)
+            with torch.no_grad():
+                mu, sigma = nets.actor_mu_sigma(R, s.detach())
+                p = torch.cat([mu, sigma], -1)
+            if actions is not None:
+                act = np.asarray(actions[turn], dtype=np.float32)
+            elif noise is not None:
+                act = nets.sample_normal(mu, sigma, noise(turn, len(ready), mu.shape[1])).numpy()
+            else:
+                act = mu.numpy()
+            obs_next_raw, rew, done = env.step(nets.map_action(act, *action_space), ready)
         else:
-            act = torch.argmax(p, -1).numpy()
-        obs_next_raw, rew, done = env.step(act, ready)
+            with torch.no_grad():
+                p = nets.actor_probs(R, s.detach())
+            if actions is not None:
+                act = np.asarray(actions[turn]).reshape(-1)
+            elif noise is not None:
+                act = nets.sample_race(p, noise(turn, len(ready), p.shape[1])).numpy()
+            else:
+                act = torch.argmax(p, -1).numpy()
+            obs_next_raw, rew, done = env.step(act, ready)
         turn += 1
         if force_length > 0:  # collector.py:253-258
             done = np.full_like(done, turn >= force_length)
@@ -94,7 +109,10 @@ def update(traj, R, opt_rl, tracker_params, opt_tracker, rms, perms, batch_size,
         v_next = nets.critic_value(R, traj.obs_next.detach()).numpy()
     returns, adv = ppo.compute_returns(v_s, v_next, traj.rew, traj.done, traj.unfinished, rms, gamma, gae_lambda)
     with torch.no_grad():
-        logp_old = nets.log_prob(nets.actor_probs(R, traj.obs.detach()), traj.act).numpy()
+        if "actor.sigma_param" in R:
+            logp_old = nets.normal_log_prob(*nets.actor_mu_sigma(R, traj.obs.detach()), traj.act).numpy()
+        else:
+            logp_old = nets.log_prob(nets.actor_probs(R, traj.obs.detach()), traj.act).numpy()
     if out is not None:
         out.update(v_s=v_s, returns=returns, adv=adv, logp_old=logp_old)
     return ppo.ppo_learn(R, opt_rl, tracker_params, opt_tracker, traj.obs, traj.act, adv, returns, v_s, logp_old,

@@ -115,8 +115,12 @@ RL_ORDER = ["preprocess.model.model.0.weight", "preprocess.model.model.0.bias",
 
 
 def rl_param_list(R):
-    """optim_RL's list: actor.parameters() + critic.parameters() -- trunk appears twice."""
+    """optim_RL's list: actor.parameters() + critic.parameters() -- trunk appears twice.  ActorProb registers
+    sigma_param on the module itself, so nn.Module.parameters() yields it first (continuous.py:160-173)."""
     trunk = [R[k] for k in RL_ORDER]
+    if "actor.sigma_param" in R:
+        return [R["actor.sigma_param"]] + trunk + [R["actor.mu.weight"], R["actor.mu.bias"]] + trunk + \
+            [R["critic.last.weight"], R["critic.last.bias"]]
     return trunk + [R["actor.last.weight"], R["actor.last.bias"]] + trunk + \
         [R["critic.last.weight"], R["critic.last.bias"]]
 
@@ -127,7 +131,8 @@ def ppo_learn(R, opt_rl, tracker_params, opt_tracker, obs, act, adv, returns, v_
     leaf when the tracker is not trained).  ``perms`` = one permutation of range(TB) per repeat.
     Returns dict of per-minibatch loss lists."""
     out = {"loss": [], "loss/clip": [], "loss/vf": [], "loss/ent": []}
-    act_t = torch.as_tensor(act, dtype=torch.long)
+    continuous = "actor.sigma_param" in R
+    act_t = torch.as_tensor(act, dtype=torch.float32) if continuous else torch.as_tensor(act, dtype=torch.long)
     adv_t, ret_t = torch.as_tensor(adv), torch.as_tensor(returns)
     vold_t, lpo_t = torch.as_tensor(v_old), torch.as_tensor(logp_old)
     plist = rl_param_list(R)
@@ -140,15 +145,20 @@ def ppo_learn(R, opt_rl, tracker_params, opt_tracker, obs, act, adv, returns, v_
         for idx in split_indices(len(perm), batch_size, np.asarray(perm)):
             idx_t = torch.as_tensor(idx, dtype=torch.long)
             s = obs[idx_t]
-            p = nets.actor_probs(R, s)
+            if continuous:
+                mu, sigma = nets.actor_mu_sigma(R, s)
+                logp = nets.normal_log_prob(mu, sigma, act_t[idx_t])
+            else:
+                p = nets.actor_probs(R, s)
+                logp = nets.log_prob(p, act_t[idx_t])
             a = adv_t[idx_t]
             a = (a - a.mean()) / a.std()  # ppo.py:185-186 (unbiased std)
-            ratio = (nets.log_prob(p, act_t[idx_t]) - lpo_t[idx_t]).exp()
+            ratio = (logp - lpo_t[idx_t]).exp()
             clip_loss = -torch.min(ratio * a, ratio.clamp(1 - eps_clip, 1 + eps_clip) * a).mean()
             value = nets.critic_value(R, s)
             v_clip = vold_t[idx_t] + (value - vold_t[idx_t]).clamp(-eps_clip, eps_clip)
             vf_loss = torch.max((ret_t[idx_t] - value) ** 2, (ret_t[idx_t] - v_clip) ** 2).mean()
-            ent_loss = nets.entropy(p).mean()
+            ent_loss = (nets.normal_entropy(sigma) if continuous else nets.entropy(p)).mean()
             loss = clip_loss + vf_coef * vf_loss - ent_coef * ent_loss
             for q in uniq:
                 q.grad = None  # optim_RL.zero_grad()

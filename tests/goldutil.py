@@ -5,6 +5,7 @@ import numpy as np
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KUAISHOU_CASES = ["kuaishou_N1", "kuaishou_N5", "kuaishou_v2"]
+TAOBAO_CASES = ["taobao_N3"]
 PARAM_ATOL = 1e-5  # 1 % of one Adam step (lr 1e-3); see tests/test_oracle_golden.py docstring
 
 
@@ -20,15 +21,24 @@ def cfg(z):
                 version="v1" if ver == 1.0 else "v2", use_ab=bool(use_ab))
 
 
+def taobao_cfg(z):
+    B, T, N, d, nhead, batch_size, repeat, iters, seed = (int(x) for x in z["cfg"])
+    thr, tau, gamma_e, ver = (float(x) for x in z["cfg_f"])
+    return dict(B=B, T=T, N=N, d=d, nhead=nhead, batch_size=batch_size, repeat=repeat, iters=iters, seed=seed, thr=thr,
+                tau=tau, gamma_exposure=gamma_e, version="v1" if ver == 1.0 else "v2")
+
+
 def turns(z, it):
     n = int(z[f"it{it}/n_turns"])
     keys = ["state", "q", "probs", "env_id", "obs_next_raw", "rew", "done", "state_next"]
+    if f"it{it}/turn0/eps" in z.files:   # continuous actor (VirtualTaobao)
+        keys = ["state", "eps", "mu", "sigma", "env_id", "obs_next_raw", "rew", "done", "state_next"]
     return [{k: z[f"it{it}/turn{t}/{k}"] for k in keys} for t in range(n)]
 
 
 def perms(z, it, n):
     """The minibatch permutations the reference drew (np.random.seed(useed) before policy.update)."""
-    c = cfg(z)
+    c = taobao_cfg(z) if "usermodel_x" in z.files else cfg(z)
     st = np.random.get_state()
     np.random.seed(int(z[f"it{it}/upd/seed"]))
     out = [np.random.permutation(n) for _ in range(c["repeat"])]

@@ -137,3 +137,84 @@ def test_replay_reference_run(name):
                 # Adam turns the reference's rounding noise there into +-lr steps, so it cannot be compared
                 mine, ref = G.drop_key_bias(mine), G.drop_key_bias(ref)
             G.assert_close(mine, ref, 1e-5, G.PARAM_ATOL, what=f"tracker param {k}")
+
+
+# ------------------------------------------------------------------ VirtualTaobao (continuous actions, dense features)
+def _make_taobao(z):
+    c = G.taobao_cfg(z)
+    UM = nets.to_params(z, "usermodel/")
+    env = oenv.TaobaoSimOracle(lambda x: nets.mmoe_forward(UM, x).reshape(-1).numpy(), max_turn=c["T"],
+                               num_leave_compute=c["N"], leave_threshold=c["thr"], tau=c["tau"],
+                               gamma_exposure=c["gamma_exposure"], version=c["version"])
+    P = nets.to_params(z, "init/tracker/")
+    P = {k: v.clone().requires_grad_(k != "pos_encoder.pe") for k, v in P.items()}
+    R = nets.rl_params_continuous(nets.to_params(z, "init/actor/"), nets.to_params(z, "init/critic/"))
+    R = {k: v.clone() for k, v in R.items()}
+    return c, UM, env, P, R
+
+
+@pytest.mark.parametrize("name", G.TAOBAO_CASES)
+def test_taobao_user_model_known_answers(name):
+    z = G.load(name)
+    UM = nets.to_params(z, "usermodel/")
+    G.assert_close(nets.mmoe_forward(UM, z["usermodel_x"]).numpy(), z["usermodel_y"], 1e-5, 1e-6, what="MMOE forward")
+
+
+@pytest.mark.parametrize("name", G.TAOBAO_CASES)
+def test_replay_reference_run_taobao(name):
+    z = G.load(name)
+    c, UM, env, P, R = _make_taobao(z)
+    space = (z["action_low"], z["action_high"])
+    tracker = nets.TrackerOracle(P, c["nhead"], c["T"], dense=True)
+    opt_rl, opt_tr, rms = ppo.AdamDup(), ppo.AdamDup(), ppo.RunningMeanStd()
+    tparams = [v for k, v in P.items() if k != "pos_encoder.pe"]
+    for it in range(c["iters"]):
+        gt = G.turns(z, it)
+        rec = []
+        noise = lambda turn, n, A: gt[turn]["eps"]  # noqa: E731  the reference's own N(0,1) draws
+        traj, res = pipeline.collect(env, tracker, R, z[f"it{it}/users"], noise=noise, record=rec,
+                                     action_space=space)
+        assert len(rec) == len(gt)
+        for t, (mine, ref) in enumerate(zip(rec, gt)):
+            assert np.array_equal(mine["env_id"], ref["env_id"]), f"ready set, turn {t}"
+            assert np.array_equal(mine["done"], ref["done"]), f"done, turn {t}"
+            G.assert_close(mine["rew"], ref["rew"], 1e-5, 1e-6, what=f"rew turn {t}")
+            G.assert_close(mine["state"], ref["state"], 1e-5, 1e-6, what=f"state turn {t}")
+            G.assert_close(mine["state_next"], ref["state_next"], 1e-5, 1e-6, what=f"state_next turn {t}")
+            G.assert_close(mine["probs"][:, :27], ref["mu"], 1e-5, 1e-6, what=f"mu turn {t}")
+            G.assert_close(mine["probs"][:, 27:], ref["sigma"], 1e-5, what=f"sigma turn {t}")
+            # sampler and action mapping on the reference's own mu / sigma / eps: bit exact
+            a_ref = nets.sample_normal(torch.tensor(ref["mu"]), torch.tensor(ref["sigma"]), ref["eps"]).numpy()
+            assert np.array_equal(nets.map_action(a_ref, *space).astype(np.float64), ref["obs_next_raw"][:, :27])
+            # observation layout [a(27), r, 0, t+1]  (simulated_env.py:50)
+            assert np.array_equal(ref["obs_next_raw"][:, 28], np.zeros(len(ref["rew"])))
+            assert np.array_equal(ref["obs_next_raw"][:, 29], np.full(len(ref["rew"]), t + 1.0))
+        assert np.array_equal(traj.lengths, z[f"it{it}/buf/lengths"])
+        assert np.array_equal(traj.done, z[f"it{it}/buf/done"])
+        G.assert_close(traj.act, z[f"it{it}/buf/act"], 1e-5, 1e-6, what="buf act")
+        G.assert_close(traj.rew, z[f"it{it}/buf/rew"], 1e-5, 1e-6, what="buf rew")
+        G.assert_close(traj.obs.detach(), z[f"it{it}/buf/obs"], 1e-5, 1e-6, what="buf obs")
+        G.assert_close(traj.obs_next.detach(), z[f"it{it}/buf/obs_next"], 1e-5, 1e-6, what="buf obs_next")
+        assert res["n/st"] == int(z[f"it{it}/res/n_st"]) and res["n/ep"] == int(z[f"it{it}/res/n_ep"])
+        assert np.array_equal(res["lens"], z[f"it{it}/res/lens"])
+        G.assert_close(res["rews"], z[f"it{it}/res/rews"], 1e-5, 1e-6, what="episode rewards")
+        out = {}
+        losses = pipeline.update(traj, R, opt_rl, tparams, opt_tr, rms, G.perms(z, it, len(traj.act)),
+                                 c["batch_size"], out=out)
+        for k in ("v_s", "returns", "adv", "logp_old"):
+            G.assert_close(out[k], z[f"it{it}/upd/{k}"], 1e-5, 1e-5, what=k)
+        G.assert_close(losses["loss/clip"], z[f"it{it}/upd/loss_clip"], 1e-5, 1e-5, what="clip loss")
+        G.assert_close(losses["loss/vf"], z[f"it{it}/upd/loss_vf"], 1e-5, 1e-6, what="vf loss")
+        G.assert_close(losses["loss/ent"], z[f"it{it}/upd/loss_ent"], 1e-5, what="entropy")
+        G.assert_close(losses["loss"], z[f"it{it}/upd/loss"], 1e-5, 1e-5, what="loss")
+        G.assert_close([rms.mean, rms.var, rms.count], z[f"it{it}/upd/ret_rms"], 1e-6, what="ret_rms")
+        Rref = nets.rl_params_continuous(nets.to_params(z, f"it{it}/after/actor/"),
+                                         nets.to_params(z, f"it{it}/after/critic/"))
+        for k in R:
+            G.assert_close(R[k].detach(), Rref[k], 1e-5, G.PARAM_ATOL, what=f"RL param {k}")
+        Pref = nets.to_params(z, f"it{it}/after/tracker/")
+        for k in P:
+            mine, ref = P[k].detach().numpy(), Pref[k].numpy()
+            if k.endswith("in_proj_bias"):
+                mine, ref = G.drop_key_bias(mine), G.drop_key_bias(ref)
+            G.assert_close(mine, ref, 1e-5, G.PARAM_ATOL, what=f"tracker param {k}")
