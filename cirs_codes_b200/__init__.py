@@ -7,13 +7,13 @@ libcirs_b200.so and a CUDA device (there is no CPU fallback on the product path)
 from .inputs import (DenseFeat, SparseFeat, SparseFeatP, VarLenSparseFeat, build_input_features,  # noqa: F401
                      compute_input_dim, get_dataset_columns, get_feature_names)
 from .data import Batch, VectorReplayBuffer  # noqa: F401
-from .net import Actor, Critic, Net, orthogonal_init  # noqa: F401
-from .env import KuaishouVectorEnv  # noqa: F401
+from .net import Actor, ActorProb, Critic, Net, orthogonal_init  # noqa: F401
+from .env import KuaishouVectorEnv, TaobaoVectorEnv  # noqa: F401
 from .state_tracker import StateTrackerTransformer  # noqa: F401
 from .policy import PPOPolicy  # noqa: F401
 from .collector import Collector  # noqa: F401
 
 __all__ = ["DenseFeat", "SparseFeat", "SparseFeatP", "VarLenSparseFeat", "build_input_features",
            "compute_input_dim", "get_dataset_columns", "get_feature_names", "Batch", "VectorReplayBuffer", "Actor",
-           "Critic", "Net", "orthogonal_init", "KuaishouVectorEnv", "StateTrackerTransformer", "PPOPolicy",
+           "ActorProb", "Critic", "Net", "orthogonal_init", "KuaishouVectorEnv", "TaobaoVectorEnv", "StateTrackerTransformer", "PPOPolicy",
            "Collector"]

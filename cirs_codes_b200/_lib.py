@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcirs_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LAYERS = 4
 HIDDEN = 64
 
@@ -23,6 +23,21 @@ class KuaishouEnvStruct(C.Structure):
                 ("r_decay", C.c_float),
                 ("normed_mat", fp), ("mat", fp), ("cat_mask", fp), ("alpha_u", fp), ("beta_i", fp), ("dist", fp),
                 ("user", fp), ("turn", fp), ("hist", fp), ("cum_rew", fp), ("seen", fp)]
+
+
+class MMOEStruct(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32), ("n_expert", C.c_int32),
+                ("expert_dim", C.c_int32),
+                ("lin_w", fp), ("w1t", fp), ("b1", fp), ("w2t", fp), ("b2", fp), ("wet", fp), ("be", fp), ("wgt", fp),
+                ("bg", fp), ("tower", fp), ("out_bias", C.c_float)]
+
+
+class TaobaoEnvStruct(C.Structure):
+    _fields_ = [("n_env", C.c_int32), ("max_turn", C.c_int32), ("num_leave_compute", C.c_int32),
+                ("version", C.c_int32), ("map_action", C.c_int32), ("act_low", C.c_float), ("act_high", C.c_float),
+                ("leave_threshold", C.c_double), ("tau", C.c_double), ("gamma_exposure", C.c_double),
+                ("um", MMOEStruct),
+                ("user", fp), ("turn", fp), ("hist", fp), ("prev_rew", fp), ("cum_rew", fp)]
 
 
 class EncoderLayerStruct(C.Structure):
@@ -42,7 +57,8 @@ class TrackerWeightsStruct(C.Structure):
 class PolicyWeightsStruct(C.Structure):
     _fields_ = [("dim_state", C.c_int32), ("n_action", C.c_int32), ("ld_action", C.c_int32),
                 ("w1t", fp), ("b1", fp), ("w2t", fp), ("b2", fp), ("w3t", fp), ("b3", fp), ("wv", fp), ("bv", fp),
-                ("flat", fp), ("n_flat", C.c_int64), ("n_trunk", C.c_int64)]
+                ("flat", fp), ("n_flat", C.c_int64), ("n_trunk", C.c_int64), ("sigma", fp),
+                ("max_action", C.c_float)]
 
 
 class PPOConfigStruct(C.Structure):
@@ -63,6 +79,8 @@ PROTOTYPES = {
     "cirs_profile_report": (i32, [C.c_char_p, i32]),
     "cirs_kuaishou_reset": (i32, [P(KuaishouEnvStruct), i32, fp, fp, fp, fp]),
     "cirs_kuaishou_step": (i32, [P(KuaishouEnvStruct), i32, fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, i32, fp]),
+    "cirs_taobao_reset": (i32, [P(TaobaoEnvStruct), i32, fp, fp, fp, fp]),
+    "cirs_taobao_step": (i32, [P(TaobaoEnvStruct), i32, fp, fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, fp, i32, fp]),
     "cirs_tracker_step": (i32, [P(TrackerWeightsStruct), i32, i32, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, i64,
                                 fp, i32, fp, fp, fp]),
     "cirs_tracker_train_workspace_bytes": (i64, [P(TrackerWeightsStruct), i32, i64]),
@@ -72,6 +90,11 @@ PROTOTYPES = {
     "cirs_actor_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp, fp,
                                 fp, fp]),
     "cirs_policy_eval": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp, fp]),
+    "cirs_actorprob_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp,
+                                    fp, fp]),
+    "cirs_actorprob_eval": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp]),
+    "cirs_rollout_taobao": (i32, [P(TaobaoEnvStruct), P(TrackerWeightsStruct), P(PolicyWeightsStruct), fp, fp, fp,
+                                  i32, fp, fp, fp, fp, fp, fp, fp, fp, fp, u64, fp, i32, i32, i32, fp]),
     "cirs_rollout_workspace_bytes": (i64, [i32, i32]),
     "cirs_rollout_kuaishou": (i32, [P(KuaishouEnvStruct), P(TrackerWeightsStruct), P(PolicyWeightsStruct), fp, fp, fp,
                                     fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, fp, fp, u64, fp, i32, i32, i32,

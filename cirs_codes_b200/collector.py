@@ -27,7 +27,7 @@ import torch
 
 from . import _lib
 from .data import Batch, VectorReplayBuffer
-from .env import KuaishouVectorEnv
+from .env import KuaishouVectorEnv, TaobaoVectorEnv
 from .state_tracker import StateTrackerTransformer
 
 
@@ -46,10 +46,12 @@ class Collector:
         assert buffer.buffer_num >= self.env_num
         self.buffer = buffer
         self.tracker = getattr(preprocess_fn, "__self__", None)
-        self.fused = bool(fused and isinstance(env, KuaishouVectorEnv)
+        self.taobao = isinstance(env, TaobaoVectorEnv)
+        self.fused = bool(fused and isinstance(env, (KuaishouVectorEnv, TaobaoVectorEnv))
                           and isinstance(self.tracker, StateTrackerTransformer)
                           and hasattr(policy, "sample_device") and isinstance(buffer, VectorReplayBuffer)
-                          and buffer.buffer_num == self.env_num and not remove_recommended_ids)
+                          and buffer.buffer_num == self.env_num and not remove_recommended_ids
+                          and getattr(policy, "continuous", False) == self.taobao)
         self.persistent = bool(persistent)    # fused rollout as ONE persistent cooperative kernel (csrc/rollout.cu)
         self.use_graph = bool(use_graph)      # else: replay the per-turn kernels from one captured CUDA graph
         self.data = Batch()
@@ -89,7 +91,7 @@ class Collector:
         assert n_episode == self.env_num, "n_episode must equal the number of environments (collector.py:198-220)"
         start = time.time()
         if self.fused and not random and noise_fn is None:
-            res = self._collect_fused(users)
+            res = self._collect_fused_taobao(users) if self.taobao else self._collect_fused(users)
         else:
             res = self._collect_generic(n_episode, random, users, noise_fn)
         self.collect_step += res["n/st"]
@@ -114,6 +116,9 @@ class Collector:
                 np.issubdtype(np.asarray(self._reset_obs).dtype, np.integer):
             self.buffer._alloc(self.data.obs.shape[-1])
             self.buffer.d_users.copy_(torch.as_tensor(np.asarray(self._reset_obs).reshape(-1).astype(np.int32)))
+        elif isinstance(self.buffer, VectorReplayBuffer) and self.taobao:
+            self.buffer._alloc(self.data.obs.shape[-1], act_dim=27, user_dim=88)
+            self.buffer.d_users_dense.copy_(torch.as_tensor(np.asarray(self._reset_obs)[:, :88].astype(np.float32)))
         step_count = episode_count = cnt_loop = 0
         ep_rews, ep_lens, ep_idxs = [], [], []
         while True:
@@ -131,6 +136,8 @@ class Collector:
                     act = self.policy.exploration_noise(act, self.data)
                 self.data.update(policy=result.get("policy", Batch()), act=act)
             action_remap = self.policy.map_action(self.data.act)
+            if self.taobao:
+                self.data.update(act_env=action_remap)      # the tracker's training pass needs the mapped action
             obs_next, rew, done, info = self.env.step(action_remap, ready)
             cnt_loop += 1
             if self.force_length > 0:
@@ -255,6 +262,45 @@ class Collector:
         self.d2h_bytes += 4 * B + 8 * B
         buf.set_from_device(lens)
         order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
+        res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])
+        res["turns"] = int(lens.max()) if len(lens) else 0
+        return res
+
+    # ---- fused path, VirtualTaobao: the whole collect is ONE kernel, one warp per environment (csrc/rollout_taobao.cu)
+    def _collect_fused_taobao(self, users):
+        env, trk, buf, pol, dev = self.env, self.tracker, self.buffer, self.policy, self.env.device
+        B, T = self.env_num, env.max_turn
+        buf._alloc(trk.dim_state, act_dim=27, user_dim=88)
+        L = buf.sub_size
+        assert L >= T or self.force_length > 0, "buffer_size must be >= env_num * max_turn (SURVEY §9 invariants)"
+        if not hasattr(self, "_f"):
+            self._f = dict(cur=torch.zeros(B, trk.dim_state, dtype=torch.float32, device=dev),
+                           rng=torch.zeros(1, dtype=torch.int64, device=dev),
+                           pin_users=torch.zeros(B, 88, dtype=torch.float32).pin_memory())
+        f = self._f
+        self.h2d_bytes = self.d2h_bytes = 0
+        if torch.is_tensor(users) and users.is_cuda:
+            buf.d_users_dense.copy_(users)
+        else:
+            users = env.draw_users(B) if users is None else np.asarray(users, dtype=np.float32).reshape(B, 88)
+            f["pin_users"].copy_(torch.from_numpy(np.ascontiguousarray(users)))
+            buf.d_users_dense.copy_(f["pin_users"], non_blocking=True)
+            self.h2d_bytes += 4 * 88 * B
+        self.data = Batch()
+        buf.reset()
+        trk.build_state(dim_batch=B, reset=True)
+        max_steps = self.force_length if self.force_length > 0 else T
+        mode = 1 if (pol._deterministic_eval and not pol.training) else 0
+        _lib.call("cirs_rollout_taobao", C.byref(env._struct_raw), C.byref(trk._w), C.byref(pol._w),
+                  _lib.ptr(buf.d_users_dense), _lib.ptr(env.active), _lib.ptr(f["cur"]), L, _lib.ptr(buf.obs),
+                  _lib.ptr(buf.obs_next), _lib.ptr(buf.d_act), _lib.ptr(buf.d_act_env), _lib.ptr(buf.d_rew),
+                  _lib.ptr(buf.d_done), _lib.ptr(buf.d_len), _lib.ptr(trk.kcache), _lib.ptr(trk.vcache), pol.seed,
+                  _lib.ptr(f["rng"]), mode, max_steps, self.force_length, _lib.stream())
+        lens = buf.d_len.cpu().numpy().astype(np.int64)
+        rews = env.cum_rew.cpu().numpy()
+        self.d2h_bytes += 4 * B + 8 * B
+        buf.set_from_device(lens)
+        order = np.lexsort((np.arange(B), lens))
         res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])
         res["turns"] = int(lens.max()) if len(lens) else 0
         return res

@@ -172,6 +172,94 @@ row_loss_kernel(int nA, int64_t ldA, cirs_ppo_config cfg, int n_global, const in
   ws.terms[4 * r + 2] = ent;
 }
 
+// ---- continuous actor (ActorProb + Independent(Normal)): per-row head forward, losses and d loss / d z, one warp per
+// row.  z = h2 W3t + b3, mu = max_action tanh(z), std = exp(sigma);  logp = sum_c Normal.log_prob(a_c)
+// (core/policy/ppo.py:183-187 with dist_fn = Independent(Normal), CIRS-RL-taobao.py:228-232).
+// Writes dz[r][32] = d loss / d z (zero padded) and dsg[r][32] = d loss / d sigma_param contributions of row r.
+#define CIRS_LOG_SQRT_2PI 0.9189385332046727f
+__global__ void __launch_bounds__(256)
+gauss_row_kernel(cirs_policy_weights W, int n, cirs_ppo_config cfg, int n_global, const int32_t* __restrict__ idx,
+                 const float* __restrict__ act, const float* __restrict__ adv, const float* __restrict__ returns,
+                 const float* __restrict__ v_old, const float* __restrict__ logp_old,
+                 const double* __restrict__ adv_stat, Workspace ws, float* __restrict__ dz, float* __restrict__ dsg) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const int nA = W.n_action, slot = idx[r];
+  const float* h2 = ws.h2 + (int64_t)r * HID;
+  float lp = 0.f, en = 0.f, df = 0.f, var = 1.f, t = 0.f;
+  if (lane < nA) {
+    float z = __ldg(W.b3 + lane);
+#pragma unroll 16
+    for (int k = 0; k < HID; ++k) z = fmaf(h2[k], __ldg(W.w3t + (size_t)k * W.ld_action + lane), z);
+    t = tanhf(z);
+    const float mu = W.max_action * t, sg = expf(__ldg(W.sigma + lane));
+    var = sg * sg;
+    df = act[(int64_t)slot * nA + lane] - mu;
+    lp = -(df * df) / (2.0f * var) - logf(sg) - CIRS_LOG_SQRT_2PI;
+    en = 0.5f + CIRS_LOG_SQRT_2PI + logf(sg);   // Normal.entropy = 0.5 + 0.5 log(2 pi) + log(std)
+  }
+  const float logp = warp_sum(lp), ent = warp_sum(en);
+  const float inv_n = 1.0f / (float)n_global;
+  float A = adv[slot];
+  if (cfg.norm_adv) {
+    const double cnt = adv_stat[0], mean = adv_stat[1] / cnt;
+    const double v2 = (adv_stat[2] - cnt * mean * mean) / (cnt - 1.0);
+    A = (float)(((double)A - mean) / sqrt(fmax(v2, 0.0)));
+  }
+  const float ratio = expf(logp - logp_old[slot]);
+  const float lo = 1.0f - cfg.eps_clip, hi = 1.0f + cfg.eps_clip;
+  const float surr1 = ratio * A, surr2 = fminf(fmaxf(ratio, lo), hi) * A;
+  const float clip_i = -fminf(surr1, surr2);
+  const float g1 = surr1 < surr2 ? 1.f : (surr1 == surr2 ? 0.5f : 0.f);
+  const float g2 = surr2 < surr1 ? 1.f : (surr1 == surr2 ? 0.5f : 0.f);
+  const bool in_clip = ratio >= lo && ratio <= hi;
+  const float coef = -(g1 * A + (in_clip ? g2 * A : 0.f)) * ratio * inv_n;   // d loss / d logp_r
+  // d logp / d mu_c = (a - mu) / var;  d mu / d z = max_action (1 - tanh^2);  d logp / d sigma_c = (a-mu)^2 / var - 1;
+  // d (-ent_coef * mean entropy) / d sigma_c = -ent_coef / n
+  float gz = 0.f, gs = 0.f;
+  if (lane < nA) {
+    gz = coef * (df / var) * W.max_action * (1.0f - t * t);
+    gs = coef * ((df * df) / var - 1.0f) - cfg.ent_coef * inv_n;
+  }
+  dz[(int64_t)r * 32 + lane] = gz;
+  dsg[(int64_t)r * 32 + lane] = gs;
+  if (lane != 0) return;
+  const float v = ws.value[r], vo = v_old[slot], R = returns[slot];
+  float vf_i, dvf;
+  if (cfg.value_clip) {
+    const float dvc = v - vo;
+    const float v_clip = vo + fminf(fmaxf(dvc, -cfg.eps_clip), cfg.eps_clip);
+    const float vf1 = (R - v) * (R - v), vf2 = (R - v_clip) * (R - v_clip);
+    vf_i = fmaxf(vf1, vf2);
+    const float w1 = vf1 > vf2 ? 1.f : (vf1 == vf2 ? 0.5f : 0.f);
+    const float w2 = vf2 > vf1 ? 1.f : (vf1 == vf2 ? 0.5f : 0.f);
+    const bool in_v = dvc >= -cfg.eps_clip && dvc <= cfg.eps_clip;
+    dvf = w1 * (-2.f * (R - v)) + (in_v ? w2 * (-2.f * (R - v_clip)) : 0.f);
+  } else {
+    vf_i = (R - v) * (R - v);
+    dvf = -2.f * (R - v);
+  }
+  ws.dv[r] = cfg.vf_coef * dvf * inv_n;
+  ws.terms[4 * r] = clip_i;
+  ws.terms[4 * r + 1] = vf_i;
+  ws.terms[4 * r + 2] = ent;
+}
+
+// out[c] = sum_r m[r][32 + c]-style column sums of an [n, 32] matrix (single CTA, fixed order: deterministic)
+__global__ void __launch_bounds__(256) colsum32_kernel(int n, const float* __restrict__ m, int n_out, float* out) {
+  __shared__ float sh[8][33];
+  const int c = threadIdx.x & 31, part = threadIdx.x >> 5;
+  float s = 0.f;
+  for (int r = part; r < n; r += 8) s += m[(int64_t)r * 32 + c];
+  sh[part][c] = s;
+  __syncthreads();
+  if (part == 0 && c < n_out) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += sh[i][c];
+    out[c] = v;
+  }
+}
+
 // ---- deterministic reduction of the per-row loss terms -> losses[4] = {loss, clip, vf, ent} / n_global
 __global__ void __launch_bounds__(1024)
 loss_reduce_kernel(int n, int n_global, cirs_ppo_config cfg, const float* __restrict__ terms, float* losses) {
@@ -300,9 +388,10 @@ extern "C" int cirs_adv_stats(int32_t n_mb, const int32_t* mb_off, const int32_t
 
 extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_policy_weights* grads,
                                   const cirs_ppo_config* cfg, int32_t n, int32_t n_global, const int32_t* idx,
-                                  const float* obs, const int32_t* act, const float* adv, const float* returns,
+                                  const float* obs, const void* act_v, const float* adv, const float* returns,
                                   const float* v_old, const float* logp_old, const double* adv_stat, float* d_obs,
                                   float* losses, void* workspace, void* stream) {
+  const int32_t* act = reinterpret_cast<const int32_t*>(act_v);
   if (!w || !grads || !cfg || !idx || !obs || !act || !adv || !returns || !v_old || !logp_old || !losses ||
       !workspace || n < 0 || n_global < n || (cfg->norm_adv && !adv_stat)) {
     cirs_set_error("cirs_ppo_minibatch: bad argument");
@@ -320,11 +409,36 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
     cudaMemsetAsync(losses, 0, 4 * sizeof(float), st);
     return CIRS_OK;
   }
-  Workspace ws = carve(workspace, n, ldA);
+  const bool gauss = w->sigma != nullptr;
+  if (gauss && (nA > 32 || !grads->sigma)) {
+    cirs_set_error("cirs_ppo_minibatch: continuous actor needs n_action <= 32 and grads->sigma");
+    return CIRS_ERR_ARG;
+  }
+  Workspace ws = carve(workspace, n, gauss ? 64 : ldA);
 
   // ---- forward
   CIRS_LAUNCH(trunk_fwd_kernel, (n + 63) / 64, 256, 0, st, *w, n, idx, obs, ws.h1, ws.h2, ws.value);
   CIRS_CHECK_LAUNCH();
+  if (gauss) {
+    float* dz = ws.logits;                      // [n, 32] d loss / d z
+    float* dsg = ws.logits + (int64_t)n * 32;   // [n, 32] d loss / d sigma_param, per row
+    CIRS_LAUNCH(gauss_row_kernel, (n + 7) / 8, 256, 0, st, *w, n, *cfg, n_global, idx,
+                reinterpret_cast<const float*>(act_v), adv, returns, v_old, logp_old, adv_stat, ws, dz, dsg);
+    CIRS_CHECK_LAUNCH();
+    CIRS_LAUNCH(loss_reduce_kernel, 1, 1024, 0, st, n, n_global, *cfg, ws.terms, losses);
+    CIRS_CHECK_LAUNCH();
+    // dW3t[k][c] = sum_r h2[r][k] dz[r][c], db3[c] = sum_r dz[r][c]
+    launch_gemm<64, 64, 16, 4>(ColMajorA{ws.h2, HID, nullptr}, RowMajorB{dz, 32, nullptr}, AtomicEp{grads->w3t, ldA},
+                               HID, nA, n, split_for(1, n, 16), grads->b3, st, "gauss_dW3_gemm");
+    CIRS_CHECK_LAUNCH();
+    CIRS_LAUNCH(colsum32_kernel, 1, 256, 0, st, n, dsg, nA, grads->sigma);
+    CIRS_CHECK_LAUNCH();
+    // dh2[r][k] = sum_c dz[r][c] W3t[k][c]
+    launch_gemm<64, 64, 16, 4>(RowMajorA{dz, 32, nullptr}, ColMajorB{w->w3t, ldA},
+                               StoreEp{ws.dh2, HID, nullptr, 0, nullptr, nullptr, 0}, n, HID, nA, 1, nullptr, st,
+                               "gauss_dh2_gemm");
+    CIRS_CHECK_LAUNCH();
+  } else {
   launch_gemm<64, 128, 16, 8>(RowMajorA{ws.h2, HID, nullptr}, RowMajorB{w->w3t, ldA, nullptr},
                               StoreEp{ws.logits, ldA, w->b3, 0, nullptr, nullptr, 0}, n, nA, HID, 1, nullptr, st, "head_logits_gemm");
   CIRS_CHECK_LAUNCH();
@@ -345,6 +459,7 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   launch_gemm<64, 64, 16, 4>(DlA{dl}, ColMajorB{w->w3t, ldA}, AtomicEp{ws.dh2, HID}, n, HID, nA,
                              split_for((n + 63) / 64, nA, 16), nullptr, st, "head_dh2_gemm");
   CIRS_CHECK_LAUNCH();
+  }
   // ---- critic head + trunk
   CIRS_LAUNCH(critic_grad_kernel, 1, 256, 0, st, n, ws.dv, ws.h2, grads->wv, grads->bv);
   CIRS_CHECK_LAUNCH();
@@ -378,7 +493,7 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
 extern "C" int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grads, float* exp_avg,
                               float* exp_avg_sq, const cirs_ppo_config* cfg, int32_t n_repeat, int32_t n_mb,
                               const int32_t* mb_off_h, const int32_t* mb_off, const int32_t* slots, const float* obs,
-                              const int32_t* act, const float* adv, const float* returns, const float* v_old,
+                              const void* act, const float* adv, const float* returns, const float* v_old,
                               const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats,
                               float* losses, int32_t* opt_state, double* opt_scratch, void* workspace,
                               void* stream) {

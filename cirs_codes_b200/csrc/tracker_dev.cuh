@@ -125,14 +125,15 @@ __device__ __forceinline__ void tracker_token_warp(const cirs_tracker_weights& W
   if (p == 0) {
     const int n_in = W.d_user_in;
     const float* src = W.emb_user ? W.emb_user + (size_t)id * d : src_dense;
-    for (int c = lane; c < n_in; c += 32) y[c] = __ldg(src + c);
+    // dense inputs may live in shared memory or have been written by this kernel: plain loads
+    for (int c = lane; c < n_in; c += 32) y[c] = W.emb_user ? __ldg(src + c) : src[c];
     __syncwarp();
     matvec<SM>(W.user_wt, W.user_b, y, n_in, d, ldd, x, lane, 0);  // ffn_user, state_tracker.py:212
   } else {
     const int n_in = W.d_item_in;  // == d (the gate multiplies the item vector elementwise)
     const float* src = W.emb_item ? W.emb_item + (size_t)id * d : src_dense;
     if (lane == 0) y[0] = rew_k;
-    for (int c = lane; c < n_in; c += 32) y[1 + c] = __ldg(src + c);
+    for (int c = lane; c < n_in; c += 32) y[1 + c] = W.emb_item ? __ldg(src + c) : src[c];
     __syncwarp();
     matvec<SM>(W.gate_wt, W.gate_b, y, 1 + n_in, d, ldd, x, lane, 2);  // g = sigmoid(W_g [r;a] + b_g), :239
     for (int c = lane; c < d; c += 32) x[c] *= y[1 + c];            // a' = g * a, :240

@@ -101,14 +101,22 @@ class VectorReplayBuffer:
         self.reset()
 
     # ------------------------------------------------------------------ storage
-    def _alloc(self, dim_state):
+    def _alloc(self, dim_state, act_dim=0, user_dim=0):
+        """act_dim > 0: continuous actions float32 [n, act_dim] (VirtualTaobao) plus the mapped action the environment
+        used (``d_act_env``, the tracker's token input) and dense user features [B, user_dim]."""
         if self._alloc_done:
             return
-        self.dim_state = int(dim_state)
+        self.dim_state, self.act_dim = int(dim_state), int(act_dim)
         n, dev = self.maxsize, self.device
+        if self.act_dim:
+            self._h_act = np.zeros((n, self.act_dim), dtype=np.float32)
+            self._h_act_env = np.zeros((n, self.act_dim), dtype=np.float32)
+            self.d_act_env = torch.zeros(n, self.act_dim, dtype=torch.float32, device=dev)
+            self.d_users_dense = torch.zeros(self.buffer_num, max(int(user_dim), 1), dtype=torch.float32, device=dev)
         self.obs = torch.zeros(n, self.dim_state, dtype=torch.float32, device=dev)
         self.obs_next = torch.zeros(n, self.dim_state, dtype=torch.float32, device=dev)
-        self.d_act = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.d_act = torch.zeros((n, self.act_dim) if self.act_dim else n,
+                                 dtype=torch.float32 if self.act_dim else torch.int32, device=dev)
         self.d_rew = torch.zeros(n, dtype=torch.float32, device=dev)
         self.d_done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.d_len = torch.zeros(self.buffer_num, dtype=torch.int32, device=dev)   # transitions per environment
@@ -123,7 +131,10 @@ class VectorReplayBuffer:
         self._ep_rew = np.zeros(B, dtype=np.float64)
         self._ep_len = np.zeros(B, dtype=np.int64)
         self._ep_idx = self._offset.copy()
-        self._h_act = np.zeros(self.maxsize, dtype=np.int64)
+        ad = getattr(self, "act_dim", 0)
+        self._h_act = np.zeros((self.maxsize, ad), dtype=np.float32) if ad else np.zeros(self.maxsize, dtype=np.int64)
+        if ad:
+            self._h_act_env = np.zeros((self.maxsize, ad), dtype=np.float32)
         self._h_rew = np.zeros(self.maxsize, dtype=np.float64)
         self._h_done = np.zeros(self.maxsize, dtype=bool)
         self._host_valid, self._dev_valid = True, True     # which side holds the truth for act / rew / done
@@ -133,7 +144,9 @@ class VectorReplayBuffer:
     # ------------------------------------------------------------------ host <-> device coherence
     def _sync_host(self):
         if not self._host_valid:
-            self._h_act = self.d_act.cpu().numpy().astype(np.int64)
+            self._h_act = self.d_act.cpu().numpy().astype(np.float32 if self.act_dim else np.int64)
+            if self.act_dim:
+                self._h_act_env = self.d_act_env.cpu().numpy()
             self._h_rew = self.d_rew.cpu().numpy().astype(np.float64)
             self._h_done = self.d_done.cpu().numpy().astype(bool)
             self._host_valid = True
@@ -141,7 +154,9 @@ class VectorReplayBuffer:
     def sync_device(self):
         """Upload host-side act / rew / done / lengths (written by ``add``) before a device-side update."""
         if not self._dev_valid:
-            self.d_act.copy_(torch.from_numpy(self._h_act.astype(np.int32)))
+            self.d_act.copy_(torch.from_numpy(self._h_act.astype(np.float32 if self.act_dim else np.int32)))
+            if self.act_dim:
+                self.d_act_env.copy_(torch.from_numpy(self._h_act_env))
             self.d_rew.copy_(torch.from_numpy(self._h_rew.astype(np.float32)))
             self.d_done.copy_(torch.from_numpy(self._h_done.astype(np.uint8)))
             self.d_len.copy_(torch.from_numpy(self._lengths.astype(np.int32)))
@@ -183,13 +198,18 @@ class VectorReplayBuffer:
         obs / obs_next (torch [n, S] on the device), act, rew, done (numpy).  Returns (ptr, ep_rew, ep_len, ep_idx)."""
         ids = np.arange(self.buffer_num) if buffer_ids is None else np.asarray(buffer_ids, dtype=np.int64)
         obs, obs_next = batch.obs, batch.obs_next
-        self._alloc(obs.shape[-1])
+        raw = np.asarray(batch.act)
+        cont = raw.ndim == 2 and np.issubdtype(raw.dtype, np.floating)
+        self._alloc(obs.shape[-1], act_dim=raw.shape[1] if cont else 0)
         self._sync_host()
-        act = np.asarray(batch.act).reshape(len(ids), -1)[:, 0].astype(np.int64)
+        act = raw.astype(np.float32) if cont else raw.reshape(len(ids), -1)[:, 0].astype(np.int64)
         rew = np.asarray(batch.rew, dtype=np.float64).reshape(-1)
         done = np.asarray(batch.done, dtype=bool).reshape(-1)
         ptr = self._offset[ids] + self._index[ids]                          # base.py:163-183 _add_index
         self._h_act[ptr], self._h_rew[ptr], self._h_done[ptr] = act, rew, done
+        if cont:   # the action the environment saw (policy.map_action), stashed by the Collector
+            env_act = batch.get("act_env") if hasattr(batch, "get") else None
+            self._h_act_env[ptr] = act if env_act is None else np.asarray(env_act, dtype=np.float32)
         pt = torch.as_tensor(ptr, device=self.device)
         self.obs.index_copy_(0, pt, obs.detach().to(torch.float32))
         self.obs_next.index_copy_(0, pt, obs_next.detach().to(torch.float32))

@@ -175,3 +175,132 @@ class KuaishouVectorEnv:
                   _lib.ptr(self.active) if use_active else None, _lib.ptr(d_act), _lib.ptr(rew), _lib.ptr(done),
                   int(L), _lib.ptr(ta), _lib.ptr(tr), _lib.ptr(td), _lib.ptr(ep_len), int(force_length),
                   _lib.stream())
+
+
+class Box:
+    """gym.spaces.Box stand-in (VirtualTB.action_space, virtualTB.py:24)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32, seed=None):
+        self.shape, self.dtype = tuple(shape), dtype
+        self.low = np.full(self.shape, low, dtype=dtype)
+        self.high = np.full(self.shape, high, dtype=dtype)
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self):
+        return self._rng.uniform(self.low, self.high).astype(self.dtype)
+
+    def seed(self, seed=None):
+        self._rng = np.random.default_rng(seed)
+
+
+class TaobaoVectorEnv:
+    """B SimulatedEnv(VirtualTB) training environments (CIRS-RL-taobao.py:152-179) stepped by ONE kernel launch
+    (csrc/env_taobao.cu): Euclidean exit test on the last min(t, N-1) actions (virtualTB.py:126-133), exposure effect
+    over the whole action history (simulated_env.py:147-168) and the reward model ``user_model.forward`` evaluated
+    inside the step (simulated_env.py:77-109; UserModel_MMOE, core/user_model_mmoe.py).
+
+    ``user_model``: the reference's UserModel_MMOE (anything with ``state_dict()``) or that state_dict itself.
+    Observations follow the reference: reset -> float64 [n, 91] = [user 88, 0, 0, 0] (virtualTB.py:54-55); step ->
+    float64 [n, 30] = [action 27, reward, 0, turn] (simulated_env.py:50).  ``step`` expects the action already mapped
+    by ``policy.map_action`` (the Collector does that, collector.py:246-250).
+    The real VirtualTB's click model and new-user generator only consume torch RNG during training and their values
+    are discarded by SimulatedEnv (simulated_env.py:114,138), so they are not evaluated; users are drawn uniformly
+    per one-hot group unless injected (``reset(users=...)``)."""
+
+    is_async = False
+    GROUPS = (8, 8, 11, 11, 11, 11, 2, 2, 3, 18, 3)   # model/UserModel.py:22-32
+
+    def __init__(self, env_num, user_model, *, max_turn=50, num_leave_compute=5, leave_threshold=3.0, tau=10.0,
+                 gamma_exposure=10.0, version="v1", device="cuda", seed=None):
+        from . import params
+        _lib.require_cuda()
+        _lib.load()
+        self.device = torch.device(device)
+        self.env_num, self.max_turn = int(env_num), int(max_turn)
+        dev, B, T = self.device, self.env_num, self.max_turn
+        sd = user_model.state_dict() if hasattr(user_model, "state_dict") else user_model
+        sd = {k: torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).detach().float().cpu()
+              for k, v in sd.items()}
+        self._um_layout = params.mmoe_layout(sd)
+        self._um_flat, out_bias = params.mmoe_pack(self._um_layout, sd, dev)
+        self.user = torch.zeros(B, 88, dtype=torch.float32, device=dev)
+        self.turn = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.hist = torch.zeros(B, T, 27, dtype=torch.float32, device=dev)
+        self.prev_rew = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.cum_rew = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.active = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self.rew = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self.action_space = [Box(-1, 1, (27,), np.float32, None if seed is None else seed + i)
+                             for i in range(min(B, 8))]
+
+        def make(map_action):
+            s = _lib.TaobaoEnvStruct()
+            s.n_env, s.max_turn, s.num_leave_compute = B, T, int(num_leave_compute)
+            s.version, s.map_action = (1 if version == "v1" else 2), int(map_action)
+            s.act_low, s.act_high = -1.0, 1.0
+            s.leave_threshold, s.tau, s.gamma_exposure = float(leave_threshold), float(tau), float(gamma_exposure)
+            params.mmoe_fill(s.um, self._um_layout, self._um_flat, out_bias)
+            s.user, s.turn, s.hist = _lib.ptr(self.user), _lib.ptr(self.turn), _lib.ptr(self.hist)
+            s.prev_rew, s.cum_rew = _lib.ptr(self.prev_rew), _lib.ptr(self.cum_rew)
+            return s
+
+        self._struct = make(0)          # step(): the caller has applied policy.map_action
+        self._struct_raw = make(1)      # fused rollout: raw policy samples, mapped inside the kernel
+        self._rng = np.random.default_rng(seed)
+
+    def __len__(self):
+        return self.env_num
+
+    def seed(self, seed=None):
+        self._rng = np.random.default_rng(seed if not isinstance(seed, (list, tuple)) else seed[0])
+        return [seed] * self.env_num
+
+    def render(self, **kwargs):
+        return None
+
+    def close(self):
+        return None
+
+    def draw_users(self, n):
+        out = np.zeros((n, 88), dtype=np.float32)
+        off = 0
+        for g in self.GROUPS:
+            out[np.arange(n), off + self._rng.integers(0, g, size=n)] = 1.0
+            off += g
+        return out
+
+    def _ids(self, id):
+        if id is None:
+            return np.arange(self.env_num, dtype=np.int64)
+        return np.atleast_1d(np.asarray(id, dtype=np.int64))
+
+    def reset(self, id=None, users=None):
+        ids = self._ids(id)
+        users = self.draw_users(len(ids)) if users is None else np.asarray(users, dtype=np.float32).reshape(len(ids), 88)
+        d_ids = torch.as_tensor(ids.astype(np.int32), device=self.device)
+        self.reset_device(torch.as_tensor(np.ascontiguousarray(users), device=self.device), d_ids)
+        return np.concatenate([users.astype(np.float64), np.zeros((len(ids), 3))], axis=1)
+
+    def step(self, action, id=None):
+        ids = self._ids(id)
+        n = len(ids)
+        act = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, 27))
+        d_ids = torch.as_tensor(ids.astype(np.int32), device=self.device)
+        d_act = torch.as_tensor(act, device=self.device)
+        rew = torch.empty(n, dtype=torch.float32, device=self.device)
+        done = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _lib.call("cirs_taobao_step", C.byref(self._struct), n, _lib.ptr(d_ids), None, _lib.ptr(d_act), None,
+                  _lib.ptr(rew), _lib.ptr(done), 0, None, None, None, None, None, 0, _lib.stream())
+        sel = torch.as_tensor(ids, device=self.device)
+        rew_h = self.prev_rew[sel].cpu().numpy()            # float64 like the reference
+        done_h = done.cpu().numpy().astype(bool)
+        turn = self.turn[sel].cpu().numpy()
+        obs = np.concatenate([act.astype(np.float64), rew_h[:, None], np.zeros((n, 1)), turn[:, None].astype(np.float64)],
+                             axis=1)
+        info = {"env_id": ids, "CTR": self.cum_rew[sel].cpu().numpy() / np.maximum(turn, 1) / 10.0}
+        return obs, rew_h, done_h, info
+
+    def reset_device(self, d_users, d_ids=None):
+        _lib.call("cirs_taobao_reset", C.byref(self._struct), int(d_users.shape[0]), _lib.ptr(d_ids),
+                  _lib.ptr(d_users), _lib.ptr(self.active), _lib.stream())

@@ -52,6 +52,25 @@ class Actor(nn.Module):
         return self
 
 
+class ActorProb(nn.Module):
+    """tianshou/utils/net/continuous.py:120-199 as CIRS-RL-taobao.py:206 uses it: ``ActorProb(net, action_shape,
+    max_action=...)`` -- a ``mu`` layer on the shared trunk and a state-independent ``sigma_param``."""
+
+    def __init__(self, preprocess_net, action_shape, hidden_sizes=(), max_action=1.0, device="cpu", unbounded=False,
+                 conditioned_sigma=False, preprocess_net_output_dim=None):
+        super().__init__()
+        assert not hidden_sizes and not unbounded and not conditioned_sigma, "not on the CIRS hot path"
+        self.device = device
+        self.preprocess = preprocess_net
+        self.output_dim = int(np.prod(action_shape))
+        self.mu = MLP(getattr(preprocess_net, "output_dim", preprocess_net_output_dim), self.output_dim)
+        self.sigma_param = nn.Parameter(torch.zeros(self.output_dim, 1))
+        self._max = float(max_action)
+
+    def to(self, *a, **k):
+        return self
+
+
 class Critic(nn.Module):
     def __init__(self, preprocess_net, hidden_sizes=(), last_size=1, preprocess_net_output_dim=None, device="cpu"):
         super().__init__()

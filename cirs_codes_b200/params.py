@@ -85,25 +85,38 @@ class FlatLayout:
 TRUNK = "preprocess.model.model."
 
 
-def policy_layout(dim_state, n_action, hidden=_lib.HIDDEN):
-    """Trunk first (the duplicated tensors of optim_RL), then actor.last, then critic.last."""
+def policy_layout(dim_state, n_action, hidden=_lib.HIDDEN, continuous=False, max_action=1.0):
+    """Trunk first (the duplicated tensors of optim_RL), then actor.last, then critic.last.
+    ``continuous``: tianshou ActorProb (utils/net/continuous.py:120-199) -- "actor.last" is its ``mu`` layer
+    (n_action <= 32) and ``sigma_param`` [n_action] follows the critic head."""
     L = FlatLayout()
     L.add("trunk.0.weight", "wt", dim_state, hidden)
     L.add("trunk.0.bias", "vec", 1, hidden)
     L.add("trunk.2.weight", "wt", hidden, hidden)
     L.add("trunk.2.bias", "vec", 1, hidden)
     L.n_trunk = L.total
-    L.add("actor.last.weight", "wt", hidden, n_action, pad=128)
-    L.add("actor.last.bias", "vec", 1, n_action, pad=128)
+    pad = 32 if continuous else 128
+    L.add("actor.last.weight", "wt", hidden, n_action, pad=pad)
+    L.add("actor.last.bias", "vec", 1, n_action, pad=pad)
     L.add("critic.last.weight", "vec", 1, hidden)  # reference shape [1, 64] -> contiguous wv[64]
     L.add("critic.last.bias", "vec", 1, 1)
-    L.dim_state, L.n_action = dim_state, n_action
+    if continuous:
+        assert n_action <= 32, "the continuous actor kernels hold one action component per lane"
+        L.add("actor.sigma_param", "vec", 1, n_action)   # reference shape [n_action, 1]
+    L.dim_state, L.n_action, L.continuous, L.max_action = dim_state, n_action, bool(continuous), float(max_action)
     return L
 
 
 def policy_sd_from_reference(actor_sd, critic_sd):
     """Merge the reference's actor / critic state_dicts (the trunk is one shared tensor set)."""
     g = lambda sd, k: sd[k]  # noqa: E731
+    if "sigma_param" in actor_sd:   # ActorProb: mu layer + state-independent log-std
+        return {"trunk.0.weight": g(actor_sd, TRUNK + "0.weight"), "trunk.0.bias": g(actor_sd, TRUNK + "0.bias"),
+                "trunk.2.weight": g(actor_sd, TRUNK + "2.weight"), "trunk.2.bias": g(actor_sd, TRUNK + "2.bias"),
+                "actor.last.weight": g(actor_sd, "mu.model.0.weight"), "actor.last.bias": g(actor_sd, "mu.model.0.bias"),
+                "actor.sigma_param": g(actor_sd, "sigma_param"),
+                "critic.last.weight": g(critic_sd, "last.model.0.weight"),
+                "critic.last.bias": g(critic_sd, "last.model.0.bias")}
     return {"trunk.0.weight": g(actor_sd, TRUNK + "0.weight"), "trunk.0.bias": g(actor_sd, TRUNK + "0.bias"),
             "trunk.2.weight": g(actor_sd, TRUNK + "2.weight"), "trunk.2.bias": g(actor_sd, TRUNK + "2.bias"),
             "actor.last.weight": g(actor_sd, "last.model.0.weight"), "actor.last.bias": g(actor_sd, "last.model.0.bias"),
@@ -114,7 +127,12 @@ def policy_sd_from_reference(actor_sd, critic_sd):
 def policy_sd_to_reference(sd):
     trunk = {TRUNK + "0.weight": sd["trunk.0.weight"], TRUNK + "0.bias": sd["trunk.0.bias"],
              TRUNK + "2.weight": sd["trunk.2.weight"], TRUNK + "2.bias": sd["trunk.2.bias"]}
-    actor = dict(trunk, **{"last.model.0.weight": sd["actor.last.weight"], "last.model.0.bias": sd["actor.last.bias"]})
+    if "actor.sigma_param" in sd:
+        actor = dict(trunk, **{"mu.model.0.weight": sd["actor.last.weight"], "mu.model.0.bias": sd["actor.last.bias"],
+                               "sigma_param": sd["actor.sigma_param"].reshape(-1, 1)})
+    else:
+        actor = dict(trunk, **{"last.model.0.weight": sd["actor.last.weight"],
+                               "last.model.0.bias": sd["actor.last.bias"]})
     critic = dict(trunk, **{"last.model.0.weight": sd["critic.last.weight"].reshape(1, -1),
                             "last.model.0.bias": sd["critic.last.bias"]})
     return actor, critic
@@ -128,7 +146,50 @@ def policy_struct(L, flat):
     s.w3t, s.b3 = L.ptr(flat, "actor.last.weight"), L.ptr(flat, "actor.last.bias")
     s.wv, s.bv = L.ptr(flat, "critic.last.weight"), L.ptr(flat, "critic.last.bias")
     s.flat, s.n_flat, s.n_trunk = flat.data_ptr(), L.total, L.n_trunk
+    s.sigma = L.ptr(flat, "actor.sigma_param") if getattr(L, "continuous", False) else None
+    s.max_action = getattr(L, "max_action", 1.0)
     return s
+
+
+# ---------------------------------------------------------------------------------------------- Taobao reward model
+def mmoe_layout(sd):
+    """UserModel_MMOE parameters used by forward() for dense feature columns and one regression task
+    (core/user_model_mmoe.py:80-98, 144-220).  ``sd``: the reference model's state_dict."""
+    w1, w2 = sd["dnn.linears.0.weight"], sd["dnn.linears.1.weight"]
+    we, wg = sd["mmoe_layer.expert_network.weight"], sd["mmoe_layer.gating_networks.0.weight"]
+    n_in, h1, h2, n_exp = int(w1.shape[1]), int(w1.shape[0]), int(w2.shape[0]), int(wg.shape[0])
+    L = FlatLayout()
+    L.add("linear_model_task.0.weight", "vec", 1, n_in)
+    L.add("dnn.linears.0.weight", "wt", n_in, h1)
+    L.add("dnn.linears.0.bias", "vec", 1, h1)
+    L.add("dnn.linears.1.weight", "wt", h1, h2)
+    L.add("dnn.linears.1.bias", "vec", 1, h2)
+    L.add("mmoe_layer.expert_network.weight", "wt", h2, int(we.shape[0]))
+    L.add("mmoe_layer.expert_network.bias", "vec", 1, int(we.shape[0]))
+    L.add("mmoe_layer.gating_networks.0.weight", "wt", h2, n_exp)
+    L.add("gate_zero_bias", "vec", 1, n_exp)
+    L.add("tower_network.0.weight", "vec", 1, int(we.shape[0]) // n_exp)
+    L.cfg = dict(n_in=n_in, h1=h1, h2=h2, n_expert=n_exp, expert_dim=int(we.shape[0]) // n_exp)
+    return L
+
+
+def mmoe_pack(L, sd, device):
+    sd = dict(sd)
+    sd["gate_zero_bias"] = torch.zeros(L.cfg["n_expert"])
+    return L.pack(sd, device), float(torch.as_tensor(sd["out.0.bias"]).reshape(-1)[0])
+
+
+def mmoe_fill(s, L, flat, out_bias):
+    """Fill a _lib.MMOEStruct in place."""
+    for k, v in L.cfg.items():
+        setattr(s, k, v)
+    s.lin_w = L.ptr(flat, "linear_model_task.0.weight")
+    s.w1t, s.b1 = L.ptr(flat, "dnn.linears.0.weight"), L.ptr(flat, "dnn.linears.0.bias")
+    s.w2t, s.b2 = L.ptr(flat, "dnn.linears.1.weight"), L.ptr(flat, "dnn.linears.1.bias")
+    s.wet, s.be = L.ptr(flat, "mmoe_layer.expert_network.weight"), L.ptr(flat, "mmoe_layer.expert_network.bias")
+    s.wgt, s.bg = L.ptr(flat, "mmoe_layer.gating_networks.0.weight"), L.ptr(flat, "gate_zero_bias")
+    s.tower = L.ptr(flat, "tower_network.0.weight")
+    s.out_bias = out_bias
 
 
 # ---------------------------------------------------------------------------------------------- state tracker

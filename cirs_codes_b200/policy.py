@@ -7,7 +7,9 @@ Host-side mirror of (SURVEY §8b "Policy"):
   tianshou/policy/modelfree/pg.py:10-139            PGPolicy (ret_rms, action scaling)
   tianshou/policy/base.py:13-423                    BasePolicy.update / map_action / compute_episodic_return
 Same constructor keywords, same ``update(0, buffer, batch_size=, repeat=) -> {"loss": [...], ...}`` result.
-Only the discrete actor over the item catalogue (KuaishouEnv) is implemented on the device in this round.
+Both actors of the reference run on the device: the discrete actor over the item catalogue (KuaishouEnv,
+tianshou Actor + Categorical) and the continuous one (VirtualTaobao, tianshou ActorProb + Independent(Normal),
+CIRS-RL-taobao.py:205-246) -- selected by the type of ``actor``.
 
 Multi-GPU: environments are sharded over ranks; each global minibatch is the union of the ranks' local minibatches.
 Gradients are summed with ONE all-reduce per minibatch (torch.distributed, NCCL over NVLink); the advantage
@@ -73,8 +75,10 @@ class PPOPolicy:
         self._gamma, self._lambda = float(discount_factor), float(gae_lambda)
         self._rew_norm, self._batch = bool(reward_normalization), int(max_batchsize)
         self._deterministic_eval = bool(deterministic_eval)
-        self.action_type = "discrete"
+        self.continuous = hasattr(actor, "sigma_param")                     # tianshou ActorProb
+        self.action_type = "continuous" if self.continuous else "discrete"  # pg.py:56-61
         self.action_space = action_space
+        self.action_scaling, self.action_bound_method = bool(action_scaling), action_bound_method
         self.seed, self._calls = int(seed), 0
         self.group = process_group
         self.c_loop = True   # single process: run the repeat x minibatch loop inside one C call (cirs_ppo_learn)
@@ -83,7 +87,8 @@ class PPOPolicy:
 
         dim_state = actor.preprocess.input_dim
         n_action = actor.output_dim
-        self.layout = params.policy_layout(dim_state, n_action)
+        self.layout = params.policy_layout(dim_state, n_action, continuous=self.continuous,
+                                           max_action=getattr(actor, "_max", 1.0))
         self.dim_state, self.n_action = dim_state, n_action
         sd = params.policy_sd_from_reference(actor.state_dict(), critic.state_dict())
         self.flat = self.layout.pack(sd, self.device)
@@ -144,9 +149,19 @@ class PPOPolicy:
             self.ret_rms.t.copy_(torch.as_tensor(sd["ret_rms"], dtype=torch.float64))
 
     def map_action(self, act):
-        """policy/base.py:143-173: identity for a discrete action space (action_bound_method="")."""
+        """policy/base.py:143-173: identity for a discrete action space; for a Box space clip to [-1, 1]
+        (action_bound_method="clip") and scale to [low, high] (action_scaling) in float32 like numpy does."""
         if torch.is_tensor(act):
             act = act.detach().cpu().numpy()
+        if self.continuous and isinstance(act, np.ndarray):
+            if self.action_bound_method == "clip":
+                act = np.clip(act, -1.0, 1.0)
+            elif self.action_bound_method == "tanh":
+                act = np.tanh(act)
+            if self.action_scaling:
+                low = np.asarray(getattr(self.action_space, "low", -1.0), dtype=np.float32)
+                high = np.asarray(getattr(self.action_space, "high", 1.0), dtype=np.float32)
+                act = low + (high - low) * (act + 1.0) / 2.0
         return act
 
     def exploration_noise(self, act, batch):
@@ -188,6 +203,8 @@ class PPOPolicy:
         obs = batch.obs if not isinstance(batch, torch.Tensor) else batch
         obs = torch.as_tensor(obs, dtype=torch.float32, device=self.device).contiguous()
         n = obs.shape[0]
+        if self.continuous:
+            return self._forward_continuous(obs, n, noise_q)
         act = torch.empty(n, dtype=torch.int32, device=self.device)
         logp = torch.empty(n, dtype=torch.float32, device=self.device)
         value = torch.empty(n, dtype=torch.float32, device=self.device)
@@ -198,6 +215,24 @@ class PPOPolicy:
             noise_q = torch.as_tensor(noise_q, dtype=torch.float32, device=self.device).contiguous()
         self.sample_device(n, obs, self.dim_state, act, logp, value, noise_q=noise_q, seen=seen)
         return Batch(logits=None, act=act.long(), state=None, dist=None, logp=logp, value=value)
+
+    def _forward_continuous(self, obs, n, noise_eps):
+        """ppo.py:144-156 with dist_fn = Independent(Normal): act = eps * sigma + mu (raw, unclipped -- the buffer stores
+        this; the environment receives map_action(act)).  ``noise_eps``: N(0,1) draws [n, n_action] (parity runs)."""
+        A = self.n_action
+        act = torch.empty(n, A, dtype=torch.float32, device=self.device)
+        mu = torch.empty(n, A, dtype=torch.float32, device=self.device)
+        logp = torch.empty(n, dtype=torch.float32, device=self.device)
+        value = torch.empty(n, dtype=torch.float32, device=self.device)
+        if noise_eps is not None:
+            noise_eps = torch.as_tensor(noise_eps, dtype=torch.float32, device=self.device).contiguous()
+        mode = 1 if (self._deterministic_eval and not self.training) else 0
+        self._calls += 1
+        _lib.call("cirs_actorprob_sample", C.byref(self._w), n, None, None, _lib.ptr(obs), self.dim_state,
+                  _lib.ptr(noise_eps), self.seed, self._calls, None, mode, _lib.ptr(act), _lib.ptr(logp),
+                  _lib.ptr(value), _lib.ptr(mu), _lib.stream())
+        sigma = self.flat[self.layout.segs["actor.sigma_param"].offset:][:A].exp().expand(n, A)
+        return Batch(logits=(mu, sigma), act=act, state=None, dist=None, logp=logp, value=value)
 
     __call__ = forward
 
@@ -253,10 +288,16 @@ class PPOPolicy:
         ws = self._ppo_ws(1)  # noqa: F841  (allocated lazily in learn)
         aws = self._actor_ws(n)
         st = _lib.stream()
-        _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
-                  _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(aws), st)
-        _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
-                  _lib.ptr(self.v_next), None, _lib.ptr(aws), st)
+        if self.continuous:
+            _lib.call("cirs_actorprob_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
+                      _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), st)
+            _lib.call("cirs_actorprob_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
+                      _lib.ptr(self.v_next), None, st)
+        else:
+            _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
+                      _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(aws), st)
+            _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
+                      _lib.ptr(self.v_next), None, _lib.ptr(aws), st)
         _lib.call("cirs_compute_returns", B, L, _lib.ptr(buffer.d_len), _lib.ptr(self.v_s), _lib.ptr(self.v_next),
                   _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_done), self._gamma, self._lambda,
                   _lib.ptr(self.ret_rms.t) if self._rew_norm else None, _lib.ptr(self._gae_scratch),
@@ -342,7 +383,7 @@ class PPOPolicy:
                 losses_all.append(losses)
         if tracker is not None:
             tracker.zero_grad()
-            tracker.backward_from_buffer(buffer, self.d_obs, buffer.d_users, tok_slot=indices)
+            tracker.backward_from_buffer(buffer, self.d_obs, getattr(buffer, "d_users", None), tok_slot=indices)
             self._allreduce(tracker.grad)
             tracker.optim_step(self.cfg_tracker)                                     # optim_state.step(), :235
         losses = torch.cat(losses_all)

@@ -198,8 +198,12 @@ class StateTrackerTransformer:
         need = lib.cirs_tracker_train_workspace_bytes(C.byref(self._w), B, n_rows)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
-        _lib.call("cirs_tracker_train", C.byref(self._w), C.byref(self._g), B, L, _lib.ptr(users),
-                  _lib.ptr(buffer.d_act), _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_len), None, None, n_tok,
+        dense = not self._w.emb_user
+        _lib.call("cirs_tracker_train", C.byref(self._w), C.byref(self._g), B, L,
+                  None if dense else _lib.ptr(users), None if dense else _lib.ptr(buffer.d_act),
+                  _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_len),
+                  _lib.ptr(buffer.d_users_dense) if dense else None, _lib.ptr(buffer.d_act_env) if dense else None,
+                  n_tok,
                   _lib.ptr(tok_slot), _lib.ptr(env_off), _lib.ptr(d_obs), _lib.ptr(obs_check), _lib.ptr(self._ws),
                   int(self._ws.numel()), _lib.stream())
 

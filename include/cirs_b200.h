@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CIRS_ABI_VERSION 4
+#define CIRS_ABI_VERSION 5
 #define CIRS_MAX_LAYERS 4
 #define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
 
@@ -78,6 +78,64 @@ int cirs_kuaishou_step(const cirs_kuaishou_env* env, int32_t n_rows, const int32
                        const int32_t* act, float* rew, uint8_t* done, int32_t traj_len, int32_t* traj_act,
                        float* traj_rew, uint8_t* traj_done, int32_t* ep_len, int32_t force_length,
                        void* stream);
+
+/* ------------------------------------------------------------------ VirtualTaobao / SimulatedEnv -------- */
+#define CIRS_TB_USER 88 /* one-hot x 11 user features, virtualTB.py:16 */
+#define CIRS_TB_ITEM 27 /* continuous item / action features, virtualTB.py:17 */
+
+/* UserModel_MMOE.forward (core/user_model_mmoe.py:144-220) for dense feature columns and one regression task: the
+ * reward model SimulatedEnv evaluates inside every VirtualTaobao step (simulated_env.py:79-86).  Read only.
+ *   y = x . lin_w  +  tower . (E(h) g(h))  + out_bias,  h = relu(W2 relu(W1 x + b1) + b2),
+ *   E(h) = (We h + be) viewed [expert_dim][n_expert], g(h) = softmax(Wg h)            (core/layers.py:67-116) */
+typedef struct {
+  int32_t n_in;                 /* 118 = 88 user + [prev reward, 0, turn] + 27 item */
+  int32_t h1, h2;               /* dnn_hidden_units, each <= 128 */
+  int32_t n_expert, expert_dim; /* 4, 8: n_expert * expert_dim <= 64, n_expert <= 32 */
+  const float* lin_w;           /* [n_in]  linear_model_task[0].weight */
+  const float *w1t, *b1;        /* dnn.linears.0  Wt[n_in][ld(h1)] */
+  const float *w2t, *b2;        /* dnn.linears.1  Wt[h1][ld(h2)] */
+  const float *wet, *be;        /* mmoe_layer.expert_network  Wt[h2][ld(n_expert*expert_dim)], output o = dim*n_expert + expert */
+  const float *wgt, *bg;        /* mmoe_layer.gating_networks[0]  Wt[h2][ld(n_expert)]; bg = zeros (the layer has no bias) */
+  const float* tower;           /* [expert_dim]  tower_network[0].weight */
+  float out_bias;               /* out[0].bias (PredictionLayer, deepctr layers/core.py:155-161) */
+} cirs_mmoe_weights;
+
+typedef struct {
+  int32_t n_env;    /* B */
+  int32_t max_turn; /* T */
+  int32_t num_leave_compute; /* N (virtualTB.py:126-133: the last min(t, N-1) actions are compared) */
+  int32_t version;  /* 1: r/(1+e)  2: r-e */
+  int32_t map_action; /* 1: `act` is the policy's raw sample and the kernel applies policy.map_action first
+                       * (clip to [-1,1], then low + (high-low)(a+1)/2 in float32; tianshou/policy/base.py:143-173) */
+  float act_low, act_high; /* action_space.low / high (virtualTB.py:24: -1, 1) */
+  double leave_threshold, tau, gamma_exposure; /* python floats in the reference */
+  cirs_mmoe_weights um;
+  /* per-environment state */
+  float* user;      /* [B, 88] cur_user */
+  int32_t* turn;    /* [B] */
+  float* hist;      /* [B, T, 27] history_action (float32 values; the reference keeps them in a float64 array) */
+  double* prev_rew; /* [B] self.reward, a feature of the next step (simulated_env.py:79) */
+  double* cum_rew;  /* [B] */
+} cirs_taobao_env;
+
+/* reset(): virtualTB.py:102-113 + simulated_env.py:59-72 with injected users[n, 88] (the reference samples them
+ * from its generator network, model/UserModel.py:40-60). */
+int cirs_taobao_reset(const cirs_taobao_env* env, int32_t n_rows, const int32_t* env_id, const float* users,
+                      uint8_t* active, void* stream);
+
+/* step(): simulated_env.py:111-168 over virtualTB.py:74-100,126-133 for n_rows environments.
+ *   act[n, 27]      action (raw policy sample when env->map_action, else already mapped)
+ *   act_env[n, 27]  optional out: the action the environment used == obs_next[:, :27] (simulated_env.py:50)
+ *   rew[n], done[n] as in cirs_kuaishou_step; obs_next = [act_env, rew, 0, turn + 1] is assembled by the caller
+ * The real environment's click model and new-user draws (virtualTB.py:84-98) only consume torch RNG and are
+ * discarded by SimulatedEnv (simulated_env.py:114,138); they are not computed.
+ * Optional trajectory outputs: traj_act[B, L, 27] receives `act` as given (the buffer keeps the RAW action,
+ * collector.py:246-250), traj_act_env[B, L, 27] the action the environment used (the tracker's token input when it
+ * is trained), traj_rew / traj_done [B, L], ep_len[B]; force_length as in cirs_kuaishou_step. */
+int cirs_taobao_step(const cirs_taobao_env* env, int32_t n_rows, const int32_t* env_id, uint8_t* active,
+                     const float* act, float* act_env, float* rew, uint8_t* done, int32_t traj_len,
+                     float* traj_act, float* traj_act_env, float* traj_rew, uint8_t* traj_done, int32_t* ep_len,
+                     int32_t force_length, void* stream);
 
 /* ------------------------------------------------------------------ StateTracker ------------------------ */
 typedef struct {
@@ -157,6 +215,11 @@ typedef struct {
   float* flat;     /* base of the flat buffer that holds all of the above, trunk first */
   int64_t n_flat;  /* floats in the flat buffer */
   int64_t n_trunk; /* leading floats that belong to the shared trunk (w1t, b1, w2t, b2) */
+  /* continuous actor (tianshou ActorProb, utils/net/continuous.py:120-199; VirtualTaobao): w3t / b3 are the `mu`
+   * layer Wt[64][ld_action] with n_action <= 32, sigma = ActorProb.sigma_param[n_action] (state independent,
+   * std = exp(sigma)), mean = max_action * tanh(.).  sigma == NULL -> discrete actor over the catalogue. */
+  float* sigma;
+  float max_action;
 } cirs_policy_weights;
 
 /* policy.forward(): core/policy/ppo.py:111-163 for the discrete actor: softmax over the whole catalogue and
@@ -184,6 +247,19 @@ int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_
 int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, const int32_t* row_idx, const float* obs,
                      const int32_t* act, float* value, float* logp, void* workspace, void* stream);
 
+/* policy.forward() for the continuous actor (core/policy/ppo.py:144-156 with dist_fn = Independent(Normal),
+ * CIRS-RL-taobao.py:228-232): mu = max_action * tanh(W3 h + b3), std = exp(sigma); act = eps * std + mu
+ * (torch.normal: multiply then add), eps ~ N(0,1) from noise_eps[n_rows, n_action] (parity runs) or Philox +
+ * Box-Muller; mode 1 -> act = mu (deterministic_eval).  Outputs per row k: act[k, n_action] (RAW, unclipped: this is
+ * what the buffer stores), logp[k] = sum_c Normal.log_prob, value[k]; mu_out[k, n_action] optional. */
+int cirs_actorprob_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_t* env_id,
+                          const uint8_t* active, const float* state, int64_t state_stride, const float* noise_eps,
+                          uint64_t seed, uint64_t offset, uint64_t* rng_counter, int32_t mode, float* act,
+                          float* logp, float* value, float* mu_out, void* stream);
+/* cirs_policy_eval for the continuous actor: act[., n_action] float, indexed like obs. */
+int cirs_actorprob_eval(const cirs_policy_weights* w, int32_t n_rows, const int32_t* row_idx, const float* obs,
+                        const float* act, float* value, float* logp, void* stream);
+
 /* ------------------------------------------------------------------ fused rollout ----------------------- */
 /* A whole Collector.collect(n_episode = B) (core/collector.py:147-367 with the fork's semantics: reset everything,
  * no reset on done, finished environments dropped) in ONE persistent cooperative kernel: reset + user token, then
@@ -201,6 +277,19 @@ int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weigh
                           float* traj_obs_next, int32_t* traj_act, float* traj_rew, uint8_t* traj_done,
                           int32_t* ep_len, float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter,
                           int32_t mode, int32_t max_steps, int32_t force_length, void* workspace, void* stream);
+
+/* A whole Collector.collect(n_episode = B) on SimulatedEnv(VirtualTB) in ONE kernel.  Nothing in a VirtualTaobao turn
+ * couples environments (the action head is 27 wide, not a catalogue), so each warp plays its environment's entire
+ * episode -- user token, then per turn actor -> sample -> map_action -> environment step (incl. the MMOE reward
+ * model) -> tracker token -> replay-buffer slots -- without any grid-wide barrier.  users[B, 88]; traj_act[B, L, 27]
+ * (raw actions), traj_act_env[B, L, 27] (mapped actions); other arrays as in cirs_rollout_kuaishou.  Philox offset of (environment e, turn t) is
+ * *rng_counter + t; the kernel's last warp to finish adds max_steps to *rng_counter.  Same device code as
+ * cirs_actorprob_sample / cirs_taobao_step / cirs_tracker_step (bit-identical results). */
+int cirs_rollout_taobao(const cirs_taobao_env* env, const cirs_tracker_weights* tw, const cirs_policy_weights* pw,
+                        const float* users, uint8_t* active, float* cur_state, int32_t traj_len, float* traj_obs,
+                        float* traj_obs_next, float* traj_act, float* traj_act_env, float* traj_rew,
+                        uint8_t* traj_done, int32_t* ep_len, float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter, int32_t mode,
+                        int32_t max_steps, int32_t force_length, void* stream);
 
 /* ------------------------------------------------------------------ returns (GAE) ----------------------- */
 /* A2CPolicy._compute_returns (a2c.py:80-109) + BasePolicy.compute_episodic_return / _gae_return
@@ -240,10 +329,12 @@ int cirs_adv_stats(int32_t n_mb, const int32_t* mb_off, const int32_t* idx, cons
  *   grads   gradient buffer (same layout as w), OVERWRITTEN with d loss / d params (local partial sums)
  *   d_obs   [., dim_state] d loss / d obs written at the minibatch's slots (the tracker's upstream gradient)
  *   losses  float[4] {loss, clip, vf, ent}: local partial sums already divided by n_global
+ * act: int32 per slot (discrete actor) or float[., n_action] per slot (continuous actor, w->sigma != NULL: Gaussian
+ *      log-prob / entropy, gradients into w3t / b3 / sigma; core/policy/ppo.py:181-220 with Independent(Normal)).
  * workspace: cirs_ppo_workspace_bytes(n_max, n_action). */
 int64_t cirs_ppo_workspace_bytes(int32_t n_rows, int32_t n_action);
 int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_policy_weights* grads, const cirs_ppo_config* cfg,
-                       int32_t n, int32_t n_global, const int32_t* idx, const float* obs, const int32_t* act,
+                       int32_t n, int32_t n_global, const int32_t* idx, const float* obs, const void* act,
                        const float* adv, const float* returns, const float* v_old, const float* logp_old,
                        const double* adv_stat, float* d_obs, float* losses, void* workspace, void* stream);
 
@@ -265,7 +356,7 @@ int cirs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
 int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grads, float* exp_avg,
                    float* exp_avg_sq, const cirs_ppo_config* cfg, int32_t n_repeat, int32_t n_mb,
                    const int32_t* mb_off_h, const int32_t* mb_off, const int32_t* slots, const float* obs,
-                   const int32_t* act, const float* adv, const float* returns, const float* v_old,
+                   const void* act, const float* adv, const float* returns, const float* v_old,
                    const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats, float* losses,
                    int32_t* opt_state, double* opt_scratch, void* workspace, void* stream);
 

@@ -58,6 +58,59 @@ def make_policy(z, c, tracker, prefix="init/", **over):
     return cb.PPOPolicy(actor, critic, optim, torch.distributions.Categorical, **kw)
 
 
+# ---------------------------------------------------------------- VirtualTaobao builders
+def taobao_user_model(z):
+    return {k[len("usermodel/"):]: torch.tensor(np.asarray(z[k])) for k in z.files if k.startswith("usermodel/")}
+
+
+def make_taobao_env(z, c, B=None, **over):
+    kw = dict(max_turn=c["T"], num_leave_compute=c["N"], leave_threshold=c["thr"], tau=c["tau"],
+              gamma_exposure=c["gamma_exposure"], version=c["version"])
+    kw.update(over)
+    return cb.TaobaoVectorEnv(B or c["B"], taobao_user_model(z), **kw)
+
+
+def make_taobao_tracker(z, c, B=None, prefix="init/tracker/"):
+    cols = cb.get_dataset_columns(c["d"], envname="VirtualTB-v0")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        trk = cb.StateTrackerTransformer(cols[0], cols[1], cols[2], dim_model=c["d"], dim_state=20,
+                                         dim_max_batch=B or c["B"], dataset="VirtualTB-v0",
+                                         has_user_embedding=cols[3], has_action_embedding=cols[4],
+                                         has_feedback_embedding=cols[5], nhead=c["nhead"], d_hid=128, nlayers=2,
+                                         dropout=0.0, device="cuda", seed=c["seed"], MAX_TURN=c["T"])
+    if z is not None and prefix is not None:
+        trk.load_state_dict({k[len(prefix):]: torch.tensor(np.asarray(z[k])) for k in z.files if k.startswith(prefix)})
+    return trk
+
+
+def make_taobao_policy(z, c, tracker, prefix="init/", load=True, **over):
+    from cirs_codes_b200.env import Box
+    net = cb.Net(20, hidden_sizes=[64, 64])
+    actor, critic = cb.ActorProb(net, (27,), max_action=1.0), cb.Critic(net)
+    if load:
+        actor.load_state_dict({k[len(prefix + "actor/"):]: torch.tensor(np.asarray(z[k])) for k in z.files
+                               if k.startswith(prefix + "actor/")})
+        critic.load_state_dict({k[len(prefix + "critic/"):]: torch.tensor(np.asarray(z[k])) for k in z.files
+                                if k.startswith(prefix + "critic/")})
+    else:
+        torch.manual_seed(c["seed"])
+        cb.orthogonal_init(actor, critic)
+    optim = [torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=1e-3)]
+    if tracker is not None:
+        optim.append(torch.optim.Adam(tracker.parameters(), lr=1e-3))
+
+    def dist(*logits):
+        return torch.distributions.Independent(torch.distributions.Normal(*logits), 1)
+
+    kw = dict(discount_factor=0.95, max_grad_norm=0.5, eps_clip=0.2, vf_coef=0.25, ent_coef=0.0,
+              reward_normalization=1, advantage_normalization=1, recompute_advantage=0, value_clip=1,
+              gae_lambda=0.95, action_space=Box(-1, 1, (27,)))
+    kw.update(over)
+    return cb.PPOPolicy(actor, critic, optim, dist, **kw)
+
+
 def synthetic_case(U=64, I=300, B=16, T=10, N=3, thr=1, d=32, nhead=4, seed=5, **kw):
     tb = synth.kuaishou_tables(U, I, seed=seed)
     c = dict(U=U, I=I, B=B, T=T, N=N, thr=thr, d=d, nhead=nhead, seed=seed, tau=100.0, gamma_exposure=10.0,
