@@ -235,6 +235,7 @@ def gpu_arm(args, cfg):
         if resident:
             users_all = [torch.as_tensor(u.astype(np.int32), device=dev) for u in users_all]
         steps, h2d, d2h, lens_all, ms = 0, 0, 0, [], 0.0
+        per_step = []
         barrier()
         for k in range(K):
             flush.fill_(float(k))                       # evict L2 between timed iterations (untimed)
@@ -245,6 +246,7 @@ def gpu_arm(args, cfg):
             e1.record()
             torch.cuda.synchronize()
             ms += e0.elapsed_time(e1)
+            per_step.append(round(e0.elapsed_time(e1), 3))
             steps += res["n/st"]
             lens_all.append(res["lens"])
             h2d += col.h2d_bytes + pol.h2d_bytes
@@ -256,6 +258,7 @@ def gpu_arm(args, cfg):
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             ms, steps = float(tm[0]), float(t[1])
+        timed.per_step = per_step
         return ms, steps, h2d / K, d2h / K, np.concatenate(lens_all)
 
     clocks = Clocks(dev.index or 0)
@@ -265,6 +268,7 @@ def gpu_arm(args, cfg):
     one_step(torch.as_tensor(rng.integers(0, cfg["U"], size=B).astype(np.int32), device=dev), True)
     l0 = lib.cirs_launch_count()
     ms_res, steps_res, _, _, lens = timed(args.steps, True)
+    per_step_res = list(timed.per_step)
     launches = lib.cirs_launch_count() - l0
     ms_e2e, steps_e2e, h2d, d2h, _ = timed(args.steps, False)
     clk = clocks.stop()
@@ -333,7 +337,7 @@ def gpu_arm(args, cfg):
             "config": {"workload": cfg["name"], "envs_per_gpu": B, "global_envs": B * world,
                        "mean_episode_len": float(np.mean(lens)), "env_steps_per_step": steps_res / args.steps,
                        "parallelism": f"env-sharded dp{world}", "l2": "192 MB flush between timed iterations",
-                       "timing": "CUDA events per step, max over ranks"},
+                       "timing": "CUDA events per step, max over ranks", "ms_each_step_rank0": per_step_res},
             "e2e": {"value": steps_e2e / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,

@@ -285,8 +285,7 @@ class PPOPolicy:
             self._gae_scratch = torch.zeros(2 * B, dtype=torch.float64, device=dev)
             self._moments = torch.zeros(3, dtype=torch.float64, device=dev)
         n = indices.numel()
-        ws = self._ppo_ws(1)  # noqa: F841  (allocated lazily in learn)
-        aws = self._actor_ws(n)
+        aws = self._actor_ws(n_slots)   # sized for a full buffer once: no allocation inside later updates
         st = _lib.stream()
         if self.continuous:
             _lib.call("cirs_actorprob_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
@@ -344,7 +343,8 @@ class PPOPolicy:
             self.h2d_bytes += 4 * n
             return torch.as_tensor(idx_h[np.random.permutation(n)].astype(np.int32), device=dev)   # batch.py:736
 
-        ws = self._ppo_ws(int(max(sizes)))
+        # a chunk of Batch.split(merge_last) never exceeds 2 * batch_size - 1 rows: size the workspace once
+        ws = self._ppo_ws(max(int(max(sizes)), min(buffer.maxsize, 2 * int(batch_size) - 1)))
         d_obs = self.d_obs if tracker is not None else None
         if world == 1 and self.c_loop:
             # single process: the whole repeat x minibatch loop is one C call (csrc/ppo.cu cirs_ppo_learn)

@@ -196,8 +196,9 @@ class StateTrackerTransformer:
             tok_slot = None
         n_rows = n_tok if compact else B * L
         need = lib.cirs_tracker_train_workspace_bytes(C.byref(self._w), B, n_rows)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+        if self._ws is None or self._ws.numel() < need:   # sized for a full buffer once: no allocation in later updates
+            need = max(need, lib.cirs_tracker_train_workspace_bytes(C.byref(self._w), B, B * L))
+            self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
         dense = not self._w.emb_user
         _lib.call("cirs_tracker_train", C.byref(self._w), C.byref(self._g), B, L,
                   None if dense else _lib.ptr(users), None if dense else _lib.ptr(buffer.d_act),
