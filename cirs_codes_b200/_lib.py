@@ -107,6 +107,8 @@ PROTOTYPES = {
                                  fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp]),
     "cirs_ppo_learn": (i32, [P(PolicyWeightsStruct), P(PolicyWeightsStruct), fp, fp, P(PPOConfigStruct), i32, i32,
                              fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp]),
+    "cirs_head_tc_enable": (None, [i32]),
+    "cirs_head_tc_timeout": (i32, []),
     "cirs_clip_adam": (i32, [fp, fp, fp, fp, i64, i64, P(PPOConfigStruct), fp, fp, fp]),
 }
 

@@ -10,6 +10,12 @@
 // and the running winner of the exponential race  argmax_j  logit_j - log q_j.  Partials per (split, row) go to
 // the workspace and a second tiny kernel merges the splits and emits act / log_prob / value.
 #include "actor_dev.cuh"
+#include "head_tc.cuh"
+
+namespace cirs_head_tc {
+int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_idx, const float* obs,
+                   const int32_t* act, float* value, float* logp, void* workspace, cudaStream_t st);
+}
 
 namespace {
 using namespace cirs_actor;
@@ -53,7 +59,9 @@ extern "C" int64_t cirs_actor_workspace_bytes(int32_t n_rows, int32_t n_action) 
   const int n_tiles = (n_action + BN - 1) / BN;
   int64_t splits = pick_split(n_rows, n_action);
   if (splits > n_tiles) splits = n_tiles;
-  return (int64_t)sizeof(Partial) * (splits + 1) * (int64_t)(n_rows > 0 ? n_rows : 1) + 256;
+  const int64_t ffma = (int64_t)sizeof(Partial) * (splits + 1) * (int64_t)(n_rows > 0 ? n_rows : 1) + 256;
+  const int64_t tc = cirs_head_tc::policy_eval_tc_workspace_bytes(n_rows > 0 ? n_rows : 1);
+  return ffma > tc ? ffma : tc;
 }
 
 extern "C" int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_t* env_id,
@@ -82,6 +90,9 @@ extern "C" int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, co
     return CIRS_ERR_ARG;
   }
   if (n_rows == 0) return CIRS_OK;
+  if (act && w->sigma == nullptr && w->dim_state <= 32 &&
+      cirs_head_tc::head_tc_enabled(n_rows, w->n_action, w->ld_action))
+    return cirs_head_tc::policy_eval_tc(w, n_rows, row_idx, obs, act, value, logp, workspace, (cudaStream_t)stream);
   HeadArgs P{};
   P.W = *w; P.n_rows = n_rows; P.gather = row_idx; P.state_by_k = 0; P.out_by_k = 0; P.active = nullptr;
   P.state = obs; P.state_stride = w->dim_state; P.noise_q = nullptr; P.mode = MODE_EVAL; P.seen = nullptr;

@@ -1,0 +1,407 @@
+// Actor head over the item catalogue on tcgen05 tensor cores (see head_tc.cuh for the three passes).
+// Replaces, for the PPO update (core/policy/ppo.py:181-220) and the policy evaluation of process_fn (ppo.py:96-109),
+// the FP32-FFMA tile GEMMs  logits = h2 W3t + b3,  dW3t = h2^T dlogits,  dh2 = dlogits W3  and the [n, n_action]
+// logits round trip through HBM that they needed.
+//
+// All MMAs are M128 x N64 x K8 kind::tf32 with K-major operands, issued by one thread; every FP32 operand is staged
+// in shared memory as a (hi, lo) pair of TF32-exact tiles and each product is hi.hi + hi.lo + lo.hi (tc_dev.cuh).
+// 256 threads per CTA: thread t owns TMEM lane t % 128 (warp % 4 selects the lane quarter, as tcgen05.ld requires)
+// and the column half t / 128 of each 64-column accumulator.
+#include "common.cuh"
+#include "tc_dev.cuh"
+#include "head_tc.cuh"
+#include <stdlib.h>
+
+namespace cirs_head_tc {
+using namespace cirs_tc;
+
+namespace {
+constexpr int NT = 256, TM = 128, TN = 64, HID = 64;
+constexpr uint32_t A_BYTES = TM * HID * 4;   // 128-row operand tile (32 KB)
+constexpr uint32_t B_BYTES = TN * HID * 4;   // 64-row operand tile (16 KB)
+constexpr uint32_t A_LBO = TM * 16, A_STEP = 2 * TM * 16;   // K-major, R = 128
+constexpr uint32_t B_LBO = TN * 16, B_STEP = 2 * TN * 16;   // K-major, R = 64
+constexpr uint32_t SBO = 128;
+constexpr uint32_t IDESC = idesc_tf32(TM, TN, 0, 0);
+constexpr int KSTEPS = HID / 8;   // every contraction here has depth 64
+#define LOG_EPS (-15.942385152878742f)            /* log(CATEGORICAL_EPS) */
+#define LOG_1M_EPS (-1.1920929665620963e-07f)     /* log(1 - CATEGORICAL_EPS) */
+
+__device__ int g_tc_timeout = 0;   // set when an mbarrier wait gives up (never expected; checked by the tests)
+
+__device__ __forceinline__ void issue(uint32_t d, const char* a_hi, const char* a_lo, const char* b_hi, const char* b_lo,
+                                      bool accumulate) {
+  mma_3xtf32(d, smem_u32(a_hi), smem_u32(a_lo), A_STEP, A_LBO, SBO, smem_u32(b_hi), smem_u32(b_lo), B_STEP, B_LBO, SBO,
+             IDESC, KSTEPS, accumulate);
+}
+__device__ __forceinline__ void wait_or_flag(uint64_t* bar, uint32_t parity) {
+  if (!mbar_wait(bar, parity)) g_tc_timeout = 1;
+}
+
+// ------------------------------------------------------------------------------------------------- pass F
+constexpr size_t F_SMEM = 2 * A_BYTES + 2 * B_BYTES + 64 * 4 + 2 * NT * 4;
+
+__global__ void __launch_bounds__(NT, 2)
+head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act, int tiles_per_split,
+                     int n_split, float* __restrict__ pm, float* __restrict__ ps, float* __restrict__ la) {
+  extern __shared__ __align__(1024) char smem[];
+  char* a_hi = smem;
+  char* a_lo = a_hi + A_BYTES;
+  char* b_hi = a_lo + A_BYTES;
+  char* b_lo = b_hi + B_BYTES;
+  float* sb3 = reinterpret_cast<float*>(b_lo + B_BYTES);
+  float* sm = sb3 + 64;
+  float* ss = sm + NT;
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int r0 = blockIdx.x * TM, split = blockIdx.y;
+  const int n_tiles = (H.nA + TN - 1) / TN;
+  const int ct0 = split * tiles_per_split, ct1 = min(n_tiles, ct0 + tiles_per_split);
+  if (warp == 0) tmem_alloc(&tmem_base, 64);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  tile_stage(a_hi, a_lo, TM, HID, tid, NT, [&](int r, int c4) {
+    return r0 + r < H.n ? ld4(H.h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  });
+  int a = -1;
+  if (act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
+  float m = -INFINITY, s = 0.f, lav = 0.f;
+  bool found = false;
+  uint32_t ph = 0, tb = 0;
+  for (int ct = ct0; ct < ct1; ++ct) {
+    const int c0 = ct * TN;
+    tile_stage_T(b_hi, b_lo, TN, HID, tid, NT, [&](int r, int c) { return __ldg(H.w3t + (size_t)c * H.ldA + c0 + r); });
+    if (tid < TN) sb3[tid] = c0 + tid < H.nA ? __ldg(H.b3 + c0 + tid) : 0.f;
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    tb = tmem_base;
+    if (tid == 0) {
+      issue(tb, a_hi, a_lo, b_hi, b_lo, false);
+      mma_commit(&bar);
+    }
+    wait_or_flag(&bar, ph);
+    ph ^= 1;
+    fence_after_sync();
+    float v[32];
+    tmem_ld32(tmem_addr(tb, (warp & 3) * 32, half * 32), v);
+    const int cb = c0 + half * 32;
+    float mt = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = cb + j < H.nA ? v[j] + sb3[half * 32 + j] : -INFINITY;
+      v[j] = x;
+      mt = fmaxf(mt, x);
+    }
+    if (a >= cb && a < cb + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j == a - cb) lav = v[j];
+      found = true;
+    }
+    if (mt > -INFINITY) {
+      const float mn = fmaxf(m, mt);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc += expf(v[j] - mn);
+      s = s * expf(m - mn) + acc;
+      m = mn;
+    }
+    fence_before_sync();
+    __syncthreads();   // the B tile and the accumulator are free again
+  }
+  sm[tid] = m;
+  ss[tid] = s;
+  __syncthreads();
+  if (half == 0 && r0 + row < H.n) {
+    const float m1 = sm[tid + TM], s1 = ss[tid + TM];
+    const float M = fmaxf(m, m1);
+    float S = 0.f;
+    if (m > -INFINITY) S += s * expf(m - M);
+    if (m1 > -INFINITY) S += s1 * expf(m1 - M);
+    pm[(size_t)(r0 + row) * n_split + split] = M;
+    ps[(size_t)(r0 + row) * n_split + split] = S;
+  }
+  if (found) la[r0 + row] = lav;
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------------- pass B2
+constexpr size_t B2_SMEM = 2 * A_BYTES + 4 * B_BYTES + 2 * A_BYTES + 64 * 4 + NT * 4;
+
+__global__ void __launch_bounds__(NT, 1)
+head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
+                   const float* __restrict__ coef, const int32_t* __restrict__ acta, int tiles_per_split, int n_split,
+                   float* __restrict__ dh2_part, float* __restrict__ ent_part) {
+  extern __shared__ __align__(1024) char smem[];
+  char* a_hi = smem;                 // h2 tile            (A of MMA1)
+  char* a_lo = a_hi + A_BYTES;
+  char* bn_hi = a_lo + A_BYTES;      // W3 tile, r = column, c = hidden   (B of MMA1)
+  char* bn_lo = bn_hi + B_BYTES;
+  char* bk_hi = bn_lo + B_BYTES;     // W3 tile, r = hidden, c = column   (B of MMA2)
+  char* bk_lo = bk_hi + B_BYTES;
+  char* dl_hi = bk_lo + B_BYTES;     // d logits tile, r = row, c = column (A of MMA2)
+  char* dl_lo = dl_hi + A_BYTES;
+  float* sb3 = reinterpret_cast<float*>(dl_lo + A_BYTES);
+  float* se = sb3 + 64;
+  __shared__ __align__(8) uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int r0 = blockIdx.x * TM, split = blockIdx.y;
+  const int n_tiles = (H.nA + TN - 1) / TN;
+  const int ct0 = split * tiles_per_split, ct1 = min(n_tiles, ct0 + tiles_per_split);
+  if (warp == 0) tmem_alloc(&tmem_base, 128);
+  if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
+  tile_stage(a_hi, a_lo, TM, HID, tid, NT, [&](int r, int c4) {
+    return r0 + r < H.n ? ld4(H.h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  });
+  const bool live = r0 + row < H.n;
+  const float rm = live ? rowm[r0 + row] : 0.f, iz = live ? rinvz[r0 + row] : 0.f, cf = live ? coef[r0 + row] : 0.f;
+  const int a = live ? acta[r0 + row] : -1;
+  const float log_z = iz > 0.f ? -logf(iz) : 0.f;
+  float ent = 0.f;
+  uint32_t ph = 0, tb = 0;
+  for (int ct = ct0; ct < ct1; ++ct) {
+    const int c0 = ct * TN;
+    tile_stage_T(bn_hi, bn_lo, TN, HID, tid, NT, [&](int r, int c) { return __ldg(H.w3t + (size_t)c * H.ldA + c0 + r); });
+    if (tid < TN) sb3[tid] = c0 + tid < H.nA ? __ldg(H.b3 + c0 + tid) : 0.f;
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    tb = tmem_base;
+    if (tid == 0) {
+      issue(tb, a_hi, a_lo, bn_hi, bn_lo, false);        // D1 = logits tile - b3
+      mma_commit(&bar1);
+    }
+    if (ct > ct0) wait_or_flag(&bar2, ph ^ 1);            // previous MMA2 has finished reading bk / dl
+    tile_stage(bk_hi, bk_lo, HID, TN, tid, NT,
+               [&](int r, int c4) { return ld4(H.w3t + (size_t)r * H.ldA + c0 + 4 * c4); });
+    wait_or_flag(&bar1, ph);
+    fence_after_sync();
+    float v[32];
+    tmem_ld32(tmem_addr(tb, (warp & 3) * 32, half * 32), v);
+    const int cb = c0 + half * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = v[j] + sb3[half * 32 + j];
+      const float p = cb + j < H.nA ? expf(x - rm) * iz : 0.f;
+      // entropy of Categorical(probs): -sum p log(clamp(p, eps, 1 - eps)); log p = x - max - log Z inside the clamp
+      const float lg = p < CATEGORICAL_EPS ? LOG_EPS : (p > 1.0f - CATEGORICAL_EPS ? LOG_1M_EPS : x - rm - log_z);
+      ent = fmaf(-p, lg, ent);
+      v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      tile_store_split(dl_hi, dl_lo, TM, row, half * 8 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 0) {
+      issue(tb + 64, dl_hi, dl_lo, bk_hi, bk_lo, ct > ct0);   // D2 += d logits . W3   (K = this tile's 64 columns)
+      mma_commit(&bar2);
+    }
+    ph ^= 1;
+  }
+  if (ct1 > ct0) wait_or_flag(&bar2, ph ^ 1);
+  fence_after_sync();
+  if (ct1 > ct0) {
+    float v[32];
+    tmem_ld32(tmem_addr(tb + 64, (warp & 3) * 32, half * 32), v);
+    if (live) {
+      float* dst = dh2_part + ((size_t)split * H.n + r0 + row) * HID + half * 32;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  }
+  se[tid] = ent;
+  fence_before_sync();
+  __syncthreads();
+  if (half == 0 && live) ent_part[(size_t)(r0 + row) * n_split + split] = ent + se[tid + TM];
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------- pass B3
+constexpr size_t B3_SMEM = 2 * A_BYTES + 4 * B_BYTES + 2 * A_BYTES + 4 * 64 * 4;
+
+__global__ void __launch_bounds__(NT, 1)
+head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
+                   const float* __restrict__ coef, const int32_t* __restrict__ acta, int rows_per_split, int n_rsplit,
+                   float* __restrict__ g_w3t, float* __restrict__ g_b3) {
+  extern __shared__ __align__(1024) char smem[];
+  char* wa_hi = smem;                // W3 tile, r = column (128), c = hidden   (A of MMA1')
+  char* wa_lo = wa_hi + A_BYTES;
+  char* hb_hi = wa_lo + A_BYTES;     // h2 tile, r = row (64), c = hidden       (B of MMA1')
+  char* hb_lo = hb_hi + B_BYTES;
+  char* ht_hi = hb_lo + B_BYTES;     // h2 tile, r = hidden, c = row            (B of MMA3)
+  char* ht_lo = ht_hi + B_BYTES;
+  char* dl_hi = ht_lo + B_BYTES;     // d logits^T tile, r = column, c = row    (A of MMA3)
+  char* dl_lo = dl_hi + A_BYTES;
+  float* srm = reinterpret_cast<float*>(dl_lo + A_BYTES);
+  float* siz = srm + 64;
+  float* scf = siz + 64;
+  int* sac = reinterpret_cast<int*>(scf + 64);
+  __shared__ __align__(8) uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, cl = tid & 127, half = tid >> 7;
+  const int c0 = blockIdx.x * TM, col = c0 + cl;
+  const int rs0 = blockIdx.y * rows_per_split, rs1 = min(H.n, rs0 + rows_per_split);
+  if (warp == 0) tmem_alloc(&tmem_base, 128);
+  if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
+  tile_stage_T(wa_hi, wa_lo, TM, HID, tid, NT, [&](int r, int c) { return __ldg(H.w3t + (size_t)c * H.ldA + c0 + r); });
+  const bool live = col < H.nA;
+  const float b3v = live ? __ldg(H.b3 + col) : 0.f;
+  float db3 = 0.f;
+  uint32_t ph = 0, tb = 0;
+  for (int r0 = rs0; r0 < rs1; r0 += TN) {
+    tile_stage(hb_hi, hb_lo, TN, HID, tid, NT, [&](int r, int c4) {
+      return r0 + r < rs1 ? ld4(H.h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    });
+    if (tid < TN) {
+      const bool ok = r0 + tid < rs1;
+      srm[tid] = ok ? rowm[r0 + tid] : 0.f;
+      siz[tid] = ok ? rinvz[r0 + tid] : 0.f;
+      scf[tid] = ok ? coef[r0 + tid] : 0.f;
+      sac[tid] = ok ? acta[r0 + tid] : -1;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    tb = tmem_base;
+    if (tid == 0) {
+      issue(tb, wa_hi, wa_lo, hb_hi, hb_lo, false);       // D1' = (logits tile)^T - b3: lane = column, 64 rows
+      mma_commit(&bar1);
+    }
+    if (r0 > rs0) wait_or_flag(&bar2, ph ^ 1);             // previous MMA3 has finished reading ht / dl
+    tile_stage_T(ht_hi, ht_lo, HID, TN, tid, NT,
+                 [&](int r, int c) { return r0 + c < rs1 ? H.h2[(size_t)(r0 + c) * HID + r] : 0.f; });
+    wait_or_flag(&bar1, ph);
+    fence_after_sync();
+    float v[32];
+    tmem_ld32(tmem_addr(tb, (warp & 3) * 32, half * 32), v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int jj = half * 32 + j;
+      const float p = expf(v[j] + b3v - srm[jj]) * siz[jj];
+      const float d = live ? scf[jj] * ((sac[jj] == col ? 1.f : 0.f) - p) : 0.f;
+      db3 += d;
+      v[j] = d;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      tile_store_split(dl_hi, dl_lo, TM, cl, half * 8 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (tid == 0) {
+      issue(tb + 64, dl_hi, dl_lo, ht_hi, ht_lo, r0 > rs0);   // D3 += d logits^T . h2   (K = this tile's 64 rows)
+      mma_commit(&bar2);
+    }
+    ph ^= 1;
+  }
+  if (rs1 > rs0) {
+    wait_or_flag(&bar2, ph ^ 1);
+    fence_after_sync();
+    float v[32];
+    tmem_ld32(tmem_addr(tb + 64, (warp & 3) * 32, half * 32), v);
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float* dst = g_w3t + (size_t)(half * 32 + j) * H.ldA + col;
+        if (n_rsplit > 1) atomicAdd(dst, v[j]); else *dst += v[j];
+      }
+      atomicAdd(g_b3 + col, db3);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+template <class K>
+void set_smem(K kernel, size_t bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+void tiles_for(int nA, int n_split, int* tiles_per_split) {
+  const int n_tiles = (nA + TN - 1) / TN;
+  *tiles_per_split = (n_tiles + n_split - 1) / n_split;
+}
+}  // namespace
+
+int plan_split(int n, int nA) {
+  const int n_tiles = (nA + TN - 1) / TN, row_tiles = (n + TM - 1) / TM;
+  int want = (2 * 148 + row_tiles - 1) / (row_tiles > 0 ? row_tiles : 1);
+  if (want > MAX_SPLIT) want = MAX_SPLIT;
+  if (want > n_tiles) want = n_tiles;
+  if (want < 1) want = 1;
+  const int per = (n_tiles + want - 1) / want;
+  return (n_tiles + per - 1) / per;
+}
+
+static int g_tc_mode = -1;   // -1: environment default (CIRS_NO_TC), 0: off, 1: on
+bool head_tc_enabled(int n, int nA, int64_t ldA) {
+  if (g_tc_mode < 0) {
+    const char* e = getenv("CIRS_NO_TC");
+    g_tc_mode = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return g_tc_mode == 1 && n > 0 && nA >= TN && (ldA % 128) == 0 && ldA >= nA;
+}
+
+int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n_split, float* pm, float* ps,
+                  float* la, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { set_smem(head_tc_stats_kernel, F_SMEM); once = true; }
+  int per;
+  tiles_for(H.nA, n_split, &per);
+  dim3 grid((H.n + TM - 1) / TM, n_split);
+  CIRS_LAUNCH(head_tc_stats_kernel, grid, NT, F_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+
+int head_tc_dh2(const HeadTc& H, const float* rowm, const float* rinvz, const float* coef, const int32_t* acta,
+                int n_split, float* dh2_part, float* ent_part, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { set_smem(head_tc_dh2_kernel, B2_SMEM); once = true; }
+  int per;
+  tiles_for(H.nA, n_split, &per);
+  dim3 grid((H.n + TM - 1) / TM, n_split);
+  CIRS_LAUNCH(head_tc_dh2_kernel, grid, NT, B2_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part, ent_part);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+
+int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const float* coef, const int32_t* acta,
+                float* g_w3t, float* g_b3, cudaStream_t st) {
+  static bool once = false;
+  if (!once) { set_smem(head_tc_dw3_kernel, B3_SMEM); once = true; }
+  const int n_ct = (H.nA + TM - 1) / TM, row_tiles = (H.n + TN - 1) / TN;
+  int n_rsplit = (3 * 148 + n_ct - 1) / n_ct;
+  if (n_rsplit > row_tiles) n_rsplit = row_tiles;
+  if (n_rsplit < 1) n_rsplit = 1;
+  int tiles_per = (row_tiles + n_rsplit - 1) / n_rsplit;
+  n_rsplit = (row_tiles + tiles_per - 1) / tiles_per;
+  dim3 grid(n_ct, n_rsplit);
+  CIRS_LAUNCH(head_tc_dw3_kernel, grid, NT, B3_SMEM, st, H, rowm, rinvz, coef, acta, tiles_per * TN, n_rsplit, g_w3t,
+              g_b3);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+
+}  // namespace cirs_head_tc
+
+extern "C" void cirs_head_tc_enable(int on) { cirs_head_tc::g_tc_mode = on < 0 ? -1 : (on ? 1 : 0); }
+
+// debug: 1 if any tensor-core kernel gave up waiting on an mbarrier since the last call (synchronises the device)
+extern "C" int cirs_head_tc_timeout(void) {
+  int v = 0, z = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&v, cirs_head_tc::g_tc_timeout, sizeof(int));
+  cudaMemcpyToSymbol(cirs_head_tc::g_tc_timeout, &z, sizeof(int));
+  return v;
+}

@@ -10,6 +10,7 @@
 // Tie semantics follow torch: min / max route half of the gradient to each argument when they are equal, clamp
 // passes the gradient on its closed interval.
 #include "gemm.cuh"
+#include "head_tc.cuh"
 #include "../../include/cirs_b200.h"
 
 namespace {
@@ -19,7 +20,10 @@ constexpr int HID = CIRS_HIDDEN;
 struct Workspace {
   float *h1, *h2, *value, *logits, *dh2, *dz2, *dz1, *rowm, *rinvz, *coef, *rowG, *dv, *terms;
   int32_t* acta;
+  // tensor-core head (head_tc.cu): per-row partials over the catalogue splits
+  float *pm, *ps, *la, *ent_part, *dh2_part;
 };
+constexpr int TC_SPLIT = cirs_head_tc::MAX_SPLIT;
 
 __host__ __device__ inline int64_t align64(int64_t x) { return (x + 63) & ~(int64_t)63; }
 
@@ -31,6 +35,8 @@ Workspace carve(void* base, int64_t n, int64_t ldA) {
   w.dh2 = take(n * HID); w.dz2 = take(n * HID); w.dz1 = take(n * HID);
   w.rowm = take(n); w.rinvz = take(n); w.coef = take(n); w.rowG = take(n); w.dv = take(n); w.terms = take(n * 4);
   w.acta = reinterpret_cast<int32_t*>(take(n));
+  w.pm = take(n * TC_SPLIT); w.ps = take(n * TC_SPLIT); w.la = take(n); w.ent_part = take(n * TC_SPLIT);
+  w.dh2_part = take(n * TC_SPLIT * HID);
   return w;
 }
 
@@ -44,7 +50,7 @@ trunk_fwd_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, 
   const int tid = threadIdx.x, r0 = blockIdx.x * BM, S = W.dim_state;
   for (int i = tid; i < BM * S; i += 256) {
     const int r = i / S, c = i % S;
-    s_in[r][c] = (r0 + r < n) ? obs[(int64_t)idx[r0 + r] * S + c] : 0.f;
+    s_in[r][c] = (r0 + r < n) ? obs[(int64_t)(idx ? idx[r0 + r] : r0 + r) * S + c] : 0.f;
   }
   __syncthreads();
   const int row = tid % BM, cg = tid / BM;
@@ -97,36 +103,14 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
   return r;
 }
 
-// ---- per-row softmax statistics, losses and d loss / d logp, d loss / d value   (one CTA per row)
-__global__ void __launch_bounds__(256)
-row_loss_kernel(int nA, int64_t ldA, cirs_ppo_config cfg, int n_global, const int32_t* __restrict__ idx,
-                const int32_t* __restrict__ act, const float* __restrict__ adv, const float* __restrict__ returns,
-                const float* __restrict__ v_old, const float* __restrict__ logp_old,
-                const double* __restrict__ adv_stat, Workspace ws) {
-  __shared__ float sh[8];
-  const int r = blockIdx.x, tid = threadIdx.x;
-  const float* L = ws.logits + (int64_t)r * ldA;
-  float mx = -INFINITY;
-  for (int c = tid; c < nA; c += 256) mx = fmaxf(mx, L[c]);
-  mx = block_reduce(mx, true, sh);
-  float z = 0.f;
-  for (int c = tid; c < nA; c += 256) z += expf(L[c] - mx);
-  z = block_reduce(z, false, sh);
-  const float invz = 1.0f / z;
-  // Categorical(probs = softmax): probs <- p / sum(p); logits = log(clamp(probs, eps, 1 - eps))
-  float ent = 0.f, pin = 0.f;
-  for (int c = tid; c < nA; c += 256) {
-    const float p = expf(L[c] - mx) * invz;
-    const bool inr = p >= CATEGORICAL_EPS && p <= 1.0f - CATEGORICAL_EPS;
-    const float pc = fminf(fmaxf(p, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS);
-    ent -= p * logf(pc);
-    if (inr) pin += p;
-  }
-  ent = block_reduce(ent, false, sh);
-  pin = block_reduce(pin, false, sh);
-  if (tid != 0) return;
-  const int slot = idx[r], a = act[slot];
-  const float pa = expf(L[a] - mx) * invz;
+// per-row tail shared by the FFMA and the tensor-core paths: Categorical.log_prob of the taken action, clipped
+// surrogate, clipped value loss and the row's d loss / d logp, d loss / d value  (ppo.py:183-207)
+__device__ __forceinline__ void row_finish(int r, int slot, int a, float mx, float invz, float la_logit, float ent,
+                                           float rowG, const cirs_ppo_config& cfg, int n_global,
+                                           const float* __restrict__ adv, const float* __restrict__ returns,
+                                           const float* __restrict__ v_old, const float* __restrict__ logp_old,
+                                           const double* __restrict__ adv_stat, const Workspace& ws) {
+  const float pa = expf(la_logit - mx) * invz;
   const bool inr_a = pa >= CATEGORICAL_EPS && pa <= 1.0f - CATEGORICAL_EPS;
   const float logp = logf(fminf(fmaxf(pa, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS));
   const float inv_n = 1.0f / (float)n_global;
@@ -165,11 +149,102 @@ row_loss_kernel(int nA, int64_t ldA, cirs_ppo_config cfg, int n_global, const in
   ws.dv[r] = cfg.vf_coef * dvf * inv_n;
   ws.rowm[r] = mx;
   ws.rinvz[r] = invz;
-  ws.rowG[r] = ent - pin;   // sum_j g_j p_j with g_j = -(log clamp(p_j) + [p_j in range])
+  ws.rowG[r] = rowG;   // sum_j g_j p_j with g_j = -(log clamp(p_j) + [p_j in range])
   ws.acta[r] = a;
   ws.terms[4 * r] = clip_i;
   ws.terms[4 * r + 1] = vf_i;
   ws.terms[4 * r + 2] = ent;
+}
+
+// ---- per-row softmax statistics, losses and d loss / d logp, d loss / d value   (one CTA per row)
+__global__ void __launch_bounds__(256)
+row_loss_kernel(int nA, int64_t ldA, cirs_ppo_config cfg, int n_global, const int32_t* __restrict__ idx,
+                const int32_t* __restrict__ act, const float* __restrict__ adv, const float* __restrict__ returns,
+                const float* __restrict__ v_old, const float* __restrict__ logp_old,
+                const double* __restrict__ adv_stat, Workspace ws) {
+  __shared__ float sh[8];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* L = ws.logits + (int64_t)r * ldA;
+  float mx = -INFINITY;
+  for (int c = tid; c < nA; c += 256) mx = fmaxf(mx, L[c]);
+  mx = block_reduce(mx, true, sh);
+  float z = 0.f;
+  for (int c = tid; c < nA; c += 256) z += expf(L[c] - mx);
+  z = block_reduce(z, false, sh);
+  const float invz = 1.0f / z;
+  // Categorical(probs = softmax): probs <- p / sum(p); logits = log(clamp(probs, eps, 1 - eps))
+  float ent = 0.f, pin = 0.f;
+  for (int c = tid; c < nA; c += 256) {
+    const float p = expf(L[c] - mx) * invz;
+    const bool inr = p >= CATEGORICAL_EPS && p <= 1.0f - CATEGORICAL_EPS;
+    const float pc = fminf(fmaxf(p, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS);
+    ent -= p * logf(pc);
+    if (inr) pin += p;
+  }
+  ent = block_reduce(ent, false, sh);
+  pin = block_reduce(pin, false, sh);
+  if (tid != 0) return;
+  const int slot = idx[r];
+  row_finish(r, slot, act[slot], mx, invz, L[act[slot]], ent, ent - pin, cfg, n_global, adv, returns, v_old, logp_old,
+             adv_stat, ws);
+}
+
+// ---- tensor-core path: merge the per-split online-softmax partials of pass F, then the same per-row tail
+__global__ void __launch_bounds__(128)
+row_loss_tc_kernel(int n, int n_split, cirs_ppo_config cfg, int n_global, const int32_t* __restrict__ idx,
+                   const int32_t* __restrict__ act, const float* __restrict__ adv, const float* __restrict__ returns,
+                   const float* __restrict__ v_old, const float* __restrict__ logp_old,
+                   const double* __restrict__ adv_stat, Workspace ws) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* pm = ws.pm + (int64_t)r * n_split;
+  const float* ps = ws.ps + (int64_t)r * n_split;
+  float mx = -INFINITY;
+  for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, pm[s]);
+  float z = 0.f;
+  for (int s = 0; s < n_split; ++s) z += ps[s] * expf(pm[s] - mx);
+  const int slot = idx[r];
+  // entropy (terms[4r+2]) and rowG are filled after pass B2 (ent_merge_kernel); rowG is only used when ent_coef != 0
+  row_finish(r, slot, act[slot], mx, 1.0f / z, ws.la[r], 0.f, 0.f, cfg, n_global, adv, returns, v_old, logp_old,
+             adv_stat, ws);
+}
+
+__global__ void ent_merge_kernel(int n, int n_split, const float* __restrict__ ent_part, float* __restrict__ terms) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float e = 0.f;
+  for (int s = 0; s < n_split; ++s) e += ent_part[(int64_t)r * n_split + s];
+  terms[4 * r + 2] = e;
+}
+
+// dz2 = (sum_splits dh2_part + dv * wv) * [h2 > 0]
+__global__ void dz2_tc_kernel(int n, int n_split, const float* __restrict__ dh2_part, const float* __restrict__ dv,
+                              const float* __restrict__ wv, const float* __restrict__ h2, float* __restrict__ dz2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * HID) return;
+  const int r = i / HID, c = i % HID;
+  float d = 0.f;
+  for (int s = 0; s < n_split; ++s) d += dh2_part[(int64_t)s * n * HID + i];
+  dz2[i] = h2[i] > 0.f ? d + dv[r] * __ldg(wv + c) : 0.f;
+}
+
+// policy evaluation (process_fn): merge pass F's partials -> Categorical.log_prob of the stored action; scatter the
+// critic value; outputs are indexed by buffer slot like the FFMA path (actor_combine_row, out_by_k = 0)
+__global__ void eval_merge_kernel(int n, int n_split, const int32_t* __restrict__ idx, const float* __restrict__ pm,
+                                  const float* __restrict__ ps, const float* __restrict__ la,
+                                  const float* __restrict__ vtmp, float* __restrict__ value, float* __restrict__ logp) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int o = idx ? idx[r] : r;
+  if (value) value[o] = vtmp[r];
+  if (!logp) return;
+  float mx = -INFINITY;
+  for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, pm[(int64_t)r * n_split + s]);
+  float z = 0.f;
+  for (int s = 0; s < n_split; ++s) z += ps[(int64_t)r * n_split + s] * expf(pm[(int64_t)r * n_split + s] - mx);
+  float pa = expf(la[r] - mx) / z;
+  pa = fminf(fmaxf(pa, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS);
+  logp[o] = logf(pa);
 }
 
 // ---- continuous actor (ActorProb + Independent(Normal)): per-row head forward, losses and d loss / d z, one warp per
@@ -368,9 +443,33 @@ int split_for(int tiles, int K, int bk) {
 
 }  // namespace
 
+// cirs_policy_eval on the tensor cores (dispatched from actor.cu): trunk -> pass F -> merge.
+namespace cirs_head_tc {
+int64_t policy_eval_tc_workspace_bytes(int64_t n) {
+  return (int64_t)sizeof(float) * (3 * align64(n * HID) / 1 + 2 * align64(n * MAX_SPLIT) + 2 * align64(n)) + 256;
+}
+int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_idx, const float* obs,
+                   const int32_t* act, float* value, float* logp, void* workspace, cudaStream_t st) {
+  float* p = reinterpret_cast<float*>(workspace);
+  auto take = [&](int64_t cnt) { float* r = p; p += align64(cnt); return r; };
+  float *h1 = take((int64_t)n * HID), *h2 = take((int64_t)n * HID), *vtmp = take(n);
+  float *pm = take((int64_t)n * MAX_SPLIT), *ps = take((int64_t)n * MAX_SPLIT), *la = take(n);
+  CIRS_LAUNCH(trunk_fwd_kernel, (n + 63) / 64, 256, 0, st, *w, n, row_idx, obs, h1, h2, vtmp);
+  CIRS_CHECK_LAUNCH();
+  const int n_split = plan_split(n, w->n_action);
+  HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action};
+  const int rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
+  if (rc) return rc;
+  CIRS_LAUNCH(eval_merge_kernel, (n + 255) / 256, 256, 0, st, n, n_split, row_idx, pm, ps, la, vtmp, value, logp);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+}  // namespace cirs_head_tc
+
 extern "C" int64_t cirs_ppo_workspace_bytes(int32_t n_rows, int32_t n_action) {
   const int64_t n = n_rows > 0 ? n_rows : 1, ldA = ((int64_t)n_action + 127) & ~127LL;
-  int64_t cnt = 5 * align64(n * HID) + align64(n * ldA) + 7 * align64(n) + align64(4 * n);
+  int64_t cnt = 5 * align64(n * HID) + align64(n * ldA) + 7 * align64(n) + align64(4 * n) +
+                3 * align64(n * TC_SPLIT) + align64(n) + align64(n * TC_SPLIT * HID);
   return cnt * (int64_t)sizeof(float) + 256;
 }
 
@@ -415,6 +514,8 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
     return CIRS_ERR_ARG;
   }
   Workspace ws = carve(workspace, n, gauss ? 64 : ldA);
+  bool tc = false;
+  int tc_split = 0;
 
   // ---- forward
   CIRS_LAUNCH(trunk_fwd_kernel, (n + 63) / 64, 256, 0, st, *w, n, idx, obs, ws.h1, ws.h2, ws.value);
@@ -438,6 +539,24 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
                                StoreEp{ws.dh2, HID, nullptr, 0, nullptr, nullptr, 0}, n, HID, nA, 1, nullptr, st,
                                "gauss_dh2_gemm");
     CIRS_CHECK_LAUNCH();
+  } else if (cfg->ent_coef == 0.f && cirs_head_tc::head_tc_enabled(n, nA, ldA)) {
+    // ---- actor head on the tensor cores: logits are recomputed per pass and never stored (head_tc.cu)
+    tc = true;
+    tc_split = cirs_head_tc::plan_split(n, nA);
+    cirs_head_tc::HeadTc H{ws.h2, n, w->w3t, ldA, w->b3, nA};
+    int rc = cirs_head_tc::head_tc_stats(H, idx, act, tc_split, ws.pm, ws.ps, ws.la, st);
+    if (rc) return rc;
+    CIRS_LAUNCH(row_loss_tc_kernel, (n + 127) / 128, 128, 0, st, n, tc_split, *cfg, n_global, idx, act, adv, returns,
+                v_old, logp_old, adv_stat, ws);
+    CIRS_CHECK_LAUNCH();
+    rc = cirs_head_tc::head_tc_dh2(H, ws.rowm, ws.rinvz, ws.coef, ws.acta, tc_split, ws.dh2_part, ws.ent_part, st);
+    if (rc) return rc;
+    CIRS_LAUNCH(ent_merge_kernel, (n + 255) / 256, 256, 0, st, n, tc_split, ws.ent_part, ws.terms);
+    CIRS_CHECK_LAUNCH();
+    CIRS_LAUNCH(loss_reduce_kernel, 1, 1024, 0, st, n, n_global, *cfg, ws.terms, losses);
+    CIRS_CHECK_LAUNCH();
+    rc = cirs_head_tc::head_tc_dw3(H, ws.rowm, ws.rinvz, ws.coef, ws.acta, grads->w3t, grads->b3, st);
+    if (rc) return rc;
   } else {
   launch_gemm<64, 128, 16, 8>(RowMajorA{ws.h2, HID, nullptr}, RowMajorB{w->w3t, ldA, nullptr},
                               StoreEp{ws.logits, ldA, w->b3, 0, nullptr, nullptr, 0}, n, nA, HID, 1, nullptr, st, "head_logits_gemm");
@@ -463,7 +582,11 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   // ---- critic head + trunk
   CIRS_LAUNCH(critic_grad_kernel, 1, 256, 0, st, n, ws.dv, ws.h2, grads->wv, grads->bv);
   CIRS_CHECK_LAUNCH();
-  CIRS_LAUNCH(dz2_kernel, (n * HID + 255) / 256, 256, 0, st, n, ws.dh2, ws.dv, w->wv, ws.h2, ws.dz2);
+  if (tc) {
+    CIRS_LAUNCH(dz2_tc_kernel, (n * HID + 255) / 256, 256, 0, st, n, tc_split, ws.dh2_part, ws.dv, w->wv, ws.h2, ws.dz2);
+  } else {
+    CIRS_LAUNCH(dz2_kernel, (n * HID + 255) / 256, 256, 0, st, n, ws.dh2, ws.dv, w->wv, ws.h2, ws.dz2);
+  }
   CIRS_CHECK_LAUNCH();
   // dW2t[k][c] = sum_r h1[r][k] dz2[r][c], db2
   launch_gemm<64, 64, 16, 4>(ColMajorA{ws.h1, HID, nullptr}, RowMajorB{ws.dz2, HID, nullptr},
