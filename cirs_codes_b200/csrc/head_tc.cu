@@ -41,6 +41,28 @@ __device__ __forceinline__ void wait_or_flag(uint64_t* bar, uint32_t parity) {
 // ------------------------------------------------------------------------------------------------- pass F
 constexpr size_t F_SMEM = 2 * A_BYTES + 2 * B_BYTES + 64 * 4 + 2 * NT * 4;
 
+// operand sources (global memory)
+struct SrcH2 {      // rows [r0, r_end) of h2 as float4 chunks, zero beyond
+  const float* h2; int r0, r_end;
+  __device__ __forceinline__ float4 operator()(int r, int c4) const {
+    return r0 + r < r_end ? ld4(h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+};
+struct SrcH2T {     // transposed: tile row = hidden index, tile column = row
+  const float* h2; int r0, r_end;
+  __device__ __forceinline__ float operator()(int r, int c) const {
+    return r0 + c < r_end ? __ldg(h2 + (size_t)(r0 + c) * HID + r) : 0.f;
+  }
+};
+struct SrcW3T {     // transposed: tile row = catalogue column c0 + r, tile column = hidden index
+  const float* w3t; int64_t ldA; int c0;
+  __device__ __forceinline__ float operator()(int r, int c) const { return __ldg(w3t + (size_t)c * ldA + c0 + r); }
+};
+struct SrcW3 {      // natural: tile row = hidden index, float4 chunks of catalogue columns
+  const float* w3t; int64_t ldA; int c0;
+  __device__ __forceinline__ float4 operator()(int r, int c4) const { return ld4(w3t + (size_t)r * ldA + c0 + 4 * c4); }
+};
+
 __global__ void __launch_bounds__(NT, 2)
 head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act, int tiles_per_split,
                      int n_split, float* __restrict__ pm, float* __restrict__ ps, float* __restrict__ la) {
@@ -60,9 +82,19 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   const int ct0 = split * tiles_per_split, ct1 = min(n_tiles, ct0 + tiles_per_split);
   if (warp == 0) tmem_alloc(&tmem_base, 64);
   if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-  tile_stage(a_hi, a_lo, TM, HID, tid, NT, [&](int r, int c4) {
-    return r0 + r < H.n ? ld4(H.h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  });
+  {
+    TileV<TM, HID, NT> ta;
+    ta.load(tid, SrcH2{H.h2, r0, H.n});
+    ta.store(a_hi, a_lo, tid);
+  }
+  TileT<TN, HID, NT> tb_;     // the NEXT catalogue tile of W3, prefetched into registers
+  float b3n = 0.f;
+  auto prefetch = [&](int ct) {
+    const int c0 = ct * TN;
+    tb_.load(tid, SrcW3T{H.w3t, H.ldA, c0});
+    b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : 0.f;
+  };
+  if (ct0 < ct1) prefetch(ct0);
   int a = -1;
   if (act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
   float m = -INFINITY, s = 0.f, lav = 0.f;
@@ -70,8 +102,8 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   uint32_t ph = 0, tb = 0;
   for (int ct = ct0; ct < ct1; ++ct) {
     const int c0 = ct * TN;
-    tile_stage_T(b_hi, b_lo, TN, HID, tid, NT, [&](int r, int c) { return __ldg(H.w3t + (size_t)c * H.ldA + c0 + r); });
-    if (tid < TN) sb3[tid] = c0 + tid < H.nA ? __ldg(H.b3 + c0 + tid) : 0.f;
+    tb_.store(b_hi, b_lo, tid);
+    if (tid < TN) sb3[tid] = b3n;
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -81,6 +113,7 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
       issue(tb, a_hi, a_lo, b_hi, b_lo, false);
       mma_commit(&bar);
     }
+    if (ct + 1 < ct1) prefetch(ct + 1);     // global loads fly behind the MMA and the epilogue
     wait_or_flag(&bar, ph);
     ph ^= 1;
     fence_after_sync();
@@ -153,9 +186,21 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   const int ct0 = split * tiles_per_split, ct1 = min(n_tiles, ct0 + tiles_per_split);
   if (warp == 0) tmem_alloc(&tmem_base, 128);
   if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
-  tile_stage(a_hi, a_lo, TM, HID, tid, NT, [&](int r, int c4) {
-    return r0 + r < H.n ? ld4(H.h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  });
+  {
+    TileV<TM, HID, NT> ta;
+    ta.load(tid, SrcH2{H.h2, r0, H.n});
+    ta.store(a_hi, a_lo, tid);
+  }
+  TileT<TN, HID, NT> tn;      // next tile, transposed (B of MMA1)
+  TileV<HID, TN, NT> tk;      // next tile, natural    (B of MMA2)
+  float b3n = 0.f;
+  auto prefetch = [&](int ct) {
+    const int c0 = ct * TN;
+    tn.load(tid, SrcW3T{H.w3t, H.ldA, c0});
+    tk.load(tid, SrcW3{H.w3t, H.ldA, c0});
+    b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : 0.f;
+  };
+  if (ct0 < ct1) prefetch(ct0);
   const bool live = r0 + row < H.n;
   const float rm = live ? rowm[r0 + row] : 0.f, iz = live ? rinvz[r0 + row] : 0.f, cf = live ? coef[r0 + row] : 0.f;
   const int a = live ? acta[r0 + row] : -1;
@@ -164,8 +209,8 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   uint32_t ph = 0, tb = 0;
   for (int ct = ct0; ct < ct1; ++ct) {
     const int c0 = ct * TN;
-    tile_stage_T(bn_hi, bn_lo, TN, HID, tid, NT, [&](int r, int c) { return __ldg(H.w3t + (size_t)c * H.ldA + c0 + r); });
-    if (tid < TN) sb3[tid] = c0 + tid < H.nA ? __ldg(H.b3 + c0 + tid) : 0.f;
+    tn.store(bn_hi, bn_lo, tid);
+    if (tid < TN) sb3[tid] = b3n;
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -176,25 +221,29 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
       mma_commit(&bar1);
     }
     if (ct > ct0) wait_or_flag(&bar2, ph ^ 1);            // previous MMA2 has finished reading bk / dl
-    tile_stage(bk_hi, bk_lo, HID, TN, tid, NT,
-               [&](int r, int c4) { return ld4(H.w3t + (size_t)r * H.ldA + c0 + 4 * c4); });
+    tk.store(bk_hi, bk_lo, tid);
+    if (ct + 1 < ct1) prefetch(ct + 1);
     wait_or_flag(&bar1, ph);
     fence_after_sync();
-    float v[32];
-    tmem_ld32(tmem_addr(tb, (warp & 3) * 32, half * 32), v);
-    const int cb = c0 + half * 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = v[j] + sb3[half * 32 + j];
-      const float p = cb + j < H.nA ? expf(x - rm) * iz : 0.f;
-      // entropy of Categorical(probs): -sum p log(clamp(p, eps, 1 - eps)); log p = x - max - log Z inside the clamp
-      const float lg = p < CATEGORICAL_EPS ? LOG_EPS : (p > 1.0f - CATEGORICAL_EPS ? LOG_1M_EPS : x - rm - log_z);
-      ent = fmaf(-p, lg, ent);
-      v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
+    for (int h16 = 0; h16 < 2; ++h16) {
+      float v[16];
+      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, half * 32 + h16 * 16), v);
+      const int cb = c0 + half * 32 + h16 * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x = v[j] + sb3[half * 32 + h16 * 16 + j];
+        const float p = cb + j < H.nA ? expf(x - rm) * iz : 0.f;
+        // entropy of Categorical(probs): -sum p log(clamp(p, eps, 1 - eps)); log p = x - max - log Z inside the clamp
+        const float lg = p < CATEGORICAL_EPS ? LOG_EPS : (p > 1.0f - CATEGORICAL_EPS ? LOG_1M_EPS : x - rm - log_z);
+        ent = fmaf(-p, lg, ent);
+        v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        tile_store_split(dl_hi, dl_lo, TM, row, half * 8 + h16 * 4 + q,
+                         make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      tile_store_split(dl_hi, dl_lo, TM, row, half * 8 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -251,22 +300,32 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   const int rs0 = blockIdx.y * rows_per_split, rs1 = min(H.n, rs0 + rows_per_split);
   if (warp == 0) tmem_alloc(&tmem_base, 128);
   if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
-  tile_stage_T(wa_hi, wa_lo, TM, HID, tid, NT, [&](int r, int c) { return __ldg(H.w3t + (size_t)c * H.ldA + c0 + r); });
+  {
+    TileT<TM, HID, NT> tw;
+    tw.load(tid, SrcW3T{H.w3t, H.ldA, c0});
+    tw.store(wa_hi, wa_lo, tid);
+  }
+  TileV<TN, HID, NT> tv;      // next row tile of h2, natural    (B of MMA1')
+  TileT<HID, TN, NT> tt;      // next row tile of h2, transposed (B of MMA3)
+  float n_rm = 0.f, n_iz = 0.f, n_cf = 0.f;
+  int n_ac = -1;
+  auto prefetch = [&](int r0) {
+    tv.load(tid, SrcH2{H.h2, r0, rs1});
+    tt.load(tid, SrcH2T{H.h2, r0, rs1});
+    const bool ok = tid < TN && r0 + tid < rs1;
+    n_rm = ok ? rowm[r0 + tid] : 0.f;
+    n_iz = ok ? rinvz[r0 + tid] : 0.f;
+    n_cf = ok ? coef[r0 + tid] : 0.f;
+    n_ac = ok ? acta[r0 + tid] : -1;
+  };
+  if (rs0 < rs1) prefetch(rs0);
   const bool live = col < H.nA;
   const float b3v = live ? __ldg(H.b3 + col) : 0.f;
   float db3 = 0.f;
   uint32_t ph = 0, tb = 0;
   for (int r0 = rs0; r0 < rs1; r0 += TN) {
-    tile_stage(hb_hi, hb_lo, TN, HID, tid, NT, [&](int r, int c4) {
-      return r0 + r < rs1 ? ld4(H.h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    });
-    if (tid < TN) {
-      const bool ok = r0 + tid < rs1;
-      srm[tid] = ok ? rowm[r0 + tid] : 0.f;
-      siz[tid] = ok ? rinvz[r0 + tid] : 0.f;
-      scf[tid] = ok ? coef[r0 + tid] : 0.f;
-      sac[tid] = ok ? acta[r0 + tid] : -1;
-    }
+    tv.store(hb_hi, hb_lo, tid);
+    if (tid < TN) { srm[tid] = n_rm; siz[tid] = n_iz; scf[tid] = n_cf; sac[tid] = n_ac; }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -277,23 +336,27 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
       mma_commit(&bar1);
     }
     if (r0 > rs0) wait_or_flag(&bar2, ph ^ 1);             // previous MMA3 has finished reading ht / dl
-    tile_stage_T(ht_hi, ht_lo, HID, TN, tid, NT,
-                 [&](int r, int c) { return r0 + c < rs1 ? H.h2[(size_t)(r0 + c) * HID + r] : 0.f; });
+    tt.store(ht_hi, ht_lo, tid);
+    if (r0 + TN < rs1) prefetch(r0 + TN);
     wait_or_flag(&bar1, ph);
     fence_after_sync();
-    float v[32];
-    tmem_ld32(tmem_addr(tb, (warp & 3) * 32, half * 32), v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int jj = half * 32 + j;
-      const float p = expf(v[j] + b3v - srm[jj]) * siz[jj];
-      const float d = live ? scf[jj] * ((sac[jj] == col ? 1.f : 0.f) - p) : 0.f;
-      db3 += d;
-      v[j] = d;
+    for (int h16 = 0; h16 < 2; ++h16) {
+      float v[16];
+      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, half * 32 + h16 * 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int jj = half * 32 + h16 * 16 + j;
+        const float p = expf(v[j] + b3v - srm[jj]) * siz[jj];
+        const float d = live ? scf[jj] * ((sac[jj] == col ? 1.f : 0.f) - p) : 0.f;
+        db3 += d;
+        v[j] = d;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        tile_store_split(dl_hi, dl_lo, TM, cl, half * 8 + h16 * 4 + q,
+                         make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      tile_store_split(dl_hi, dl_lo, TM, cl, half * 8 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     fence_async_smem();
     fence_before_sync();
     __syncthreads();

@@ -111,6 +111,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 // TMEM address of (lane, column) relative to an allocation base
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, uint32_t lane, uint32_t col) {
   return base + (lane << 16) + col;
@@ -136,9 +149,76 @@ __device__ __forceinline__ void tile_store_split(char* hi, char* lo, int R, int 
   *reinterpret_cast<float4*>(lo + off) =
       make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
 }
-// Cooperative staging of an R x C tile (R % 8 == 0, C % 16 == 0) from a row-major source: src(r, c4) returns the
-// float4 of row r, columns 4*c4 .. 4*c4+3 (zero outside the matrix).  Lane mapping: 8 rows x 4 chunks per warp step,
-// so global reads are 64-byte row segments and shared stores are conflict-free 16-byte vectors.
+// Cooperative staging of an R x C tile (R % 8 == 0, C % 16 == 0) from a row-major source, split into a LOAD phase
+// (global -> registers, all loads of a thread issued back to back so their latencies overlap, and early enough to
+// prefetch the next tile behind the current tile's MMA + epilogue) and a STORE phase (registers -> hi / lo tiles).
+// src(r, c4) returns the float4 of row r, columns 4*c4 .. 4*c4+3 (zero outside the matrix).  Lane mapping: 8 rows x 4
+// chunks per warp step, so global reads are 64-byte row segments and shared stores conflict-free 16-byte vectors.
+template <int R, int C, int NTHREADS>
+struct TileV {
+  static constexpr int RGS = R / 8, CQS = C / 16, NW = NTHREADS / 32;
+  static constexpr int STEPS = (RGS * CQS + NW - 1) / NW;
+  float4 buf[STEPS];
+  template <class Src>
+  __device__ __forceinline__ void load(int tid, Src src) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) {
+      const int w = warp + i * NW;
+      if (RGS * CQS % NW == 0 || w < RGS * CQS) {
+        const int rg = w % RGS, cq = w / RGS;
+        buf[i] = src(rg * 8 + (lane & 7), cq * 4 + (lane >> 3));
+      }
+    }
+  }
+  __device__ __forceinline__ void store(char* hi, char* lo, int tid) const {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) {
+      const int w = warp + i * NW;
+      if (RGS * CQS % NW == 0 || w < RGS * CQS) {
+        const int rg = w % RGS, cq = w / RGS;
+        tile_store_split(hi, lo, R, rg * 8 + (lane & 7), cq * 4 + (lane >> 3), buf[i]);
+      }
+    }
+  }
+};
+// Transposing variant: the source is contiguous along r (the tile's row index), src(r, c) returns one element.
+// Lane mapping: 4 consecutive c x 8 consecutive r per warp step -> global reads are 32-byte segments along r, the
+// 4-byte shared stores of a warp cover 128 contiguous bytes (conflict free).
+template <int R, int C, int NTHREADS>
+struct TileT {
+  static constexpr int RGS = R / 8, C4S = C / 4, NW = NTHREADS / 32;
+  static constexpr int STEPS = (RGS * C4S + NW - 1) / NW;
+  float buf[STEPS];
+  template <class Src>
+  __device__ __forceinline__ void load(int tid, Src src) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) {
+      const int w = warp + i * NW;
+      if (RGS * C4S % NW == 0 || w < RGS * C4S) {
+        const int rg = w % RGS, c4 = w / RGS;
+        buf[i] = src(rg * 8 + (lane >> 2), c4 * 4 + (lane & 3));
+      }
+    }
+  }
+  __device__ __forceinline__ void store(char* hi, char* lo, int tid) const {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) {
+      const int w = warp + i * NW;
+      if (RGS * C4S % NW == 0 || w < RGS * C4S) {
+        const int rg = w % RGS, c4 = w / RGS;
+        const float x = buf[i], h = tf32_hi(x);
+        const uint32_t off = tile_chunk_off(R, rg * 8 + (lane >> 2), c4) + (uint32_t)(lane & 3) * 4u;
+        *reinterpret_cast<float*>(hi + off) = h;
+        *reinterpret_cast<float*>(lo + off) = tf32_hi(x - h);
+      }
+    }
+  }
+};
+// run-time-shaped one-shot versions (tests/tc_probe.cu)
 template <class Src>
 __device__ __forceinline__ void tile_stage(char* hi, char* lo, int R, int C, int tid, int nthreads, Src src) {
   const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
@@ -147,25 +227,6 @@ __device__ __forceinline__ void tile_stage(char* hi, char* lo, int R, int C, int
     const int rg = w % rgs, cq = w / rgs;
     const int r = rg * 8 + (lane & 7), c4 = cq * 4 + (lane >> 3);
     tile_store_split(hi, lo, R, r, c4, src(r, c4));
-  }
-}
-
-// Transposing variant: the source is contiguous along r (the tile's row index), src(r, c) returns one element.
-// Lane mapping: 4 consecutive c x 8 consecutive r per warp step -> global reads are 32-byte segments along r, the
-// 4-byte shared stores of a warp cover 128 contiguous bytes (conflict free).
-template <class Src>
-__device__ __forceinline__ void tile_stage_T(char* hi, char* lo, int R, int C, int tid, int nthreads, Src src) {
-  const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-  const int rgs = R >> 3, c4s = C >> 2;
-  const int cl = lane & 3, rl = lane >> 2;
-  for (int w = warp; w < rgs * c4s; w += nwarps) {
-    const int rg = w % rgs, c4 = w / rgs;
-    const int r = rg * 8 + rl, c = c4 * 4 + cl;
-    const float x = src(r, c);
-    const float h = tf32_hi(x);
-    const uint32_t off = tile_chunk_off(R, r, c4) + (uint32_t)cl * 4u;
-    *reinterpret_cast<float*>(hi + off) = h;
-    *reinterpret_cast<float*>(lo + off) = tf32_hi(x - h);
   }
 }
 
