@@ -17,6 +17,8 @@
 #include <cooperative_groups.h>
 
 #include "actor_dev.cuh"
+#include "actor_tc_dev.cuh"
+#include "head_tc.cuh"
 #include "env_dev.cuh"
 #include "tracker_dev.cuh"
 
@@ -58,13 +60,18 @@ struct RolloutArgs {
   int smem_w_off;           // float offset of the staged weights inside dynamic shared memory
   long long* dbg;           // [1 + 3 * max_steps] turns played, then per turn {n_active, ns phase A, ns phase B}
   int scratch_per_warp;
+  // tensor-core head (actor_tc_dev.cuh): CTA s owns catalogue slice s
+  int n_slices;             // ceil(n_action / 80) <= grid
+  int tc_keep_off;          // float offset of the launch-lifetime shared-memory region (W3 slice, mbarriers)
+  int* tc_timeout;          // set when an mbarrier wait gives up (never expected)
 };
 
 // SMW: the tracker's weights are staged once in shared memory (they are re-read by every warp at every turn; from L2
 // each token is ~55 dependent round trips of ~0.6 us, from shared memory ~20x less)
-template <bool SMW>
-__global__ void __launch_bounds__(NT, SMW ? 1 : 2) rollout_kuaishou_kernel(RolloutArgs A) {
-  extern __shared__ __align__(16) float smem_dyn[];
+// TC: phase A on the tcgen05 tensor cores (3xTF32), each CTA keeping its slice of W3 in shared memory for the launch
+template <bool SMW, bool TC>
+__global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kernel(RolloutArgs A) {
+  extern __shared__ __align__(128) float smem_dyn[];
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warps_per_cta = NT / 32;
@@ -86,8 +93,16 @@ __global__ void __launch_bounds__(NT, SMW ? 1 : 2) rollout_kuaishou_kernel(Rollo
     __syncthreads();
   }
 
+  cirs_actor_tc::TcSmem TS{};
+  cirs_actor_tc::TcState tst{0u, 0u};
+  if (TC) {
+    TS = cirs_actor_tc::tc_carve(reinterpret_cast<char*>(smem_dyn), reinterpret_cast<char*>(smem_dyn + A.tc_keep_off));
+    cirs_actor_tc::tc_setup(A.H.W, blockIdx.x, A.n_slices, TS, tid);
+  }
+
   // ---- reset + user token (position 0); every environment starts in the compact list of turn 0
   if (blockIdx.x == 0 && tid == 0) {
+    *A.tc_timeout = 0;
     *A.n_active = B;
     A.count[0] = B;
     A.count[1] = 0;
@@ -126,10 +141,15 @@ __global__ void __launch_bounds__(NT, SMW ? 1 : 2) rollout_kuaishou_kernel(Rollo
     H.tiles_per_split = (n_col_tiles + n_split - 1) / n_split;
     H.n_split = (n_col_tiles + H.tiles_per_split - 1) / H.tiles_per_split;
     // ---- phase A: actor head partials over the compact rows
-    const int n_items = row_tiles * H.n_split;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      actor_head_body(H, w % row_tiles, w / row_tiles, smem_dyn);
-      __syncthreads();
+    if (TC) {
+      H.n_split = A.n_slices;
+      if ((int)blockIdx.x < A.n_slices) cirs_actor_tc::tc_head_turn(H, blockIdx.x, TS, tid, tst, A.tc_timeout);
+    } else {
+      const int n_items = row_tiles * H.n_split;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        actor_head_body(H, w % row_tiles, w / row_tiles, smem_dyn);
+        __syncthreads();
+      }
     }
     __threadfence();
     grid.sync();
@@ -177,16 +197,20 @@ __global__ void __launch_bounds__(NT, SMW ? 1 : 2) rollout_kuaishou_kernel(Rollo
       A.dbg[3 + 3 * t] = gtime_ns() - t1;
     }
   }
+  if (TC) cirs_actor_tc::tc_teardown(TS, tid);
 }
 
 }  // namespace
 
 // workspace: [counters 256 B][phase timers][list 2*B i32][h2 B*64 f32][head partials]
 constexpr int64_t DBG_BYTES = 8 * (1 + 6 * 512);   // phase timers of up to 512 turns
-static int64_t partial_capacity(int32_t n_env) { return ((int64_t)n_env + 64) * 96 + 64 * 1024; }
+static int64_t partial_capacity(int32_t n_env, int32_t n_action) {
+  const int64_t ffma = ((int64_t)n_env + 64) * 96 + 64 * 1024;
+  const int64_t tc = (int64_t)((n_action + cirs_actor_tc::SLICE - 1) / cirs_actor_tc::SLICE + 1) * ((int64_t)n_env + 128);
+  return ffma > tc ? ffma : tc;
+}
 extern "C" int64_t cirs_rollout_workspace_bytes(int32_t n_env, int32_t n_action) {
-  (void)n_action;
-  return 256 + DBG_BYTES + (int64_t)sizeof(int32_t) * 2 * n_env + 64 + (int64_t)sizeof(float) * HID * n_env + 64 + (int64_t)sizeof(Partial) * partial_capacity(n_env);
+  return 256 + DBG_BYTES + (int64_t)sizeof(int32_t) * 2 * n_env + 64 + (int64_t)sizeof(float) * HID * n_env + 64 + (int64_t)sizeof(Partial) * partial_capacity(n_env, n_action);
 }
 
 extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weights* tw,
@@ -208,45 +232,68 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   }
   if (env->n_env <= 0) return CIRS_OK;
   const int per_warp = cirs_tracker::tracker_scratch_floats(*tw);
-  size_t smem = SMEM_BYTES;
-  if ((size_t)per_warp * (NT / 32) * sizeof(float) > smem) smem = (size_t)per_warp * (NT / 32) * sizeof(float);
-  if (smem > 200 * 1024) {
-    cirs_set_error("cirs_rollout_kuaishou: shared memory budget exceeded");
-    return CIRS_ERR_ARG;
-  }
-  RolloutArgs A{};
-  // stage the tracker weights in shared memory when they fit next to the head's tiles (d = 32: 113 KB + 77 KB)
+  const size_t scratch_bytes = (size_t)per_warp * (NT / 32) * sizeof(float);
   constexpr size_t SMEM_MAX = 224 * 1024;
+  auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
+  RolloutArgs A{};
+  // tensor-core head: needs one catalogue slice per CTA (checked against the grid below) and plain sampling modes
+  const int n_slices = (pw->n_action + cirs_actor_tc::SLICE - 1) / cirs_actor_tc::SLICE;
+  bool tc = cirs_head_tc::head_tc_enabled(env->n_env, pw->n_action, pw->ld_action) && (mode == 0 || mode == 1) &&
+            pw->dim_state <= 32;
+  // the tracker's weights staged in shared memory when they fit next to the head's buffers (d = 32: 113 KB)
   const float* w_lo = tw->user_wt;
   const int64_t w_count = tw->flat ? (tw->flat + tw->n_flat) - w_lo : 0;
-  bool smw = tw->flat != nullptr && w_count > 0 && (w_count % 4) == 0 && ((uintptr_t)w_lo % 16) == 0 &&
-             smem + (size_t)w_count * sizeof(float) <= SMEM_MAX && tw->dec_b >= w_lo && tw->dec_b < w_lo + w_count &&
-             tw->gate_wt >= w_lo;
-  for (int l = 0; smw && l < tw->nlayers; ++l)
-    smw = tw->layer[l].in_wt >= w_lo && tw->layer[l].n2_b < w_lo + w_count;
-  if (smw) {
-    A.w_lo = w_lo; A.w_count = (int)w_count; A.smem_w_off = (int)(smem / sizeof(float));
-    smem += (size_t)w_count * sizeof(float);
-  }
-  static int max_ctas_v[2] = {0, 0};
-  int& max_ctas = max_ctas_v[smw ? 1 : 0];
-  if (!max_ctas) {
-    int dev = 0, per_sm = 0, n_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  bool smw_ok = tw->flat != nullptr && w_count > 0 && (w_count % 4) == 0 && ((uintptr_t)w_lo % 16) == 0 &&
+                tw->dec_b >= w_lo && tw->dec_b < w_lo + w_count && tw->gate_wt >= w_lo;
+  for (int l = 0; smw_ok && l < tw->nlayers; ++l)
+    smw_ok = tw->layer[l].in_wt >= w_lo && tw->layer[l].n2_b < w_lo + w_count;
+  size_t smem = 0;
+  bool smw = false;
+  static int max_ctas_v[4] = {0, 0, 0, 0};
+  int max_ctas = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    size_t head = tc ? up128(cirs_actor_tc::TURN_BYTES > scratch_bytes ? cirs_actor_tc::TURN_BYTES : scratch_bytes)
+                     : up128(SMEM_BYTES > scratch_bytes ? SMEM_BYTES : scratch_bytes);
+    size_t keep_off = head;
+    if (tc) head += up128(cirs_actor_tc::KEEP_BYTES);
+    if (head > SMEM_MAX) {
+      if (tc) { tc = false; continue; }
+      cirs_set_error("cirs_rollout_kuaishou: shared memory budget exceeded");
+      return CIRS_ERR_ARG;
+    }
+    smw = smw_ok && head + (size_t)w_count * sizeof(float) <= SMEM_MAX;
+    smem = head;
+    A.tc_keep_off = (int)(keep_off / sizeof(float));
     if (smw) {
-      cudaFuncSetAttribute(rollout_kuaishou_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true>, NT, smem);
+      A.w_lo = w_lo; A.w_count = (int)w_count; A.smem_w_off = (int)(smem / sizeof(float));
+      smem += (size_t)w_count * sizeof(float);
     } else {
-      cudaFuncSetAttribute(rollout_kuaishou_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<false>, NT, smem);
+      A.w_lo = nullptr; A.w_count = 0; A.smem_w_off = 0;
     }
-    if (per_sm < 1) {
-      cirs_set_error("cirs_rollout_kuaishou: kernel does not fit on an SM");
-      return CIRS_ERR_CUDA;
+    int& mc = max_ctas_v[(smw ? 1 : 0) + (tc ? 2 : 0)];
+    if (!mc) {
+      int dev = 0, per_sm = 0, n_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      const void* fn = tc ? (smw ? (const void*)rollout_kuaishou_kernel<true, true> : (const void*)rollout_kuaishou_kernel<false, true>)
+                          : (smw ? (const void*)rollout_kuaishou_kernel<true, false> : (const void*)rollout_kuaishou_kernel<false, false>);
+      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+      if (tc && smw) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true, true>, NT, smem);
+      else if (tc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<false, true>, NT, smem);
+      else if (smw) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true, false>, NT, smem);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<false, false>, NT, smem);
+      if (per_sm < 1) {
+        cirs_set_error("cirs_rollout_kuaishou: kernel does not fit on an SM");
+        return CIRS_ERR_CUDA;
+      }
+      if (tc && per_sm > 1) per_sm = 1;   // TMEM: 256 columns per CTA, keep one CTA per SM
+      mc = per_sm * n_sm;
     }
-    max_ctas = per_sm * n_sm;
+    max_ctas = mc;
+    if (tc && n_slices > max_ctas) { tc = false; continue; }   // catalogue too wide for one slice per CTA
+    break;
   }
+  A.n_slices = n_slices;
   A.E = *env; A.T = *tw;
   A.H.W = *pw; A.H.n_rows = env->n_env; A.H.gather = nullptr; A.H.state_by_k = 0; A.H.out_by_k = 0;
   A.H.active = active; A.H.state = cur_state; A.H.state_stride = tw->dim_state; A.H.noise_q = nullptr;
@@ -266,7 +313,8 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.h2 = reinterpret_cast<float*>(((uintptr_t)(A.list + 2 * (size_t)env->n_env) + 63) & ~(uintptr_t)63);
   A.H.h2_in = A.h2;
   A.H.part = reinterpret_cast<Partial*>(((uintptr_t)(A.h2 + (size_t)env->n_env * HID) + 63) & ~(uintptr_t)63);
-  if ((int64_t)(grid + 96) * BM > partial_capacity(env->n_env)) {
+  A.tc_timeout = reinterpret_cast<int*>(wsp + 128);
+  if ((int64_t)(grid + 96) * BM > partial_capacity(env->n_env, pw->n_action)) {
     cirs_set_error("cirs_rollout_kuaishou: workspace too small for this grid");
     return CIRS_ERR_ARG;
   }
@@ -277,9 +325,9 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.scratch_per_warp = per_warp;
   void* params[] = {&A};
   const bool prof = cirs_profile_begin("rollout_kuaishou_kernel", (cudaStream_t)stream);
-  cudaError_t err = cudaLaunchCooperativeKernel(
-      smw ? (void*)rollout_kuaishou_kernel<true> : (void*)rollout_kuaishou_kernel<false>, dim3(grid), dim3(NT), params,
-      smem, (cudaStream_t)stream);
+  void* fn = tc ? (smw ? (void*)rollout_kuaishou_kernel<true, true> : (void*)rollout_kuaishou_kernel<false, true>)
+                : (smw ? (void*)rollout_kuaishou_kernel<true, false> : (void*)rollout_kuaishou_kernel<false, false>);
+  cudaError_t err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), params, smem, (cudaStream_t)stream);
   cirs_note_launch();
   if (prof) cirs_profile_end((cudaStream_t)stream);
   if (err != cudaSuccess) {
