@@ -122,49 +122,60 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
     const int k = rt * ROWS + row;
     const bool live = k < P.n_rows;
     const int rid = live ? (P.gather ? P.gather[k] : k) : -1;
-    float m = -INFINITY, z = 0.f, bs = -INFINITY, bl = 0.f;
+    // Race in the probability domain: candidate j beats the running winner iff  e_j / q_j > e_best / q_best  with
+    // e = exp(l - m) relative to the running maximum (rescaled together with the softmax sum when m grows) and
+    // q = -log(u) ~ Exp(1).  One fast log per element instead of the two of the Gumbel form; the winner's score
+    // l - log(q) (log domain, what the cross-slice merge compares) is formed once per row tile.
+    float m = -INFINITY, z = 0.f, e_best = 0.f, q_best = 1.f, bl = 0.f;
     int bi = 0x7fffffff;
     const int lbase = half * (SLICE / 2);          // column offset inside the slice
     const int cbase = slice * SLICE + lbase;       // catalogue column
-#pragma unroll 1
-    for (int ch = 0; ch < SLICE / 16; ++ch) {
-      float v[8];
-      tmem_ld8(tmem_addr(tb + 128u * b, (warp & 3) * 32, lbase + ch * 8), v);
+    constexpr int NCH = SLICE / 16;                // chunks of 8 columns per thread
+    uint32_t vr[2][8];
+    tmem_ld8_issue(tmem_addr(tb + 128u * b, (warp & 3) * 32, lbase), vr[0]);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      tmem_ld8_wait(vr[ch & 1]);
+      if (ch + 1 < NCH) tmem_ld8_issue(tmem_addr(tb + 128u * b, (warp & 3) * 32, lbase + (ch + 1) * 8), vr[(ch + 1) & 1]);
       if (!live) continue;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int nb = cbase + ch * 8 + 4 * q;
+      for (int q4 = 0; q4 < 2; ++q4) {
+        const int nb = cbase + ch * 8 + 4 * q4;
         if (nb >= nA) continue;
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        float qn[4] = {1.f, 1.f, 1.f, 1.f};
         if (P.mode == MODE_SAMPLE) {
           const uint4 rnd = philox4x32(make_uint4((uint32_t)rid, (uint32_t)(nb >> 2), (uint32_t)offset,
                                                   (uint32_t)(offset >> 32)),
                                        make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-          g[0] = -logf(-logf(u01(rnd.x)) + 1e-30f);  // Gumbel = -log(q), q = -log(u) ~ Exp(1)
-          g[1] = -logf(-logf(u01(rnd.y)) + 1e-30f);
-          g[2] = -logf(-logf(u01(rnd.z)) + 1e-30f);
-          g[3] = -logf(-logf(u01(rnd.w)) + 1e-30f);
+          const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float u = u01(rr[j]), w = 1.0f - u;   // u in (0, 1], w exact
+            const float ql = w * fmaf(w, fmaf(w, 0.33333334f, 0.5f), 1.0f);   // -log(1 - w) for small w
+            qn[j] = fmaxf(w < 0.00390625f ? ql : -__logf(u), 1e-30f);
+          }
         }
         float l[4], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          l[j] = nb + j < nA ? v[4 * q + j] + S.b3[lbase + ch * 8 + 4 * q + j] : -INFINITY;
+          l[j] = nb + j < nA ? __uint_as_float(vr[ch & 1][4 * q4 + j]) + S.b3[lbase + ch * 8 + 4 * q4 + j] : -INFINITY;
           mx = fmaxf(mx, l[j]);
         }
-        const float M = fmaxf(m, mx);
-        float zz = z * __expf(m - M);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) zz += __expf(l[j] - M);
-        z = zz;
-        m = M;
+        if (mx > m) {
+          const float sc = __expf(m - mx);   // m = -inf at the start: exp(-inf) = 0
+          z *= sc;
+          e_best *= sc;
+          m = mx;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (l[j] == -INFINITY) continue;
-          const float sc = l[j] + g[j];
-          if (sc > bs) { bs = sc; bl = l[j]; bi = nb + j; }
+          const float e = __expf(l[j] - m);   // 0 for masked columns
+          z += e;
+          if (e * q_best > qn[j] * e_best) { e_best = e; q_best = qn[j]; bl = l[j]; bi = nb + j; }
         }
       }
     }
+    float bs = bi == 0x7fffffff ? -INFINITY : bl - logf(q_best);
     S.red[tid] = m; S.red[NT + tid] = z; S.red[2 * NT + tid] = bs; S.red[3 * NT + tid] = bl;
     S.red[4 * NT + tid] = __int_as_float(bi);
     fence_before_sync();
