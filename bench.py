@@ -275,6 +275,19 @@ def gpu_arm(args, cfg):
 
     # ---- per-kernel durations, live, CUDA events on the launching stream (separate pass: events perturb the step)
     kern, roof = {}, None
+    # every rank runs the profiled steps (the update contains collectives); rank 0 reports
+    col.use_graph = False          # per-kernel events need real launches, not a graph replay
+    col.persistent = bool(args.profile_persistent)
+    for _ in range(2):
+        one_step(rng.integers(0, cfg["U"], size=B), False)
+    lib.cirs_profile_enable(1)
+    lens_p = []
+    n_prof = min(args.steps, 3)
+    for _ in range(n_prof):
+        lens_p.append(one_step(rng.integers(0, cfg["U"], size=B), False)["lens"])
+    rep = _lib.profile_report()
+    lib.cirs_profile_enable(0)
+    lens_p = np.concatenate(lens_p)
     if rank == 0:
         peaks = {}
         try:
@@ -284,18 +297,6 @@ def gpu_arm(args, cfg):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
-        col.use_graph = False          # per-kernel events need real launches, not a graph replay
-        col.persistent = bool(args.profile_persistent)
-        for _ in range(2):
-            one_step(rng.integers(0, cfg["U"], size=B), False)
-        lib.cirs_profile_enable(1)
-        lens_p = []
-        n_prof = min(args.steps, 3)
-        for _ in range(n_prof):
-            lens_p.append(one_step(rng.integers(0, cfg["U"], size=B), False)["lens"])
-        rep = _lib.profile_report()
-        lib.cirs_profile_enable(0)
-        lens_p = np.concatenate(lens_p)
         total_ms = sum(v[1] for v in rep.values())
         n_tr = int(lens_p.sum())
         A, S = cfg["I"], REF["dim_state"]
@@ -309,6 +310,11 @@ def gpu_arm(args, cfg):
             "head_dW3_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
             "head_dh2_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
             "row_loss_kernel": ("hbm", 4.0 * A * n_tr * cfg["repeat"]),
+            # tensor-core head (csrc/head_tc.cu): algorithmic flops of the FP32 contractions they replace; each is
+            # executed as three kind::tf32 MMAs (3xTF32), so the tensor pipe does 3x these flops at the TF32 rate
+            "head_tc_stats_kernel": ("tensor", 2.0 * 64 * A * n_tr * (cfg["repeat"] + 1)),
+            "head_tc_dh2_kernel": ("tensor", 2 * 2.0 * 64 * A * n_tr * cfg["repeat"]),
+            "head_tc_dw3_kernel": ("tensor", 2 * 2.0 * 64 * A * n_tr * cfg["repeat"]),
         }
         for name, (cnt, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
             kern[name] = {"launches": cnt, "ms": round(ms, 4), "share": round(ms / total_ms, 4)}
@@ -323,7 +329,8 @@ def gpu_arm(args, cfg):
             roof = {"kernel": top, "bound": kern[top]["bound"], "achieved": kern[top]["achieved"],
                     "peak": kern[top]["peak"], "unit": kern[top]["unit"], "frac": kern[top]["frac"], "traffic": None,
                     "peak_source": which, "share_of_step": kern[top]["share"],
-                    "note": "FP32 FFMA GEMM measured against the bf16 tensor peak" if kern[top]["bound"] == "tensor"
+                    "note": "FP32-accurate contraction (3xTF32 tcgen05 MMAs, or FFMA) measured against the dense bf16 tensor "
+                            "peak; the 3xTF32 scheme's own ceiling is peak/6" if kern[top]["bound"] == "tensor"
                     else "algorithmic bytes 57+20w+20t per env-step"}
     out = None
     if rank == 0:
