@@ -5,8 +5,9 @@
 //
 // All MMAs are M128 x N64 x K8 kind::tf32 with K-major operands, issued by one thread; every FP32 operand is staged
 // in shared memory as a (hi, lo) pair of TF32-exact tiles and each product is hi.hi + hi.lo + lo.hi (tc_dev.cuh).
-// 256 threads per CTA: thread t owns TMEM lane t % 128 (warp % 4 selects the lane quarter, as tcgen05.ld requires)
-// and the column half t / 128 of each 64-column accumulator.
+// Thread t owns TMEM lane t % 128 (warp % 4 selects the lane quarter, as tcgen05.ld requires) and the column group
+// t / 128 of each 64-column accumulator: halves with 256 threads (pass F, two CTAs per SM), quarters with 512 threads
+// (passes B2 / B3, one CTA per SM) -- four resident warps per scheduler hide the epilogue's instruction latency.
 #include "common.cuh"
 #include "tc_dev.cuh"
 #include "head_tc.cuh"
@@ -16,7 +17,7 @@ namespace cirs_head_tc {
 using namespace cirs_tc;
 
 namespace {
-constexpr int NT = 256, TM = 128, TN = 64, HID = 64;
+constexpr int NT = 256, NTB = 512, TM = 128, TN = 64, HID = 64;   // threads: pass F / passes B2, B3
 constexpr uint32_t A_BYTES = TM * HID * 4;   // 128-row operand tile (32 KB)
 constexpr uint32_t B_BYTES = TN * HID * 4;   // 64-row operand tile (16 KB)
 constexpr uint32_t A_LBO = TM * 16, A_STEP = 2 * TM * 16;   // K-major, R = 128
@@ -161,9 +162,9 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
 }
 
 // ------------------------------------------------------------------------------------------------- pass B2
-constexpr size_t B2_SMEM = 2 * A_BYTES + 4 * B_BYTES + 2 * A_BYTES + 64 * 4 + NT * 4;
+constexpr size_t B2_SMEM = 2 * A_BYTES + 4 * B_BYTES + 2 * A_BYTES + 64 * 4 + NTB * 4;
 
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NTB, 1)
 head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
                    const float* __restrict__ coef, const int32_t* __restrict__ acta, int tiles_per_split, int n_split,
                    float* __restrict__ dh2_part, float* __restrict__ ent_part) {
@@ -180,19 +181,19 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   float* se = sb3 + 64;
   __shared__ __align__(8) uint64_t bar1, bar2;
   __shared__ uint32_t tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, qt = tid >> 7;   // qt: column quarter (16 columns)
   const int r0 = blockIdx.x * TM, split = blockIdx.y;
   const int n_tiles = (H.nA + TN - 1) / TN;
   const int ct0 = split * tiles_per_split, ct1 = min(n_tiles, ct0 + tiles_per_split);
   if (warp == 0) tmem_alloc(&tmem_base, 128);
   if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
   {
-    TileV<TM, HID, NT> ta;
+    TileV<TM, HID, NTB> ta;
     ta.load(tid, SrcH2{H.h2, r0, H.n});
     ta.store(a_hi, a_lo, tid);
   }
-  TileT<TN, HID, NT> tn;      // next tile, transposed (B of MMA1)
-  TileV<HID, TN, NT> tk;      // next tile, natural    (B of MMA2)
+  TileT<TN, HID, NTB> tn;      // next tile, transposed (B of MMA1)
+  TileV<HID, TN, NTB> tk;      // next tile, natural    (B of MMA2)
   float b3n = 0.f;
   auto prefetch = [&](int ct) {
     const int c0 = ct * TN;
@@ -225,14 +226,13 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
     if (ct + 1 < ct1) prefetch(ct + 1);
     wait_or_flag(&bar1, ph);
     fence_after_sync();
-#pragma unroll
-    for (int h16 = 0; h16 < 2; ++h16) {
+    {
       float v[16];
-      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, half * 32 + h16 * 16), v);
-      const int cb = c0 + half * 32 + h16 * 16;
+      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, qt * 16), v);
+      const int cb = c0 + qt * 16;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float x = v[j] + sb3[half * 32 + h16 * 16 + j];
+        const float x = v[j] + sb3[qt * 16 + j];
         const float p = cb + j < H.nA ? expf(x - rm) * iz : 0.f;
         // entropy of Categorical(probs): -sum p log(clamp(p, eps, 1 - eps)); log p = x - max - log Z inside the clamp
         const float lg = p < CATEGORICAL_EPS ? LOG_EPS : (p > 1.0f - CATEGORICAL_EPS ? LOG_1M_EPS : x - rm - log_z);
@@ -241,8 +241,7 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        tile_store_split(dl_hi, dl_lo, TM, row, half * 8 + h16 * 4 + q,
-                         make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        tile_store_split(dl_hi, dl_lo, TM, row, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     }
     fence_async_smem();
     fence_before_sync();
@@ -257,26 +256,27 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   if (ct1 > ct0) wait_or_flag(&bar2, ph ^ 1);
   fence_after_sync();
   if (ct1 > ct0) {
-    float v[32];
-    tmem_ld32(tmem_addr(tb + 64, (warp & 3) * 32, half * 32), v);
+    float v[16];
+    tmem_ld16(tmem_addr(tb + 64, (warp & 3) * 32, qt * 16), v);
     if (live) {
-      float* dst = dh2_part + ((size_t)split * H.n + r0 + row) * HID + half * 32;
+      float* dst = dh2_part + ((size_t)split * H.n + r0 + row) * HID + qt * 16;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < 4; ++q)
         *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
   }
   se[tid] = ent;
   fence_before_sync();
   __syncthreads();
-  if (half == 0 && live) ent_part[(size_t)(r0 + row) * n_split + split] = ent + se[tid + TM];
+  if (qt == 0 && live)
+    ent_part[(size_t)(r0 + row) * n_split + split] = (ent + se[tid + TM]) + (se[tid + 2 * TM] + se[tid + 3 * TM]);
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------------- pass B3
 constexpr size_t B3_SMEM = 2 * A_BYTES + 4 * B_BYTES + 2 * A_BYTES + 4 * 64 * 4;
 
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NTB, 1)
 head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
                    const float* __restrict__ coef, const int32_t* __restrict__ acta, int rows_per_split, int n_rsplit,
                    float* __restrict__ g_w3t, float* __restrict__ g_b3) {
@@ -295,18 +295,18 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   int* sac = reinterpret_cast<int*>(scf + 64);
   __shared__ __align__(8) uint64_t bar1, bar2;
   __shared__ uint32_t tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, cl = tid & 127, half = tid >> 7;
+  const int tid = threadIdx.x, warp = tid >> 5, cl = tid & 127, qt = tid >> 7;   // qt: quarter of 16 rows / hidden units
   const int c0 = blockIdx.x * TM, col = c0 + cl;
   const int rs0 = blockIdx.y * rows_per_split, rs1 = min(H.n, rs0 + rows_per_split);
   if (warp == 0) tmem_alloc(&tmem_base, 128);
   if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
   {
-    TileT<TM, HID, NT> tw;
+    TileT<TM, HID, NTB> tw;
     tw.load(tid, SrcW3T{H.w3t, H.ldA, c0});
     tw.store(wa_hi, wa_lo, tid);
   }
-  TileV<TN, HID, NT> tv;      // next row tile of h2, natural    (B of MMA1')
-  TileT<HID, TN, NT> tt;      // next row tile of h2, transposed (B of MMA3)
+  TileV<TN, HID, NTB> tv;      // next row tile of h2, natural    (B of MMA1')
+  TileT<HID, TN, NTB> tt;      // next row tile of h2, transposed (B of MMA3)
   float n_rm = 0.f, n_iz = 0.f, n_cf = 0.f;
   int n_ac = -1;
   auto prefetch = [&](int r0) {
@@ -340,13 +340,12 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
     if (r0 + TN < rs1) prefetch(r0 + TN);
     wait_or_flag(&bar1, ph);
     fence_after_sync();
-#pragma unroll
-    for (int h16 = 0; h16 < 2; ++h16) {
+    {
       float v[16];
-      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, half * 32 + h16 * 16), v);
+      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, qt * 16), v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int jj = half * 32 + h16 * 16 + j;
+        const int jj = qt * 16 + j;
         const float p = expf(v[j] + b3v - srm[jj]) * siz[jj];
         const float d = live ? scf[jj] * ((sac[jj] == col ? 1.f : 0.f) - p) : 0.f;
         db3 += d;
@@ -354,8 +353,7 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        tile_store_split(dl_hi, dl_lo, TM, cl, half * 8 + h16 * 4 + q,
-                         make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        tile_store_split(dl_hi, dl_lo, TM, cl, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     }
     fence_async_smem();
     fence_before_sync();
@@ -370,12 +368,12 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   if (rs1 > rs0) {
     wait_or_flag(&bar2, ph ^ 1);
     fence_after_sync();
-    float v[32];
-    tmem_ld32(tmem_addr(tb + 64, (warp & 3) * 32, half * 32), v);
+    float v[16];
+    tmem_ld16(tmem_addr(tb + 64, (warp & 3) * 32, qt * 16), v);
     if (live) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float* dst = g_w3t + (size_t)(half * 32 + j) * H.ldA + col;
+      for (int j = 0; j < 16; ++j) {
+        float* dst = g_w3t + (size_t)(qt * 16 + j) * H.ldA + col;
         if (n_rsplit > 1) atomicAdd(dst, v[j]); else *dst += v[j];
       }
       atomicAdd(g_b3 + col, db3);
@@ -434,7 +432,7 @@ int head_tc_dh2(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
-  CIRS_LAUNCH(head_tc_dh2_kernel, grid, NT, B2_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part, ent_part);
+  CIRS_LAUNCH(head_tc_dh2_kernel, grid, NTB, B2_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part, ent_part);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }
@@ -450,7 +448,7 @@ int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   int tiles_per = (row_tiles + n_rsplit - 1) / n_rsplit;
   n_rsplit = (row_tiles + tiles_per - 1) / tiles_per;
   dim3 grid(n_ct, n_rsplit);
-  CIRS_LAUNCH(head_tc_dw3_kernel, grid, NT, B3_SMEM, st, H, rowm, rinvz, coef, acta, tiles_per * TN, n_rsplit, g_w3t,
+  CIRS_LAUNCH(head_tc_dw3_kernel, grid, NTB, B3_SMEM, st, H, rowm, rinvz, coef, acta, tiles_per * TN, n_rsplit, g_w3t,
               g_b3);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;

@@ -40,55 +40,182 @@ Workspace carve(void* base, int64_t n, int64_t ldA) {
   return w;
 }
 
-// ---- trunk forward on gathered observation rows: h1, h2 (row-major) and the critic value
+// ---- trunk forward on gathered observation rows: h1, h2 (row-major) and the critic value.
+// 32 rows per CTA, thread = (row, group of 8 outputs); the weights are read as warp-uniform float4 (one broadcast load
+// per 4 FMAs).  Accumulation order (bias first, k ascending, fmaf) is the one of actor_trunk_warp / actor_head_body,
+// so all three produce bit-identical h2.
 __global__ void __launch_bounds__(256)
 trunk_fwd_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, const float* __restrict__ obs,
                  float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ value) {
-  constexpr int BM = 64, LD = BM + 1;
-  __shared__ float s_in[BM][33];
-  __shared__ float hT[HID][LD];
-  const int tid = threadIdx.x, r0 = blockIdx.x * BM, S = W.dim_state;
-  for (int i = tid; i < BM * S; i += 256) {
+  constexpr int R = 32;
+  __shared__ float s_in[R][33];
+  __shared__ float hT[HID][R + 1];
+  const int tid = threadIdx.x, r0 = blockIdx.x * R, S = W.dim_state;
+  for (int i = tid; i < R * S; i += 256) {
     const int r = i / S, c = i % S;
     s_in[r][c] = (r0 + r < n) ? obs[(int64_t)(idx ? idx[r0 + r] : r0 + r) * S + c] : 0.f;
   }
   __syncthreads();
-  const int row = tid % BM, cg = tid / BM;
+  const int row = tid % R, og = tid / R;   // og: outputs og*8 .. og*8+7 (uniform per warp)
   const bool ok = r0 + row < n;
-  float acc[16];
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __ldg(W.b1 + cg * 16 + j);
+  for (int j = 0; j < 8; ++j) acc[j] = __ldg(W.b1 + og * 8 + j);
+#pragma unroll 4
   for (int k = 0; k < S; ++k) {
     const float x = s_in[row][k];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, __ldg(W.w1t + (size_t)k * HID + cg * 16 + j), acc[j]);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W.w1t + (size_t)k * HID + og * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W.w1t + (size_t)k * HID + og * 8 + 4));
+    acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+    acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
   }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float v = fmaxf(acc[j], 0.f);
-    hT[cg * 16 + j][row] = v;
-    if (ok) h1[(int64_t)(r0 + row) * HID + cg * 16 + j] = v;
+  for (int j = 0; j < 8; ++j) {
+    acc[j] = fmaxf(acc[j], 0.f);
+    hT[og * 8 + j][row] = acc[j];
+  }
+  if (ok) {
+    float4* d = reinterpret_cast<float4*>(h1 + (int64_t)(r0 + row) * HID + og * 8);
+    d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = __ldg(W.b2 + cg * 16 + j);
+  for (int j = 0; j < 8; ++j) acc[j] = __ldg(W.b2 + og * 8 + j);
+#pragma unroll 8
   for (int k = 0; k < HID; ++k) {
     const float x = hT[k][row];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, __ldg(W.w2t + (size_t)k * HID + cg * 16 + j), acc[j]);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W.w2t + (size_t)k * HID + og * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W.w2t + (size_t)k * HID + og * 8 + 4));
+    acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+    acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float v = fmaxf(acc[j], 0.f);
-    hT[cg * 16 + j][row] = v;
-    if (ok) h2[(int64_t)(r0 + row) * HID + cg * 16 + j] = v;
+  for (int j = 0; j < 8; ++j) {
+    acc[j] = fmaxf(acc[j], 0.f);
+    hT[og * 8 + j][row] = acc[j];
+  }
+  if (ok) {
+    float4* d = reinterpret_cast<float4*>(h2 + (int64_t)(r0 + row) * HID + og * 8);
+    d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
   __syncthreads();
-  if (tid < BM && r0 + tid < n) {
+  if (tid < R && r0 + tid < n) {
     float v = __ldg(W.bv);
     for (int k = 0; k < HID; ++k) v = fmaf(hT[k][tid], __ldg(W.wv + k), v);
     value[r0 + tid] = v;
+  }
+}
+
+// ---- trunk + critic backward in ONE kernel (replaces critic grad, dz2, dW2, dz1, dW1, d obs: six launches).
+// 32 rows per CTA.  dh2: [n, 64] when n_split == 0, else the tensor-core pass's partials [n_split, n, 64].
+// Parameter gradients are accumulated with atomicAdd into the (zeroed) flat gradient buffer; d_obs rows are stored
+// at the minibatch's buffer slots (the upstream gradient of the tracker's training pass).
+__global__ void __launch_bounds__(256)
+trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int32_t* __restrict__ idx,
+                 const float* __restrict__ obs, const float* __restrict__ dh2, int n_split,
+                 const float* __restrict__ dv, const float* __restrict__ h1, const float* __restrict__ h2,
+                 float* __restrict__ d_obs) {
+  constexpr int R = 32, LD = HID + 1;
+  __shared__ float s_dz2[R][LD], s_h1[R][LD], s_t[R][LD];   // s_t: h2, later dz1
+  __shared__ float s_obs[R][33], s_dv[R];
+  const int tid = threadIdx.x, r0 = blockIdx.x * R, S = W.dim_state;
+  for (int i = tid; i < R * HID; i += 256) {
+    const int r = i / HID, c = i % HID, gr = r0 + r;
+    float z = 0.f, a1 = 0.f, a2 = 0.f;
+    if (gr < n) {
+      const int64_t o = (int64_t)gr * HID + c;
+      a2 = h2[o];
+      a1 = h1[o];
+      float d;
+      if (n_split > 0) {
+        d = 0.f;
+        for (int sp = 0; sp < n_split; ++sp) d += dh2[(int64_t)sp * n * HID + o];
+      } else {
+        d = dh2[o];
+      }
+      z = a2 > 0.f ? d + dv[gr] * __ldg(W.wv + c) : 0.f;      // dz2 = (dh2 + dv wv) [h2 > 0]
+    }
+    s_dz2[r][c] = z; s_h1[r][c] = a1; s_t[r][c] = a2;
+  }
+  for (int i = tid; i < R * S; i += 256) {
+    const int r = i / S, c = i % S;
+    s_obs[r][c] = (r0 + r < n) ? obs[(int64_t)idx[r0 + r] * S + c] : 0.f;
+  }
+  if (tid < R) s_dv[tid] = (r0 + tid < n) ? dv[r0 + tid] : 0.f;
+  __syncthreads();
+  // critic.last and b2 gradients
+  if (tid < HID) {
+    float gw = 0.f, gb = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) { gw = fmaf(s_dv[r], s_t[r][tid], gw); gb += s_dz2[r][tid]; }
+    atomicAdd(G.wv + tid, gw);
+    atomicAdd(G.b2 + tid, gb);
+  } else if (tid == HID) {
+    float g = 0.f;
+    for (int r = 0; r < R; ++r) g += s_dv[r];
+    atomicAdd(G.bv, g);
+  }
+  // dW2t[k][c] += sum_r h1[r][k] dz2[r][c]:  thread = (k, 16 columns)
+  {
+    const int k = tid >> 2, cq = (tid & 3) * 16;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const float x = s_h1[r][k];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, s_dz2[r][cq + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) atomicAdd(G.w2t + (size_t)k * HID + cq + j, acc[j]);
+  }
+  __syncthreads();   // s_t (h2) is consumed
+  // dz1[r][k] = (sum_c dz2[r][c] W2t[k][c]) [h1 > 0]:  thread = (row, 8 k)
+  {
+    const int r = tid % R, kg = (tid / R) * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int c4 = 0; c4 < HID / 4; ++c4) {
+      const float z0 = s_dz2[r][4 * c4], z1 = s_dz2[r][4 * c4 + 1], z2 = s_dz2[r][4 * c4 + 2], z3 = s_dz2[r][4 * c4 + 3];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W.w2t + (size_t)(kg + j) * HID + 4 * c4));
+        acc[j] = fmaf(z0, w.x, acc[j]); acc[j] = fmaf(z1, w.y, acc[j]);
+        acc[j] = fmaf(z2, w.z, acc[j]); acc[j] = fmaf(z3, w.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_t[r][kg + j] = s_h1[r][kg + j] > 0.f ? acc[j] : 0.f;
+  }
+  __syncthreads();
+  // b1, dW1t[s][c] += sum_r obs[r][s] dz1[r][c]
+  if (tid < HID) {
+    float gb = 0.f;
+    for (int r = 0; r < R; ++r) gb += s_t[r][tid];
+    atomicAdd(G.b1 + tid, gb);
+  }
+  for (int o = tid; o < S * HID; o += 256) {
+    const int sI = o / HID, c = o % HID;
+    float a = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) a = fmaf(s_obs[r][sI], s_t[r][c], a);
+    atomicAdd(G.w1t + (size_t)sI * HID + c, a);
+  }
+  // d_obs[slot][s] = sum_c dz1[r][c] W1t[s][c]
+  if (d_obs) {
+    for (int o = tid; o < R * S; o += 256) {
+      const int r = o / S, sI = o % S;
+      if (r0 + r >= n) continue;
+      float a = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < HID; ++c) a = fmaf(s_t[r][c], __ldg(W.w1t + (size_t)sI * HID + c), a);
+      d_obs[(int64_t)idx[r0 + r] * S + sI] = a;
+    }
   }
 }
 
@@ -215,17 +342,6 @@ __global__ void ent_merge_kernel(int n, int n_split, const float* __restrict__ e
   float e = 0.f;
   for (int s = 0; s < n_split; ++s) e += ent_part[(int64_t)r * n_split + s];
   terms[4 * r + 2] = e;
-}
-
-// dz2 = (sum_splits dh2_part + dv * wv) * [h2 > 0]
-__global__ void dz2_tc_kernel(int n, int n_split, const float* __restrict__ dh2_part, const float* __restrict__ dv,
-                              const float* __restrict__ wv, const float* __restrict__ h2, float* __restrict__ dz2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * HID) return;
-  const int r = i / HID, c = i % HID;
-  float d = 0.f;
-  for (int s = 0; s < n_split; ++s) d += dh2_part[(int64_t)s * n * HID + i];
-  dz2[i] = h2[i] > 0.f ? d + dv[r] * __ldg(wv + c) : 0.f;
 }
 
 // policy evaluation (process_fn): merge pass F's partials -> Categorical.log_prob of the stored action; scatter the
@@ -384,35 +500,6 @@ struct DlB {  // B(k = row, n = column): contiguous along n
   __device__ __forceinline__ float operator()(int k, int n) const { return d.at(k, n); }
 };
 
-// dz2 = (dh2 + dv * wv) * [h2 > 0]
-__global__ void dz2_kernel(int n, const float* __restrict__ dh2, const float* __restrict__ dv,
-                           const float* __restrict__ wv, const float* __restrict__ h2, float* __restrict__ dz2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * HID) return;
-  const int r = i / HID, c = i % HID;
-  dz2[i] = h2[i] > 0.f ? dh2[i] + dv[r] * __ldg(wv + c) : 0.f;
-}
-
-// critic.last gradients: g_wv[c] = sum_r dv[r] h2[r][c], g_bv = sum_r dv[r]   (single CTA, fixed order)
-__global__ void __launch_bounds__(256)
-critic_grad_kernel(int n, const float* __restrict__ dv, const float* __restrict__ h2, float* g_wv, float* g_bv) {
-  __shared__ float sh[4][HID + 1];
-  const int c = threadIdx.x % HID, part = threadIdx.x / HID;
-  float s = 0.f, sb = 0.f;
-  for (int r = part; r < n; r += 4) {
-    const float d = dv[r];
-    s = fmaf(d, h2[(int64_t)r * HID + c], s);
-    sb += d;
-  }
-  sh[part][c] = s;
-  if (c == 0) sh[part][HID] = sb;
-  __syncthreads();
-  if (part == 0) {
-    g_wv[c] = sh[0][c] + sh[1][c] + sh[2][c] + sh[3][c];
-    if (c == 0) g_bv[0] = sh[0][HID] + sh[1][HID] + sh[2][HID] + sh[3][HID];
-  }
-}
-
 __global__ void __launch_bounds__(1024)
 adv_stats_kernel(const int32_t* __restrict__ mb_off, const int32_t* __restrict__ idx, const float* __restrict__ adv,
                  double* __restrict__ stats) {
@@ -454,7 +541,7 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
   auto take = [&](int64_t cnt) { float* r = p; p += align64(cnt); return r; };
   float *h1 = take((int64_t)n * HID), *h2 = take((int64_t)n * HID), *vtmp = take(n);
   float *pm = take((int64_t)n * MAX_SPLIT), *ps = take((int64_t)n * MAX_SPLIT), *la = take(n);
-  CIRS_LAUNCH(trunk_fwd_kernel, (n + 63) / 64, 256, 0, st, *w, n, row_idx, obs, h1, h2, vtmp);
+  CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, row_idx, obs, h1, h2, vtmp);
   CIRS_CHECK_LAUNCH();
   const int n_split = plan_split(n, w->n_action);
   HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action};
@@ -518,7 +605,7 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   int tc_split = 0;
 
   // ---- forward
-  CIRS_LAUNCH(trunk_fwd_kernel, (n + 63) / 64, 256, 0, st, *w, n, idx, obs, ws.h1, ws.h2, ws.value);
+  CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, idx, obs, ws.h1, ws.h2, ws.value);
   CIRS_CHECK_LAUNCH();
   if (gauss) {
     float* dz = ws.logits;                      // [n, 32] d loss / d z
@@ -579,33 +666,10 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
                              split_for((n + 63) / 64, nA, 16), nullptr, st, "head_dh2_gemm");
   CIRS_CHECK_LAUNCH();
   }
-  // ---- critic head + trunk
-  CIRS_LAUNCH(critic_grad_kernel, 1, 256, 0, st, n, ws.dv, ws.h2, grads->wv, grads->bv);
+  // ---- critic head + trunk: one fused kernel
+  CIRS_LAUNCH(trunk_bwd_kernel, (n + 31) / 32, 256, 0, st, *w, *grads, n, idx, obs, tc ? ws.dh2_part : ws.dh2,
+              tc ? tc_split : 0, ws.dv, ws.h1, ws.h2, d_obs);
   CIRS_CHECK_LAUNCH();
-  if (tc) {
-    CIRS_LAUNCH(dz2_tc_kernel, (n * HID + 255) / 256, 256, 0, st, n, tc_split, ws.dh2_part, ws.dv, w->wv, ws.h2, ws.dz2);
-  } else {
-    CIRS_LAUNCH(dz2_kernel, (n * HID + 255) / 256, 256, 0, st, n, ws.dh2, ws.dv, w->wv, ws.h2, ws.dz2);
-  }
-  CIRS_CHECK_LAUNCH();
-  // dW2t[k][c] = sum_r h1[r][k] dz2[r][c], db2
-  launch_gemm<64, 64, 16, 4>(ColMajorA{ws.h1, HID, nullptr}, RowMajorB{ws.dz2, HID, nullptr},
-                             AtomicEp{grads->w2t, HID}, HID, HID, n, split_for(1, n, 16), grads->b2, st, "trunk_dW2_gemm");
-  CIRS_CHECK_LAUNCH();
-  // dz1[r][k] = (sum_c dz2[r][c] W2t[k][c]) * [h1 > 0]
-  launch_gemm<64, 64, 16, 4>(RowMajorA{ws.dz2, HID, nullptr}, ColMajorB{w->w2t, HID},
-                             StoreEp{ws.dz1, HID, nullptr, 0, nullptr, ws.h1, HID}, n, HID, HID, 1, nullptr, st, "trunk_dz1_gemm");
-  CIRS_CHECK_LAUNCH();
-  // dW1t[s][c] = sum_r obs[idx[r]][s] dz1[r][c], db1
-  launch_gemm<64, 64, 16, 4>(ColMajorA{obs, S, idx}, RowMajorB{ws.dz1, HID, nullptr}, AtomicEp{grads->w1t, HID}, S,
-                             HID, n, split_for(1, n, 16), grads->b1, st, "trunk_dW1_gemm");
-  CIRS_CHECK_LAUNCH();
-  // d_obs[idx[r]][s] = sum_c dz1[r][c] W1t[s][c]
-  if (d_obs) {
-    launch_gemm<64, 64, 16, 4>(RowMajorA{ws.dz1, HID, nullptr}, ColMajorB{w->w1t, HID},
-                               StoreEp{d_obs, S, nullptr, 0, idx, nullptr, 0}, n, S, HID, 1, nullptr, st, "trunk_dobs_gemm");
-    CIRS_CHECK_LAUNCH();
-  }
   return CIRS_OK;
 }
 
