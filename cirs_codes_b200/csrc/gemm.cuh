@@ -83,42 +83,45 @@ gemm_kernel(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split, float* __
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   float csum = 0.f;  // column sum of B over this CTA's k-range (bias gradient), column n0 + tid % BN
 
-  for (int k0 = kb; k0 < ke; k0 += BK) {
-    // ---- stage A tile (BM x BK) as As[k][m]
-    if (LA::INNER_IS_K) {
-#pragma unroll 2
-      for (int i = tid; i < BM * BK; i += NT) {
-        const int kk = i % BK, mm = i / BK;
-        const int m = m0 + mm, k = k0 + kk;
-        As[kk][mm] = (m < M && k < ke) ? la(m, k) : 0.f;
-      }
-    } else {
-#pragma unroll 2
-      for (int i = tid; i < BM * BK; i += NT) {
-        const int mm = i % BM, kk = i / BM;
-        const int m = m0 + mm, k = k0 + kk;
-        As[kk][mm] = (m < M && k < ke) ? la(m, k) : 0.f;
-      }
+  // Register double buffering: the operand elements of k-step s+1 are loaded from global memory into registers
+  // before the FMAs of k-step s, so the load latency hides behind the math instead of adding to every step.
+  constexpr int NA = BM * BK / NT, NB = BN * BK / NT;
+  static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile must be a multiple of the CTA size");
+  float ra[NA], rb[NB];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int i = tid + j * NT;
+      const int kk = LA::INNER_IS_K ? i % BK : i / BM, mm = LA::INNER_IS_K ? i / BK : i % BM;
+      const int m = m0 + mm, k = k0 + kk;
+      ra[j] = (m < M && k < ke) ? la(m, k) : 0.f;
     }
-    // ---- stage B tile (BK x BN) as Bs[k][n]
-    if (LB::INNER_IS_K) {
-#pragma unroll 2
-      for (int i = tid; i < BN * BK; i += NT) {
-        const int kk = i % BK, nn = i / BK;
-        const int n = n0 + nn, k = k0 + kk;
-        Bs[kk][nn] = (n < N && k < ke) ? lb(k, n) : 0.f;
-      }
-    } else {
-#pragma unroll 2
-      for (int i = tid; i < BN * BK; i += NT) {
-        const int nn = i % BN, kk = i / BN;
-        const int n = n0 + nn, k = k0 + kk;
-        const float v = (n < N && k < ke) ? lb(k, n) : 0.f;
-        Bs[kk][nn] = v;
-        if (NT % BN == 0) csum += v;  // nn == tid % BN for every i when NT % BN == 0
-      }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int i = tid + j * NT;
+      const int kk = LB::INNER_IS_K ? i % BK : i / BN, nn = LB::INNER_IS_K ? i / BK : i % BN;
+      const int n = n0 + nn, k = k0 + kk;
+      rb[j] = (n < N && k < ke) ? lb(k, n) : 0.f;
+    }
+  };
+  if (kb < ke) load_tiles(kb);
+  for (int k0 = kb; k0 < ke; k0 += BK) {
+    // ---- registers -> shared: As[k][m], Bs[k][n]
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int i = tid + j * NT;
+      const int kk = LA::INNER_IS_K ? i % BK : i / BM, mm = LA::INNER_IS_K ? i / BK : i % BM;
+      As[kk][mm] = ra[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int i = tid + j * NT;
+      const int kk = LB::INNER_IS_K ? i % BK : i / BN, nn = LB::INNER_IS_K ? i / BK : i % BN;
+      Bs[kk][nn] = rb[j];
+      if (!LB::INNER_IS_K && NT % BN == 0) csum += rb[j];  // nn == tid % BN for every j when NT % BN == 0
     }
     __syncthreads();
+    if (k0 + BK < ke) load_tiles(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[TM];

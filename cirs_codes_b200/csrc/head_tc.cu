@@ -25,6 +25,7 @@ constexpr uint32_t B_LBO = TN * 16, B_STEP = 2 * TN * 16;   // K-major, R = 64
 constexpr uint32_t SBO = 128;
 constexpr uint32_t IDESC = idesc_tf32(TM, TN, 0, 0);
 constexpr int KSTEPS = HID / 8;   // every contraction here has depth 64
+#define MASKED (-1.0e30f)                         /* bias of the padding columns: exp(. - max) == 0 */
 #define LOG_EPS (-15.942385152878742f)            /* log(CATEGORICAL_EPS) */
 #define LOG_1M_EPS (-1.1920929665620963e-07f)     /* log(1 - CATEGORICAL_EPS) */
 
@@ -93,12 +94,12 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   auto prefetch = [&](int ct) {
     const int c0 = ct * TN;
     tb_.load(tid, SrcW3T{H.w3t, H.ldA, c0});
-    b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : 0.f;
+    b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : MASKED;
   };
   if (ct0 < ct1) prefetch(ct0);
   int a = -1;
   if (act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
-  float m = -INFINITY, s = 0.f, lav = 0.f;
+  float m = MASKED, s = 0.f, lav = 0.f;
   bool found = false;
   uint32_t ph = 0, tb = 0;
   for (int ct = ct0; ct < ct1; ++ct) {
@@ -121,10 +122,10 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
     float v[32];
     tmem_ld32(tmem_addr(tb, (warp & 3) * 32, half * 32), v);
     const int cb = c0 + half * 32;
-    float mt = -INFINITY;
+    float mt = MASKED;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float x = cb + j < H.nA ? v[j] + sb3[half * 32 + j] : -INFINITY;
+      const float x = v[j] + sb3[half * 32 + j];   // padding columns carry the MASKED bias
       v[j] = x;
       mt = fmaxf(mt, x);
     }
@@ -134,12 +135,12 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
         if (j == a - cb) lav = v[j];
       found = true;
     }
-    if (mt > -INFINITY) {
+    if (mt > 0.5f * MASKED) {
       const float mn = fmaxf(m, mt);
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc += expf(v[j] - mn);
-      s = s * expf(m - mn) + acc;
+      for (int j = 0; j < 32; ++j) acc += fast_exp(v[j] - mn);
+      s = s * fast_exp(m - mn) + acc;
       m = mn;
     }
     fence_before_sync();
@@ -151,9 +152,7 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   if (half == 0 && r0 + row < H.n) {
     const float m1 = sm[tid + TM], s1 = ss[tid + TM];
     const float M = fmaxf(m, m1);
-    float S = 0.f;
-    if (m > -INFINITY) S += s * expf(m - M);
-    if (m1 > -INFINITY) S += s1 * expf(m1 - M);
+    const float S = s * fast_exp(m - M) + s1 * fast_exp(m1 - M);   // an empty half has s == 0
     pm[(size_t)(r0 + row) * n_split + split] = M;
     ps[(size_t)(r0 + row) * n_split + split] = S;
   }
@@ -199,7 +198,7 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
     const int c0 = ct * TN;
     tn.load(tid, SrcW3T{H.w3t, H.ldA, c0});
     tk.load(tid, SrcW3{H.w3t, H.ldA, c0});
-    b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : 0.f;
+    b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : MASKED;
   };
   if (ct0 < ct1) prefetch(ct0);
   const bool live = r0 + row < H.n;
@@ -232,16 +231,16 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
       const int cb = c0 + qt * 16;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float x = v[j] + sb3[qt * 16 + j];
-        const float p = cb + j < H.nA ? expf(x - rm) * iz : 0.f;
-        // entropy of Categorical(probs): -sum p log(clamp(p, eps, 1 - eps)); log p = x - max - log Z inside the clamp
-        const float lg = p < CATEGORICAL_EPS ? LOG_EPS : (p > 1.0f - CATEGORICAL_EPS ? LOG_1M_EPS : x - rm - log_z);
+        const float xm = v[j] + sb3[qt * 16 + j] - rm;          // logit - max (padding columns: -1e30)
+        const float p = fast_exp(xm) * iz;
+        // entropy of Categorical(probs): -sum p log(clamp(p, eps, 1 - eps)) with log clamp(p) = clamp(log p)
+        const float lg = fminf(fmaxf(xm - log_z, LOG_EPS), LOG_1M_EPS);
         ent = fmaf(-p, lg, ent);
         v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        tile_store_split(dl_hi, dl_lo, TM, row, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        tile_store_split_trunc(dl_hi, dl_lo, TM, row, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     }
     fence_async_smem();
     fence_before_sync();
@@ -320,7 +319,7 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   };
   if (rs0 < rs1) prefetch(rs0);
   const bool live = col < H.nA;
-  const float b3v = live ? __ldg(H.b3 + col) : 0.f;
+  const float b3v = live ? __ldg(H.b3 + col) : MASKED;
   float db3 = 0.f;
   uint32_t ph = 0, tb = 0;
   for (int r0 = rs0; r0 < rs1; r0 += TN) {
@@ -346,14 +345,14 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int jj = qt * 16 + j;
-        const float p = expf(v[j] + b3v - srm[jj]) * siz[jj];
-        const float d = live ? scf[jj] * ((sac[jj] == col ? 1.f : 0.f) - p) : 0.f;
+        const float p = fast_exp(v[j] + b3v - srm[jj]) * siz[jj];   // padding columns / rows: bias -1e30 or 1/Z = 0
+        const float d = scf[jj] * ((sac[jj] == col ? 1.f : 0.f) - p);
         db3 += d;
         v[j] = d;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        tile_store_split(dl_hi, dl_lo, TM, cl, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        tile_store_split_trunc(dl_hi, dl_lo, TM, cl, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
     }
     fence_async_smem();
     fence_before_sync();

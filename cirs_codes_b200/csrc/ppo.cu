@@ -122,23 +122,52 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
   __shared__ float s_dz2[R][LD], s_h1[R][LD], s_t[R][LD];   // s_t: h2, later dz1
   __shared__ float s_obs[R][33], s_dv[R];
   const int tid = threadIdx.x, r0 = blockIdx.x * R, S = W.dim_state;
-  for (int i = tid; i < R * HID; i += 256) {
-    const int r = i / HID, c = i % HID, gr = r0 + r;
-    float z = 0.f, a1 = 0.f, a2 = 0.f;
-    if (gr < n) {
-      const int64_t o = (int64_t)gr * HID + c;
-      a2 = h2[o];
-      a1 = h1[o];
-      float d;
-      if (n_split > 0) {
-        d = 0.f;
-        for (int sp = 0; sp < n_split; ++sp) d += dh2[(int64_t)sp * n * HID + o];
-      } else {
-        d = dh2[o];
-      }
-      z = a2 > 0.f ? d + dv[gr] * __ldg(W.wv + c) : 0.f;      // dz2 = (dh2 + dv wv) [h2 > 0]
+  {
+    // each thread owns 8 (row, column) elements; the split partials of all 8 are loaded together so that their
+    // latencies overlap (the partials are [n_split, n, 64])
+    constexpr int E = R * HID / 256;
+    float d[E];
+    int64_t off[E];
+    bool okv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = tid + e * 256, gr = r0 + i / HID;
+      okv[e] = gr < n;
+      off[e] = (int64_t)gr * HID + (i % HID);
+      d[e] = 0.f;
     }
-    s_dz2[r][c] = z; s_h1[r][c] = a1; s_t[r][c] = a2;
+    if (n_split > 0) {
+      const int64_t stride = (int64_t)n * HID;
+      int sp = 0;
+      for (; sp + 4 <= n_split; sp += 4) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if (!okv[e]) continue;
+          const float* q = dh2 + (int64_t)sp * stride + off[e];
+          d[e] += (q[0] + q[stride]) + (q[2 * stride] + q[3 * stride]);
+        }
+      }
+      for (; sp < n_split; ++sp) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (okv[e]) d[e] += dh2[(int64_t)sp * stride + off[e]];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (okv[e]) d[e] = dh2[off[e]];
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = tid + e * 256, r = i / HID, c = i % HID;
+      float z = 0.f, a1 = 0.f, a2 = 0.f;
+      if (okv[e]) {
+        a2 = h2[off[e]];
+        a1 = h1[off[e]];
+        z = a2 > 0.f ? d[e] + dv[r0 + r] * __ldg(W.wv + c) : 0.f;      // dz2 = (dh2 + dv wv) [h2 > 0]
+      }
+      s_dz2[r][c] = z; s_h1[r][c] = a1; s_t[r][c] = a2;
+    }
   }
   for (int i = tid; i < R * S; i += 256) {
     const int r = i / S, c = i % S;

@@ -161,6 +161,19 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(r);
 }
 
+// exp(x) with ~2 ulp error in 6 instructions: ex2.approx of the rounded product x * log2(e), corrected to first order
+// for the product's rounding error and the low part of log2(e).  x <= 0 in all uses; exp(-1e30) = 0 (no NaN).
+__device__ __forceinline__ float fast_exp(float x) {
+  const float t = x * 1.4426950408889634f;
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  const float e = fmaf(x, 1.4426950408889634f, -t) + x * 1.925963033500011e-8f;
+  return fmaf(r, e * 0.6931471805599453f, r);
+}
+// cheaper split for operands that only need ~2^-22 relative accuracy (gradients): hi by truncation, lo = x - hi exact
+// (the MMA truncates lo to TF32)
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 // byte offset of the 16-byte chunk (r, c4 = c / 4) inside an R-row tile
 __device__ __forceinline__ uint32_t tile_chunk_off(int R, int r, int c4) {
   return (uint32_t)c4 * (uint32_t)(R * 16) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
@@ -172,6 +185,12 @@ __device__ __forceinline__ void tile_store_split(char* hi, char* lo, int R, int 
   *reinterpret_cast<float4*>(hi + off) = h;
   *reinterpret_cast<float4*>(lo + off) =
       make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+}
+__device__ __forceinline__ void tile_store_split_trunc(char* hi, char* lo, int R, int r, int c4, float4 v) {
+  const uint32_t off = tile_chunk_off(R, r, c4);
+  float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
+  *reinterpret_cast<float4*>(hi + off) = h;
+  *reinterpret_cast<float4*>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
 }
 // Cooperative staging of an R x C tile (R % 8 == 0, C % 16 == 0) from a row-major source, split into a LOAD phase
 // (global -> registers, all loads of a thread issued back to back so their latencies overlap, and early enough to
