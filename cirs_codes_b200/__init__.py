@@ -12,8 +12,10 @@ from .env import KuaishouVectorEnv, TaobaoVectorEnv  # noqa: F401
 from .state_tracker import StateTrackerTransformer  # noqa: F401
 from .policy import PPOPolicy  # noqa: F401
 from .collector import Collector  # noqa: F401
+from .collector_set import CollectorSet  # noqa: F401
+from .trainer import onpolicy_trainer, save_checkpoint, load_checkpoint  # noqa: F401
 
 __all__ = ["DenseFeat", "SparseFeat", "SparseFeatP", "VarLenSparseFeat", "build_input_features",
            "compute_input_dim", "get_dataset_columns", "get_feature_names", "Batch", "VectorReplayBuffer", "Actor",
            "ActorProb", "Critic", "Net", "orthogonal_init", "KuaishouVectorEnv", "TaobaoVectorEnv", "StateTrackerTransformer", "PPOPolicy",
-           "Collector"]
+           "Collector", "CollectorSet", "onpolicy_trainer", "save_checkpoint", "load_checkpoint"]

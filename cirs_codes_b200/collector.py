@@ -50,8 +50,13 @@ class Collector:
         self.fused = bool(fused and isinstance(env, (KuaishouVectorEnv, TaobaoVectorEnv))
                           and isinstance(self.tracker, StateTrackerTransformer)
                           and hasattr(policy, "sample_device") and isinstance(buffer, VectorReplayBuffer)
-                          and buffer.buffer_num == self.env_num and not remove_recommended_ids
+                          and buffer.buffer_num == self.env_num
+                          and not (remove_recommended_ids and self.taobao)
                           and getattr(policy, "continuous", False) == self.taobao)
+        if self.fused and remove_recommended_ids:
+            env.enable_seen()   # the device-side set of already-recommended items (core/policy/utils.py:7-27)
+        if remove_recommended_ids:
+            persistent = True                 # the per-turn kernel chain has no device-side seen mask
         self.persistent = bool(persistent)    # fused rollout as ONE persistent cooperative kernel (csrc/rollout.cu)
         self.use_graph = bool(use_graph)      # else: replay the per-turn kernels from one captured CUDA graph
         self.data = Batch()
@@ -238,6 +243,8 @@ class Collector:
             # the whole rollout in ONE persistent cooperative kernel (csrc/rollout.cu)
             pol = self.policy
             mode = 1 if (pol._deterministic_eval and not pol.training) else 0
+            if self.remove_recommended_ids:
+                mode |= 4
             _lib.call("cirs_rollout_kuaishou", C.byref(env._struct), C.byref(trk._w), C.byref(pol._w),
                       _lib.ptr(f["d_users"]), _lib.ptr(env.active), _lib.ptr(f["act"]), _lib.ptr(f["logp"]),
                       _lib.ptr(f["value"]), _lib.ptr(f["cur"]), _lib.ptr(env.rew), _lib.ptr(env.done), L,

@@ -88,6 +88,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
   const int n_rt = (P.n_rows + ROWS - 1) / ROWS;
   const uint32_t tb = *S.tmem;
   const int nA = P.W.n_action;
+  const int seen_words = (nA + 31) >> 5;
   const uint64_t offset = P.offset + (P.rng_counter ? (uint64_t)*P.rng_counter : 0ull);
   auto issue = [&](int rt) {
     mma_3xtf32(tb + 128u * (rt & 1), smem_u32(S.a_hi), smem_u32(S.a_lo), A_STEP, A_LBO, 128u, smem_u32(S.w_hi),
@@ -155,12 +156,17 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
             qn[j] = fmaxf(w < 0.00390625f ? ql : -__logf(u), 1e-30f);
           }
         }
+        // remove_recommended_ids (core/policy/utils.py:30-58): items already shown this episode leave the distribution
+        uint32_t seen_bits = 0u;
+        if (P.seen) seen_bits = P.seen[(size_t)rid * seen_words + (nb >> 5)] >> (nb & 31);
         float l[4], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          l[j] = nb + j < nA ? __uint_as_float(vr[ch & 1][4 * q4 + j]) + S.b3[lbase + ch * 8 + 4 * q4 + j] : -INFINITY;
+          const bool ok = nb + j < nA && !((seen_bits >> j) & 1u);
+          l[j] = ok ? __uint_as_float(vr[ch & 1][4 * q4 + j]) + S.b3[lbase + ch * 8 + 4 * q4 + j] : -INFINITY;
           mx = fmaxf(mx, l[j]);
         }
+        if (mx == -INFINITY) continue;
         if (mx > m) {
           const float sc = __expf(m - mx);   // m = -inf at the start: exp(-inf) = 0
           z *= sc;

@@ -221,8 +221,8 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
                                      float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter, int32_t mode,
                                      int32_t max_steps, int32_t force_length, void* workspace, void* stream) {
   if (!env || !tw || !pw || !users || !active || !act || !logp || !value || !cur_state || !rew || !done || !ep_len ||
-      !kcache || !vcache || !workspace || max_steps < 0) {
-    cirs_set_error("cirs_rollout_kuaishou: null argument");
+      !kcache || !vcache || !workspace || max_steps < 0 || (mode & 3) > 1) {
+    cirs_set_error("cirs_rollout_kuaishou: null argument or bad mode");
     return CIRS_ERR_ARG;
   }
   if (!tw->emb_user || !tw->emb_item || tw->d % tw->nhead != 0 || tw->nlayers > CIRS_MAX_LAYERS ||
@@ -238,6 +238,12 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   RolloutArgs A{};
   // tensor-core head: needs one catalogue slice per CTA (checked against the grid below) and plain sampling modes
   const int n_slices = (pw->n_action + cirs_actor_tc::SLICE - 1) / cirs_actor_tc::SLICE;
+  const bool mask_seen = (mode & 4) != 0;   // remove_recommended_ids: mask the items in env->seen
+  mode &= 3;
+  if (mask_seen && !env->seen) {
+    cirs_set_error("cirs_rollout_kuaishou: mode bit 2 (remove recommended ids) needs env->seen");
+    return CIRS_ERR_ARG;
+  }
   bool tc = cirs_head_tc::head_tc_enabled(env->n_env, pw->n_action, pw->ld_action) && (mode == 0 || mode == 1) &&
             pw->dim_state <= 32;
   // the tracker's weights staged in shared memory when they fit next to the head's buffers (d = 32: 113 KB)
@@ -298,7 +304,7 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.H.W = *pw; A.H.n_rows = env->n_env; A.H.gather = nullptr; A.H.state_by_k = 0; A.H.out_by_k = 0;
   A.H.active = active; A.H.state = cur_state; A.H.state_stride = tw->dim_state; A.H.noise_q = nullptr;
   A.H.seed = seed; A.H.offset = 1ull << 40; A.H.rng_counter = reinterpret_cast<unsigned long long*>(rng_counter);
-  A.H.mode = mode; A.H.seen = nullptr; A.H.act_in = nullptr; A.H.value = value;
+  A.H.mode = mode; A.H.seen = mask_seen ? env->seen : nullptr; A.H.act_in = nullptr; A.H.value = value;
   int grid = max_ctas;
   if (!plan_head(A.H, grid)) {
     cirs_set_error("cirs_rollout_kuaishou: unsupported head shape");

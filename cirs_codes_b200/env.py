@@ -110,6 +110,15 @@ class KuaishouVectorEnv:
         self.action_space = [Discrete(self.n_item, None if seed is None else seed + i) for i in range(min(B, 8))]
         self._rng = np.random.default_rng(seed)
 
+    def enable_seen(self):
+        """Allocate the per-environment bitset of already-recommended items (remove_recommended_ids on the device);
+        the step kernel sets the bit of every action and reset clears it."""
+        if self.seen is None:
+            self.seen = torch.zeros(self.env_num, (self.n_item + 31) // 32, dtype=torch.int32,
+                                    device=self.user.device)
+            self._struct.seen = _lib.ptr(self.seen)
+        return self.seen
+
     # ------------------------------------------------------------------ gym / tianshou surface
     def __len__(self):
         return self.env_num

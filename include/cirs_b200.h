@@ -272,7 +272,9 @@ int cirs_actorprob_eval(const cirs_policy_weights* w, int32_t n_rows, const int3
  * per turn  actor head -> sample -> environment step -> tracker token -> replay-buffer slots, until every episode
  * has ended or max_steps turns were played.  All arrays are per environment slot ([B] or [B, .]); traj_* are the
  * replay buffer's env-major arrays (traj_len slots per environment); ep_len[e] = episode length.
- * rng_counter: device uint64, advanced once per turn (Philox offset of the sampler).  mode: 0 sample, 1 argmax.
+ * rng_counter: device uint64, advanced once per turn (Philox offset of the sampler).  mode: 0 sample, 1 argmax;
+ * + 4: remove_recommended_ids (core/policy/utils.py:7-58; the test collectors NX_0 / NX_x of core/collector_set.py:19) --
+ * items in env->seen (maintained by the environment step) are masked out of the softmax and of the race.
  * Same device code as cirs_actor_sample / cirs_kuaishou_step / cirs_tracker_step (bit-identical results).
  * The workspace's bytes [256, 256 + 8 * (1 + 3 * 512)) hold int64 phase timers written by the kernel:
  * turns played, then per turn {running environments, ns in the actor-head phase, ns in the per-environment phase}. */

@@ -388,3 +388,86 @@ def test_fused_collect_matches_generic(H):
         assert a["res"]["n/st"] == b["res"]["n/st"] and np.array_equal(a["res"]["lens"], b["res"]["lens"])
         G.assert_close(a["res"]["rews"], b["res"]["rews"], 1e-6, what="episode rewards")
         assert a["lens"].min() >= 1 and a["lens"].max() <= c["T"]
+
+
+@pytest.mark.parametrize("force_length", [0, 6])
+def test_fused_test_collectors_match_generic(H, force_length):
+    """The test-time collectors of core/collector_set.py:19-33 (raw KuaishouEnv reward, remove_recommended_ids,
+    force_length) on the fused path == the reference's generic loop (host-built seen bitset, core/policy/utils.py:7-27);
+    argmax actions.  No item may repeat inside an episode."""
+    import cirs_codes_b200 as cb
+    z, c = H.synthetic_case(U=64, I=300, B=40, T=12, N=3, thr=1, d=32)
+    users = np.random.default_rng(2).integers(0, c["U"], size=c["B"])
+    outs = []
+    for fused in (True, False):
+        env = H.make_env(z, c, simulated=False)
+        trk = H.make_tracker(None, c)
+        sd = trk.state_dict()
+        g = torch.Generator().manual_seed(3)
+        sd["embedding_dict.feat_user.weight"] = torch.randn(c["U"], c["d"], generator=g) * 0.1
+        sd["embedding_dict.feat_item.weight"] = torch.randn(c["I"], c["d"], generator=g) * 0.1
+        trk.load_state_dict(sd)
+        pol = H.make_policy(None, c, None, deterministic_eval=True)
+        pol.eval()
+        buf = cb.VectorReplayBuffer(c["B"] * c["T"], c["B"])
+        col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state, fused=fused, remove_recommended_ids=True,
+                           force_length=force_length)
+        assert col.fused == fused
+        res = col.collect(n_episode=c["B"], users=users)
+        idx = buf.sample_index(0)
+        outs.append(dict(res=res, lens=buf._lengths.copy(), act=buf.act[idx].copy(), rew=buf.rew[idx].copy(),
+                         done=buf.done[idx].copy()))
+    a, b = outs
+    assert np.array_equal(a["lens"], b["lens"]) and np.array_equal(a["act"], b["act"])
+    assert np.array_equal(a["done"], b["done"])
+    G.assert_close(a["rew"], b["rew"], 1e-6, what="rew")
+    if force_length:
+        assert np.all(a["lens"] == force_length)
+    off = np.concatenate([[0], np.cumsum(a["lens"])])
+    for e in range(c["B"]):
+        ep = a["act"][off[e]:off[e + 1]]
+        assert len(np.unique(ep)) == len(ep), "an item was recommended twice in one episode"
+
+
+def test_collector_set_keys(H):
+    """CollectorSet.collect merges the three collectors' results with the reference's key prefixes."""
+    import cirs_codes_b200 as cb
+    z, c = H.synthetic_case(U=64, I=300, B=16, T=12, N=3, thr=1, d=32)
+    trk = H.make_tracker(None, c)
+    pol = H.make_policy(None, c, None)
+    envs = {"FB": H.make_env(z, c, simulated=False), "NX_0": H.make_env(z, c, simulated=False),
+            "NX_5": H.make_env(z, c, simulated=False)}
+    cs = cb.CollectorSet(pol, envs, c["B"] * c["T"], c["B"], preprocess_fn=trk.build_state, force_length=5)
+    res = cs.collect(n_episode=c["B"])
+    for k in ("n/ep", "n/st", "rew", "len", "NX_0_rew", "NX_0_len", "NX_5_rew", "NX_5_len", "NX_5_lens"):
+        assert k in res, k
+    assert np.all(res["NX_5_lens"] == 5) and res["n/ep"] == c["B"]
+    assert cs.collect_step == res["n/st"]
+
+
+def test_trainer_end_to_end_and_checkpoint(H, tmp_path):
+    """CIRS-RL-kuaishou.py:288-358 on the CUDA path: train collector + CollectorSet through onpolicy_trainer for two
+    epochs, then the reference-layout checkpoint round trip."""
+    import cirs_codes_b200 as cb
+    z, c = H.synthetic_case(U=64, I=300, B=16, T=10, N=1, thr=0, d=32)
+    trk = H.make_tracker(None, c)
+    pol = H.make_policy(None, c, trk)
+    train = cb.Collector(pol, H.make_env(z, c), cb.VectorReplayBuffer(c["B"] * c["T"], c["B"]),
+                         preprocess_fn=trk.build_state)
+    envs = {k: H.make_env(z, c, simulated=False) for k in ("FB", "NX_0", "NX_4")}
+    test = cb.CollectorSet(pol, envs, c["B"] * c["T"], c["B"], preprocess_fn=trk.build_state, force_length=4)
+    info = cb.onpolicy_trainer(pol, train, test, trk, max_epoch=2, step_per_epoch=60, repeat_per_collect=2,
+                               episode_per_test=c["B"], batch_size=64, episode_per_collect=c["B"], verbose=False)
+    assert info["train_step"] >= 120 and info["test_episode"] == 3 * c["B"] and np.isfinite(info["best_reward"])
+    path = str(tmp_path / "ck.pt")
+    cb.save_checkpoint(path, pol, trk)
+    before = pol.flat.clone(), trk.flat.clone(), pol.exp_avg.clone()
+    pol.flat.zero_(); trk.flat.zero_(); pol.exp_avg.zero_()
+    ck = cb.load_checkpoint(path, pol, trk)
+    assert set(ck) == {"policy", "optim_RL", "optim_state", "state_tracker"}
+    assert torch.equal(pol.flat, before[0]) and torch.equal(pol.exp_avg, before[2])
+    # padding columns aside, the tracker's parameters survive the state_dict round trip
+    sd = trk.state_dict()
+    trk2 = H.make_tracker(None, c)
+    trk2.load_state_dict(sd)
+    assert torch.equal(trk2.flat, trk.flat)

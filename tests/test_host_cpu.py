@@ -148,3 +148,61 @@ def test_feature_columns_surface():
     assert cb.compute_input_dim(a) == 32 and cb.build_input_features(u + f) == {"feat_user": (0, 1), "feat_feedback": (1, 2)}
     u, a, f, hu, ha, hf = cb.get_dataset_columns(27, "VirtualTB-v0")
     assert cb.compute_input_dim(u) == 88 and cb.compute_input_dim(a) == 27 and hu and ha
+
+
+def test_trainer_loop_with_stub_collectors():
+    """onpolicy_trainer control flow (core/trainer/onpolicy.py:156-240) on stub collectors / policy: collects until
+    step_per_epoch, updates after every collect, evaluates once per epoch (+ once before training), hooks fire."""
+    from cirs_codes_b200.trainer import MovAvg, onpolicy_trainer
+
+    class Col:
+        def __init__(self, policy, n_st):
+            self.policy, self.n_st, self.buffer = policy, n_st, object()
+            self.collect_step = self.collect_episode = 0
+            self.collect_time = 1e-3
+            self.calls = self.resets = 0
+
+        def reset_stat(self):
+            self.collect_step = self.collect_episode = 0
+
+        def reset_env(self):
+            self.resets += 1
+
+        def reset_buffer(self, keep_statistics=False):
+            pass
+
+        def collect(self, n_step=None, n_episode=None):
+            self.calls += 1
+            self.collect_step += self.n_st
+            self.collect_episode += n_episode
+            return {"n/ep": n_episode, "n/st": self.n_st, "rew": float(self.calls), "rew_std": 0.0, "len": 3.0,
+                    "rews": np.ones(n_episode), "lens": np.full(n_episode, 3)}
+
+    class Pol:
+        callbacks = []
+        updates, mode = 0, None
+
+        def train(self):
+            self.mode = "train"
+
+        def eval(self):
+            self.mode = "eval"
+
+        def update(self, sample_size, buffer, batch_size=None, repeat=1):
+            assert self.mode == "train" and sample_size == 0
+            self.updates += 1
+            return {"loss": [1.0, 3.0], "loss/clip": [0.5, 0.5]}
+
+    pol = Pol()
+    tr, te = Col(pol, 40), Col(pol, 7)
+    saved = []
+    info = onpolicy_trainer(pol, tr, te, None, max_epoch=3, step_per_epoch=100, repeat_per_collect=2,
+                            episode_per_test=5, batch_size=64, episode_per_collect=10, verbose=False,
+                            save_model_fn=lambda epoch, policy: saved.append(epoch))
+    assert tr.calls == 9 and pol.updates == 9            # ceil(100 / 40) = 3 collects per epoch
+    assert te.calls == 4 and te.resets == 4              # one evaluation before training + one per epoch
+    assert saved == [1, 2, 3]
+    assert info["train_step"] == 360 and info["test_episode"] == 20 and info["best_reward"] == 4.0
+    m = MovAvg(size=3)
+    m.add([1.0, 2.0]); m.add(6.0); m.add(float("inf"))
+    assert m.get() == 3.0 and m.add(9.0) == (2.0 + 6.0 + 9.0) / 3
