@@ -206,3 +206,66 @@ def test_trainer_loop_with_stub_collectors():
     m = MovAvg(size=3)
     m.add([1.0, 2.0]); m.add(6.0); m.add(float("inf"))
     assert m.get() == 3.0 and m.add(9.0) == (2.0 + 6.0 + 9.0) / 3
+
+
+def test_coverage_callback_matches_reference():
+    """Callback_Coverage_Count (evaluation.py:286-371) on this package's buffer: our one-shot version against a brute
+    force over the stored episodes, and -- in the build container, where /root/reference exists -- against the
+    REFERENCE's own callback walking buffer.prev / next / last_index of the same buffer."""
+    import importlib.util
+    import pandas as pd
+    from cirs_codes_b200.data import Batch, VectorReplayBuffer
+    from cirs_codes_b200.evaluation import Callback_Coverage_Count
+    rng = np.random.default_rng(4)
+    n_item, B, L = 50, 6, 7
+    cats = rng.integers(0, 9, size=(n_item, 4))
+
+    class Env:
+        mat = [np.zeros((3, n_item))]
+
+    class Col:
+        pass
+
+    class Set:
+        env = Env()
+        collector_dict = {}
+
+    results, episodes = {}, {}
+    for name in ("FB", "NX_0"):
+        buf = VectorReplayBuffer(B * L, B, device="cpu")
+        lens = rng.integers(1, L + 1, size=B)
+        ready, t, eps = np.arange(B), 0, [[] for _ in range(B)]
+        first = None
+        while len(ready):
+            acts = rng.integers(0, n_item, size=len(ready))
+            done = lens[ready] == t + 1
+            ptr, *_ = buf.add(Batch(obs=torch.zeros(len(ready), 2), obs_next=torch.zeros(len(ready), 2), act=acts,
+                                    rew=np.ones(len(ready)), done=done), buffer_ids=ready)
+            first = ptr if first is None else first
+            for e, a in zip(ready, acts):
+                eps[e].append(int(a))
+            ready, t = ready[~done], t + 1
+        c = Col()
+        c.buffer = buf
+        Set.collector_dict[name] = c
+        episodes[name] = eps
+        pre = "" if name == "FB" else name + "_"
+        results[pre + "idxs"], results["n/ep"] = first, B
+    dom = {"feat": [(3, 40), (5, 30), (1, 20), (7, 10)]}
+    mine = Callback_Coverage_Count(Set, cats, need_transform=False, item_feat_domination=dom, top_rate=0.6)
+    got = mine.on_epoch_end(1, dict(results))
+    for name in ("FB", "NX_0"):
+        pre = "" if name == "FB" else name + "_"
+        flat = np.concatenate([np.array(e) for e in episodes[name]])
+        assert got[pre + "CV"] == len(set(flat)) / n_item and got[pre + "CV_turn"] == len(set(flat)) / len(flat)
+        assert got[pre + "ifeat_feat"] == np.mean([3 in cats[a] for a in flat])   # cumulative shares .4, .7: only value 3
+    ref_path = "/root/reference/evaluation.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("ref_evaluation", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        df = pd.DataFrame(cats, columns=[f"feat{i}" for i in range(4)])
+        theirs = ref.Callback_Coverage_Count(Set, df, need_transform=False, item_feat_domination=dom, lbe_photo=None,
+                                             top_rate=0.6).on_epoch_end(1, dict(results))
+        for k in ("CV", "CV_turn", "ifeat_feat", "NX_0_CV", "NX_0_CV_turn", "NX_0_ifeat_feat"):
+            assert abs(theirs[k] - got[k]) < 1e-12, (k, theirs[k], got[k])
