@@ -19,12 +19,14 @@ def dominated_values(sorted_items, top_rate):
     return np.array([v for v, _ in sorted_items])[:max(ind, 1)]
 
 
-def feat_dominate_rate(item_cats, acts, sorted_items, top_rate=0.6):
-    """Share of recommendations whose item carries at least one dominated category (evaluation.py:35-47).
-    ``item_cats``: int array [n_item, n_feat] (the ``feat0..3`` columns, 0 = padding)."""
-    dom = dominated_values(sorted_items, top_rate)
-    cats = np.asarray(item_cats)[np.asarray(acts, dtype=np.int64)]
-    return float(np.isin(cats, dom).any(axis=1).sum() / max(len(cats), 1))
+def dominate_rate(cats, dom):
+    """evaluation.py:38-47: per recommendation, the per-value match COUNTS are combined with a bitwise OR into an
+    integer array that is then summed -- for items whose feature columns are distinct (the real data) this is the
+    share of recommendations carrying a dominated category; the integer arithmetic is reproduced as written."""
+    acc = np.zeros(len(cats), dtype=np.int64)
+    for v in dom:
+        acc |= (cats == v).sum(axis=1)
+    return float(acc.sum() / max(len(cats), 1))
 
 
 class Callback_Coverage_Count:
@@ -66,7 +68,7 @@ class Callback_Coverage_Count:
             if self.item_feat_domination is not None and "feat" in self.item_feat_domination and len(acts):
                 cats = self._item_cats(acts)
                 dom = dominated_values(self.item_feat_domination["feat"], self.top_rate)
-                res["ifeat_feat"] = float(np.isin(cats, dom).any(axis=1).sum() / len(cats))
+                res["ifeat_feat"] = dominate_rate(cats, dom)
             out.update(res if name == "FB" else {name + "_" + k: v for k, v in res.items()})
         results.update(out)
         return results

@@ -218,7 +218,7 @@ def test_coverage_callback_matches_reference():
     from cirs_codes_b200.evaluation import Callback_Coverage_Count
     rng = np.random.default_rng(4)
     n_item, B, L = 50, 6, 7
-    cats = rng.integers(0, 9, size=(n_item, 4))
+    cats = np.stack([rng.permutation(9)[:4] for _ in range(n_item)])   # distinct categories per item, like the data
 
     class Env:
         mat = [np.zeros((3, n_item))]
