@@ -118,9 +118,10 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
                  const float* __restrict__ obs, const float* __restrict__ dh2, int n_split,
                  const float* __restrict__ dv, const float* __restrict__ h1, const float* __restrict__ h2,
                  float* __restrict__ d_obs) {
-  constexpr int R = 32, LD = HID + 1;
+  constexpr int R = 16, LD = HID + 1;   // 16 rows per CTA: ~100 CTAs per 1.6k-row minibatch, every phase is short
   __shared__ float s_dz2[R][LD], s_h1[R][LD], s_t[R][LD];   // s_t: h2, later dz1
   __shared__ float s_obs[R][33], s_dv[R];
+  static_assert(256 % R == 0 && HID % (256 / R) == 0, "row tile");
   const int tid = threadIdx.x, r0 = blockIdx.x * R, S = W.dim_state;
   {
     // each thread owns 8 (row, column) elements; the split partials of all 8 are loaded together so that their
@@ -203,23 +204,25 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
     for (int j = 0; j < 16; ++j) atomicAdd(G.w2t + (size_t)k * HID + cq + j, acc[j]);
   }
   __syncthreads();   // s_t (h2) is consumed
-  // dz1[r][k] = (sum_c dz2[r][c] W2t[k][c]) [h1 > 0]:  thread = (row, 8 k)
+  // dz1[r][k] = (sum_c dz2[r][c] W2t[k][c]) [h1 > 0]:  thread = (row, KPT consecutive k)
   {
-    const int r = tid % R, kg = (tid / R) * 8;
-    float acc[8];
+    constexpr int KPT = HID / (256 / R);
+    const int r = tid % R, kg = (tid / R) * KPT;
+    float acc[KPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < KPT; ++j) acc[j] = 0.f;
+#pragma unroll 4
     for (int c4 = 0; c4 < HID / 4; ++c4) {
       const float z0 = s_dz2[r][4 * c4], z1 = s_dz2[r][4 * c4 + 1], z2 = s_dz2[r][4 * c4 + 2], z3 = s_dz2[r][4 * c4 + 3];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < KPT; ++j) {
         const float4 w = __ldg(reinterpret_cast<const float4*>(W.w2t + (size_t)(kg + j) * HID + 4 * c4));
         acc[j] = fmaf(z0, w.x, acc[j]); acc[j] = fmaf(z1, w.y, acc[j]);
         acc[j] = fmaf(z2, w.z, acc[j]); acc[j] = fmaf(z3, w.w, acc[j]);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s_t[r][kg + j] = s_h1[r][kg + j] > 0.f ? acc[j] : 0.f;
+    for (int j = 0; j < KPT; ++j) s_t[r][kg + j] = s_h1[r][kg + j] > 0.f ? acc[j] : 0.f;
   }
   __syncthreads();
   // b1, dW1t[s][c] += sum_r obs[r][s] dz1[r][c]
@@ -696,7 +699,7 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   CIRS_CHECK_LAUNCH();
   }
   // ---- critic head + trunk: one fused kernel
-  CIRS_LAUNCH(trunk_bwd_kernel, (n + 31) / 32, 256, 0, st, *w, *grads, n, idx, obs, tc ? ws.dh2_part : ws.dh2,
+  CIRS_LAUNCH(trunk_bwd_kernel, (n + 15) / 16, 256, 0, st, *w, *grads, n, idx, obs, tc ? ws.dh2_part : ws.dh2,
               tc ? tc_split : 0, ws.dv, ws.h1, ws.h2, d_obs);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;

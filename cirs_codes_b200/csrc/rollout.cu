@@ -64,31 +64,43 @@ struct RolloutArgs {
   int n_slices;             // ceil(n_action / 80) <= grid
   int tc_keep_off;          // float offset of the launch-lifetime shared-memory region (W3 slice, mbarriers)
   int* tc_timeout;          // set when an mbarrier wait gives up (never expected)
+  int group_ok;             // phase B may use warp groups (scratch slices large enough for the extra buffers)
 };
 
 // SMW: the tracker's weights are staged once in shared memory (they are re-read by every warp at every turn; from L2
 // each token is ~55 dependent round trips of ~0.6 us, from shared memory ~20x less)
 // TC: phase A on the tcgen05 tensor cores (3xTF32), each CTA keeping its slice of W3 in shared memory for the launch
 template <bool SMW, bool TC>
-__global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kernel(RolloutArgs A) {
+__global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kernel(const RolloutArgs A) {
   extern __shared__ __align__(128) float smem_dyn[];
+  // The two structs that change during the launch (tracker weight pointers rebased into shared memory; the head's
+  // per-turn row list / split plan) live ONCE per CTA in shared memory.  Writing to the kernel parameter instead makes
+  // the compiler keep a private copy of the whole argument block in local memory for every thread (1.1 KB x 256),
+  // which cannot stay in the small L1 left beside 226 KB of shared memory: every pointer fetch became an L2 round
+  // trip and dominated the per-environment phase.
+  __shared__ cirs_tracker_weights sT;
+  __shared__ HeadArgs sH;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warps_per_cta = NT / 32;
   const int gwarp = blockIdx.x * warps_per_cta + warp, n_warps = gridDim.x * warps_per_cta;
   const int B = A.n_env;
   float* scratch = smem_dyn + (size_t)warp * A.scratch_per_warp;
+  if (tid == 0) { sT = A.T; sH = A.H; }
+  __syncthreads();
   if (SMW) {
     float* wsm = smem_dyn + A.smem_w_off;
     for (int i = tid; i < A.w_count / 4; i += NT)
       reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(A.w_lo) + i);
-    const ptrdiff_t shift = wsm - A.w_lo;   // rebase every weight pointer into the staged copy
-    A.T.user_wt += shift; A.T.user_b += shift; A.T.gate_wt += shift; A.T.gate_b += shift;
-    A.T.dec_wt += shift; A.T.dec_b += shift;
-    for (int l = 0; l < A.T.nlayers; ++l) {
-      cirs_encoder_layer& Y = A.T.layer[l];
-      Y.in_wt += shift; Y.in_b += shift; Y.out_wt += shift; Y.out_b += shift; Y.l1_wt += shift; Y.l1_b += shift;
-      Y.l2_wt += shift; Y.l2_b += shift; Y.n1_w += shift; Y.n1_b += shift; Y.n2_w += shift; Y.n2_b += shift;
+    if (tid == 0) {
+      const ptrdiff_t shift = wsm - A.w_lo;   // rebase every weight pointer into the staged copy
+      sT.user_wt += shift; sT.user_b += shift; sT.gate_wt += shift; sT.gate_b += shift;
+      sT.dec_wt += shift; sT.dec_b += shift;
+      for (int l = 0; l < sT.nlayers; ++l) {
+        cirs_encoder_layer& Y = sT.layer[l];
+        Y.in_wt += shift; Y.in_b += shift; Y.out_wt += shift; Y.out_b += shift; Y.l1_wt += shift; Y.l1_b += shift;
+        Y.l2_wt += shift; Y.l2_b += shift; Y.n1_w += shift; Y.n1_b += shift; Y.n2_w += shift; Y.n2_b += shift;
+      }
     }
     __syncthreads();
   }
@@ -114,7 +126,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       A.ep_len[e] = 0;
       A.list[e] = e;
     }
-    cirs_tracker::tracker_token_warp<SMW>(A.T, B, e, e, 0, u, nullptr, 0.f, A.kcache, A.vcache, scratch, lane, nullptr, 0,
+    cirs_tracker::tracker_token_warp<SMW>(sT, B, e, e, 0, u, nullptr, 0.f, A.kcache, A.vcache, scratch, lane, nullptr, 0,
                                      A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
     __syncwarp();
     actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, scratch, A.h2 + (size_t)e * HID,
@@ -132,17 +144,23 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
     const bool timer = blockIdx.x == 0 && tid == 0;
     long long t0 = 0, t1 = 0;
     if (timer) t0 = gtime_ns();
-    HeadArgs H = A.H;
-    H.n_rows = n_act;
-    H.gather = A.list + (size_t)(t & 1) * B;
     const int row_tiles = (n_act + BM - 1) / BM;
-    int n_split = gridDim.x / row_tiles;
-    n_split = n_split < 1 ? 1 : (n_split > n_col_tiles ? n_col_tiles : n_split);
-    H.tiles_per_split = (n_col_tiles + n_split - 1) / n_split;
-    H.n_split = (n_col_tiles + H.tiles_per_split - 1) / H.tiles_per_split;
+    if (tid == 0) {   // this turn's head plan (shared by the CTA)
+      sH.n_rows = n_act;
+      sH.gather = A.list + (size_t)(t & 1) * B;
+      if (TC) {
+        sH.n_split = A.n_slices;
+      } else {
+        int n_split = gridDim.x / row_tiles;
+        n_split = n_split < 1 ? 1 : (n_split > n_col_tiles ? n_col_tiles : n_split);
+        sH.tiles_per_split = (n_col_tiles + n_split - 1) / n_split;
+        sH.n_split = (n_col_tiles + sH.tiles_per_split - 1) / sH.tiles_per_split;
+      }
+    }
+    __syncthreads();
+    const HeadArgs& H = sH;
     // ---- phase A: actor head partials over the compact rows
     if (TC) {
-      H.n_split = A.n_slices;
       if ((int)blockIdx.x < A.n_slices) cirs_actor_tc::tc_head_turn(H, blockIdx.x, TS, tid, tst, A.tc_timeout);
     } else {
       const int n_items = row_tiles * H.n_split;
@@ -154,8 +172,13 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
     __threadfence();
     grid.sync();
     if (timer) t1 = gtime_ns();
-    // ---- phase B: one warp per running environment
+    // ---- phase B: per running environment -- merge partials -> action, environment step, tracker token, trunk.
+    // One warp per environment while they outnumber the warps; once few are left, G = 2 / 4 / 8 warps share one
+    // environment's tracker token (tracker_token_group) so the dependent chain per turn gets shorter.
     int32_t* list_next = A.list + (size_t)((t + 1) & 1) * B;
+    int G = 1;
+    if (A.group_ok) G = n_act * 8 <= n_warps ? 8 : (n_act * 4 <= n_warps ? 4 : (n_act * 2 <= n_warps ? 2 : 1));
+    if (G == 1) {
     for (int k = gwarp; k < n_act; k += n_warps) {
       const int e = H.gather[k];
       const bool sub = timer && k == 0;   // sub-phase timers of the first environment of block 0 / warp 0
@@ -172,7 +195,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       __syncwarp();
       if (sub) s2 = gtime_ns();
       const float r = A.rew[e];
-      cirs_tracker::tracker_token_warp<SMW>(A.T, B, e, e, t + 1, a, nullptr, r, A.kcache, A.vcache, scratch, lane, nullptr,
+      cirs_tracker::tracker_token_warp<SMW>(sT, B, e, e, t + 1, a, nullptr, r, A.kcache, A.vcache, scratch, lane, nullptr,
                                        0, A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
       if (!d) {   // trunk + critic of the new state, consumed by the next turn's head phase
         __syncwarp();
@@ -182,6 +205,53 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       if (sub) {
         long long* q = A.dbg + 1 + 3 * 512 + 3 * t;
         q[0] = s1 - s0; q[1] = s2 - s1; q[2] = gtime_ns() - s2;
+      }
+    }
+    } else {
+      const int groups_per_cta = warps_per_cta / G, group = warp / G, wg = warp % G;
+      const int ggroup = blockIdx.x * groups_per_cta + group, n_groups = gridDim.x * groups_per_cta;
+      float* gscr = smem_dyn + (size_t)(group * G) * A.scratch_per_warp;   // the group's first warp's scratch slice
+      float* xtra = gscr + A.scratch_per_warp;                              // ... and the second warp's
+      int* mail = reinterpret_cast<int*>(xtra + 2 * ((A.T.d + 31) & ~31));  // action, done, reward of this turn
+      const int bar_id = 1 + group, nthr = 32 * G;
+      for (int k = ggroup; k < n_act; k += n_groups) {
+        const int e = H.gather[k];
+        const bool sub = timer && k == 0;
+        long long s0 = 0, s2 = 0;
+        if (sub) s0 = gtime_ns();
+        if (wg == 0) {
+          const int a = actor_combine_warp(H, k, lane, A.act, A.logp);
+          const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len,
+                                                      A.traj_act, A.traj_rew, A.traj_done, A.ep_len, A.force_length,
+                                                      A.n_active);
+          __syncwarp();
+          if (lane == 0) {
+            if (!d) {
+              const int kn = atomicAdd(A.count + ((t + 1) & 1), 1);
+              list_next[kn] = e;
+            }
+            mail[0] = a; mail[1] = d ? 1 : 0;
+            reinterpret_cast<float*>(mail)[2] = A.rew[e];
+          }
+        }
+        cirs_tracker::group_sync(bar_id, nthr);
+        const int a = mail[0];
+        const bool d = mail[1] != 0;
+        const float r = reinterpret_cast<const float*>(mail)[2];
+        if (sub) s2 = gtime_ns();
+        cirs_tracker::tracker_token_group<SMW>(sT, B, e, t + 1, a, r, A.kcache, A.vcache, gscr, xtra, lane, wg, G, bar_id,
+                                               A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next,
+                                               sub ? A.dbg + 1 + 6 * 512 - 16 : nullptr);
+        if (wg == 0 && !d) {
+          __syncwarp();
+          actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, gscr, A.h2 + (size_t)e * HID,
+                           A.value + e);
+        }
+        cirs_tracker::group_sync(bar_id, nthr);   // scratch and mail are reused by the group's next environment
+        if (sub) {
+          long long* q = A.dbg + 1 + 3 * 512 + 3 * t;
+          q[0] = A.dbg[1 + 6 * 512 - 16 + 10] - s2; q[1] = s2 - s0; q[2] = gtime_ns() - s2;   // token, combine+env, token+trunk
+        }
       }
     }
     if (blockIdx.x == 0 && tid == 0) {
@@ -329,6 +399,8 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.rew = rew; A.done = done; A.traj_obs = traj_obs; A.traj_obs_next = traj_obs_next; A.traj_act = traj_act;
   A.traj_rew = traj_rew; A.traj_done = traj_done; A.ep_len = ep_len; A.kcache = kcache; A.vcache = vcache;
   A.scratch_per_warp = per_warp;
+  // group mode keeps two extra [d] vectors and a 3-word mailbox in the group's second scratch slice
+  A.group_ok = per_warp >= 2 * ((tw->d + 31) & ~31) + 8 ? 1 : 0;
   void* params[] = {&A};
   const bool prof = cirs_profile_begin("rollout_kuaishou_kernel", (cudaStream_t)stream);
   void* fn = tc ? (smw ? (void*)rollout_kuaishou_kernel<true, true> : (void*)rollout_kuaishou_kernel<false, true>)

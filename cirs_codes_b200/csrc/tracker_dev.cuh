@@ -232,4 +232,207 @@ __device__ __forceinline__ void tracker_token_warp(const cirs_tracker_weights& W
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Group version: G warps (G = 2, 4, 8; all in one CTA) cooperate on ONE token.  A single warp walking the 2-layer
+// transformer step is a ~30 us chain of dependent shared-memory loads and FMAs; with few environments still running
+// most of the SM's warps idle, so the matrix-vector products are split over the group's warps (each warp owns a
+// contiguous range of output quads), heads are split for the attention scores, and cheap element-wise stages are
+// computed redundantly by every warp into write-only buffers (no in-place updates, so no barrier is needed for
+// them).  Warps meet at a named barrier (bar.sync id, 32 G) after every split stage: 12 barriers per token.
+// Scratch: ``x`` = the group's first warp's slice, ``xtra`` = at least 2 * round_up(d, 32) more floats.
+
+__device__ __forceinline__ void group_sync(int bar_id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(n_threads) : "memory");
+}
+
+// this warp's share of y[o] = act(b[o] + sum_i Wt[i][o] x[i]); no trailing synchronisation
+template <bool SM>
+__device__ __forceinline__ void matvec_part(const float* __restrict__ Wt, const float* __restrict__ b, const float* x,
+                                            int n_in, int n_out, int ldo, float* y, int lane, int act, int wg, int G) {
+  const int nq_total = (n_out + 3) >> 2;
+  const int qpw = min(32, (nq_total + G - 1) / G);          // quads per warp (<= 32: n_out <= 128 G)
+  for (int q0 = wg * qpw; q0 < nq_total; q0 += G * qpw) {
+    const int nq = min(qpw, nq_total - q0);
+    const int P = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : nq <= 16 ? 16 : 32;
+    const int Gi = 32 / P, q = lane & (P - 1), g = lane / P;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nq) {
+      const float* w = Wt + 4 * (q0 + q) + (size_t)g * ldo;
+      const int step = Gi * ldo;
+#pragma unroll 8
+      for (int i = g; i < n_in; i += Gi) {
+        const float xi = x[i];
+        const float4 w4 = ldw4<SM>(w);
+        acc.x = fmaf(w4.x, xi, acc.x);
+        acc.y = fmaf(w4.y, xi, acc.y);
+        acc.z = fmaf(w4.z, xi, acc.z);
+        acc.w = fmaf(w4.w, xi, acc.w);
+        w += step;
+      }
+    }
+    for (int off = P; off < 32; off <<= 1) {
+      acc.x += __shfl_xor_sync(FULL_MASK, acc.x, off);
+      acc.y += __shfl_xor_sync(FULL_MASK, acc.y, off);
+      acc.z += __shfl_xor_sync(FULL_MASK, acc.z, off);
+      acc.w += __shfl_xor_sync(FULL_MASK, acc.w, off);
+    }
+    if (g == 0 && q < nq) {
+      const float v4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = 4 * (q0 + q) + j;
+        if (o < n_out) {
+          float v = v4[j] + ldw<SM>(b + o);
+          if (act == 1) v = fmaxf(v, 0.f);
+          else if (act == 2) v = 1.f / (1.f + expf(-v));
+          y[o] = v;
+        }
+      }
+    }
+  }
+}
+
+// out <- LayerNorm(xin + yin) * w + b, all d elements by THIS warp (out is neither xin nor yin)
+template <bool SM>
+__device__ __forceinline__ void add_layernorm_to(float* out, const float* xin, const float* yin,
+                                                 const float* __restrict__ w, const float* __restrict__ b, int d,
+                                                 int lane) {
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s += xin[c] + yin[c];
+  const float mu = warp_sum(s) / d;
+  float q = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = xin[c] + yin[c] - mu;
+    q += v * v;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / d + 1e-5f);
+  for (int c = lane; c < d; c += 32) out[c] = (xin[c] + yin[c] - mu) * rstd * ldw<SM>(w + c) + ldw<SM>(b + c);
+  __syncwarp();
+}
+
+template <bool SM>
+__device__ __forceinline__ void tracker_token_group(const cirs_tracker_weights& W, int n_env, int e, int p, int id,
+                                                    float rew_k, float* __restrict__ kcache,
+                                                    float* __restrict__ vcache, float* x, float* xtra, int lane, int wg,
+                                                    int G, int bar_id, float* __restrict__ cur_state, int traj_len,
+                                                    float* __restrict__ traj_obs, float* __restrict__ traj_obs_next,
+                                                    long long* tq = nullptr) {
+  // tq (optional, one group only): %globaltimer stamps after token / per layer: in-proj, attention, out-proj+LN, FFN+LN / decoder
+  int tqi = 0;
+  auto stamp = [&]() {
+    if (tq && wg == 0 && lane == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); tq[tqi++] = t_; }
+  };
+  stamp();
+  const int d = W.d, nh = W.nhead, dh = d / nh, dhid = W.d_hid;
+  const int ldd = (d + 31) & ~31, ld3 = (3 * d + 31) & ~31, ldh = (dhid + 31) & ~31, lds = (W.dim_state + 31) & ~31;
+  const int nthr = 32 * G;
+  float* y = x + ldd;                                 // token inputs [1 + d]
+  float* qkv = y + max(ldd, ((max(W.d_user_in, W.d_item_in + 1) + 31) & ~31));  // [3d]
+  float* hid = qkv + ld3;                             // [d_hid] (also attention output o[d])
+  float* prob = hid + max(ldh, ldd);                  // [nhead][max_len]
+  float* x2 = xtra;                                   // [d] second activation buffer (ping-pong with x)
+  float* yb = xtra + ldd;                             // [d] output of gate / out_proj / linear2 / decoder
+
+  // ---- token (embedding tables only: the Kuaishou rollout); every warp fills y redundantly (write-only)
+  if (p == 0) {
+    const float* src = W.emb_user + (size_t)id * d;
+    for (int c = lane; c < W.d_user_in; c += 32) y[c] = __ldg(src + c);
+    __syncwarp();
+    matvec_part<SM>(W.user_wt, W.user_b, y, W.d_user_in, d, ldd, yb, lane, 0, wg, G);
+    group_sync(bar_id, nthr);
+    const float sq = sqrtf((float)d);
+    for (int c = lane; c < d; c += 32) x[c] = yb[c] * sq + __ldg(W.pe + c);
+  } else {
+    const float* src = W.emb_item + (size_t)id * d;
+    if (lane == 0) y[0] = rew_k;
+    for (int c = lane; c < W.d_item_in; c += 32) y[1 + c] = __ldg(src + c);
+    __syncwarp();
+    matvec_part<SM>(W.gate_wt, W.gate_b, y, 1 + W.d_item_in, d, ldd, yb, lane, 2, wg, G);
+    group_sync(bar_id, nthr);
+    const float sq = sqrtf((float)d);
+    for (int c = lane; c < d; c += 32) x[c] = (yb[c] * y[1 + c]) * sq + __ldg(W.pe + (size_t)p * d + c);
+  }
+  __syncwarp();
+  stamp();
+
+  const float scale = 1.0f / sqrtf((float)dh);
+  for (int l = 0; l < W.nlayers; ++l) {
+    const cirs_encoder_layer& L = W.layer[l];
+    matvec_part<SM>(L.in_wt, L.in_b, x, d, 3 * d, ld3, qkv, lane, 0, wg, G);
+    group_sync(bar_id, nthr);
+    stamp();
+    float* kc = kcache + ((size_t)l * n_env + e) * W.max_len * d;
+    float* vc = vcache + ((size_t)l * n_env + e) * W.max_len * d;
+    if (wg == G - 1) {   // the last warp (it owns no head when G > nhead) stores this position's K / V
+      for (int c = lane; c < d; c += 32) {
+        kc[(size_t)p * d + c] = qkv[d + c];
+        vc[(size_t)p * d + c] = qkv[2 * d + c];
+      }
+    }
+    // scores + softmax of head h by warp h % G: lane j (chunks of 32) owns cached position j
+    for (int h = wg; h < nh; h += G) {
+      const float* q = qkv + h * dh;
+      float* ph = prob + h * W.max_len;
+      for (int j0 = 0; j0 <= p; j0 += 32) {
+        const int j = j0 + lane;
+        if (j <= p) {
+          const float* kr = (j == p) ? (qkv + d) : (kc + (size_t)j * d);
+          float a = 0.f;
+#pragma unroll 4
+          for (int c = 0; c < dh; ++c) a = fmaf(q[c] * scale, kr[h * dh + c], a);
+          ph[j] = a;
+        }
+      }
+      __syncwarp();
+      float mx = -INFINITY;
+      for (int j = lane; j <= p; j += 32) mx = fmaxf(mx, ph[j]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j <= p; j += 32) {
+        const float ex = expf(ph[j] - mx);
+        ph[j] = ex;
+        sum += ex;
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      for (int j = lane; j <= p; j += 32) ph[j] *= inv;
+    }
+    group_sync(bar_id, nthr);
+    // o[c] = sum_j prob[head(c)][j] V[j][c]: every warp computes all of o (write-only ``hid``)
+    for (int c = lane; c < d; c += 32) {
+      const float* pr = prob + (c / dh) * W.max_len;
+      float a = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < p; ++j) a = fmaf(pr[j], vc[(size_t)j * d + c], a);
+      a = fmaf(pr[p], qkv[2 * d + c], a);
+      hid[c] = a;
+    }
+    __syncwarp();
+    stamp();
+    matvec_part<SM>(L.out_wt, L.out_b, hid, d, d, ldd, yb, lane, 0, wg, G);
+    group_sync(bar_id, nthr);
+    add_layernorm_to<SM>(x2, x, yb, L.n1_w, L.n1_b, d, lane);
+    stamp();
+    matvec_part<SM>(L.l1_wt, L.l1_b, x2, d, dhid, ldh, hid, lane, 1, wg, G);
+    group_sync(bar_id, nthr);
+    matvec_part<SM>(L.l2_wt, L.l2_b, hid, dhid, d, ldd, yb, lane, 0, wg, G);
+    group_sync(bar_id, nthr);
+    add_layernorm_to<SM>(x, x2, yb, L.n2_w, L.n2_b, d, lane);
+    stamp();
+  }
+  // decoder -> state
+  matvec_part<SM>(W.dec_wt, W.dec_b, x, d, W.dim_state, lds, yb, lane, 0, wg, G);
+  group_sync(bar_id, nthr);
+  stamp();
+  if (wg == 0) {
+    const int S = W.dim_state;
+    for (int c = lane; c < S; c += 32) {
+      const float v = yb[c];
+      if (cur_state) cur_state[(size_t)e * S + c] = v;
+      if (traj_obs && p < traj_len) traj_obs[((size_t)e * traj_len + p) * S + c] = v;
+      if (traj_obs_next && p >= 1 && p - 1 < traj_len) traj_obs_next[((size_t)e * traj_len + p - 1) * S + c] = v;
+    }
+  }
+}
+
 }  // namespace cirs_tracker

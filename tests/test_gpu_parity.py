@@ -383,8 +383,10 @@ def test_fused_collect_matches_generic(H):
         assert np.array_equal(a["lens"], b["lens"]) and np.array_equal(a["act"], b["act"])
         assert np.array_equal(a["done"], b["done"])
         G.assert_close(a["rew"], b["rew"], 1e-6, what="rew")
-        G.assert_close(a["obs"], b["obs"], 1e-6, 1e-7, what="obs")
-        G.assert_close(a["obs_next"], b["obs_next"], 1e-6, 1e-7, what="obs_next")
+        # states: FP32 rounding level -- the persistent kernel splits the tracker's matrix-vector products over warp
+        # groups once few environments are left, which changes the summation order
+        G.assert_close(a["obs"], b["obs"], 1e-6, 1e-6, what="obs")
+        G.assert_close(a["obs_next"], b["obs_next"], 1e-6, 1e-6, what="obs_next")
         assert a["res"]["n/st"] == b["res"]["n/st"] and np.array_equal(a["res"]["lens"], b["res"]["lens"])
         G.assert_close(a["res"]["rews"], b["res"]["rews"], 1e-6, what="episode rewards")
         assert a["lens"].min() >= 1 and a["lens"].max() <= c["T"]
