@@ -271,6 +271,7 @@ def gpu_arm(args, cfg):
     per_step_res = list(timed.per_step)
     launches = lib.cirs_launch_count() - l0
     ms_e2e, steps_e2e, h2d, d2h, _ = timed(args.steps, False)
+    per_step_e2e = list(timed.per_step)
     clk = clocks.stop()
 
     # ---- per-kernel durations, live, CUDA events on the launching stream (separate pass: events perturb the step)
@@ -325,9 +326,15 @@ def gpu_arm(args, cfg):
                 kern[name].update(bound=bound, achieved=round(ach, 3), peak=peak, frac=round(ach / peak, 5),
                                   unit="GB/s" if bound == "hbm" else "TFLOP/s")
         top = next((k for k in kern if "bound" in kern[k]), None)
+        traffic = {}
+        try:   # DRAM bytes per launch from this round's ncu --set full captures (profiles/), same workload
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        except Exception:
+            pass
         if top:
             roof = {"kernel": top, "bound": kern[top]["bound"], "achieved": kern[top]["achieved"],
-                    "peak": kern[top]["peak"], "unit": kern[top]["unit"], "frac": kern[top]["frac"], "traffic": None,
+                    "peak": kern[top]["peak"], "unit": kern[top]["unit"], "frac": kern[top]["frac"],
+                    "traffic": traffic.get(top) if cfg["name"].startswith("configs[1]") else None,
                     "peak_source": which, "share_of_step": kern[top]["share"],
                     "note": "FP32-accurate contraction (3xTF32 tcgen05 MMAs, or FFMA) measured against the dense bf16 tensor "
                             "peak; the 3xTF32 scheme's own ceiling is peak/6" if kern[top]["bound"] == "tensor"
@@ -346,7 +353,8 @@ def gpu_arm(args, cfg):
                        "parallelism": f"env-sharded dp{world}", "l2": "192 MB flush between timed iterations",
                        "timing": "CUDA events per step, max over ranks", "ms_each_step_rank0": per_step_res},
             "e2e": {"value": steps_e2e / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+                    "ms_each_step_rank0": per_step_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
         }
     if dist is not None:

@@ -254,6 +254,26 @@ class PPOPolicy:
         return torch.from_numpy(bits.view(np.int32)).to(self.device)
 
     # ------------------------------------------------------------------ update
+    def _h2d_i32(self, arr):
+        """Host int array -> device int32 tensor through a small ring of pinned staging buffers (asynchronous copy on
+        the current stream; a buffer is reused only after the copy that read it has completed)."""
+        n = int(len(arr))
+        ring = getattr(self, "_pin_ring", None)
+        if ring is None or ring[0][0].numel() < n:
+            cap = max(n, 2 * (ring[0][0].numel() if ring else 0), 4096)
+            ring = [[torch.empty(cap, dtype=torch.int32).pin_memory(), None] for _ in range(4)]
+            self._pin_ring, self._pin_next = ring, 0
+        slot = self._pin_ring[self._pin_next]
+        self._pin_next = (self._pin_next + 1) % len(self._pin_ring)
+        if slot[1] is not None:
+            slot[1].synchronize()
+        slot[0][:n].numpy()[:] = arr
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        out.copy_(slot[0][:n], non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return out
+
     def _ppo_ws(self, n):
         if n > self._ws_ppo_rows:
             need = _lib.load().cirs_ppo_workspace_bytes(n, self.n_action)
@@ -314,7 +334,7 @@ class PPOPolicy:
         self.updating = True
         buffer.sync_device()
         idx_h = buffer.sample_index(0)
-        indices = torch.as_tensor(idx_h.astype(np.int32), device=self.device)
+        indices = self._h2d_i32(idx_h)
         self.h2d_bytes, self.d2h_bytes = indices.numel() * 4, 0
         self.process_fn(buffer, indices)
         result = self.learn(buffer, idx_h, indices, batch_size or len(idx_h), repeat, perms=perms)
@@ -337,11 +357,11 @@ class PPOPolicy:
         def slots_for(step):
             if perms is not None:
                 self.h2d_bytes += 4 * n
-                return torch.as_tensor(idx_h[np.asarray(perms[step])].astype(np.int32), device=dev)
+                return self._h2d_i32(idx_h[np.asarray(perms[step])])
             if self.perm_on_device:
                 return indices[torch.randperm(n, device=dev)]
             self.h2d_bytes += 4 * n
-            return torch.as_tensor(idx_h[np.random.permutation(n)].astype(np.int32), device=dev)   # batch.py:736
+            return self._h2d_i32(idx_h[np.random.permutation(n)])   # batch.py:736
 
         # a chunk of Batch.split(merge_last) never exceeds 2 * batch_size - 1 rows: size the workspace once
         ws = self._ppo_ws(max(int(max(sizes)), min(buffer.maxsize, 2 * int(batch_size) - 1)))

@@ -473,3 +473,24 @@ def test_trainer_end_to_end_and_checkpoint(H, tmp_path):
     trk2 = H.make_tracker(None, c)
     trk2.load_state_dict(sd)
     assert torch.equal(trk2.flat, trk.flat)
+
+
+def test_fused_collect_wide_catalogue_falls_back_to_ffma_head(H):
+    """A catalogue wider than one 80-column slice per SM (148 x 80 = 11840 items) cannot use the tensor-core head
+    phase of the persistent kernel; the launcher must fall back to the FFMA head phase and still match the generic loop."""
+    import cirs_codes_b200 as cb
+    z, c = H.synthetic_case(U=32, I=12100, B=8, T=5, N=2, thr=1, d=32)
+    users = np.random.default_rng(5).integers(0, c["U"], size=c["B"])
+    outs = []
+    for fused in (True, False):
+        env, trk = H.make_env(z, c), H.make_tracker(None, c)
+        pol = H.make_policy(None, c, None, deterministic_eval=True)
+        pol.eval()
+        buf = cb.VectorReplayBuffer(c["B"] * c["T"], c["B"])
+        col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state, fused=fused)
+        res = col.collect(n_episode=c["B"], users=users)
+        idx = buf.sample_index(0)
+        outs.append((buf._lengths.copy(), buf.act[idx].copy(), buf.rew[idx].copy(), res["n/st"]))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    G.assert_close(outs[0][2], outs[1][2], 1e-6, what="rew")
+    assert outs[0][3] == outs[1][3]
