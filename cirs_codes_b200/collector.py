@@ -264,14 +264,26 @@ class Collector:
             self._graph.replay()                                     # the whole rollout: ONE graph launch
         else:
             self._rollout_body(max_steps, poll=True)
-        lens = buf.d_len.cpu().numpy().astype(np.int64)             # the collect's D2H read (also a sync)
-        rews = env.cum_rew.cpu().numpy()
+        lens, rews = self._read_back(buf.d_len, env.cum_rew)        # the collect's D2H read (one synchronisation)
         self.d2h_bytes += 4 * B + 8 * B
         buf.set_from_device(lens)
         order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
         res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])
         res["turns"] = int(lens.max()) if len(lens) else 0
         return res
+
+    def _read_back(self, d_len, d_rew):
+        """Episode lengths (i32) and cumulative rewards (f64) -> pinned host buffers, two asynchronous copies and ONE
+        stream synchronisation."""
+        B = self.env_num
+        if not hasattr(self, "_pin_out"):
+            self._pin_out = (torch.zeros(B, dtype=torch.int32).pin_memory(),
+                             torch.zeros(B, dtype=torch.float64).pin_memory())
+        p_len, p_rew = self._pin_out
+        p_len.copy_(d_len[:B], non_blocking=True)
+        p_rew.copy_(d_rew[:B], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return p_len.numpy().astype(np.int64), p_rew.numpy().copy()
 
     # ---- fused path, VirtualTaobao: the whole collect is ONE kernel, one warp per environment (csrc/rollout_taobao.cu)
     def _collect_fused_taobao(self, users):
@@ -303,8 +315,7 @@ class Collector:
                   _lib.ptr(buf.obs_next), _lib.ptr(buf.d_act), _lib.ptr(buf.d_act_env), _lib.ptr(buf.d_rew),
                   _lib.ptr(buf.d_done), _lib.ptr(buf.d_len), _lib.ptr(trk.kcache), _lib.ptr(trk.vcache), pol.seed,
                   _lib.ptr(f["rng"]), mode, max_steps, self.force_length, _lib.stream())
-        lens = buf.d_len.cpu().numpy().astype(np.int64)
-        rews = env.cum_rew.cpu().numpy()
+        lens, rews = self._read_back(buf.d_len, env.cum_rew)
         self.d2h_bytes += 4 * B + 8 * B
         buf.set_from_device(lens)
         order = np.lexsort((np.arange(B), lens))

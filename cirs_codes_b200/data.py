@@ -230,15 +230,16 @@ class VectorReplayBuffer:
     def sample_index(self, batch_size):
         """manager.py:144-169 with batch_size == 0: every stored transition, env-major, oldest first."""
         assert batch_size == 0, "only sample(0) (all data, on-policy) is on the hot path"
-        out = []
-        for i in range(self.buffer_num):
-            n, idx = self._lengths[i], self._index[i]
-            if n == self.sub_size and idx != 0:                             # wrapped ring: base.py:267-275
-                loc = np.concatenate([np.arange(idx, self.sub_size), np.arange(idx)])
-            else:
-                loc = np.arange(n)
-            out.append(loc + self._offset[i])
-        return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+        lens = self._lengths
+        wrapped = (lens == self.sub_size) & (self._index != 0)              # wrapped ring: base.py:267-275
+        n = int(lens.sum())
+        if n == 0:
+            return np.zeros(0, dtype=np.int64)
+        start = np.cumsum(lens) - lens                                      # first flat position of every sub-buffer
+        loc = np.arange(n) - np.repeat(start, lens)                         # 0 .. len-1 inside each sub-buffer
+        if wrapped.any():                                                   # oldest first: start reading at the write index
+            loc = (loc + np.repeat(np.where(wrapped, self._index, 0), lens)) % self.sub_size
+        return loc + np.repeat(self._offset, lens)
 
     def sample(self, batch_size):
         idx = self.sample_index(batch_size)

@@ -351,7 +351,7 @@ class PPOPolicy:
         sizes = sharded_sizes(n, batch_size, dist if world > 1 else None, self.group, dev)
         offs = np.zeros(len(sizes) + 1, dtype=np.int32)
         offs[1:] = np.cumsum(sizes)
-        d_offs = torch.as_tensor(offs, device=dev)
+        d_offs = self._h2d_i32(offs)                 # pinned, asynchronous: no host sync in front of the learn loop
         n_mb = len(sizes)
 
         def slots_for(step):

@@ -185,11 +185,12 @@ class StateTrackerTransformer:
         env_off = None
         n_tok = 0
         if compact:
-            lens = buffer._lengths
-            off = np.zeros(B + 1, dtype=np.int32)
-            off[1:] = np.cumsum(lens)
-            n_tok = int(off[-1])
-            env_off = torch.as_tensor(off, device=self.device)
+            n_tok = int(buffer._lengths.sum())
+            # first compact row of every environment, computed on the device from the lengths the rollout wrote (no
+            # host -> device copy, hence no synchronisation in front of the training pass)
+            buffer.sync_device()
+            env_off = torch.zeros(B + 1, dtype=torch.int32, device=self.device)
+            env_off[1:] = torch.cumsum(buffer.d_len[:B], 0)
             if tok_slot is None:
                 tok_slot = torch.as_tensor(buffer.sample_index(0).astype(np.int32), device=self.device)
         else:
