@@ -4,8 +4,8 @@ replicated.  The reference has no multi-GPU path; this is the new 
 Rollout needs no communication.  During the update every GLOBAL minibatch j is the union over ranks of the ranks'
 local chunk j, so all ranks must agree on the number of minibatches even though they hold different numbers of
 transitions (episode lengths differ).  Collectives per update:
-  * 1 x all-reduce(MAX) of the local minibatch count                       (here)
-  * 1 x all-reduce(SUM) of the return moments                              (policy.process_fn)
+  * 1 x all-reduce(SUM) of the return moments + every rank's transition count (policy.process_fn); the minibatch
+    plan follows from the counts without further communication (plan_from_counts)
   * per repeat 1 x all-reduce(SUM) of the advantage moments of all minibatches   (policy.learn)
   * per minibatch ONE all-reduce(SUM) of the flat actor/critic gradient    (policy.learn; NCCL over NVLink)
   * 1 x all-reduce(SUM) of the tracker's flat gradient, 1 x of the losses  (policy.learn)
@@ -43,6 +43,20 @@ def sharded_sizes(n_local, batch_size, dist=None, group=None, device="cpu"):
     t = torch.tensor([len(local)], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return even_sizes(n_local, int(t.item()))
+
+
+def plan_from_counts(n_all, rank, batch_size):
+    """Minibatch plan of one update when every rank knows every rank's transition count (``n_all``, gathered once
+    per update together with the return moments): the number of global minibatches is the max over ranks of the
+    reference's own split count, every rank cuts its transitions into that many near-equal chunks, and the size of
+    global minibatch j is the sum of the ranks' j-th chunks -- all without further communication or host syncs.
+    Returns (local chunk sizes of ``rank``, global minibatch sizes)."""
+    n_all = [int(x) for x in n_all]
+    n_mb = max(len(split_sizes(n, batch_size)) for n in n_all)
+    n_mb = max(n_mb, 1)
+    per_rank = [even_sizes(n, n_mb) for n in n_all]
+    n_glob = [sum(pr[j] for pr in per_rank) for j in range(n_mb)]
+    return per_rank[rank], n_glob
 
 
 def init_from_env(backend="nccl"):

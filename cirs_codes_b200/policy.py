@@ -321,8 +321,21 @@ class PPOPolicy:
                   _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_done), self._gamma, self._lambda,
                   _lib.ptr(self.ret_rms.t) if self._rew_norm else None, _lib.ptr(self._gae_scratch),
                   _lib.ptr(self._moments) if self._rew_norm else None, _lib.ptr(self.returns), _lib.ptr(self.adv), st)
+        dist, world = self._world()
+        self._n_all = None
+        if world > 1:
+            # ONE collective: the raw return moments and, in slot 3 + rank, this rank's transition count; the counts
+            # give every rank the whole minibatch plan of this update (parallel.plan_from_counts)
+            rank = dist.get_rank(self.group)
+            m = torch.zeros(3 + world, dtype=torch.float64, device=dev)
+            if self._rew_norm:
+                m[:3] = self._moments
+            m[3 + rank] = float(n)
+            self._allreduce(m)
+            if self._rew_norm:
+                self._moments.copy_(m[:3])
+            self._n_all = m[3:].round().to(torch.int64).cpu().numpy()
         if self._rew_norm:
-            self._allreduce(self._moments)
             _lib.call("cirs_rms_update", _lib.ptr(self.ret_rms.t), _lib.ptr(self._moments), st)
 
     def update(self, sample_size, buffer, batch_size=None, repeat=1, perms=None, **kwargs):
@@ -347,8 +360,12 @@ class PPOPolicy:
         dist, world = self._world()
         tracker = self.state_tracker if self.cfg_tracker is not None else None
         losses_all = []
-        from .parallel import sharded_sizes
-        sizes = sharded_sizes(n, batch_size, dist if world > 1 else None, self.group, dev)
+        from .parallel import plan_from_counts, sharded_sizes
+        n_glob_plan = None
+        if world > 1 and getattr(self, "_n_all", None) is not None:
+            sizes, n_glob_plan = plan_from_counts(self._n_all, dist.get_rank(self.group), batch_size)
+        else:
+            sizes = sharded_sizes(n, batch_size, dist if world > 1 else None, self.group, dev)
         offs = np.zeros(len(sizes) + 1, dtype=np.int32)
         offs[1:] = np.cumsum(sizes)
         d_offs = self._h2d_i32(offs)                 # pinned, asynchronous: no host sync in front of the learn loop
@@ -379,13 +396,17 @@ class PPOPolicy:
                       _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), _lib.ptr(ws), st)
             losses_all.append(losses)
         else:
+            # advantage moments of every minibatch of every repeat (they depend on the permutations only): ONE collective
+            slots_all = [slots_for(step) for step in range(repeat)]
+            stats_all = torch.zeros(repeat, n_mb, 3, dtype=torch.float64, device=dev)
             for step in range(repeat):
-                d_slots = slots_for(step)
-                stats = torch.zeros(n_mb, 3, dtype=torch.float64, device=dev)
-                _lib.call("cirs_adv_stats", n_mb, _lib.ptr(d_offs), _lib.ptr(d_slots), _lib.ptr(self.adv),
-                          _lib.ptr(stats), st)
-                self._allreduce(stats)
-                n_glob = stats[:, 0].round().to(torch.int64).cpu().numpy()
+                _lib.call("cirs_adv_stats", n_mb, _lib.ptr(d_offs), _lib.ptr(slots_all[step]), _lib.ptr(self.adv),
+                          stats_all.data_ptr() + 24 * n_mb * step, st)
+            self._allreduce(stats_all)
+            for step in range(repeat):
+                d_slots, stats = slots_all[step], stats_all[step]
+                n_glob = n_glob_plan if n_glob_plan is not None else \
+                    stats[:, 0].round().to(torch.int64).cpu().numpy()
                 losses = torch.zeros(n_mb, 4, dtype=torch.float32, device=dev)
                 if tracker is not None:
                     self.d_obs.zero_()                                               # optim_state.zero_grad(), :174

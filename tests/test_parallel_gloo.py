@@ -26,6 +26,12 @@ def _worker(rank, world, port, n_per_rank, batch_size, q):
     assert (r, w) == (rank, world)
     n = n_per_rank[rank]
     sizes = parallel.sharded_sizes(n, batch_size, dist, None, "cpu")
+    # the same plan from the gathered counts (what policy.process_fn / learn use): no MAX all-reduce, no host sync
+    cnt = torch.zeros(world, dtype=torch.float64)
+    cnt[rank] = n
+    dist.all_reduce(cnt)
+    sizes2, n_glob = parallel.plan_from_counts(cnt.numpy(), rank, batch_size)
+    assert sizes2 == sizes and sum(n_glob) == sum(n_per_rank) and len(n_glob) == len(sizes)
     rng = np.random.default_rng(100 + rank)
     adv = rng.normal(1.0, 2.0, size=n)
     perm = rng.permutation(n)
