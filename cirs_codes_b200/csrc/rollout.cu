@@ -64,7 +64,7 @@ struct RolloutArgs {
   int n_slices;             // ceil(n_action / 80) <= grid
   int tc_keep_off;          // float offset of the launch-lifetime shared-memory region (W3 slice, mbarriers)
   int* tc_timeout;          // set when an mbarrier wait gives up (never expected)
-  int group_ok;             // phase B may use warp groups (scratch slices large enough for the extra buffers)
+  int xtra_off;             // float offset, inside a warp's scratch slice, of the group token's extra buffers
 };
 
 // SMW: the tracker's weights are staged once in shared memory (they are re-read by every warp at every turn; from L2
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       A.ep_len[e] = 0;
       A.list[e] = e;
     }
-    cirs_tracker::tracker_token_warp<SMW>(sT, B, e, e, 0, u, nullptr, 0.f, A.kcache, A.vcache, scratch, lane, nullptr, 0,
-                                     A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
+    cirs_tracker::tracker_token_group<SMW>(sT, B, e, 0, u, 0.f, A.kcache, A.vcache, scratch, scratch + A.xtra_off, lane, 0, 1,
+                                           1 + warp, A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
     __syncwarp();
     actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, scratch, A.h2 + (size_t)e * HID,
                      A.value + e);
@@ -176,42 +176,12 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
     // One warp per environment while they outnumber the warps; once few are left, G = 2 / 4 / 8 warps share one
     // environment's tracker token (tracker_token_group) so the dependent chain per turn gets shorter.
     int32_t* list_next = A.list + (size_t)((t + 1) & 1) * B;
-    int G = 1;
-    if (A.group_ok) G = n_act * 8 <= n_warps ? 8 : (n_act * 4 <= n_warps ? 4 : (n_act * 2 <= n_warps ? 2 : 1));
-    if (G == 1) {
-    for (int k = gwarp; k < n_act; k += n_warps) {
-      const int e = H.gather[k];
-      const bool sub = timer && k == 0;   // sub-phase timers of the first environment of block 0 / warp 0
-      long long s0 = 0, s1 = 0, s2 = 0;
-      if (sub) s0 = gtime_ns();
-      const int a = actor_combine_warp(H, k, lane, A.act, A.logp);
-      if (sub) s1 = gtime_ns();
-      const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len, A.traj_act,
-                                                  A.traj_rew, A.traj_done, A.ep_len, A.force_length, A.n_active);
-      if (lane == 0 && !d) {
-        const int kn = atomicAdd(A.count + ((t + 1) & 1), 1);
-        list_next[kn] = e;
-      }
-      __syncwarp();
-      if (sub) s2 = gtime_ns();
-      const float r = A.rew[e];
-      cirs_tracker::tracker_token_warp<SMW>(sT, B, e, e, t + 1, a, nullptr, r, A.kcache, A.vcache, scratch, lane, nullptr,
-                                       0, A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
-      if (!d) {   // trunk + critic of the new state, consumed by the next turn's head phase
-        __syncwarp();
-        actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, scratch, A.h2 + (size_t)e * HID,
-                         A.value + e);
-      }
-      if (sub) {
-        long long* q = A.dbg + 1 + 3 * 512 + 3 * t;
-        q[0] = s1 - s0; q[1] = s2 - s1; q[2] = gtime_ns() - s2;
-      }
-    }
-    } else {
+    const int G = n_act * 8 <= n_warps ? 8 : (n_act * 4 <= n_warps ? 4 : (n_act * 2 <= n_warps ? 2 : 1));
+    {
       const int groups_per_cta = warps_per_cta / G, group = warp / G, wg = warp % G;
       const int ggroup = blockIdx.x * groups_per_cta + group, n_groups = gridDim.x * groups_per_cta;
       float* gscr = smem_dyn + (size_t)(group * G) * A.scratch_per_warp;   // the group's first warp's scratch slice
-      float* xtra = gscr + A.scratch_per_warp;                              // ... and the second warp's
+      float* xtra = gscr + A.xtra_off;                                      // two extra [d] vectors + mailbox
       int* mail = reinterpret_cast<int*>(xtra + 2 * ((A.T.d + 31) & ~31));  // action, done, reward of this turn
       const int bar_id = 1 + group, nthr = 32 * G;
       for (int k = ggroup; k < n_act; k += n_groups) {
@@ -242,7 +212,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
         cirs_tracker::tracker_token_group<SMW>(sT, B, e, t + 1, a, r, A.kcache, A.vcache, gscr, xtra, lane, wg, G, bar_id,
                                                A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next,
                                                sub ? A.dbg + 1 + 6 * 512 - 16 : nullptr);
-        if (wg == 0 && !d) {
+        if (wg == 0 && !d) {   // trunk + critic of the new state, consumed by the next turn's head phase
           __syncwarp();
           actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, gscr, A.h2 + (size_t)e * HID,
                            A.value + e);
@@ -301,7 +271,9 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     return CIRS_ERR_ARG;
   }
   if (env->n_env <= 0) return CIRS_OK;
-  const int per_warp = cirs_tracker::tracker_scratch_floats(*tw);
+  // per-warp scratch: the token step's buffers + two extra [d] vectors and a small mailbox (tracker_token_group)
+  const int xtra_off = cirs_tracker::tracker_scratch_floats(*tw);
+  const int per_warp = xtra_off + 2 * ((tw->d + 31) & ~31) + 32;
   const size_t scratch_bytes = (size_t)per_warp * (NT / 32) * sizeof(float);
   constexpr size_t SMEM_MAX = 224 * 1024;
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
@@ -399,8 +371,7 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.rew = rew; A.done = done; A.traj_obs = traj_obs; A.traj_obs_next = traj_obs_next; A.traj_act = traj_act;
   A.traj_rew = traj_rew; A.traj_done = traj_done; A.ep_len = ep_len; A.kcache = kcache; A.vcache = vcache;
   A.scratch_per_warp = per_warp;
-  // group mode keeps two extra [d] vectors and a 3-word mailbox in the group's second scratch slice
-  A.group_ok = per_warp >= 2 * ((tw->d + 31) & ~31) + 8 ? 1 : 0;
+  A.xtra_off = xtra_off;
   void* params[] = {&A};
   const bool prof = cirs_profile_begin("rollout_kuaishou_kernel", (cudaStream_t)stream);
   void* fn = tc ? (smw ? (void*)rollout_kuaishou_kernel<true, true> : (void*)rollout_kuaishou_kernel<false, true>)
