@@ -90,8 +90,8 @@ extern "C" int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, co
     return CIRS_ERR_ARG;
   }
   if (n_rows == 0) return CIRS_OK;
-  if (act && w->sigma == nullptr && w->dim_state <= 32 &&
-      cirs_head_tc::head_tc_enabled(n_rows, w->n_action, w->ld_action))
+  // tensor-core path; a value-only evaluation (act == NULL: V(obs_next)) is just the trunk kernel + scatter
+  if (w->sigma == nullptr && w->dim_state <= 32 && cirs_head_tc::head_tc_enabled(n_rows, w->n_action, w->ld_action))
     return cirs_head_tc::policy_eval_tc(w, n_rows, row_idx, obs, act, value, logp, workspace, (cudaStream_t)stream);
   HeadArgs P{};
   P.W = *w; P.n_rows = n_rows; P.gather = row_idx; P.state_by_k = 0; P.out_by_k = 0; P.active = nullptr;

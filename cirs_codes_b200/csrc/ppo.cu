@@ -50,7 +50,13 @@ trunk_fwd_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, 
   constexpr int R = 32;
   __shared__ float s_in[R][33];
   __shared__ float hT[HID][R + 1];
+  __shared__ __align__(16) float s_w1[32 * HID];    // W1t [dim_state <= 32][64]
+  __shared__ __align__(16) float s_w2[HID * HID];   // W2t [64][64]
   const int tid = threadIdx.x, r0 = blockIdx.x * R, S = W.dim_state;
+  // stage the trunk's weights once per CTA: every load of a thread is in flight at the same time (one L2 round trip)
+  // instead of a dependent L1-miss per k-step of the loops below
+  for (int i = tid; i < S * HID / 4; i += 256) reinterpret_cast<float4*>(s_w1)[i] = __ldg(reinterpret_cast<const float4*>(W.w1t) + i);
+  for (int i = tid; i < HID * HID / 4; i += 256) reinterpret_cast<float4*>(s_w2)[i] = __ldg(reinterpret_cast<const float4*>(W.w2t) + i);
   for (int i = tid; i < R * S; i += 256) {
     const int r = i / S, c = i % S;
     s_in[r][c] = (r0 + r < n) ? obs[(int64_t)(idx ? idx[r0 + r] : r0 + r) * S + c] : 0.f;
@@ -64,8 +70,8 @@ trunk_fwd_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, 
 #pragma unroll 4
   for (int k = 0; k < S; ++k) {
     const float x = s_in[row][k];
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W.w1t + (size_t)k * HID + og * 8));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W.w1t + (size_t)k * HID + og * 8 + 4));
+    const float4 w0 = *reinterpret_cast<const float4*>(s_w1 + k * HID + og * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(s_w1 + k * HID + og * 8 + 4);
     acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
     acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
   }
@@ -85,8 +91,8 @@ trunk_fwd_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, 
 #pragma unroll 8
   for (int k = 0; k < HID; ++k) {
     const float x = hT[k][row];
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W.w2t + (size_t)k * HID + og * 8));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W.w2t + (size_t)k * HID + og * 8 + 4));
+    const float4 w0 = *reinterpret_cast<const float4*>(s_w2 + k * HID + og * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(s_w2 + k * HID + og * 8 + 4);
     acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
     acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
   }
@@ -121,8 +127,12 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
   constexpr int R = 16, LD = HID + 1;   // 16 rows per CTA: ~100 CTAs per 1.6k-row minibatch, every phase is short
   __shared__ float s_dz2[R][LD], s_h1[R][LD], s_t[R][LD];   // s_t: h2, later dz1
   __shared__ float s_obs[R][33], s_dv[R];
+  __shared__ float s_w1c[HID * 33];                 // W1t transposed: [64][dim_state (+ pad)], conflict-free for d obs
+  __shared__ __align__(16) float s_w2[HID * HID];   // W2t [64][64]
   static_assert(256 % R == 0 && HID % (256 / R) == 0, "row tile");
   const int tid = threadIdx.x, r0 = blockIdx.x * R, S = W.dim_state;
+  for (int i = tid; i < S * HID; i += 256) s_w1c[(i % HID) * 33 + i / HID] = __ldg(W.w1t + i);
+  for (int i = tid; i < HID * HID / 4; i += 256) reinterpret_cast<float4*>(s_w2)[i] = __ldg(reinterpret_cast<const float4*>(W.w2t) + i);
   {
     // each thread owns 8 (row, column) elements; the split partials of all 8 are loaded together so that their
     // latencies overlap (the partials are [n_split, n, 64])
@@ -216,7 +226,7 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
       const float z0 = s_dz2[r][4 * c4], z1 = s_dz2[r][4 * c4 + 1], z2 = s_dz2[r][4 * c4 + 2], z3 = s_dz2[r][4 * c4 + 3];
 #pragma unroll
       for (int j = 0; j < KPT; ++j) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(W.w2t + (size_t)(kg + j) * HID + 4 * c4));
+        const float4 w = *reinterpret_cast<const float4*>(s_w2 + (kg + j) * HID + 4 * c4);
         acc[j] = fmaf(z0, w.x, acc[j]); acc[j] = fmaf(z1, w.y, acc[j]);
         acc[j] = fmaf(z2, w.z, acc[j]); acc[j] = fmaf(z3, w.w, acc[j]);
       }
@@ -245,7 +255,7 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
       if (r0 + r >= n) continue;
       float a = 0.f;
 #pragma unroll 8
-      for (int c = 0; c < HID; ++c) a = fmaf(s_t[r][c], __ldg(W.w1t + (size_t)sI * HID + c), a);
+      for (int c = 0; c < HID; ++c) a = fmaf(s_t[r][c], s_w1c[c * 33 + sI], a);
       d_obs[(int64_t)idx[r0 + r] * S + sI] = a;
     }
   }
@@ -575,11 +585,15 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
   float *pm = take((int64_t)n * MAX_SPLIT), *ps = take((int64_t)n * MAX_SPLIT), *la = take(n);
   CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, row_idx, obs, h1, h2, vtmp);
   CIRS_CHECK_LAUNCH();
-  const int n_split = plan_split(n, w->n_action);
-  HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action};
-  const int rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
-  if (rc) return rc;
-  CIRS_LAUNCH(eval_merge_kernel, (n + 255) / 256, 256, 0, st, n, n_split, row_idx, pm, ps, la, vtmp, value, logp);
+  int n_split = 0;
+  if (act) {   // log-probs of the stored actions; a value-only evaluation needs the trunk alone
+    n_split = plan_split(n, w->n_action);
+    HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action};
+    const int rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
+    if (rc) return rc;
+  }
+  CIRS_LAUNCH(eval_merge_kernel, (n + 255) / 256, 256, 0, st, n, n_split, row_idx, pm, ps, la, vtmp, value,
+              act ? logp : nullptr);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }

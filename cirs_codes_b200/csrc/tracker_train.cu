@@ -368,20 +368,20 @@ int splitk(int tiles, int K) {
 // Y[M,N] = X[M,K] Wt[K][ldw] + b (+ relu) (+ res)
 void linear_fwd(const float* X, int ldx, const float* Wt, int ldw, const float* b, float* Y, int ldy, int M, int N,
                 int K, int relu, const float* res, int ldr, cudaStream_t st) {
-  launch_gemm<64, 64, 16, 4>(RowMajorA{X, ldx, nullptr}, RowMajorB{Wt, ldw, nullptr},
+  launch_gemm<64, 64, 32, 4>(RowMajorA{X, ldx, nullptr}, RowMajorB{Wt, ldw, nullptr},
                              StoreEp{Y, ldy, b, relu, nullptr, nullptr, 0, res, ldr}, M, N, K, 1, nullptr, st, "tracker_linear_fwd_gemm");
 }
 // dX[M,K] = dY[M,N] Wt^T (* mask) (+ res)
 void linear_bwd_x(const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int N, int K,
                   const float* mask, int ldm, const float* res, int ldr, cudaStream_t st) {
-  launch_gemm<64, 64, 16, 4>(RowMajorA{dY, ldy, nullptr}, ColMajorB{Wt, ldw},
+  launch_gemm<64, 64, 32, 4>(RowMajorA{dY, ldy, nullptr}, ColMajorB{Wt, ldw},
                              StoreEp{dX, ldx, nullptr, 0, nullptr, mask, ldm, res, ldr}, M, K, N, 1, nullptr, st, "tracker_linear_dx_gemm");
 }
 // gWt[K][ldw] += X^T dY,  gb[N] += colsum(dY)
 void linear_bwd_w(const float* X, int ldx, const float* dY, int ldy, float* gWt, int ldw, float* gb, int M, int N,
                   int K, cudaStream_t st) {
   const int tiles = ((K + 63) / 64) * ((N + 63) / 64);
-  launch_gemm<64, 64, 16, 4>(ColMajorA{X, ldx, nullptr}, RowMajorB{dY, ldy, nullptr}, AtomicEp{gWt, ldw}, K, N, M,
+  launch_gemm<64, 64, 32, 4>(ColMajorA{X, ldx, nullptr}, RowMajorB{dY, ldy, nullptr}, AtomicEp{gWt, ldw}, K, N, M,
                              splitk(tiles, M), gb, st, "tracker_linear_dw_gemm");
 }
 
@@ -466,7 +466,7 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
     x = y.x2;
   }
   if (obs_check)   // decoded states, scattered to their buffer slots
-    launch_gemm<64, 64, 16, 4>(RowMajorA{x, d, nullptr}, RowMajorB{W.dec_wt, lds, nullptr},
+    launch_gemm<64, 64, 32, 4>(RowMajorA{x, d, nullptr}, RowMajorB{W.dec_wt, lds, nullptr},
                                StoreEp{obs_check, S, W.dec_b, 0, tok_slot, nullptr, 0, nullptr, 0}, M, S, d, 1, nullptr,
                                st, "tracker_linear_fwd_gemm");
   CIRS_CHECK_LAUNCH();
@@ -475,9 +475,9 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
   // ================= backward
   const int ln_grid = min((M + 7) / 8, 148 * 4);
   // decoder: d_obs rows are gathered from their buffer slots
-  launch_gemm<64, 64, 16, 4>(ColMajorA{x, d, nullptr}, RowMajorB{d_obs, S, tok_slot}, AtomicEp{G.dec_wt, lds}, d, S, M,
+  launch_gemm<64, 64, 32, 4>(ColMajorA{x, d, nullptr}, RowMajorB{d_obs, S, tok_slot}, AtomicEp{G.dec_wt, lds}, d, S, M,
                              splitk(1, M), G.dec_b, st, "tracker_linear_dw_gemm");
-  launch_gemm<64, 64, 16, 4>(RowMajorA{d_obs, S, tok_slot}, ColMajorB{W.dec_wt, lds},
+  launch_gemm<64, 64, 32, 4>(RowMajorA{d_obs, S, tok_slot}, ColMajorB{W.dec_wt, lds},
                              StoreEp{b.da, d, nullptr, 0, nullptr, nullptr, 0, nullptr, 0}, M, d, S, 1, nullptr, st,
                              "tracker_linear_dx_gemm");                                               // da = dX_last
   for (int l = nl - 1; l >= 0; --l) {
