@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcirs_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LAYERS = 4
 HIDDEN = 64
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CIRS_ABI_VERSION 5
+#define CIRS_ABI_VERSION 6
 #define CIRS_MAX_LAYERS 4
 #define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
 
