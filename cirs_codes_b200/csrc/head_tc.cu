@@ -160,32 +160,62 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
-// ------------------------------------------------------------------------------------------------- pass B2
-constexpr size_t B2_SMEM = 2 * A_BYTES + 4 * B_BYTES + 2 * A_BYTES + 64 * 4 + NTB * 4;
+// ------------------------------------------------------------------------------------------------- passes B2 / B3
+// Software pipeline shared by both backward passes (tile t, buffers b = t & 1):
+//     stage operands of tile t+1 -> MMA1(t+1) into the other logits accumulator   | overlaps
+//     epilogue(t): TMEM logits -> d logits, written BACK TO TMEM as the (hi, lo) A operand  | MMA1(t+1) and MMA2(t-1)
+//     MMA2(t): D2 += d logits[tmem] . B2[smem]
+// d logits never touch shared memory (tcgen05.st), which frees the 64 KB that double-buffer the B operands.
+// TMEM columns (512 allocated): logits accumulators [0,64) [64,128) | D2 [128,192) | d logits hi/lo, two buffers [192,448).
+constexpr uint32_t T_D1 = 0, T_D2 = 128, T_DL = 192;
+__device__ __forceinline__ uint32_t t_dl_hi(int b) { return T_DL + 128u * b; }
+__device__ __forceinline__ uint32_t t_dl_lo(int b) { return T_DL + 128u * b + 64u; }
+
+// D (+)= A[tmem hi/lo] . B[smem hi/lo], 3 TF32 products per k-step of 8
+__device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const char* b_hi, const char* b_lo,
+                                         bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  const uint32_t bh0 = smem_u32(b_hi), bl0 = smem_u32(b_lo);
+#pragma unroll
+  for (int j = 0; j < KSTEPS; ++j) {
+    const uint64_t bh = smem_desc(bh0 + j * B_STEP, B_LBO, SBO), bl = smem_desc(bl0 + j * B_STEP, B_LBO, SBO);
+    mma_tf32_ts(d, a_lo + 8 * j, bh, IDESC, acc);
+    mma_tf32_ts(d, a_hi + 8 * j, bl, IDESC, 1u);
+    mma_tf32_ts(d, a_hi + 8 * j, bh, IDESC, 1u);
+    acc = 1u;
+  }
+}
+// 16 d-logit values of this thread's lane -> TMEM (hi by truncation, lo = x - hi: gradients need ~2^-22, tc_dev.cuh)
+__device__ __forceinline__ void store_dl(uint32_t tb, int b, uint32_t lane_base, int col0, const float (&v)[16]) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { hi[j] = tf32_trunc(v[j]); lo[j] = v[j] - hi[j]; }
+  tmem_st16(tmem_addr(tb + t_dl_hi(b), lane_base, col0), hi);
+  tmem_st16(tmem_addr(tb + t_dl_lo(b), lane_base, col0), lo);
+  tmem_st_wait();
+}
+
+constexpr size_t B2_SMEM = 2 * A_BYTES + 8 * B_BYTES + 2 * 64 * 4 + NTB * 4;
 
 __global__ void __launch_bounds__(NTB, 1)
 head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
                    const float* __restrict__ coef, const int32_t* __restrict__ acta, int tiles_per_split, int n_split,
                    float* __restrict__ dh2_part, float* __restrict__ ent_part) {
   extern __shared__ __align__(1024) char smem[];
-  char* a_hi = smem;                 // h2 tile            (A of MMA1)
+  char* a_hi = smem;                         // h2 tile                            (A of MMA1)
   char* a_lo = a_hi + A_BYTES;
-  char* bn_hi = a_lo + A_BYTES;      // W3 tile, r = column, c = hidden   (B of MMA1)
-  char* bn_lo = bn_hi + B_BYTES;
-  char* bk_hi = bn_lo + B_BYTES;     // W3 tile, r = hidden, c = column   (B of MMA2)
-  char* bk_lo = bk_hi + B_BYTES;
-  char* dl_hi = bk_lo + B_BYTES;     // d logits tile, r = row, c = column (A of MMA2)
-  char* dl_lo = dl_hi + A_BYTES;
-  float* sb3 = reinterpret_cast<float*>(dl_lo + A_BYTES);
-  float* se = sb3 + 64;
-  __shared__ __align__(8) uint64_t bar1, bar2;
+  char* bn = a_lo + A_BYTES;                 // 2 x { W3 tile r = column, c = hidden: hi, lo }   (B of MMA1)
+  char* bk = bn + 4 * B_BYTES;               // 2 x { W3 tile r = hidden, c = column: hi, lo }   (B of MMA2)
+  float* sb3 = reinterpret_cast<float*>(bk + 4 * B_BYTES);   // 2 x 64
+  float* se = sb3 + 128;
+  __shared__ __align__(8) uint64_t bar1[2], bar2[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, qt = tid >> 7;   // qt: column quarter (16 columns)
   const int r0 = blockIdx.x * TM, split = blockIdx.y;
   const int n_tiles = (H.nA + TN - 1) / TN;
-  const int ct0 = split * tiles_per_split, ct1 = min(n_tiles, ct0 + tiles_per_split);
-  if (warp == 0) tmem_alloc(&tmem_base, 128);
-  if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
+  const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2[0], 1); mbar_init(&bar2[1], 1); mbar_fence_init(); }
   {
     TileV<TM, HID, NTB> ta;
     ta.load(tid, SrcH2{H.h2, r0, H.n});
@@ -194,69 +224,84 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   TileT<TN, HID, NTB> tn;      // next tile, transposed (B of MMA1)
   TileV<HID, TN, NTB> tk;      // next tile, natural    (B of MMA2)
   float b3n = 0.f;
-  auto prefetch = [&](int ct) {
-    const int c0 = ct * TN;
+  auto prefetch = [&](int t) {
+    const int c0 = (ct0 + t) * TN;
     tn.load(tid, SrcW3T{H.w3t, H.ldA, c0});
     tk.load(tid, SrcW3{H.w3t, H.ldA, c0});
     b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : MASKED;
   };
-  if (ct0 < ct1) prefetch(ct0);
+  auto stage = [&](int b) {   // registers -> shared buffers b
+    tn.store(bn + 2 * b * B_BYTES, bn + (2 * b + 1) * B_BYTES, tid);
+    tk.store(bk + 2 * b * B_BYTES, bk + (2 * b + 1) * B_BYTES, tid);
+    if (tid < TN) sb3[64 * b + tid] = b3n;
+  };
   const bool live = r0 + row < H.n;
   const float rm = live ? rowm[r0 + row] : 0.f, iz = live ? rinvz[r0 + row] : 0.f, cf = live ? coef[r0 + row] : 0.f;
   const int a = live ? acta[r0 + row] : -1;
   const float log_z = iz > 0.f ? -logf(iz) : 0.f;
   float ent = 0.f;
-  uint32_t ph = 0, tb = 0;
-  for (int ct = ct0; ct < ct1; ++ct) {
-    const int c0 = ct * TN;
-    tn.store(bn_hi, bn_lo, tid);
-    if (tid < TN) sb3[tid] = b3n;
+  uint32_t tb = 0;
+  if (T > 0) {
+    prefetch(0);
+    stage(0);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     tb = tmem_base;
     if (tid == 0) {
-      issue(tb, a_hi, a_lo, bn_hi, bn_lo, false);        // D1 = logits tile - b3
-      mma_commit(&bar1);
+      issue(tb + T_D1, a_hi, a_lo, bn, bn + B_BYTES, false);
+      mma_commit(&bar1[0]);
     }
-    if (ct > ct0) wait_or_flag(&bar2, ph ^ 1);            // previous MMA2 has finished reading bk / dl
-    tk.store(bk_hi, bk_lo, tid);
-    if (ct + 1 < ct1) prefetch(ct + 1);
-    wait_or_flag(&bar1, ph);
+    if (T > 1) prefetch(1);
+  }
+  for (int t = 0; t < T; ++t) {
+    const int b = t & 1, nb = b ^ 1;
+    if (t + 1 < T) {
+      if (t >= 1) wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);   // MMA2(t-1) no longer reads bk[nb] / d logits[nb]
+      stage(nb);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      fence_after_sync();
+      if (tid == 0) {
+        issue(tb + T_D1 + 64u * nb, a_hi, a_lo, bn + 2 * nb * B_BYTES, bn + (2 * nb + 1) * B_BYTES, false);
+        mma_commit(&bar1[nb]);
+      }
+      if (t + 2 < T) prefetch(t + 2);
+    } else if (t >= 1) {
+      wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);
+    }
+    wait_or_flag(&bar1[b], (t >> 1) & 1);
     fence_after_sync();
     {
       float v[16];
-      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, qt * 16), v);
-      const int cb = c0 + qt * 16;
+      tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
+      const int cb = (ct0 + t) * TN + qt * 16;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float xm = v[j] + sb3[qt * 16 + j] - rm;          // logit - max (padding columns: -1e30)
+        const float xm = v[j] + sb3[64 * b + qt * 16 + j] - rm;   // logit - max (padding columns: -1e30)
         const float p = fast_exp(xm) * iz;
         // entropy of Categorical(probs): -sum p log(clamp(p, eps, 1 - eps)) with log clamp(p) = clamp(log p)
         const float lg = fminf(fmaxf(xm - log_z, LOG_EPS), LOG_1M_EPS);
         ent = fmaf(-p, lg, ent);
         v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        tile_store_split_trunc(dl_hi, dl_lo, TM, row, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      store_dl(tb, b, (warp & 3) * 32, qt * 16, v);
     }
-    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 0) {
-      issue(tb + 64, dl_hi, dl_lo, bk_hi, bk_lo, ct > ct0);   // D2 += d logits . W3   (K = this tile's 64 columns)
-      mma_commit(&bar2);
+    if (tid == 0) {   // D2 += d logits . W3   (K = this tile's 64 columns)
+      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk + 2 * b * B_BYTES, bk + (2 * b + 1) * B_BYTES, t > 0);
+      mma_commit(&bar2[b]);
     }
-    ph ^= 1;
   }
-  if (ct1 > ct0) wait_or_flag(&bar2, ph ^ 1);
-  fence_after_sync();
-  if (ct1 > ct0) {
+  if (T > 0) {
+    wait_or_flag(&bar2[(T - 1) & 1], ((T - 1) >> 1) & 1);   // commits cover every earlier MMA of the issuing thread
+    fence_after_sync();
     float v[16];
-    tmem_ld16(tmem_addr(tb + 64, (warp & 3) * 32, qt * 16), v);
+    tmem_ld16(tmem_addr(tb + T_D2, (warp & 3) * 32, qt * 16), v);
     if (live) {
       float* dst = dh2_part + ((size_t)split * H.n + r0 + row) * HID + qt * 16;
 #pragma unroll
@@ -269,36 +314,29 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   __syncthreads();
   if (qt == 0 && live)
     ent_part[(size_t)(r0 + row) * n_split + split] = (ent + se[tid + TM]) + (se[tid + 2 * TM] + se[tid + 3 * TM]);
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------------- pass B3
-constexpr size_t B3_SMEM = 2 * A_BYTES + 4 * B_BYTES + 2 * A_BYTES + 4 * 64 * 4;
+constexpr size_t B3_SMEM = 2 * A_BYTES + 8 * B_BYTES + 2 * 4 * 64 * 4;
 
 __global__ void __launch_bounds__(NTB, 1)
 head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
                    const float* __restrict__ coef, const int32_t* __restrict__ acta, int rows_per_split, int n_rsplit,
                    float* __restrict__ g_w3t, float* __restrict__ g_b3) {
   extern __shared__ __align__(1024) char smem[];
-  char* wa_hi = smem;                // W3 tile, r = column (128), c = hidden   (A of MMA1')
+  char* wa_hi = smem;                        // W3 tile, r = column (128), c = hidden   (A of MMA1')
   char* wa_lo = wa_hi + A_BYTES;
-  char* hb_hi = wa_lo + A_BYTES;     // h2 tile, r = row (64), c = hidden       (B of MMA1')
-  char* hb_lo = hb_hi + B_BYTES;
-  char* ht_hi = hb_lo + B_BYTES;     // h2 tile, r = hidden, c = row            (B of MMA3)
-  char* ht_lo = ht_hi + B_BYTES;
-  char* dl_hi = ht_lo + B_BYTES;     // d logits^T tile, r = column, c = row    (A of MMA3)
-  char* dl_lo = dl_hi + A_BYTES;
-  float* srm = reinterpret_cast<float*>(dl_lo + A_BYTES);
-  float* siz = srm + 64;
-  float* scf = siz + 64;
-  int* sac = reinterpret_cast<int*>(scf + 64);
-  __shared__ __align__(8) uint64_t bar1, bar2;
+  char* hb = wa_lo + A_BYTES;                // 2 x { h2 tile r = row (64), c = hidden: hi, lo }   (B of MMA1')
+  char* ht = hb + 4 * B_BYTES;               // 2 x { h2 tile r = hidden, c = row: hi, lo }        (B of MMA3)
+  float* stats = reinterpret_cast<float*>(ht + 4 * B_BYTES);   // 2 x { max[64], 1/Z[64], coef[64], action[64] }
+  __shared__ __align__(8) uint64_t bar1[2], bar2[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, cl = tid & 127, qt = tid >> 7;   // qt: quarter of 16 rows / hidden units
   const int c0 = blockIdx.x * TM, col = c0 + cl;
   const int rs0 = blockIdx.y * rows_per_split, rs1 = min(H.n, rs0 + rows_per_split);
-  if (warp == 0) tmem_alloc(&tmem_base, 128);
-  if (tid == 0) { mbar_init(&bar1, 1); mbar_init(&bar2, 1); mbar_fence_init(); }
+  const int T = rs1 > rs0 ? (rs1 - rs0 + TN - 1) / TN : 0;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2[0], 1); mbar_init(&bar2[1], 1); mbar_fence_init(); }
   {
     TileT<TM, HID, NTB> tw;
     tw.load(tid, SrcW3T{H.w3t, H.ldA, c0});
@@ -308,7 +346,8 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   TileT<HID, TN, NTB> tt;      // next row tile of h2, transposed (B of MMA3)
   float n_rm = 0.f, n_iz = 0.f, n_cf = 0.f;
   int n_ac = -1;
-  auto prefetch = [&](int r0) {
+  auto prefetch = [&](int t) {
+    const int r0 = rs0 + t * TN;
     tv.load(tid, SrcH2{H.h2, r0, rs1});
     tt.load(tid, SrcH2T{H.h2, r0, rs1});
     const bool ok = tid < TN && r0 + tid < rs1;
@@ -317,58 +356,78 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
     n_cf = ok ? coef[r0 + tid] : 0.f;
     n_ac = ok ? acta[r0 + tid] : -1;
   };
-  if (rs0 < rs1) prefetch(rs0);
+  auto stage = [&](int b) {
+    tv.store(hb + 2 * b * B_BYTES, hb + (2 * b + 1) * B_BYTES, tid);
+    tt.store(ht + 2 * b * B_BYTES, ht + (2 * b + 1) * B_BYTES, tid);
+    if (tid < TN) {
+      float* sp = stats + 256 * b;
+      sp[tid] = n_rm; sp[64 + tid] = n_iz; sp[128 + tid] = n_cf; reinterpret_cast<int*>(sp)[192 + tid] = n_ac;
+    }
+  };
   const bool live = col < H.nA;
   const float b3v = live ? __ldg(H.b3 + col) : MASKED;
   float db3 = 0.f;
-  uint32_t ph = 0, tb = 0;
-  for (int r0 = rs0; r0 < rs1; r0 += TN) {
-    tv.store(hb_hi, hb_lo, tid);
-    if (tid < TN) { srm[tid] = n_rm; siz[tid] = n_iz; scf[tid] = n_cf; sac[tid] = n_ac; }
+  uint32_t tb = 0;
+  if (T > 0) {
+    prefetch(0);
+    stage(0);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     tb = tmem_base;
     if (tid == 0) {
-      issue(tb, wa_hi, wa_lo, hb_hi, hb_lo, false);       // D1' = (logits tile)^T - b3: lane = column, 64 rows
-      mma_commit(&bar1);
+      issue(tb + T_D1, wa_hi, wa_lo, hb, hb + B_BYTES, false);   // (logits tile)^T - b3: lane = column, 64 rows
+      mma_commit(&bar1[0]);
     }
-    if (r0 > rs0) wait_or_flag(&bar2, ph ^ 1);             // previous MMA3 has finished reading ht / dl
-    tt.store(ht_hi, ht_lo, tid);
-    if (r0 + TN < rs1) prefetch(r0 + TN);
-    wait_or_flag(&bar1, ph);
+    if (T > 1) prefetch(1);
+  }
+  for (int t = 0; t < T; ++t) {
+    const int b = t & 1, nb = b ^ 1;
+    if (t + 1 < T) {
+      if (t >= 1) wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);   // MMA3(t-1) no longer reads ht[nb] / d logits[nb]
+      stage(nb);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      fence_after_sync();
+      if (tid == 0) {
+        issue(tb + T_D1 + 64u * nb, wa_hi, wa_lo, hb + 2 * nb * B_BYTES, hb + (2 * nb + 1) * B_BYTES, false);
+        mma_commit(&bar1[nb]);
+      }
+      if (t + 2 < T) prefetch(t + 2);
+    } else if (t >= 1) {
+      wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);
+    }
+    wait_or_flag(&bar1[b], (t >> 1) & 1);
     fence_after_sync();
     {
+      const float* sp = stats + 256 * b;
       float v[16];
-      tmem_ld16(tmem_addr(tb, (warp & 3) * 32, qt * 16), v);
+      tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int jj = qt * 16 + j;
-        const float p = fast_exp(v[j] + b3v - srm[jj]) * siz[jj];   // padding columns / rows: bias -1e30 or 1/Z = 0
-        const float d = scf[jj] * ((sac[jj] == col ? 1.f : 0.f) - p);
+        const float p = fast_exp(v[j] + b3v - sp[jj]) * sp[64 + jj];   // padding columns / rows: bias -1e30 or 1/Z = 0
+        const float d = sp[128 + jj] * ((reinterpret_cast<const int*>(sp)[192 + jj] == col ? 1.f : 0.f) - p);
         db3 += d;
         v[j] = d;
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        tile_store_split_trunc(dl_hi, dl_lo, TM, cl, qt * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      store_dl(tb, b, (warp & 3) * 32, qt * 16, v);
     }
-    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 0) {
-      issue(tb + 64, dl_hi, dl_lo, ht_hi, ht_lo, r0 > rs0);   // D3 += d logits^T . h2   (K = this tile's 64 rows)
-      mma_commit(&bar2);
+    if (tid == 0) {   // D3 += d logits^T . h2   (K = this tile's 64 rows)
+      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht + 2 * b * B_BYTES, ht + (2 * b + 1) * B_BYTES, t > 0);
+      mma_commit(&bar2[b]);
     }
-    ph ^= 1;
   }
-  if (rs1 > rs0) {
-    wait_or_flag(&bar2, ph ^ 1);
+  if (T > 0) {
+    wait_or_flag(&bar2[(T - 1) & 1], ((T - 1) >> 1) & 1);
     fence_after_sync();
     float v[16];
-    tmem_ld16(tmem_addr(tb + 64, (warp & 3) * 32, qt * 16), v);
+    tmem_ld16(tmem_addr(tb + T_D2, (warp & 3) * 32, qt * 16), v);
     if (live) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -380,7 +439,7 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 template <class K>

@@ -5,6 +5,6 @@
 set -e
 cd "$(dirname "$0")"
 mkdir -p bin
-for p in tc_probe tc_probe2; do
+for p in tc_probe tc_probe2 tc_probe3; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 --extended-lambda -o bin/$p $p.cu
 done
