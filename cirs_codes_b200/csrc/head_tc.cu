@@ -195,9 +195,9 @@ __device__ __forceinline__ void store_dl(uint32_t tb, int b, uint32_t lane_base,
   tmem_st_wait();
 }
 
-constexpr size_t B2_SMEM = 2 * A_BYTES + 8 * B_BYTES + 2 * 64 * 4 + NTB * 4;
+constexpr size_t B2_SMEM = 2 * A_BYTES + 6 * B_BYTES + 2 * 64 * 4 + NTB * 4;
 
-__global__ void __launch_bounds__(NTB, 1)
+__global__ void __launch_bounds__(NTB + 32, 1)
 head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
                    const float* __restrict__ coef, const int32_t* __restrict__ acta, int tiles_per_split, int n_split,
                    float* __restrict__ dh2_part, float* __restrict__ ent_part) {
@@ -205,76 +205,80 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   char* a_hi = smem;                         // h2 tile                            (A of MMA1)
   char* a_lo = a_hi + A_BYTES;
   char* bn = a_lo + A_BYTES;                 // 2 x { W3 tile r = column, c = hidden: hi, lo }   (B of MMA1)
-  char* bk = bn + 4 * B_BYTES;               // 2 x { W3 tile r = hidden, c = column: hi, lo }   (B of MMA2)
-  float* sb3 = reinterpret_cast<float*>(bk + 4 * B_BYTES);   // 2 x 64
+  char* bk = bn + 4 * B_BYTES;               // 1 x { W3 tile r = hidden, c = column: hi, lo }   (B of MMA2)
+  float* sb3 = reinterpret_cast<float*>(bk + 2 * B_BYTES);   // 2 x 64
   float* se = sb3 + 128;
-  __shared__ __align__(8) uint64_t bar1[2], bar2[2];
+  __shared__ __align__(8) uint64_t bar1[2], bar2;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, qt = tid >> 7;   // qt: column quarter (16 columns)
+  const bool worker = tid < NTB, issuer = tid == NTB;   // warp 16 only issues MMAs (the issue of a 24-MMA batch blocks
+                                                        // for ~0.7 us: a worker that issued kept all others waiting)
   const int r0 = blockIdx.x * TM, split = blockIdx.y;
   const int n_tiles = (H.nA + TN - 1) / TN;
   const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
   if (warp == 0) tmem_alloc(&tmem_base, 512);
-  if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2[0], 1); mbar_init(&bar2[1], 1); mbar_fence_init(); }
-  {
+  if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2, 1); mbar_fence_init(); }
+  if (worker) {
     TileV<TM, HID, NTB> ta;
     ta.load(tid, SrcH2{H.h2, r0, H.n});
     ta.store(a_hi, a_lo, tid);
   }
-  TileT<TN, HID, NTB> tn;      // next tile, transposed (B of MMA1)
-  TileV<HID, TN, NTB> tk;      // next tile, natural    (B of MMA2)
+  // Register prefetch, one tile ahead of use: ``tn`` (transposed W3 tile, B of MMA1) holds tile t+1 while tile t is in
+  // its epilogue; ``tk`` (natural W3 tile, B of MMA2) lags one tile behind it, because MMA2(t) is only issued after the
+  // epilogue of tile t -- which lets its single shared buffer be rewritten late, after MMA2(t-1) has long finished.
+  TileT<TN, HID, NTB> tn;
+  TileV<HID, TN, NTB> tk;
   float b3n = 0.f;
-  auto prefetch = [&](int t) {
+  auto load_n = [&](int t) {
+    if (!worker) return;
     const int c0 = (ct0 + t) * TN;
     tn.load(tid, SrcW3T{H.w3t, H.ldA, c0});
-    tk.load(tid, SrcW3{H.w3t, H.ldA, c0});
     b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : MASKED;
   };
-  auto stage = [&](int b) {   // registers -> shared buffers b
+  auto load_k = [&](int t) { if (worker) tk.load(tid, SrcW3{H.w3t, H.ldA, (ct0 + t) * TN}); };
+  auto stage_n = [&](int b) {
+    if (!worker) return;
     tn.store(bn + 2 * b * B_BYTES, bn + (2 * b + 1) * B_BYTES, tid);
-    tk.store(bk + 2 * b * B_BYTES, bk + (2 * b + 1) * B_BYTES, tid);
     if (tid < TN) sb3[64 * b + tid] = b3n;
   };
-  const bool live = r0 + row < H.n;
+  const bool live = worker && r0 + row < H.n;
   const float rm = live ? rowm[r0 + row] : 0.f, iz = live ? rinvz[r0 + row] : 0.f, cf = live ? coef[r0 + row] : 0.f;
   const int a = live ? acta[r0 + row] : -1;
   const float log_z = iz > 0.f ? -logf(iz) : 0.f;
   float ent = 0.f;
   uint32_t tb = 0;
   if (T > 0) {
-    prefetch(0);
-    stage(0);
+    load_n(0);
+    load_k(0);
+    stage_n(0);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     tb = tmem_base;
-    if (tid == 0) {
+    if (issuer) {
       issue(tb + T_D1, a_hi, a_lo, bn, bn + B_BYTES, false);
       mma_commit(&bar1[0]);
     }
-    if (T > 1) prefetch(1);
+    if (T > 1) load_n(1);
   }
   for (int t = 0; t < T; ++t) {
     const int b = t & 1, nb = b ^ 1;
-    if (t + 1 < T) {
-      if (t >= 1) wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);   // MMA2(t-1) no longer reads bk[nb] / d logits[nb]
-      stage(nb);
+    if (t + 1 < T) {   // logits MMA of the next tile runs behind this tile's epilogue
+      stage_n(nb);
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
-      if (tid == 0) {
+      if (issuer) {
         issue(tb + T_D1 + 64u * nb, a_hi, a_lo, bn + 2 * nb * B_BYTES, bn + (2 * nb + 1) * B_BYTES, false);
         mma_commit(&bar1[nb]);
       }
-      if (t + 2 < T) prefetch(t + 2);
-    } else if (t >= 1) {
-      wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);
+      if (t + 2 < T) load_n(t + 2);
     }
-    wait_or_flag(&bar1[b], (t >> 1) & 1);
-    fence_after_sync();
-    {
+    if (worker) {
+      wait_or_flag(&bar1[b], (t >> 1) & 1);
+      fence_after_sync();
       float v[16];
       tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
       const int cb = (ct0 + t) * TN + qt * 16;
@@ -288,17 +292,21 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
         v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
       }
       store_dl(tb, b, (warp & 3) * 32, qt * 16, v);
+      if (t >= 1) wait_or_flag(&bar2, (t - 1) & 1);   // MMA2(t-1), issued a whole epilogue ago, no longer reads bk
+      tk.store(bk, bk + B_BYTES, tid);
+      if (t + 1 < T) load_k(t + 1);
     }
+    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 0) {   // D2 += d logits . W3   (K = this tile's 64 columns)
-      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk + 2 * b * B_BYTES, bk + (2 * b + 1) * B_BYTES, t > 0);
-      mma_commit(&bar2[b]);
+    if (issuer) {   // D2 += d logits . W3   (K = this tile's 64 columns); runs behind the next tile's staging + epilogue
+      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk, bk + B_BYTES, t > 0);
+      mma_commit(&bar2);
     }
   }
-  if (T > 0) {
-    wait_or_flag(&bar2[(T - 1) & 1], ((T - 1) >> 1) & 1);   // commits cover every earlier MMA of the issuing thread
+  if (T > 0 && worker) {
+    wait_or_flag(&bar2, (T - 1) & 1);
     fence_after_sync();
     float v[16];
     tmem_ld16(tmem_addr(tb + T_D2, (warp & 3) * 32, qt * 16), v);
@@ -309,7 +317,7 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
         *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
   }
-  se[tid] = ent;
+  if (worker) se[tid] = ent;
   fence_before_sync();
   __syncthreads();
   if (qt == 0 && live)
@@ -317,9 +325,9 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-constexpr size_t B3_SMEM = 2 * A_BYTES + 8 * B_BYTES + 2 * 4 * 64 * 4;
+constexpr size_t B3_SMEM = 2 * A_BYTES + 6 * B_BYTES + 2 * 4 * 64 * 4;
 
-__global__ void __launch_bounds__(NTB, 1)
+__global__ void __launch_bounds__(NTB + 32, 1)
 head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
                    const float* __restrict__ coef, const int32_t* __restrict__ acta, int rows_per_split, int n_rsplit,
                    float* __restrict__ g_w3t, float* __restrict__ g_b3) {
@@ -327,81 +335,83 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   char* wa_hi = smem;                        // W3 tile, r = column (128), c = hidden   (A of MMA1')
   char* wa_lo = wa_hi + A_BYTES;
   char* hb = wa_lo + A_BYTES;                // 2 x { h2 tile r = row (64), c = hidden: hi, lo }   (B of MMA1')
-  char* ht = hb + 4 * B_BYTES;               // 2 x { h2 tile r = hidden, c = row: hi, lo }        (B of MMA3)
-  float* stats = reinterpret_cast<float*>(ht + 4 * B_BYTES);   // 2 x { max[64], 1/Z[64], coef[64], action[64] }
-  __shared__ __align__(8) uint64_t bar1[2], bar2[2];
+  char* ht = hb + 4 * B_BYTES;               // 1 x { h2 tile r = hidden, c = row: hi, lo }        (B of MMA3)
+  float* stats = reinterpret_cast<float*>(ht + 2 * B_BYTES);   // 2 x { max[64], 1/Z[64], coef[64], action[64] }
+  __shared__ __align__(8) uint64_t bar1[2], bar2;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, cl = tid & 127, qt = tid >> 7;   // qt: quarter of 16 rows / hidden units
+  const bool worker = tid < NTB, issuer = tid == NTB;   // warp 16 only issues MMAs
   const int c0 = blockIdx.x * TM, col = c0 + cl;
   const int rs0 = blockIdx.y * rows_per_split, rs1 = min(H.n, rs0 + rows_per_split);
   const int T = rs1 > rs0 ? (rs1 - rs0 + TN - 1) / TN : 0;
   if (warp == 0) tmem_alloc(&tmem_base, 512);
-  if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2[0], 1); mbar_init(&bar2[1], 1); mbar_fence_init(); }
-  {
+  if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2, 1); mbar_fence_init(); }
+  if (worker) {
     TileT<TM, HID, NTB> tw;
     tw.load(tid, SrcW3T{H.w3t, H.ldA, c0});
     tw.store(wa_hi, wa_lo, tid);
   }
-  TileV<TN, HID, NTB> tv;      // next row tile of h2, natural    (B of MMA1')
-  TileT<HID, TN, NTB> tt;      // next row tile of h2, transposed (B of MMA3)
+  // register prefetch as in pass B2: ``tv`` (natural h2 tile, B of MMA1') one tile ahead, ``tt`` (transposed, B of MMA3)
+  // one tile behind it
+  TileV<TN, HID, NTB> tv;
+  TileT<HID, TN, NTB> tt;
   float n_rm = 0.f, n_iz = 0.f, n_cf = 0.f;
   int n_ac = -1;
-  auto prefetch = [&](int t) {
+  auto load_v = [&](int t) {
+    if (!worker) return;
     const int r0 = rs0 + t * TN;
     tv.load(tid, SrcH2{H.h2, r0, rs1});
-    tt.load(tid, SrcH2T{H.h2, r0, rs1});
     const bool ok = tid < TN && r0 + tid < rs1;
     n_rm = ok ? rowm[r0 + tid] : 0.f;
     n_iz = ok ? rinvz[r0 + tid] : 0.f;
     n_cf = ok ? coef[r0 + tid] : 0.f;
     n_ac = ok ? acta[r0 + tid] : -1;
   };
-  auto stage = [&](int b) {
+  auto load_t = [&](int t) { if (worker) tt.load(tid, SrcH2T{H.h2, rs0 + t * TN, rs1}); };
+  auto stage_v = [&](int b) {
+    if (!worker) return;
     tv.store(hb + 2 * b * B_BYTES, hb + (2 * b + 1) * B_BYTES, tid);
-    tt.store(ht + 2 * b * B_BYTES, ht + (2 * b + 1) * B_BYTES, tid);
     if (tid < TN) {
       float* sp = stats + 256 * b;
       sp[tid] = n_rm; sp[64 + tid] = n_iz; sp[128 + tid] = n_cf; reinterpret_cast<int*>(sp)[192 + tid] = n_ac;
     }
   };
-  const bool live = col < H.nA;
+  const bool live = worker && col < H.nA;
   const float b3v = live ? __ldg(H.b3 + col) : MASKED;
   float db3 = 0.f;
   uint32_t tb = 0;
   if (T > 0) {
-    prefetch(0);
-    stage(0);
+    load_v(0);
+    load_t(0);
+    stage_v(0);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     tb = tmem_base;
-    if (tid == 0) {
+    if (issuer) {
       issue(tb + T_D1, wa_hi, wa_lo, hb, hb + B_BYTES, false);   // (logits tile)^T - b3: lane = column, 64 rows
       mma_commit(&bar1[0]);
     }
-    if (T > 1) prefetch(1);
+    if (T > 1) load_v(1);
   }
   for (int t = 0; t < T; ++t) {
     const int b = t & 1, nb = b ^ 1;
     if (t + 1 < T) {
-      if (t >= 1) wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);   // MMA3(t-1) no longer reads ht[nb] / d logits[nb]
-      stage(nb);
+      stage_v(nb);
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
-      if (tid == 0) {
+      if (issuer) {
         issue(tb + T_D1 + 64u * nb, wa_hi, wa_lo, hb + 2 * nb * B_BYTES, hb + (2 * nb + 1) * B_BYTES, false);
         mma_commit(&bar1[nb]);
       }
-      if (t + 2 < T) prefetch(t + 2);
-    } else if (t >= 1) {
-      wait_or_flag(&bar2[nb], ((t - 1) >> 1) & 1);
+      if (t + 2 < T) load_v(t + 2);
     }
-    wait_or_flag(&bar1[b], (t >> 1) & 1);
-    fence_after_sync();
-    {
+    if (worker) {
+      wait_or_flag(&bar1[b], (t >> 1) & 1);
+      fence_after_sync();
       const float* sp = stats + 256 * b;
       float v[16];
       tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
@@ -414,17 +424,21 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
         v[j] = d;
       }
       store_dl(tb, b, (warp & 3) * 32, qt * 16, v);
+      if (t >= 1) wait_or_flag(&bar2, (t - 1) & 1);   // MMA3(t-1) no longer reads ht
+      tt.store(ht, ht + B_BYTES, tid);
+      if (t + 1 < T) load_t(t + 1);
     }
+    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (tid == 0) {   // D3 += d logits^T . h2   (K = this tile's 64 rows)
-      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht + 2 * b * B_BYTES, ht + (2 * b + 1) * B_BYTES, t > 0);
-      mma_commit(&bar2[b]);
+    if (issuer) {   // D3 += d logits^T . h2   (K = this tile's 64 rows)
+      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht, ht + B_BYTES, t > 0);
+      mma_commit(&bar2);
     }
   }
-  if (T > 0) {
-    wait_or_flag(&bar2[(T - 1) & 1], ((T - 1) >> 1) & 1);
+  if (T > 0 && worker) {
+    wait_or_flag(&bar2, (T - 1) & 1);
     fence_after_sync();
     float v[16];
     tmem_ld16(tmem_addr(tb + T_D2, (warp & 3) * 32, qt * 16), v);
@@ -490,7 +504,7 @@ int head_tc_dh2(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
-  CIRS_LAUNCH(head_tc_dh2_kernel, grid, NTB, B2_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part, ent_part);
+  CIRS_LAUNCH(head_tc_dh2_kernel, grid, NTB + 32, B2_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part, ent_part);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }
@@ -506,7 +520,7 @@ int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   int tiles_per = (row_tiles + n_rsplit - 1) / n_rsplit;
   n_rsplit = (row_tiles + tiles_per - 1) / tiles_per;
   dim3 grid(n_ct, n_rsplit);
-  CIRS_LAUNCH(head_tc_dw3_kernel, grid, NTB, B3_SMEM, st, H, rowm, rinvz, coef, acta, tiles_per * TN, n_rsplit, g_w3t,
+  CIRS_LAUNCH(head_tc_dw3_kernel, grid, NTB + 32, B3_SMEM, st, H, rowm, rinvz, coef, acta, tiles_per * TN, n_rsplit, g_w3t,
               g_b3);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
