@@ -60,7 +60,9 @@ extern "C" int64_t cirs_actor_workspace_bytes(int32_t n_rows, int32_t n_action) 
   int64_t splits = pick_split(n_rows, n_action);
   if (splits > n_tiles) splits = n_tiles;
   const int64_t ffma = (int64_t)sizeof(Partial) * (splits + 1) * (int64_t)(n_rows > 0 ? n_rows : 1) + 256;
-  const int64_t tc = cirs_head_tc::policy_eval_tc_workspace_bytes(n_rows > 0 ? n_rows : 1);
+  const int64_t ldA = ((int64_t)n_action + 127) & ~127LL;
+  const int64_t tc = cirs_head_tc::policy_eval_tc_workspace_bytes(n_rows > 0 ? n_rows : 1) +
+                     cirs_head_tc::policy_eval_tc_image_bytes(ldA);
   return ffma > tc ? ffma : tc;
 }
 

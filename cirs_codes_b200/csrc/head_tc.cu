@@ -3,8 +3,10 @@
 // the FP32-FFMA tile GEMMs  logits = h2 W3t + b3,  dW3t = h2^T dlogits,  dh2 = dlogits W3  and the [n, n_action]
 // logits round trip through HBM that they needed.
 //
-// All MMAs are M128 x N64 x K8 kind::tf32 with K-major operands, issued by one thread; every FP32 operand is staged
-// in shared memory as a (hi, lo) pair of TF32-exact tiles and each product is hi.hi + hi.lo + lo.hi (tc_dev.cuh).
+// All MMAs are M128 x N64 x K8 kind::tf32 with K-major operands, issued by one thread; every FP32 operand is a (hi, lo)
+// pair of TF32-exact tiles and each product is hi.hi + hi.lo + lo.hi (tc_dev.cuh).  W3 is split once per weight update
+// into tile images in global memory (head_tc_pack) that the passes copy into shared memory; h2 is split while staging;
+// d logits go back to TMEM as the A operand of the second MMA.
 // Thread t owns TMEM lane t % 128 (warp % 4 selects the lane quarter, as tcgen05.ld requires) and the column group
 // t / 128 of each 64-column accumulator: halves with 256 threads (pass F, two CTAs per SM), quarters with 512 threads
 // (passes B2 / B3, one CTA per SM) -- four resident warps per scheduler hide the epilogue's instruction latency.
@@ -56,13 +58,70 @@ struct SrcH2T {     // transposed: tile row = hidden index, tile column = row
     return r0 + c < r_end ? __ldg(h2 + (size_t)(r0 + c) * HID + r) : 0.f;
   }
 };
-struct SrcW3T {     // transposed: tile row = catalogue column c0 + r, tile column = hidden index
-  const float* w3t; int64_t ldA; int c0;
-  __device__ __forceinline__ float operator()(int r, int c) const { return __ldg(w3t + (size_t)c * ldA + c0 + r); }
-};
-struct SrcW3 {      // natural: tile row = hidden index, float4 chunks of catalogue columns
-  const float* w3t; int64_t ldA; int c0;
-  __device__ __forceinline__ float4 operator()(int r, int c4) const { return ld4(w3t + (size_t)r * ldA + c0 + 4 * c4); }
+// ---- pre-split operand-tile images of W3 --------------------------------------------------------------------
+// For every 64-column catalogue tile ct:   imgN[ct] = { hi, lo } of the tile laid out with tile row = column, tile
+// column = hidden (B operand of the logits MMA);  imgK[ct] = { hi, lo } with tile row = hidden, tile column = column
+// (B operand of the d h2 MMA).  For every 128-column tile: imgA = { hi, lo } with tile row = column (128), tile
+// column = hidden (A operand of pass B3's transposed logits MMA).  All in the exact shared-memory byte layout.
+constexpr int64_t IMG_B = 2 * (B_BYTES / 4);   // floats per (hi, lo) pair of a 64-row tile
+constexpr int64_t IMG_A = 2 * (A_BYTES / 4);   // ... of a 128-row tile
+__host__ __device__ inline int64_t img_n_off(int64_t ct) { return ct * IMG_B; }
+__host__ __device__ inline int64_t img_k_off(int64_t n64, int64_t ct) { return n64 * IMG_B + ct * IMG_B; }
+__host__ __device__ inline int64_t img_a_off(int64_t n64, int64_t c128) { return 2 * n64 * IMG_B + c128 * IMG_A; }
+
+__global__ void __launch_bounds__(256)
+head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, float* __restrict__ img) {
+  __shared__ float s[HID][TN + 1];   // s[k][col]
+  const int ct = blockIdx.x, tid = threadIdx.x, c0 = ct * TN;
+  const int64_t n64 = ldA / TN;
+  for (int i = tid; i < HID * TN / 4; i += 256) {
+    const int k = i / (TN / 4), c4 = i % (TN / 4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w3t + (size_t)k * ldA + c0) + c4);
+    s[k][4 * c4] = v.x; s[k][4 * c4 + 1] = v.y; s[k][4 * c4 + 2] = v.z; s[k][4 * c4 + 3] = v.w;
+  }
+  __syncthreads();
+  float4* n_hi = reinterpret_cast<float4*>(img + img_n_off(ct));
+  float4* n_lo = n_hi + B_BYTES / 16;
+  float4* k_hi = reinterpret_cast<float4*>(img + img_k_off(n64, ct));
+  float4* k_lo = k_hi + B_BYTES / 16;
+  float4* a_hi = reinterpret_cast<float4*>(img + img_a_off(n64, ct >> 1));
+  float4* a_lo = a_hi + A_BYTES / 16;
+  auto split4 = [](float4 v, float4& h, float4& l) {
+    h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+  };
+  for (int i = tid; i < HID * TN / 4; i += 256) {
+    // 16-byte chunk i of a 64-row tile: chunk column c4 = i / 64, tile row r = i % 64 (tile_chunk_off)
+    const int c4 = i / TN, r = i % TN;
+    float4 h, l;
+    split4(make_float4(s[4 * c4][r], s[4 * c4 + 1][r], s[4 * c4 + 2][r], s[4 * c4 + 3][r]), h, l);   // row = column r
+    n_hi[i] = h; n_lo[i] = l;
+    const int ia = c4 * TM + (ct & 1) * TN + r;                                                     // 128-row tile
+    a_hi[ia] = h; a_lo[ia] = l;
+    split4(make_float4(s[r][4 * c4], s[r][4 * c4 + 1], s[r][4 * c4 + 2], s[r][4 * c4 + 3]), h, l);   // row = hidden r
+    k_hi[i] = h; k_lo[i] = l;
+  }
+}
+
+// (hi, lo) image pair of one operand tile: global -> registers (early) -> shared (late), plain 16-byte copies
+template <int TILE_BYTES, int NTHREADS>
+struct TileImg {
+  static constexpr int STEPS = TILE_BYTES / 16 / NTHREADS;
+  static_assert(TILE_BYTES / 16 % NTHREADS == 0, "tile / thread count");
+  float4 h[STEPS], l[STEPS];
+  __device__ __forceinline__ void load(int tid, const float* pair) {
+    const float4* ph = reinterpret_cast<const float4*>(pair);
+    const float4* pl = ph + TILE_BYTES / 16;
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) { h[i] = __ldg(ph + tid + i * NTHREADS); l[i] = __ldg(pl + tid + i * NTHREADS); }
+  }
+  __device__ __forceinline__ void store(char* hi, char* lo, int tid) const {
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) {
+      reinterpret_cast<float4*>(hi)[tid + i * NTHREADS] = h[i];
+      reinterpret_cast<float4*>(lo)[tid + i * NTHREADS] = l[i];
+    }
+  }
 };
 
 __global__ void __launch_bounds__(NT, 2)
@@ -89,11 +148,11 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
     ta.load(tid, SrcH2{H.h2, r0, H.n});
     ta.store(a_hi, a_lo, tid);
   }
-  TileT<TN, HID, NT> tb_;     // the NEXT catalogue tile of W3, prefetched into registers
+  TileImg<B_BYTES, NT> tb_;   // the NEXT catalogue tile of W3 (pre-split image), prefetched into registers
   float b3n = 0.f;
   auto prefetch = [&](int ct) {
     const int c0 = ct * TN;
-    tb_.load(tid, SrcW3T{H.w3t, H.ldA, c0});
+    tb_.load(tid, H.img + img_n_off(ct));
     b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : MASKED;
   };
   if (ct0 < ct1) prefetch(ct0);
@@ -226,16 +285,17 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   // Register prefetch, one tile ahead of use: ``tn`` (transposed W3 tile, B of MMA1) holds tile t+1 while tile t is in
   // its epilogue; ``tk`` (natural W3 tile, B of MMA2) lags one tile behind it, because MMA2(t) is only issued after the
   // epilogue of tile t -- which lets its single shared buffer be rewritten late, after MMA2(t-1) has long finished.
-  TileT<TN, HID, NTB> tn;
-  TileV<HID, TN, NTB> tk;
+  TileImg<B_BYTES, NTB> tn;
+  TileImg<B_BYTES, NTB> tk;
+  const int64_t n64 = H.ldA / TN;
   float b3n = 0.f;
   auto load_n = [&](int t) {
     if (!worker) return;
     const int c0 = (ct0 + t) * TN;
-    tn.load(tid, SrcW3T{H.w3t, H.ldA, c0});
+    tn.load(tid, H.img + img_n_off(ct0 + t));
     b3n = (tid < TN && c0 + tid < H.nA) ? __ldg(H.b3 + c0 + tid) : MASKED;
   };
-  auto load_k = [&](int t) { if (worker) tk.load(tid, SrcW3{H.w3t, H.ldA, (ct0 + t) * TN}); };
+  auto load_k = [&](int t) { if (worker) tk.load(tid, H.img + img_k_off(n64, ct0 + t)); };
   auto stage_n = [&](int b) {
     if (!worker) return;
     tn.store(bn + 2 * b * B_BYTES, bn + (2 * b + 1) * B_BYTES, tid);
@@ -347,8 +407,8 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2, 1); mbar_fence_init(); }
   if (worker) {
-    TileT<TM, HID, NTB> tw;
-    tw.load(tid, SrcW3T{H.w3t, H.ldA, c0});
+    TileImg<A_BYTES, NTB> tw;
+    tw.load(tid, H.img + img_a_off(H.ldA / TN, blockIdx.x));
     tw.store(wa_hi, wa_lo, tid);
   }
   // register prefetch as in pass B2: ``tv`` (natural h2 tile, B of MMA1') one tile ahead, ``tt`` (transposed, B of MMA3)
@@ -465,6 +525,17 @@ void tiles_for(int nA, int n_split, int* tiles_per_split) {
   *tiles_per_split = (n_tiles + n_split - 1) / n_split;
 }
 }  // namespace
+
+int64_t head_tc_image_floats(int64_t ldA) {
+  const int64_t n64 = ldA / TN;
+  return 2 * n64 * IMG_B + (n64 / 2) * IMG_A;
+}
+
+int head_tc_pack(const float* w3t, int64_t ldA, float* img, cudaStream_t st) {
+  CIRS_LAUNCH(head_tc_pack_kernel, (int)(ldA / TN), 256, 0, st, w3t, ldA, img);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
 
 int plan_split(int n, int nA) {
   const int n_tiles = (nA + TN - 1) / TN, row_tiles = (n + TM - 1) / TM;

@@ -24,7 +24,15 @@ struct HeadTc {
   int64_t ldA;
   const float* b3;      // [nA]
   int nA;
+  // W3 pre-split into TF32 (hi, lo) operand-tile images (head_tc_pack): the passes copy them into shared memory
+  // instead of splitting / transposing W3 again for every tile of every CTA
+  const float* img;     // head_tc_image_floats(ldA) floats
 };
+
+// floats of the image buffer for a catalogue padded to ldA columns
+int64_t head_tc_image_floats(int64_t ldA);
+// (re)build the images from w3t; call after every change of the weights (once per minibatch / evaluation)
+int head_tc_pack(const float* w3t, int64_t ldA, float* img, cudaStream_t st);
 
 // number of catalogue splits used for n rows (<= MAX_SPLIT); partial arrays are [n, n_split]
 int plan_split(int n, int nA);
@@ -46,6 +54,7 @@ int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const fl
 
 // cirs_policy_eval (values + log-probs of stored actions, process_fn) through trunk -> pass F -> merge (ppo.cu)
 int64_t policy_eval_tc_workspace_bytes(int64_t n);
+int64_t policy_eval_tc_image_bytes(int64_t ldA);
 
 // true when the tensor-core path can be used for this shape (and CIRS_NO_TC is not set in the environment)
 bool head_tc_enabled(int n, int nA, int64_t ldA);

@@ -21,7 +21,7 @@ struct Workspace {
   float *h1, *h2, *value, *logits, *dh2, *dz2, *dz1, *rowm, *rinvz, *coef, *rowG, *dv, *terms;
   int32_t* acta;
   // tensor-core head (head_tc.cu): per-row partials over the catalogue splits
-  float *pm, *ps, *la, *ent_part, *dh2_part;
+  float *pm, *ps, *la, *ent_part, *dh2_part, *w3img;
 };
 constexpr int TC_SPLIT = cirs_head_tc::MAX_SPLIT;
 
@@ -37,6 +37,7 @@ Workspace carve(void* base, int64_t n, int64_t ldA) {
   w.acta = reinterpret_cast<int32_t*>(take(n));
   w.pm = take(n * TC_SPLIT); w.ps = take(n * TC_SPLIT); w.la = take(n); w.ent_part = take(n * TC_SPLIT);
   w.dh2_part = take(n * TC_SPLIT * HID);
+  w.w3img = take(cirs_head_tc::head_tc_image_floats(ldA < 128 ? 128 : ldA));
   return w;
 }
 
@@ -577,19 +578,25 @@ namespace cirs_head_tc {
 int64_t policy_eval_tc_workspace_bytes(int64_t n) {
   return (int64_t)sizeof(float) * (3 * align64(n * HID) / 1 + 2 * align64(n * MAX_SPLIT) + 2 * align64(n)) + 256;
 }
+int64_t policy_eval_tc_image_bytes(int64_t ldA) {
+  return (int64_t)sizeof(float) * align64(head_tc_image_floats(ldA < 128 ? 128 : ldA));
+}
 int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_idx, const float* obs,
                    const int32_t* act, float* value, float* logp, void* workspace, cudaStream_t st) {
   float* p = reinterpret_cast<float*>(workspace);
   auto take = [&](int64_t cnt) { float* r = p; p += align64(cnt); return r; };
   float *h1 = take((int64_t)n * HID), *h2 = take((int64_t)n * HID), *vtmp = take(n);
   float *pm = take((int64_t)n * MAX_SPLIT), *ps = take((int64_t)n * MAX_SPLIT), *la = take(n);
+  float* img = take(head_tc_image_floats(w->ld_action));
   CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, row_idx, obs, h1, h2, vtmp);
   CIRS_CHECK_LAUNCH();
   int n_split = 0;
   if (act) {   // log-probs of the stored actions; a value-only evaluation needs the trunk alone
     n_split = plan_split(n, w->n_action);
-    HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action};
-    const int rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
+    int rc = head_tc_pack(w->w3t, w->ld_action, img, st);
+    if (rc) return rc;
+    HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action, img};
+    rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
     if (rc) return rc;
   }
   CIRS_LAUNCH(eval_merge_kernel, (n + 255) / 256, 256, 0, st, n, n_split, row_idx, pm, ps, la, vtmp, value,
@@ -602,7 +609,8 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
 extern "C" int64_t cirs_ppo_workspace_bytes(int32_t n_rows, int32_t n_action) {
   const int64_t n = n_rows > 0 ? n_rows : 1, ldA = ((int64_t)n_action + 127) & ~127LL;
   int64_t cnt = 5 * align64(n * HID) + align64(n * ldA) + 7 * align64(n) + align64(4 * n) +
-                3 * align64(n * TC_SPLIT) + align64(n) + align64(n * TC_SPLIT * HID);
+                3 * align64(n * TC_SPLIT) + align64(n) + align64(n * TC_SPLIT * HID) +
+                align64(cirs_head_tc::head_tc_image_floats(ldA < 128 ? 128 : ldA));
   return cnt * (int64_t)sizeof(float) + 256;
 }
 
@@ -676,8 +684,10 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
     // ---- actor head on the tensor cores: logits are recomputed per pass and never stored (head_tc.cu)
     tc = true;
     tc_split = cirs_head_tc::plan_split(n, nA);
-    cirs_head_tc::HeadTc H{ws.h2, n, w->w3t, ldA, w->b3, nA};
-    int rc = cirs_head_tc::head_tc_stats(H, idx, act, tc_split, ws.pm, ws.ps, ws.la, st);
+    int rc = cirs_head_tc::head_tc_pack(w->w3t, ldA, ws.w3img, st);   // the weights changed in the last Adam step
+    if (rc) return rc;
+    cirs_head_tc::HeadTc H{ws.h2, n, w->w3t, ldA, w->b3, nA, ws.w3img};
+    rc = cirs_head_tc::head_tc_stats(H, idx, act, tc_split, ws.pm, ws.ps, ws.la, st);
     if (rc) return rc;
     CIRS_LAUNCH(row_loss_tc_kernel, (n + 127) / 128, 128, 0, st, n, tc_split, *cfg, n_global, idx, act, adv, returns,
                 v_old, logp_old, adv_stat, ws);
