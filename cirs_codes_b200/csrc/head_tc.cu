@@ -45,19 +45,6 @@ __device__ __forceinline__ void wait_or_flag(uint64_t* bar, uint32_t parity) {
 // ------------------------------------------------------------------------------------------------- pass F
 constexpr size_t F_SMEM = 2 * A_BYTES + 2 * B_BYTES + 64 * 4 + 2 * NT * 4;
 
-// operand sources (global memory)
-struct SrcH2 {      // rows [r0, r_end) of h2 as float4 chunks, zero beyond
-  const float* h2; int r0, r_end;
-  __device__ __forceinline__ float4 operator()(int r, int c4) const {
-    return r0 + r < r_end ? ld4(h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-};
-struct SrcH2T {     // transposed: tile row = hidden index, tile column = row
-  const float* h2; int r0, r_end;
-  __device__ __forceinline__ float operator()(int r, int c) const {
-    return r0 + c < r_end ? __ldg(h2 + (size_t)(r0 + c) * HID + r) : 0.f;
-  }
-};
 // ---- pre-split operand-tile images of W3 --------------------------------------------------------------------
 // For every 64-column catalogue tile ct:   imgN[ct] = { hi, lo } of the tile laid out with tile row = column, tile
 // column = hidden (B operand of the logits MMA);  imgK[ct] = { hi, lo } with tile row = hidden, tile column = column
@@ -103,6 +90,47 @@ head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, float* __restric
   }
 }
 
+// h2 [n, 64]: for every 64-row tile t  Hn[t] = { hi, lo } with tile row = row, tile column = hidden (B operand of pass
+// B3's logits MMA), Ht[t] = { hi, lo } with tile row = hidden, tile column = row (B operand of the d W3 MMA); for every
+// 128-row tile Ha = { hi, lo } with tile row = row (A operand of passes F / B2).  n64 = number of 64-row tiles (even).
+__host__ __device__ inline int64_t himg_n_off(int64_t t) { return t * IMG_B; }
+__host__ __device__ inline int64_t himg_t_off(int64_t n64, int64_t t) { return n64 * IMG_B + t * IMG_B; }
+__host__ __device__ inline int64_t himg_a_off(int64_t n64, int64_t t128) { return 2 * n64 * IMG_B + t128 * IMG_A; }
+__host__ __device__ inline int64_t h2_tiles64(int64_t n) { return 2 * ((n + TM - 1) / TM); }
+
+__global__ void __launch_bounds__(256)
+head_tc_pack_h2_kernel(const float* __restrict__ h2, int n, float* __restrict__ himg) {
+  __shared__ float s[TN][HID + 1];   // s[row][hidden]
+  const int t = blockIdx.x, tid = threadIdx.x, r0 = t * TN;
+  const int64_t n64 = h2_tiles64(n);
+  for (int i = tid; i < TN * HID / 4; i += 256) {
+    const int r = i / (HID / 4), c4 = i % (HID / 4);
+    const float4 v = r0 + r < n ? ld4(h2 + (size_t)(r0 + r) * HID + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s[r][4 * c4] = v.x; s[r][4 * c4 + 1] = v.y; s[r][4 * c4 + 2] = v.z; s[r][4 * c4 + 3] = v.w;
+  }
+  __syncthreads();
+  float4* n_hi = reinterpret_cast<float4*>(himg + himg_n_off(t));
+  float4* n_lo = n_hi + B_BYTES / 16;
+  float4* t_hi = reinterpret_cast<float4*>(himg + himg_t_off(n64, t));
+  float4* t_lo = t_hi + B_BYTES / 16;
+  float4* a_hi = reinterpret_cast<float4*>(himg + himg_a_off(n64, t >> 1));
+  float4* a_lo = a_hi + A_BYTES / 16;
+  auto split4 = [](float4 v, float4& h, float4& l) {
+    h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+  };
+  for (int i = tid; i < TN * HID / 4; i += 256) {
+    const int c4 = i / TN, r = i % TN;
+    float4 h, l;
+    split4(make_float4(s[r][4 * c4], s[r][4 * c4 + 1], s[r][4 * c4 + 2], s[r][4 * c4 + 3]), h, l);   // row = row r
+    n_hi[i] = h; n_lo[i] = l;
+    const int ia = c4 * TM + (t & 1) * TN + r;
+    a_hi[ia] = h; a_lo[ia] = l;
+    split4(make_float4(s[4 * c4][r], s[4 * c4 + 1][r], s[4 * c4 + 2][r], s[4 * c4 + 3][r]), h, l);   // row = hidden r
+    t_hi[i] = h; t_lo[i] = l;
+  }
+}
+
 // (hi, lo) image pair of one operand tile: global -> registers (early) -> shared (late), plain 16-byte copies
 template <int TILE_BYTES, int NTHREADS>
 struct TileImg {
@@ -144,8 +172,8 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   if (warp == 0) tmem_alloc(&tmem_base, 64);
   if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   {
-    TileV<TM, HID, NT> ta;
-    ta.load(tid, SrcH2{H.h2, r0, H.n});
+    TileImg<A_BYTES, NT> ta;
+    ta.load(tid, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x));
     ta.store(a_hi, a_lo, tid);
   }
   TileImg<B_BYTES, NT> tb_;   // the NEXT catalogue tile of W3 (pre-split image), prefetched into registers
@@ -278,8 +306,8 @@ head_tc_dh2_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   if (tid == 0) { mbar_init(&bar1[0], 1); mbar_init(&bar1[1], 1); mbar_init(&bar2, 1); mbar_fence_init(); }
   if (worker) {
-    TileV<TM, HID, NTB> ta;
-    ta.load(tid, SrcH2{H.h2, r0, H.n});
+    TileImg<A_BYTES, NTB> ta;
+    ta.load(tid, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x));
     ta.store(a_hi, a_lo, tid);
   }
   // Register prefetch, one tile ahead of use: ``tn`` (transposed W3 tile, B of MMA1) holds tile t+1 while tile t is in
@@ -413,21 +441,22 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   }
   // register prefetch as in pass B2: ``tv`` (natural h2 tile, B of MMA1') one tile ahead, ``tt`` (transposed, B of MMA3)
   // one tile behind it
-  TileV<TN, HID, NTB> tv;
-  TileT<HID, TN, NTB> tt;
+  TileImg<B_BYTES, NTB> tv;
+  TileImg<B_BYTES, NTB> tt;
+  const int64_t h64 = h2_tiles64(H.n);
   float n_rm = 0.f, n_iz = 0.f, n_cf = 0.f;
   int n_ac = -1;
   auto load_v = [&](int t) {
     if (!worker) return;
     const int r0 = rs0 + t * TN;
-    tv.load(tid, SrcH2{H.h2, r0, rs1});
+    tv.load(tid, H.himg + himg_n_off(r0 / TN));
     const bool ok = tid < TN && r0 + tid < rs1;
     n_rm = ok ? rowm[r0 + tid] : 0.f;
     n_iz = ok ? rinvz[r0 + tid] : 0.f;
     n_cf = ok ? coef[r0 + tid] : 0.f;
     n_ac = ok ? acta[r0 + tid] : -1;
   };
-  auto load_t = [&](int t) { if (worker) tt.load(tid, SrcH2T{H.h2, rs0 + t * TN, rs1}); };
+  auto load_t = [&](int t) { if (worker) tt.load(tid, H.himg + himg_t_off(h64, rs0 / TN + t)); };
   auto stage_v = [&](int b) {
     if (!worker) return;
     tv.store(hb + 2 * b * B_BYTES, hb + (2 * b + 1) * B_BYTES, tid);
@@ -533,6 +562,17 @@ int64_t head_tc_image_floats(int64_t ldA) {
 
 int head_tc_pack(const float* w3t, int64_t ldA, float* img, cudaStream_t st) {
   CIRS_LAUNCH(head_tc_pack_kernel, (int)(ldA / TN), 256, 0, st, w3t, ldA, img);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+
+int64_t head_tc_h2_image_floats(int64_t n) {
+  const int64_t n64 = h2_tiles64(n > 0 ? n : 1);
+  return 2 * n64 * IMG_B + (n64 / 2) * IMG_A;
+}
+
+int head_tc_pack_h2(const float* h2, int n, float* himg, cudaStream_t st) {
+  CIRS_LAUNCH(head_tc_pack_h2_kernel, (int)h2_tiles64(n), 256, 0, st, h2, n, himg);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }

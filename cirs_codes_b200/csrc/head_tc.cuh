@@ -27,12 +27,16 @@ struct HeadTc {
   // W3 pre-split into TF32 (hi, lo) operand-tile images (head_tc_pack): the passes copy them into shared memory
   // instead of splitting / transposing W3 again for every tile of every CTA
   const float* img;     // head_tc_image_floats(ldA) floats
+  const float* himg;    // the same for h2 (head_tc_pack_h2): head_tc_h2_image_floats(n) floats
 };
 
 // floats of the image buffer for a catalogue padded to ldA columns
 int64_t head_tc_image_floats(int64_t ldA);
 // (re)build the images from w3t; call after every change of the weights (once per minibatch / evaluation)
 int head_tc_pack(const float* w3t, int64_t ldA, float* img, cudaStream_t st);
+// images of the trunk output h2 [n, 64] (rows beyond n are zero); rebuilt once per minibatch after the trunk forward
+int64_t head_tc_h2_image_floats(int64_t n);
+int head_tc_pack_h2(const float* h2, int n, float* himg, cudaStream_t st);
 
 // number of catalogue splits used for n rows (<= MAX_SPLIT); partial arrays are [n, n_split]
 int plan_split(int n, int nA);

@@ -21,7 +21,7 @@ struct Workspace {
   float *h1, *h2, *value, *logits, *dh2, *dz2, *dz1, *rowm, *rinvz, *coef, *rowG, *dv, *terms;
   int32_t* acta;
   // tensor-core head (head_tc.cu): per-row partials over the catalogue splits
-  float *pm, *ps, *la, *ent_part, *dh2_part, *w3img;
+  float *pm, *ps, *la, *ent_part, *dh2_part, *w3img, *h2img;
 };
 constexpr int TC_SPLIT = cirs_head_tc::MAX_SPLIT;
 
@@ -38,6 +38,7 @@ Workspace carve(void* base, int64_t n, int64_t ldA) {
   w.pm = take(n * TC_SPLIT); w.ps = take(n * TC_SPLIT); w.la = take(n); w.ent_part = take(n * TC_SPLIT);
   w.dh2_part = take(n * TC_SPLIT * HID);
   w.w3img = take(cirs_head_tc::head_tc_image_floats(ldA < 128 ? 128 : ldA));
+  w.h2img = take(cirs_head_tc::head_tc_h2_image_floats(n));
   return w;
 }
 
@@ -576,7 +577,8 @@ int split_for(int tiles, int K, int bk) {
 // cirs_policy_eval on the tensor cores (dispatched from actor.cu): trunk -> pass F -> merge.
 namespace cirs_head_tc {
 int64_t policy_eval_tc_workspace_bytes(int64_t n) {
-  return (int64_t)sizeof(float) * (3 * align64(n * HID) / 1 + 2 * align64(n * MAX_SPLIT) + 2 * align64(n)) + 256;
+  return (int64_t)sizeof(float) * (3 * align64(n * HID) / 1 + 2 * align64(n * MAX_SPLIT) + 2 * align64(n) +
+                                   align64(head_tc_h2_image_floats(n))) + 256;
 }
 int64_t policy_eval_tc_image_bytes(int64_t ldA) {
   return (int64_t)sizeof(float) * align64(head_tc_image_floats(ldA < 128 ? 128 : ldA));
@@ -587,6 +589,7 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
   auto take = [&](int64_t cnt) { float* r = p; p += align64(cnt); return r; };
   float *h1 = take((int64_t)n * HID), *h2 = take((int64_t)n * HID), *vtmp = take(n);
   float *pm = take((int64_t)n * MAX_SPLIT), *ps = take((int64_t)n * MAX_SPLIT), *la = take(n);
+  float* himg = take(head_tc_h2_image_floats(n));
   float* img = take(head_tc_image_floats(w->ld_action));
   CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, row_idx, obs, h1, h2, vtmp);
   CIRS_CHECK_LAUNCH();
@@ -595,7 +598,9 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
     n_split = plan_split(n, w->n_action);
     int rc = head_tc_pack(w->w3t, w->ld_action, img, st);
     if (rc) return rc;
-    HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action, img};
+    rc = head_tc_pack_h2(h2, n, himg, st);
+    if (rc) return rc;
+    HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action, img, himg};
     rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
     if (rc) return rc;
   }
@@ -610,7 +615,8 @@ extern "C" int64_t cirs_ppo_workspace_bytes(int32_t n_rows, int32_t n_action) {
   const int64_t n = n_rows > 0 ? n_rows : 1, ldA = ((int64_t)n_action + 127) & ~127LL;
   int64_t cnt = 5 * align64(n * HID) + align64(n * ldA) + 7 * align64(n) + align64(4 * n) +
                 3 * align64(n * TC_SPLIT) + align64(n) + align64(n * TC_SPLIT * HID) +
-                align64(cirs_head_tc::head_tc_image_floats(ldA < 128 ? 128 : ldA));
+                align64(cirs_head_tc::head_tc_image_floats(ldA < 128 ? 128 : ldA)) +
+                align64(cirs_head_tc::head_tc_h2_image_floats(n));
   return cnt * (int64_t)sizeof(float) + 256;
 }
 
@@ -686,7 +692,9 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
     tc_split = cirs_head_tc::plan_split(n, nA);
     int rc = cirs_head_tc::head_tc_pack(w->w3t, ldA, ws.w3img, st);   // the weights changed in the last Adam step
     if (rc) return rc;
-    cirs_head_tc::HeadTc H{ws.h2, n, w->w3t, ldA, w->b3, nA, ws.w3img};
+    rc = cirs_head_tc::head_tc_pack_h2(ws.h2, n, ws.h2img, st);
+    if (rc) return rc;
+    cirs_head_tc::HeadTc H{ws.h2, n, w->w3t, ldA, w->b3, nA, ws.w3img, ws.h2img};
     rc = cirs_head_tc::head_tc_stats(H, idx, act, tc_split, ws.pm, ws.ps, ws.la, st);
     if (rc) return rc;
     CIRS_LAUNCH(row_loss_tc_kernel, (n + 127) / 128, 128, 0, st, n, tc_split, *cfg, n_global, idx, act, adv, returns,
