@@ -385,6 +385,34 @@ void linear_bwd_w(const float* X, int ldx, const float* dY, int ldy, float* gWt,
                              splitk(tiles, M), gb, st, "tracker_linear_dw_gemm");
 }
 
+// The weight-gradient GEMM of a layer (X^T dY) and the GEMM that propagates dY to the layer's input are independent:
+// both only read dY.  These small GEMMs fill a fraction of the GPU each (25-50 CTAs), so the weight-gradient one is
+// forked onto a side stream and joined again before dY's buffer can be reused.
+struct SideStream {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok() {
+    if (!side) {
+      if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) { side = nullptr; return false; }
+      cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+    }
+    return true;
+  }
+};
+SideStream g_side;
+
+template <class FW, class FX>
+void fork_join(cudaStream_t st, FW dw, FX dx) {
+  if (!g_side.ok()) { dw(st); dx(st); return; }
+  cudaEventRecord(g_side.fork, st);
+  cudaStreamWaitEvent(g_side.side, g_side.fork, 0);
+  dw(g_side.side);
+  dx(st);
+  cudaEventRecord(g_side.join, g_side.side);
+  cudaStreamWaitEvent(st, g_side.join, 0);
+}
+
 }  // namespace
 
 extern "C" int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_t n_env,
@@ -487,18 +515,18 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
     const float* xin = l == 0 ? b.x0 : b.layer[l - 1].x2;
     CIRS_LAUNCH(ln_bwd_kernel, ln_grid, 256, 0, st, M, d, b.da, y.r2, y.st2, Y.n2_w, b.db, Gy.n2_w, Gy.n2_b);  // db = dR2
     CIRS_CHECK_LAUNCH();
-    linear_bwd_w(y.h, dhid, b.db, d, Gy.l2_wt, ldd, Gy.l2_b, M, d, dhid, st);
-    linear_bwd_x(b.db, d, Y.l2_wt, ldd, b.dh, dhid, M, d, dhid, y.h, dhid, nullptr, 0, st);            // dh (relu mask)
-    linear_bwd_w(y.x1, d, b.dh, dhid, Gy.l1_wt, ldh, Gy.l1_b, M, dhid, d, st);
-    linear_bwd_x(b.dh, dhid, Y.l1_wt, ldh, b.da, d, M, dhid, d, nullptr, 0, b.db, d, st);              // da = dX1
+    fork_join(st, [&](cudaStream_t s2) { linear_bwd_w(y.h, dhid, b.db, d, Gy.l2_wt, ldd, Gy.l2_b, M, d, dhid, s2); },
+              [&](cudaStream_t s1) { linear_bwd_x(b.db, d, Y.l2_wt, ldd, b.dh, dhid, M, d, dhid, y.h, dhid, nullptr, 0, s1); });  // dh (relu mask)
+    fork_join(st, [&](cudaStream_t s2) { linear_bwd_w(y.x1, d, b.dh, dhid, Gy.l1_wt, ldh, Gy.l1_b, M, dhid, d, s2); },
+              [&](cudaStream_t s1) { linear_bwd_x(b.dh, dhid, Y.l1_wt, ldh, b.da, d, M, dhid, d, nullptr, 0, b.db, d, s1); });    // da = dX1
     CIRS_LAUNCH(ln_bwd_kernel, ln_grid, 256, 0, st, M, d, b.da, y.r1, y.st1, Y.n1_w, b.db, Gy.n1_w, Gy.n1_b);  // db = dR1
     CIRS_CHECK_LAUNCH();
-    linear_bwd_w(y.o, d, b.db, d, Gy.out_wt, ldd, Gy.out_b, M, d, d, st);
-    linear_bwd_x(b.db, d, Y.out_wt, ldd, b.dtmp, d, M, d, d, nullptr, 0, nullptr, 0, st);              // dtmp = dO
+    fork_join(st, [&](cudaStream_t s2) { linear_bwd_w(y.o, d, b.db, d, Gy.out_wt, ldd, Gy.out_b, M, d, d, s2); },
+              [&](cudaStream_t s1) { linear_bwd_x(b.db, d, Y.out_wt, ldd, b.dtmp, d, M, d, d, nullptr, 0, nullptr, 0, s1); });    // dtmp = dO
     CIRS_LAUNCH(attn_bwd_kernel, dim3(B, nh), ATT_WARPS * 32, att_smem, st, map, d, nh, ep_len, y.qkv, b.dtmp, b.dqkv);
     CIRS_CHECK_LAUNCH();
-    linear_bwd_w(xin, d, b.dqkv, 3 * d, Gy.in_wt, ld3, Gy.in_b, M, 3 * d, d, st);
-    linear_bwd_x(b.dqkv, 3 * d, Y.in_wt, ld3, b.da, d, M, 3 * d, d, nullptr, 0, b.db, d, st);          // da = dX_in
+    fork_join(st, [&](cudaStream_t s2) { linear_bwd_w(xin, d, b.dqkv, 3 * d, Gy.in_wt, ld3, Gy.in_b, M, 3 * d, d, s2); },
+              [&](cudaStream_t s1) { linear_bwd_x(b.dqkv, 3 * d, Y.in_wt, ld3, b.da, d, M, 3 * d, d, nullptr, 0, b.db, d, s1); });  // da = dX_in
   }
   // tokens: dZ -> dtmp, direct item gradient -> db
   CIRS_LAUNCH(token_bwd_kernel, M, 64, 0, st, W, map, ep_len, b.in, b.g, b.da, b.dtok0, b.dtmp, b.db);
