@@ -365,15 +365,127 @@ int splitk(int tiles, int K) {
   return s < 1 ? 1 : s;
 }
 
+// ---- one-shot linear kernel for the tracker's skinny GEMMs (K <= 128): Y[M, N] = ep(X[M, K] . Wop[K, N]).
+// The tile GEMM walks K in steps with a load -> sync -> compute round trip per step; for these shapes (a few thousand
+// rows, K and N of 32 .. 128) that chain IS the run time.  Here a CTA loads its 32 rows of X and the whole K x 128
+// weight block with every load in flight at once, synchronises once and computes from shared memory.
+//   B_TRANS = false: Wop[k][n] = W[k * ldw + n]   (forward: Wt k-major)
+//   B_TRANS = true : Wop[k][n] = W[n * ldw + k]   (input gradient: dX = dY . Wt^T)
+// Epilogue as StoreEp: + bias, relu, * [mask > 0], + residual.
+constexpr int SK_BM = 32, SK_BN = 128, SK_MAXK = 128, SK_LDX = SK_BM + 4, SK_LDW = SK_BN + 4;
+constexpr size_t SK_SMEM = sizeof(float) * (SK_MAXK * SK_LDX + SK_MAXK * SK_LDW);
+
+template <bool B_TRANS>
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                     const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int N, int K, int relu,
+                     const float* __restrict__ mask, int ldm, const float* __restrict__ res, int ldr) {
+  extern __shared__ __align__(16) float sk_smem[];
+  float* Xs = sk_smem;                       // [K][SK_LDX]  k-major: Xs[k][m]
+  float* Ws = sk_smem + SK_MAXK * SK_LDX;    // [K][SK_LDW]  Ws[k][n]
+  const int tid = threadIdx.x, m0 = blockIdx.x * SK_BM, n0 = blockIdx.y * SK_BN;
+  const int nc = min(SK_BN, N - n0);         // columns of this CTA
+  const int k4 = K >> 2;
+  for (int i = tid; i < SK_BM * k4; i += 256) {     // X tile, transposed into Xs[k][m]
+    const int m = i / k4, c = i % k4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + m < M) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m0 + m) * ldx) + c);
+    Xs[(4 * c) * SK_LDX + m] = v.x; Xs[(4 * c + 1) * SK_LDX + m] = v.y;
+    Xs[(4 * c + 2) * SK_LDX + m] = v.z; Xs[(4 * c + 3) * SK_LDX + m] = v.w;
+  }
+  if (!B_TRANS) {
+    const int n4 = (nc + 3) >> 2;
+    for (int i = tid; i < K * n4; i += 256) {
+      const int k = i / n4, c = i % n4;
+      *reinterpret_cast<float4*>(Ws + k * SK_LDW + 4 * c) =
+          __ldg(reinterpret_cast<const float4*>(W + (size_t)k * ldw + n0) + c);   // ldw is padded to 32: in bounds
+    }
+  } else {
+    for (int i = tid; i < nc * k4; i += 256) {
+      const int n = i / k4, c = i % k4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + n) * ldw) + c);
+      Ws[(4 * c) * SK_LDW + n] = v.x; Ws[(4 * c + 1) * SK_LDW + n] = v.y;
+      Ws[(4 * c + 2) * SK_LDW + n] = v.z; Ws[(4 * c + 3) * SK_LDW + n] = v.w;
+    }
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;    // 4 rows (ty) x 4 columns (tx) per thread
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  if (4 * tx < nc) {
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(Xs + k * SK_LDX + 4 * ty);
+      const float4 b = *reinterpret_cast<const float4*>(Ws + k * SK_LDW + 4 * tx);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[i][0] = fmaf(av[i], b.x, acc[i][0]);
+        acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(av[i], b.z, acc[i][2]);
+        acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + 4 * ty + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + 4 * tx + j;
+        if (n >= N) continue;
+        float v = acc[i][j];
+        if (bias) v += __ldg(bias + n);
+        if (relu) v = fmaxf(v, 0.f);
+        if (mask && !(mask[(size_t)m * ldm + n] > 0.f)) v = 0.f;
+        if (res) v += res[(size_t)m * ldr + n];
+        Y[(size_t)m * ldy + n] = v;
+      }
+    }
+  }
+}
+
+// true when the one-shot kernel handles the shape (16-byte aligned rows, K a multiple of 4 and <= 128)
+inline bool skinny_ok(const void* X, int ldx, const void* W, int ldw, int K) {
+  return K >= 4 && K <= SK_MAXK && (K & 3) == 0 && (ldx & 3) == 0 && (ldw & 3) == 0 &&
+         ((uintptr_t)X & 15) == 0 && ((uintptr_t)W & 15) == 0;
+}
+template <bool B_TRANS>
+void launch_skinny(const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y, int ldy, int M, int N,
+                   int K, int relu, const float* mask, int ldm, const float* res, int ldr, cudaStream_t st,
+                   const char* tag) {
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(skinny_linear_kernel<B_TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM);
+    once = true;
+  }
+  dim3 grid((M + SK_BM - 1) / SK_BM, (N + SK_BN - 1) / SK_BN);
+  const bool prof = cirs_profile_begin(tag, st);
+  skinny_linear_kernel<B_TRANS><<<grid, 256, SK_SMEM, st>>>(X, ldx, W, ldw, bias, Y, ldy, M, N, K, relu, mask, ldm, res,
+                                                             ldr);
+  cirs_note_launch();
+  if (prof) cirs_profile_end(st);
+}
+
 // Y[M,N] = X[M,K] Wt[K][ldw] + b (+ relu) (+ res)
 void linear_fwd(const float* X, int ldx, const float* Wt, int ldw, const float* b, float* Y, int ldy, int M, int N,
                 int K, int relu, const float* res, int ldr, cudaStream_t st) {
+  if (skinny_ok(X, ldx, Wt, ldw, K)) {
+    launch_skinny<false>(X, ldx, Wt, ldw, b, Y, ldy, M, N, K, relu, nullptr, 0, res, ldr, st, "tracker_linear_fwd_gemm");
+    return;
+  }
   launch_gemm<64, 64, 32, 4>(RowMajorA{X, ldx, nullptr}, RowMajorB{Wt, ldw, nullptr},
                              StoreEp{Y, ldy, b, relu, nullptr, nullptr, 0, res, ldr}, M, N, K, 1, nullptr, st, "tracker_linear_fwd_gemm");
 }
 // dX[M,K] = dY[M,N] Wt^T (* mask) (+ res)
 void linear_bwd_x(const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int N, int K,
                   const float* mask, int ldm, const float* res, int ldr, cudaStream_t st) {
+  // dX[m][kk] = sum_n dY[m][n] Wt[kk][n]: contraction over N (the layer's outputs), K_in outputs per row
+  if (skinny_ok(dY, ldy, Wt, ldw, N)) {
+    launch_skinny<true>(dY, ldy, Wt, ldw, nullptr, dX, ldx, M, K, N, 0, mask, ldm, res, ldr, st, "tracker_linear_dx_gemm");
+    return;
+  }
   launch_gemm<64, 64, 32, 4>(RowMajorA{dY, ldy, nullptr}, ColMajorB{Wt, ldw},
                              StoreEp{dX, ldx, nullptr, 0, nullptr, mask, ldm, res, ldr}, M, K, N, 1, nullptr, st, "tracker_linear_dx_gemm");
 }
