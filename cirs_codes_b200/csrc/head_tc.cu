@@ -55,12 +55,15 @@ constexpr int64_t IMG_A = 2 * (A_BYTES / 4);   // ... of a 128-row tile
 __host__ __device__ inline int64_t img_n_off(int64_t ct) { return ct * IMG_B; }
 __host__ __device__ inline int64_t img_k_off(int64_t n64, int64_t ct) { return n64 * IMG_B + ct * IMG_B; }
 __host__ __device__ inline int64_t img_a_off(int64_t n64, int64_t c128) { return 2 * n64 * IMG_B + c128 * IMG_A; }
+__host__ __device__ inline int64_t img_bias_off(int64_t n64) { return 2 * n64 * IMG_B + (n64 / 2) * IMG_A; }   // [ldA] bias, MASKED padding
 
 __global__ void __launch_bounds__(256)
-head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, float* __restrict__ img) {
+head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, const float* __restrict__ b3, int nA,
+                    float* __restrict__ img) {
   __shared__ float s[HID][TN + 1];   // s[k][col]
   const int ct = blockIdx.x, tid = threadIdx.x, c0 = ct * TN;
   const int64_t n64 = ldA / TN;
+  if (tid < TN) img[img_bias_off(n64) + c0 + tid] = c0 + tid < nA ? __ldg(b3 + c0 + tid) : MASKED;
   for (int i = tid; i < HID * TN / 4; i += 256) {
     const int k = i / (TN / 4), c4 = i % (TN / 4);
     const float4 v = __ldg(reinterpret_cast<const float4*>(w3t + (size_t)k * ldA + c0) + c4);
@@ -245,6 +248,128 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   }
   if (found) la[r0 + row] = lav;
   if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------------- pass F, TMA-fed
+// Warp-specialised variant of pass F.  Warps 0-7 (256 threads) only run epilogues; warp 8's lane 0 is the
+// producer + MMA issuer: it moves the pre-split operand images (h2 row tile once, one W3 tile + its bias per catalogue
+// tile) into shared memory with cp.async.bulk (1-D TMA, completion counted in bytes on an mbarrier), issues the
+// 24 MMAs of a tile into one of two TMEM accumulators and re-arms the copy of the next tile as soon as the MMA that
+// read the previous one has completed.  The workers never touch W3 and there is no CTA-wide barrier in the loop:
+//   tma_b     (tx count)   copy of tile t landed            issuer waits
+//   mma[b]    (commit)     accumulator b holds tile t       workers wait
+//   dfree[b]  (8 arrivals) workers have read accumulator b and bias buffer b of tile t into registers   issuer waits
+constexpr int NTF = NT + 32;
+constexpr size_t FT_SMEM = 2 * A_BYTES + 2 * B_BYTES + 2 * 64 * 4 + 2 * NT * 4;
+
+__global__ void __launch_bounds__(NTF, 2)
+head_tc_stats_tma_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act,
+                         int tiles_per_split, int n_split, float* __restrict__ pm, float* __restrict__ ps,
+                         float* __restrict__ la) {
+  extern __shared__ __align__(1024) char smem[];
+  char* a_hi = smem;
+  char* a_lo = a_hi + A_BYTES;
+  char* b_hi = a_lo + A_BYTES;
+  char* b_lo = b_hi + B_BYTES;
+  float* sb3 = reinterpret_cast<float*>(b_lo + B_BYTES);   // 2 x 64
+  float* sm = sb3 + 128;
+  float* ss = sm + NT;
+  __shared__ __align__(8) uint64_t tma_a, tma_b, mma[2], dfree[2];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, half = (tid >> 7) & 1;
+  const bool worker = tid < NT, issuer = tid == NT;
+  const int r0 = blockIdx.x * TM, split = blockIdx.y;
+  const int n_tiles = (H.nA + TN - 1) / TN;
+  const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
+  const int64_t n64 = H.ldA / TN;
+  if (warp == 0) tmem_alloc(&tmem_base, 128);
+  if (tid == 0) {
+    mbar_init(&tma_a, 1); mbar_init(&tma_b, 1); mbar_init(&mma[0], 1); mbar_init(&mma[1], 1);
+    mbar_init(&dfree[0], NT / 32); mbar_init(&dfree[1], NT / 32);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (issuer) {
+    auto copy_tile = [&](int t) {   // W3 image (hi, lo are adjacent: one 32 KB copy) + 64 bias values of tile t
+      const int ct = ct0 + t;
+      mbar_expect_tx(&tma_b, 2 * B_BYTES + 64 * 4);
+      bulk_g2s(b_hi, H.img + img_n_off(ct), 2 * B_BYTES, &tma_b);
+      bulk_g2s(sb3 + 64 * (t & 1), H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_b);
+    };
+    if (T > 0) {
+      mbar_expect_tx(&tma_a, 2 * A_BYTES);
+      bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
+      copy_tile(0);
+      wait_or_flag(&tma_a, 0);
+    }
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      wait_or_flag(&tma_b, t & 1);                                  // tile t and its bias are in shared memory
+      if (t >= 2) wait_or_flag(&dfree[b], ((t - 2) >> 1) & 1);      // accumulator b was read by epilogue(t-2)
+      fence_after_sync();
+      issue(tb + 64u * b, a_hi, a_lo, b_hi, b_lo, false);
+      mma_commit(&mma[b]);
+      if (t + 1 < T) {
+        wait_or_flag(&mma[b], (t >> 1) & 1);                        // MMA(t) no longer reads the B tile
+        if (t >= 1) wait_or_flag(&dfree[b ^ 1], ((t - 1) >> 1) & 1);   // bias buffer (t+1)&1 was read by epilogue(t-1)
+        copy_tile(t + 1);
+      }
+    }
+  }
+  int a = -1;
+  if (worker && act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
+  float m = MASKED, s = 0.f, lav = 0.f;
+  bool found = false;
+  if (worker) {
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, cb = (ct0 + t) * TN + half * 32;
+      wait_or_flag(&mma[b], (t >> 1) & 1);
+      fence_after_sync();
+      float v[32];
+      tmem_ld32(tmem_addr(tb + 64u * b, (warp & 3) * 32, half * 32), v);
+      float mt = MASKED;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = v[j] + sb3[64 * b + half * 32 + j];   // padding columns carry the MASKED bias
+        v[j] = x;
+        mt = fmaxf(mt, x);
+      }
+      // accumulator b and bias buffer b are in registers now: hand them back to the issuer (one arrival per warp)
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dfree[b]);
+      if (a >= cb && a < cb + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j == a - cb) lav = v[j];
+        found = true;
+      }
+      if (mt > 0.5f * MASKED) {
+        const float mn = fmaxf(m, mt);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += fast_exp(v[j] - mn);
+        s = s * fast_exp(m - mn) + acc;
+        m = mn;
+      }
+    }
+    sm[tid] = m;
+    ss[tid] = s;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (worker && half == 0 && r0 + row < H.n) {
+    const float m1 = sm[tid + TM], s1 = ss[tid + TM];
+    const float M = fmaxf(m, m1);
+    const float S = s * fast_exp(m - M) + s1 * fast_exp(m1 - M);   // an empty half has s == 0
+    pm[(size_t)(r0 + row) * n_split + split] = M;
+    ps[(size_t)(r0 + row) * n_split + split] = S;
+  }
+  if (found) la[r0 + row] = lav;
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------------- passes B2 / B3
@@ -557,11 +682,11 @@ void tiles_for(int nA, int n_split, int* tiles_per_split) {
 
 int64_t head_tc_image_floats(int64_t ldA) {
   const int64_t n64 = ldA / TN;
-  return 2 * n64 * IMG_B + (n64 / 2) * IMG_A;
+  return 2 * n64 * IMG_B + (n64 / 2) * IMG_A + ldA;
 }
 
-int head_tc_pack(const float* w3t, int64_t ldA, float* img, cudaStream_t st) {
-  CIRS_LAUNCH(head_tc_pack_kernel, (int)(ldA / TN), 256, 0, st, w3t, ldA, img);
+int head_tc_pack(const float* w3t, int64_t ldA, const float* b3, int nA, float* img, cudaStream_t st) {
+  CIRS_LAUNCH(head_tc_pack_kernel, (int)(ldA / TN), 256, 0, st, w3t, ldA, b3, nA, img);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }
@@ -599,10 +724,22 @@ bool head_tc_enabled(int n, int nA, int64_t ldA) {
 int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n_split, float* pm, float* ps,
                   float* la, cudaStream_t st) {
   static bool once = false;
-  if (!once) { set_smem(head_tc_stats_kernel, F_SMEM); once = true; }
+  static int use_tma = 1;
+  if (!once) {
+    set_smem(head_tc_stats_kernel, F_SMEM);
+    set_smem(head_tc_stats_tma_kernel, FT_SMEM);
+    const char* e = getenv("CIRS_NO_TMA");
+    use_tma = (e && e[0] && e[0] != '0') ? 0 : 1;
+    once = true;
+  }
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
+  if (use_tma) {   // warp-specialised pass F fed by cp.async.bulk (CIRS_NO_TMA=1 selects the register-staged kernel)
+    CIRS_LAUNCH(head_tc_stats_tma_kernel, grid, NTF, FT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
+    CIRS_CHECK_LAUNCH();
+    return CIRS_OK;
+  }
   CIRS_LAUNCH(head_tc_stats_kernel, grid, NT, F_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;

@@ -33,7 +33,7 @@ struct HeadTc {
 // floats of the image buffer for a catalogue padded to ldA columns
 int64_t head_tc_image_floats(int64_t ldA);
 // (re)build the images from w3t; call after every change of the weights (once per minibatch / evaluation)
-int head_tc_pack(const float* w3t, int64_t ldA, float* img, cudaStream_t st);
+int head_tc_pack(const float* w3t, int64_t ldA, const float* b3, int nA, float* img, cudaStream_t st);
 // images of the trunk output h2 [n, 64] (rows beyond n are zero); rebuilt once per minibatch after the trunk forward
 int64_t head_tc_h2_image_floats(int64_t n);
 int head_tc_pack_h2(const float* h2, int n, float* himg, cudaStream_t st);

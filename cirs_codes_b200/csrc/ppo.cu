@@ -596,7 +596,7 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
   int n_split = 0;
   if (act) {   // log-probs of the stored actions; a value-only evaluation needs the trunk alone
     n_split = plan_split(n, w->n_action);
-    int rc = head_tc_pack(w->w3t, w->ld_action, img, st);
+    int rc = head_tc_pack(w->w3t, w->ld_action, w->b3, w->n_action, img, st);
     if (rc) return rc;
     rc = head_tc_pack_h2(h2, n, himg, st);
     if (rc) return rc;
@@ -690,7 +690,7 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
     // ---- actor head on the tensor cores: logits are recomputed per pass and never stored (head_tc.cu)
     tc = true;
     tc_split = cirs_head_tc::plan_split(n, nA);
-    int rc = cirs_head_tc::head_tc_pack(w->w3t, ldA, ws.w3img, st);   // the weights changed in the last Adam step
+    int rc = cirs_head_tc::head_tc_pack(w->w3t, ldA, w->b3, nA, ws.w3img, st);   // the weights changed in the last Adam step
     if (rc) return rc;
     rc = cirs_head_tc::head_tc_pack_h2(ws.h2, n, ws.h2img, st);
     if (rc) return rc;
