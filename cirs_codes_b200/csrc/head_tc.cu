@@ -670,6 +670,268 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------- passes B2 / B3, TMA-fed
+// Same warp specialisation as pass F (TMA): warps 0-15 run epilogues only, lane 0 of warp 16 feeds the shared-memory
+// operand buffers with cp.async.bulk and issues both MMAs of a tile.  The tensor pipe executes MMAs in issue order
+// (MMA1(t+1) is issued before MMA2(t), MMA1(t+2) after it), so "MMA1(t+2) complete" implies "MMA2(t) complete": the
+// workers may overwrite the d-logits operand buffer b of tile t when they start tile t+2 without a barrier of its own.
+//   tma_n[b]  logits-MMA B tile (+ bias / row statistics) of tile t landed        issuer waits
+//   tma_k     second-MMA B tile of tile t landed                                   issuer waits
+//   mma1[b]   logits accumulator b holds tile t                                    workers wait
+//   dlr[b]    (16 arrivals) d logits of tile t are in TMEM buffer b; accumulator b, bias / statistics buffer b consumed
+//   mma2      second MMA of tile t complete (single B buffer free again)           issuer waits; workers at the end
+constexpr size_t B2T_SMEM = 2 * A_BYTES + 6 * B_BYTES + 2 * 64 * 4 + NTB * 4;
+
+__global__ void __launch_bounds__(NTB + 32, 1)
+head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
+                       const float* __restrict__ coef, const int32_t* __restrict__ acta, int tiles_per_split,
+                       int n_split, float* __restrict__ dh2_part, float* __restrict__ ent_part) {
+  extern __shared__ __align__(1024) char smem[];
+  char* a_hi = smem;                         // h2 tile (hi, lo adjacent)          (A of MMA1)
+  char* a_lo = a_hi + A_BYTES;
+  char* bn = a_lo + A_BYTES;                 // 2 x { W3 tile r = column, c = hidden: hi, lo }   (B of MMA1)
+  char* bk = bn + 4 * B_BYTES;               // 1 x { W3 tile r = hidden, c = column: hi, lo }   (B of MMA2)
+  float* sb3 = reinterpret_cast<float*>(bk + 2 * B_BYTES);   // 2 x 64
+  float* se = sb3 + 128;
+  __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k, mma1[2], mma2, dlr[2];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, qt = (tid >> 7) & 3;
+  const bool worker = tid < NTB, issuer = tid == NTB;
+  const int r0 = blockIdx.x * TM, split = blockIdx.y;
+  const int n_tiles = (H.nA + TN - 1) / TN;
+  const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
+  const int64_t n64 = H.ldA / TN;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&tma_a, 1); mbar_init(&tma_n[0], 1); mbar_init(&tma_n[1], 1); mbar_init(&tma_k, 1);
+    mbar_init(&mma1[0], 1); mbar_init(&mma1[1], 1); mbar_init(&mma2, 1);
+    mbar_init(&dlr[0], NTB / 32); mbar_init(&dlr[1], NTB / 32);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (issuer && T > 0) {
+    auto copy_n = [&](int t) {
+      const int ct = ct0 + t, b = t & 1;
+      mbar_expect_tx(&tma_n[b], 2 * B_BYTES + 64 * 4);
+      bulk_g2s(bn + 2 * b * B_BYTES, H.img + img_n_off(ct), 2 * B_BYTES, &tma_n[b]);
+      bulk_g2s(sb3 + 64 * b, H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_n[b]);
+    };
+    auto copy_k = [&](int t) {
+      mbar_expect_tx(&tma_k, 2 * B_BYTES);
+      bulk_g2s(bk, H.img + img_k_off(n64, ct0 + t), 2 * B_BYTES, &tma_k);
+    };
+    mbar_expect_tx(&tma_a, 2 * A_BYTES);
+    bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
+    copy_n(0);
+    copy_k(0);
+    wait_or_flag(&tma_a, 0);
+    wait_or_flag(&tma_n[0], 0);
+    fence_after_sync();
+    issue(tb + T_D1, a_hi, a_lo, bn, bn + B_BYTES, false);
+    mma_commit(&mma1[0]);
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, nb = b ^ 1;
+      if (t + 1 < T) {
+        if (t >= 1) {
+          wait_or_flag(&mma1[nb], ((t - 1) >> 1) & 1);   // MMA1(t-1) no longer reads bn[nb]
+          wait_or_flag(&dlr[nb], ((t - 1) >> 1) & 1);    // epilogue(t-1) consumed accumulator nb and bias buffer nb
+        }
+        copy_n(t + 1);
+        wait_or_flag(&tma_n[nb], ((t + 1) >> 1) & 1);
+        fence_after_sync();
+        issue(tb + T_D1 + 64u * nb, a_hi, a_lo, bn + 2 * nb * B_BYTES, bn + (2 * nb + 1) * B_BYTES, false);
+        mma_commit(&mma1[nb]);
+      }
+      if (t >= 1) {
+        wait_or_flag(&mma2, (t - 1) & 1);                // MMA2(t-1) no longer reads bk
+        copy_k(t);
+      }
+      wait_or_flag(&dlr[b], (t >> 1) & 1);               // d logits of tile t are in TMEM
+      wait_or_flag(&tma_k, t & 1);
+      fence_after_sync();
+      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk, bk + B_BYTES, t > 0);
+      mma_commit(&mma2);
+    }
+  }
+  const bool live = worker && r0 + row < H.n;
+  float ent = 0.f;
+  if (worker) {
+    const float rm = live ? rowm[r0 + row] : 0.f, iz = live ? rinvz[r0 + row] : 0.f, cf = live ? coef[r0 + row] : 0.f;
+    const int a = live ? acta[r0 + row] : -1;
+    const float log_z = iz > 0.f ? -logf(iz) : 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      wait_or_flag(&mma1[b], (t >> 1) & 1);
+      fence_after_sync();
+      float v[16];
+      tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
+      const int cb = (ct0 + t) * TN + qt * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float xm = v[j] + sb3[64 * b + qt * 16 + j] - rm;   // logit - max (padding columns: -1e30)
+        const float p = fast_exp(xm) * iz;
+        const float lg = fminf(fmaxf(xm - log_z, LOG_EPS), LOG_1M_EPS);
+        ent = fmaf(-p, lg, ent);
+        v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
+      }
+      store_dl(tb, b, (warp & 3) * 32, qt * 16, v);
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dlr[b]);
+      // follow every phase of mma2 in order (a parity wait is only unambiguous one phase at a time); MMA2(t-1) was
+      // issued a whole epilogue ago, so this does not stall
+      if (t >= 1) wait_or_flag(&mma2, (t - 1) & 1);
+    }
+    if (T > 0) {
+      wait_or_flag(&mma2, (T - 1) & 1);
+      fence_after_sync();
+      float v[16];
+      tmem_ld16(tmem_addr(tb + T_D2, (warp & 3) * 32, qt * 16), v);
+      if (live) {
+        float* dst = dh2_part + ((size_t)split * H.n + r0 + row) * HID + qt * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+    se[tid] = ent;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (qt == 0 && live)
+    ent_part[(size_t)(r0 + row) * n_split + split] = (ent + se[tid + TM]) + (se[tid + 2 * TM] + se[tid + 3 * TM]);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// pass B3, TMA-fed.  Row statistics of a 64-row tile (max, 1/Z, coef, action: four contiguous 256-byte slices of the
+// per-row arrays, which the caller pads with zeros / -1 up to a multiple of 64 rows) travel with the h2 tile.
+constexpr size_t B3T_SMEM = 2 * A_BYTES + 6 * B_BYTES + 2 * 4 * 64 * 4;
+
+__global__ void __launch_bounds__(NTB + 32, 1)
+head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
+                       const float* __restrict__ coef, const int32_t* __restrict__ acta, int rows_per_split,
+                       int n_rsplit, float* __restrict__ g_w3t, float* __restrict__ g_b3) {
+  extern __shared__ __align__(1024) char smem[];
+  char* wa_hi = smem;                        // W3 tile, r = column (128), c = hidden (hi, lo adjacent)   (A of MMA1')
+  char* wa_lo = wa_hi + A_BYTES;
+  char* hb = wa_lo + A_BYTES;                // 2 x { h2 tile r = row (64), c = hidden: hi, lo }   (B of MMA1')
+  char* ht = hb + 4 * B_BYTES;               // 1 x { h2 tile r = hidden, c = row: hi, lo }        (B of MMA3)
+  float* stats = reinterpret_cast<float*>(ht + 2 * B_BYTES);   // 2 x { max[64], 1/Z[64], coef[64], action[64] }
+  __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k, mma1[2], mma2, dlr[2];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cl = tid & 127, qt = (tid >> 7) & 3;
+  const bool worker = tid < NTB, issuer = tid == NTB;
+  const int c0 = blockIdx.x * TM, col = c0 + cl;
+  const int rs0 = blockIdx.y * rows_per_split, rs1 = min(H.n, rs0 + rows_per_split);
+  const int T = rs1 > rs0 ? (rs1 - rs0 + TN - 1) / TN : 0;
+  const int64_t h64 = h2_tiles64(H.n);
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&tma_a, 1); mbar_init(&tma_n[0], 1); mbar_init(&tma_n[1], 1); mbar_init(&tma_k, 1);
+    mbar_init(&mma1[0], 1); mbar_init(&mma1[1], 1); mbar_init(&mma2, 1);
+    mbar_init(&dlr[0], NTB / 32); mbar_init(&dlr[1], NTB / 32);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (issuer && T > 0) {
+    auto copy_n = [&](int t) {
+      const int r0 = rs0 + t * TN, b = t & 1;
+      float* sp = stats + 256 * b;
+      mbar_expect_tx(&tma_n[b], 2 * B_BYTES + 4 * 64 * 4);
+      bulk_g2s(hb + 2 * b * B_BYTES, H.himg + himg_n_off(r0 / TN), 2 * B_BYTES, &tma_n[b]);
+      bulk_g2s(sp, rowm + r0, 64 * 4, &tma_n[b]);
+      bulk_g2s(sp + 64, rinvz + r0, 64 * 4, &tma_n[b]);
+      bulk_g2s(sp + 128, coef + r0, 64 * 4, &tma_n[b]);
+      bulk_g2s(sp + 192, acta + r0, 64 * 4, &tma_n[b]);
+    };
+    auto copy_k = [&](int t) {
+      mbar_expect_tx(&tma_k, 2 * B_BYTES);
+      bulk_g2s(ht, H.himg + himg_t_off(h64, rs0 / TN + t), 2 * B_BYTES, &tma_k);
+    };
+    mbar_expect_tx(&tma_a, 2 * A_BYTES);
+    bulk_g2s(wa_hi, H.img + img_a_off(H.ldA / TN, blockIdx.x), 2 * A_BYTES, &tma_a);
+    copy_n(0);
+    copy_k(0);
+    wait_or_flag(&tma_a, 0);
+    wait_or_flag(&tma_n[0], 0);
+    fence_after_sync();
+    issue(tb + T_D1, wa_hi, wa_lo, hb, hb + B_BYTES, false);   // (logits tile)^T - b3: lane = column, 64 rows
+    mma_commit(&mma1[0]);
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, nb = b ^ 1;
+      if (t + 1 < T) {
+        if (t >= 1) {
+          wait_or_flag(&mma1[nb], ((t - 1) >> 1) & 1);
+          wait_or_flag(&dlr[nb], ((t - 1) >> 1) & 1);
+        }
+        copy_n(t + 1);
+        wait_or_flag(&tma_n[nb], ((t + 1) >> 1) & 1);
+        fence_after_sync();
+        issue(tb + T_D1 + 64u * nb, wa_hi, wa_lo, hb + 2 * nb * B_BYTES, hb + (2 * nb + 1) * B_BYTES, false);
+        mma_commit(&mma1[nb]);
+      }
+      if (t >= 1) {
+        wait_or_flag(&mma2, (t - 1) & 1);
+        copy_k(t);
+      }
+      wait_or_flag(&dlr[b], (t >> 1) & 1);
+      wait_or_flag(&tma_k, t & 1);
+      fence_after_sync();
+      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht, ht + B_BYTES, t > 0);   // D3 += d logits^T . h2
+      mma_commit(&mma2);
+    }
+  }
+  const bool live = worker && col < H.nA;
+  if (worker) {
+    const float b3v = live ? __ldg(H.b3 + col) : MASKED;
+    float db3 = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      wait_or_flag(&mma1[b], (t >> 1) & 1);
+      fence_after_sync();
+      const float* sp = stats + 256 * b;
+      float v[16];
+      tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int jj = qt * 16 + j;
+        const float p = fast_exp(v[j] + b3v - sp[jj]) * sp[64 + jj];   // padding columns / rows: bias -1e30 or 1/Z = 0
+        const float d = sp[128 + jj] * ((reinterpret_cast<const int*>(sp)[192 + jj] == col ? 1.f : 0.f) - p);
+        db3 += d;
+        v[j] = d;
+      }
+      store_dl(tb, b, (warp & 3) * 32, qt * 16, v);
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dlr[b]);
+      if (t >= 1) wait_or_flag(&mma2, (t - 1) & 1);   // follow every phase of mma2 in order
+    }
+    if (T > 0) {
+      wait_or_flag(&mma2, (T - 1) & 1);
+      fence_after_sync();
+      float v[16];
+      tmem_ld16(tmem_addr(tb + T_D2, (warp & 3) * 32, qt * 16), v);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float* dst = g_w3t + (size_t)(qt * 16 + j) * H.ldA + col;
+          if (n_rsplit > 1) atomicAdd(dst, v[j]); else *dst += v[j];
+        }
+        atomicAdd(g_b3 + col, db3);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 template <class K>
 void set_smem(K kernel, size_t bytes) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -712,30 +974,35 @@ int plan_split(int n, int nA) {
   return (n_tiles + per - 1) / per;
 }
 
-static int g_tc_mode = -1;   // -1: environment default (CIRS_NO_TC), 0: off, 1: on
+static int g_tc_mode = -1;   // -1: environment default (CIRS_NO_TC), 0: off, 1: on (TMA-fed kernels), 2: on, register-staged
+static bool tma_on() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("CIRS_NO_TMA");
+    env = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return env == 1 && g_tc_mode != 2;
+}
 bool head_tc_enabled(int n, int nA, int64_t ldA) {
   if (g_tc_mode < 0) {
     const char* e = getenv("CIRS_NO_TC");
     g_tc_mode = (e && e[0] && e[0] != '0') ? 0 : 1;
   }
-  return g_tc_mode == 1 && n > 0 && nA >= TN && (ldA % 128) == 0 && ldA >= nA;
+  return g_tc_mode >= 1 && n > 0 && nA >= TN && (ldA % 128) == 0 && ldA >= nA;
 }
 
 int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n_split, float* pm, float* ps,
                   float* la, cudaStream_t st) {
   static bool once = false;
-  static int use_tma = 1;
   if (!once) {
     set_smem(head_tc_stats_kernel, F_SMEM);
     set_smem(head_tc_stats_tma_kernel, FT_SMEM);
-    const char* e = getenv("CIRS_NO_TMA");
-    use_tma = (e && e[0] && e[0] != '0') ? 0 : 1;
     once = true;
   }
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
-  if (use_tma) {   // warp-specialised pass F fed by cp.async.bulk (CIRS_NO_TMA=1 selects the register-staged kernel)
+  if (tma_on()) {   // warp-specialised pass F fed by cp.async.bulk (CIRS_NO_TMA=1 selects the register-staged kernel)
     CIRS_LAUNCH(head_tc_stats_tma_kernel, grid, NTF, FT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
     CIRS_CHECK_LAUNCH();
     return CIRS_OK;
@@ -748,10 +1015,20 @@ int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n
 int head_tc_dh2(const HeadTc& H, const float* rowm, const float* rinvz, const float* coef, const int32_t* acta,
                 int n_split, float* dh2_part, float* ent_part, cudaStream_t st) {
   static bool once = false;
-  if (!once) { set_smem(head_tc_dh2_kernel, B2_SMEM); once = true; }
+  if (!once) {
+    set_smem(head_tc_dh2_kernel, B2_SMEM);
+    set_smem(head_tc_dh2_tma_kernel, B2T_SMEM);
+    once = true;
+  }
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
+  if (tma_on()) {
+    CIRS_LAUNCH(head_tc_dh2_tma_kernel, grid, NTB + 32, B2T_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part,
+                ent_part);
+    CIRS_CHECK_LAUNCH();
+    return CIRS_OK;
+  }
   CIRS_LAUNCH(head_tc_dh2_kernel, grid, NTB + 32, B2_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part, ent_part);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
@@ -760,7 +1037,11 @@ int head_tc_dh2(const HeadTc& H, const float* rowm, const float* rinvz, const fl
 int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const float* coef, const int32_t* acta,
                 float* g_w3t, float* g_b3, cudaStream_t st) {
   static bool once = false;
-  if (!once) { set_smem(head_tc_dw3_kernel, B3_SMEM); once = true; }
+  if (!once) {
+    set_smem(head_tc_dw3_kernel, B3_SMEM);
+    set_smem(head_tc_dw3_tma_kernel, B3T_SMEM);
+    once = true;
+  }
   const int n_ct = (H.nA + TM - 1) / TM, row_tiles = (H.n + TN - 1) / TN;
   int n_rsplit = (3 * 148 + n_ct - 1) / n_ct;
   if (n_rsplit > row_tiles) n_rsplit = row_tiles;
@@ -768,6 +1049,12 @@ int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   int tiles_per = (row_tiles + n_rsplit - 1) / n_rsplit;
   n_rsplit = (row_tiles + tiles_per - 1) / tiles_per;
   dim3 grid(n_ct, n_rsplit);
+  if (tma_on()) {   // needs the per-row arrays padded with zeros / -1 up to a multiple of 64 rows (row_loss_tc_kernel)
+    CIRS_LAUNCH(head_tc_dw3_tma_kernel, grid, NTB + 32, B3T_SMEM, st, H, rowm, rinvz, coef, acta, tiles_per * TN, n_rsplit,
+                g_w3t, g_b3);
+    CIRS_CHECK_LAUNCH();
+    return CIRS_OK;
+  }
   CIRS_LAUNCH(head_tc_dw3_kernel, grid, NTB + 32, B3_SMEM, st, H, rowm, rinvz, coef, acta, tiles_per * TN, n_rsplit, g_w3t,
               g_b3);
   CIRS_CHECK_LAUNCH();
@@ -776,7 +1063,7 @@ int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const fl
 
 }  // namespace cirs_head_tc
 
-extern "C" void cirs_head_tc_enable(int on) { cirs_head_tc::g_tc_mode = on < 0 ? -1 : (on ? 1 : 0); }
+extern "C" void cirs_head_tc_enable(int on) { cirs_head_tc::g_tc_mode = on < 0 ? -1 : (on > 2 ? 1 : on); }
 
 // debug: 1 if any tensor-core kernel gave up waiting on an mbarrier since the last call (synchronises the device)
 extern "C" int cirs_head_tc_timeout(void) {

@@ -367,7 +367,11 @@ row_loss_tc_kernel(int n, int n_split, cirs_ppo_config cfg, int n_global, const 
                    const float* __restrict__ v_old, const float* __restrict__ logp_old,
                    const double* __restrict__ adv_stat, Workspace ws) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+  if (r >= n) {
+    // rows up to the next multiple of 64: neutral statistics, so that pass B3 can bulk-copy whole 64-row slices
+    if (r < ((n + 63) & ~63)) { ws.rowm[r] = 0.f; ws.rinvz[r] = 0.f; ws.coef[r] = 0.f; ws.acta[r] = -1; }
+    return;
+  }
   const float* pm = ws.pm + (int64_t)r * n_split;
   const float* ps = ws.ps + (int64_t)r * n_split;
   float mx = -INFINITY;

@@ -37,9 +37,10 @@ int64_t cirs_launch_count(void);
  * cirs_profile_report synchronises the device and writes "kernel_name count total_ms" lines into buf. */
 void cirs_profile_enable(int on);
 int cirs_profile_report(char* buf, int n);
-/* Actor-head contractions of cirs_ppo_minibatch / cirs_policy_eval: 1 = tcgen05 tensor cores with 3xTF32 split
- * precision (default; csrc/head_tc.cu), 0 = FP32 FFMA tile GEMMs (csrc/gemm.cuh), -1 = default (environment variable
- * CIRS_NO_TC=1 selects FFMA).  Both are CUDA paths with the same results within the 1e-5 parity bar. */
+/* Actor-head contractions of cirs_ppo_minibatch / cirs_policy_eval / cirs_rollout_kuaishou: 1 = tcgen05 tensor cores
+ * with 3xTF32 split precision, warp-specialised kernels fed by cp.async.bulk (default; csrc/head_tc.cu), 2 = the same
+ * with register-staged operands (also CIRS_NO_TMA=1), 0 = FP32 FFMA tile GEMMs (csrc/gemm.cuh), -1 = default
+ * (environment variable CIRS_NO_TC=1 selects FFMA).  All are CUDA paths with the same results within the 1e-5 bar. */
 void cirs_head_tc_enable(int on);
 /* 1 if a tensor-core kernel gave up waiting on an mbarrier since the last call (synchronises; never expected). */
 int cirs_head_tc_timeout(void);

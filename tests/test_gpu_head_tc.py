@@ -38,7 +38,7 @@ def _minibatch(pol, n, seed, tc):
     d_obs = torch.zeros(n_slots, S, device=dev)
     losses = torch.zeros(4, device=dev)
     ws = torch.empty(lib.cirs_ppo_workspace_bytes(n, A), dtype=torch.uint8, device=dev)
-    lib.cirs_head_tc_enable(1 if tc else 0)
+    lib.cirs_head_tc_enable(int(tc))   # 0 FFMA, 1 tcgen05 + TMA-fed warp-specialised kernels, 2 tcgen05 register-staged
     try:
         _lib.call("cirs_ppo_minibatch", C.byref(pol._w), C.byref(pol._g), C.byref(pol.cfg), n, n, _lib.ptr(idx),
                   _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv), _lib.ptr(ret), _lib.ptr(v_old), _lib.ptr(logp_old),
@@ -86,10 +86,11 @@ def test_tc_minibatch_matches_ffma_and_fp64(H, n, I):
     # random (not near-uniform) logits: scale the head so that probabilities spread over several orders of magnitude
     seg = pol.layout.segs["actor.last.weight"]
     pol.flat[seg.offset:seg.offset + seg.size].mul_(8.0)
-    l_f, g_f, do_f, inp = _minibatch(pol, n, 3, tc=False)
-    l_t, g_t, do_t, _ = _minibatch(pol, n, 3, tc=True)
+    l_f, g_f, do_f, inp = _minibatch(pol, n, 3, tc=0)
+    l_t, g_t, do_t, _ = _minibatch(pol, n, 3, tc=1)
+    l_r, g_r, do_r, _ = _minibatch(pol, n, 3, tc=2)
     ref = _reference(pol, inp, n)
-    for name, l in (("ffma", l_f), ("tc", l_t)):
+    for name, l in (("ffma", l_f), ("tc", l_t), ("tc-register-staged", l_r)):
         G.assert_close(l[0], ref["loss"], 1e-5, 1e-6, what=f"{name} loss")
         G.assert_close(l[1], ref["clip"], 1e-5, 1e-6, what=f"{name} clip")
         G.assert_close(l[2], ref["vf"], 1e-5, what=f"{name} vf")
@@ -108,6 +109,7 @@ def test_tc_minibatch_matches_ffma_and_fp64(H, n, I):
     # and the two CUDA paths agree with each other at the same level
     scale = g_f.abs().max().item()
     assert (g_f - g_t).abs().max().item() <= 2e-5 * scale
+    assert (g_r - g_t).abs().max().item() <= 2e-5 * scale and (do_r - do_t).abs().max().item() <= 2e-5 * do_t.abs().max().item()
 
 
 def test_tc_policy_eval_matches_ffma(H):
