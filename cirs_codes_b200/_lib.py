@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcirs_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LAYERS = 4
 HIDDEN = 64
 
@@ -67,6 +67,13 @@ class PPOConfigStruct(C.Structure):
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float)]
 
 
+class UserModelStruct(C.Structure):
+    _fields_ = [(k, fp) for k in ("emb_user", "emb_item", "emb_feat", "lin_user", "lin_item", "lin_feat",
+                                  "lin_dense", "w1", "b1", "w2", "b2", "w_last")] + \
+               [("out_bias", C.c_float), ("emb_dim", C.c_int32), ("n_feat", C.c_int32), ("n_dense", C.c_int32),
+                ("hidden", C.c_int32)]
+
+
 i32, i64, u64, f64 = C.c_int32, C.c_int64, C.c_uint64, C.c_double
 P = C.POINTER
 
@@ -109,6 +116,10 @@ PROTOTYPES = {
                              fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp]),
     "cirs_head_tc_enable": (None, [i32]),
     "cirs_head_tc_timeout": (i32, []),
+    "cirs_user_model_workspace_bytes": (i64, [i32, i32, i32]),
+    "cirs_user_model_predict_all": (i32, [P(UserModelStruct), i32, fp, i32, fp, fp, fp, i32, fp, fp, fp, fp]),
+    "cirs_user_model_tc_enable": (None, [i32]),
+    "cirs_user_model_timeout": (i32, []),
     "cirs_clip_adam": (i32, [fp, fp, fp, fp, i64, i64, P(PPOConfigStruct), fp, fp, fp]),
 }
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CIRS_ABI_VERSION 6
+#define CIRS_ABI_VERSION 7
 #define CIRS_MAX_LAYERS 4
 #define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
 
@@ -368,6 +368,46 @@ int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grad
                    const void* act, const float* adv, const float* returns, const float* v_old,
                    const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats, float* losses,
                    int32_t* opt_state, double* opt_scratch, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ user model -> normed_mat ------------ */
+/* The DeepFM user model of stage 1 (UserModel_Pairwise, core/user_model_pairwise.py:36-132) with the feature columns
+ * of CIRS-UserModel-kuaishou.py:115-123: sparse user_id, photo_id, n_feat slots sharing ONE "feat" embedding table
+ * (padding row 0 = zeros), n_dense dense item features; dnn_hidden_units = (64, 64).  Tensors are in the reference's
+ * torch layout (Linear weight = [out][in]); cirs_codes_b200/user_model.py fills the struct from a state_dict. */
+typedef struct {
+  const float* emb_user;  /* [vocab_user, emb_dim]   embedding_dict.user_id.weight */
+  const float* emb_item;  /* [vocab_item, emb_dim]   embedding_dict.photo_id.weight */
+  const float* emb_feat;  /* [vocab_feat, emb_dim]   embedding_dict.feat.weight */
+  const float* lin_user;  /* [vocab_user]            linear.embedding_dict.user_id.weight (core/layers.py:20-73) */
+  const float* lin_item;  /* [vocab_item] */
+  const float* lin_feat;  /* [vocab_feat] */
+  const float* lin_dense; /* [n_dense]               linear.weight */
+  const float* w1;        /* [64][emb_dim * (2 + n_feat) + n_dense]   dnn.linears.0.weight; input order = user, item,
+                             feat slots, dense (combined_dnn_input) */
+  const float* b1;        /* [64] */
+  const float* w2;        /* [64][64]                dnn.linears.1.weight */
+  const float* b2;        /* [64] */
+  const float* w_last;    /* [64]                    last.weight (no bias, user_model_pairwise.py:66) */
+  float out_bias;         /* out.bias (PredictionLayer, task "regression": bias only) */
+  int32_t emb_dim, n_feat, n_dense, hidden;
+} cirs_user_model;
+
+/* KuaishouEnv.compute_normed_reward (environments/KuaishouRec/env/kuaishouEnv.py:113-145): predict every user in
+ * user_ids[n_user] (raw ids, lbe_user.classes_) on every item (item_ids[n_item] raw photo ids, item_feat[n_item,
+ * n_feat], item_dense[n_item, n_dense]: the rows of df_photo_env) with UserModel_Pairwise.forward
+ * (user_model_pairwise.py:98-132, 154-156), then, if normalise != 0, (pred - min) / (max - min) over the table.
+ *   out     float[n_user * n_item] row-major, 16-byte aligned; minmax (optional) float[2] = {min, max} of the raw
+ *           predictions.  Arithmetic is FP32 like the reference's torch path (normalisation in FP64 like numpy).
+ *   workspace  cirs_user_model_workspace_bytes(n_user, n_item, emb_dim) bytes, 16-byte aligned.
+ * The 64 x 64 hidden contraction runs on the tcgen05 tensor cores (3xTF32) for emb_dim in {8, 16, 32};
+ * cirs_user_model_tc_enable(0) selects the FP32-FFMA kernel (-1 = default, CIRS_NO_TC=1 also selects FFMA). */
+int64_t cirs_user_model_workspace_bytes(int32_t n_user, int32_t n_item, int32_t emb_dim);
+int cirs_user_model_predict_all(const cirs_user_model* m, int32_t n_user, const int32_t* user_ids, int32_t n_item,
+                                const int32_t* item_ids, const int32_t* item_feat, const float* item_dense,
+                                int32_t normalise, float* out, float* minmax, void* workspace, void* stream);
+void cirs_user_model_tc_enable(int on);
+/* 1 if the tensor-core kernel gave up waiting on an mbarrier since the last call (synchronises; never expected). */
+int cirs_user_model_timeout(void);
 
 #ifdef __cplusplus
 }

@@ -50,14 +50,14 @@ def test_struct_sizes_match_c_layout():
     prog = r'''
 #include <stdio.h>
 #include "cirs_b200.h"
-int main(void){printf("%zu %zu %zu %zu %zu\n", sizeof(cirs_kuaishou_env), sizeof(cirs_encoder_layer),
+int main(void){printf("%zu %zu %zu %zu %zu %zu\n", sizeof(cirs_user_model), sizeof(cirs_kuaishou_env), sizeof(cirs_encoder_layer),
   sizeof(cirs_tracker_weights), sizeof(cirs_policy_weights), sizeof(cirs_ppo_config)); return 0;}'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(prog)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o",
                         os.path.join(d, "t")], check=True)
         got = [int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True).stdout.split()]
-    want = [ctypes.sizeof(s) for s in (_lib.KuaishouEnvStruct, _lib.EncoderLayerStruct, _lib.TrackerWeightsStruct,
+    want = [ctypes.sizeof(s) for s in (_lib.UserModelStruct, _lib.KuaishouEnvStruct, _lib.EncoderLayerStruct, _lib.TrackerWeightsStruct,
                                        _lib.PolicyWeightsStruct, _lib.PPOConfigStruct)]
     assert got == want
 

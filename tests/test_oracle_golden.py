@@ -218,3 +218,17 @@ def test_replay_reference_run_taobao(name):
             if k.endswith("in_proj_bias"):
                 mine, ref = G.drop_key_bias(mine), G.drop_key_bias(ref)
             G.assert_close(mine, ref, 1e-5, G.PARAM_ATOL, what=f"tracker param {k}")
+
+
+def test_user_model_oracle_vs_golden():
+    """oracle/user_model.py against the reference's own UserModel_Pairwise.forward / KuaishouEnv.compute_normed_reward
+    outputs (tests/golden/user_model_deepfm.npz, recorded by oracle/make_golden_user_model.py)."""
+    import os
+    from oracle import user_model as um
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "user_model_deepfm.npz"))
+    P = {k[3:]: g[k] for k in g.files if k.startswith("sd.")}
+    pm = um.predict_mat(P, g["users"], g["items"], g["item_feat"], g["item_dense"])
+    np.testing.assert_allclose(pm[g["raw_rows"]], g["raw_pred"], rtol=1e-5, atol=1e-5)
+    nm = um.compute_normed_reward(P, g["users"], g["items"], g["item_feat"], g["item_dense"])
+    assert nm.min() == 0.0 and nm.max() == 1.0
+    np.testing.assert_allclose(nm, g["normed_mat"], rtol=1e-5, atol=1e-6)
