@@ -29,13 +29,18 @@ namespace cirs_um {
 using namespace cirs_tc;
 
 constexpr int HID = CIRS_HIDDEN, TM = 128, NT = 256;
-constexpr uint32_t A_BYTES = TM * HID * 4;    // 128-row operand tile, 32 KB
-constexpr uint32_t B_BYTES = HID * HID * 4;   // W2 operand tile, 16 KB
-constexpr uint32_t A_LBO = TM * 16, A_STEP = 2 * TM * 16;
+constexpr int KB = HID + 8;                   // contraction depth incl. the bias k-step: h1 | 1 0 0 0 0 0 0 0
+constexpr uint32_t B_BYTES = HID * KB * 4;    // operand tile of [W2 | b2 | 0..]: 64 rows x 72 columns, 18 KB
 constexpr uint32_t B_LBO = HID * 16, B_STEP = 2 * HID * 16;
 constexpr uint32_t SBO = 128;
 constexpr uint32_t IDESC = idesc_tf32(TM, HID, 0, 0);
-constexpr size_t TC_SMEM = 2 * A_BYTES + 2 * B_BYTES + 2 * HID * 4 + TM * 4;
+// TMEM columns of one CTA (256 allocated; two CTAs per SM own all 512): accumulator | h1 hi (+ bias k-step) | h1 lo
+constexpr uint32_t T_D = 0, T_AHI = 64, T_ALO = 64 + KB, T_COLS = 256;
+// dynamic shared memory: the (hi, lo) image of W2 + w_last + half-row partials; padded to 100 KB so that at most two
+// CTAs share an SM whatever the register allocation (a third CTA would block in tcgen05.alloc)
+constexpr size_t TC_SMEM_USED = 2 * B_BYTES + HID * 4 + TM * 4;
+constexpr size_t TC_SMEM = 100 * 1024;
+static_assert(TC_SMEM_USED <= TC_SMEM, "smem");
 
 __device__ int g_um_timeout = 0;
 
@@ -137,6 +142,9 @@ um_prep_items_kernel(cirs_user_model m, const int32_t* __restrict__ item_ids, co
     char* hi = reinterpret_cast<char*>(w.w2img);
     char* lo = hi + B_BYTES;
     for (int c4 = 0; c4 < HID / 4; ++c4) tile_store_split(hi, lo, HID, j, c4, ld4(m.w2 + j * HID + 4 * c4));
+    // bias k-step: column 64 = b2[j] (the A operand carries a constant 1 there), columns 65..71 zero
+    tile_store_split(hi, lo, HID, j, HID / 4, make_float4(m.b2[j], 0.f, 0.f, 0.f));
+    tile_store_split(hi, lo, HID, j, HID / 4 + 1, make_float4(0.f, 0.f, 0.f, 0.f));
     w.b2w[2 * j] = m.b2[j];
     w.b2w[2 * j + 1] = m.w_last[j];
     if (j == 0) { w.minmax[0] = INT_MAX; w.minmax[1] = INT_MIN; }
@@ -163,28 +171,56 @@ __device__ __forceinline__ void publish_minmax(float vmin, float vmax, int* minm
 
 // ---------------------------------------------------------------------------------------------- tensor-core path
 // 256 threads: thread t owns item row t % 128 (= TMEM lane) and half t / 128 of the 64 hidden columns.
+// The h1 tile never touches shared memory: each thread writes its 32 (hi, lo) values straight into TMEM
+// (tcgen05.st) and the MMAs take A from TMEM, B = [W2 | b2] from shared memory -- an M128 x N64 x K8 MMA with both
+// operands in shared memory reads 6 KB per instruction and is bound by that (measured 57 cycles); with A in TMEM it
+// reads 2 KB.  The bias rides in a ninth k-step (A column 64 == 1), so the epilogue is relu + one FMA per element.
+__device__ __forceinline__ void um_issue(uint32_t tb, uint32_t b_hi, uint32_t b_lo) {
+  // bias k-step first (overwrites the accumulator), then the 8 k-steps of the contraction, small terms first
+  const uint64_t bbh = smem_desc(b_hi + (HID / 8) * B_STEP, B_LBO, SBO), bbl = smem_desc(b_lo + (HID / 8) * B_STEP, B_LBO, SBO);
+  mma_tf32_ts(tb + T_D, tb + T_AHI + HID, bbl, IDESC, 0u);
+  mma_tf32_ts(tb + T_D, tb + T_AHI + HID, bbh, IDESC, 1u);
+#pragma unroll
+  for (int j = 0; j < HID / 8; ++j) {
+    const uint64_t bh = smem_desc(b_hi + j * B_STEP, B_LBO, SBO), bl = smem_desc(b_lo + j * B_STEP, B_LBO, SBO);
+    mma_tf32_ts(tb + T_D, tb + T_ALO + 8 * j, bh, IDESC, 1u);
+    mma_tf32_ts(tb + T_D, tb + T_AHI + 8 * j, bl, IDESC, 1u);
+    mma_tf32_ts(tb + T_D, tb + T_AHI + 8 * j, bh, IDESC, 1u);
+  }
+}
+
 template <int DE>
 __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
   extern __shared__ __align__(1024) char smem[];
-  char* a_hi = smem;
-  char* a_lo = a_hi + A_BYTES;
-  char* b_hi = a_lo + A_BYTES;
+  char* b_hi = smem;
   char* b_lo = b_hi + B_BYTES;
-  float2* sbw = reinterpret_cast<float2*>(b_lo + B_BYTES);       // (b2[k], w_last[k])
-  float* part = reinterpret_cast<float*>(sbw + HID);             // half 1's partial result per row
+  float* swl = reinterpret_cast<float*>(b_lo + B_BYTES);   // w_last[64]
+  float* part = swl + HID;                                 // half 1's partial result per row
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const uint32_t lane_base = (warp & 3) * 32;
   constexpr int DH = DE / 2;   // FM dimensions per half
-  if (warp == 0) tmem_alloc(&tmem_base, 64);
+  if (warp == 0) tmem_alloc(&tmem_base, T_COLS);
   if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   for (int k = tid; k < (int)(2 * B_BYTES / 16); k += NT)
     reinterpret_cast<float4*>(b_hi)[k] = __ldg(reinterpret_cast<const float4*>(a.w2img) + k);
-  if (tid < HID) sbw[tid] = reinterpret_cast<const float2*>(a.b2w)[tid];
+  if (tid < HID) swl[tid] = a.b2w[2 * tid + 1];
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (half == 0) {   // constant A columns of the bias k-step
+    const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    tmem_st8(tmem_addr(tb + T_AHI + HID, lane_base, 0), one);
+    tmem_st_wait();
+  }
   float vmin = INFINITY, vmax = -INFINITY;
   uint32_t ph = 0;
   const int n_chunks = a.n_itile * a.n_uchunk;
-  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+  bool dead = false;
+  for (int c = blockIdx.x; c < n_chunks && !dead; c += gridDim.x) {
     const int it = c % a.n_itile, uc = c / a.n_itile;
     const int i = it * TM + row;
     const bool iv = i < a.I;
@@ -212,25 +248,29 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
       for (int k = 0; k < 8; ++k) p[k] = __ldg(ps + k);
     }
     for (int u = u0; u < u1; ++u) {
-      // h1 = relu(P[u] + Q[i]) -> (hi, lo) operand tile, K-major
+      // h1 = relu(P[u] + Q[i]) -> (hi, lo) A operand in TMEM: lane = row, column = hidden index
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float4 x = make_float4(fmaxf(p[k].x + q[k].x, 0.f), fmaxf(p[k].y + q[k].y, 0.f), fmaxf(p[k].z + q[k].z, 0.f),
-                               fmaxf(p[k].w + q[k].w, 0.f));
-        const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-        const uint32_t off = tile_chunk_off(TM, row, half * 8 + k);
-        *reinterpret_cast<float4*>(a_hi + off) = h;
-        // x - hi is exact in FP32 and has <= 13 significant bits; the MMA truncates it to TF32 (2^-22 of x)
-        *reinterpret_cast<float4*>(a_lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+      for (int g = 0; g < 2; ++g) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 pp = p[4 * g + k], qq = q[4 * g + k];
+          const float x0 = fmaxf(pp.x + qq.x, 0.f), x1 = fmaxf(pp.y + qq.y, 0.f), x2 = fmaxf(pp.z + qq.z, 0.f),
+                      x3 = fmaxf(pp.w + qq.w, 0.f);
+          hi[4 * k] = tf32_hi(x0); hi[4 * k + 1] = tf32_hi(x1); hi[4 * k + 2] = tf32_hi(x2); hi[4 * k + 3] = tf32_hi(x3);
+          // x - hi is exact in FP32 and has <= 13 significant bits; the MMA truncates it to TF32 (2^-22 of x)
+          lo[4 * k] = x0 - hi[4 * k]; lo[4 * k + 1] = x1 - hi[4 * k + 1]; lo[4 * k + 2] = x2 - hi[4 * k + 2];
+          lo[4 * k + 3] = x3 - hi[4 * k + 3];
+        }
+        tmem_st16(tmem_addr(tb + T_AHI, lane_base, half * 32 + g * 16), hi);
+        tmem_st16(tmem_addr(tb + T_ALO, lane_base, half * 32 + g * 16), lo);
       }
-      fence_async_smem();
+      tmem_st_wait();
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
-      const uint32_t tb = tmem_base;
       if (tid == 0) {
-        mma_3xtf32(tb, smem_u32(a_hi), smem_u32(a_lo), A_STEP, A_LBO, SBO, smem_u32(b_hi), smem_u32(b_lo), B_STEP, B_LBO,
-                   SBO, IDESC, HID / 8, false);
+        um_issue(tb, smem_u32(b_hi), smem_u32(b_lo));
         mma_commit(&bar);
       }
       // behind the MMAs: this user's FM / linear terms, the next user's P
@@ -251,22 +291,30 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) p[k] = __ldg(ps + k);
       }
-      if (!mbar_wait(&bar, ph)) g_um_timeout = 1;
+      const bool ok = mbar_wait(&bar, ph);
       ph ^= 1;
       fence_after_sync();
       float v[32];
-      tmem_ld32(tmem_addr(tb, (warp & 3) * 32, half * 32), v);
+      tmem_ld32(tmem_addr(tb + T_D, lane_base, half * 32), v);
       float acc0 = fm, acc1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; k += 2) {
-        const float4 bw = *reinterpret_cast<const float4*>(sbw + half * 32 + k);   // (b2, w, b2, w), broadcast
-        acc0 = fmaf(fmaxf(v[k] + bw.x, 0.f), bw.y, acc0);
-        acc1 = fmaf(fmaxf(v[k + 1] + bw.z, 0.f), bw.w, acc1);
+      for (int k = 0; k < 32; k += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(swl + half * 32 + k);   // broadcast
+        acc0 = fmaf(fmaxf(v[k], 0.f), w.x, acc0);
+        acc1 = fmaf(fmaxf(v[k + 1], 0.f), w.y, acc1);
+        acc0 = fmaf(fmaxf(v[k + 2], 0.f), w.z, acc0);
+        acc1 = fmaf(fmaxf(v[k + 3], 0.f), w.w, acc1);
       }
       const float y = acc0 + acc1;
       if (half == 1) part[row] = y;
       fence_before_sync();
-      __syncthreads();   // accumulator and operand tile are free again; half 1's partial is visible
+      // accumulator and operand columns are free again; half 1's partial is visible.  A wait that gave up (never
+      // expected) ends the kernel for the whole CTA instead of spinning once per tile.
+      if (__syncthreads_or(!ok)) {
+        if (tid == 0) g_um_timeout = 1;
+        dead = true;
+        break;
+      }
       if (half == 0 && iv) {
         const float r = y + part[row];
         a.out[(int64_t)u * a.I + i] = r;
@@ -276,8 +324,9 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
     }
   }
   publish_minmax(vmin, vmax, a.minmax);
+  fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 64);
+  if (warp == 0) tmem_dealloc(tmem_base, T_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------- FFMA path
