@@ -363,7 +363,7 @@ def gpu_arm(args, cfg):
     return out
 
 
-def user_model_arm(cfg, dev, reps=5, cpu_users=24):
+def user_model_arm(cfg, dev, reps=5, cpu_users=1024):
     """SURVEY §8f-3, the step BEFORE the path: KuaishouEnv.compute_normed_reward over the full U x I table
     (cirs_user_model_predict_all, csrc/user_model.cu).  Reports user-item pairs/s resident and end to end (host
     state_dict in, host table out), the per-kernel CUDA-event times, the tensor roofline of the pair kernel, the FFMA
@@ -429,6 +429,11 @@ def user_model_arm(cfg, dev, reps=5, cpu_users=24):
     except Exception:
         pass
     tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    except Exception:
+        pass
     pairs = float(U) * I
     pk = next((k for k in res["tc"]["kernels"] if k.startswith("um_pairs_tc_kernel")), None)
     k_ms = res["tc"]["kernels"][pk]["ms_per_launch"] if pk else res["tc"]["ms"]
@@ -442,7 +447,8 @@ def user_model_arm(cfg, dev, reps=5, cpu_users=24):
         "e2e": {"value": pairs / (float(np.median(e2e_ms)) * 1e-3), "unit": "pairs/s", "ms": float(np.median(e2e_ms)),
                 "h2d_bytes": int(h2d), "d2h_bytes": int(pairs * 4)},
         "roofline": {"kernel": pk, "bound": "tensor", "achieved": round(ach, 2), "peak": tc_peak, "unit": "TFLOP/s",
-                     "frac": round(ach / tc_peak, 5), "traffic": None,
+                     "frac": round(ach / tc_peak, 5),
+                     "traffic": traffic.get(pk) if (U, I) == (7176, 10728) else None,
                      "hbm_GBps_of_result_writes": round(pairs * 4 / (k_ms * 1e-3) / 1e9, 1),
                      "note": "8.4 kFLOP per pair after hoisting the one-sided parts (the reference's unfactorised forward "
                              "is 20.8 kFLOP per pair); 3xTF32 -> the tensor pipe executes 3x the contraction's flops at the "
