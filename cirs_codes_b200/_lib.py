@@ -120,6 +120,7 @@ PROTOTYPES = {
     "cirs_user_model_predict_all": (i32, [P(UserModelStruct), i32, fp, i32, fp, fp, fp, i32, fp, fp, fp, fp]),
     "cirs_user_model_tc_enable": (None, [i32]),
     "cirs_user_model_timeout": (i32, []),
+    "cirs_user_model_debug_phases": (i32, [P(i64)]),
     "cirs_clip_adam": (i32, [fp, fp, fp, fp, i64, i64, P(PPOConfigStruct), fp, fp, fp]),
 }
 

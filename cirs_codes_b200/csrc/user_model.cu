@@ -43,6 +43,7 @@ constexpr size_t TC_SMEM = 100 * 1024;
 static_assert(TC_SMEM_USED <= TC_SMEM, "smem");
 
 __device__ int g_um_timeout = 0;
+__device__ unsigned long long g_um_phase[8];   // TIMING instantiation: cycles of CTA 0 / thread 0 per phase (profiling aid)
 
 // order-preserving float <-> int map (an involution) so that atomicMin / atomicMax on ints order floats
 __device__ __forceinline__ int f2ord(float f) {
@@ -195,7 +196,16 @@ __device__ __forceinline__ float tf32_rna_pos(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
-template <int DE>
+// one lane of a converged warp (elect.sync): code under it is provably executed by a single thread, which lets the
+// compiler keep the MMA descriptors in uniform registers.  Issued under `if (tid == 0)` every tcgen05.mma cost ~8 SASS
+// instructions (R2UR + a divergence waterfall) and 72 cycles: 1860 of a tile's 3350 cycles went into issuing.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+template <int DE, bool TIMING>
 __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
   extern __shared__ __align__(1024) char smem[];
   char* b_hi = smem;
@@ -205,8 +215,11 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int warp_u = __shfl_sync(FULL_MASK, warp, 0);   // the same value, known to be warp-uniform
   const uint32_t lane_base = (warp & 3) * 32;
   constexpr int DH = DE / 2;   // FM dimensions per half
+  const bool timing = TIMING && blockIdx.x == 0 && tid == 0;
+  unsigned tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 32-bit cycle sums: one CTA's launch is ~10^7 cycles
   if (warp == 0) tmem_alloc(&tmem_base, T_COLS);
   if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   for (int k = tid; k < (int)(2 * B_BYTES / 16); k += NT)
@@ -254,6 +267,8 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
       for (int k = 0; k < 8; ++k) p[k] = __ldg(ps + k);
     }
     for (int u = u0; u < u1; ++u) {
+      unsigned tk0 = 0;
+      if (timing) tk0 = (unsigned)clock();
       // h1 = relu(P[u] + Q[i]) -> (hi, lo) A operand in TMEM: lane = row, column = hidden index
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -274,12 +289,18 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
       }
       tmem_st_wait();
       fence_before_sync();
+      if (timing) { const unsigned t = (unsigned)clock(); tacc[0] += t - tk0; tk0 = t; }
       __syncthreads();
       fence_after_sync();
-      if (tid == 0) {
-        um_issue(tb, smem_u32(b_hi), smem_u32(b_lo));
-        mma_commit(&bar);
+      if (timing) { const unsigned t = (unsigned)clock(); tacc[1] += t - tk0; tk0 = t; }
+      if (warp_u == 0) {
+        if (elect_one()) {
+          um_issue(tb, smem_u32(b_hi), smem_u32(b_lo));
+          mma_commit(&bar);
+        }
+        __syncwarp();
       }
+      if (timing) { const unsigned t = (unsigned)clock(); tacc[2] += t - tk0; tk0 = t; }
       // behind the MMAs: this user's FM / linear terms, the next user's P
       float fm = half == 0 ? ci + __ldg(a.lu + u) : 0.f;
       {
@@ -298,9 +319,11 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) p[k] = __ldg(ps + k);
       }
+      if (timing) { const unsigned t = (unsigned)clock(); tacc[3] += t - tk0; tk0 = t; }
       const bool ok = mbar_wait(&bar, ph);
       ph ^= 1;
       fence_after_sync();
+      if (timing) { const unsigned t = (unsigned)clock(); tacc[4] += t - tk0; tk0 = t; }
       float v[32];
       tmem_ld32(tmem_addr(tb + T_D, lane_base, half * 32), v);
       float acc0 = fm, acc1 = 0.f;
@@ -315,6 +338,7 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
       const float y = acc0 + acc1;
       if (half == 1) part[row] = y;
       fence_before_sync();
+      if (timing) { const unsigned t = (unsigned)clock(); tacc[5] += t - tk0; tk0 = t; }
       // accumulator and operand columns are free again; half 1's partial is visible.  A wait that gave up (never
       // expected) ends the kernel for the whole CTA instead of spinning once per tile.
       if (__syncthreads_or(!ok)) {
@@ -322,14 +346,18 @@ __global__ void __launch_bounds__(NT, 2) um_pairs_tc_kernel(PairArgs a) {
         dead = true;
         break;
       }
+      if (timing) { const unsigned t = (unsigned)clock(); tacc[6] += t - tk0; tk0 = t; }
       if (half == 0 && iv) {
         const float r = y + part[row];
         a.out[(int64_t)u * a.I + i] = r;
         vmin = fminf(vmin, r);
         vmax = fmaxf(vmax, r);
       }
+      if (timing) tacc[7] += 1;
     }
   }
+  if (timing)
+    for (int k = 0; k < 8; ++k) g_um_phase[k] = tacc[k];
   publish_minmax(vmin, vmax, a.minmax);
   fence_before_sync();
   __syncthreads();
@@ -438,6 +466,11 @@ extern "C" int cirs_user_model_timeout(void) {
   return v;
 }
 
+extern "C" int cirs_user_model_debug_phases(int64_t* out8_h) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out8_h, g_um_phase, 8 * sizeof(int64_t)) == cudaSuccess ? CIRS_OK : CIRS_ERR_CUDA;
+}
+
 extern "C" int64_t cirs_user_model_workspace_bytes(int32_t n_user, int32_t n_item, int32_t emb_dim) {
   return ws_floats(n_user, n_item, emb_dim) * 4;
 }
@@ -490,14 +523,19 @@ extern "C" int cirs_user_model_predict_all(const cirs_user_model* m, int32_t n_u
     const int grid = n_chunks < grid_max ? n_chunks : grid_max;
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(um_pairs_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-      cudaFuncSetAttribute(um_pairs_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-      cudaFuncSetAttribute(um_pairs_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+      cudaFuncSetAttribute(um_pairs_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+      cudaFuncSetAttribute(um_pairs_tc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+      cudaFuncSetAttribute(um_pairs_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+      cudaFuncSetAttribute(um_pairs_tc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
       attr_done = true;
     }
-    if (de == 8) CIRS_LAUNCH(um_pairs_tc_kernel<8>, grid, NT, TC_SMEM, st, a);
-    else if (de == 16) CIRS_LAUNCH(um_pairs_tc_kernel<16>, grid, NT, TC_SMEM, st, a);
-    else CIRS_LAUNCH(um_pairs_tc_kernel<32>, grid, NT, TC_SMEM, st, a);
+    const char* fl = getenv("CIRS_UM_FLAGS");   // 4: per-phase cycle counters (cirs_user_model_debug_phases)
+    const bool timing = fl && (atoi(fl) & 4) && de == 16;
+    // the macro stringifies its first argument: keep the template commas inside parentheses
+    if (timing) CIRS_LAUNCH((um_pairs_tc_kernel<16, true>), grid, NT, TC_SMEM, st, a);
+    else if (de == 8) CIRS_LAUNCH((um_pairs_tc_kernel<8, false>), grid, NT, TC_SMEM, st, a);
+    else if (de == 16) CIRS_LAUNCH((um_pairs_tc_kernel<16, false>), grid, NT, TC_SMEM, st, a);
+    else CIRS_LAUNCH((um_pairs_tc_kernel<32, false>), grid, NT, TC_SMEM, st, a);
   } else {
     a.users_per_chunk = FF_UCHUNK;
     a.n_uchunk = (n_user + FF_UCHUNK - 1) / FF_UCHUNK;

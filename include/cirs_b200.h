@@ -408,6 +408,10 @@ int cirs_user_model_predict_all(const cirs_user_model* m, int32_t n_user, const 
 void cirs_user_model_tc_enable(int on);
 /* 1 if the tensor-core kernel gave up waiting on an mbarrier since the last call (synchronises; never expected). */
 int cirs_user_model_timeout(void);
+/* Profiling aid: with the environment variable CIRS_UM_FLAGS=4 thread 0 of CTA 0 of the tensor-core kernel accumulates
+ * clock64() cycles per phase of its tile loop; out8_h (HOST int64[8]) = {stage, barrier, MMA issue, FM / prefetch,
+ * MMA wait, epilogue, barrier, tiles} of the last launch.  Synchronises. */
+int cirs_user_model_debug_phases(int64_t* out8_h);
 
 #ifdef __cplusplus
 }
