@@ -177,16 +177,20 @@ __device__ __forceinline__ void publish_minmax(float vmin, float vmax, int* minm
 // operands in shared memory reads 6 KB per instruction and is bound by that (measured 57 cycles); with A in TMEM it
 // reads 2 KB.  The bias rides in a ninth k-step (A column 64 == 1), so the epilogue is relu + one FMA per element.
 __device__ __forceinline__ void um_issue(uint32_t tb, uint32_t b_hi, uint32_t b_lo) {
+  // One descriptor per operand tile; k-step j is the same descriptor with the start-address field advanced by
+  // j * B_STEP / 16 (shared addresses are < 256 KB, so the 14-bit field never carries): one add per MMA operand
+  // instead of rebuilding the descriptor (shift, mask, or) -- the issuing lane's instruction stream is what paces
+  // the batch.
+  const uint64_t dh = smem_desc(b_hi, B_LBO, SBO), dl = smem_desc(b_lo, B_LBO, SBO);
+  constexpr uint64_t KSTEP = B_STEP >> 4;
   // bias k-step first (overwrites the accumulator), then the 8 k-steps of the contraction, small terms first
-  const uint64_t bbh = smem_desc(b_hi + (HID / 8) * B_STEP, B_LBO, SBO), bbl = smem_desc(b_lo + (HID / 8) * B_STEP, B_LBO, SBO);
-  mma_tf32_ts(tb + T_D, tb + T_AHI + HID, bbl, IDESC, 0u);
-  mma_tf32_ts(tb + T_D, tb + T_AHI + HID, bbh, IDESC, 1u);
+  mma_tf32_ts(tb + T_D, tb + T_AHI + HID, dl + (HID / 8) * KSTEP, IDESC, 0u);
+  mma_tf32_ts(tb + T_D, tb + T_AHI + HID, dh + (HID / 8) * KSTEP, IDESC, 1u);
 #pragma unroll
   for (int j = 0; j < HID / 8; ++j) {
-    const uint64_t bh = smem_desc(b_hi + j * B_STEP, B_LBO, SBO), bl = smem_desc(b_lo + j * B_STEP, B_LBO, SBO);
-    mma_tf32_ts(tb + T_D, tb + T_ALO + 8 * j, bh, IDESC, 1u);
-    mma_tf32_ts(tb + T_D, tb + T_AHI + 8 * j, bl, IDESC, 1u);
-    mma_tf32_ts(tb + T_D, tb + T_AHI + 8 * j, bh, IDESC, 1u);
+    mma_tf32_ts(tb + T_D, tb + T_ALO + 8 * j, dh + j * KSTEP, IDESC, 1u);
+    mma_tf32_ts(tb + T_D, tb + T_AHI + 8 * j, dl + j * KSTEP, IDESC, 1u);
+    mma_tf32_ts(tb + T_D, tb + T_AHI + 8 * j, dh + j * KSTEP, IDESC, 1u);
   }
 }
 

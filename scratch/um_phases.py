@@ -26,8 +26,8 @@ def run(flags, reps=5):
         e0.record(); um.predict_all(w, users, items, feat, dense, normalise=False, out=out, workspace=ws); e1.record()
         torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
     return float(np.median(ms))
-res = {"ms": run(0)}
-for fl in (4,):
+res = {"ms": run(0), "ms_two_groups": run(8)}
+for fl in (4, 12):
     run(fl, 1)
     buf = (C.c_int64 * 8)()
     lib.cirs_user_model_debug_phases(buf)
