@@ -40,6 +40,16 @@ def test_product_path_fails_loudly_without_cuda():
     from cirs_codes_b200._lib import CirsError
     with pytest.raises(CirsError):
         cb.KuaishouVectorEnv(2, np.zeros((3, 4)), [[1]] * 4, normed_mat=np.zeros((3, 4)))
+    # the reward-table producer has no CPU path either
+    from cirs_codes_b200 import user_model as um
+    from oracle import user_model as oum
+
+    class Lbe:
+        classes_ = np.arange(3)
+    with pytest.raises(CirsError):
+        um.UserModelWeights(oum.synth_params(4, 5, 8))
+    with pytest.raises(CirsError):
+        um.compute_normed_reward(oum.synth_params(4, 5, 8), Lbe(), Lbe(), None)
 
 
 def test_struct_sizes_match_c_layout():
