@@ -404,7 +404,8 @@ def user_model_arm(cfg, dev, reps=5, cpu_users=1024):
         rep = _lib.profile_report()
         lib.cirs_profile_enable(0)
         res[tag] = {"ms": float(np.median(ms)), "ms_each": [round(x, 3) for x in ms],
-                    "kernels": {k: {"launches": c, "ms_per_launch": round(t / c, 4)} for k, (c, t) in rep.items()}}
+                    # names are the stringified launch expressions: "(um_pairs_tc_kernel<16, false>)" -> strip the parentheses
+                    "kernels": {k.strip("()"): {"launches": c, "ms_per_launch": round(t / c, 4)} for k, (c, t) in rep.items()}}
     lib.cirs_user_model_tc_enable(-1)
     timeout = int(lib.cirs_user_model_timeout())
     # end to end: host state_dict -> device weights, ids / item table H2D, table D2H into pinned memory
@@ -448,7 +449,8 @@ def user_model_arm(cfg, dev, reps=5, cpu_users=1024):
                 "h2d_bytes": int(h2d), "d2h_bytes": int(pairs * 4)},
         "roofline": {"kernel": pk, "bound": "tensor", "achieved": round(ach, 2), "peak": tc_peak, "unit": "TFLOP/s",
                      "frac": round(ach / tc_peak, 5),
-                     "traffic": traffic.get(pk) if (U, I) == (7176, 10728) else None,
+                     "traffic": next((v for k, v in traffic.items() if k.startswith("um_pairs_tc_kernel")), None)
+                     if (U, I) == (7176, 10728) else None,
                      "hbm_GBps_of_result_writes": round(pairs * 4 / (k_ms * 1e-3) / 1e9, 1),
                      "note": "8.4 kFLOP per pair after hoisting the one-sided parts (the reference's unfactorised forward "
                              "is 20.8 kFLOP per pair); 3xTF32 -> the tensor pipe executes 3x the contraction's flops at the "
