@@ -85,15 +85,19 @@ struct SrcRows {   // gathered h2 rows of one 128-row tile of the compact row li
 __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const TcSmem& S, int tid, TcState& st,
                                              int* timeout_flag) {
   const int warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const bool warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform: the MMAs are issued under elect.sync (tc_dev.cuh)
   const int n_rt = (P.n_rows + ROWS - 1) / ROWS;
   const uint32_t tb = *S.tmem;
   const int nA = P.W.n_action;
   const int seen_words = (nA + 31) >> 5;
   const uint64_t offset = P.offset + (P.rng_counter ? (uint64_t)*P.rng_counter : 0ull);
-  auto issue = [&](int rt) {
-    mma_3xtf32(tb + 128u * (rt & 1), smem_u32(S.a_hi), smem_u32(S.a_lo), A_STEP, A_LBO, 128u, smem_u32(S.w_hi),
-               smem_u32(S.w_lo), W_STEP, W_LBO, 128u, IDESC, HID / 8, false);
-    mma_commit(&S.bar[rt & 1]);
+  auto issue = [&](int rt) {   // called by all lanes of warp 0
+    if (elect_one()) {
+      mma_3xtf32(tb + 128u * (rt & 1), smem_u32(S.a_hi), smem_u32(S.a_lo), A_STEP, A_LBO, 128u, smem_u32(S.w_hi),
+                 smem_u32(S.w_lo), W_STEP, W_LBO, 128u, IDESC, HID / 8, false);
+      mma_commit(&S.bar[rt & 1]);
+    }
+    __syncwarp();
   };
   TileV<ROWS, HID, NT> ta;
   ta.load(tid, SrcRows{P.h2_in, P.gather, 0, P.n_rows});
@@ -102,7 +106,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  if (tid == 0) issue(0);
+  if (warp0) issue(0);
   if (n_rt > 1) ta.load(tid, SrcRows{P.h2_in, P.gather, ROWS, P.n_rows});
   for (int rt = 0; rt < n_rt; ++rt) {
     const int b = rt & 1;
@@ -116,7 +120,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
-      if (tid == 0) issue(rt + 1);
+      if (warp0) issue(rt + 1);
       if (rt + 2 < n_rt) ta.load(tid, SrcRows{P.h2_in, P.gather, (rt + 2) * ROWS, P.n_rows});
     }
     // ---- epilogue: thread = (row, column half of 40)

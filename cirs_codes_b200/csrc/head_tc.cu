@@ -38,6 +38,11 @@ __device__ __forceinline__ void issue(uint32_t d, const char* a_hi, const char* 
   mma_3xtf32(d, smem_u32(a_hi), smem_u32(a_lo), A_STEP, A_LBO, SBO, smem_u32(b_hi), smem_u32(b_lo), B_STEP, B_LBO, SBO,
              IDESC, KSTEPS, accumulate);
 }
+// warp-collective forms for the issuer warp of the TMA-fed kernels (tc_dev.cuh elect_one)
+__device__ __forceinline__ void w_issue(uint32_t d, const char* a_hi, const char* a_lo, const char* b_hi, const char* b_lo,
+                                        bool accumulate) {
+  if (elect_one()) issue(d, a_hi, a_lo, b_hi, b_lo, accumulate);
+}
 __device__ __forceinline__ void wait_or_flag(uint64_t* bar, uint32_t parity) {
   if (!mbar_wait(bar, parity)) g_tc_timeout = 1;
 }
@@ -277,7 +282,7 @@ head_tc_stats_tma_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_
   __shared__ __align__(8) uint64_t tma_a, tma_b, mma[2], dfree[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, half = (tid >> 7) & 1;
-  const bool worker = tid < NT, issuer = tid == NT;
+  const bool worker = tid < NT, issuer = __shfl_sync(FULL_MASK, warp, 0) == NT / 32;
   const int r0 = blockIdx.x * TM, split = blockIdx.y;
   const int n_tiles = (H.nA + TN - 1) / TN;
   const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
@@ -295,13 +300,13 @@ head_tc_stats_tma_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_
   if (issuer) {
     auto copy_tile = [&](int t) {   // W3 image (hi, lo are adjacent: one 32 KB copy) + 64 bias values of tile t
       const int ct = ct0 + t;
-      mbar_expect_tx(&tma_b, 2 * B_BYTES + 64 * 4);
-      bulk_g2s(b_hi, H.img + img_n_off(ct), 2 * B_BYTES, &tma_b);
-      bulk_g2s(sb3 + 64 * (t & 1), H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_b);
+      w_expect_tx(&tma_b, 2 * B_BYTES + 64 * 4);
+      w_bulk_g2s(b_hi, H.img + img_n_off(ct), 2 * B_BYTES, &tma_b);
+      w_bulk_g2s(sb3 + 64 * (t & 1), H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_b);
     };
     if (T > 0) {
-      mbar_expect_tx(&tma_a, 2 * A_BYTES);
-      bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
+      w_expect_tx(&tma_a, 2 * A_BYTES);
+      w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
       copy_tile(0);
       wait_or_flag(&tma_a, 0);
     }
@@ -310,8 +315,8 @@ head_tc_stats_tma_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_
       wait_or_flag(&tma_b, t & 1);                                  // tile t and its bias are in shared memory
       if (t >= 2) wait_or_flag(&dfree[b], ((t - 2) >> 1) & 1);      // accumulator b was read by epilogue(t-2)
       fence_after_sync();
-      issue(tb + 64u * b, a_hi, a_lo, b_hi, b_lo, false);
-      mma_commit(&mma[b]);
+      w_issue(tb + 64u * b, a_hi, a_lo, b_hi, b_lo, false);
+      w_commit(&mma[b]);
       if (t + 1 < T) {
         wait_or_flag(&mma[b], (t >> 1) & 1);                        // MMA(t) no longer reads the B tile
         if (t >= 1) wait_or_flag(&dfree[b ^ 1], ((t - 1) >> 1) & 1);   // bias buffer (t+1)&1 was read by epilogue(t-1)
@@ -387,15 +392,20 @@ __device__ __forceinline__ uint32_t t_dl_lo(int b) { return T_DL + 128u * b + 64
 __device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const char* b_hi, const char* b_lo,
                                          bool accumulate) {
   uint32_t acc = accumulate ? 1u : 0u;
-  const uint32_t bh0 = smem_u32(b_hi), bl0 = smem_u32(b_lo);
+  const uint64_t bh0 = smem_desc(smem_u32(b_hi), B_LBO, SBO), bl0 = smem_desc(smem_u32(b_lo), B_LBO, SBO);
+  constexpr uint64_t BS = B_STEP >> 4;
 #pragma unroll
   for (int j = 0; j < KSTEPS; ++j) {
-    const uint64_t bh = smem_desc(bh0 + j * B_STEP, B_LBO, SBO), bl = smem_desc(bl0 + j * B_STEP, B_LBO, SBO);
-    mma_tf32_ts(d, a_lo + 8 * j, bh, IDESC, acc);
-    mma_tf32_ts(d, a_hi + 8 * j, bl, IDESC, 1u);
-    mma_tf32_ts(d, a_hi + 8 * j, bh, IDESC, 1u);
+    mma_tf32_ts(d, a_lo + 8 * j, bh0 + j * BS, IDESC, acc);
+    mma_tf32_ts(d, a_hi + 8 * j, bl0 + j * BS, IDESC, 1u);
+    mma_tf32_ts(d, a_hi + 8 * j, bh0 + j * BS, IDESC, 1u);
     acc = 1u;
   }
+}
+// warp-collective form for the issuer warp of the TMA-fed kernels (tc_dev.cuh elect_one)
+__device__ __forceinline__ void w_issue_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const char* b_hi, const char* b_lo,
+                                           bool accumulate) {
+  if (elect_one()) issue_ts(d, a_hi, a_lo, b_hi, b_lo, accumulate);
 }
 // 16 d-logit values of this thread's lane -> TMEM (hi by truncation, lo = x - hi: gradients need ~2^-22, tc_dev.cuh)
 __device__ __forceinline__ void store_dl(uint32_t tb, int b, uint32_t lane_base, int col0, const float (&v)[16]) {
@@ -696,7 +706,7 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k, mma1[2], mma2, dlr[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, qt = (tid >> 7) & 3;
-  const bool worker = tid < NTB, issuer = tid == NTB;
+  const bool worker = tid < NTB, issuer = __shfl_sync(FULL_MASK, warp, 0) == NTB / 32;
   const int r0 = blockIdx.x * TM, split = blockIdx.y;
   const int n_tiles = (H.nA + TN - 1) / TN;
   const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
@@ -715,23 +725,23 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   if (issuer && T > 0) {
     auto copy_n = [&](int t) {
       const int ct = ct0 + t, b = t & 1;
-      mbar_expect_tx(&tma_n[b], 2 * B_BYTES + 64 * 4);
-      bulk_g2s(bn + 2 * b * B_BYTES, H.img + img_n_off(ct), 2 * B_BYTES, &tma_n[b]);
-      bulk_g2s(sb3 + 64 * b, H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_n[b]);
+      w_expect_tx(&tma_n[b], 2 * B_BYTES + 64 * 4);
+      w_bulk_g2s(bn + 2 * b * B_BYTES, H.img + img_n_off(ct), 2 * B_BYTES, &tma_n[b]);
+      w_bulk_g2s(sb3 + 64 * b, H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_n[b]);
     };
     auto copy_k = [&](int t) {
-      mbar_expect_tx(&tma_k, 2 * B_BYTES);
-      bulk_g2s(bk, H.img + img_k_off(n64, ct0 + t), 2 * B_BYTES, &tma_k);
+      w_expect_tx(&tma_k, 2 * B_BYTES);
+      w_bulk_g2s(bk, H.img + img_k_off(n64, ct0 + t), 2 * B_BYTES, &tma_k);
     };
-    mbar_expect_tx(&tma_a, 2 * A_BYTES);
-    bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
+    w_expect_tx(&tma_a, 2 * A_BYTES);
+    w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
     copy_n(0);
     copy_k(0);
     wait_or_flag(&tma_a, 0);
     wait_or_flag(&tma_n[0], 0);
     fence_after_sync();
-    issue(tb + T_D1, a_hi, a_lo, bn, bn + B_BYTES, false);
-    mma_commit(&mma1[0]);
+    w_issue(tb + T_D1, a_hi, a_lo, bn, bn + B_BYTES, false);
+    w_commit(&mma1[0]);
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, nb = b ^ 1;
       if (t + 1 < T) {
@@ -742,8 +752,8 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
         copy_n(t + 1);
         wait_or_flag(&tma_n[nb], ((t + 1) >> 1) & 1);
         fence_after_sync();
-        issue(tb + T_D1 + 64u * nb, a_hi, a_lo, bn + 2 * nb * B_BYTES, bn + (2 * nb + 1) * B_BYTES, false);
-        mma_commit(&mma1[nb]);
+        w_issue(tb + T_D1 + 64u * nb, a_hi, a_lo, bn + 2 * nb * B_BYTES, bn + (2 * nb + 1) * B_BYTES, false);
+        w_commit(&mma1[nb]);
       }
       if (t >= 1) {
         wait_or_flag(&mma2, (t - 1) & 1);                // MMA2(t-1) no longer reads bk
@@ -752,8 +762,8 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
       wait_or_flag(&dlr[b], (t >> 1) & 1);               // d logits of tile t are in TMEM
       wait_or_flag(&tma_k, t & 1);
       fence_after_sync();
-      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk, bk + B_BYTES, t > 0);
-      mma_commit(&mma2);
+      w_issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk, bk + B_BYTES, t > 0);
+      w_commit(&mma2);
     }
   }
   const bool live = worker && r0 + row < H.n;
@@ -823,7 +833,7 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k, mma1[2], mma2, dlr[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cl = tid & 127, qt = (tid >> 7) & 3;
-  const bool worker = tid < NTB, issuer = tid == NTB;
+  const bool worker = tid < NTB, issuer = __shfl_sync(FULL_MASK, warp, 0) == NTB / 32;
   const int c0 = blockIdx.x * TM, col = c0 + cl;
   const int rs0 = blockIdx.y * rows_per_split, rs1 = min(H.n, rs0 + rows_per_split);
   const int T = rs1 > rs0 ? (rs1 - rs0 + TN - 1) / TN : 0;
@@ -843,26 +853,26 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
     auto copy_n = [&](int t) {
       const int r0 = rs0 + t * TN, b = t & 1;
       float* sp = stats + 256 * b;
-      mbar_expect_tx(&tma_n[b], 2 * B_BYTES + 4 * 64 * 4);
-      bulk_g2s(hb + 2 * b * B_BYTES, H.himg + himg_n_off(r0 / TN), 2 * B_BYTES, &tma_n[b]);
-      bulk_g2s(sp, rowm + r0, 64 * 4, &tma_n[b]);
-      bulk_g2s(sp + 64, rinvz + r0, 64 * 4, &tma_n[b]);
-      bulk_g2s(sp + 128, coef + r0, 64 * 4, &tma_n[b]);
-      bulk_g2s(sp + 192, acta + r0, 64 * 4, &tma_n[b]);
+      w_expect_tx(&tma_n[b], 2 * B_BYTES + 4 * 64 * 4);
+      w_bulk_g2s(hb + 2 * b * B_BYTES, H.himg + himg_n_off(r0 / TN), 2 * B_BYTES, &tma_n[b]);
+      w_bulk_g2s(sp, rowm + r0, 64 * 4, &tma_n[b]);
+      w_bulk_g2s(sp + 64, rinvz + r0, 64 * 4, &tma_n[b]);
+      w_bulk_g2s(sp + 128, coef + r0, 64 * 4, &tma_n[b]);
+      w_bulk_g2s(sp + 192, acta + r0, 64 * 4, &tma_n[b]);
     };
     auto copy_k = [&](int t) {
-      mbar_expect_tx(&tma_k, 2 * B_BYTES);
-      bulk_g2s(ht, H.himg + himg_t_off(h64, rs0 / TN + t), 2 * B_BYTES, &tma_k);
+      w_expect_tx(&tma_k, 2 * B_BYTES);
+      w_bulk_g2s(ht, H.himg + himg_t_off(h64, rs0 / TN + t), 2 * B_BYTES, &tma_k);
     };
-    mbar_expect_tx(&tma_a, 2 * A_BYTES);
-    bulk_g2s(wa_hi, H.img + img_a_off(H.ldA / TN, blockIdx.x), 2 * A_BYTES, &tma_a);
+    w_expect_tx(&tma_a, 2 * A_BYTES);
+    w_bulk_g2s(wa_hi, H.img + img_a_off(H.ldA / TN, blockIdx.x), 2 * A_BYTES, &tma_a);
     copy_n(0);
     copy_k(0);
     wait_or_flag(&tma_a, 0);
     wait_or_flag(&tma_n[0], 0);
     fence_after_sync();
-    issue(tb + T_D1, wa_hi, wa_lo, hb, hb + B_BYTES, false);   // (logits tile)^T - b3: lane = column, 64 rows
-    mma_commit(&mma1[0]);
+    w_issue(tb + T_D1, wa_hi, wa_lo, hb, hb + B_BYTES, false);   // (logits tile)^T - b3: lane = column, 64 rows
+    w_commit(&mma1[0]);
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, nb = b ^ 1;
       if (t + 1 < T) {
@@ -873,8 +883,8 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
         copy_n(t + 1);
         wait_or_flag(&tma_n[nb], ((t + 1) >> 1) & 1);
         fence_after_sync();
-        issue(tb + T_D1 + 64u * nb, wa_hi, wa_lo, hb + 2 * nb * B_BYTES, hb + (2 * nb + 1) * B_BYTES, false);
-        mma_commit(&mma1[nb]);
+        w_issue(tb + T_D1 + 64u * nb, wa_hi, wa_lo, hb + 2 * nb * B_BYTES, hb + (2 * nb + 1) * B_BYTES, false);
+        w_commit(&mma1[nb]);
       }
       if (t >= 1) {
         wait_or_flag(&mma2, (t - 1) & 1);
@@ -883,8 +893,8 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
       wait_or_flag(&dlr[b], (t >> 1) & 1);
       wait_or_flag(&tma_k, t & 1);
       fence_after_sync();
-      issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht, ht + B_BYTES, t > 0);   // D3 += d logits^T . h2
-      mma_commit(&mma2);
+      w_issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht, ht + B_BYTES, t > 0);   // D3 += d logits^T . h2
+      w_commit(&mma2);
     }
   }
   const bool live = worker && col < H.nA;

@@ -320,19 +320,45 @@ __device__ __forceinline__ void tile_stage(char* hi, char* lo, int R, int C, int
 // Issue the three TF32 products of one k-step range: D (+)= A.B with A, B given as hi / lo tiles.
 //   a_hi/a_lo, b_hi/b_lo : shared addresses (u32) of the tiles' first k-step
 //   a_step, b_step       : byte advance per k-step (8 K elements);  lbo / sbo per operand as in the header comment
+// One descriptor per operand tile; k-step j is the same descriptor with the start-address field advanced by j * step / 16
+// (shared addresses are < 256 KB, so the 14-bit field never carries): one add per MMA operand instead of rebuilding the
+// descriptor -- the issuing lane's instruction stream paces the batch (measured in user_model.cu: 47 -> 37 cycles / MMA).
 __device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_step,
                                            uint32_t a_lbo, uint32_t a_sbo, uint32_t b_hi, uint32_t b_lo,
                                            uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
                                            int ksteps, bool accumulate_first) {
   uint32_t acc = accumulate_first ? 1u : 0u;
+  const uint64_t ah0 = smem_desc(a_hi, a_lbo, a_sbo), al0 = smem_desc(a_lo, a_lbo, a_sbo);
+  const uint64_t bh0 = smem_desc(b_hi, b_lbo, b_sbo), bl0 = smem_desc(b_lo, b_lbo, b_sbo);
+  const uint64_t as = a_step >> 4, bs = b_step >> 4;
+#pragma unroll
   for (int j = 0; j < ksteps; ++j) {
-    const uint64_t ah = smem_desc(a_hi + j * a_step, a_lbo, a_sbo), al = smem_desc(a_lo + j * a_step, a_lbo, a_sbo);
-    const uint64_t bh = smem_desc(b_hi + j * b_step, b_lbo, b_sbo), bl = smem_desc(b_lo + j * b_step, b_lbo, b_sbo);
-    mma_tf32(d_tmem, al, bh, idesc, acc);   // small terms first
-    mma_tf32(d_tmem, ah, bl, idesc, 1u);
-    mma_tf32(d_tmem, ah, bh, idesc, 1u);
+    mma_tf32(d_tmem, al0 + j * as, bh0 + j * bs, idesc, acc);   // small terms first
+    mma_tf32(d_tmem, ah0 + j * as, bl0 + j * bs, idesc, 1u);
+    mma_tf32(d_tmem, ah0 + j * as, bh0 + j * bs, idesc, 1u);
     acc = 1u;
   }
+}
+
+// One lane of a converged warp (elect.sync).  Code under it is provably executed by a single thread, which lets the
+// compiler keep the MMA descriptors / TMEM addresses in uniform registers: under `if (tid == X)` every tcgen05.mma costs
+// an R2UR + ELECT + BRA.U.ANY divergence waterfall (~8 SASS instructions, 72 cycles per MMA measured in user_model.cu
+// against the tensor pipe's 31).  The same lane is elected every time for the same mask, so single-thread program order
+// holds across consecutive elected regions.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp-collective forms of the single-thread operations of a producer / issuer warp (all 32 lanes call them)
+__device__ __forceinline__ void w_expect_tx(uint64_t* bar, uint32_t bytes) {
+  if (elect_one()) mbar_expect_tx(bar, bytes);
+}
+__device__ __forceinline__ void w_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  if (elect_one()) bulk_g2s(smem_dst, gmem_src, bytes, bar);
+}
+__device__ __forceinline__ void w_commit(uint64_t* bar) {
+  if (elect_one()) mma_commit(bar);
 }
 
 }  // namespace cirs_tc
