@@ -32,14 +32,27 @@ warnings.filterwarnings("ignore")
 
 CONFIGS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on (512 envs per GPU -> 4096 at 8 GPUs)
-    "configs1": dict(U=7176, I=10728, B=512, d=32, nhead=4, T=30, N=1, thr=0, batch_size=1024, repeat=2,
+    "configs1": dict(kind="kuaishou", U=7176, I=10728, B=512, d=32, nhead=4, T=30, N=1, thr=0, batch_size=1024, repeat=2,
                      name="configs[1]: KuaishouEnv 7176x10728 synthetic, 512 envs/GPU, emb_dim=32, max_turn=30, "
                           "N=1 thr=0 (reference defaults), PPO batch 1024 x repeat 2"),
     # BASELINE.json configs[2]
-    "configs2": dict(U=7176, I=10728, B=4096, d=64, nhead=4, T=30, N=5, thr=0, batch_size=4096, repeat=2,
+    "configs2": dict(kind="kuaishou", U=7176, I=10728, B=4096, d=64, nhead=4, T=30, N=5, thr=0, batch_size=4096, repeat=2,
                      name="configs[2]: KuaishouEnv 7176x10728 synthetic, 4096 envs/GPU, emb_dim=64, window N=5, "
                           "PPO batch 4096 x repeat 2"),
-    "small": dict(U=300, I=1000, B=64, d=32, nhead=4, T=12, N=1, thr=0, batch_size=128, repeat=2,
+    # BASELINE.json configs[4]: 16384 envs over 8 GPUs = 2048 per GPU, emb_dim = 128
+    "configs4": dict(kind="kuaishou", U=7176, I=10728, B=2048, d=128, nhead=4, T=30, N=1, thr=0, batch_size=4096, repeat=2,
+                     name="configs[4]: KuaishouEnv 7176x10728 synthetic, 2048 envs/GPU (16384 at 8 GPUs), emb_dim=128, "
+                          "full 10728-item head, PPO batch 4096 x repeat 2"),
+    # BASELINE.json configs[3]: 8192 envs over 4 GPUs = 2048 per GPU.  The reference asserts dim_model == 27 for
+    # VirtualTaobao (CIRS-RL-taobao.py:194), so "emb_dim=32" of the config line cannot be built: d = 27, 3 heads.
+    "configs3": dict(kind="taobao", B=2048, d=27, nhead=3, T=50, N=5, thr=1.0, tau=10.0, batch_size=4096, repeat=2,
+                     name="configs[3]: VirtualTaobao SimulatedEnv, 2048 envs/GPU (8192 at 4 GPUs), Euclidean exit "
+                          "d_Q=1.0 N=5, dim_model=27 (reference-mandated), max_turn=50, PPO batch 4096 x repeat 2"),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable plumbing case (Transformer tracker: the reference has no
+    # "Avg" tracker)
+    "configs0": dict(kind="taobao", B=1, d=27, nhead=3, T=50, N=5, thr=3.0, tau=10.0, batch_size=64, repeat=1,
+                     name="configs[0]: VirtualTaobao SimulatedEnv, 1 env, dim_model=27, PPO 1 epoch (plumbing)"),
+    "small": dict(kind="kuaishou", U=300, I=1000, B=64, d=32, nhead=4, T=12, N=1, thr=0, batch_size=128, repeat=2,
                   name="small (debug)"),
 }
 REF = dict(tau=100.0, gamma_exposure=10.0, r_decay=1.0, version="v1", dim_state=20, lr=1e-3, gamma=0.95,
@@ -48,7 +61,17 @@ REF = dict(tau=100.0, gamma_exposure=10.0, r_decay=1.0, version="v1", dim_state=
 
 def tables(cfg, seed=2023):
     from cirs_codes_b200 import synth
+    if cfg["kind"] == "taobao":
+        return {"usermodel": synth.mmoe_state_dict(seed)}
     return synth.kuaishou_tables(cfg["U"], cfg["I"], seed=seed)
+
+
+def draw_users(cfg, rng, B):
+    """The episode's users: ids for KuaishouEnv, one-hot x 11 vectors [B, 88] for VirtualTaobao."""
+    if cfg["kind"] == "taobao":
+        from cirs_codes_b200 import synth
+        return synth.taobao_users(B, seed=int(rng.integers(0, 2 ** 31)))
+    return rng.integers(0, cfg["U"], size=B)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
@@ -57,26 +80,46 @@ def oracle_objects(cfg, tb, B, seed):
     from oracle import env as oenv, nets, ppo
     import torch.nn as nn
     torch.manual_seed(seed)
-    d, S, I = cfg["d"], REF["dim_state"], cfg["I"]
-    env = oenv.KuaishouSimOracle(tb["mat"], tb["normed_mat"], tb["cats"], tb["alpha_u"], tb["beta_i"],
-                                 max_turn=cfg["T"], num_leave_compute=cfg["N"], leave_threshold=cfg["thr"],
-                                 tau=REF["tau"], gamma_exposure=REF["gamma_exposure"], r_decay=REF["r_decay"],
-                                 version=REF["version"])
-    P = {"embedding_dict.feat_user.weight": torch.randn(cfg["U"], d) * 1e-4,
-         "embedding_dict.feat_item.weight": torch.randn(I, d) * 1e-4}
+    d, S = cfg["d"], REF["dim_state"]
+    taobao = cfg["kind"] == "taobao"
+    if taobao:
+        UM = {k: torch.as_tensor(v) for k, v in tb["usermodel"].items()}
+        UM["linear_model_task.0.weight"] = UM["linear_model_task.0.weight"].reshape(-1)
+
+        def reward_fn(x):
+            with torch.no_grad():
+                return nets.mmoe_forward(UM, x).reshape(-1).numpy()
+
+        env = oenv.TaobaoSimOracle(reward_fn, max_turn=cfg["T"], num_leave_compute=cfg["N"],
+                                   leave_threshold=cfg["thr"], tau=cfg["tau"],
+                                   gamma_exposure=REF["gamma_exposure"], version=REF["version"])
+        P = {}
+        d_user_in, n_out = 88, 27
+    else:
+        I = cfg["I"]
+        env = oenv.KuaishouSimOracle(tb["mat"], tb["normed_mat"], tb["cats"], tb["alpha_u"], tb["beta_i"],
+                                     max_turn=cfg["T"], num_leave_compute=cfg["N"], leave_threshold=cfg["thr"],
+                                     tau=REF["tau"], gamma_exposure=REF["gamma_exposure"], r_decay=REF["r_decay"],
+                                     version=REF["version"])
+        P = {"embedding_dict.feat_user.weight": torch.randn(cfg["U"], d) * 1e-4,
+             "embedding_dict.feat_item.weight": torch.randn(I, d) * 1e-4}
+        d_user_in, n_out = d, I
     enc = nn.TransformerEncoder(nn.TransformerEncoderLayer(d, cfg["nhead"], 128, 0.0), 2, enable_nested_tensor=False)
-    for name, mod in (("ffn_user", nn.Linear(d, d)), ("fnn_gate", nn.Linear(1 + d, d)), ("transformer_encoder", enc),
-                      ("decoder", nn.Linear(d, S))):
+    for name, mod in (("ffn_user", nn.Linear(d_user_in, d)), ("fnn_gate", nn.Linear(1 + d, d)),
+                      ("transformer_encoder", enc), ("decoder", nn.Linear(d, S))):
         for k, v in mod.state_dict().items():
             P[f"{name}.{k}"] = v.detach().clone()
     P = {k: v.requires_grad_(True) for k, v in P.items()}
     R = {}
+    last = "actor.mu" if taobao else "actor.last"
     for k, shape in (("preprocess.model.model.0", (64, S)), ("preprocess.model.model.2", (64, 64)),
-                     ("actor.last", (I, 64)), ("critic.last", (1, 64))):
+                     (last, (n_out, 64)), ("critic.last", (1, 64))):
         w = torch.empty(*shape)
         nn.init.orthogonal_(w)
         R[k + ".weight"], R[k + ".bias"] = w, torch.zeros(shape[0])
-    tracker = nets.TrackerOracle(P, cfg["nhead"], cfg["T"])
+    if taobao:
+        R["actor.sigma_param"] = torch.zeros(27, 1)
+    tracker = nets.TrackerOracle(P, cfg["nhead"], cfg["T"], dense=taobao)
     return env, tracker, P, R, ppo.AdamDup(), ppo.AdamDup(), ppo.RunningMeanStd()
 
 
@@ -85,10 +128,16 @@ def oracle_step(cfg, objs, users, rng):
     from oracle import pipeline
     env, tracker, P, R, opt_rl, opt_tr, rms = objs
 
-    def noise(turn, n, A):
-        return torch.empty(n, A).exponential_(1)
+    if cfg["kind"] == "taobao":
+        def noise(turn, n, A):
+            return torch.randn(n, A)
+        space = (np.full(27, -1.0, np.float32), np.full(27, 1.0, np.float32))
+    else:
+        def noise(turn, n, A):
+            return torch.empty(n, A).exponential_(1)
+        space = None
 
-    traj, res = pipeline.collect(env, tracker, R, users, noise=noise)
+    traj, res = pipeline.collect(env, tracker, R, users, noise=noise, action_space=space)
     n = len(traj.act)
     perms = [rng.permutation(n) for _ in range(cfg["repeat"])]
     pipeline.update(traj, R, opt_rl, list(P.values()), opt_tr, rms, perms, cfg["batch_size"], gamma=REF["gamma"],
@@ -97,26 +146,41 @@ def oracle_step(cfg, objs, users, rng):
     return res["n/st"]
 
 
-def cpu_arm(cfg, tb, B_sample, budget_s, max_steps, seed=0):
-    """Time the CPU oracle port (all host threads) on a bounded sample: B_sample environments of the same workload,
-    whole iterations until ``budget_s`` seconds or ``max_steps`` iterations."""
+def cpu_arm(cfg, tb, B_sample, budget_s, max_steps, seed=0, warm=1):
+    """Time the CPU oracle port (all host threads) on the SAME frozen workload as the GPU arm: B_sample environments,
+    the same users every iteration, and the policy / tracker / Adam / return statistics restored to their initial
+    values before every iteration (the iteration still performs its full update); whole iterations until
+    ``budget_s`` seconds or ``max_steps`` iterations, the first ``warm`` untimed."""
+    import copy
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     objs = oracle_objects(cfg, tb, B_sample, seed)
+    env, tracker, P, R, opt_rl, opt_tr, rms = objs
+    P0 = {k: v.detach().clone() for k, v in P.items()}
+    R0 = {k: v.detach().clone() for k, v in R.items()}
     rng = np.random.default_rng(seed)
-    steps, t_total, it = 0, 0.0, 0
-    while it < max_steps and (t_total < budget_s or it == 0):
-        users = rng.integers(0, cfg["U"], size=B_sample)
+    users = draw_users(cfg, np.random.default_rng(5), B_sample)
+    steps, t_total, it, timed = 0, 0.0, 0, 0
+    while it < max_steps and (t_total < budget_s or timed == 0):
+        with torch.no_grad():
+            for k in P:
+                P[k].copy_(P0[k])
+                P[k].grad = None
+            for k in R:
+                R[k] = R0[k].detach().clone()
+        from oracle import ppo
+        objs = (env, tracker, P, R, ppo.AdamDup(), ppo.AdamDup(), ppo.RunningMeanStd())
         t0 = time.perf_counter()
         n = oracle_step(cfg, objs, users, rng)
         dt = time.perf_counter() - t0
-        if it > 0 or max_steps == 1:       # first iteration is warm-up unless it is the only one
-            steps, t_total = steps + n, t_total + dt
+        if it >= warm or max_steps == 1:
+            steps, t_total, timed = steps + n, t_total + dt, timed + 1
         it += 1
     return dict(value=steps / max(t_total, 1e-9), unit="env-steps/s", cores=cores, kind="port",
-                sample=f"{B_sample} envs x {max(it - 1, 1)} iterations of the same workload (oracle/pipeline.py collect + "
-                       f"update, torch CPU {torch.get_num_threads()} threads), {t_total:.1f} s"), steps, t_total, it
+                sample=f"{B_sample} envs x {timed} iterations of the same frozen workload (oracle/pipeline.py collect "
+                       f"+ update, torch CPU {torch.get_num_threads()} threads), {t_total:.1f} s",
+                env_steps_per_step=steps / max(timed, 1)), steps, t_total, timed
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -130,7 +194,7 @@ class Clocks:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                       stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -157,14 +221,51 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def window(t, N):
+    """Number of history items the exit test of turn t reads (kuaishouEnv.py:199-218 with the negative-slice quirk)."""
+    return np.where(t == 0, 0, np.where(t < N, t - np.maximum(0, 2 * t - N), N))
+
+
 def k1_bytes(lens, N):
     """Algorithmic HBM bytes of the env-step kernel over whole episodes (mask-recompute variant):
     bytes(t) = 57 + 20 w(t, N) + 20 t."""
     tot = 0
     for n, c in zip(*np.unique(lens, return_counts=True)):
         t = np.arange(int(n))
-        w = np.where(t == 0, 0, np.where(t < N, t - np.maximum(0, 2 * t - N), N))
-        tot += int(c) * int(np.sum(57 + 20 * w + 20 * t))
+        tot += int(c) * int(np.sum(57 + 20 * window(t, N) + 20 * t))
+    return tot
+
+
+def rollout_bytes(cfg, lens):
+    """Algorithmic HBM bytes of ONE launch of the fused rollout kernel: per env-step K1
+    (57 + 20 w + 20 t) + K2 (one embedding row, this position's K / V written and the p cached positions read for
+    every layer, the state) + the replay-buffer rows (obs, obs_next, act, rew, done); per launch W3 + b3 once and the
+    tracker's dense weights once; per episode the user token."""
+    d, S, nl = cfg["d"], REF["dim_state"], 2
+    tot = 0
+    for n, c in zip(*np.unique(lens, return_counts=True)):
+        t = np.arange(int(n))
+        k1 = 57 + 20 * window(t, cfg["N"]) + 20 * t
+        p = t + 1                                                    # sequence position of the action token
+        k2 = 4 * d + 2 * nl * 4 * d * (1 + p) + 4 * S
+        traj = 2 * 4 * S + 4 + 4 + 1
+        tot += int(c) * (int(np.sum(k1 + k2 + traj)) + 4 * d + 2 * nl * 4 * d + 4 * S)   # + user token (position 0)
+    tot += 4 * (64 * cfg["I"] + cfg["I"])                           # W3, b3
+    tot += 4 * (2 * (4 * d * d + 2 * d * 128 + 9 * d + 128) + 2 * d * d + 2 * d + d * S + S)   # tracker dense weights
+    return tot
+
+
+def taobao_bytes(cfg, lens):
+    """Algorithmic HBM bytes of one launch of rollout_taobao_kernel: per env-step 705 + 108 (min(t, N-1) + t) (SURVEY
+    8d: user row, MMOE inputs, history rows) + K/V cache traffic + trajectory rows."""
+    d, S, nl, N = cfg["d"], REF["dim_state"], 2, cfg["N"]
+    tot = 0
+    for n, c in zip(*np.unique(lens, return_counts=True)):
+        t = np.arange(int(n))
+        k1 = 705 + 108 * (np.minimum(t, N - 1) + t)
+        k2 = 2 * nl * 4 * d * (2 + t) + 4 * S
+        traj = 2 * 4 * S + 2 * 4 * 27 + 4 + 1
+        tot += int(c) * int(np.sum(k1 + k2 + traj))
     return tot
 
 
@@ -172,6 +273,8 @@ def setup_workload(cfg, tb, dev, rank=0):
     """Build env / tracker / policy / buffer / collector for a config through the public (reference-facing) API."""
     import torch
     import cirs_codes_b200 as cb
+    if cfg["kind"] == "taobao":
+        return setup_taobao(cfg, tb, dev, rank)
     B, T = cfg["B"], cfg["T"]
 
     class _E:
@@ -203,6 +306,62 @@ def setup_workload(cfg, tb, dev, rank=0):
     return env, trk, pol, buf, col
 
 
+def setup_taobao(cfg, tb, dev, rank=0):
+    """CIRS-RL-taobao.py:152-260 through this package's classes: SimulatedEnv(VirtualTB) with the MMOE reward model,
+    dense-input tracker (dim_model 27), ActorProb + Independent(Normal)."""
+    import torch
+    import cirs_codes_b200 as cb
+    from cirs_codes_b200.env import Box
+    B, T = cfg["B"], cfg["T"]
+    env = cb.TaobaoVectorEnv(B, tb["usermodel"], max_turn=T, num_leave_compute=cfg["N"], leave_threshold=cfg["thr"],
+                             tau=cfg["tau"], gamma_exposure=REF["gamma_exposure"], version=REF["version"], device=dev,
+                             seed=1000 + rank)
+    cols = cb.get_dataset_columns(cfg["d"], envname="VirtualTB-v0")
+    trk = cb.StateTrackerTransformer(cols[0], cols[1], cols[2], dim_model=cfg["d"], dim_state=REF["dim_state"],
+                                     dim_max_batch=B, dataset="VirtualTB-v0", has_user_embedding=cols[3],
+                                     has_action_embedding=cols[4], has_feedback_embedding=cols[5], nhead=cfg["nhead"],
+                                     d_hid=128, nlayers=2, dropout=0.0, device=dev, seed=2023, MAX_TURN=T)
+    torch.manual_seed(2023)
+    net = cb.Net(REF["dim_state"], hidden_sizes=[64, 64])
+    actor, critic = cb.ActorProb(net, (27,), max_action=1.0), cb.Critic(net)
+    cb.orthogonal_init(actor, critic)
+    optim = [torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=REF["lr"]),
+             torch.optim.Adam(trk.parameters(), lr=REF["lr"])]
+
+    def dist(*logits):
+        return torch.distributions.Independent(torch.distributions.Normal(*logits), 1)
+
+    pol = cb.PPOPolicy(actor, critic, optim, dist, discount_factor=REF["gamma"], max_grad_norm=REF["max_grad_norm"],
+                       eps_clip=REF["eps_clip"], vf_coef=REF["vf_coef"], ent_coef=REF["ent_coef"],
+                       reward_normalization=1, advantage_normalization=1, recompute_advantage=0, value_clip=1,
+                       gae_lambda=REF["gae_lambda"], action_space=Box(-1, 1, (27,)), device=dev, seed=77 + rank)
+    buf = cb.VectorReplayBuffer(B * T, B, device=dev)
+    col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state)
+    assert col.fused
+    return env, trk, pol, buf, col
+
+
+class Frozen:
+    """Snapshot of everything a training iteration changes (policy / tracker parameters, Adam moments and step
+    counters, the running return statistics, the sampler's counters).  Restored before EVERY iteration -- warm-up,
+    resident arm, end-to-end arm, profile pass, at every --gpus N and --steps K -- so each iteration is the same
+    workload: the same users play against the same (initial) policy with the same sampler stream, and the iteration
+    still performs its full update.  The restore (a few device-to-device copies) sits with the L2 flush between the
+    timed iterations, outside the event-timed region."""
+
+    def __init__(self, pol, trk, col):
+        self.pol, self.col = pol, col
+        self.tensors = [pol.flat, pol.exp_avg, pol.exp_avg_sq, pol.opt_state, pol.ret_rms.t, trk.flat, trk.exp_avg,
+                        trk.exp_avg_sq, trk.opt_state, col._f["rng"]]
+        self.saved = [t.clone() for t in self.tensors]
+        self.calls = pol._calls
+
+    def restore(self):
+        for t, s in zip(self.tensors, self.saved):
+            t.copy_(s)
+        self.pol._calls = self.calls
+
+
 def gpu_arm(args, cfg):
     import torch
     import cirs_codes_b200 as cb
@@ -214,15 +373,29 @@ def gpu_arm(args, cfg):
     dist = torch.distributed if world > 1 else None
     tb = tables(cfg)
     B, T = cfg["B"], cfg["T"]
+    taobao = cfg["kind"] == "taobao"
     env, trk, pol, buf, col = setup_workload(cfg, tb, dev, rank)
+    if args.rollout != "persistent":
+        col.persistent, col.use_graph = False, args.rollout == "graph"
     lib = _lib.load()
-    rng = np.random.default_rng(5 + rank)
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
-    def one_step(users, resident):
-        pol.perm_on_device = resident
-        res = col.collect(n_episode=B, users=users)
-        pol.update(0, buf, batch_size=cfg["batch_size"], repeat=cfg["repeat"])
+    # ---- the frozen workload: this rank's users (fixed), the initial policy, fixed minibatch permutations
+    users_h = draw_users(cfg, np.random.default_rng(5 + rank), B)
+    users_d = torch.as_tensor(users_h.astype(np.float32 if taobao else np.int32), device=dev)
+    col.collect(n_episode=B, users=users_h)          # allocations; episode lengths are not yet the frozen ones
+    frozen = Frozen(pol, trk, col)
+    frozen.restore()
+    res0 = col.collect(n_episode=B, users=users_h)   # the frozen iteration's collect: its transition count fixes n
+    n_tr = int(res0["n/st"])
+    prng = np.random.default_rng(99 + rank)
+    perms_h = [prng.permutation(n_tr).astype(np.int32) for _ in range(cfg["repeat"])]
+    perms_d = [torch.as_tensor(p, device=dev) for p in perms_h]
+
+    def one_step(resident):
+        res = col.collect(n_episode=B, users=users_d if resident else users_h)
+        assert res["n/st"] == n_tr, "the frozen workload moved"
+        pol.update(0, buf, batch_size=cfg["batch_size"], repeat=cfg["repeat"], perms=perms_d if resident else perms_h)
         return res
 
     def barrier():
@@ -231,24 +404,24 @@ def gpu_arm(args, cfg):
         torch.cuda.synchronize()
 
     def timed(K, resident):
-        users_all = [rng.integers(0, cfg["U"], size=B) for _ in range(K)]
-        if resident:
-            users_all = [torch.as_tensor(u.astype(np.int32), device=dev) for u in users_all]
-        steps, h2d, d2h, lens_all, ms = 0, 0, 0, [], 0.0
+        steps, h2d, d2h, ms = 0, 0, 0, 0.0
         per_step = []
         barrier()
         for k in range(K):
+            frozen.restore()
             flush.fill_(float(k))                       # evict L2 between timed iterations (untimed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()                          # ranks enter every timed iteration together
+                torch.cuda.synchronize()
             e0.record()
-            res = one_step(users_all[k], resident)
+            res = one_step(resident)
             e1.record()
             torch.cuda.synchronize()
             ms += e0.elapsed_time(e1)
             per_step.append(round(e0.elapsed_time(e1), 3))
             steps += res["n/st"]
-            lens_all.append(res["lens"])
             h2d += col.h2d_bytes + pol.h2d_bytes
             d2h += col.d2h_bytes + pol.d2h_bytes
         barrier()
@@ -259,36 +432,39 @@ def gpu_arm(args, cfg):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             ms, steps = float(tm[0]), float(t[1])
         timed.per_step = per_step
-        return ms, steps, h2d / K, d2h / K, np.concatenate(lens_all)
+        return ms, steps, h2d / K, d2h / K
 
     clocks = Clocks(dev.index or 0)
-    clocks.start()                  # sampler runs through warm-up and both timed regions (nvidia-smi starts slowly)
+    clocks.start()                  # sampler runs through warm-up, both timed regions and the profile pass
     for _ in range(max(args.warmup, 3)):
-        one_step(rng.integers(0, cfg["U"], size=B), False)
-    one_step(torch.as_tensor(rng.integers(0, cfg["U"], size=B).astype(np.int32), device=dev), True)
+        frozen.restore()
+        one_step(False)
+    frozen.restore()
+    one_step(True)
     l0 = lib.cirs_launch_count()
-    ms_res, steps_res, _, _, lens = timed(args.steps, True)
+    ms_res, steps_res, _, _ = timed(args.steps, True)
     per_step_res = list(timed.per_step)
     launches = lib.cirs_launch_count() - l0
-    ms_e2e, steps_e2e, h2d, d2h, _ = timed(args.steps, False)
+    ms_e2e, steps_e2e, h2d, d2h = timed(args.steps, False)
     per_step_e2e = list(timed.per_step)
-    clk = clocks.stop()
+    lens = np.asarray(res0["lens"])
 
-    # ---- per-kernel durations, live, CUDA events on the launching stream (separate pass: events perturb the step)
+    # ---- per-kernel durations, live, CUDA events on the launching stream (separate pass: events perturb the step);
+    # the workload is the same frozen iteration, so the algorithmic work per launch is exactly the timed region's
     kern, roof = {}, None
-    # every rank runs the profiled steps (the update contains collectives); rank 0 reports
     col.use_graph = False          # per-kernel events need real launches, not a graph replay
-    col.persistent = bool(args.profile_persistent)
+    col.persistent = bool(args.profile_persistent) and args.rollout == "persistent"
     for _ in range(2):
-        one_step(rng.integers(0, cfg["U"], size=B), False)
+        frozen.restore()
+        one_step(False)
     lib.cirs_profile_enable(1)
-    lens_p = []
-    n_prof = min(args.steps, 3)
+    n_prof = max(3, min(args.steps, 10))
     for _ in range(n_prof):
-        lens_p.append(one_step(rng.integers(0, cfg["U"], size=B), False)["lens"])
+        frozen.restore()
+        one_step(False)
     rep = _lib.profile_report()
     lib.cirs_profile_enable(0)
-    lens_p = np.concatenate(lens_p)
+    clk = clocks.stop()
     if rank == 0:
         peaks = {}
         try:
@@ -299,62 +475,92 @@ def gpu_arm(args, cfg):
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "of measured (MEASURED_PEAKS.json)" if peaks else "of fallback (B200_PROFILING.md)"
         total_ms = sum(v[1] for v in rep.values())
-        n_tr = int(lens_p.sum())
-        A, S = cfg["I"], REF["dim_state"]
+        S = REF["dim_state"]
+        A = 27 if taobao else cfg["I"]
+        rp = cfg["repeat"]
         head_flops = 2.0 * (S * 64 + 64 * 64 + 64 * A)
-        algo = {  # algorithmic work over the profiled pass, per kernel (DESIGN.md "kernels")
-            # the persistent rollout kernel = K3 (head contraction) + K1 + K2 for every env-step of the collect
-            "rollout_kuaishou_kernel": ("tensor", head_flops * n_tr),
-            "kuaishou_step_kernel": ("hbm", k1_bytes(lens_p, cfg["N"])),
-            "actor_head_kernel": ("tensor", head_flops * n_tr * (1 + 1) + 2.0 * (S * 64 + 64 * 64) * n_tr),
-            "head_logits_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
-            "head_dW3_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
-            "head_dh2_gemm": ("tensor", 2.0 * 64 * A * n_tr * cfg["repeat"]),
-            "row_loss_kernel": ("hbm", 4.0 * A * n_tr * cfg["repeat"]),
+        # algorithmic work of ONE iteration per kernel family (DESIGN.md "kernels"); prefix match on the kernel name
+        algo = {
+            "rollout_kuaishou_kernel": ("hbm", None if taobao else rollout_bytes(cfg, lens), head_flops * n_tr),
+            "rollout_taobao_kernel": ("hbm", taobao_bytes(cfg, lens) if taobao else None, None),
+            "kuaishou_step_kernel": ("hbm", None if taobao else k1_bytes(lens, cfg["N"]), None),
+            "actor_head_kernel": ("tensor", None, head_flops * n_tr),
             # tensor-core head (csrc/head_tc.cu): algorithmic flops of the FP32 contractions they replace; each is
-            # executed as three kind::tf32 MMAs (3xTF32), so the tensor pipe does 3x these flops at the TF32 rate
-            "head_tc_stats_kernel": ("tensor", 2.0 * 64 * A * n_tr * (cfg["repeat"] + 1)),
-            "head_tc_dh2_kernel": ("tensor", 2 * 2.0 * 64 * A * n_tr * cfg["repeat"]),
-            "head_tc_dw3_kernel": ("tensor", 2 * 2.0 * 64 * A * n_tr * cfg["repeat"]),
+            # executed as three kind::tf32 MMAs (3xTF32), so the tensor pipe does 3x these flops at the TF32 rate.
+            # F runs once per process_fn (log-prob of the stored actions) and once per minibatch row and repeat.
+            "head_tc_stats": ("tensor", None, 2.0 * 64 * A * n_tr * (rp + 1)),
+            "head_tc_dh2": ("tensor", None, 2 * 2.0 * 64 * A * n_tr * rp),
+            "head_tc_dw3": ("tensor", None, 2 * 2.0 * 64 * A * n_tr * rp),
+            "head_logits_gemm": ("tensor", None, 2.0 * 64 * A * n_tr * rp),
+            "head_dW3_gemm": ("tensor", None, 2.0 * 64 * A * n_tr * rp),
+            "head_dh2_gemm": ("tensor", None, 2.0 * 64 * A * n_tr * rp),
         }
         for name, (cnt, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
-            kern[name] = {"launches": cnt, "ms": round(ms, 4), "share": round(ms / total_ms, 4)}
-            if name in algo:
-                bound, work = algo[name]
-                ach = work / (ms * 1e-3) / (1e9 if bound == "hbm" else 1e12)
-                peak = hbm_peak if bound == "hbm" else tc_peak
-                kern[name].update(bound=bound, achieved=round(ach, 3), peak=peak, frac=round(ach / peak, 5),
-                                  unit="GB/s" if bound == "hbm" else "TFLOP/s")
+            kern[name] = {"launches": cnt, "ms": round(ms, 4), "share": round(ms / total_ms, 4),
+                          "us_per_step": round(1e3 * ms / n_prof, 2)}
+            base = name.strip("()").split("<")[0].split("::")[-1]
+            key = next((k for k in algo if base.startswith(k)), None)
+            if key is None:
+                continue
+            bound, nbytes, flops = algo[key]
+            sec = ms * 1e-3 / n_prof                          # this kernel family's time per iteration
+            if nbytes is not None:
+                ach = nbytes / sec / 1e9
+                kern[name].update(bound="hbm", achieved=round(ach, 3), peak=hbm_peak, frac=round(ach / hbm_peak, 6),
+                                  unit="GB/s", algorithmic_bytes_per_step=int(nbytes))
+            if flops is not None:
+                ach = flops / sec / 1e12
+                t = {"achieved": round(ach, 3), "peak": tc_peak, "frac": round(ach / tc_peak, 6), "unit": "TFLOP/s",
+                     "algorithmic_flops_per_step": flops}
+                if nbytes is None:
+                    kern[name].update(bound="tensor", **t)
+                else:
+                    kern[name]["tensor"] = t
         top = next((k for k in kern if "bound" in kern[k]), None)
         traffic = {}
-        try:   # DRAM bytes per launch from this round's ncu --set full captures (profiles/), same workload
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        try:   # DRAM bytes per launch from the ncu --set full captures kept under profiles/ (same workload)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             pass
         if top:
-            roof = {"kernel": top, "bound": kern[top]["bound"], "achieved": kern[top]["achieved"],
-                    "peak": kern[top]["peak"], "unit": kern[top]["unit"], "frac": kern[top]["frac"],
-                    "traffic": traffic.get(top) if cfg["name"].startswith("configs[1]") else None,
-                    "peak_source": which, "share_of_step": kern[top]["share"],
-                    "note": "FP32-accurate contraction (3xTF32 tcgen05 MMAs, or FFMA) measured against the dense bf16 tensor "
-                            "peak; the 3xTF32 scheme's own ceiling is peak/6" if kern[top]["bound"] == "tensor"
-                    else "algorithmic bytes 57+20w+20t per env-step"}
+            k = kern[top]
+            roof = {"kernel": top, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"],
+                    "frac": k["frac"], "traffic": traffic.get(args.config, {}).get(top.strip("()").split("<")[0]),
+                    "peak_source": which, "share_of_step": k["share"], "launches_per_step": k["launches"] / n_prof,
+                    "us_per_launch": round(1e3 * k["ms"] / k["launches"], 2)}
+            if k["bound"] == "hbm":
+                roof["algorithmic_bytes_per_launch"] = int(k["algorithmic_bytes_per_step"] * n_prof / k["launches"])
+                roof["note"] = ("algorithmic bytes per launch = sum over the collect's env-steps of K1 (57+20w+20t) + K2 "
+                                "(embedding row, K/V cache rows, state) + replay-buffer rows, + W3 and the tracker's "
+                                "dense weights once (bench.rollout_bytes); the kernel is latency-bound, see DESIGN.md")
+                if "tensor" in k:
+                    roof["tensor"] = dict(k["tensor"], note="head contraction as FP32-accurate 3xTF32 tcgen05 MMAs "
+                                                            "against the dense bf16 peak; the scheme's own ceiling is peak/6")
+            else:
+                roof["note"] = ("FP32-accurate contraction (3xTF32 tcgen05 MMAs) measured against the dense bf16 tensor "
+                                "peak; the 3xTF32 scheme's own ceiling is peak/6")
     out = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu, *_ = cpu_arm(cfg, tb, min(B, args.cpu_envs), args.cpu_seconds, 50)
+            cpu, *_ = cpu_arm(cfg, tb, min(B, args.cpu_envs or 512), args.cpu_seconds, 50)
         out = {
             "metric": "env-steps/sec (rollout+PPO update)", "value": steps_res / (ms_res * 1e-3), "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["name"], "envs_per_gpu": B, "global_envs": B * world,
-                       "mean_episode_len": float(np.mean(lens)), "env_steps_per_step": steps_res / args.steps,
+                       "frozen": "every iteration (warm-up, timed, e2e, profile; any --steps / --gpus) restores the "
+                                 "initial policy / tracker / Adam / return statistics and replays the same users, so "
+                                 "env_steps_per_step is a constant of the config; the iteration still runs its full "
+                                 "update",
+                       "mean_episode_len": float(np.mean(lens)), "max_episode_len": int(np.max(lens)),
+                       "env_steps_per_step": steps_res / args.steps,
+                       "env_steps_per_step_rank0": n_tr,
                        "parallelism": f"env-sharded dp{world}", "l2": "192 MB flush between timed iterations",
                        "timing": "CUDA events per step, max over ranks", "ms_each_step_rank0": per_step_res},
             "e2e": {"value": steps_e2e / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                    "ms_each_step_rank0": per_step_e2e},
+                    "env_steps_per_step": steps_e2e / args.steps, "ms_each_step_rank0": per_step_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
         }
     if dist is not None:
@@ -464,12 +670,13 @@ def user_model_arm(cfg, dev, reps=5, cpu_users=1024):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="configs1", choices=sorted(CONFIGS))
     ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
-    ap.add_argument("--cpu-envs", type=int, default=128)
+    ap.add_argument("--cpu-envs", type=int, default=0,
+                    help="environments of the CPU arms (0 = the config's full count per GPU, at most 4096)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rollout", default="persistent", choices=["persistent", "graph", "eager"])
@@ -486,16 +693,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # the reference's algorithm on this box's host cores: the CPU oracle port (the Python reference itself cannot
+        # travel to the GPU box), at the config's FULL environment count per GPU, same frozen workload as the GPU arm;
+        # bounded to ~2 minutes of timed iterations
         tb = tables(cfg)
-        B = min(cfg["B"], args.cpu_envs)
-        cpu, steps, t_total, it = cpu_arm(cfg, tb, B, 1e9, args.warmup + args.steps if args.steps < 20 else 20)
+        B = min(cfg["B"], args.cpu_envs or 4096)
+        cpu, steps, t_total, it = cpu_arm(cfg, tb, B, 120.0, args.warmup + args.steps, warm=min(args.warmup, 1))
         v = cpu["value"]
-        cpu["value"] = v
         print(json.dumps({
             "impl": "reference", "metric": "env-steps/sec (rollout+PPO update)", "value": v, "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(it - 1, 1),
+            "n_gpus": args.gpus, "steps": it, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_total / max(it, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "sample_envs": B}, "cpu_baseline": cpu,
+            "config": {"workload": cfg["name"], "envs": B, "env_steps_per_step": cpu["env_steps_per_step"],
+                       "frozen": "same frozen workload as the GPU arm (initial policy restored every iteration)"},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     if args.only_user_model:
@@ -504,7 +715,7 @@ def main():
         return
     out = gpu_arm(args, cfg)
     if out is not None:
-        if not args.no_user_model and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        if not args.no_user_model and int(os.environ.get("WORLD_SIZE", "1")) == 1 and cfg["kind"] == "kuaishou":
             import torch
             torch.cuda.empty_cache()
             try:

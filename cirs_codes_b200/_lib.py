@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcirs_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LAYERS = 4
 HIDDEN = 64
 
@@ -101,11 +101,11 @@ PROTOTYPES = {
                                     fp, fp]),
     "cirs_actorprob_eval": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp]),
     "cirs_rollout_taobao": (i32, [P(TaobaoEnvStruct), P(TrackerWeightsStruct), P(PolicyWeightsStruct), fp, fp, fp,
-                                  i32, fp, fp, fp, fp, fp, fp, fp, fp, fp, u64, fp, i32, i32, i32, fp]),
+                                  i32, fp, fp, fp, fp, fp, fp, fp, fp, fp, i32, u64, fp, i32, i32, i32, fp]),
     "cirs_rollout_workspace_bytes": (i64, [i32, i32]),
     "cirs_rollout_kuaishou": (i32, [P(KuaishouEnvStruct), P(TrackerWeightsStruct), P(PolicyWeightsStruct), fp, fp, fp,
-                                    fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, fp, fp, u64, fp, i32, i32, i32,
-                                    fp, fp]),
+                                    fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, fp, fp, i32, u64, fp, i32, i32,
+                                    i32, fp, fp]),
     "cirs_compute_returns": (i32, [i32, i32, fp, fp, fp, fp, fp, f64, f64, fp, fp, fp, fp, fp, fp]),
     "cirs_rms_update": (i32, [fp, fp, fp]),
     "cirs_adv_stats": (i32, [i32, fp, fp, fp, fp, fp]),
@@ -113,9 +113,16 @@ PROTOTYPES = {
     "cirs_ppo_minibatch": (i32, [P(PolicyWeightsStruct), P(PolicyWeightsStruct), P(PPOConfigStruct), i32, i32, fp,
                                  fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp]),
     "cirs_ppo_learn": (i32, [P(PolicyWeightsStruct), P(PolicyWeightsStruct), fp, fp, P(PPOConfigStruct), i32, i32,
-                             fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp]),
+                             fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp, fp, fp]),
+    "cirs_update_plan": (i32, [i32, i32, fp, fp, fp, fp]),
+    "cirs_gather_i32": (i32, [fp, fp, fp, i32, fp]),
+    "cirs_comm_unique_id": (i32, [fp]),
+    "cirs_comm_create": (i32, [fp, i32, i32, P(fp)]),
+    "cirs_comm_destroy": (i32, [fp]),
+    "cirs_comm_allreduce": (i32, [fp, fp, i64, i32, fp]),
     "cirs_head_tc_enable": (None, [i32]),
     "cirs_head_tc_timeout": (i32, []),
+    "cirs_head_tc_timeout_peek": (i32, [fp, fp]),
     "cirs_user_model_workspace_bytes": (i64, [i32, i32, i32]),
     "cirs_user_model_predict_all": (i32, [P(UserModelStruct), i32, fp, i32, fp, fp, fp, i32, fp, fp, fp, fp]),
     "cirs_user_model_tc_enable": (None, [i32]),

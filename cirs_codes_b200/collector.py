@@ -226,7 +226,9 @@ class Collector:
         B, T = self.env_num, env.max_turn
         buf._alloc(trk.dim_state)
         L = buf.sub_size
-        assert L >= T or self.force_length > 0, "buffer_size must be >= env_num * max_turn (SURVEY §9 invariants)"
+        max_steps = self.force_length if self.force_length > 0 else T
+        assert L >= max_steps, "buffer_size must be >= env_num * max(max_turn, force_length) (SURVEY §9 invariants)"
+        assert self.force_length <= T, "force_length must not exceed the environments' max_turn"
         f = self._fused_state()
         self.h2d_bytes = self.d2h_bytes = 0
         if torch.is_tensor(users) and users.is_cuda:                # inputs already resident in HBM
@@ -238,7 +240,7 @@ class Collector:
             self.h2d_bytes += 4 * B
         self.data = Batch()
         buf.reset()
-        max_steps = self.force_length if self.force_length > 0 else T
+        trk.build_state(dim_batch=B, reset=True)       # K/V caches sized for THIS collector's environments
         if self.persistent:
             # the whole rollout in ONE persistent cooperative kernel (csrc/rollout.cu)
             pol = self.policy
@@ -250,8 +252,8 @@ class Collector:
                       _lib.ptr(f["value"]), _lib.ptr(f["cur"]), _lib.ptr(env.rew), _lib.ptr(env.done), L,
                       _lib.ptr(buf.obs), _lib.ptr(buf.obs_next), _lib.ptr(buf.d_act), _lib.ptr(buf.d_rew),
                       _lib.ptr(buf.d_done), _lib.ptr(buf.d_len), _lib.ptr(trk.kcache), _lib.ptr(trk.vcache),
-                      pol.seed, _lib.ptr(f["rng"]), mode, max_steps, self.force_length, _lib.ptr(f["ws_roll"]),
-                      _lib.stream())
+                      int(trk.kcache.shape[1]), pol.seed, _lib.ptr(f["rng"]), mode, max_steps, self.force_length,
+                      _lib.ptr(f["ws_roll"]), _lib.stream())
             buf.d_users.copy_(f["d_users"])
         elif self.use_graph:
             if self._graph is None:
@@ -264,25 +266,35 @@ class Collector:
             self._graph.replay()                                     # the whole rollout: ONE graph launch
         else:
             self._rollout_body(max_steps, poll=True)
-        lens, rews = self._read_back(buf.d_len, env.cum_rew)        # the collect's D2H read (one synchronisation)
-        self.d2h_bytes += 4 * B + 8 * B
+        buf.plan_device()                                           # sample_index(0) / offsets for the update, on device
+        if hasattr(self.policy, "post_collect"):
+            self.policy.post_collect(buf)                           # multi-GPU: transition counts ride on the read-back
+        flag = f["ws_roll"][128:132].view(torch.int32) if self.persistent else None
+        lens, rews = self._read_back(buf.d_len, env.cum_rew, flag)  # the collect's D2H read (one synchronisation)
+        self.d2h_bytes += 4 * B + 8 * B + 4
         buf.set_from_device(lens)
         order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
         res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])
         res["turns"] = int(lens.max()) if len(lens) else 0
         return res
 
-    def _read_back(self, d_len, d_rew):
-        """Episode lengths (i32) and cumulative rewards (f64) -> pinned host buffers, two asynchronous copies and ONE
-        stream synchronisation."""
+    def _read_back(self, d_len, d_rew, d_flag=None):
+        """Episode lengths (i32) and cumulative rewards (f64) -> pinned host buffers, asynchronous copies and ONE
+        stream synchronisation.  ``d_flag``: the rollout kernel's "an mbarrier wait gave up" word (never expected):
+        a set flag means the head phase computed with incomplete data, so the collect raises instead of returning."""
         B = self.env_num
         if not hasattr(self, "_pin_out"):
             self._pin_out = (torch.zeros(B, dtype=torch.int32).pin_memory(),
-                             torch.zeros(B, dtype=torch.float64).pin_memory())
-        p_len, p_rew = self._pin_out
+                             torch.zeros(B, dtype=torch.float64).pin_memory(),
+                             torch.zeros(1, dtype=torch.int32).pin_memory())
+        p_len, p_rew, p_flag = self._pin_out
         p_len.copy_(d_len[:B], non_blocking=True)
         p_rew.copy_(d_rew[:B], non_blocking=True)
+        if d_flag is not None:
+            p_flag.copy_(d_flag, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if d_flag is not None and int(p_flag[0]):
+            raise _lib.CirsError("cirs_rollout_kuaishou: a tcgen05 mbarrier wait timed out; the rollout is invalid")
         return p_len.numpy().astype(np.int64), p_rew.numpy().copy()
 
     # ---- fused path, VirtualTaobao: the whole collect is ONE kernel, one warp per environment (csrc/rollout_taobao.cu)
@@ -291,7 +303,9 @@ class Collector:
         B, T = self.env_num, env.max_turn
         buf._alloc(trk.dim_state, act_dim=27, user_dim=88)
         L = buf.sub_size
-        assert L >= T or self.force_length > 0, "buffer_size must be >= env_num * max_turn (SURVEY §9 invariants)"
+        max_steps = self.force_length if self.force_length > 0 else T
+        assert L >= max_steps, "buffer_size must be >= env_num * max(max_turn, force_length) (SURVEY §9 invariants)"
+        assert self.force_length <= T, "force_length must not exceed the environments' max_turn"
         if not hasattr(self, "_f"):
             self._f = dict(cur=torch.zeros(B, trk.dim_state, dtype=torch.float32, device=dev),
                            rng=torch.zeros(1, dtype=torch.int64, device=dev),
@@ -308,13 +322,16 @@ class Collector:
         self.data = Batch()
         buf.reset()
         trk.build_state(dim_batch=B, reset=True)
-        max_steps = self.force_length if self.force_length > 0 else T
         mode = 1 if (pol._deterministic_eval and not pol.training) else 0
         _lib.call("cirs_rollout_taobao", C.byref(env._struct_raw), C.byref(trk._w), C.byref(pol._w),
                   _lib.ptr(buf.d_users_dense), _lib.ptr(env.active), _lib.ptr(f["cur"]), L, _lib.ptr(buf.obs),
                   _lib.ptr(buf.obs_next), _lib.ptr(buf.d_act), _lib.ptr(buf.d_act_env), _lib.ptr(buf.d_rew),
-                  _lib.ptr(buf.d_done), _lib.ptr(buf.d_len), _lib.ptr(trk.kcache), _lib.ptr(trk.vcache), pol.seed,
-                  _lib.ptr(f["rng"]), mode, max_steps, self.force_length, _lib.stream())
+                  _lib.ptr(buf.d_done), _lib.ptr(buf.d_len), _lib.ptr(trk.kcache), _lib.ptr(trk.vcache),
+                  int(trk.kcache.shape[1]), pol.seed, _lib.ptr(f["rng"]), mode, max_steps, self.force_length,
+                  _lib.stream())
+        buf.plan_device()
+        if hasattr(pol, "post_collect"):
+            pol.post_collect(buf)
         lens, rews = self._read_back(buf.d_len, env.cum_rew)
         self.d2h_bytes += 4 * B + 8 * B
         buf.set_from_device(lens)

@@ -74,6 +74,11 @@ extern "C" int cirs_kuaishou_step(const cirs_kuaishou_env* env, int32_t n_rows, 
     cirs_set_error("cirs_kuaishou_step: trajectory outputs must be given together");
     return CIRS_ERR_ARG;
   }
+  if (force_length > env->max_turn || (traj_act && force_length > traj_len)) {
+    // the history has max_turn slots and the trajectory traj_len: a longer forced episode would read / write past them
+    cirs_set_error("cirs_kuaishou_step: force_length exceeds env->max_turn or traj_len");
+    return CIRS_ERR_ARG;
+  }
   if (n_rows == 0) return CIRS_OK;
   const int grid = (n_rows + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   CIRS_LAUNCH(kuaishou_step_kernel, grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream, 

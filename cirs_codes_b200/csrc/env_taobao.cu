@@ -76,6 +76,10 @@ extern "C" int cirs_taobao_step(const cirs_taobao_env* env, int32_t n_rows, cons
     cirs_set_error("cirs_taobao_step: trajectory outputs must be given together");
     return CIRS_ERR_ARG;
   }
+  if (force_length > env->max_turn || (traj_rew && force_length > traj_len)) {
+    cirs_set_error("cirs_taobao_step: force_length exceeds env->max_turn or traj_len");
+    return CIRS_ERR_ARG;
+  }
   if (n_rows == 0) return CIRS_OK;
   const int grid = (n_rows + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   CIRS_LAUNCH(taobao_step_kernel, grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream, *env, n_rows, env_id, active,

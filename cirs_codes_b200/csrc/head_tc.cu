@@ -1080,6 +1080,21 @@ extern "C" int cirs_head_tc_timeout(void) {
   int v = 0, z = 0;
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(&v, cirs_head_tc::g_tc_timeout, sizeof(int));
-  cudaMemcpyToSymbol(cirs_head_tc::g_tc_timeout, &z, sizeof(int));
+  if (v) cudaMemcpyToSymbol(cirs_head_tc::g_tc_timeout, &z, sizeof(int));
   return v;
+}
+// stream-ordered copy of the flag into PINNED host memory (no synchronisation): the product path folds it into the
+// update's own read-back and raises when it is set (policy.py)
+extern "C" int cirs_head_tc_timeout_peek(int32_t* out_pinned_h, void* stream) {
+  if (!out_pinned_h) {
+    cirs_set_error("cirs_head_tc_timeout_peek: null argument");
+    return CIRS_ERR_ARG;
+  }
+  cudaError_t e = cudaMemcpyFromSymbolAsync(out_pinned_h, cirs_head_tc::g_tc_timeout, sizeof(int), 0,
+                                            cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    cirs_set_error(cudaGetErrorString(e));
+    return CIRS_ERR_CUDA;
+  }
+  return CIRS_OK;
 }

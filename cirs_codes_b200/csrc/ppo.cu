@@ -741,35 +741,50 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   return CIRS_OK;
 }
 
-// The whole learn() loop of one update for a single process (core/policy/ppo.py:173-233): for every repeat, the
-// advantage statistics of all minibatches, then per minibatch forward / loss / backward / clip / Adam -- issued
-// back to back from C so that the host pays one call instead of ~20 launches' worth of interpreter overhead per
-// minibatch.  Multi-process runs use the per-minibatch entry points with an all-reduce in between.
+// The whole learn() loop of one update (core/policy/ppo.py:173-233): the advantage statistics of every minibatch of
+// every repeat (they depend on the permutations only), then per repeat and minibatch forward / loss / backward /
+// [gradient all-reduce] / clip / Adam -- issued back to back from C so that the host pays one call instead of ~20
+// launches' worth of interpreter overhead per minibatch.  With a communicator (comm.cu) this is the data-parallel
+// loop of SURVEY 8e: every rank holds its own chunk of each global minibatch; the statistics are summed over ranks
+// once, the flat gradient once per minibatch, everything stream-ordered.
+int cirs_comm_allreduce_impl(void* comm, void* buf, int64_t count, int dtype, cudaStream_t st);
+
 extern "C" int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grads, float* exp_avg,
                               float* exp_avg_sq, const cirs_ppo_config* cfg, int32_t n_repeat, int32_t n_mb,
                               const int32_t* mb_off_h, const int32_t* mb_off, const int32_t* slots, const float* obs,
                               const void* act, const float* adv, const float* returns, const float* v_old,
                               const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats,
-                              float* losses, int32_t* opt_state, double* opt_scratch, void* workspace,
-                              void* stream) {
+                              float* losses, int32_t* opt_state, double* opt_scratch, void* workspace, void* comm,
+                              const int32_t* n_global_h, void* stream) {
   if (!w || !grads || !exp_avg || !exp_avg_sq || !cfg || !mb_off_h || !mb_off || !slots || !adv_stats || !losses ||
-      !opt_state || !opt_scratch || n_repeat < 0 || n_mb < 0) {
+      !opt_state || !opt_scratch || n_repeat < 0 || n_mb < 0 || (comm && !n_global_h)) {
     cirs_set_error("cirs_ppo_learn: bad argument");
     return CIRS_ERR_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t n = mb_off_h[n_mb];
   for (int r = 0; r < n_repeat; ++r) {
+    int rc = cirs_adv_stats(n_mb, mb_off, slots + (int64_t)r * n, adv, adv_stats + (int64_t)r * n_mb * 3, stream);
+    if (rc) return rc;
+  }
+  if (comm) {
+    int rc = cirs_comm_allreduce_impl(comm, adv_stats, (int64_t)n_repeat * n_mb * 3, 1, st);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < n_repeat; ++r) {
     const int32_t* sl = slots + (int64_t)r * n;
     double* stats = adv_stats + (int64_t)r * n_mb * 3;
-    int rc = cirs_adv_stats(n_mb, mb_off, sl, adv, stats, stream);
-    if (rc) return rc;
     if (d_obs) cudaMemsetAsync(d_obs, 0, sizeof(float) * d_obs_floats, st);   // optim_state.zero_grad(), ppo.py:174
     for (int j = 0; j < n_mb; ++j) {
       const int b = mb_off_h[j], cnt = mb_off_h[j + 1] - b;
-      rc = cirs_ppo_minibatch(w, grads, cfg, cnt, cnt, sl + b, obs, act, adv, returns, v_old, logp_old,
-                              stats + 3 * j, d_obs, losses + 4 * ((int64_t)r * n_mb + j), workspace, stream);
+      int rc = cirs_ppo_minibatch(w, grads, cfg, cnt, n_global_h ? n_global_h[j] : cnt, sl + b, obs, act, adv, returns,
+                                  v_old, logp_old, stats + 3 * j, d_obs, losses + 4 * ((int64_t)r * n_mb + j), workspace,
+                                  stream);
       if (rc) return rc;
+      if (comm) {   // ONE collective per minibatch: the flat actor / critic gradient (2.8 MB at 10728 items)
+        rc = cirs_comm_allreduce_impl(comm, grads->flat, grads->n_flat, 0, st);
+        if (rc) return rc;
+      }
       rc = cirs_clip_adam(w->flat, grads->flat, exp_avg, exp_avg_sq, w->n_flat, w->n_trunk, cfg, opt_state,
                           opt_scratch, stream);
       if (rc) return rc;

@@ -242,6 +242,22 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
 
 }  // namespace
 
+// cooperative-launch capacity (resident CTAs) per (device, kernel variant, dynamic shared memory); thread-safe
+#include <map>
+#include <mutex>
+#include <tuple>
+static std::mutex g_occ_mu;
+static std::map<std::tuple<int, int, size_t>, int> g_occ;
+static int occupancy_cache_get(int dev, int variant, size_t smem) {
+  std::lock_guard<std::mutex> lk(g_occ_mu);
+  auto it = g_occ.find(std::make_tuple(dev, variant, smem));
+  return it == g_occ.end() ? 0 : it->second;
+}
+static void occupancy_cache_put(int dev, int variant, size_t smem, int v) {
+  std::lock_guard<std::mutex> lk(g_occ_mu);
+  g_occ[std::make_tuple(dev, variant, smem)] = v;
+}
+
 // workspace: [counters 256 B][phase timers][list 2*B i32][h2 B*64 f32][head partials]
 constexpr int64_t DBG_BYTES = 8 * (1 + 6 * 512);   // phase timers of up to 512 turns
 static int64_t partial_capacity(int32_t n_env, int32_t n_action) {
@@ -258,8 +274,9 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
                                      int32_t* act, float* logp, float* value, float* cur_state, float* rew,
                                      uint8_t* done, int32_t traj_len, float* traj_obs, float* traj_obs_next,
                                      int32_t* traj_act, float* traj_rew, uint8_t* traj_done, int32_t* ep_len,
-                                     float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter, int32_t mode,
-                                     int32_t max_steps, int32_t force_length, void* workspace, void* stream) {
+                                     float* kcache, float* vcache, int32_t kv_n_env, uint64_t seed,
+                                     uint64_t* rng_counter, int32_t mode, int32_t max_steps, int32_t force_length,
+                                     void* workspace, void* stream) {
   if (!env || !tw || !pw || !users || !active || !act || !logp || !value || !cur_state || !rew || !done || !ep_len ||
       !kcache || !vcache || !workspace || max_steps < 0 || (mode & 3) > 1) {
     cirs_set_error("cirs_rollout_kuaishou: null argument or bad mode");
@@ -268,6 +285,16 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   if (!tw->emb_user || !tw->emb_item || tw->d % tw->nhead != 0 || tw->nlayers > CIRS_MAX_LAYERS ||
       tw->d_item_in != tw->d || tw->d_user_in != tw->d || max_steps + 1 > tw->max_len || max_steps > 512) {
     cirs_set_error("cirs_rollout_kuaishou: unsupported tracker shape (needs embedding tables, max_steps < max_len)");
+    return CIRS_ERR_ARG;
+  }
+  if (kv_n_env != env->n_env) {
+    cirs_set_error("cirs_rollout_kuaishou: the K/V caches are sized for a different number of environments "
+                   "(kv_n_env != env->n_env): rebuild them (build_state(dim_batch, reset=True)) before the collect");
+    return CIRS_ERR_ARG;
+  }
+  if (force_length > env->max_turn || max_steps > env->max_turn ||
+      (traj_len > 0 && (max_steps > traj_len || force_length > traj_len))) {
+    cirs_set_error("cirs_rollout_kuaishou: max_steps / force_length exceed env->max_turn or the trajectory length");
     return CIRS_ERR_ARG;
   }
   if (env->n_env <= 0) return CIRS_OK;
@@ -297,7 +324,6 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     smw_ok = tw->layer[l].in_wt >= w_lo && tw->layer[l].n2_b < w_lo + w_count;
   size_t smem = 0;
   bool smw = false;
-  static int max_ctas_v[4] = {0, 0, 0, 0};
   int max_ctas = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     size_t head = tc ? up128(cirs_actor_tc::TURN_BYTES > scratch_bytes ? cirs_actor_tc::TURN_BYTES : scratch_bytes)
@@ -318,10 +344,11 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     } else {
       A.w_lo = nullptr; A.w_count = 0; A.smem_w_off = 0;
     }
-    int& mc = max_ctas_v[(smw ? 1 : 0) + (tc ? 2 : 0)];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int mc = occupancy_cache_get(dev, (smw ? 1 : 0) + (tc ? 2 : 0), smem);
     if (!mc) {
-      int dev = 0, per_sm = 0, n_sm = 0;
-      cudaGetDevice(&dev);
+      int per_sm = 0, n_sm = 0;
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
       const void* fn = tc ? (smw ? (const void*)rollout_kuaishou_kernel<true, true> : (const void*)rollout_kuaishou_kernel<false, true>)
                           : (smw ? (const void*)rollout_kuaishou_kernel<true, false> : (const void*)rollout_kuaishou_kernel<false, false>);
@@ -336,6 +363,7 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
       }
       if (tc && per_sm > 1) per_sm = 1;   // TMEM: 256 columns per CTA, keep one CTA per SM
       mc = per_sm * n_sm;
+      occupancy_cache_put(dev, (smw ? 1 : 0) + (tc ? 2 : 0), smem, mc);
     }
     max_ctas = mc;
     if (tc && n_slices > max_ctas) { tc = false; continue; }   // catalogue too wide for one slice per CTA

@@ -72,8 +72,9 @@ extern "C" int cirs_rollout_taobao(const cirs_taobao_env* env, const cirs_tracke
                                    const cirs_policy_weights* pw, const float* users, uint8_t* active,
                                    float* cur_state, int32_t traj_len, float* traj_obs, float* traj_obs_next,
                                    float* traj_act, float* traj_act_env, float* traj_rew, uint8_t* traj_done,
-                                   int32_t* ep_len, float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter, int32_t mode,
-                                   int32_t max_steps, int32_t force_length, void* stream) {
+                                   int32_t* ep_len, float* kcache, float* vcache, int32_t kv_n_env, uint64_t seed,
+                                   uint64_t* rng_counter, int32_t mode, int32_t max_steps, int32_t force_length,
+                                   void* stream) {
   if (!env || !tw || !pw || !users || !active || !cur_state || !traj_obs || !traj_obs_next || !traj_act || !traj_act_env || !traj_rew ||
       !traj_done || !ep_len || !kcache || !vcache || max_steps < 1) {
     cirs_set_error("cirs_rollout_taobao: null argument");
@@ -84,6 +85,15 @@ extern "C" int cirs_rollout_taobao(const cirs_taobao_env* env, const cirs_tracke
       pw->n_action != NI || pw->dim_state != tw->dim_state || pw->dim_state > 32 || !env->map_action) {
     cirs_set_error("cirs_rollout_taobao: unsupported shapes (dense 88 / 27 tracker inputs, d = 27, continuous actor "
                    "with 27 actions, env->map_action = 1, max_steps < max_len)");
+    return CIRS_ERR_ARG;
+  }
+  if (kv_n_env != env->n_env) {
+    cirs_set_error("cirs_rollout_taobao: the K/V caches are sized for a different number of environments "
+                   "(kv_n_env != env->n_env): rebuild them (build_state(dim_batch, reset=True)) before the collect");
+    return CIRS_ERR_ARG;
+  }
+  if (force_length > env->max_turn || max_steps > env->max_turn || max_steps > traj_len || force_length > traj_len) {
+    cirs_set_error("cirs_rollout_taobao: max_steps / force_length exceed env->max_turn or the trajectory length");
     return CIRS_ERR_ARG;
   }
   Args A{};

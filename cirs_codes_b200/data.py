@@ -121,6 +121,9 @@ class VectorReplayBuffer:
         self.d_done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.d_len = torch.zeros(self.buffer_num, dtype=torch.int32, device=dev)   # transitions per environment
         self.d_users = torch.zeros(self.buffer_num, dtype=torch.int32, device=dev)  # episode's user (tracker bwd)
+        # sample_index(0) and the per-environment offsets of the last fused collect, built on the device
+        self.d_index = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.d_env_off = torch.zeros(self.buffer_num + 1, dtype=torch.int32, device=dev)
         self._alloc_done = True
 
     def reset(self, keep_statistics=False):
@@ -138,6 +141,7 @@ class VectorReplayBuffer:
         self._h_rew = np.zeros(self.maxsize, dtype=np.float64)
         self._h_done = np.zeros(self.maxsize, dtype=bool)
         self._host_valid, self._dev_valid = True, True     # which side holds the truth for act / rew / done
+        self._plan_ok = False                              # d_index / d_env_off describe the stored transitions
         if self._alloc_done:
             self.d_len.zero_()
 
@@ -161,6 +165,15 @@ class VectorReplayBuffer:
             self.d_done.copy_(torch.from_numpy(self._h_done.astype(np.uint8)))
             self.d_len.copy_(torch.from_numpy(self._lengths.astype(np.int32)))
             self._dev_valid = True
+
+    def plan_device(self):
+        """sample_index(0) on the device from the lengths the rollout kernel wrote (csrc/util.cu cirs_update_plan):
+        ``d_index[:n]`` = stored slots env-major, ``d_env_off[e]`` = first compact row of environment e,
+        ``d_env_off[B]`` = n.  Stream-ordered; the update reads them without any host round trip."""
+        from . import _lib
+        _lib.call("cirs_update_plan", self.buffer_num, self.sub_size, _lib.ptr(self.d_len), _lib.ptr(self.d_index),
+                  _lib.ptr(self.d_env_off), _lib.stream())
+        self._plan_ok = True
 
     def set_from_device(self, lengths):
         """Called by the fused rollout: the kernels wrote obs / obs_next / act / rew / done for env-major slots
@@ -225,6 +238,7 @@ class VectorReplayBuffer:
         self._ep_rew[fin], self._ep_len[fin] = 0.0, 0
         self._ep_idx[fin] = self._offset[fin] + self._index[fin]
         self._dev_valid = False
+        self._plan_ok = False
         return ptr, ep_rew, ep_len, ep_idx
 
     def sample_index(self, batch_size):

@@ -72,3 +72,25 @@ def init_from_env(backend="nccl"):
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world
+
+
+def create_comm(dist, group, device):
+    """The C-side NCCL communicator (csrc/comm.cu) for ``group``: rank 0 draws the unique id, torch.distributed
+    broadcasts its 128 bytes, every rank initialises with its CUDA device current.  Returns the opaque handle."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ident = (C.c_ubyte * 128)()
+    if rank == 0:
+        _lib.call("cirs_comm_unique_id", C.cast(ident, C.c_void_p))
+    t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device=device)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    raw = bytes(t.cpu().tolist())
+    ident = (C.c_ubyte * 128).from_buffer_copy(raw)
+    torch.cuda.set_device(device)
+    handle = C.c_void_p()
+    _lib.call("cirs_comm_create", C.cast(ident, C.c_void_p), rank, world, C.byref(handle))
+    assert lib is not None and handle.value
+    return handle

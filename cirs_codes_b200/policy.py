@@ -58,7 +58,7 @@ class PPOPolicy:
                  max_grad_norm=None, gae_lambda=0.95, max_batchsize=256, discount_factor=0.99,
                  reward_normalization=False, action_scaling=True, action_bound_method="clip", action_space=None,
                  lr_scheduler=None, deterministic_eval=False, state_tracker=None, device="cuda", seed=0,
-                 process_group=None, perm_on_device=False, **kwargs):
+                 process_group=None, **kwargs):
         _lib.require_cuda()
         _lib.load()
         assert dual_clip is None, "dual_clip is not used by CIRS (CIRS-RL-kuaishou.py:277-279)"
@@ -81,9 +81,26 @@ class PPOPolicy:
         self.action_scaling, self.action_bound_method = bool(action_scaling), action_bound_method
         self.seed, self._calls = int(seed), 0
         self.group = process_group
-        self.c_loop = True   # single process: run the repeat x minibatch loop inside one C call (cirs_ppo_learn)
-        self.perm_on_device = bool(perm_on_device)   # minibatch permutations from torch.randperm on the device
+        self.use_c_comm = True   # NCCL process groups: gradient all-reduces issued from C inside cirs_ppo_learn
+        self.c_loop = True       # False: per-minibatch entry points driven from Python (tests; gloo groups)
         self.h2d_bytes = self.d2h_bytes = 0          # host<->device traffic of the last update()
+        # The reference builds ONE Net shared by actor and critic (CIRS-RL-kuaishou.py:245-247) and lists its tensors
+        # twice in optim_RL / clip_grad_norm_; this implementation reproduces exactly that structure.
+        # A separate critic trunk, or an optimizer over de-duplicated parameters, would train differently: refuse it.
+        if actor.preprocess is not critic.preprocess:
+            a_sd, c_sd = actor.preprocess.state_dict(), critic.preprocess.state_dict()
+            same = a_sd.keys() == c_sd.keys() and all(torch.equal(a_sd[k], c_sd[k]) for k in a_sd)
+            raise ValueError("PPOPolicy: actor.preprocess must BE critic.preprocess (the reference's shared trunk); "
+                             + ("the two trunks hold equal tensors but are distinct modules" if same
+                                else "the critic has its own trunk weights, which this path would discard"))
+        trunk_ids = {id(p) for p in actor.preprocess.parameters()}
+        first = (optim[0] if isinstance(optim, (list, tuple)) else optim)
+        listed = [id(p) for g in first.param_groups for p in g["params"]]
+        dup = {i for i in trunk_ids if listed.count(i) == 2}
+        if trunk_ids and dup != trunk_ids:
+            raise ValueError("PPOPolicy: the policy optimizer must list the shared trunk's parameters twice, i.e. "
+                             "Adam(list(actor.parameters()) + list(critic.parameters())) as in "
+                             "CIRS-RL-kuaishou.py:256-258 (duplicate-trunk clip / Adam semantics, SURVEY 7.3-2)")
 
         dim_state = actor.preprocess.input_dim
         n_action = actor.output_dim
@@ -101,6 +118,9 @@ class PPOPolicy:
 
         def hyper(opt):
             g = opt.param_groups[0]
+            if g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False):
+                raise ValueError("PPOPolicy: weight_decay / amsgrad / maximize are not implemented by csrc/optim.cu "
+                                 "(the reference uses plain Adam, CIRS-RL-kuaishou.py:256-259)")
             return float(g["lr"]), tuple(g.get("betas", (0.9, 0.999))), float(g.get("eps", 1e-8))
 
         lr, betas, eps = hyper(self.optim[0])
@@ -292,6 +312,56 @@ class PPOPolicy:
         if world > 1:
             dist.all_reduce(t, group=self.group)
 
+    # ------------------------------------------------------------------ multi-GPU plumbing
+    def _comm(self):
+        """The C-side communicator of this policy's process group (csrc/comm.cu; NCCL), created on first use: rank 0
+        draws the NCCL unique id and torch.distributed broadcasts it.  None for a single process or a CPU (gloo) group
+        -- the latter keeps the per-minibatch Python loop with torch.distributed collectives (CPU tests)."""
+        dist, world = self._world()
+        if world == 1 or not self.use_c_comm:
+            return None
+        if getattr(self, "_c_comm", None) is None:
+            if dist.get_backend(self.group) != "nccl":
+                self.use_c_comm = False
+                return None
+            from .parallel import create_comm
+            self._c_comm = create_comm(dist, self.group, self.device)
+        return self._c_comm
+
+    def post_collect(self, buffer):
+        """Called by the fused Collector between the rollout kernel and its read-back: every rank's transition count
+        (buffer.d_env_off[B], written by cirs_update_plan) is summed into slot ``rank`` of a [world] vector and copied
+        to pinned host memory, so the collect's ONE synchronisation also delivers the minibatch plan of the following
+        update (parallel.plan_from_counts) -- no host sync inside update()."""
+        dist, world = self._world()
+        self._n_all_pin = None
+        if world == 1:
+            return
+        rank = dist.get_rank(self.group)
+        if getattr(self, "_cnt_dev", None) is None:
+            self._cnt_dev = torch.zeros(world, dtype=torch.int32, device=self.device)
+            self._cnt_pin = torch.zeros(world, dtype=torch.int32).pin_memory()
+        self._cnt_dev.zero_()
+        self._cnt_dev[rank:rank + 1].copy_(buffer.d_env_off[buffer.buffer_num:buffer.buffer_num + 1])
+        comm = self._comm()
+        if comm is not None:
+            _lib.call("cirs_comm_allreduce", comm, _lib.ptr(self._cnt_dev), world, 2, _lib.stream())
+        else:
+            dist.all_reduce(self._cnt_dev, group=self.group)
+        self._cnt_pin.copy_(self._cnt_dev, non_blocking=True)
+        self._n_all_pin = (self._cnt_pin, buffer)
+
+    def _allreduce(self, t):
+        dist, world = self._world()
+        if world == 1:
+            return
+        comm = self._comm()
+        if comm is not None and t.dtype in (torch.float32, torch.float64, torch.int32):
+            code = {torch.float32: 0, torch.float64: 1, torch.int32: 2}[t.dtype]
+            _lib.call("cirs_comm_allreduce", comm, _lib.ptr(t), t.numel(), code, _lib.stream())
+        else:
+            dist.all_reduce(t, group=self.group)
+
     def process_fn(self, buffer, indices):
         """core/policy/ppo.py:96-109 + a2c.py:80-109: critic values, GAE / returns, old log-probs -- all on the
         device, results stay per buffer slot."""
@@ -323,7 +393,13 @@ class PPOPolicy:
                   _lib.ptr(self._moments) if self._rew_norm else None, _lib.ptr(self.returns), _lib.ptr(self.adv), st)
         dist, world = self._world()
         self._n_all = None
-        if world > 1:
+        pin = getattr(self, "_n_all_pin", None)
+        if world > 1 and pin is not None and pin[1] is buffer and int(pin[0][dist.get_rank(self.group)]) == n:
+            # the counts travelled with the collect's read-back (post_collect): no collective, no host sync here
+            self._n_all = pin[0].numpy().astype(np.int64)
+            if self._rew_norm:
+                self._allreduce(self._moments)
+        elif world > 1:
             # ONE collective: the raw return moments and, in slot 3 + rank, this rank's transition count; the counts
             # give every rank the whole minibatch plan of this update (parallel.plan_from_counts)
             rank = dist.get_rank(self.group)
@@ -335,34 +411,43 @@ class PPOPolicy:
             if self._rew_norm:
                 self._moments.copy_(m[:3])
             self._n_all = m[3:].round().to(torch.int64).cpu().numpy()
+        self._n_all_pin = None
         if self._rew_norm:
             _lib.call("cirs_rms_update", _lib.ptr(self.ret_rms.t), _lib.ptr(self._moments), st)
 
-    def update(self, sample_size, buffer, batch_size=None, repeat=1, perms=None, **kwargs):
-        """policy/base.py:219-244: sample(0) -> process_fn -> learn.  ``perms`` (list of one permutation of
-        range(n) per repeat) overrides np.random.permutation for replayable parity runs."""
+    def update(self, sample_size, buffer, batch_size=None, repeat=1, perms=None, mb_sizes=None, **kwargs):
+        """policy/base.py:219-244: sample(0) -> process_fn -> learn.  ``perms`` (one permutation of range(n) per
+        repeat: host arrays, or int32 CUDA tensors already resident in HBM) overrides np.random.permutation for
+        replayable parity runs and for the resident-input benchmark arm.  ``mb_sizes`` (tests only) replaces the
+        minibatch sizes Batch.split would produce, so that one process can replay a data-parallel run's plan."""
         if buffer is None or len(buffer) == 0:
             return {}
         assert sample_size == 0, "on-policy: the whole buffer is used (core/trainer/onpolicy.py:199)"
         self.updating = True
         buffer.sync_device()
-        idx_h = buffer.sample_index(0)
-        indices = self._h2d_i32(idx_h)
-        self.h2d_bytes, self.d2h_bytes = indices.numel() * 4, 0
+        n = len(buffer)
+        self.h2d_bytes, self.d2h_bytes = 0, 0
+        if getattr(buffer, "_plan_ok", False):
+            indices = buffer.d_index[:n]       # sample_index(0) built on the device by the collect (cirs_update_plan)
+        else:
+            indices = self._h2d_i32(buffer.sample_index(0))
+            self.h2d_bytes += 4 * n
         self.process_fn(buffer, indices)
-        result = self.learn(buffer, idx_h, indices, batch_size or len(idx_h), repeat, perms=perms)
+        result = self.learn(buffer, n, indices, batch_size or n, repeat, perms=perms, mb_sizes=mb_sizes)
         self.updating = False
         return result
 
-    def learn(self, buffer, idx_h, indices, batch_size, repeat, perms=None):
+    def learn(self, buffer, n, indices, batch_size, repeat, perms=None, mb_sizes=None):
         """core/policy/ppo.py:166-246."""
-        n, dev, st = len(idx_h), self.device, _lib.stream()
+        dev, st = self.device, _lib.stream()
         dist, world = self._world()
         tracker = self.state_tracker if self.cfg_tracker is not None else None
-        losses_all = []
         from .parallel import plan_from_counts, sharded_sizes
         n_glob_plan = None
-        if world > 1 and getattr(self, "_n_all", None) is not None:
+        if mb_sizes is not None:
+            assert world == 1 and sum(mb_sizes) == n
+            sizes = [int(x) for x in mb_sizes]
+        elif world > 1 and getattr(self, "_n_all", None) is not None:
             sizes, n_glob_plan = plan_from_counts(self._n_all, dist.get_rank(self.group), batch_size)
         else:
             sizes = sharded_sizes(n, batch_size, dist if world > 1 else None, self.group, dev)
@@ -370,66 +455,92 @@ class PPOPolicy:
         offs[1:] = np.cumsum(sizes)
         d_offs = self._h2d_i32(offs)                 # pinned, asynchronous: no host sync in front of the learn loop
         n_mb = len(sizes)
-
-        def slots_for(step):
-            if perms is not None:
+        if getattr(self, "_learn_cap", (0, 0)) < (repeat * buffer.maxsize, repeat * (n_mb + 1)):
+            self._learn_cap = (repeat * buffer.maxsize, repeat * (n_mb + 1))
+            self._slots = torch.zeros(repeat * buffer.maxsize, dtype=torch.int32, device=dev)
+            self._stats = torch.zeros(repeat * (n_mb + 1) * 3, dtype=torch.float64, device=dev)
+            self._losses = torch.zeros(repeat * (n_mb + 1) * 4, dtype=torch.float32, device=dev)
+        d_slots, stats, losses = self._slots[:repeat * n], self._stats[:repeat * n_mb * 3], \
+            self._losses[:repeat * n_mb * 4]
+        for step in range(repeat):                  # minibatch order of repeat ``step``: indices[perm]  (batch.py:736)
+            if perms is not None and torch.is_tensor(perms[step]) and perms[step].is_cuda:
+                d_perm = perms[step]
+            else:
+                perm = np.asarray(perms[step]) if perms is not None else np.random.permutation(n)
+                d_perm = self._h2d_i32(perm)
                 self.h2d_bytes += 4 * n
-                return self._h2d_i32(idx_h[np.asarray(perms[step])])
-            if self.perm_on_device:
-                return indices[torch.randperm(n, device=dev)]
-            self.h2d_bytes += 4 * n
-            return self._h2d_i32(idx_h[np.random.permutation(n)])   # batch.py:736
+            assert d_perm.numel() == n and d_perm.dtype == torch.int32
+            _lib.call("cirs_gather_i32", d_slots.data_ptr() + 4 * n * step, _lib.ptr(indices), _lib.ptr(d_perm), n, st)
 
         # a chunk of Batch.split(merge_last) never exceeds 2 * batch_size - 1 rows: size the workspace once
         ws = self._ppo_ws(max(int(max(sizes)), min(buffer.maxsize, 2 * int(batch_size) - 1)))
         d_obs = self.d_obs if tracker is not None else None
-        if world == 1 and self.c_loop:
-            # single process: the whole repeat x minibatch loop is one C call (csrc/ppo.cu cirs_ppo_learn)
-            d_slots = torch.cat([slots_for(step) for step in range(repeat)])
-            stats = torch.zeros(repeat * n_mb, 3, dtype=torch.float64, device=dev)
-            losses = torch.zeros(repeat * n_mb, 4, dtype=torch.float32, device=dev)
+        comm = self._comm()
+        if self.c_loop and (world == 1 or comm is not None):
+            # the whole repeat x minibatch loop is ONE C call (csrc/ppo.cu cirs_ppo_learn); with a communicator the
+            # gradient all-reduce of every minibatch is issued from C between its kernels and clip + Adam
+            n_glob = None
+            if world > 1:
+                assert n_glob_plan is not None
+                n_glob = np.ascontiguousarray(n_glob_plan, dtype=np.int32)
             _lib.call("cirs_ppo_learn", C.byref(self._w), C.byref(self._g), _lib.ptr(self.exp_avg),
                       _lib.ptr(self.exp_avg_sq), C.byref(self.cfg), repeat, n_mb, offs.ctypes.data, _lib.ptr(d_offs),
                       _lib.ptr(d_slots), _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act), _lib.ptr(self.adv),
                       _lib.ptr(self.returns), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(stats),
                       _lib.ptr(d_obs), d_obs.numel() if d_obs is not None else 0, _lib.ptr(losses),
-                      _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), _lib.ptr(ws), st)
-            losses_all.append(losses)
+                      _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), _lib.ptr(ws), comm,
+                      n_glob.ctypes.data if n_glob is not None else None, st)
         else:
+            # CPU-side process group (gloo; tests): per-minibatch entry points with torch.distributed collectives.
             # advantage moments of every minibatch of every repeat (they depend on the permutations only): ONE collective
-            slots_all = [slots_for(step) for step in range(repeat)]
-            stats_all = torch.zeros(repeat, n_mb, 3, dtype=torch.float64, device=dev)
             for step in range(repeat):
-                _lib.call("cirs_adv_stats", n_mb, _lib.ptr(d_offs), _lib.ptr(slots_all[step]), _lib.ptr(self.adv),
-                          stats_all.data_ptr() + 24 * n_mb * step, st)
-            self._allreduce(stats_all)
+                _lib.call("cirs_adv_stats", n_mb, _lib.ptr(d_offs), d_slots.data_ptr() + 4 * n * step,
+                          _lib.ptr(self.adv), stats.data_ptr() + 24 * n_mb * step, st)
+            self._allreduce(stats)
             for step in range(repeat):
-                d_slots, stats = slots_all[step], stats_all[step]
                 n_glob = n_glob_plan if n_glob_plan is not None else \
-                    stats[:, 0].round().to(torch.int64).cpu().numpy()
-                losses = torch.zeros(n_mb, 4, dtype=torch.float32, device=dev)
+                    stats.view(repeat, n_mb, 3)[step, :, 0].round().to(torch.int64).cpu().numpy()
                 if tracker is not None:
                     self.d_obs.zero_()                                               # optim_state.zero_grad(), :174
                 for j in range(n_mb):
                     b, e = int(offs[j]), int(offs[j + 1])
                     _lib.call("cirs_ppo_minibatch", C.byref(self._w), C.byref(self._g), C.byref(self.cfg), e - b,
-                              int(n_glob[j]), d_slots.data_ptr() + 4 * b, _lib.ptr(buffer.obs),
+                              int(n_glob[j]), d_slots.data_ptr() + 4 * (n * step + b), _lib.ptr(buffer.obs),
                               _lib.ptr(buffer.d_act), _lib.ptr(self.adv), _lib.ptr(self.returns), _lib.ptr(self.v_s),
-                              _lib.ptr(self.logp_old), stats.data_ptr() + 24 * j, _lib.ptr(d_obs),
-                              losses.data_ptr() + 16 * j, _lib.ptr(ws), st)
+                              _lib.ptr(self.logp_old), stats.data_ptr() + 24 * (n_mb * step + j), _lib.ptr(d_obs),
+                              losses.data_ptr() + 16 * (n_mb * step + j), _lib.ptr(ws), st)
                     self._allreduce(self.grad)                                       # ONE collective per minibatch
                     _lib.call("cirs_clip_adam", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
                               _lib.ptr(self.exp_avg_sq), self.layout.total, self.layout.n_trunk, C.byref(self.cfg),
                               _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), st)
-                losses_all.append(losses)
         if tracker is not None:
             tracker.zero_grad()
             tracker.backward_from_buffer(buffer, self.d_obs, getattr(buffer, "d_users", None), tok_slot=indices)
             self._allreduce(tracker.grad)
             tracker.optim_step(self.cfg_tracker)                                     # optim_state.step(), :235
-        losses = torch.cat(losses_all)
         self._allreduce(losses)
-        lh = losses.cpu().numpy().astype(np.float64)                                 # the update's only D2H read
-        self.d2h_bytes += losses.numel() * 4
+        if getattr(self, "_tc_flag", None) is None:
+            self._tc_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _lib.call("cirs_head_tc_timeout_peek", self._tc_flag.data_ptr(), st)
+        lh = self._d2h_f32(losses).reshape(-1, 4).astype(np.float64)                 # the update's only D2H read
+        self.d2h_bytes += losses.numel() * 4 + 4
+        self.check_timeouts()
         return {"loss": lh[:, 0].tolist(), "loss/clip": lh[:, 1].tolist(), "loss/vf": lh[:, 2].tolist(),
                 "loss/ent": lh[:, 3].tolist()}
+
+    def _d2h_f32(self, t):
+        """Device float32 vector -> host numpy through a pinned buffer (one asynchronous copy + one stream sync)."""
+        pin = getattr(self, "_pin_f32", None)
+        if pin is None or pin.numel() < t.numel():
+            pin = self._pin_f32 = torch.empty(max(t.numel(), 256), dtype=torch.float32).pin_memory()
+        pin[:t.numel()].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pin[:t.numel()].numpy().copy()
+
+    def check_timeouts(self):
+        """A tensor-core kernel that gave up waiting on an mbarrier (never expected) computed with incomplete data: the
+        host raises instead of carrying on with silently wrong gradients.  The flag lives in managed / device memory
+        was copied to pinned memory in front of the update's read-back (cirs_head_tc_timeout_peek)."""
+        if int(self._tc_flag[0]):
+            _lib.load().cirs_head_tc_timeout()   # clears the device-side flag
+            raise _lib.CirsError("a tcgen05 head kernel timed out waiting on an mbarrier: results are invalid")

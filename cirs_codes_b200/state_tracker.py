@@ -123,13 +123,15 @@ class StateTrackerTransformer:
         if reset and dim_batch:
             B, c = int(dim_batch), self.layout.cfg
             if getattr(self, "n_env", None) != B:
+                # one K/V cache per environment count, kept: train and test collectors of different sizes alternate
+                # (onpolicy_trainer) without reallocating, and pointers captured in CUDA graphs stay valid
+                kv = self.__dict__.setdefault("_kv", {})
+                if B not in kv:
+                    k = torch.zeros(c["nlayers"], B, c["max_len"], c["d"], dtype=torch.float32, device=self.device)
+                    kv[B] = (k, torch.zeros_like(k), torch.zeros(B, dtype=torch.int32, device=self.device))
                 self.n_env = B
-                self.kcache = torch.zeros(c["nlayers"], B, c["max_len"], c["d"], dtype=torch.float32,
-                                          device=self.device)
-                self.vcache = torch.zeros_like(self.kcache)
-                self.len_data = torch.zeros(B, dtype=torch.int32, device=self.device)
-            else:
-                self.len_data.zero_()
+                self.kcache, self.vcache, self.len_data = kv[B]
+            self.len_data.zero_()
             return None
         res = {}
         if obs is not None:
@@ -189,10 +191,11 @@ class StateTrackerTransformer:
             # first compact row of every environment, computed on the device from the lengths the rollout wrote (no
             # host -> device copy, hence no synchronisation in front of the training pass)
             buffer.sync_device()
-            env_off = torch.zeros(B + 1, dtype=torch.int32, device=self.device)
-            env_off[1:] = torch.cumsum(buffer.d_len[:B], 0)
+            if not getattr(buffer, "_plan_ok", False):
+                buffer.plan_device()        # env_off / sample_index(0) on the device (csrc/util.cu)
+            env_off = buffer.d_env_off
             if tok_slot is None:
-                tok_slot = torch.as_tensor(buffer.sample_index(0).astype(np.int32), device=self.device)
+                tok_slot = buffer.d_index[:n_tok]
         else:
             tok_slot = None
         n_rows = n_tok if compact else B * L

@@ -71,3 +71,21 @@ def taobao_users(n, seed=2023):
         out[np.arange(n), off + k] = 1.0
         off += g
     return out
+
+
+def mmoe_state_dict(seed=2023, n_in=118, hidden=(64, 64), n_expert=4, expert_dim=8):
+    """A synthetic UserModel_MMOE state_dict with the reference's parameter names and shapes for the VirtualTaobao
+    columns (core/user_model_mmoe.py:80-98; CIRS-UserModel-taobao.py dnn_hidden_units (64, 64), 4 experts of width 8):
+    the reward model SimulatedEnv evaluates inside every step.  Weights N(0, 0.15) so predictions land inside the
+    clamp range [0, 10] with a useful spread; bias 4.0."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f = lambda *s: rng.normal(0.0, 0.15, size=s).astype(np.float32)  # noqa: E731
+    h1, h2 = hidden
+    return {
+        "linear_model_task.0.weight": f(n_in, 1), "dnn.linears.0.weight": f(h1, n_in), "dnn.linears.0.bias": f(h1),
+        "dnn.linears.1.weight": f(h2, h1), "dnn.linears.1.bias": f(h2),
+        "mmoe_layer.expert_network.weight": f(n_expert * expert_dim, h2),
+        "mmoe_layer.expert_network.bias": f(n_expert * expert_dim),
+        "mmoe_layer.gating_networks.0.weight": f(n_expert, h2), "tower_network.0.weight": f(1, expert_dim),
+        "out.0.bias": np.full((1, 1), 4.0, dtype=np.float32),
+    }

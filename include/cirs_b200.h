@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CIRS_ABI_VERSION 7
+#define CIRS_ABI_VERSION 8
 #define CIRS_MAX_LAYERS 4
 #define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
 
@@ -44,6 +44,9 @@ int cirs_profile_report(char* buf, int n);
 void cirs_head_tc_enable(int on);
 /* 1 if a tensor-core kernel gave up waiting on an mbarrier since the last call (synchronises; never expected). */
 int cirs_head_tc_timeout(void);
+/* Stream-ordered copy of that flag into PINNED host memory, without synchronising or clearing: the host path folds it
+ * into the update's own read-back and raises when it is set. */
+int cirs_head_tc_timeout_peek(int32_t* out_pinned_h, void* stream);
 
 /* ------------------------------------------------------------------ KuaishouEnv / SimulatedEnv ---------- */
 typedef struct {
@@ -277,15 +280,21 @@ int cirs_actorprob_eval(const cirs_policy_weights* w, int32_t n_rows, const int3
  * + 4: remove_recommended_ids (core/policy/utils.py:7-58; the test collectors NX_0 / NX_x of core/collector_set.py:19) --
  * items in env->seen (maintained by the environment step) are masked out of the softmax and of the race.
  * Same device code as cirs_actor_sample / cirs_kuaishou_step / cirs_tracker_step (bit-identical results).
+ * kv_n_env: environment capacity of kcache / vcache ([nlayers, kv_n_env, max_len, d]); must equal env->n_env (the
+ * layer stride), anything else is rejected instead of writing past the caches.  force_length must not exceed
+ * env->max_turn (the history has max_turn slots) and, like max_steps, traj_len when trajectories are recorded.
  * The workspace's bytes [256, 256 + 8 * (1 + 3 * 512)) hold int64 phase timers written by the kernel:
- * turns played, then per turn {running environments, ns in the actor-head phase, ns in the per-environment phase}. */
+ * turns played, then per turn {running environments, ns in the actor-head phase, ns in the per-environment phase};
+ * the int32 at byte 128 is set when a tensor-core mbarrier wait gave up (never expected; the host checks it after
+ * the collect's read-back and raises). */
 int64_t cirs_rollout_workspace_bytes(int32_t n_env, int32_t n_action);
 int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weights* tw, const cirs_policy_weights* pw,
                           const int32_t* users, uint8_t* active, int32_t* act, float* logp, float* value,
                           float* cur_state, float* rew, uint8_t* done, int32_t traj_len, float* traj_obs,
                           float* traj_obs_next, int32_t* traj_act, float* traj_rew, uint8_t* traj_done,
-                          int32_t* ep_len, float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter,
-                          int32_t mode, int32_t max_steps, int32_t force_length, void* workspace, void* stream);
+                          int32_t* ep_len, float* kcache, float* vcache, int32_t kv_n_env, uint64_t seed,
+                          uint64_t* rng_counter, int32_t mode, int32_t max_steps, int32_t force_length,
+                          void* workspace, void* stream);
 
 /* A whole Collector.collect(n_episode = B) on SimulatedEnv(VirtualTB) in ONE kernel.  Nothing in a VirtualTaobao turn
  * couples environments (the action head is 27 wide, not a catalogue), so each warp plays its environment's entire
@@ -297,8 +306,9 @@ int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weigh
 int cirs_rollout_taobao(const cirs_taobao_env* env, const cirs_tracker_weights* tw, const cirs_policy_weights* pw,
                         const float* users, uint8_t* active, float* cur_state, int32_t traj_len, float* traj_obs,
                         float* traj_obs_next, float* traj_act, float* traj_act_env, float* traj_rew,
-                        uint8_t* traj_done, int32_t* ep_len, float* kcache, float* vcache, uint64_t seed, uint64_t* rng_counter, int32_t mode,
-                        int32_t max_steps, int32_t force_length, void* stream);
+                        uint8_t* traj_done, int32_t* ep_len, float* kcache, float* vcache, int32_t kv_n_env,
+                        uint64_t seed, uint64_t* rng_counter, int32_t mode, int32_t max_steps, int32_t force_length,
+                        void* stream);
 
 /* ------------------------------------------------------------------ returns (GAE) ----------------------- */
 /* A2CPolicy._compute_returns (a2c.py:80-109) + BasePolicy.compute_episodic_return / _gae_return
@@ -356,18 +366,44 @@ int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_policy_weights* 
 int cirs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t n_dup,
                    const cirs_ppo_config* cfg, int32_t* state, double* scratch, void* stream);
 
-/* The whole learn() loop of one update for a single process (core/policy/ppo.py:173-233): n_repeat passes over
- * n_mb minibatches; slots[r * n + i] is the i-th buffer slot of repeat r's permutation (n = mb_off_h[n_mb]),
- * minibatch j = entries mb_off_h[j] .. mb_off_h[j+1].  mb_off_h is a HOST array, mb_off its device copy.
+/* The whole learn() loop of one update (core/policy/ppo.py:173-233): n_repeat passes over n_mb minibatches;
+ * slots[r * n + i] is the i-th buffer slot of repeat r's permutation (n = mb_off_h[n_mb]), minibatch j = entries
+ * mb_off_h[j] .. mb_off_h[j+1].  mb_off_h is a HOST array, mb_off its device copy.
  * adv_stats: double[n_repeat * n_mb * 3] device scratch; losses: float[n_repeat * n_mb * 4] on the device.
  * d_obs (optional, d_obs_floats elements) is zeroed at the start of every repeat and receives d loss / d obs.
- * exp_avg / exp_avg_sq / opt_state / opt_scratch: Adam state as in cirs_clip_adam (n_dup = w->n_trunk). */
+ * exp_avg / exp_avg_sq / opt_state / opt_scratch: Adam state as in cirs_clip_adam (n_dup = w->n_trunk).
+ * Data parallel: comm != NULL (cirs_comm_create) -> this rank holds ITS chunk of every global minibatch;
+ * the advantage moments are summed over ranks once, the flat gradient once per minibatch (stream-ordered
+ * all-reduces between the minibatch kernels and clip + Adam); n_global_h[n_mb] (HOST) = rows of each global
+ * minibatch, over which the losses are averaged.  comm == NULL: single process, n_global_h may be NULL. */
 int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grads, float* exp_avg,
                    float* exp_avg_sq, const cirs_ppo_config* cfg, int32_t n_repeat, int32_t n_mb,
                    const int32_t* mb_off_h, const int32_t* mb_off, const int32_t* slots, const float* obs,
                    const void* act, const float* adv, const float* returns, const float* v_old,
                    const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats, float* losses,
-                   int32_t* opt_state, double* opt_scratch, void* workspace, void* stream);
+                   int32_t* opt_state, double* opt_scratch, void* workspace, void* comm, const int32_t* n_global_h,
+                   void* stream);
+
+/* Front end of the update on the device (no host round trip between the rollout and the update):
+ * cirs_update_plan = VectorReplayBuffer.sample_index(0) (tianshou/data/buffer/manager.py:144-169) for buffers the
+ * fused rollout filled: tok_slot[i] = i-th stored slot, env-major (e * traj_len + t, t < n_slot[e]); env_off[e] =
+ * first compact row of environment e (n_env + 1 entries, env_off[n_env] = number of stored transitions).
+ * tok_slot may be NULL.  cirs_gather_i32: dst[i] = src[idx[i]] -- the minibatch order indices[perm] of one repeat
+ * (tianshou/data/batch.py:733-744). */
+int cirs_update_plan(int32_t n_env, int32_t traj_len, const int32_t* n_slot, int32_t* tok_slot, int32_t* env_off,
+                     void* stream);
+int cirs_gather_i32(int32_t* dst, const int32_t* src, const int32_t* idx, int32_t n, void* stream);
+
+/* ------------------------------------------------------------------ multi-GPU ---------------- */
+/* One process per GPU, environments sharded over ranks, parameters replicated; the reference has no multi-GPU path.
+ * A communicator wraps an NCCL communicator of the NCCL library already loaded in the process (resolved with dlopen:
+ * no link-time dependency).  Rank 0 calls cirs_comm_unique_id (128 bytes, HOST) and sends the id to the other ranks
+ * by any means (this repo: torch.distributed broadcast); every rank then calls cirs_comm_create with its CUDA device
+ * current.  cirs_comm_allreduce: stream-ordered in-place SUM over ranks; dtype 0 = float32, 1 = float64, 2 = int32. */
+int cirs_comm_unique_id(void* id128_h);
+int cirs_comm_create(const void* id128_h, int32_t rank, int32_t world, void** comm_out);
+int cirs_comm_destroy(void* comm);
+int cirs_comm_allreduce(void* comm, void* buf, int64_t count, int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------ user model -> normed_mat ------------ */
 /* The DeepFM user model of stage 1 (UserModel_Pairwise, core/user_model_pairwise.py:36-132) with the feature columns
