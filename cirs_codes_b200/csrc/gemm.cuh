@@ -63,9 +63,11 @@ struct AtomicEp {  // C[m*ld + n] += acc   (split-K partial sums)
 };
 
 // ---- kernel -------------------------------------------------------------------------------------------
+// the CTA-level body: tile (bx, by) of C, k-range of split bz.  gemm_kernel maps blockIdx onto it; grouped launches
+// (tracker_fused.cuh) map a flat CTA index onto (problem, tile, split) themselves.
 template <int BM, int BN, int BK, int TM, class LA, class LB, class EP>
-__global__ void __launch_bounds__((BM / TM) * (BN / 4))
-gemm_kernel(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split, float* __restrict__ colsum) {
+__device__ __forceinline__ void gemm_tile(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split,
+                                          float* __restrict__ colsum, int bx, int by, int bz) {
   constexpr int TN = 4;
   constexpr int NTX = BN / TN, NTY = BM / TM, NT = NTX * NTY;
   constexpr int LDA_S = BM + 4, LDB_S = BN + 4;  // +4 keeps float4 alignment and staggers banks
@@ -73,8 +75,8 @@ gemm_kernel(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split, float* __
   __shared__ __align__(16) float Bs[BK][LDB_S];
   static_assert(TM % 4 == 0, "TM must be a multiple of 4");
   const int tid = threadIdx.x, tx = tid % NTX, ty = tid / NTX;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+  const int m0 = by * BM, n0 = bx * BN;
+  const int kb = bz * k_per_split, ke = min(K, kb + k_per_split);
 
   float acc[TM][TN];
 #pragma unroll
@@ -151,10 +153,16 @@ gemm_kernel(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split, float* __
       if (n < N) ep(m, n, acc[i][j]);
     }
   }
-  if (colsum != nullptr && !LB::INNER_IS_K && NT % BN == 0 && blockIdx.y == 0) {
+  if (colsum != nullptr && !LB::INNER_IS_K && NT % BN == 0 && by == 0) {
     const int n = n0 + tid % BN;
     if (n < N) atomicAdd(colsum + n, csum);
   }
+}
+
+template <int BM, int BN, int BK, int TM, class LA, class LB, class EP>
+__global__ void __launch_bounds__((BM / TM) * (BN / 4))
+gemm_kernel(LA la, LB lb, EP ep, int M, int N, int K, int k_per_split, float* __restrict__ colsum) {
+  gemm_tile<BM, BN, BK, TM>(la, lb, ep, M, N, K, k_per_split, colsum, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // Host launcher.  split_k: number of K partitions (epilogue must accumulate when > 1).

@@ -13,7 +13,10 @@
 // Linear layers, their input gradients and their weight gradients run on the FP32 tile GEMM (gemm.cuh); attention,
 // LayerNorm, the reward gate and the embedding scatter are small dedicated kernels.  All reductions that feed a
 // parameter gradient use float atomics at CTA granularity (order-dependent in the last bits only).
+#include <stdlib.h>
+
 #include "gemm.cuh"
+#include "tracker_fused.cuh"
 #include "../../include/cirs_b200.h"
 
 namespace {
@@ -527,19 +530,127 @@ void fork_join(cudaStream_t st, FW dw, FX dx) {
 
 }  // namespace
 
+// ---- fused path (tracker_fused.cuh): chunk kernel + grouped weight-gradient launch
+static int g_fused_mode = -1;   // -1 default (on unless CIRS_K6_UNFUSED=1), 0 off, 1 on
+static bool fused_enabled() {
+  if (g_fused_mode >= 0) return g_fused_mode != 0;
+  const char* e = getenv("CIRS_K6_UNFUSED");
+  return !(e && e[0] == '1');
+}
+extern "C" void cirs_tracker_train_fused_enable(int on) { g_fused_mode = on < 0 ? -1 : (on ? 1 : 0); }
+
+struct FusedPlan { bool ok; int TM, ldx, ldb, q; size_t smem; };
+static FusedPlan fused_plan(const cirs_tracker_weights& W, int max_ep_len) {
+  FusedPlan P{};
+  const int d = W.d;
+  int wide = 3 * d;
+  if (W.d_hid > wide) wide = W.d_hid;
+  if (1 + W.d_user_in > wide) wide = 1 + W.d_user_in;
+  if (1 + d > wide) wide = 1 + d;
+  if (W.dim_state > wide) wide = W.dim_state;
+  P.ldx = cirs_k6::up4(d) + 4;
+  P.ldb = cirs_k6::up4(wide) + 4;
+  // measured on B200: the chunk kernel beats the layer-by-layer launches for d <= 64 (configs[1]: 0.30 vs 0.56 ms,
+  // configs[2]: 1.03 vs 1.40 ms); at d = 128 its 32-row chunks lose (2.0 vs 1.25 ms), so that shape keeps the launches
+  if (d > 64) return P;
+  for (int TM : {64, 32}) {
+    const size_t smem = cirs_k6::chunk_smem_bytes(TM, d, W.nhead, P.ldx, P.ldb);
+    // the probabilities of a chunk's attention live in the weight stage: [longest episode][TM * nhead] floats
+    if (smem <= 224 * 1024 && max_ep_len <= TM &&
+        (size_t)max_ep_len * TM * W.nhead <= (size_t)cirs_k6::WS_K * cirs_k6::WS_LD) {
+      P.ok = true; P.TM = TM; P.smem = smem; P.q = TM - max_ep_len + 1;
+      return P;
+    }
+  }
+  return P;
+}
+
+static int fused_train(const cirs_tracker_weights& W, const cirs_tracker_weights& G, int B, int L, int M,
+                       const int32_t* users, const int32_t* act, const float* rew, const int32_t* ep_len,
+                       const float* dense_user, const float* dense_item, const int32_t* tok_slot,
+                       const int32_t* env_off, const float* d_obs, float* obs_check, float* workspace,
+                       const FusedPlan& P, cudaStream_t st) {
+  using namespace cirs_k6;
+  const int d = W.d, dhid = W.d_hid, S = W.dim_state, nl = W.nlayers, dui = W.d_user_in;
+  cirs_k6::Args A{};
+  A.W = W; A.G = G;
+  A.S = cirs_k6::carve(workspace, M, d, dhid, nl, dui);
+  A.n_env = B; A.L = L; A.M = M; A.q = P.q;
+  A.users = users; A.act = act; A.ep_len = ep_len; A.tok_slot = tok_slot; A.env_off = env_off;
+  A.rew = rew; A.dense_user = dense_user; A.dense_item = dense_item; A.d_obs = d_obs; A.obs_check = obs_check;
+  A.ldx = P.ldx; A.ldb = P.ldb;
+  const int n_chunks = (M + P.q - 1) / P.q;
+  const int grid = n_chunks < 148 ? n_chunks : 148;
+  static bool attr64 = false, attr32 = false;
+  if (P.TM == 64) {
+    if (!attr64) { cudaFuncSetAttribute(tracker_chunk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); attr64 = true; }
+    const bool prof = cirs_profile_begin("tracker_chunk_kernel", st);
+    tracker_chunk_kernel<64><<<grid, NT, P.smem, st>>>(A);
+    cirs_note_launch();
+    if (prof) cirs_profile_end(st);
+  } else {
+    if (!attr32) { cudaFuncSetAttribute(tracker_chunk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024); attr32 = true; }
+    const bool prof = cirs_profile_begin("tracker_chunk_kernel", st);
+    tracker_chunk_kernel<32><<<grid, NT, P.smem, st>>>(A);
+    cirs_note_launch();
+    if (prof) cirs_profile_end(st);
+  }
+  CIRS_CHECK_LAUNCH();
+  if (!d_obs) return CIRS_OK;
+  // ---- every Linear's weight / bias gradient in one grouped split-K launch
+  const int ldd = up32(d), ld3 = up32(3 * d), ldh = up32(dhid), lds = up32(S);
+  DwArgs D{};
+  int np = 0, cta = 0;
+  auto add = [&](const float* x, int ldx, const float* dy, int ldy, const int32_t* rows, float* gw, int ldw, float* gb,
+                 int k_in, int n_out) {
+    DwProblem& p = D.p[np++];
+    p.x = x; p.ldx = ldx; p.dy = dy; p.ldy = ldy; p.dy_rows = rows; p.gw = gw; p.ldw = ldw; p.gb = gb;
+    p.k_in = k_in; p.n_out = n_out; p.tiles_n = (n_out + 63) / 64; p.tiles_k = (k_in + 63) / 64; p.cta0 = cta;
+    cta += p.tiles_n * p.tiles_k;   // per split; scaled below
+  };
+  const float* x_last = nl ? A.S.layer[nl - 1].x2 : A.S.x0;
+  add(x_last, d, d_obs, S, tok_slot, G.dec_wt, lds, G.dec_b, d, S);
+  for (int l = 0; l < nl; ++l) {
+    const LayerSave& y = A.S.layer[l];
+    const cirs_encoder_layer& Gy = G.layer[l];
+    const float* xin = l == 0 ? A.S.x0 : A.S.layer[l - 1].x2;
+    add(y.h, dhid, y.dr2, d, nullptr, Gy.l2_wt, ldd, Gy.l2_b, dhid, d);
+    add(y.x1, d, y.dh, dhid, nullptr, Gy.l1_wt, ldh, Gy.l1_b, d, dhid);
+    add(y.o, d, y.dr1, d, nullptr, Gy.out_wt, ldd, Gy.out_b, d, d);
+    add(xin, d, y.dqkv, 3 * d, nullptr, Gy.in_wt, ld3, Gy.in_b, d, 3 * d);
+  }
+  add(A.S.in, 1 + d, A.S.dz, d, nullptr, G.gate_wt, ldd, G.gate_b, 1 + d, d);
+  add(A.S.u, dui, A.S.dtok0, d, nullptr, G.user_wt, ldd, G.user_b, dui, d);
+  const int tiles_total = cta;
+  int splits = (2 * 148 + tiles_total - 1) / tiles_total;
+  const int max_s = (M + 63) / 64;
+  if (splits > max_s) splits = max_s;
+  if (splits < 1) splits = 1;
+  int kps = (M + splits - 1) / splits;
+  kps = ((kps + 31) / 32) * 32;
+  splits = (M + kps - 1) / kps;
+  for (int i = 0; i < np; ++i) D.p[i].cta0 *= splits;
+  D.n_prob = np; D.M = M; D.splits = splits; D.k_per_split = kps;
+  CIRS_LAUNCH(tracker_dw_grouped_kernel, tiles_total * splits, 256, 0, st, D);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+
 extern "C" int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_t n_env,
                                                       int64_t n_rows) {
   if (!w) return 0;
   const Bufs b = carve(nullptr, n_env, n_rows, w->d, w->d_hid, w->nlayers, w->d_user_in);
-  return b.total * (int64_t)sizeof(float) + 256;
+  const cirs_k6::Save s = cirs_k6::carve(nullptr, n_rows, w->d, w->d_hid, w->nlayers, w->d_user_in);
+  const int64_t t = b.total > s.total ? b.total : s.total;
+  return t * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights* grads, int32_t n_env,
                                   int32_t traj_len, const int32_t* users, const int32_t* traj_act,
                                   const float* traj_rew, const int32_t* ep_len, const float* dense_user,
                                   const float* dense_item, int32_t n_tok, const int32_t* tok_slot,
-                                  const int32_t* env_off, const float* d_obs, float* obs_check, void* workspace,
-                                  int64_t workspace_bytes, void* stream) {
+                                  const int32_t* env_off, int32_t max_ep_len, const float* d_obs, float* obs_check,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
   if (!w || !grads || !traj_rew || !ep_len || !workspace || n_env < 0 || traj_len < 1) {
     cirs_set_error("cirs_tracker_train: null argument");
     return CIRS_ERR_ARG;
@@ -569,6 +680,12 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
   const int B = n_env, L = traj_len, M = (int)n_rows, d = w->d, dhid = w->d_hid, S = w->dim_state, nl = w->nlayers;
   const int ldd = up32(d), ld3 = up32(3 * d), ldh = up32(dhid), lds = up32(S), dui = w->d_user_in;
   const int nh = w->nhead, dh = d / nh;
+  if (tok_slot && fused_enabled()) {
+    const FusedPlan P = fused_plan(*w, max_ep_len > 0 && max_ep_len <= L ? max_ep_len : L);
+    if (P.ok)
+      return fused_train(*w, *grads, B, L, M, users, traj_act, traj_rew, ep_len, dense_user, dense_item, tok_slot,
+                         env_off, d_obs, obs_check, reinterpret_cast<float*>(workspace), P, st);
+  }
   Bufs b = carve(reinterpret_cast<float*>(workspace), B, M, d, dhid, nl, dui);
   const size_t att_smem = attn_smem_bytes(L, dh, ATT_WARPS);
   if (att_smem > 200 * 1024) {

@@ -84,12 +84,12 @@ def create_comm(dist, group, device):
     ident = (C.c_ubyte * 128)()
     if rank == 0:
         _lib.call("cirs_comm_unique_id", C.cast(ident, C.c_void_p))
+    device = torch.device("cuda", torch.cuda.current_device())   # one process per GPU: the current device is the rank's
     t = torch.tensor(list(bytes(ident)), dtype=torch.uint8, device=device)
     src = dist.get_global_rank(group, 0) if group is not None else 0
     dist.broadcast(t, src=src, group=group)
     raw = bytes(t.cpu().tolist())
     ident = (C.c_ubyte * 128).from_buffer_copy(raw)
-    torch.cuda.set_device(device)
     handle = C.c_void_p()
     _lib.call("cirs_comm_create", C.cast(ident, C.c_void_p), rank, world, C.byref(handle))
     assert lib is not None and handle.value

@@ -209,7 +209,8 @@ class StateTrackerTransformer:
                   _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_len),
                   _lib.ptr(buffer.d_users_dense) if dense else None, _lib.ptr(buffer.d_act_env) if dense else None,
                   n_tok,
-                  _lib.ptr(tok_slot), _lib.ptr(env_off), _lib.ptr(d_obs), _lib.ptr(obs_check), _lib.ptr(self._ws),
+                  _lib.ptr(tok_slot), _lib.ptr(env_off), int(buffer._lengths.max()) if compact else 0,
+                  _lib.ptr(d_obs), _lib.ptr(obs_check), _lib.ptr(self._ws),
                   int(self._ws.numel()), _lib.stream())
 
     def optim_step(self, cfg_struct):

@@ -211,8 +211,14 @@ int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights* w, int32_
 int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights* grads, int32_t n_env,
                        int32_t traj_len, const int32_t* users, const int32_t* traj_act, const float* traj_rew,
                        const int32_t* ep_len, const float* dense_user, const float* dense_item, int32_t n_tok,
-                       const int32_t* tok_slot, const int32_t* env_off, const float* d_obs, float* obs_check,
-                       void* workspace, int64_t workspace_bytes, void* stream);
+                       const int32_t* tok_slot, const int32_t* env_off, int32_t max_ep_len, const float* d_obs,
+                       float* obs_check, void* workspace, int64_t workspace_bytes, void* stream);
+/* Compact mode runs as TWO launches by default (csrc/tracker_fused.cuh): a chunk kernel that carries whole
+ * environments through the forward and backward pass inside one CTA, and one grouped split-K launch for every
+ * Linear's weight gradient.  max_ep_len (0 = unknown -> traj_len) is the longest stored episode: it sizes the chunks.
+ * cirs_tracker_train_fused_enable(0) selects the layer-by-layer launches instead (-1 = default; CIRS_K6_UNFUSED=1);
+ * both are CUDA paths with the same results within the parity bar (tests/test_gpu_tracker_train.py runs both). */
+void cirs_tracker_train_fused_enable(int on);
 
 /* ------------------------------------------------------------------ policy / value heads ---------------- */
 typedef struct {

@@ -25,11 +25,27 @@ def _replay(H, z, c, it, trk, pol):
     return buf, res
 
 
+@pytest.fixture
+def unfused():
+    """Select the layer-by-layer launches of K6 for one test, then restore the default (fused chunk kernel)."""
+    from cirs_codes_b200 import _lib
+    _lib.load().cirs_tracker_train_fused_enable(0)
+    yield
+    _lib.load().cirs_tracker_train_fused_enable(-1)
+
+
+@pytest.mark.parametrize("name", G.KUAISHOU_CASES)
+def test_tracker_train_unfused_path_vs_autograd(H, name, unfused):
+    """The second CUDA path of K6 (one launch per layer operation) against the same autograd reference."""
+    test_tracker_train_forward_and_grads_vs_autograd(H, name, True)
+
+
 @pytest.mark.parametrize("compact", [True, False])
 @pytest.mark.parametrize("name", G.KUAISHOU_CASES)
 def test_tracker_train_forward_and_grads_vs_autograd(H, name, compact):
     """One full-sequence pass: (a) its decoded states equal the states the rollout stored; (b) the parameter
-    gradients for a random upstream d_obs equal torch autograd through the oracle's encoder."""
+    gradients for a random upstream d_obs equal torch autograd through the oracle's encoder.  compact = True runs the
+    fused chunk kernel + grouped weight-gradient launch (csrc/tracker_fused.cuh), False the padded layer-by-layer path."""
     from oracle import nets
     z = G.load(name)
     c = G.cfg(z)
