@@ -8,14 +8,17 @@ from .inputs import (DenseFeat, SparseFeat, SparseFeatP, VarLenSparseFeat, build
                      compute_input_dim, get_dataset_columns, get_feature_names)
 from .data import Batch, VectorReplayBuffer  # noqa: F401
 from .net import Actor, ActorProb, Critic, Net, orthogonal_init  # noqa: F401
-from .env import KuaishouVectorEnv, TaobaoVectorEnv  # noqa: F401
+from .env import KuaishouVectorEnv, TaobaoVectorEnv, VirtualTBVectorEnv  # noqa: F401
 from .state_tracker import StateTrackerTransformer  # noqa: F401
 from .policy import PPOPolicy  # noqa: F401
 from .collector import Collector  # noqa: F401
 from .collector_set import CollectorSet  # noqa: F401
 from .trainer import onpolicy_trainer, save_checkpoint, load_checkpoint  # noqa: F401
+from .loggers import BasicLogger, LoggerCallback_Policy, ScalarRecorder  # noqa: F401
+from .evaluation import Callback_Coverage_Count  # noqa: F401
 
 __all__ = ["DenseFeat", "SparseFeat", "SparseFeatP", "VarLenSparseFeat", "build_input_features",
            "compute_input_dim", "get_dataset_columns", "get_feature_names", "Batch", "VectorReplayBuffer", "Actor",
-           "ActorProb", "Critic", "Net", "orthogonal_init", "KuaishouVectorEnv", "TaobaoVectorEnv", "StateTrackerTransformer", "PPOPolicy",
-           "Collector", "CollectorSet", "onpolicy_trainer", "save_checkpoint", "load_checkpoint"]
+           "ActorProb", "Critic", "Net", "orthogonal_init", "KuaishouVectorEnv", "TaobaoVectorEnv", "VirtualTBVectorEnv", "StateTrackerTransformer", "PPOPolicy",
+           "Collector", "CollectorSet", "onpolicy_trainer", "save_checkpoint", "load_checkpoint", "BasicLogger",
+           "LoggerCallback_Policy", "ScalarRecorder", "Callback_Coverage_Count"]

@@ -40,6 +40,10 @@ class TaobaoEnvStruct(C.Structure):
                 ("user", fp), ("turn", fp), ("hist", fp), ("prev_rew", fp), ("cum_rew", fp)]
 
 
+class VirtualTBStruct(C.Structure):
+    _fields_ = [(k, fp) for k in ("g1t", "g1b", "g2t", "g2b", "a1t", "a1b", "a2t", "a2b", "a3t", "a3b")]
+
+
 class EncoderLayerStruct(C.Structure):
     _fields_ = [(k, fp) for k in ("in_wt", "in_b", "out_wt", "out_b", "l1_wt", "l1_b", "l2_wt", "l2_b",
                                   "n1_w", "n1_b", "n2_w", "n2_b")]
@@ -88,6 +92,9 @@ PROTOTYPES = {
     "cirs_kuaishou_step": (i32, [P(KuaishouEnvStruct), i32, fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, i32, fp]),
     "cirs_taobao_reset": (i32, [P(TaobaoEnvStruct), i32, fp, fp, fp, fp]),
     "cirs_taobao_step": (i32, [P(TaobaoEnvStruct), i32, fp, fp, fp, fp, fp, fp, i32, fp, fp, fp, fp, fp, i32, fp]),
+    "cirs_virtualtb_generate_users": (i32, [P(VirtualTBStruct), i32, fp, fp, u64, u64, fp, fp]),
+    "cirs_virtualtb_step": (i32, [P(TaobaoEnvStruct), P(VirtualTBStruct), i32, fp, fp, fp, u64, u64, fp, fp, fp, i32,
+                                  fp]),
     "cirs_tracker_step": (i32, [P(TrackerWeightsStruct), i32, i32, fp, fp, fp, i32, fp, fp, fp, fp, fp, fp, i64,
                                 fp, i32, fp, fp, fp]),
     "cirs_tracker_train_workspace_bytes": (i64, [P(TrackerWeightsStruct), i32, i64]),
@@ -117,6 +124,7 @@ PROTOTYPES = {
                              fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp, fp, fp]),
     "cirs_update_plan": (i32, [i32, i32, fp, fp, fp, fp]),
     "cirs_gather_i32": (i32, [fp, fp, fp, i32, fp]),
+    "cirs_coverage_count": (i32, [i32, fp, fp, i32, fp, fp, fp, fp]),
     "cirs_comm_unique_id": (i32, [fp]),
     "cirs_comm_create": (i32, [fp, i32, i32, P(fp)]),
     "cirs_comm_destroy": (i32, [fp]),

@@ -682,7 +682,10 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
   const int nh = w->nhead, dh = d / nh;
   if (tok_slot && fused_enabled()) {
     const FusedPlan P = fused_plan(*w, max_ep_len > 0 && max_ep_len <= L ? max_ep_len : L);
-    if (P.ok)
+    // one CTA carries a chunk through ~100 dependent stages: a latency design that wins while the chunks fit a few
+    // waves of the 148 SMs (Kuaishou: 30-200 chunks); with thousands of chunks (VirtualTaobao at 2048 x 50 tokens) the
+    // throughput-oriented layer-by-layer launches are faster (measured 5.0 vs 9.7 ms)
+    if (P.ok && (M + P.q - 1) / P.q <= 4 * 148)
       return fused_train(*w, *grads, B, L, M, users, traj_act, traj_rew, ep_len, dense_user, dense_item, tok_slot,
                          env_off, d_obs, obs_check, reinterpret_cast<float*>(workspace), P, st);
   }

@@ -59,7 +59,60 @@ gather_i32_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, co
   if (i < n) dst[i] = src[idx[i]];
 }
 
+// coverage of a collect (evaluation.py:286-371): distinct recommended items (bitset + popcount) and the weighted count
+// sum_i weight[act_i] (dominated-category metrics: weight = the per-item value the reference's integer arithmetic yields)
+__global__ void __launch_bounds__(256)
+coverage_mark_kernel(int n, const int32_t* __restrict__ idx, const int32_t* __restrict__ act, int n_item,
+                     const int32_t* __restrict__ weight, uint32_t* __restrict__ bits, unsigned long long* out) {
+  __shared__ unsigned long long sh[8];
+  unsigned long long w = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int a = act[idx ? idx[i] : i];
+    if (a >= 0 && a < n_item) {
+      atomicOr(bits + (a >> 5), 1u << (a & 31));
+      if (weight) w += (unsigned long long)weight[a];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(FULL_MASK, w, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    if (t) atomicAdd(out + 2, t);
+  }
+}
+__global__ void __launch_bounds__(256)
+coverage_count_kernel(int words, const uint32_t* __restrict__ bits, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) c += __popc(bits[i]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 }  // namespace
+
+extern "C" int cirs_coverage_count(int32_t n, const int32_t* idx, const int32_t* act, int32_t n_item,
+                                   const int32_t* item_weight, uint32_t* bits, int64_t* out3, void* stream) {
+  if (n < 0 || n_item <= 0 || !act || !bits || !out3) {
+    cirs_set_error("cirs_coverage_count: bad argument");
+    return CIRS_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int words = (n_item + 31) / 32;
+  cudaMemsetAsync(bits, 0, sizeof(uint32_t) * words, st);
+  cudaMemsetAsync(out3, 0, 3 * sizeof(int64_t), st);
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(out3);
+  if (n > 0) {
+    int grid = (n + 255) / 256;
+    if (grid > 148 * 4) grid = 148 * 4;
+    CIRS_LAUNCH(coverage_mark_kernel, grid, 256, 0, st, n, idx, act, n_item, item_weight, bits, out);
+    CIRS_CHECK_LAUNCH();
+    CIRS_LAUNCH(coverage_count_kernel, (words + 255) / 256, 256, 0, st, words, bits, out);
+    CIRS_CHECK_LAUNCH();
+  }
+  return CIRS_OK;
+}
 
 extern "C" int cirs_update_plan(int32_t n_env, int32_t traj_len, const int32_t* n_slot, int32_t* tok_slot,
                                 int32_t* env_off, void* stream) {

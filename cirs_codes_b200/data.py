@@ -47,9 +47,53 @@ class Batch:
                 out.__dict__[k] = np.asarray(v)[idx]
         return out
 
-    def __setitem__(self, k, v):
-        assert isinstance(k, str)
-        self.__setattr__(k, v)
+    def __setitem__(self, index, value):
+        """tianshou/data/batch.py:244-267: ``b["key"] = v`` assigns a key; ``b[index] = other`` assigns the rows
+        ``index`` of every key from a Batch / dict with a subset of this Batch's keys (keys missing there are filled
+        with 0 / None / an empty Batch, like the reference); creating keys by item assignment is refused."""
+        if isinstance(index, str):
+            self.__setattr__(index, value)
+            return
+        if isinstance(value, dict):
+            value = Batch(value)
+        if not isinstance(value, Batch):
+            raise ValueError("Batch does not supported tensor assignment. Use a compatible Batch or dict instead.")
+        if not set(value.keys()).issubset(self.__dict__.keys()):
+            raise ValueError("Creating keys is not supported by item assignment.")
+        for key, val in self.__dict__.items():
+            if isinstance(val, Batch) and val.is_empty():
+                continue
+            ii = index
+            if torch.is_tensor(val) and isinstance(index, np.ndarray):
+                ii = torch.as_tensor(index, device=val.device)
+            if key in value.__dict__:
+                src = value.__dict__[key]
+                if isinstance(val, Batch):
+                    val[index] = src
+                elif torch.is_tensor(val):
+                    val[ii] = torch.as_tensor(src, dtype=val.dtype, device=val.device)
+                else:
+                    val[index] = src
+            elif isinstance(val, Batch):
+                pass
+            elif torch.is_tensor(val) or (isinstance(val, np.ndarray) and
+                                          issubclass(val.dtype.type, (np.bool_, np.number))):
+                val[ii] = 0
+            elif val is not None:
+                val[index] = None
+
+    def split(self, size, shuffle=True, merge_last=False):
+        """tianshou/data/batch.py:721-744: yield minibatches of ``size`` rows (the whole Batch when it is shorter);
+        ``merge_last`` folds a short last chunk into the previous one.  np.random.permutation like the reference."""
+        length = len(self)
+        assert size >= 1
+        indices = np.random.permutation(length) if shuffle else np.arange(length)
+        merge_last = merge_last and length % size > 0
+        for idx in range(0, length, size):
+            if merge_last and idx + size + size >= length:
+                yield self[indices[idx:]]
+                break
+            yield self[indices[idx:idx + size]]
 
     def __contains__(self, k):
         return k in self.__dict__

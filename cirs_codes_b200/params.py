@@ -261,3 +261,31 @@ def tracker_struct(L, flat, pe):
     s.dec_wt, s.dec_b = L.ptr(flat, "decoder.weight"), L.ptr(flat, "decoder.bias")
     s.flat, s.n_flat = flat.data_ptr(), L.total
     return s
+
+
+# ---------------------------------------------------------------------------------------------- raw VirtualTaobao
+def virtualtb_pack(generator_sd=None, action_sd=None, device="cuda"):
+    """The shipped VirtualTB networks (virtualTB/data/generator_model.pt = UserModel.generator_model.state_dict(),
+    action_model.pt = ActionModel.model.state_dict(); keys "0.weight", "0.bias", "2.weight", ...) -> one flat device
+    buffer + a filled _lib.VirtualTBStruct.  Either may be None."""
+    L = FlatLayout()
+    sd = {}
+    if generator_sd is not None:
+        L.add("g.0.weight", "wt", 128, 128); L.add("g.0.bias", "vec", 1, 128)
+        L.add("g.2.weight", "wt", 128, 88); L.add("g.2.bias", "vec", 1, 88)
+        sd.update({"g." + k: v for k, v in generator_sd.items()})
+    if action_sd is not None:
+        L.add("a.0.weight", "wt", 116, 128); L.add("a.0.bias", "vec", 1, 128)
+        L.add("a.2.weight", "wt", 128, 256); L.add("a.2.bias", "vec", 1, 256)
+        L.add("a.4.weight", "wt", 256, 21); L.add("a.4.bias", "vec", 1, 21)
+        sd.update({"a." + k: v for k, v in action_sd.items()})
+    flat = L.pack(sd, device)
+    s = _lib.VirtualTBStruct()
+    if generator_sd is not None:
+        s.g1t, s.g1b = L.ptr(flat, "g.0.weight"), L.ptr(flat, "g.0.bias")
+        s.g2t, s.g2b = L.ptr(flat, "g.2.weight"), L.ptr(flat, "g.2.bias")
+    if action_sd is not None:
+        s.a1t, s.a1b = L.ptr(flat, "a.0.weight"), L.ptr(flat, "a.0.bias")
+        s.a2t, s.a2b = L.ptr(flat, "a.2.weight"), L.ptr(flat, "a.2.bias")
+        s.a3t, s.a3b = L.ptr(flat, "a.4.weight"), L.ptr(flat, "a.4.bias")
+    return flat, s

@@ -136,6 +136,9 @@ class PPOPolicy:
                 for p in self.optim[1].param_groups[0]["params"]:
                     self.state_tracker = getattr(p, "_cirs_owner", self.state_tracker)
         self.ret_rms = RunningMeanStd(self.device)
+        self._bridge_optim()
+        if self.state_tracker is not None and len(self.optim) > 1:
+            self.state_tracker.bridge_optim(self.optim[1])
         self._ws_actor = self._ws_ppo = None
         self._ws_actor_rows = self._ws_ppo_rows = 0
 
@@ -158,15 +161,83 @@ class PPOPolicy:
         a, c = params.policy_sd_to_reference(self.layout.unpack(self.flat))
         out = {"actor." + k: v for k, v in a.items()}
         out.update({"critic." + k: v for k, v in c.items()})
-        out["ret_rms"] = self.ret_rms.t.detach().cpu()
-        return out
+        return out      # tianshou keeps ret_rms outside the state_dict too (a plain attribute); see trainer.save_checkpoint
 
     def load_state_dict(self, sd, strict=True):
         a = {k[len("actor."):]: v for k, v in sd.items() if k.startswith("actor.")}
         c = {k[len("critic."):]: v for k, v in sd.items() if k.startswith("critic.")}
         self.flat.copy_(self.layout.pack(params.policy_sd_from_reference(a, c), self.device))
-        if "ret_rms" in sd:
+        if "ret_rms" in sd:   # checkpoints written by round 1 of this package
             self.ret_rms.t.copy_(torch.as_tensor(sd["ret_rms"], dtype=torch.float64))
+
+    # ------------------------------------------------------------------ optimizer state <-> torch.optim.Adam
+    def _optim_names(self):
+        """{id(parameter): key of the flat layout} for the tensors ``optim[0]`` lists (actor / critic modules)."""
+        names = {}
+        for n, p in self.actor.named_parameters():
+            if n.startswith("preprocess."):
+                key = "trunk." + n[len("preprocess.model.model."):]
+            elif n == "sigma_param":
+                key = "actor.sigma_param"
+            else:
+                key = "actor.last." + n.rsplit(".", 1)[1]
+            names[id(p)] = key
+        for n, p in self.critic.named_parameters():
+            if not n.startswith("preprocess."):
+                names[id(p)] = "critic.last." + n.rsplit(".", 1)[1]
+        return names
+
+    def _bridge_optim(self):
+        """Make ``optim[0].state_dict()`` / ``.load_state_dict()`` -- what the reference's checkpoint code calls
+        (CIRS-RL-kuaishou.py:340-358) -- carry the Adam moments that live in this policy's flat device buffers, in
+        torch.optim.Adam's own layout (per-tensor exp_avg / exp_avg_sq / step, the shared trunk stepping twice per
+        update).  The torch optimizer never steps; it is the hyper-parameter carrier and the checkpoint format."""
+        opt = self.optim[0]
+        if getattr(opt, "_cirs_bridged", False):
+            return
+        orig_sd, orig_load = opt.state_dict, opt.load_state_dict
+
+        def state_dict():
+            self.push_optim_state()
+            return orig_sd()
+
+        def load_state_dict(sd):
+            orig_load(sd)
+            self.pull_optim_state()
+
+        opt.state_dict, opt.load_state_dict, opt._cirs_bridged = state_dict, load_state_dict, True
+
+    def push_optim_state(self):
+        """device moments -> optim[0].state (reference tensor shapes)."""
+        names, opt = self._optim_names(), self.optim[0]
+        m, v = self.layout.unpack(self.exp_avg), self.layout.unpack(self.exp_avg_sq)
+        steps = self.opt_state.cpu().numpy()
+        if int(steps[0]) == 0:
+            opt.state.clear()
+            return
+        for g in opt.param_groups:
+            for p in g["params"]:
+                key = names[id(p)]
+                step = steps[1] if key.startswith("trunk.") else steps[0]
+                opt.state[p] = {"step": torch.tensor(float(step)), "exp_avg": m[key].reshape(p.shape).clone(),
+                                "exp_avg_sq": v[key].reshape(p.shape).clone()}
+
+    def pull_optim_state(self):
+        """optim[0].state (e.g. just loaded from a reference checkpoint) -> device moments and step counters."""
+        names, opt = self._optim_names(), self.optim[0]
+        m, v = self.layout.unpack(self.exp_avg), self.layout.unpack(self.exp_avg_sq)
+        steps = [0, 0]
+        for g in opt.param_groups:
+            for p in g["params"]:
+                st = opt.state.get(p)
+                if not st:
+                    continue
+                key = names[id(p)]
+                m[key], v[key] = st["exp_avg"].reshape(m[key].shape), st["exp_avg_sq"].reshape(v[key].shape)
+                steps[1 if key.startswith("trunk.") else 0] = int(float(st["step"]))
+        self.exp_avg.copy_(self.layout.pack(m, self.device))
+        self.exp_avg_sq.copy_(self.layout.pack(v, self.device))
+        self.opt_state.copy_(torch.tensor(steps, dtype=torch.int32))
 
     def map_action(self, act):
         """policy/base.py:143-173: identity for a discrete action space; for a Box space clip to [-1, 1]

@@ -99,12 +99,52 @@ class StateTrackerTransformer:
         self.flat.copy_(self.layout.pack(sd, self.device))
 
     def parameters(self):
-        """A single Parameter aliasing the flat device buffer, so that ``torch.optim.Adam(tracker.parameters(),
-        lr=...)`` (CIRS-RL-kuaishou.py:259) can be constructed unchanged; PPOPolicy reads lr / betas / eps from that
-        optimiser and finds the tracker through ``_cirs_owner``.  The update itself runs in csrc/optim.cu."""
-        p = torch.nn.Parameter(self.flat, requires_grad=False)
-        p._cirs_owner = self
-        return [p]
+        """One host Parameter per reference tensor, in the reference module's registration order, so that
+        ``torch.optim.Adam(tracker.parameters(), lr=...)`` (CIRS-RL-kuaishou.py:259) is constructed unchanged and its
+        ``state_dict()`` has the reference's layout (checkpoints, CIRS-RL-kuaishou.py:340-358).  PPOPolicy reads
+        lr / betas / eps from that optimiser and finds the tracker through ``_cirs_owner``; the parameters are keys
+        and checkpoint views only -- the update itself runs in csrc/optim.cu on the flat device buffer."""
+        if getattr(self, "_host_params", None) is None:
+            sd = self.layout.unpack(self.flat)
+            self._host_params = []
+            for k, v in sd.items():
+                p = torch.nn.Parameter(v.clone(), requires_grad=False)
+                p._cirs_owner, p._cirs_key = self, k
+                self._host_params.append(p)
+        return list(self._host_params)
+
+    def bridge_optim(self, opt):
+        """``opt.state_dict()`` / ``opt.load_state_dict()`` carry the Adam moments of the flat device buffer in
+        torch.optim.Adam's per-tensor layout (see PPOPolicy._bridge_optim)."""
+        if getattr(opt, "_cirs_bridged", False):
+            return
+        orig_sd, orig_load = opt.state_dict, opt.load_state_dict
+        keyed = [p for g in opt.param_groups for p in g["params"] if hasattr(p, "_cirs_key")]
+
+        def state_dict():
+            step = int(self.opt_state[0])
+            opt.state.clear()
+            if step:
+                m, v = self.layout.unpack(self.exp_avg), self.layout.unpack(self.exp_avg_sq)
+                for p in keyed:
+                    opt.state[p] = {"step": torch.tensor(float(step)), "exp_avg": m[p._cirs_key].clone(),
+                                    "exp_avg_sq": v[p._cirs_key].clone()}
+            return orig_sd()
+
+        def load_state_dict(sd):
+            orig_load(sd)
+            m, v = self.layout.unpack(self.exp_avg), self.layout.unpack(self.exp_avg_sq)
+            step = 0
+            for p in keyed:
+                st = opt.state.get(p)
+                if st:
+                    m[p._cirs_key], v[p._cirs_key] = st["exp_avg"], st["exp_avg_sq"]
+                    step = int(float(st["step"]))
+            self.exp_avg.copy_(self.layout.pack(m, self.device))
+            self.exp_avg_sq.copy_(self.layout.pack(v, self.device))
+            self.opt_state.copy_(torch.tensor([step, 2 * step], dtype=torch.int32))
+
+        opt.state_dict, opt.load_state_dict, opt._cirs_bridged = state_dict, load_state_dict, True
 
     def to(self, *a, **k):
         return self

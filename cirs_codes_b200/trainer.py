@@ -170,28 +170,36 @@ def onpolicy_trainer(policy, train_collector, test_collector, state_tracker=None
     return gather_info(start_time, train_collector, test_collector, best_reward, best_reward_std)
 
 
-def save_checkpoint(path, policy, state_tracker):
-    """The reference's checkpoint dictionary (CIRS-RL-kuaishou.py:340-358).  'policy' / 'state_tracker' are state
-    dicts in the reference's parameter naming; the optimizer entries hold this package's flat Adam state."""
+def save_checkpoint(path, policy, state_tracker, optim=None):
+    """The reference's checkpoint dictionary (CIRS-RL-kuaishou.py:340-358): 'policy' / 'state_tracker' are state dicts
+    in the reference's parameter naming, 'optim_RL' / 'optim_state' are ``torch.optim.Adam.state_dict()``s in the
+    reference's parameter order (the policy's and the tracker's torch optimizers are bridged to the device-side Adam
+    state, PPOPolicy._bridge_optim) -- a checkpoint written here loads into the reference's optimizers and vice versa.
+    The running return statistics (a plain attribute of tianshou's policy, not part of its state_dict) travel under the
+    extra key 'ret_rms'."""
     import torch
-
-    def adam(obj):
-        return {"exp_avg": obj.exp_avg.detach().cpu(), "exp_avg_sq": obj.exp_avg_sq.detach().cpu(),
-                "step": obj.opt_state.detach().cpu()}
-
-    torch.save({"policy": policy.state_dict(), "optim_RL": adam(policy), "optim_state": adam(state_tracker),
-                "state_tracker": state_tracker.state_dict()}, path)
+    optim = optim or policy.optim
+    torch.save({"policy": policy.state_dict(), "optim_RL": optim[0].state_dict(),
+                "optim_state": optim[1].state_dict() if len(optim) > 1 else {},
+                "state_tracker": state_tracker.state_dict(), "ret_rms": policy.ret_rms.t.detach().cpu()}, path)
 
 
-def load_checkpoint(path, policy, state_tracker):
+def load_checkpoint(path, policy, state_tracker, optim=None):
+    """Inverse of save_checkpoint; also reads a checkpoint written by the reference (no 'ret_rms' key).  Optimizer
+    entries that cannot be restored raise instead of silently resetting Adam."""
     import torch
     ck = torch.load(path, map_location="cpu", weights_only=False)
+    optim = optim or policy.optim
     policy.load_state_dict(ck["policy"])
     state_tracker.load_state_dict(ck["state_tracker"])
-    for obj, key in ((policy, "optim_RL"), (state_tracker, "optim_state")):
-        st = ck.get(key, {})
-        if "exp_avg" in st and st["exp_avg"].numel() == obj.exp_avg.numel():
-            obj.exp_avg.copy_(st["exp_avg"])
-            obj.exp_avg_sq.copy_(st["exp_avg_sq"])
-            obj.opt_state.copy_(st["step"])
+    if "ret_rms" in ck:
+        policy.ret_rms.t.copy_(torch.as_tensor(ck["ret_rms"], dtype=torch.float64))
+    for opt, key in ((optim[0], "optim_RL"), (optim[1] if len(optim) > 1 else None, "optim_state")):
+        if opt is None:
+            continue
+        st = ck.get(key)
+        if not isinstance(st, dict) or "param_groups" not in st:
+            raise ValueError(f"checkpoint entry '{key}' is not a torch.optim.Adam state_dict: the optimizer state "
+                             "cannot be restored (re-save the checkpoint with this version, or drop the entry)")
+        opt.load_state_dict(st)
     return ck

@@ -147,6 +147,33 @@ int cirs_taobao_step(const cirs_taobao_env* env, int32_t n_rows, const int32_t* 
                      float* traj_act, float* traj_act_env, float* traj_rew, uint8_t* traj_done, int32_t* ep_len,
                      int32_t force_length, void* stream);
 
+/* The raw VirtualTaobao environment: user generator and click model with the weights the reference ships
+ * (virtualTB/data/generator_model.pt, action_model.pt), k-major like every Linear here.  Either half may be NULL when
+ * only the other entry point is used. */
+typedef struct {
+  const float *g1t, *g1b; /* generator_model.0  Wt[128][128]   (model/UserModel.py:9-13) */
+  const float *g2t, *g2b; /* generator_model.2  Wt[128][96]    (88 outputs) */
+  const float *a1t, *a1b; /* ActionModel.model.0  Wt[116][128] (model/ActionModel.py:8-14) */
+  const float *a2t, *a2b; /* ActionModel.model.2  Wt[128][256] */
+  const float *a3t, *a3b; /* ActionModel.model.4  Wt[256][32]  (21 outputs: 11 click counts, 10 page actions) */
+} cirs_virtualtb_weights;
+
+/* UserModel.generate (model/UserModel.py:40-60): n users, one-hot x 11 feature groups -> users[n, 88].
+ *   z [n, 128] the generator's seeds (torch.rand) or NULL -> Philox uniform [0, 1)
+ *   q [n, 88]  Exp(1) race draws of the 11 multinomials (draw j belongs to feature j) or NULL -> Philox */
+int cirs_virtualtb_generate_users(const cirs_virtualtb_weights* w, int32_t n, const float* z, const float* q,
+                                  uint64_t seed, uint64_t offset, float* users, void* stream);
+
+/* VirtualTB.step (envs/virtualTB.py:74-100) for n_rows environments of a cirs_taobao_env (its reward model `um` is
+ * not used): act[n, 27] (already mapped by policy.map_action), reward = the click count a = ActionModel.predict(user,
+ * total_turn, action)[0]; click[n, 2] (optional) = (a, b), the `lst_action` part of the next observation
+ * [action 27, a, b, total_turn].  q [n, 21]: Exp(1) race draws of the two multinomials (11 + 10) or NULL -> Philox.
+ * The new user drawn when an episode ends (virtualTB.py:96-98) is not generated: the Collector never steps a
+ * finished environment again before its reset (core/collector.py:294-311). */
+int cirs_virtualtb_step(const cirs_taobao_env* env, const cirs_virtualtb_weights* w, int32_t n_rows,
+                        const int32_t* env_id, const float* act, const float* q, uint64_t seed, uint64_t offset,
+                        float* rew, uint8_t* done, int32_t* click, int32_t force_length, void* stream);
+
 /* ------------------------------------------------------------------ StateTracker ------------------------ */
 typedef struct {
   float *in_wt, *in_b;     /* self_attn.in_proj  Wt[d][ld3d], b[3d] */
@@ -399,6 +426,15 @@ int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grad
 int cirs_update_plan(int32_t n_env, int32_t traj_len, const int32_t* n_slot, int32_t* tok_slot, int32_t* env_off,
                      void* stream);
 int cirs_gather_i32(int32_t* dst, const int32_t* src, const int32_t* idx, int32_t n, void* stream);
+
+/* Test-time coverage metrics of a collect on the device (evaluation.py:286-371 Callback_Coverage_Count):
+ * over the n stored transitions act[idx[i]] (idx NULL -> act[i]): out3[0] = number of DISTINCT recommended items
+ * (CV = out3[0] / n_item, CV_turn = out3[0] / n), out3[2] = sum_i item_weight[act_i] when item_weight is given (the
+ * dominated-category rate ifeat_* = out3[2] / n with item_weight[j] = the value get_feat_dominate_dict's integer
+ * arithmetic assigns to item j, evaluation.py:10-77; built once per callback on the host).  out3[1] is unused (0).
+ * bits: uint32[ceil(n_item / 32)] scratch.  Stream-ordered. */
+int cirs_coverage_count(int32_t n, const int32_t* idx, const int32_t* act, int32_t n_item, const int32_t* item_weight,
+                        uint32_t* bits, int64_t* out3, void* stream);
 
 /* ------------------------------------------------------------------ multi-GPU ---------------- */
 /* One process per GPU, environments sharded over ranks, parameters replicated; the reference has no multi-GPU path.

@@ -26,7 +26,7 @@ class KuaishouSimOracle:
 
     def __init__(self, mat, normed_mat, cats, alpha_u=None, beta_i=None, dist=None, *, max_turn=30,
                  num_leave_compute=1, leave_threshold=0, tau=100.0, gamma_exposure=10.0, r_decay=1.0,
-                 version="v1", simulated=True):
+                 version="v1", simulated=True, raw_user=None, raw_item=None):
         self.mat = np.asarray(mat, dtype=np.float64)
         self.normed = None if normed_mat is None else np.asarray(normed_mat, dtype=np.float64)
         self.cats = np.asarray(cats)
@@ -37,6 +37,10 @@ class KuaishouSimOracle:
         self.T, self.N, self.thr = int(max_turn), int(num_leave_compute), leave_threshold
         self.tau, self.gamma_e, self.r_decay, self.version = float(tau), float(gamma_exposure), float(r_decay), version
         self.simulated = simulated
+        # lbe_user.classes_ / lbe_photo.classes_: alpha_u / beta_i are then indexed by RAW id, through
+        # lbe_*.inverse_transform(encoded) == classes_[encoded]  (simulated_env.py:157-161)
+        self.raw_user = None if raw_user is None else np.asarray(raw_user)
+        self.raw_item = None if raw_item is None else np.asarray(raw_item)
 
     def reset(self, users):
         """kuaishouEnv.py:182-190, simulated_env.py:59-72.  users are injected (the reference draws
@@ -95,7 +99,9 @@ class KuaishouSimOracle:
                     dist = self._distance(a, hist)
                     E = float(np.sum(np.exp(-(t - np.arange(t)) * dist / self.tau)))
                     if self.alpha is not None:
-                        E = E * self.alpha[u] * self.beta[a]
+                        u_id = u if self.raw_user is None else int(self.raw_user[u])
+                        p_id = a if self.raw_item is None else int(self.raw_item[a])
+                        E = E * self.alpha[u_id] * self.beta[p_id]
                     E = E * self.gamma_e
                 r = self.normed[u, a]  # simulated_env.py:100
                 # clip0 == np.amax(x, 0) is an identity on scalars (util.py:53-54)
@@ -165,3 +171,48 @@ class TaobaoSimOracle:
             rew[k], done[k] = r, d
             obs[k] = np.concatenate([a, [r, 0.0, float(t + 1)]])  # simulated_env.py:50
         return obs, rew, done
+
+
+class VirtualTBOracle:
+    """The raw VirtualTB environment's two networks (environments/VirtualTaobao/virtualTB/model/UserModel.py:13-60,
+    model/ActionModel.py:6-23) in numpy float32, with the multinomial draws as explicit exponential races
+    argmax_j p_j / q_j (what torch.multinomial(p, 1) computes) so that recorded noise can be replayed.
+    ``gen`` / ``act``: state_dicts of generator_model / ActionModel.model ("0.weight", "0.bias", "2.weight", ...)."""
+
+    GROUPS = (0, 8, 16, 27, 38, 49, 60, 62, 64, 67, 85, 88)  # UserModel.py:22-32
+
+    def __init__(self, gen=None, act=None):
+        f = lambda sd: None if sd is None else {k: np.asarray(v, dtype=np.float32) for k, v in sd.items()}  # noqa: E731
+        self.gen, self.act = f(gen), f(act)
+
+    @staticmethod
+    def _softmax(x):
+        e = np.exp(x - x.max(axis=1, keepdims=True))
+        return e / e.sum(axis=1, keepdims=True)
+
+    @staticmethod
+    def _leaky(x):
+        return np.where(x > 0, x, np.float32(0.01) * x)
+
+    def generate(self, z, q):
+        """UserModel.generate: z [n,128] uniform seeds, q [n,88] Exp(1) draws -> one-hot x 11 users [n,88]."""
+        g = self.gen
+        h = self._leaky(np.asarray(z, np.float32) @ g["0.weight"].T + g["0.bias"])
+        x = h @ g["2.weight"].T + g["2.bias"]
+        out = np.zeros_like(x)
+        for lo, hi in zip(self.GROUPS[:-1], self.GROUPS[1:]):
+            p = self._softmax(x[:, lo:hi])
+            out[np.arange(len(x)), lo + np.argmax(p / np.asarray(q, np.float32)[:, lo:hi], axis=1)] = 1.0
+        return out
+
+    def click(self, user, page, action, q):
+        """ActionModel.predict(user [n,88], page [n,1], action [n,27]) with q [n,21] -> int [n,2] = (a, b)."""
+        a = self.act
+        x = np.concatenate([user, page, action], axis=1).astype(np.float32)
+        h = self._leaky(x @ a["0.weight"].T + a["0.bias"])
+        h = self._leaky(h @ a["2.weight"].T + a["2.bias"])
+        y = h @ a["4.weight"].T + a["4.bias"]
+        q = np.asarray(q, np.float32)
+        ca = np.argmax(self._softmax(y[:, :11]) / q[:, :11], axis=1)
+        cb = np.argmax(self._softmax(y[:, 11:]) / q[:, 11:], axis=1)
+        return np.stack([ca, cb], axis=1)

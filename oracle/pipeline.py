@@ -31,10 +31,15 @@ class Trajectory:
         return u
 
 
-def collect(env, tracker, R, users, *, actions=None, noise=None, force_length=0, record=None, action_space=None):
+def collect(env, tracker, R, users, *, actions=None, noise=None, force_length=0, record=None, action_space=None,
+            remove_recommended=False):
     """One Collector.collect(n_episode=B).  Actions come from, in order of preference: ``actions`` (teacher
     forcing: list per turn of arrays aligned with the ready set), ``noise`` (callable(turn, n, A) -> q, Exp(1)
-    race noise) or argmax of the probabilities.  Returns (Trajectory, result-dict like collector.py:352-362)."""
+    race noise) or argmax of the probabilities.  Returns (Trajectory, result-dict like collector.py:352-362).
+    ``remove_recommended`` (the NX_* test collectors, core/collector_set.py:19): the items already recommended in the
+    running episode (get_recommended_ids, core/policy/utils.py:7-27) are removed from the actor's probabilities
+    before Categorical renormalises and samples (removed_recommended_id_from_embedding :30-58, ppo.py:134-160);
+    ``noise`` stays indexed by ORIGINAL catalogue column (the masked columns' draws are unused)."""
     B = len(users)
     obs0 = env.reset(users)
     tracker.reset(B)
@@ -61,10 +66,24 @@ def collect(env, tracker, R, users, *, actions=None, noise=None, force_length=0,
         else:
             with torch.no_grad():
                 p = nets.actor_probs(R, s.detach())
+            if remove_recommended:
+                keep = torch.ones_like(p, dtype=torch.bool)
+                for k, e in enumerate(ready):
+                    if per_env[e]["act"]:
+                        keep[k, torch.as_tensor(np.asarray(per_env[e]["act"], dtype=np.int64))] = False
+                p = torch.where(keep, p, torch.zeros_like(p))    # masked_select + Categorical's renormalisation
+                p = p / p.sum(-1, keepdim=True)
             if actions is not None:
                 act = np.asarray(actions[turn]).reshape(-1)
+                if remove_recommended:
+                    assert all(int(a) not in per_env[e]["act"] for a, e in zip(act, ready)), \
+                        "a forced action repeats an item of its episode"
             elif noise is not None:
-                act = nets.sample_race(p, noise(turn, len(ready), p.shape[1])).numpy()
+                q = torch.as_tensor(noise(turn, len(ready), p.shape[1]))
+                if remove_recommended:   # p = 0 on masked columns: p / q = 0 there, never the argmax
+                    act = torch.argmax(p / q, -1).numpy()
+                else:
+                    act = nets.sample_race(p, q).numpy()
             else:
                 act = torch.argmax(p, -1).numpy()
             obs_next_raw, rew, done = env.step(act, ready)

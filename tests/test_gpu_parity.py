@@ -466,7 +466,7 @@ def test_trainer_end_to_end_and_checkpoint(H, tmp_path):
     before = pol.flat.clone(), trk.flat.clone(), pol.exp_avg.clone()
     pol.flat.zero_(); trk.flat.zero_(); pol.exp_avg.zero_()
     ck = cb.load_checkpoint(path, pol, trk)
-    assert set(ck) == {"policy", "optim_RL", "optim_state", "state_tracker"}
+    assert set(ck) == {"policy", "optim_RL", "optim_state", "state_tracker", "ret_rms"}
     assert torch.equal(pol.flat, before[0]) and torch.equal(pol.exp_avg, before[2])
     # padding columns aside, the tracker's parameters survive the state_dict round trip
     sd = trk.state_dict()
@@ -494,3 +494,62 @@ def test_fused_collect_wide_catalogue_falls_back_to_ffma_head(H):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     G.assert_close(outs[0][2], outs[1][2], 1e-6, what="rew")
     assert outs[0][3] == outs[1][3]
+
+
+def test_checkpoint_is_reference_adam_format(H, tmp_path):
+    """save_checkpoint writes torch.optim.Adam state_dicts in the reference's parameter order (CIRS-RL-kuaishou.py:
+    340-358): they load into plain torch optimizers built the way the reference builds them (trunk listed twice), the
+    moments equal the device-side Adam state, and a fresh policy restored from the file continues identically."""
+    import cirs_codes_b200 as cb
+    z = G.load("kuaishou_N5")
+    c = G.cfg(z)
+
+    def build():
+        trk = H.make_tracker(z, c)
+        pol = H.make_policy(z, c, trk)
+        return trk, pol
+
+    trk, pol = build()
+    col, buf, res = _golden_collect(H, z, c, 0, trk, pol)
+    perms = G.perms(z, 0, len(buf))
+    pol.update(0, buf, batch_size=c["batch_size"], repeat=c["repeat"], perms=perms)
+    path = str(tmp_path / "ck.pt")
+    cb.save_checkpoint(path, pol, trk)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) >= {"policy", "optim_RL", "optim_state", "state_tracker"} and "ret_rms" not in ck["policy"]
+    # (a) plain torch optimizers over reference-shaped modules accept the entries
+    net = cb.Net(20, hidden_sizes=[64, 64])
+    actor, critic = cb.Actor(net, c["I"]), cb.Critic(net)
+    opt_rl = torch.optim.Adam(list(actor.parameters()) + list(critic.parameters()), lr=1e-3)
+    opt_rl.load_state_dict(ck["optim_RL"])
+    n_mb = len(G.perms(z, 0, len(buf))) * len(pol_split(len(buf), c["batch_size"]))
+    trunk_p = next(iter(net.parameters()))
+    assert float(opt_rl.state[trunk_p]["step"]) == 2 * n_mb            # the shared trunk steps twice per minibatch
+    last_p = actor.last.model[0].weight
+    assert float(opt_rl.state[last_p]["step"]) == n_mb
+    m = pol.layout.unpack(pol.exp_avg)
+    assert torch.equal(opt_rl.state[last_p]["exp_avg"], m["actor.last.weight"])
+    assert torch.equal(opt_rl.state[trunk_p]["exp_avg"], m["trunk.0.weight"])
+    ref_like = [torch.nn.Parameter(v.clone()) for v in trk.layout.unpack(trk.flat).values()]
+    opt_tr = torch.optim.Adam(ref_like, lr=1e-3)
+    opt_tr.load_state_dict(ck["optim_state"])
+    assert float(opt_tr.state[ref_like[0]]["step"]) == 1               # one tracker step per update (ppo.py:235)
+    assert torch.equal(opt_tr.state[ref_like[0]]["exp_avg"], trk.layout.unpack(trk.exp_avg)[
+        "embedding_dict.feat_user.weight"])
+    # (b) round trip into fresh objects: parameters, moments, counters, return statistics
+    trk2, pol2 = build()
+    cb.load_checkpoint(path, pol2, trk2)
+    for a, b in ((pol.flat, pol2.flat), (pol.exp_avg, pol2.exp_avg), (pol.exp_avg_sq, pol2.exp_avg_sq),
+                 (pol.opt_state, pol2.opt_state), (trk.flat, trk2.flat), (trk.exp_avg, trk2.exp_avg),
+                 (trk.exp_avg_sq, trk2.exp_avg_sq), (trk.opt_state, trk2.opt_state), (pol.ret_rms.t, pol2.ret_rms.t)):
+        assert torch.equal(a, b)
+    # (c) an entry that is not an Adam state_dict is refused, not silently skipped
+    ck["optim_RL"] = {"exp_avg": torch.zeros(3)}
+    torch.save(ck, path)
+    with pytest.raises(ValueError):
+        cb.load_checkpoint(path, pol2, trk2)
+
+
+def pol_split(n, size):
+    from cirs_codes_b200.parallel import split_sizes
+    return split_sizes(n, size)

@@ -356,3 +356,88 @@ def test_fused_rollout_matches_generic(H):
         G.assert_close(a[k], b[k], 1e-6, 1e-7, what=k)
     assert a["res"]["n/st"] == b["res"]["n/st"] and np.array_equal(a["res"]["lens"], b["res"]["lens"])
     G.assert_close(a["res"]["rews"], b["res"]["rews"], 1e-6, what="episode rewards")
+
+
+# ------------------------------------------------------------------ E6: raw VirtualTB -- user generator, click model, step
+def _vtb():
+    z = G.load("taobao_usergen")
+    sub = lambda p: {k[len(p):]: z[k] for k in z.files if k.startswith(p)}  # noqa: E731
+    return z, sub("generator/"), sub("action/")
+
+
+def test_virtualtb_user_generator_vs_golden():
+    """UserModel.generate on the device (csrc/virtualtb.cu) with the reference's recorded seeds z and race noise q:
+    the one-hot users are exactly the reference's; with its own Philox draws it still produces valid one-hot x 11
+    users whose per-group frequencies follow the generator's softmax probabilities."""
+    import cirs_codes_b200 as cb
+    from cirs_codes_b200 import env as E, params
+    from oracle import env as oenv
+    z, gen, act = _vtb()
+    packed = params.virtualtb_pack(generator_sd=E._cpu_sd(gen), device="cuda")
+    got = E.generate_users(packed, len(z["gen/z"]), torch.device("cuda"), z=z["gen/z"], q=z["gen/q"]).cpu().numpy()
+    assert np.array_equal(got, z["gen/user"])
+    # the TaobaoVectorEnv draws its users through the same kernel when it is given the generator
+    env = cb.TaobaoVectorEnv(4, H_um(), generator=gen, seed=3)
+    u = env.draw_users(512)
+    off = np.array(oenv.VirtualTBOracle.GROUPS)
+    assert u.shape == (512, 88) and np.all(u.sum(1) == 11)
+    assert all(np.all(u[:, lo:hi].sum(1) == 1) for lo, hi in zip(off[:-1], off[1:]))
+    u2 = env.draw_users(512)
+    assert not np.array_equal(u, u2)                       # a fresh Philox offset per call
+    # distribution check: mean one-hot frequency vs mean softmax probability over many seeds (same z distribution)
+    rng = np.random.default_rng(0)
+    zz = rng.random((4096, 128), dtype=np.float32)
+    o = oenv.VirtualTBOracle(gen, None)
+    h = o._leaky(zz @ o.gen["0.weight"].T + o.gen["0.bias"])
+    x = h @ o.gen["2.weight"].T + o.gen["2.bias"]
+    want = np.concatenate([o._softmax(x[:, lo:hi]) for lo, hi in zip(off[:-1], off[1:])], axis=1).mean(0)
+    mine = E.generate_users(packed, 4096, torch.device("cuda"), seed=11, offset=1, z=zz).cpu().numpy().mean(0)
+    assert np.abs(mine - want).max() < 0.03, float(np.abs(mine - want).max())
+
+
+def H_um():
+    z = G.load("taobao_N3")
+    return {k[len("usermodel/"):]: torch.tensor(np.asarray(z[k])) for k in z.files if k.startswith("usermodel/")}
+
+
+def test_virtualtb_step_vs_golden_and_oracle():
+    """VirtualTB.step on the device: clicks (a, b) of the reference's recorded click-model calls are exact; a
+    teacher-forced episode against the oracle (exit test, turn counter, observation layout)."""
+    import cirs_codes_b200 as cb
+    from oracle import env as oenv
+    z, gen, act = _vtb()
+    n = len(z["click/act"])
+    env = cb.VirtualTBVectorEnv(n, gen, act, max_turn=50, num_leave_compute=5, leave_threshold=3.0, seed=5)
+    env.reset(users=z["click/user"])
+    # the golden calls used arbitrary page numbers: set the environments' turn counters to them
+    env.turn.copy_(torch.as_tensor(z["click/page"].reshape(-1).astype(np.int32), device="cuda"))
+    obs, rew, done, info = env.step(z["click/act"], q=z["click/q"])
+    assert np.array_equal(rew.astype(np.int64), z["click/result"][:, 0])
+    live = ~done
+    assert np.array_equal(obs[live, 27:29].astype(np.int64), z["click/result"][live])
+    assert np.array_equal(obs[:, 29].astype(np.int64), z["click/page"].reshape(-1).astype(np.int64) + 1)
+    # a short episode with the oracle's click model and its own noise: rewards exact, exit test on repeated actions
+    o = oenv.VirtualTBOracle(gen, act)
+    B = 8
+    env = cb.VirtualTBVectorEnv(B, gen, act, max_turn=6, num_leave_compute=3, leave_threshold=1.0, seed=5)
+    users = z["gen/user"][:B]
+    first = env.reset(users=users)
+    assert first.shape == (B, 91) and np.array_equal(first[:, :88], users) and np.all(first[:, 88:] == 0)
+    rng = np.random.default_rng(2)
+    prev = None
+    for t in range(6):
+        a = rng.uniform(-1, 1, size=(B, 27)).astype(np.float32)
+        if t == 2:
+            a[:4] = prev[:4] + 0.01                       # within the exit radius of the previous action -> leave
+        q = rng.exponential(size=(B, 21)).astype(np.float32)
+        obs, rew, done, info = env.step(a, q=q)
+        want = o.click(users, np.full((B, 1), t, np.float32), a, q)
+        assert np.array_equal(rew.astype(np.int64), want[:, 0])
+        exp_done = np.zeros(B, bool)
+        if t == 2:
+            exp_done[:4] = True
+        if t == 5:
+            exp_done[:] = True                             # t >= max_turn - 1
+        assert np.array_equal(done, exp_done), (t, done)
+        assert np.all(obs[:, 29] == t + 1) and np.array_equal(obs[:, :27].astype(np.float32), a)
+        prev = a

@@ -279,3 +279,78 @@ def test_coverage_callback_matches_reference():
                                              top_rate=0.6).on_epoch_end(1, dict(results))
         for k in ("CV", "CV_turn", "ifeat_feat", "NX_0_CV", "NX_0_CV_turn", "NX_0_ifeat_feat"):
             assert abs(theirs[k] - got[k]) < 1e-12, (k, theirs[k], got[k])
+
+
+def test_batch_item_assignment_and_split_match_tianshou():
+    """D1: Batch.__setitem__(index) and Batch.split (tianshou/data/batch.py:244-267, 721-744) against tianshou's own
+    Batch when the reference tree is present (build container); otherwise against their documented behaviour."""
+    import torch
+    from cirs_codes_b200.data import Batch
+    b = Batch(obs=torch.arange(12.).reshape(6, 2), act=np.arange(6), info=Batch(), rew=np.zeros(6))
+    b[np.array([1, 3])] = Batch(obs=torch.full((2, 2), -1.), act=np.array([10, 30]))
+    assert b.act.tolist() == [0, 10, 2, 30, 4, 5] and b.obs[3].tolist() == [-1., -1.]
+    assert b.rew.tolist() == [0.] * 6                       # a key missing on the right-hand side is zero-filled
+    b[0] = {"act": 7}
+    assert b.act[0] == 7 and b.obs[0].tolist() == [0., 0.]  # ... including tensors
+    with pytest.raises(ValueError):
+        b[0] = Batch(new_key=1)
+    with pytest.raises(ValueError):
+        b[0] = np.zeros(2)
+    sizes = [len(x) for x in Batch(a=np.arange(10)).split(4, shuffle=False, merge_last=True)]
+    assert sizes == [4, 6]
+    sizes = [len(x) for x in Batch(a=np.arange(10)).split(4, shuffle=False)]
+    assert sizes == [4, 4, 2]
+    assert [len(x) for x in Batch(a=np.arange(3)).split(8)] == [3]
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):
+        from oracle import ref_shims
+        ref_shims.install()
+        from tianshou.data import Batch as TB
+        np.random.seed(3)
+        mine = [x.a.tolist() for x in Batch(a=np.arange(23)).split(5, shuffle=True, merge_last=True)]
+        np.random.seed(3)
+        theirs = [x.a.tolist() for x in TB(a=np.arange(23)).split(5, shuffle=True, merge_last=True)]
+        assert mine == theirs
+        t = TB(obs=np.arange(12.).reshape(6, 2), act=np.arange(6), rew=np.zeros(6))
+        m = Batch(obs=np.arange(12.).reshape(6, 2), act=np.arange(6), rew=np.ones(6))
+        t.rew[:] = 1
+        t[np.array([1, 3])] = TB(act=np.array([10, 30]))
+        m[np.array([1, 3])] = Batch(act=np.array([10, 30]))
+        assert np.array_equal(t.act, m.act) and np.array_equal(t.rew, m.rew) and np.array_equal(t.obs, m.obs)
+
+
+def test_loggers_match_reference_format(tmp_path):
+    """LoggerCallback_Policy's Info line and BasicLogger's scalar keys (util/utils.py:84-136,
+    tianshou/utils/log_tools.py:84-200); compared with the reference's own classes when the reference tree is present."""
+    import cirs_codes_b200 as cb
+    results = {"n/ep": 4, "n/st": 20, "rew": 12.5, "CV": 0.123456, "CV_turn": 0.5, "ifeat_feat": 0.75,
+               "NX_0_n/st": 16, "NX_0_rew": 10.0, "NX_0_CV": 0.2, "NX_0_CV_turn": 0.9, "NX_0_ifeat_feat": 0.5,
+               "NX_10_n/st": 40, "NX_10_rew": 30.0, "NX_10_CV": 0.3, "NX_10_CV_turn": 1.0, "NX_10_ifeat_feat": 0.25}
+    path = tmp_path / "log.txt"
+    line = cb.LoggerCallback_Policy(str(path), 10).on_epoch_end(3, dict(results))
+    assert line.startswith("Epoch: [3], Info: [{'num_test': 4, 'CV': '0.12346', 'CV_turn': '0.50000', 'ctr': '2.50000'")
+    assert "'NX_10_ifeat_feat': 0.25" in line and path.read_text().strip() == line
+    rec = cb.ScalarRecorder()
+    lg = cb.BasicLogger(rec, train_interval=1, update_interval=1)
+    r = {"n/ep": 2, "rews": np.array([1., 3.]), "lens": np.array([2, 4])}
+    lg.log_train_data(r, 10)
+    lg.log_test_data(dict(r), 10)
+    lg.log_update_data({"loss": 0.5}, 7)
+    lg.save_data(1, 10, 7, lambda *a: None)
+    assert r["rew"] == 2.0 and set(rec.scalars) == {"train/n/ep", "train/rew", "train/len", "test/rew", "test/len",
+                                                      "test/rew_std", "test/len_std", "loss", "save/epoch",
+                                                      "save/env_step", "save/gradient_step"}
+    assert lg.restore_data() == (1, 10, 7)
+    if os.path.isdir("/root/reference"):
+        from oracle import ref_shims
+        ref_shims.install()
+        import util.utils as ru
+        got = []
+
+        class _L:
+            def info(self, msg):
+                got.append(msg)
+
+        ru.logger = _L()
+        ru.LoggerCallback_Policy(str(tmp_path / "x.log"), 10).on_epoch_end(3, dict(results))
+        assert got and got[0] == line

@@ -232,3 +232,79 @@ def test_user_model_oracle_vs_golden():
     nm = um.compute_normed_reward(P, g["users"], g["items"], g["item_feat"], g["item_dense"])
     assert nm.min() == 0.0 and nm.max() == 1.0
     np.testing.assert_allclose(nm, g["normed_mat"], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ label encoders, test collectors (kuaishou_testcol)
+def _testcol():
+    z = G.load("kuaishou_testcol")
+    U, I, B, T, N, thr, d, nhead, force_length, seed = (int(x) for x in z["cfg"])
+    tau, gamma_e, r_decay = (float(x) for x in z["cfg_f"])
+    return z, dict(U=U, I=I, B=B, T=T, N=N, thr=thr, d=d, nhead=nhead, force_length=force_length, seed=seed, tau=tau,
+                   gamma_exposure=gamma_e, r_decay=r_decay)
+
+
+def test_oracle_raw_id_alpha_beta_vs_golden():
+    """SimulatedEnv whose alpha_u / beta_i are indexed by RAW id through NON-identity label encoders
+    (simulated_env.py:157-161), teacher-forced with the reference's recorded actions."""
+    z, c = _testcol()
+    env = oenv.KuaishouSimOracle(z["mat"], z["normed_mat"], z["cats"], z["alpha_raw"], z["beta_raw"],
+                                 max_turn=c["T"], num_leave_compute=c["N"], leave_threshold=c["thr"], tau=c["tau"],
+                                 gamma_exposure=c["gamma_exposure"], r_decay=c["r_decay"], version="v1",
+                                 raw_user=z["raw_user"], raw_item=z["raw_item"])
+    assert np.isnan(z["alpha_raw"]).any(), "the raw-id tables must have holes an encoded index would hit"
+    for ep in range(int(z["sim/n_ep"])):
+        env.reset(z[f"sim/ep{ep}/user"])
+        for t, a in enumerate(z[f"sim/ep{ep}/act"]):
+            _, rew, done = env.step([a])
+            assert bool(done[0]) == bool(z[f"sim/ep{ep}/done"][t])
+            G.assert_close(rew[0], z[f"sim/ep{ep}/rew"][t], 1e-9, what=f"ep{ep} turn {t}")
+
+
+@pytest.mark.parametrize("cname", ["FB", "NX_0", "NX_5"])
+def test_oracle_test_collectors_vs_golden(cname):
+    """core/collector_set.py:13-77 on raw KuaishouEnv: free browsing, remove_recommended_ids, + force_length, replayed
+    with the reference's recorded race noise: actions / done / lengths exact, rewards and states 1e-5."""
+    z, c = _testcol()
+    env = oenv.KuaishouSimOracle(z["mat"], None, z["cats"], max_turn=c["T"], num_leave_compute=c["N"],
+                                 leave_threshold=c["thr"], simulated=False)
+    P = nets.to_params(z, "init/tracker/")
+    R = nets.rl_params(nets.to_params(z, "init/actor/"), nets.to_params(z, "init/critic/"))
+    tracker = nets.TrackerOracle(P, c["nhead"], c["T"], keep_graph=False)
+    n_turns = int(z[f"{cname}/n_turns"])
+    gt = [{k: z[f"{cname}/turn{t}/{k}"] for k in ("state", "q", "act", "env_id", "rew", "done", "state_next",
+                                                    "n_masked")} for t in range(n_turns)]
+    rec = []
+    traj, res = pipeline.collect(env, tracker, R, z[f"{cname}/users"], noise=lambda t, n, A: gt[t]["q"],
+                                 force_length=c["force_length"] if cname == "NX_5" else 0, record=rec,
+                                 remove_recommended=cname != "FB")
+    assert len(rec) == n_turns
+    for t, (mine, ref) in enumerate(zip(rec, gt)):
+        assert np.array_equal(mine["env_id"], ref["env_id"]), f"ready set, turn {t}"
+        assert np.array_equal(mine["act"], ref["act"]), f"actions, turn {t}"
+        assert np.array_equal(mine["done"], ref["done"]), f"done, turn {t}"
+        assert int(ref["n_masked"]) == (t if cname != "FB" else 0)
+        G.assert_close(mine["rew"], ref["rew"], 1e-6, what=f"rew turn {t}")
+        G.assert_close(mine["state"], ref["state"], 1e-5, 1e-6, what=f"state turn {t}")
+    assert np.array_equal(traj.lengths, z[f"{cname}/buf/lengths"])
+    assert np.array_equal(traj.act, z[f"{cname}/buf/act"])
+    assert np.array_equal(res["lens"], z[f"{cname}/res/lens"])
+    G.assert_close(res["rews"], z[f"{cname}/res/rews"], 1e-6, what="episode rewards")
+    if cname != "FB":
+        off = np.concatenate([[0], np.cumsum(traj.lengths)])
+        assert all(len(set(traj.act[off[e]:off[e + 1]])) == off[e + 1] - off[e] for e in range(c["B"]))
+
+
+# ------------------------------------------------------------------ raw VirtualTB: generator and click model
+def _sub(z, prefix):
+    return {k[len(prefix):]: z[k] for k in z.files if k.startswith(prefix)}
+
+
+def test_oracle_virtualtb_generator_and_click_model_vs_golden():
+    """UserModel.generate and ActionModel.predict with the shipped weights and the reference's recorded seeds / race
+    noise (oracle/make_golden_extra.py usergen): the generated one-hot users and the (a, b) click results are exact."""
+    z = G.load("taobao_usergen")
+    o = oenv.VirtualTBOracle(_sub(z, "generator/"), _sub(z, "action/"))
+    users = o.generate(z["gen/z"], z["gen/q"])
+    assert np.array_equal(users, z["gen/user"]) and np.all(users.sum(1) == 11)
+    got = o.click(z["click/user"], z["click/page"], z["click/act"], z["click/q"])
+    assert np.array_equal(got, z["click/result"])
