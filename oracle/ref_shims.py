@@ -140,4 +140,11 @@ def install():
     for p in (REF + "/environments/VirtualTaobao", REF + "/DeepCTR-Torch", REF + "/tianshou", REF):
         if p not in sys.path:
             sys.path.insert(0, p)
+    # this repository's root stays in front: DeepCTR-Torch ships a top-level ``tests`` package that would otherwise
+    # shadow ours (multiprocessing children re-import ``tests.*`` through the parent's sys.path)
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root in sys.path:
+        sys.path.remove(root)
+    sys.path.insert(0, root)
     install._done = True
