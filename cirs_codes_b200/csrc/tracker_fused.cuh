@@ -135,6 +135,114 @@ __device__ __forceinline__ void tile_linear(const float* Xs, int ldx, const floa
   __syncthreads();   // the outputs are visible to the whole CTA
 }
 
+// ---- the same product with the weight matrix RESIDENT in shared memory (rows k-major like the global layout, row
+// stride ldw = padded width + 4 floats, so both orientations read conflict-free 16-byte words):
+//   TRANS = false: thread owns columns 4 tx .. + 3 of each 128-column block  (Wop[k][n] = Ws[k * ldw + n])
+//   TRANS = true : thread owns the n-indices tx + 32 j, j < 4, and reads Ws[n * ldw + k .. k + 3] as one float4: lane
+//                  stride = one row = 4 (mod 32) floats                     (Wop[k][n] = Ws[n * ldw + k])
+// No weight traffic, no barrier inside: one barrier in front (the X tile is complete) and one behind.
+template <int TM, bool TRANS, class Ep>
+__device__ __forceinline__ void tile_linear_res(const float* Xs, int ldx, const float* Ws, int ldw, int m, int N, int K,
+                                                Ep ep) {
+  constexpr int RPT = TM / 8;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int K4 = up4(K);
+  const float* xr = Xs + (size_t)(ty * RPT) * ldx;
+  __syncthreads();
+  for (int n0 = 0; n0 < N; n0 += 128) {
+    float acc[RPT][4];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    if (!TRANS) {
+      if (n0 + 4 * tx < N) {
+        const float* wp = Ws + n0 + 4 * tx;
+#pragma unroll 2
+        for (int k = 0; k < K4; k += 4) {
+          float4 b[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(wp + (size_t)(k + j) * ldw);
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + (size_t)i * ldx + k);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[i][0] = fmaf(av[j], b[j].x, acc[i][0]);
+              acc[i][1] = fmaf(av[j], b[j].y, acc[i][1]);
+              acc[i][2] = fmaf(av[j], b[j].z, acc[i][2]);
+              acc[i][3] = fmaf(av[j], b[j].w, acc[i][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = ty * RPT + i;
+          if (r >= m) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n0 + 4 * tx + j < N) ep(r, n0 + 4 * tx + j, acc[i][j]);
+        }
+      }
+    } else {
+      const float* wp[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ok[j] = n0 + tx + 32 * j < N;
+        wp[j] = Ws + (size_t)(ok[j] ? n0 + tx + 32 * j : 0) * ldw;
+      }
+      if (ok[0]) {
+#pragma unroll 2
+        for (int k = 0; k < K4; k += 4) {
+          float4 w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(wp[j] + k);
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + (size_t)i * ldx + k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[i][j] = fmaf(a.x, w[j].x, fmaf(a.y, w[j].y, fmaf(a.z, w[j].z, fmaf(a.w, w[j].w, acc[i][j]))));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = ty * RPT + i;
+          if (r >= m) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (ok[j]) ep(r, n0 + tx + 32 * j, acc[i][j]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// the tracker's Linear weights: id -> (global pointer, its row stride, rows, resident copy, the copy's row stride)
+enum { M_USER = 0, M_GATE = 1, M_LAYER0 = 2, M_PER_LAYER = 4 };   // per layer: in, out, l1, l2; then the decoder
+constexpr int MAX_MATS = 2 + 4 * CIRS_MAX_LAYERS + 1;
+struct Mat { const float* g; const float* s; int ldw, rows, lds; };
+__device__ __forceinline__ int m_in(int l) { return M_LAYER0 + M_PER_LAYER * l; }
+__device__ __forceinline__ int m_out(int l) { return M_LAYER0 + M_PER_LAYER * l + 1; }
+__device__ __forceinline__ int m_l1(int l) { return M_LAYER0 + M_PER_LAYER * l + 2; }
+__device__ __forceinline__ int m_l2(int l) { return M_LAYER0 + M_PER_LAYER * l + 3; }
+
+// floats of shared memory the resident copies need (rows rounded up to 4, row stride = padded width + 4)
+__host__ __device__ inline int resident_floats(const cirs_tracker_weights& W) {
+  const int d = W.d, ldd = (d + 31) & ~31, ld3 = (3 * d + 31) & ~31, ldh = (W.d_hid + 31) & ~31,
+            lds = (W.dim_state + 31) & ~31;
+  int n = up4(W.d_user_in) * (ldd + 4) + up4(1 + W.d_item_in) * (ldd + 4) + up4(d) * (lds + 4);
+  n += W.nlayers * (up4(d) * (ld3 + 4) + up4(d) * (ldd + 4) + up4(d) * (ldh + 4) + up4(W.d_hid) * (ldd + 4));
+  return n;
+}
+
+template <int TM, bool TRANS, bool RES, class Ep>
+__device__ __forceinline__ void lin(const float* Xs, int ldx, const Mat& M, int m, int N, int K, float* stage, Ep ep) {
+  if (RES) tile_linear_res<TM, TRANS>(Xs, ldx, M.s, M.lds, m, N, K, ep);
+  else tile_linear<TM, TRANS>(Xs, ldx, M.g, M.ldw, m, N, K, stage, ep);
+}
+
 // one warp per row: X = LayerNorm(R) * w + b (biased variance, eps 1e-5); statistics to ST (global)
 __device__ __forceinline__ void ln_fwd_rows(const float* Rs, float* Xs, int ldx, int m, int d, const float* __restrict__ w,
                                             const float* __restrict__ b, float* __restrict__ xg, float* __restrict__ st,
@@ -350,7 +458,9 @@ __device__ __forceinline__ void attn_backward(const float* QKV, float* dQKV, int
   __syncthreads();
 }
 
-template <int TM>
+// RES: every Linear weight of the tracker is copied into shared memory once per CTA (d <= 32: ~120 KB) and all the
+// stage products run from there (tile_linear_res); otherwise weight blocks stream through the stage (tile_linear).
+template <int TM, bool RES>
 __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
   extern __shared__ __align__(16) float sm[];
   const cirs_tracker_weights& W = A.W;
@@ -365,13 +475,48 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
   float* zs = ys + TM * ldx;
   float* big = zs + TM * ldx;
   float* big2 = big + TM * ldb;
-  float* stage = big2 + TM * ldb;
-  float* stat = stage + WS_K * WS_LD;            // [3][TM][nh] attention row statistics (backward)
+  float* stage = big2 + TM * ldb;                // weight stage (streaming) / attention probabilities
+  float* stat = stage + (RES ? TM * TM * nh : WS_K * WS_LD);   // [3][TM][nh] attention row statistics (backward)
   float* pw = stat + 3 * TM * nh;                // [8 warps][2][TM] probability / dS scratch
   float* lnacc = pw + 8 * 2 * TM;                // [2 d]
   int* rpos = reinterpret_cast<int*>(lnacc + 2 * ((d + 3) & ~3));   // [TM] position of the row inside its episode
   int* renv = rpos + TM;                         // [TM] environment of the row
   int* rstart = renv + TM;                       // [TM] chunk-local first row of the row's environment
+  __shared__ Mat mats[MAX_MATS];
+  if (tid == 0) {
+    float* wres = reinterpret_cast<float*>(rstart + TM);
+    wres = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wres) + 15) & ~(uintptr_t)15);
+    auto put = [&](int id, const float* g, int ldw, int rows) {
+      Mat& M = mats[id];
+      M.g = g; M.ldw = ldw; M.rows = rows; M.lds = ldw + 4; M.s = wres;
+      if (RES) wres += up4(rows) * (ldw + 4);
+    };
+    put(M_USER, W.user_wt, ldd, dui);
+    put(M_GATE, W.gate_wt, ldd, 1 + d);
+    for (int l = 0; l < nl; ++l) {
+      put(m_in(l), W.layer[l].in_wt, ld3, d);
+      put(m_out(l), W.layer[l].out_wt, ldd, d);
+      put(m_l1(l), W.layer[l].l1_wt, ldh, d);
+      put(m_l2(l), W.layer[l].l2_wt, ldd, dhid);
+    }
+    put(M_LAYER0 + M_PER_LAYER * nl, W.dec_wt, lds, d);
+  }
+  __syncthreads();
+  const int M_DEC = M_LAYER0 + M_PER_LAYER * nl;
+  if (RES) {   // resident copies: [up4(rows)][ldw + 4], zero beyond the matrix
+    for (int id = 0; id <= M_DEC; ++id) {
+      const Mat M = mats[id];
+      float* dst = const_cast<float*>(M.s);
+      const int r4 = up4(M.rows), w4 = M.ldw >> 2;
+      for (int i = tid; i < r4 * (w4 + 1); i += NT) {
+        const int r = i / (w4 + 1), c = (i % (w4 + 1)) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < M.rows && c < M.ldw) v = __ldg(reinterpret_cast<const float4*>(M.g + (size_t)r * M.ldw + c));
+        *reinterpret_cast<float4*>(dst + (size_t)r * M.lds + c) = v;
+      }
+    }
+    __syncthreads();
+  }
 
   const float sq = sqrtf((float)d), scale = 1.0f / sqrtf((float)dh);
   const int n_chunks = (A.M + A.q - 1) / A.q;
@@ -419,7 +564,7 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       big[(size_t)r * ldb + c] = v;
       A.S.u[(row0 + r) * dui + c] = v;
     }
-    tile_linear<TM, false>(big, ldb, W.user_wt, ldd, m, d, dui, stage, [&](int r, int c, float v) {
+    lin<TM, false, RES>(big, ldb, mats[M_USER], m, d, dui, stage, [&](int r, int c, float v) {
       if (rpos[r] == 0) zs[(size_t)r * ldx + c] = v + __ldg(W.user_b + c);
     });
     for (int i = tid; i < TM * ldb; i += NT) big[i] = 0.f;
@@ -435,7 +580,7 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       big[(size_t)r * ldb + c] = v;
       A.S.in[(row0 + r) * (1 + d) + c] = v;
     }
-    tile_linear<TM, false>(big, ldb, W.gate_wt, ldd, m, d, 1 + d, stage, [&](int r, int c, float v) {
+    lin<TM, false, RES>(big, ldb, mats[M_GATE], m, d, 1 + d, stage, [&](int r, int c, float v) {
       float g = 0.f;
       if (rpos[r] >= 1) {
         g = 1.f / (1.f + expf(-(v + __ldg(W.gate_b + c))));
@@ -455,7 +600,7 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       const cirs_encoder_layer& Y = W.layer[l];
       const LayerSave& y = A.S.layer[l];
       // ---- qkv = x Win + b
-      tile_linear<TM, false>(xs, ldx, Y.in_wt, ld3, m, 3 * d, d, stage, [&](int r, int c, float v) {
+      lin<TM, false, RES>(xs, ldx, mats[m_in(l)], m, 3 * d, d, stage, [&](int r, int c, float v) {
         v += __ldg(Y.in_b + c);
         big[(size_t)r * ldb + c] = v;
         y.qkv[(row0 + r) * 3 * d + c] = v;
@@ -465,19 +610,19 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       // stage is free between two linears), conflict-free because consecutive threads are consecutive tasks.
       attn_forward<TM>(big, ldb, ys, ldx, stage, rstart, m, d, nh, dh, scale, y.o, row0);
       // ---- r1 = x + o Wout + b;  x1 = LN1(r1)
-      tile_linear<TM, false>(ys, ldx, Y.out_wt, ldd, m, d, d, stage, [&](int r, int c, float v) {
+      lin<TM, false, RES>(ys, ldx, mats[m_out(l)], m, d, d, stage, [&](int r, int c, float v) {
         v += __ldg(Y.out_b + c) + xs[(size_t)r * ldx + c];
         zs[(size_t)r * ldx + c] = v;
         y.r1[(row0 + r) * d + c] = v;
       });
       ln_fwd_rows(zs, ys, ldx, m, d, Y.n1_w, Y.n1_b, y.x1, y.st1, row0);
       // ---- h = relu(x1 W1 + b1);  r2 = x1 + h W2 + b2;  x2 = LN2(r2)
-      tile_linear<TM, false>(ys, ldx, Y.l1_wt, ldh, m, dhid, d, stage, [&](int r, int c, float v) {
+      lin<TM, false, RES>(ys, ldx, mats[m_l1(l)], m, dhid, d, stage, [&](int r, int c, float v) {
         v = fmaxf(v + __ldg(Y.l1_b + c), 0.f);
         big[(size_t)r * ldb + c] = v;
         y.h[(row0 + r) * dhid + c] = v;
       });
-      tile_linear<TM, false>(big, ldb, Y.l2_wt, ldd, m, d, dhid, stage, [&](int r, int c, float v) {
+      lin<TM, false, RES>(big, ldb, mats[m_l2(l)], m, d, dhid, stage, [&](int r, int c, float v) {
         v += __ldg(Y.l2_b + c) + ys[(size_t)r * ldx + c];
         zs[(size_t)r * ldx + c] = v;
         y.r2[(row0 + r) * d + c] = v;
@@ -485,7 +630,7 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       ln_fwd_rows(zs, xs, ldx, m, d, Y.n2_w, Y.n2_b, y.x2, y.st2, row0);
     }
     if (A.obs_check)   // decoded states at their buffer slots (tests)
-      tile_linear<TM, false>(xs, ldx, W.dec_wt, lds, m, S, d, stage, [&](int r, int c, float v) {
+      lin<TM, false, RES>(xs, ldx, mats[M_DEC], m, S, d, stage, [&](int r, int c, float v) {
         A.obs_check[(size_t)A.tok_slot[row0 + r] * S + c] = v + __ldg(W.dec_b + c);
       });
     if (!A.d_obs) { __syncthreads(); continue; }
@@ -496,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       const int r = i / ldb, c = i % ldb;
       big[i] = (r < m && c < S) ? A.d_obs[(size_t)A.tok_slot[row0 + r] * S + c] : 0.f;
     }
-    tile_linear<TM, true>(big, ldb, W.dec_wt, lds, m, d, S, stage,
+    lin<TM, true, RES>(big, ldb, mats[M_DEC], m, d, S, stage,
                           [&](int r, int c, float v) { xs[(size_t)r * ldx + c] = v; });   // xs = da
     for (int l = nl - 1; l >= 0; --l) {
       const cirs_encoder_layer& Y = W.layer[l];
@@ -507,19 +652,19 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       ln_bwd_rows(xs, ys, zs, ldx, m, d, y.st2, row0, Y.n2_w, Gy.n2_w, Gy.n2_b, lnacc, y.dr2);
       // ---- dh = (dR2 W2^T) [h > 0]  -> big;   dx1 = dh W1^T + dR2 -> ys
       for (int i = tid; i < TM * ldb; i += NT) big[i] = 0.f;
-      tile_linear<TM, true>(zs, ldx, Y.l2_wt, ldd, m, dhid, d, stage, [&](int r, int c, float v) {
+      lin<TM, true, RES>(zs, ldx, mats[m_l2(l)], m, dhid, d, stage, [&](int r, int c, float v) {
         if (!(y.h[(row0 + r) * dhid + c] > 0.f)) v = 0.f;
         big[(size_t)r * ldb + c] = v;
         y.dh[(row0 + r) * dhid + c] = v;
       });
-      tile_linear<TM, true>(big, ldb, Y.l1_wt, ldh, m, d, dhid, stage, [&](int r, int c, float v) {
+      lin<TM, true, RES>(big, ldb, mats[m_l1(l)], m, d, dhid, stage, [&](int r, int c, float v) {
         ys[(size_t)r * ldx + c] = v + zs[(size_t)r * ldx + c];
       });
       // ---- LN1: zs = dR1
       load_rows<TM>(xs, ldx, y.r1, row0, m, d, d);
       ln_bwd_rows(ys, xs, zs, ldx, m, d, y.st1, row0, Y.n1_w, Gy.n1_w, Gy.n1_b, lnacc, y.dr1);
       // ---- dO = dR1 Wout^T -> ys
-      tile_linear<TM, true>(zs, ldx, Y.out_wt, ldd, m, d, d, stage,
+      lin<TM, true, RES>(zs, ldx, mats[m_out(l)], m, d, d, stage,
                             [&](int r, int c, float v) { ys[(size_t)r * ldx + c] = v; });
       // ---- attention backward: qkv -> big, dqkv -> big2
       load_rows<TM>(big, ldb, y.qkv, row0, m, 3 * d, 3 * d);
@@ -531,7 +676,7 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
         y.dqkv[(row0 + r) * 3 * d + c] = big2[(size_t)r * ldb + c];
       }
       // ---- dx_in = dqkv Win^T + dR1 -> xs (da of the layer below)
-      tile_linear<TM, true>(big2, ldb, Y.in_wt, ld3, m, d, 3 * d, stage, [&](int r, int c, float v) {
+      lin<TM, true, RES>(big2, ldb, mats[m_in(l)], m, d, 3 * d, stage, [&](int r, int c, float v) {
         xs[(size_t)r * ldx + c] = v + zs[(size_t)r * ldx + c];
       });
     }
@@ -556,23 +701,24 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
     }
     __syncthreads();
     if (G.emb_item)
-      tile_linear<TM, true>(ys, ldx, W.gate_wt, ldd, m, 1 + d, d, stage, [&](int r, int c, float v) {
+      lin<TM, true, RES>(ys, ldx, mats[M_GATE], m, 1 + d, d, stage, [&](int r, int c, float v) {
         if (c >= 1 && rpos[r] >= 1) {
           const int item = A.act[(size_t)renv[r] * L + rpos[r] - 1];
           atomicAdd(G.emb_item + (size_t)item * d + c - 1, v + zs[(size_t)r * ldx + c - 1]);
         }
       });
     if (G.emb_user)
-      tile_linear<TM, true>(xs, ldx, W.user_wt, ldd, m, dui, d, stage, [&](int r, int c, float v) {
+      lin<TM, true, RES>(xs, ldx, mats[M_USER], m, dui, d, stage, [&](int r, int c, float v) {
         if (rpos[r] == 0) atomicAdd(G.emb_user + (size_t)A.users[renv[r]] * d + c, v);
       });
     __syncthreads();
   }
 }
 
-inline size_t chunk_smem_bytes(int TM, int d, int nh, int ldx, int ldb) {
-  return sizeof(float) * ((size_t)3 * TM * ldx + 2 * TM * ldb + WS_K * WS_LD + 3 * TM * nh + 8 * 2 * TM +
-                          2 * ((d + 3) & ~3)) + sizeof(int) * 3 * TM + 64;
+inline size_t chunk_smem_bytes(int TM, int d, int nh, int ldx, int ldb, int resident_fl = -1) {
+  const size_t stage = resident_fl >= 0 ? (size_t)TM * TM * nh : (size_t)WS_K * WS_LD;
+  return sizeof(float) * ((size_t)3 * TM * ldx + 2 * TM * ldb + stage + 3 * TM * nh + 8 * 2 * TM +
+                          2 * ((d + 3) & ~3) + (resident_fl >= 0 ? resident_fl + 4 : 0)) + sizeof(int) * 3 * TM + 64;
 }
 
 // ---- grouped weight-gradient launch: problem i computes gW_i[K_i][ldw_i] += X_i^T dY_i over all M rows (+ bias
