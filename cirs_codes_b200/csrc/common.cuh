@@ -67,4 +67,12 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 // uniform in (0, 1]
 __device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 1) * (1.0f / 16777216.0f); }
 
+// ---- cp.async (LDGSTS): global -> shared without staging registers; completion by commit / wait groups
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

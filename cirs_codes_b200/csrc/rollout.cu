@@ -21,6 +21,7 @@
 #include "head_tc.cuh"
 #include "env_dev.cuh"
 #include "tracker_dev.cuh"
+#include "tracker_cta_dev.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -59,13 +60,108 @@ struct RolloutArgs {
   int w_count;
   int smem_w_off;           // float offset of the staged weights inside dynamic shared memory
   long long* dbg;           // [1 + 3 * max_steps] turns played, then per turn {n_active, ns phase A, ns phase B}
-  int scratch_per_warp;
+  int row_floats;           // per-row scratch of the cooperative token step + 128 floats for the trunk
+  // phase-B staging inside the per-turn shared region (behind the RB rows of scratch; float offsets, -1 = absent):
+  int part_off;             // CTA_RB * 128 floats: partial sums of the split FFN product
+  int trunk_w_off;          // the trunk's weights (w1t | b1 | w2t | b2 | wv | bv), re-fetched every turn with cp.async
+  int kv_off, kv_cap;       // prefetch area for the rows' cached K / V positions and its capacity in floats
   // tensor-core head (actor_tc_dev.cuh): CTA s owns catalogue slice s
   int n_slices;             // ceil(n_action / 80) <= grid
   int tc_keep_off;          // float offset of the launch-lifetime shared-memory region (W3 slice, mbarriers)
   int* tc_timeout;          // set when an mbarrier wait gives up (never expected)
-  int xtra_off;             // float offset, inside a warp's scratch slice, of the group token's extra buffers
 };
+
+// Trunk + critic of R rows by the whole CTA, in the operation order of actor_trunk_warp / actor_head_body (bias first, k
+// ascending, fmaf) so that h2 is bit-identical to the stand-alone kernels'.  The rows' states sit in the token step's
+// scratch at sc[r * stride + state_off]; the last 128 floats of a row's scratch hold h1 | h2.
+// layout of the trunk's weights when staged in shared memory (floats)
+__host__ __device__ inline int trunk_w_floats(int S) { return S * HID + HID + HID * HID + HID + HID + 4; }
+
+__device__ __forceinline__ void trunk_rows(const cirs_policy_weights& W, int R, float* sc, int stride, int state_off,
+                                           const int* row_e, float* __restrict__ h2_out, float* __restrict__ value_out,
+                                           const float* ws = nullptr) {
+  const int S = W.dim_state, tid = threadIdx.x;
+  const int H1 = stride - 128, H2 = stride - 64;
+  // ws: w1t [S][64] | b1 | w2t [64][64] | b2 | wv | bv in shared memory; otherwise the weights come from global memory
+  const float* w1t = ws ? ws : W.w1t;
+  const float* b1 = ws ? ws + S * HID : W.b1;
+  const float* w2t = ws ? b1 + HID : W.w2t;
+  const float* b2 = ws ? w2t + HID * HID : W.b2;
+  const float* wv = ws ? b2 + HID : W.wv;
+  const float* bv = ws ? wv + HID : W.bv;
+  for (int idx = tid; idx < R * HID; idx += NT) {
+    const int r = idx / HID, o = idx % HID;
+    const float* s = sc + (size_t)r * stride + state_off;
+    float a = b1[o];
+    float wv1[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) wv1[k] = k < S ? w1t[(size_t)k * HID + o] : 0.f;   // every load in flight at once
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < S) a = fmaf(s[k], wv1[k], a);
+    sc[(size_t)r * stride + H1 + o] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < R * HID; idx += NT) {
+    const int r = idx / HID, o = idx % HID;
+    const float* h1 = sc + (size_t)r * stride + H1;
+    float a = b2[o];
+#pragma unroll
+    for (int k0 = 0; k0 < HID; k0 += 32) {
+      float w2[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) w2[k] = w2t[(size_t)(k0 + k) * HID + o];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) a = fmaf(h1[k0 + k], w2[k], a);
+    }
+    a = fmaxf(a, 0.f);
+    sc[(size_t)r * stride + H2 + o] = a;
+    h2_out[(size_t)row_e[r] * HID + o] = a;
+  }
+  __syncthreads();
+  if (tid < R && value_out) {
+    const float* h2 = sc + (size_t)tid * stride + H2;
+    float v = bv[0];
+    for (int k = 0; k < HID; ++k) v = fmaf(h2[k], wv[k], v);
+    value_out[row_e[tid]] = v;
+  }
+  __syncthreads();
+}
+
+// cp.async the trunk's weights into shared memory (issued at the start of phase B, consumed at its end)
+__device__ __forceinline__ void prefetch_trunk(const cirs_policy_weights& W, float* ws) {
+  const int S = W.dim_state, tid = threadIdx.x;
+  float* b1 = ws + S * HID;
+  float* w2t = b1 + HID;
+  float* b2 = w2t + HID * HID;
+  float* wv = b2 + HID;
+  float* bv = wv + HID;
+  for (int i = tid; i < S * HID / 4; i += NT) cp_async16(ws + 4 * i, W.w1t + 4 * i);
+  for (int i = tid; i < HID * HID / 4; i += NT) cp_async16(w2t + 4 * i, W.w2t + 4 * i);
+  if (tid < HID / 4) {
+    cp_async16(b1 + 4 * tid, W.b1 + 4 * tid);
+    cp_async16(b2 + 4 * tid, W.b2 + 4 * tid);
+    cp_async16(wv + 4 * tid, W.wv + 4 * tid);
+  }
+  if (tid == 0) bv[0] = __ldg(W.bv);
+}
+
+// cp.async the cached K / V rows (positions 0 .. p-1, every layer) of the R rows into shared memory
+__device__ __forceinline__ void prefetch_kv(const cirs_tracker_weights& W, int n_env, int R, const int* row_e, int p,
+                                            const float* __restrict__ kcache, const float* __restrict__ vcache,
+                                            float* kv_s, int kv_ld) {
+  const int d = W.d, d4 = d >> 2, nl = W.nlayers;
+  const int total = R * nl * 2 * p * d4;
+  for (int i = threadIdx.x; i < total; i += NT) {
+    int x = i;
+    const int c4 = x % d4; x /= d4;
+    const int j = x % p; x /= p;
+    const int which = x & 1; x >>= 1;
+    const int l = x % nl, r = x / nl;
+    const float* src = (which ? vcache : kcache) + (((size_t)l * n_env + row_e[r]) * W.max_len + j) * d + 4 * c4;
+    cp_async16(kv_s + ((size_t)((r * nl + l) * 2 + which) * p + j) * kv_ld + 4 * c4, src);
+  }
+}
 
 // SMW: the tracker's weights are staged once in shared memory (they are re-read by every warp at every turn; from L2
 // each token is ~55 dependent round trips of ~0.6 us, from shared memory ~20x less)
@@ -85,7 +181,6 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
   const int warps_per_cta = NT / 32;
   const int gwarp = blockIdx.x * warps_per_cta + warp, n_warps = gridDim.x * warps_per_cta;
   const int B = A.n_env;
-  float* scratch = smem_dyn + (size_t)warp * A.scratch_per_warp;
   if (tid == 0) { sT = A.T; sH = A.H; }
   __syncthreads();
   if (SMW) {
@@ -113,24 +208,34 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
   }
 
   // ---- reset + user token (position 0); every environment starts in the compact list of turn 0
+  __shared__ int row_e[cirs_tracker::CTA_RB], row_a[cirs_tracker::CTA_RB];
+  __shared__ float row_r[cirs_tracker::CTA_RB];
+  constexpr int RB = cirs_tracker::CTA_RB;
   if (blockIdx.x == 0 && tid == 0) {
     *A.tc_timeout = 0;
     *A.n_active = B;
     A.count[0] = B;
     A.count[1] = 0;
   }
-  for (int e = gwarp; e < B; e += n_warps) {
-    const int u = A.users[e];
-    cirs_env::kuaishou_reset_warp(A.E, e, u, lane, A.active);
-    if (lane == 0) {
-      A.ep_len[e] = 0;
-      A.list[e] = e;
+  for (int j0 = 0; (int)blockIdx.x + j0 * (int)gridDim.x < B; j0 += RB) {
+    const int left = B - ((int)blockIdx.x + j0 * (int)gridDim.x);
+    const int R = min(RB, (left + (int)gridDim.x - 1) / (int)gridDim.x);
+    if (warp < R) {
+      const int e = blockIdx.x + (j0 + warp) * gridDim.x;
+      const int u = A.users[e];
+      cirs_env::kuaishou_reset_warp(A.E, e, u, lane, A.active);
+      if (lane == 0) {
+        A.ep_len[e] = 0;
+        A.list[e] = e;
+        row_e[warp] = e; row_a[warp] = u; row_r[warp] = 0.f;
+      }
     }
-    cirs_tracker::tracker_token_group<SMW>(sT, B, e, 0, u, 0.f, A.kcache, A.vcache, scratch, scratch + A.xtra_off, lane, 0, 1,
-                                           1 + warp, A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next);
-    __syncwarp();
-    actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, scratch, A.h2 + (size_t)e * HID,
-                     A.value + e);
+    __syncthreads();
+    const int off = cirs_tracker::tracker_token_cta<SMW>(sT, B, R, 0, row_e, row_a, row_r, A.kcache, A.vcache, smem_dyn,
+                                                         A.row_floats, A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next,
+                                                         nullptr, nullptr, 0,
+                                                         A.part_off >= 0 ? smem_dyn + A.part_off : nullptr);
+    trunk_rows(A.H.W, R, smem_dyn, A.row_floats, off, row_e, A.h2, A.value);
   }
   __threadfence();
   grid.sync();
@@ -172,57 +277,56 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
     __threadfence();
     grid.sync();
     if (timer) t1 = gtime_ns();
-    // ---- phase B: per running environment -- merge partials -> action, environment step, tracker token, trunk.
-    // One warp per environment while they outnumber the warps; once few are left, G = 2 / 4 / 8 warps share one
-    // environment's tracker token (tracker_token_group) so the dependent chain per turn gets shorter.
+    // ---- phase B: per running environment -- merge partials -> action, environment step (one warp per row), then the
+    // tracker token and the trunk + critic of the new state for all of this CTA's rows together (tracker_cta_dev.cuh).
+    // Row k of the compact list belongs to CTA k % gridDim: at most ceil(n_act / 148) rows per CTA, RB per pass.
     int32_t* list_next = A.list + (size_t)((t + 1) & 1) * B;
-    const int G = n_act * 8 <= n_warps ? 8 : (n_act * 4 <= n_warps ? 4 : (n_act * 2 <= n_warps ? 2 : 1));
-    {
-      const int groups_per_cta = warps_per_cta / G, group = warp / G, wg = warp % G;
-      const int ggroup = blockIdx.x * groups_per_cta + group, n_groups = gridDim.x * groups_per_cta;
-      float* gscr = smem_dyn + (size_t)(group * G) * A.scratch_per_warp;   // the group's first warp's scratch slice
-      float* xtra = gscr + A.xtra_off;                                      // two extra [d] vectors + mailbox
-      int* mail = reinterpret_cast<int*>(xtra + 2 * ((A.T.d + 31) & ~31));  // action, done, reward of this turn
-      const int bar_id = 1 + group, nthr = 32 * G;
-      for (int k = ggroup; k < n_act; k += n_groups) {
-        const int e = H.gather[k];
-        const bool sub = timer && k == 0;
-        long long s0 = 0, s2 = 0;
-        if (sub) s0 = gtime_ns();
-        if (wg == 0) {
-          const int a = actor_combine_warp(H, k, lane, A.act, A.logp);
-          const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len,
-                                                      A.traj_act, A.traj_rew, A.traj_done, A.ep_len, A.force_length,
-                                                      A.n_active);
-          __syncwarp();
-          if (lane == 0) {
-            if (!d) {
-              const int kn = atomicAdd(A.count + ((t + 1) & 1), 1);
-              list_next[kn] = e;
-            }
-            mail[0] = a; mail[1] = d ? 1 : 0;
-            reinterpret_cast<float*>(mail)[2] = A.rew[e];
+    for (int j0 = 0; (int)blockIdx.x + j0 * (int)gridDim.x < n_act; j0 += RB) {
+      const int left = n_act - ((int)blockIdx.x + j0 * (int)gridDim.x);
+      const int R = min(RB, (left + (int)gridDim.x - 1) / (int)gridDim.x);
+      // stage stamps of CTA 0's first pass of the LAST turn played so far: dbg[1 + 3 * 512 ..) = {start, after combine +
+      // env, 18 token stamps, after trunk}
+      long long* tq = (timer || (blockIdx.x == 0)) && j0 == 0 ? A.dbg + 1 + 3 * 512 : nullptr;
+      if (tq && tid == 0) tq[0] = gtime_ns();
+      // this turn's position is t + 1: the cached positions 0 .. t of the rows and the trunk's weights are fetched
+      // into shared memory in the background (cp.async) while the rows' warps merge the head partials and step the
+      // environment; the token step then never waits on L2 for them
+      const int p = t + 1;
+      const int kv_ld = A.T.d + 4;
+      const bool kv_fit = A.kv_off >= 0 && (A.T.d & 3) == 0 &&
+                          (int64_t)R * A.T.nlayers * 2 * p * kv_ld <= (int64_t)A.kv_cap;
+      if (warp < R && lane == 0) row_e[warp] = H.gather[blockIdx.x + (j0 + warp) * gridDim.x];
+      __syncthreads();
+      if (A.trunk_w_off >= 0 && j0 == 0) prefetch_trunk(A.H.W, smem_dyn + A.trunk_w_off);
+      if (kv_fit) prefetch_kv(A.T, B, R, row_e, p, A.kcache, A.vcache, smem_dyn + A.kv_off, kv_ld);
+      cp_async_commit();
+      if (warp < R) {
+        const int k = blockIdx.x + (j0 + warp) * gridDim.x;
+        const int e = row_e[warp];
+        const int a = actor_combine_warp(H, k, lane, A.act, A.logp);
+        const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len,
+                                                    A.traj_act, A.traj_rew, A.traj_done, A.ep_len, A.force_length,
+                                                    A.n_active);
+        __syncwarp();
+        if (lane == 0) {
+          if (!d) {
+            const int kn = atomicAdd(A.count + ((t + 1) & 1), 1);
+            list_next[kn] = e;
           }
-        }
-        cirs_tracker::group_sync(bar_id, nthr);
-        const int a = mail[0];
-        const bool d = mail[1] != 0;
-        const float r = reinterpret_cast<const float*>(mail)[2];
-        if (sub) s2 = gtime_ns();
-        cirs_tracker::tracker_token_group<SMW>(sT, B, e, t + 1, a, r, A.kcache, A.vcache, gscr, xtra, lane, wg, G, bar_id,
-                                               A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next,
-                                               sub ? A.dbg + 1 + 6 * 512 - 16 : nullptr);
-        if (wg == 0 && !d) {   // trunk + critic of the new state, consumed by the next turn's head phase
-          __syncwarp();
-          actor_trunk_warp(A.H.W, A.cur_state + (size_t)e * A.T.dim_state, lane, gscr, A.h2 + (size_t)e * HID,
-                           A.value + e);
-        }
-        cirs_tracker::group_sync(bar_id, nthr);   // scratch and mail are reused by the group's next environment
-        if (sub) {
-          long long* q = A.dbg + 1 + 3 * 512 + 3 * t;
-          q[0] = A.dbg[1 + 6 * 512 - 16 + 10] - s2; q[1] = s2 - s0; q[2] = gtime_ns() - s2;   // token, combine+env, token+trunk
+          row_e[warp] = e; row_a[warp] = a; row_r[warp] = A.rew[e];
         }
       }
+      cp_async_wait_all();
+      __syncthreads();
+      if (tq && tid == 0) tq[1] = gtime_ns();
+      const int off = cirs_tracker::tracker_token_cta<SMW>(sT, B, R, p, row_e, row_a, row_r, A.kcache, A.vcache,
+                                                           smem_dyn, A.row_floats, A.cur_state, A.traj_len, A.traj_obs,
+                                                           A.traj_obs_next, tq ? tq + 2 : nullptr,
+                                                           kv_fit ? smem_dyn + A.kv_off : nullptr, kv_ld,
+                                                           A.part_off >= 0 ? smem_dyn + A.part_off : nullptr);
+      trunk_rows(A.H.W, R, smem_dyn, A.row_floats, off, row_e, A.h2, A.value,
+                 A.trunk_w_off >= 0 ? smem_dyn + A.trunk_w_off : nullptr);   // consumed by the next turn's head phase
+      if (tq && tid == 0) tq[22] = gtime_ns();
     }
     if (blockIdx.x == 0 && tid == 0) {
       A.count[t & 1] = 0;   // consumed; it becomes the append counter of turn t + 1's phase B
@@ -298,10 +402,9 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     return CIRS_ERR_ARG;
   }
   if (env->n_env <= 0) return CIRS_OK;
-  // per-warp scratch: the token step's buffers + two extra [d] vectors and a small mailbox (tracker_token_group)
-  const int xtra_off = cirs_tracker::tracker_scratch_floats(*tw);
-  const int per_warp = xtra_off + 2 * ((tw->d + 31) & ~31) + 32;
-  const size_t scratch_bytes = (size_t)per_warp * (NT / 32) * sizeof(float);
+  // scratch of the cooperative token step: CTA_RB rows x (token buffers + 128 floats for the trunk's h1 | h2)
+  const int row_floats = cirs_tracker::cta_row_floats(*tw) + 128;
+  const size_t scratch_bytes = (size_t)row_floats * cirs_tracker::CTA_RB * sizeof(float);
   constexpr size_t SMEM_MAX = 224 * 1024;
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
   RolloutArgs A{};
@@ -338,6 +441,16 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     smw = smw_ok && head + (size_t)w_count * sizeof(float) <= SMEM_MAX;
     smem = head;
     A.tc_keep_off = (int)(keep_off / sizeof(float));
+    {   // phase-B staging behind the rows' scratch, inside the per-turn region [0, keep_off)
+      size_t off = up128(scratch_bytes);
+      const size_t part_bytes = (size_t)cirs_tracker::CTA_RB * 128 * sizeof(float);
+      const size_t tw_bytes = up128((size_t)trunk_w_floats(pw->dim_state) * sizeof(float));
+      A.part_off = A.trunk_w_off = A.kv_off = -1;
+      A.kv_cap = 0;
+      if (off + part_bytes <= keep_off) { A.part_off = (int)(off / sizeof(float)); off += part_bytes; }
+      if (off + tw_bytes <= keep_off && (pw->dim_state * HID) % 4 == 0) { A.trunk_w_off = (int)(off / sizeof(float)); off += tw_bytes; }
+      if (off + 4096 <= keep_off) { A.kv_off = (int)(off / sizeof(float)); A.kv_cap = (int)((keep_off - off) / sizeof(float)); }
+    }
     if (smw) {
       A.w_lo = w_lo; A.w_count = (int)w_count; A.smem_w_off = (int)(smem / sizeof(float));
       smem += (size_t)w_count * sizeof(float);
@@ -398,8 +511,7 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.users = users; A.active = active; A.act = act; A.logp = logp; A.value = value; A.cur_state = cur_state;
   A.rew = rew; A.done = done; A.traj_obs = traj_obs; A.traj_obs_next = traj_obs_next; A.traj_act = traj_act;
   A.traj_rew = traj_rew; A.traj_done = traj_done; A.ep_len = ep_len; A.kcache = kcache; A.vcache = vcache;
-  A.scratch_per_warp = per_warp;
-  A.xtra_off = xtra_off;
+  A.row_floats = row_floats;
   void* params[] = {&A};
   const bool prof = cirs_profile_begin("rollout_kuaishou_kernel", (cudaStream_t)stream);
   void* fn = tc ? (smw ? (void*)rollout_kuaishou_kernel<true, true> : (void*)rollout_kuaishou_kernel<false, true>)

@@ -46,7 +46,9 @@ col.persistent = True
 r = col.collect(n_episode=B, users=rng.integers(0, cfg["U"], size=B))
 dbg = col._f["ws_roll"][256:256 + 8 * (1 + 6 * 512)].view(torch.int64).cpu().numpy()
 nt = int(dbg[0]); print("persistent turns", nt, "lens max", r["turns"])
-for t in range(nt): print(f"  turn {t:2d} n_act {dbg[1+3*t]:5d}  phaseA {dbg[2+3*t]/1e3:7.1f} us  phaseB {dbg[3+3*t]/1e3:7.1f} us   env0: combine {dbg[1+1536+3*t]/1e3:5.1f} env {dbg[2+1536+3*t]/1e3:5.1f} tracker {dbg[3+1536+3*t]/1e3:5.1f}")
-
-tq = dbg[1 + 6 * 512 - 16: 1 + 6 * 512 - 16 + 11]
-print("group-mode token stamps of the LAST turn (us since start):", [(int(x - tq[0]) / 1e3) for x in tq])
+for t in range(nt): print(f"  turn {t:2d} n_act {dbg[1+3*t]:5d}  phaseA {dbg[2+3*t]/1e3:7.1f} us  phaseB {dbg[3+3*t]/1e3:7.1f} us")
+tq = dbg[1 + 3 * 512: 1 + 3 * 512 + 23]
+names = ["combine+env", "tok-in"] + [f"L{l}:{n}" for l in range(2) for n in ("inproj", "attn", "outproj", "ln1", "l1", "l2", "ln2")] + ["dec", "store", "trunk"]
+print("phase-B stage times of CTA 0, last turn (us):")
+for i in range(1, 21): print(f"   {names[i-1] if i-1 < len(names) else i}: {(tq[i]-tq[i-1])/1e3:.2f}")
+print(f"   trunk: {(tq[22]-tq[21])/1e3:.2f}   total {(tq[22]-tq[0])/1e3:.2f}")
