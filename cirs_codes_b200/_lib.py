@@ -121,7 +121,7 @@ PROTOTYPES = {
     "cirs_ppo_minibatch": (i32, [P(PolicyWeightsStruct), P(PolicyWeightsStruct), P(PPOConfigStruct), i32, i32, fp,
                                  fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp]),
     "cirs_ppo_learn": (i32, [P(PolicyWeightsStruct), P(PolicyWeightsStruct), fp, fp, P(PPOConfigStruct), i32, i32,
-                             fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp, fp, fp]),
+                             fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp, fp, i32, fp]),
     "cirs_update_plan": (i32, [i32, i32, fp, fp, fp, fp]),
     "cirs_gather_i32": (i32, [fp, fp, fp, i32, fp]),
     "cirs_coverage_count": (i32, [i32, fp, fp, i32, fp, fp, fp, fp]),
@@ -129,6 +129,8 @@ PROTOTYPES = {
     "cirs_comm_create": (i32, [fp, i32, i32, P(fp)]),
     "cirs_comm_destroy": (i32, [fp]),
     "cirs_comm_allreduce": (i32, [fp, fp, i64, i32, fp]),
+    "cirs_comm_group_begin": (i32, [fp]),
+    "cirs_comm_group_end": (i32, [fp]),
     "cirs_head_tc_enable": (None, [i32]),
     "cirs_head_tc_timeout": (i32, []),
     "cirs_head_tc_timeout_peek": (i32, [fp, fp]),

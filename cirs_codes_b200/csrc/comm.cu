@@ -26,6 +26,8 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 Nccl g_nccl;
@@ -46,7 +48,10 @@ bool nccl_load() {
   *(void**)&n.CommDestroy = dlsym(h, "ncclCommDestroy");
   *(void**)&n.AllReduce = dlsym(h, "ncclAllReduce");
   *(void**)&n.GetErrorString = dlsym(h, "ncclGetErrorString");
-  if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllReduce || !n.GetErrorString) {
+  *(void**)&n.GroupStart = dlsym(h, "ncclGroupStart");
+  *(void**)&n.GroupEnd = dlsym(h, "ncclGroupEnd");
+  if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllReduce || !n.GetErrorString || !n.GroupStart ||
+      !n.GroupEnd) {
     cirs_set_error("cirs_comm: libnccl.so.2 lacks an expected symbol");
     return false;
   }
@@ -121,6 +126,18 @@ extern "C" int cirs_comm_destroy(void* comm) {
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
   delete c;
   return CIRS_OK;
+}
+
+// all-reduces issued between begin and end travel as ONE fused NCCL operation (ncclGroupStart / ncclGroupEnd)
+extern "C" int cirs_comm_group_begin(void* comm) {
+  if (!comm) return CIRS_OK;
+  ncclResult_t r = g_nccl.GroupStart();
+  return r ? nccl_fail("ncclGroupStart", r) : CIRS_OK;
+}
+extern "C" int cirs_comm_group_end(void* comm) {
+  if (!comm) return CIRS_OK;
+  ncclResult_t r = g_nccl.GroupEnd();
+  return r ? nccl_fail("ncclGroupEnd", r) : CIRS_OK;
 }
 
 extern "C" int cirs_comm_allreduce(void* comm, void* buf, int64_t count, int32_t dtype, void* stream) {

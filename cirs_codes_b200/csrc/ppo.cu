@@ -755,7 +755,7 @@ extern "C" int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_we
                               const void* act, const float* adv, const float* returns, const float* v_old,
                               const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats,
                               float* losses, int32_t* opt_state, double* opt_scratch, void* workspace, void* comm,
-                              const int32_t* n_global_h, void* stream) {
+                              const int32_t* n_global_h, int32_t n_stats_tail, void* stream) {
   if (!w || !grads || !exp_avg || !exp_avg_sq || !cfg || !mb_off_h || !mb_off || !slots || !adv_stats || !losses ||
       !opt_state || !opt_scratch || n_repeat < 0 || n_mb < 0 || (comm && !n_global_h)) {
     cirs_set_error("cirs_ppo_learn: bad argument");
@@ -768,7 +768,9 @@ extern "C" int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_we
     if (rc) return rc;
   }
   if (comm) {
-    int rc = cirs_comm_allreduce_impl(comm, adv_stats, (int64_t)n_repeat * n_mb * 3, 1, st);
+    // n_stats_tail more doubles behind the statistics ride on the same collective (the raw return moments)
+    int rc = cirs_comm_allreduce_impl(comm, adv_stats, (int64_t)n_repeat * n_mb * 3 + (n_stats_tail > 0 ? n_stats_tail : 0),
+                                      1, st);
     if (rc) return rc;
   }
   for (int r = 0; r < n_repeat; ++r) {

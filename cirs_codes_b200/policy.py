@@ -469,7 +469,10 @@ class PPOPolicy:
             # the counts travelled with the collect's read-back (post_collect): no collective, no host sync here
             self._n_all = pin[0].numpy().astype(np.int64)
             if self._rew_norm:
-                self._allreduce(self._moments)
+                if self.c_loop and self._comm() is not None:
+                    self._defer_moments = True      # they ride on learn()'s advantage-statistics all-reduce
+                else:
+                    self._allreduce(self._moments)
         elif world > 1:
             # ONE collective: the raw return moments and, in slot 3 + rank, this rank's transition count; the counts
             # give every rank the whole minibatch plan of this update (parallel.plan_from_counts)
@@ -483,7 +486,7 @@ class PPOPolicy:
                 self._moments.copy_(m[:3])
             self._n_all = m[3:].round().to(torch.int64).cpu().numpy()
         self._n_all_pin = None
-        if self._rew_norm:
+        if self._rew_norm and not getattr(self, "_defer_moments", False):
             _lib.call("cirs_rms_update", _lib.ptr(self.ret_rms.t), _lib.ptr(self._moments), st)
 
     def update(self, sample_size, buffer, batch_size=None, repeat=1, perms=None, mb_sizes=None, **kwargs):
@@ -529,7 +532,7 @@ class PPOPolicy:
         if getattr(self, "_learn_cap", (0, 0)) < (repeat * buffer.maxsize, repeat * (n_mb + 1)):
             self._learn_cap = (repeat * buffer.maxsize, repeat * (n_mb + 1))
             self._slots = torch.zeros(repeat * buffer.maxsize, dtype=torch.int32, device=dev)
-            self._stats = torch.zeros(repeat * (n_mb + 1) * 3, dtype=torch.float64, device=dev)
+            self._stats = torch.zeros(repeat * (n_mb + 1) * 3 + 3, dtype=torch.float64, device=dev)
             self._losses = torch.zeros(repeat * (n_mb + 1) * 4, dtype=torch.float32, device=dev)
         d_slots, stats, losses = self._slots[:repeat * n], self._stats[:repeat * n_mb * 3], \
             self._losses[:repeat * n_mb * 4]
@@ -550,17 +553,24 @@ class PPOPolicy:
         if self.c_loop and (world == 1 or comm is not None):
             # the whole repeat x minibatch loop is ONE C call (csrc/ppo.cu cirs_ppo_learn); with a communicator the
             # gradient all-reduce of every minibatch is issued from C between its kernels and clip + Adam
-            n_glob = None
+            n_glob, tail = None, 0
             if world > 1:
                 assert n_glob_plan is not None
                 n_glob = np.ascontiguousarray(n_glob_plan, dtype=np.int32)
+                if getattr(self, "_defer_moments", False):   # return moments behind the statistics: one collective
+                    tail = 3
+                    self._stats[repeat * n_mb * 3:repeat * n_mb * 3 + 3].copy_(self._moments)
             _lib.call("cirs_ppo_learn", C.byref(self._w), C.byref(self._g), _lib.ptr(self.exp_avg),
                       _lib.ptr(self.exp_avg_sq), C.byref(self.cfg), repeat, n_mb, offs.ctypes.data, _lib.ptr(d_offs),
                       _lib.ptr(d_slots), _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act), _lib.ptr(self.adv),
                       _lib.ptr(self.returns), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(stats),
                       _lib.ptr(d_obs), d_obs.numel() if d_obs is not None else 0, _lib.ptr(losses),
                       _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), _lib.ptr(ws), comm,
-                      n_glob.ctypes.data if n_glob is not None else None, st)
+                      n_glob.ctypes.data if n_glob is not None else None, tail, st)
+            if tail:
+                self._moments.copy_(self._stats[repeat * n_mb * 3:repeat * n_mb * 3 + 3])
+                _lib.call("cirs_rms_update", _lib.ptr(self.ret_rms.t), _lib.ptr(self._moments), st)
+                self._defer_moments = False
         else:
             # CPU-side process group (gloo; tests): per-minibatch entry points with torch.distributed collectives.
             # advantage moments of every minibatch of every repeat (they depend on the permutations only): ONE collective
@@ -587,9 +597,15 @@ class PPOPolicy:
         if tracker is not None:
             tracker.zero_grad()
             tracker.backward_from_buffer(buffer, self.d_obs, getattr(buffer, "d_users", None), tok_slot=indices)
+            if comm is not None:       # tracker gradient + losses: one fused NCCL operation
+                _lib.call("cirs_comm_group_begin", comm)
             self._allreduce(tracker.grad)
+            self._allreduce(losses)
+            if comm is not None:
+                _lib.call("cirs_comm_group_end", comm)
             tracker.optim_step(self.cfg_tracker)                                     # optim_state.step(), :235
-        self._allreduce(losses)
+        else:
+            self._allreduce(losses)
         if getattr(self, "_tc_flag", None) is None:
             self._tc_flag = torch.zeros(1, dtype=torch.int32).pin_memory()
         _lib.call("cirs_head_tc_timeout_peek", self._tc_flag.data_ptr(), st)

@@ -408,14 +408,16 @@ int cirs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_s
  * Data parallel: comm != NULL (cirs_comm_create) -> this rank holds ITS chunk of every global minibatch;
  * the advantage moments are summed over ranks once, the flat gradient once per minibatch (stream-ordered
  * all-reduces between the minibatch kernels and clip + Adam); n_global_h[n_mb] (HOST) = rows of each global
- * minibatch, over which the losses are averaged.  comm == NULL: single process, n_global_h may be NULL. */
+ * minibatch, over which the losses are averaged.  comm == NULL: single process, n_global_h may be NULL.
+ * n_stats_tail: that many further doubles stored right behind adv_stats are summed over ranks by the same collective
+ * (this repo: the raw return moments of cirs_compute_returns, so that they cost no collective of their own). */
 int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grads, float* exp_avg,
                    float* exp_avg_sq, const cirs_ppo_config* cfg, int32_t n_repeat, int32_t n_mb,
                    const int32_t* mb_off_h, const int32_t* mb_off, const int32_t* slots, const float* obs,
                    const void* act, const float* adv, const float* returns, const float* v_old,
                    const float* logp_old, double* adv_stats, float* d_obs, int64_t d_obs_floats, float* losses,
                    int32_t* opt_state, double* opt_scratch, void* workspace, void* comm, const int32_t* n_global_h,
-                   void* stream);
+                   int32_t n_stats_tail, void* stream);
 
 /* Front end of the update on the device (no host round trip between the rollout and the update):
  * cirs_update_plan = VectorReplayBuffer.sample_index(0) (tianshou/data/buffer/manager.py:144-169) for buffers the
@@ -446,6 +448,9 @@ int cirs_comm_unique_id(void* id128_h);
 int cirs_comm_create(const void* id128_h, int32_t rank, int32_t world, void** comm_out);
 int cirs_comm_destroy(void* comm);
 int cirs_comm_allreduce(void* comm, void* buf, int64_t count, int32_t dtype, void* stream);
+/* All-reduces issued between group_begin and group_end travel as one fused NCCL operation. */
+int cirs_comm_group_begin(void* comm);
+int cirs_comm_group_end(void* comm);
 
 /* ------------------------------------------------------------------ user model -> normed_mat ------------ */
 /* The DeepFM user model of stage 1 (UserModel_Pairwise, core/user_model_pairwise.py:36-132) with the feature columns
