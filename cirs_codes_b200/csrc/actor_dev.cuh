@@ -39,6 +39,8 @@ struct HeadArgs {
   int tiles_per_split, n_split;
   Partial* part;          // [n_split, n_rows]
   float* value;
+  int icdf;               // MODE_SAMPLE without the per-element race: the partials carry (m, z) only and the caller
+                          // samples by inverse CDF (actor_combine_icdf_warp; the persistent rollout)
 };
 
 __device__ __forceinline__ void merge_ms(float& m, float& z, float m2, float z2) {
@@ -202,7 +204,7 @@ __device__ __forceinline__ void actor_head_body(const HeadArgs& P, int bx, int b
         uint32_t seen_bits = 0u;
         if (P.seen) seen_bits = P.seen[(size_t)rid[i] * seen_words + (nb >> 5)] >> (nb & 31);
         float g[4] = {0.f, 0.f, 0.f, 0.f};
-        if (P.mode == MODE_SAMPLE) {
+        if (P.mode == MODE_SAMPLE && !P.icdf) {
           if (P.noise_q) {
             const float* q = P.noise_q + (size_t)(r0 + ty * TM + i) * nA + nb;
 #pragma unroll
@@ -354,6 +356,159 @@ __device__ __forceinline__ int actor_combine_warp(const HeadArgs& P, int k, int 
     }
   }
   return bi;
+}
+
+// Categorical.sample by INVERSE CDF over the catalogue-split partials (the persistent rollout's sampler).
+// The exponential race needs one Exp(1) draw per (row, item): 5.5 M Philox + log evaluations per turn at 512 rows, which
+// was 60 % of the head phase.  Inverse CDF needs ONE uniform per row: with M = max_s m_s and Z = sum_s z_s e^{m_s - M}
+// (the softmax denominator) draw target = u Z, walk the splits in catalogue order to the one that contains the target,
+// recompute that split's `width` logits from h2 (64 x width FMAs by one warp, W3 from L2) and walk its columns.  The
+// result is distributed exactly as softmax(logits) (up to float rounding of the partial sums; a target that lands
+// beyond the recomputed columns by rounding takes the last unmasked one).  Masked items (seen) are excluded in both
+// passes.  All 32 lanes call it; every lane returns the action.  h2: the row's trunk output (64 floats, global).
+// (__noinline__: called once per row and turn; keeps its ~100 registers of load batches out of the persistent kernel's
+// own allocation, which sits at the 255-register limit)
+template <int MAXC>   // columns per lane of the recomputed split: split_width <= 32 * MAXC
+__device__ __noinline__ int actor_combine_icdf_warp(const HeadArgs& P, int k, int lane, int32_t* __restrict__ act,
+                                                       float* __restrict__ logp, const float* h2, int split_width,
+                                                       uint64_t offset) {
+  const int id = P.gather ? P.gather[k] : k;
+  const int nA = P.W.n_action;
+  constexpr int MAXS = 8;   // splits per lane: n_split <= 256
+  float ms[MAXS], zs[MAXS];
+  float M = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXS; ++i) {
+    const int s = lane + 32 * i;
+    ms[i] = -INFINITY; zs[i] = 0.f;
+    if (s < P.n_split) {
+      const Partial p = P.part[(size_t)s * P.n_rows + k];
+      ms[i] = p.m; zs[i] = p.z;
+      M = fmaxf(M, p.m);
+    }
+  }
+  M = warp_max(M);
+  float Z = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXS; ++i) {
+    zs[i] = (ms[i] == -INFINITY) ? 0.f : zs[i] * __expf(ms[i] - M);
+    Z += zs[i];
+  }
+  Z = warp_sum(Z);
+  // one uniform in (0, 1) per (row, turn)
+  const uint4 rnd = philox4x32(make_uint4((uint32_t)id, 0x1cdfu, (uint32_t)offset, (uint32_t)(offset >> 32)),
+                               make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+  const float u = ((rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float target = u * Z;
+  // split containing the target: inclusive prefix sums in split order (lane-strided ownership: round i covers 32 splits)
+  float carry = 0.f, before = 0.f;
+  int s_star = -1;
+#pragma unroll
+  for (int i = 0; i < MAXS; ++i) {
+    if (32 * i >= P.n_split) break;
+    float v = zs[i];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(FULL_MASK, v, o);
+      if (lane >= o) v += t;
+    }
+    const float incl = carry + v;
+    const unsigned hit = __ballot_sync(FULL_MASK, s_star < 0 && zs[i] > 0.f && incl >= target);
+    if (s_star < 0 && hit) {
+      const int l = __ffs(hit) - 1;
+      s_star = 32 * i + l;
+      before = __shfl_sync(FULL_MASK, incl - zs[i], l);
+    }
+    carry = __shfl_sync(FULL_MASK, incl, 31);
+  }
+  if (s_star < 0) {   // rounding: the target is a hair above the total -> last split with mass
+    for (int i = MAXS - 1; i >= 0 && s_star < 0; --i) {
+      const unsigned any = __ballot_sync(FULL_MASK, zs[i] > 0.f);
+      if (any) { const int l = 31 - __clz(any); s_star = 32 * i + l; before = carry - __shfl_sync(FULL_MASK, zs[i], l); }
+    }
+    if (s_star < 0) s_star = 0;
+  }
+  const float resid = target - before;
+  // recompute the split's logits: lane owns columns c0 + lane + 32 j
+  const int c0 = s_star * split_width;
+  float e[MAXC], lg[MAXC];
+  const int seen_words = (nA + 31) >> 5;
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) { e[j] = 0.f; lg[j] = -INFINITY; }
+  {
+    float acc[MAXC];
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) acc[j] = 0.f;
+    const int ldA = P.W.ld_action;
+    const float h_lo = h2[lane], h_hi = h2[lane + 32];   // the row's trunk output: two values per lane, shuffled out below
+    bool okc[MAXC];
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) okc[j] = lane + 32 * j < split_width && c0 + lane + 32 * j < ldA;
+    const float* wbase = P.W.w3t + c0 + lane;
+    constexpr int KB = MAXC <= 3 ? 16 : 4;   // KB x MAXC loads in flight per batch (W3 is L2 resident)
+#pragma unroll
+    for (int k0 = 0; k0 < HID; k0 += KB) {
+      float wv[KB][MAXC];
+#pragma unroll
+      for (int u = 0; u < KB; ++u)
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) wv[u][j] = okc[j] ? __ldg(wbase + (size_t)(k0 + u) * ldA + 32 * j) : 0.f;
+#pragma unroll
+      for (int u = 0; u < KB; ++u) {
+        const float hv = __shfl_sync(FULL_MASK, (k0 + u) < 32 ? h_lo : h_hi, (k0 + u) & 31);
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) acc[j] = fmaf(hv, wv[u][j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int c = c0 + lane + 32 * j;
+      if (lane + 32 * j < split_width && c < nA) {
+        bool ok = true;
+        if (P.seen) ok = !((P.seen[(size_t)id * seen_words + (c >> 5)] >> (c & 31)) & 1u);
+        if (ok) { lg[j] = acc[j] + __ldg(P.W.b3 + c); e[j] = __expf(lg[j] - M); }
+      }
+    }
+  }
+  // column containing the residual target, in column order (round j covers columns c0 + 32 j .. + 31)
+  int a = -1;
+  float la = 0.f;
+  carry = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    if (32 * j >= split_width) break;
+    float v = e[j];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(FULL_MASK, v, o);
+      if (lane >= o) v += t;
+    }
+    const float incl = carry + v;
+    const unsigned hit = __ballot_sync(FULL_MASK, a < 0 && e[j] > 0.f && incl >= resid);
+    if (a < 0 && hit) {
+      const int l = __ffs(hit) - 1;
+      a = c0 + 32 * j + l;
+      la = __shfl_sync(FULL_MASK, lg[j], l);
+    }
+    carry = __shfl_sync(FULL_MASK, incl, 31);
+  }
+  if (a < 0) {   // rounding (FFMA vs 3xTF32 sums): the last unmasked column of the split
+    for (int j = MAXC - 1; j >= 0 && a < 0; --j) {
+      const unsigned any = __ballot_sync(FULL_MASK, e[j] > 0.f);
+      if (any) { const int l = 31 - __clz(any); a = c0 + 32 * j + l; la = __shfl_sync(FULL_MASK, lg[j], l); }
+    }
+    if (a < 0) { a = min(c0, nA - 1); la = M; }
+  }
+  if (lane == 0) {
+    const int o = P.out_by_k ? k : id;
+    if (act) act[o] = a;
+    if (logp) {
+      float pa = expf(la - M) / Z;
+      pa = fminf(fmaxf(pa, CATEGORICAL_EPS), 1.0f - CATEGORICAL_EPS);
+      logp[o] = logf(pa);
+    }
+  }
+  return a;
 }
 
 inline int pick_split(int n_rows, int n_action, int target_ctas = 2 * 148) {

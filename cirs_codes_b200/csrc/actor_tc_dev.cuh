@@ -83,7 +83,12 @@ struct SrcRows {   // gathered h2 rows of one 128-row tile of the compact row li
 // One turn's actor-head partials for this CTA's slice.  P: n_rows / gather (compact list of running environments),
 // h2_in, part (n_split == number of slices), mode, seed, offset, rng_counter.  Every thread of the CTA calls it.
 __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const TcSmem& S, int tid, TcState& st,
-                                             int* timeout_flag) {
+                                             int* timeout_flag, long long* tq = nullptr) {
+  // tq (optional, one CTA): %globaltimer stamps {entry, h2 tile staged, first MMA done, epilogue done, partials written}
+  auto stamp = [&](int i) {
+    if (tq && tid == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); tq[i] = t_; }
+  };
+  stamp(0);
   const int warp = tid >> 5, row = tid & 127, half = tid >> 7;
   const bool warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;   // warp-uniform: the MMAs are issued under elect.sync (tc_dev.cuh)
   const int n_rt = (P.n_rows + ROWS - 1) / ROWS;
@@ -107,6 +112,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
   __syncthreads();
   fence_after_sync();
   if (warp0) issue(0);
+  stamp(1);
   if (n_rt > 1) ta.load(tid, SrcRows{P.h2_in, P.gather, ROWS, P.n_rows});
   for (int rt = 0; rt < n_rt; ++rt) {
     const int b = rt & 1;
@@ -114,6 +120,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
     if (!mbar_wait(&S.bar[b], use & 1u)) *timeout_flag = 1;
     ++use;
     fence_after_sync();
+    if (rt == 0) stamp(2);
     if (rt + 1 < n_rt) {   // the h2 tile is free again: next row tile's MMA runs behind this tile's epilogue
       ta.store(S.a_hi, S.a_lo, tid);
       fence_async_smem();
@@ -148,7 +155,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
         const int nb = cbase + ch * 8 + 4 * q4;
         if (nb >= nA) continue;
         float qn[4] = {1.f, 1.f, 1.f, 1.f};
-        if (P.mode == MODE_SAMPLE) {
+        if (P.mode == MODE_SAMPLE && !P.icdf) {
           const uint4 rnd = philox4x32(make_uint4((uint32_t)rid, (uint32_t)(nb >> 2), (uint32_t)offset,
                                                   (uint32_t)(offset >> 32)),
                                        make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
@@ -186,6 +193,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
       }
     }
     float bs = bi == 0x7fffffff ? -INFINITY : bl - logf(q_best);
+    if (rt == 0) stamp(3);
     S.red[tid] = m; S.red[NT + tid] = z; S.red[2 * NT + tid] = bs; S.red[3 * NT + tid] = bl;
     S.red[4 * NT + tid] = __int_as_float(bi);
     fence_before_sync();
@@ -199,6 +207,7 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
       P.part[(size_t)slice * P.n_rows + k] = p;
     }
     __syncthreads();   // red is reused by the next row tile
+    if (rt == 0) stamp(4);
   }
 }
 

@@ -250,23 +250,33 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
     long long t0 = 0, t1 = 0;
     if (timer) t0 = gtime_ns();
     const int row_tiles = (n_act + BM - 1) / BM;
+    // the sampler's Philox offset of this turn (block 0 bumps the counter at the end of the turn, behind a grid barrier)
+    const uint64_t turn_off = A.H.offset + (A.H.rng_counter ? (uint64_t)*A.H.rng_counter : 0ull);
     if (tid == 0) {   // this turn's head plan (shared by the CTA)
       sH.n_rows = n_act;
       sH.gather = A.list + (size_t)(t & 1) * B;
       if (TC) {
         sH.n_split = A.n_slices;
+        // inverse-CDF sampling in phase B (no per-element race in the epilogue) once the head phase walks five or more
+        // 128-row tiles: measured on B200 the epilogue drops from 8.1 to 3.5 us per tile while the per-row split
+        // recompute adds ~7 us to phase B, so it pays from ~5 tiles (configs[2]: 32 tiles per turn, rollout 1.99 ->
+        // 1.70 ms; configs[1] with its 4 tiles keeps the race)
+        sH.icdf = sH.mode == MODE_SAMPLE && (n_act + cirs_actor_tc::ROWS - 1) / cirs_actor_tc::ROWS >= 5;
       } else {
         int n_split = gridDim.x / row_tiles;
         n_split = n_split < 1 ? 1 : (n_split > n_col_tiles ? n_col_tiles : n_split);
         sH.tiles_per_split = (n_col_tiles + n_split - 1) / n_split;
         sH.n_split = (n_col_tiles + sH.tiles_per_split - 1) / sH.tiles_per_split;
+        sH.icdf = sH.mode == MODE_SAMPLE && sH.tiles_per_split * BN <= 256 && sH.n_split <= 256 && row_tiles >= 10;
       }
     }
     __syncthreads();
     const HeadArgs& H = sH;
     // ---- phase A: actor head partials over the compact rows
     if (TC) {
-      if ((int)blockIdx.x < A.n_slices) cirs_actor_tc::tc_head_turn(H, blockIdx.x, TS, tid, tst, A.tc_timeout);
+      if ((int)blockIdx.x < A.n_slices)
+        cirs_actor_tc::tc_head_turn(H, blockIdx.x, TS, tid, tst, A.tc_timeout,
+                                    blockIdx.x == 0 ? A.dbg + 1 + 3 * 512 + 32 : nullptr);
     } else {
       const int n_items = row_tiles * H.n_split;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
     }
     __threadfence();
     grid.sync();
-    if (timer) t1 = gtime_ns();
+    if (timer) { t1 = gtime_ns(); A.dbg[1 + 3 * 512 + 32 + 5] = t1; A.dbg[1 + 3 * 512 + 32 + 6] = t0; }
     // ---- phase B: per running environment -- merge partials -> action, environment step (one warp per row), then the
     // tracker token and the trunk + critic of the new state for all of this CTA's rows together (tracker_cta_dev.cuh).
     // Row k of the compact list belongs to CTA k % gridDim: at most ceil(n_act / 148) rows per CTA, RB per pass.
@@ -303,7 +313,13 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       if (warp < R) {
         const int k = blockIdx.x + (j0 + warp) * gridDim.x;
         const int e = row_e[warp];
-        const int a = actor_combine_warp(H, k, lane, A.act, A.logp);
+        int a;
+        if (!H.icdf) a = actor_combine_warp(H, k, lane, A.act, A.logp);
+        else if (TC) a = actor_combine_icdf_warp<(cirs_actor_tc::SLICE + 31) / 32>(H, k, lane, A.act, A.logp,
+                                                                                   A.h2 + (size_t)e * HID,
+                                                                                   cirs_actor_tc::SLICE, turn_off);
+        else a = actor_combine_icdf_warp<8>(H, k, lane, A.act, A.logp, A.h2 + (size_t)e * HID,
+                                            H.tiles_per_split * BN, turn_off);
         const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len,
                                                     A.traj_act, A.traj_rew, A.traj_done, A.ep_len, A.force_length,
                                                     A.n_active);

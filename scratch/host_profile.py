@@ -52,3 +52,7 @@ names = ["combine+env", "tok-in"] + [f"L{l}:{n}" for l in range(2) for n in ("in
 print("phase-B stage times of CTA 0, last turn (us):")
 for i in range(1, 21): print(f"   {names[i-1] if i-1 < len(names) else i}: {(tq[i]-tq[i-1])/1e3:.2f}")
 print(f"   trunk: {(tq[22]-tq[21])/1e3:.2f}   total {(tq[22]-tq[0])/1e3:.2f}")
+
+ta = dbg[1 + 3 * 512 + 32: 1 + 3 * 512 + 32 + 7]
+print("phase-A stamps of CTA 0, last turn (us): turn start -> entry %.2f, stage h2 tile %.2f, MMA %.2f, epilogue %.2f, merge+partials %.2f, fence+grid.sync %.2f" % (
+    (ta[0]-ta[6])/1e3, (ta[1]-ta[0])/1e3, (ta[2]-ta[1])/1e3, (ta[3]-ta[2])/1e3, (ta[4]-ta[3])/1e3, (ta[5]-ta[4])/1e3))

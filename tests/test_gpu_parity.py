@@ -553,3 +553,44 @@ def test_checkpoint_is_reference_adam_format(H, tmp_path):
 def pol_split(n, size):
     from cirs_codes_b200.parallel import split_sizes
     return split_sizes(n, size)
+
+
+def test_rollout_inverse_cdf_sampler_distribution(H):
+    """The persistent rollout samples by inverse CDF over the catalogue-slice partials (actor_combine_icdf_warp) when a
+    turn has many running environments (>= 5 row tiles; 16384 here): the first actions of many environments that share
+    one user (hence one state) must follow the oracle's softmax probabilities, be reproducible for a fixed seed /
+    counter, and change when the counter advances."""
+    import cirs_codes_b200 as cb
+    from oracle import nets
+    z = G.load("kuaishou_N1")
+    c = G.cfg(z)
+    B = 16384
+    outs = []
+    for rep in range(2):
+        env, trk = H.make_env(z, c, B=B), H.make_tracker(z, c, B=B)
+        pol = H.make_policy(z, c, None, seed=321)
+        buf = cb.VectorReplayBuffer(B * c["T"], B)
+        col = cb.Collector(pol, env, buf, preprocess_fn=trk.build_state, force_length=1)
+        assert col.fused and col.persistent
+        users = np.full(B, int(z["it0/users"][0]))
+        col.collect(n_episode=B, users=users)
+        first = buf.act.reshape(B, buf.sub_size)[:, 0].copy()
+        col.collect(n_episode=B, users=users)          # the device-side counter advanced: different draws
+        second = buf.act.reshape(B, buf.sub_size)[:, 0].copy()
+        outs.append((first, second))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert not np.array_equal(outs[0][0], outs[0][1])
+    R = nets.rl_params(nets.to_params(z, "init/actor/"), nets.to_params(z, "init/critic/"))
+    s0 = torch.tensor(z["it0/s0"][:1])
+    p = nets.actor_probs(R, s0).detach().numpy()[0]
+    acts = np.concatenate([outs[0][0], outs[0][1]])
+    n = len(acts)
+    cnt = np.bincount(acts, minlength=c["I"])
+    assert cnt.sum() == n and acts.min() >= 0 and acts.max() < c["I"]
+    err = np.abs(cnt / n - p)
+    assert err.max() < 5 * np.sqrt(p.max() / n) + 1e-3, err.max()
+    # chi-square over the well-populated items
+    big = p * n >= 20
+    chi2 = float((((cnt - p * n) ** 2) / (p * n))[big].sum())
+    dof = int(big.sum())
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof)
