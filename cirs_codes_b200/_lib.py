@@ -99,7 +99,7 @@ PROTOTYPES = {
                                 fp, i32, fp, fp, fp]),
     "cirs_tracker_train_workspace_bytes": (i64, [P(TrackerWeightsStruct), i32, i64]),
     "cirs_tracker_train": (i32, [P(TrackerWeightsStruct), P(TrackerWeightsStruct), i32, i32, fp, fp, fp, fp, fp,
-                                 fp, i32, fp, fp, i32, fp, fp, fp, i64, fp]),
+                                 fp, i32, fp, fp, i32, fp, fp, fp, i64, i32, fp]),
     "cirs_tracker_train_fused_enable": (None, [i32]),
     "cirs_actor_workspace_bytes": (i64, [i32, i32]),
     "cirs_actor_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp, fp,

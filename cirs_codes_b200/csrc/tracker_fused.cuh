@@ -59,6 +59,8 @@ struct Args {
   const float *rew, *dense_user, *dense_item, *d_obs;
   float* obs_check;
   int ldx, ldb;                       // shared tile strides: [TM][ldx] (width d), [TM][ldb] (width max(3d, dhid, 1+dui))
+  int phase;                          // 3 = forward + backward in one launch, 1 = forward only (activations -> workspace),
+                                      // 2 = backward only (after a phase-1 launch on the same workspace)
 };
 
 // ---- Y[m x N] = X[m x K] . Wop[K x N] out of shared memory; W streamed through the stage in 128 x 128 blocks.
@@ -553,6 +555,7 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
     __syncthreads();
 
     // ================================================= forward
+    if (A.phase & 1) {
     // ---- tokens.  user rows: big = u (position 0), tok = ffn_user(u);  action rows: big = [rew ; a], tok = sigmoid(gate) a
     for (int i = tid; i < m * dui; i += NT) {
       const int r = i / dui, c = i % dui;
@@ -633,7 +636,8 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
       lin<TM, false, RES>(xs, ldx, mats[M_DEC], m, S, d, stage, [&](int r, int c, float v) {
         A.obs_check[(size_t)A.tok_slot[row0 + r] * S + c] = v + __ldg(W.dec_b + c);
       });
-    if (!A.d_obs) { __syncthreads(); continue; }
+    }   // forward
+    if (!A.d_obs || !(A.phase & 2)) { __syncthreads(); continue; }
 
     // ================================================= backward
     // ---- decoder: da = d_obs Wdec^T  (the weight gradient comes from the grouped launch)

@@ -578,7 +578,7 @@ static int fused_train(const cirs_tracker_weights& W, const cirs_tracker_weights
                        const int32_t* users, const int32_t* act, const float* rew, const int32_t* ep_len,
                        const float* dense_user, const float* dense_item, const int32_t* tok_slot,
                        const int32_t* env_off, const float* d_obs, float* obs_check, float* workspace,
-                       const FusedPlan& P, cudaStream_t st) {
+                       const FusedPlan& P, int phase, cudaStream_t st) {
   using namespace cirs_k6;
   const int d = W.d, dhid = W.d_hid, S = W.dim_state, nl = W.nlayers, dui = W.d_user_in;
   cirs_k6::Args A{};
@@ -588,6 +588,7 @@ static int fused_train(const cirs_tracker_weights& W, const cirs_tracker_weights
   A.users = users; A.act = act; A.ep_len = ep_len; A.tok_slot = tok_slot; A.env_off = env_off;
   A.rew = rew; A.dense_user = dense_user; A.dense_item = dense_item; A.d_obs = d_obs; A.obs_check = obs_check;
   A.ldx = P.ldx; A.ldb = P.ldb;
+  A.phase = phase;
   const int n_chunks = (M + P.q - 1) / P.q;
   const int grid = n_chunks < 148 ? n_chunks : 148;
   static bool attr_set = false;
@@ -606,7 +607,7 @@ static int fused_train(const cirs_tracker_weights& W, const cirs_tracker_weights
     if (prof) cirs_profile_end(st);
   }
   CIRS_CHECK_LAUNCH();
-  if (!d_obs) return CIRS_OK;
+  if (!d_obs || !(phase & 2)) return CIRS_OK;
   // ---- every Linear's weight / bias gradient in one grouped split-K launch
   const int ldd = up32(d), ld3 = up32(3 * d), ldh = up32(dhid), lds = up32(S);
   DwArgs D{};
@@ -660,7 +661,12 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
                                   const float* traj_rew, const int32_t* ep_len, const float* dense_user,
                                   const float* dense_item, int32_t n_tok, const int32_t* tok_slot,
                                   const int32_t* env_off, int32_t max_ep_len, const float* d_obs, float* obs_check,
-                                  void* workspace, int64_t workspace_bytes, void* stream) {
+                                  void* workspace, int64_t workspace_bytes, int32_t phase, void* stream) {
+  if (phase == 0) phase = 3;
+  if (phase < 1 || phase > 3) {
+    cirs_set_error("cirs_tracker_train: phase must be 0 / 3 (forward + backward), 1 (forward only) or 2 (backward only)");
+    return CIRS_ERR_ARG;
+  }
   if (!w || !grads || !traj_rew || !ep_len || !workspace || n_env < 0 || traj_len < 1) {
     cirs_set_error("cirs_tracker_train: null argument");
     return CIRS_ERR_ARG;
@@ -697,8 +703,10 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
     // throughput-oriented layer-by-layer launches are faster (measured 5.0 vs 9.7 ms)
     if (P.ok && (M + P.q - 1) / P.q <= 4 * 148)
       return fused_train(*w, *grads, B, L, M, users, traj_act, traj_rew, ep_len, dense_user, dense_item, tok_slot,
-                         env_off, d_obs, obs_check, reinterpret_cast<float*>(workspace), P, st);
+                         env_off, d_obs, obs_check, reinterpret_cast<float*>(workspace), P, phase, st);
   }
+  // layer-by-layer launches: the early forward-only call is a no-op, the later call runs the whole pass
+  if (phase == 1 && !obs_check) return CIRS_OK;
   Bufs b = carve(reinterpret_cast<float*>(workspace), B, M, d, dhid, nl, dui);
   const size_t att_smem = attn_smem_bytes(L, dh, ATT_WARPS);
   if (att_smem > 200 * 1024) {

@@ -83,6 +83,9 @@ class PPOPolicy:
         self.group = process_group
         self.use_c_comm = True   # NCCL process groups: gradient all-reduces issued from C inside cirs_ppo_learn
         self.c_loop = True       # False: per-minibatch entry points driven from Python (tests; gloo groups)
+        # K6's forward half on a side stream beside the PPO minibatches (cirs_tracker_train phase 1 / 2).  Measured on
+        # B200 at configs[1]: 1.672 vs 1.654 ms per iteration -- the stream fork / join costs what the overlap hides, so off
+        self.overlap_tracker_forward = False
         self.h2d_bytes = self.d2h_bytes = 0          # host<->device traffic of the last update()
         # The reference builds ONE Net shared by actor and critic (CIRS-RL-kuaishou.py:245-247) and lists its tensors
         # twice in optim_RL / clip_grad_norm_; this implementation reproduces exactly that structure.
@@ -506,6 +509,13 @@ class PPOPolicy:
         else:
             indices = self._h2d_i32(buffer.sample_index(0))
             self.h2d_bytes += 4 * n
+        # the tracker's training forward needs neither returns nor gradients: start it now on a side stream, beside
+        # the head passes of process_fn / learn (joined before the tracker's backward in learn)
+        self._trk_fwd = False
+        if self.overlap_tracker_forward and self.state_tracker is not None and self.cfg_tracker is not None \
+                and getattr(buffer, "_plan_ok", False):
+            self.state_tracker.forward_async(buffer, getattr(buffer, "d_users", None), tok_slot=indices)
+            self._trk_fwd = True
         self.process_fn(buffer, indices)
         result = self.learn(buffer, n, indices, batch_size or n, repeat, perms=perms, mb_sizes=mb_sizes)
         self.updating = False
@@ -596,7 +606,8 @@ class PPOPolicy:
                               _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), st)
         if tracker is not None:
             tracker.zero_grad()
-            tracker.backward_from_buffer(buffer, self.d_obs, getattr(buffer, "d_users", None), tok_slot=indices)
+            tracker.backward_from_buffer(buffer, self.d_obs, getattr(buffer, "d_users", None), tok_slot=indices,
+                                         after_forward=getattr(self, "_trk_fwd", False))
             if comm is not None:       # tracker gradient + losses: one fused NCCL operation
                 _lib.call("cirs_comm_group_begin", comm)
             self._allreduce(tracker.grad)

@@ -218,11 +218,29 @@ class StateTrackerTransformer:
     def zero_grad(self):
         self.grad.zero_()
 
-    def backward_from_buffer(self, buffer, d_obs, users, obs_check=None, compact=True, tok_slot=None):
+    def forward_async(self, buffer, users, tok_slot=None):
+        """Issue the forward half of the training pass (it needs no upstream gradient) on a side stream, so that it
+        runs beside the PPO minibatches; ``backward_from_buffer(..., after_forward=True)`` later joins and runs the
+        backward half.  Tracker weights and buffer must not change in between (they do not: the tracker's Adam step is
+        the last thing an update does)."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._fwd_done = torch.cuda.Event()
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.backward_from_buffer(buffer, None, users, tok_slot=tok_slot, phase=1)
+            self._fwd_done.record(self._side)
+
+    def backward_from_buffer(self, buffer, d_obs, users, obs_check=None, compact=True, tok_slot=None, phase=0,
+                             after_forward=False):
         """Accumulate d loss / d tracker-params into self.grad given d_obs[B*L, S] (zero rows = no gradient).
         ``compact``: process only the stored transitions' tokens (rows = buffer.sample_index(0)) instead of all B*L
         padded slots."""
         lib = _lib.load()
+        if after_forward:
+            torch.cuda.current_stream().wait_event(self._fwd_done)
+            phase = 2
         B, L = buffer.buffer_num, buffer.sub_size
         env_off = None
         n_tok = 0
@@ -251,7 +269,7 @@ class StateTrackerTransformer:
                   n_tok,
                   _lib.ptr(tok_slot), _lib.ptr(env_off), int(buffer._lengths.max()) if compact else 0,
                   _lib.ptr(d_obs), _lib.ptr(obs_check), _lib.ptr(self._ws),
-                  int(self._ws.numel()), _lib.stream())
+                  int(self._ws.numel()), int(phase), _lib.stream())
 
     def optim_step(self, cfg_struct):
         """optim_state.step() (core/policy/ppo.py:235): plain Adam, no clipping."""

@@ -239,8 +239,12 @@ int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights
                        int32_t traj_len, const int32_t* users, const int32_t* traj_act, const float* traj_rew,
                        const int32_t* ep_len, const float* dense_user, const float* dense_item, int32_t n_tok,
                        const int32_t* tok_slot, const int32_t* env_off, int32_t max_ep_len, const float* d_obs,
-                       float* obs_check, void* workspace, int64_t workspace_bytes, void* stream);
-/* Compact mode runs as TWO launches by default (csrc/tracker_fused.cuh): a chunk kernel that carries whole
+                       float* obs_check, void* workspace, int64_t workspace_bytes, int32_t phase, void* stream);
+/* phase: 0 or 3 = the whole pass; 1 = forward only (needs no d_obs: it can be issued on a side stream as soon as the
+ * rollout has ended, beside the PPO minibatches); 2 = backward only, after a phase-1 call with the same arguments and
+ * workspace and unchanged tracker weights.  The layer-by-layer path treats phase 1 as a no-op and runs everything in
+ * phase 2.
+ * Compact mode runs as TWO launches by default (csrc/tracker_fused.cuh): a chunk kernel that carries whole
  * environments through the forward and backward pass inside one CTA, and one grouped split-K launch for every
  * Linear's weight gradient.  max_ep_len (0 = unknown -> traj_len) is the longest stored episode: it sizes the chunks.
  * cirs_tracker_train_fused_enable(0) selects the layer-by-layer launches instead (-1 = default; CIRS_K6_UNFUSED=1);

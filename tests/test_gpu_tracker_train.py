@@ -129,3 +129,24 @@ def test_full_iterations_vs_golden(H, name):
             if k.endswith("in_proj_bias"):
                 mine, ref = G.drop_key_bias(mine), G.drop_key_bias(ref)   # zero-gradient key bias, see CPU test
             G.assert_close(mine, ref, 1e-5, 2 * G.PARAM_ATOL, what=k)
+
+
+def test_tracker_train_split_phases_match_single_pass(H):
+    """cirs_tracker_train phase 1 (forward only, no upstream gradient needed) followed by phase 2 (backward only) on the
+    same workspace == the single-launch pass: identical parameter gradients."""
+    z = G.load("kuaishou_N5")
+    c = G.cfg(z)
+    trk = H.make_tracker(z, c)
+    pol = H.make_policy(z, c, None)
+    buf, _ = _replay(H, z, c, 0, trk, pol)
+    buf.sync_device()
+    B, L, S = c["B"], buf.sub_size, 20
+    d_dobs = torch.tensor(np.random.default_rng(1).normal(size=(B * L, S)).astype(np.float32), device="cuda")
+    trk.zero_grad()
+    trk.backward_from_buffer(buf, d_dobs, buf.d_users)
+    one = trk.grad.clone()
+    trk.zero_grad()
+    trk.forward_async(buf, buf.d_users)
+    trk.backward_from_buffer(buf, d_dobs, buf.d_users, after_forward=True)
+    torch.cuda.synchronize()
+    G.assert_close(trk.grad.cpu().numpy(), one.cpu().numpy(), 1e-6, 1e-7, what="split-phase gradients")
