@@ -124,6 +124,7 @@ PROTOTYPES = {
                              fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, fp, i64, fp, fp, fp, fp, fp, fp, i32, fp]),
     "cirs_update_plan": (i32, [i32, i32, fp, fp, fp, fp]),
     "cirs_gather_i32": (i32, [fp, fp, fp, i32, fp]),
+    "cirs_zero": (i32, [fp, i64, fp]),
     "cirs_coverage_count": (i32, [i32, fp, fp, i32, fp, fp, fp, fp]),
     "cirs_comm_unique_id": (i32, [fp]),
     "cirs_comm_create": (i32, [fp, i32, i32, P(fp)]),

@@ -114,6 +114,21 @@ extern "C" int cirs_coverage_count(int32_t n, const int32_t* idx, const int32_t*
   return CIRS_OK;
 }
 
+// stream-ordered zero fill (cudaMemsetAsync): gradient buffers are cleared without a library fill kernel
+extern "C" int cirs_zero(void* ptr, int64_t bytes, void* stream) {
+  if (bytes < 0 || (bytes > 0 && !ptr)) {
+    cirs_set_error("cirs_zero: bad argument");
+    return CIRS_ERR_ARG;
+  }
+  if (bytes == 0) return CIRS_OK;
+  const cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    cirs_set_error(cudaGetErrorString(e));
+    return CIRS_ERR_CUDA;
+  }
+  return CIRS_OK;
+}
+
 extern "C" int cirs_update_plan(int32_t n_env, int32_t traj_len, const int32_t* n_slot, int32_t* tok_slot,
                                 int32_t* env_off, void* stream) {
   if (n_env < 0 || traj_len <= 0 || !n_slot || !env_off) {

@@ -415,7 +415,7 @@ class PPOPolicy:
         if getattr(self, "_cnt_dev", None) is None:
             self._cnt_dev = torch.zeros(world, dtype=torch.int32, device=self.device)
             self._cnt_pin = torch.zeros(world, dtype=torch.int32).pin_memory()
-        self._cnt_dev.zero_()
+        _lib.call("cirs_zero", _lib.ptr(self._cnt_dev), world * 4, _lib.stream())
         self._cnt_dev[rank:rank + 1].copy_(buffer.d_env_off[buffer.buffer_num:buffer.buffer_num + 1])
         comm = self._comm()
         if comm is not None:
@@ -591,8 +591,8 @@ class PPOPolicy:
             for step in range(repeat):
                 n_glob = n_glob_plan if n_glob_plan is not None else \
                     stats.view(repeat, n_mb, 3)[step, :, 0].round().to(torch.int64).cpu().numpy()
-                if tracker is not None:
-                    self.d_obs.zero_()                                               # optim_state.zero_grad(), :174
+                if tracker is not None:                                              # optim_state.zero_grad(), :174
+                    _lib.call("cirs_zero", _lib.ptr(self.d_obs), self.d_obs.numel() * 4, st)
                 for j in range(n_mb):
                     b, e = int(offs[j]), int(offs[j + 1])
                     _lib.call("cirs_ppo_minibatch", C.byref(self._w), C.byref(self._g), C.byref(self.cfg), e - b,

@@ -216,7 +216,7 @@ class StateTrackerTransformer:
 
     # ------------------------------------------------------------------ training (K6 + K7)
     def zero_grad(self):
-        self.grad.zero_()
+        _lib.call("cirs_zero", _lib.ptr(self.grad), self.grad.numel() * 4, _lib.stream())
 
     def forward_async(self, buffer, users, tok_slot=None):
         """Issue the forward half of the training pass (it needs no upstream gradient) on a side stream, so that it

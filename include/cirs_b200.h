@@ -432,6 +432,8 @@ int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_weights* grad
 int cirs_update_plan(int32_t n_env, int32_t traj_len, const int32_t* n_slot, int32_t* tok_slot, int32_t* env_off,
                      void* stream);
 int cirs_gather_i32(int32_t* dst, const int32_t* src, const int32_t* idx, int32_t n, void* stream);
+/* Stream-ordered zero fill of a device buffer (optim_state.zero_grad(), core/policy/ppo.py:174, for the flat gradient buffers). */
+int cirs_zero(void* ptr, int64_t bytes, void* stream);
 
 /* Test-time coverage metrics of a collect on the device (evaluation.py:286-371 Callback_Coverage_Count):
  * over the n stored transitions act[idx[i]] (idx NULL -> act[i]): out3[0] = number of DISTINCT recommended items

@@ -149,4 +149,6 @@ def test_tracker_train_split_phases_match_single_pass(H):
     trk.forward_async(buf, buf.d_users)
     trk.backward_from_buffer(buf, d_dobs, buf.d_users, after_forward=True)
     torch.cuda.synchronize()
-    G.assert_close(trk.grad.cpu().numpy(), one.cpu().numpy(), 1e-6, 1e-7, what="split-phase gradients")
+    # float atomics accumulate the chunks' contributions in a different order from launch to launch: rounding level
+    scale = float(one.abs().max())
+    G.assert_close(trk.grad.cpu().numpy(), one.cpu().numpy(), 1e-5, 1e-6 * scale, what="split-phase gradients")
