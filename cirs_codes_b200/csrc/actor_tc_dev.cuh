@@ -5,8 +5,10 @@
 // environments in tiles of 128 rows: gathers their trunk outputs h2 (FP32, [B, 64]) into a K-major (hi, lo) tile,
 // issues D[128 x 80] = h2 . W3_slice as 3 x 8 kind::tf32 MMAs into one of two TMEM accumulators, and while the
 // tensor core works on the next row tile the 256 threads run the epilogue of the previous one straight out of TMEM:
-// online softmax (max, sum) and the running winner of the race  argmax_j logit_j + Gumbel_j  with the SAME Philox
-// stream, keyed by (environment, column / 4), as the FFMA path (actor_dev.cuh) -- so both paths draw identical noise.
+// softmax partials (max, sum) and the slice's candidate action by the two-level sampler described at the epilogue
+// (inverse CDF inside a 40-column unit, exponential race across units; Philox4x32-10 keyed by (environment, unit)).
+// The draws differ from the FFMA path's per-element race (actor_dev.cuh) -- same distribution, different stream;
+// MODE_ARGMAX is deterministic and identical on both paths.
 // One Partial per (slice, row) goes to the workspace; actor_combine_warp merges the slices unchanged.
 #pragma once
 #include "actor_dev.cuh"
@@ -70,20 +72,45 @@ __device__ __forceinline__ void tc_teardown(const TcSmem& S, int tid) {
   if (tid < 32) tmem_dealloc(*S.tmem, TMEM_COLS);
 }
 
-struct SrcRows {   // gathered h2 rows of one 128-row tile of the compact row list
-  const float* h2; const int32_t* gather; int k0, n_rows;
-  __device__ __forceinline__ float4 operator()(int r, int c4) const {
-    const int k = k0 + r;
-    if (k >= n_rows) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const int id = gather ? gather[k] : k;
-    return *reinterpret_cast<const float4*>(h2 + (size_t)id * HID + 4 * c4);   // written this launch: no __ldg
+// The h2 rows of the running environments reach phase A as ready-made operand-tile IMAGES in global memory: phase B
+// writes every row's trunk output, already split into TF32 (hi, lo), at its position in the NEXT turn's compact row
+// list ([tile][hi | lo][A_BYTES], the shared-memory tile layout byte for byte), so staging a row tile is a straight
+// 16-byte copy of the tile's first `rows` rows -- no gather, no split arithmetic, nothing for rows that are not there.
+__device__ __forceinline__ void h2_image_store(char* img, int kn, int o, float v) {   // row kn of the list, hidden o
+  char* tile = img + (size_t)(kn / ROWS) * (2 * A_BYTES);
+  const uint32_t off = tile_chunk_off(ROWS, kn % ROWS, o >> 2) + (uint32_t)(o & 3) * 4u;
+  const float h = tf32_hi(v);
+  *reinterpret_cast<float*>(tile + off) = h;
+  *reinterpret_cast<float*>(tile + A_BYTES + off) = tf32_hi(v - h);
+}
+struct RawTile {   // register prefetch of one tile image (behind the previous tile's MMA + epilogue)
+  float4 h[ROWS * HID / 4 / NT], l[ROWS * HID / 4 / NT];
+  __device__ __forceinline__ void load(int tid, const char* tile, int rows) {
+#pragma unroll
+    for (int i = 0; i < ROWS * HID / 4 / NT; ++i) {
+      const int idx = tid + i * NT;
+      if ((idx & (ROWS - 1)) < rows) {   // written during this launch by other CTAs: L2 loads (ld.global.cg)
+        h[i] = __ldcg(reinterpret_cast<const float4*>(tile + (size_t)idx * 16));
+        l[i] = __ldcg(reinterpret_cast<const float4*>(tile + A_BYTES + (size_t)idx * 16));
+      }
+    }
+  }
+  __device__ __forceinline__ void store(char* hi, char* lo, int tid, int rows) const {
+#pragma unroll
+    for (int i = 0; i < ROWS * HID / 4 / NT; ++i) {
+      const int idx = tid + i * NT;
+      if ((idx & (ROWS - 1)) < rows) {
+        *reinterpret_cast<float4*>(hi + (size_t)idx * 16) = h[i];
+        *reinterpret_cast<float4*>(lo + (size_t)idx * 16) = l[i];
+      }
+    }
   }
 };
 
 // One turn's actor-head partials for this CTA's slice.  P: n_rows / gather (compact list of running environments),
-// h2_in, part (n_split == number of slices), mode, seed, offset, rng_counter.  Every thread of the CTA calls it.
-__device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const TcSmem& S, int tid, TcState& st,
-                                             int* timeout_flag, long long* tq = nullptr) {
+// part (n_split == number of slices), mode, seed, offset, rng_counter.  Every thread of the CTA calls it.
+__device__ __forceinline__ void tc_head_turn(const HeadArgs& P, const char* h2_img, int slice, const TcSmem& S, int tid,
+                                             TcState& st, int* timeout_flag, long long* tq = nullptr) {
   // tq (optional, one CTA): %globaltimer stamps {entry, h2 tile staged, first MMA done, epilogue done, partials written}
   auto stamp = [&](int i) {
     if (tq && tid == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); tq[i] = t_; }
@@ -104,16 +131,25 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
     }
     __syncwarp();
   };
-  TileV<ROWS, HID, NT> ta;
-  ta.load(tid, SrcRows{P.h2_in, P.gather, 0, P.n_rows});
-  ta.store(S.a_hi, S.a_lo, tid);
+  auto rows_of = [&](int rt) { return min(ROWS, P.n_rows - rt * ROWS); };
+  {   // first tile: cp.async straight into the operand tile (nothing to hide it behind)
+    const int rows = rows_of(0);
+    for (int idx = tid; idx < ROWS * HID / 4; idx += NT)
+      if ((idx & (ROWS - 1)) < rows) {
+        cp_async16(S.a_hi + (size_t)idx * 16, h2_img + (size_t)idx * 16);
+        cp_async16(S.a_lo + (size_t)idx * 16, h2_img + A_BYTES + (size_t)idx * 16);
+      }
+    cp_async_commit();
+    cp_async_wait_all();
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   if (warp0) issue(0);
   stamp(1);
-  if (n_rt > 1) ta.load(tid, SrcRows{P.h2_in, P.gather, ROWS, P.n_rows});
+  RawTile ta;
+  if (n_rt > 1) ta.load(tid, h2_img + (size_t)1 * 2 * A_BYTES, rows_of(1));
   for (int rt = 0; rt < n_rt; ++rt) {
     const int b = rt & 1;
     uint32_t& use = b ? st.use1 : st.use0;
@@ -122,77 +158,82 @@ __device__ __forceinline__ void tc_head_turn(const HeadArgs& P, int slice, const
     fence_after_sync();
     if (rt == 0) stamp(2);
     if (rt + 1 < n_rt) {   // the h2 tile is free again: next row tile's MMA runs behind this tile's epilogue
-      ta.store(S.a_hi, S.a_lo, tid);
+      ta.store(S.a_hi, S.a_lo, tid, rows_of(rt + 1));
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
       if (warp0) issue(rt + 1);
-      if (rt + 2 < n_rt) ta.load(tid, SrcRows{P.h2_in, P.gather, (rt + 2) * ROWS, P.n_rows});
+      if (rt + 2 < n_rt) ta.load(tid, h2_img + (size_t)(rt + 2) * 2 * A_BYTES, rows_of(rt + 2));
     }
     // ---- epilogue: thread = (row, column half of 40)
     const int k = rt * ROWS + row;
     const bool live = k < P.n_rows;
     const int rid = live ? (P.gather ? P.gather[k] : k) : -1;
-    // Race in the probability domain: candidate j beats the running winner iff  e_j / q_j > e_best / q_best  with
-    // e = exp(l - m) relative to the running maximum (rescaled together with the softmax sum when m grows) and
-    // q = -log(u) ~ Exp(1).  One fast log per element instead of the two of the Gumbel form; the winner's score
-    // l - log(q) (log domain, what the cross-slice merge compares) is formed once per row tile.
-    float m = -INFINITY, z = 0.f, e_best = 0.f, q_best = 1.f, bl = 0.f;
+    // Two-level sampler.  The thread's 40 columns form one UNIT of the catalogue.  Inside the unit the candidate is
+    // drawn by inverse CDF (one uniform: P(j | unit) = e_j / z_unit); across the 270 units of a row the winner is the
+    // exponential race over the unit masses (one Exp(1) draw q per unit: P(unit) = mass_unit / Z), carried in the log
+    // domain as best_s = m + log z - log q, which is exactly what merge_best / actor_combine_warp compare.  Hence
+    // P(j) = softmax(logits)_j as for Categorical.sample (core/policy/ppo.py:135), with 2 random numbers per unit instead
+    // of one Philox draw + one log per ELEMENT (the per-element race was ~110 instructions per element, 8.2 us per row
+    // tile; this is ~12).  MODE_ARGMAX: the unit's first maximum, best_s = its logit (ties -> lowest index in the merge).
+    float m = -INFINITY, z = 0.f, bl = 0.f, bs = -INFINITY;
     int bi = 0x7fffffff;
     const int lbase = half * (SLICE / 2);          // column offset inside the slice
     const int cbase = slice * SLICE + lbase;       // catalogue column
     constexpr int NCH = SLICE / 16;                // chunks of 8 columns per thread
-    uint32_t vr[2][8];
-    tmem_ld8_issue(tmem_addr(tb + 128u * b, (warp & 3) * 32, lbase), vr[0]);
+    constexpr int NC = SLICE / 2;                  // columns per thread
+    uint32_t vr[NCH][8];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      tmem_ld8_wait(vr[ch & 1]);
-      if (ch + 1 < NCH) tmem_ld8_issue(tmem_addr(tb + 128u * b, (warp & 3) * 32, lbase + (ch + 1) * 8), vr[(ch + 1) & 1]);
-      if (!live) continue;
+    for (int ch = 0; ch < NCH; ++ch) tmem_ld8_issue(tmem_addr(tb + 128u * b, (warp & 3) * 32, lbase + ch * 8), vr[ch]);
 #pragma unroll
-      for (int q4 = 0; q4 < 2; ++q4) {
-        const int nb = cbase + ch * 8 + 4 * q4;
-        if (nb >= nA) continue;
-        float qn[4] = {1.f, 1.f, 1.f, 1.f};
-        if (P.mode == MODE_SAMPLE && !P.icdf) {
-          const uint4 rnd = philox4x32(make_uint4((uint32_t)rid, (uint32_t)(nb >> 2), (uint32_t)offset,
-                                                  (uint32_t)(offset >> 32)),
-                                       make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-          const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+    for (int ch = 0; ch < NCH; ++ch) tmem_ld8_wait(vr[ch]);
+    if (live) {
+      float l[NC];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float u = u01(rr[j]), w = 1.0f - u;   // u in (0, 1], w exact
-            const float ql = w * fmaf(w, fmaf(w, 0.33333334f, 0.5f), 1.0f);   // -log(1 - w) for small w
-            qn[j] = fmaxf(w < 0.00390625f ? ql : -__logf(u), 1e-30f);
-          }
-        }
+      for (int g = 0; g < NC / 4; ++g) {
+        const int nb = cbase + 4 * g;
         // remove_recommended_ids (core/policy/utils.py:30-58): items already shown this episode leave the distribution
         uint32_t seen_bits = 0u;
-        if (P.seen) seen_bits = P.seen[(size_t)rid * seen_words + (nb >> 5)] >> (nb & 31);
-        float l[4], mx = -INFINITY;
+        if (P.seen && nb < nA) seen_bits = P.seen[(size_t)rid * seen_words + (nb >> 5)] >> (nb & 31);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const bool ok = nb + j < nA && !((seen_bits >> j) & 1u);
-          l[j] = ok ? __uint_as_float(vr[ch & 1][4 * q4 + j]) + S.b3[lbase + ch * 8 + 4 * q4 + j] : -INFINITY;
-          mx = fmaxf(mx, l[j]);
+          l[4 * g + j] = ok ? __uint_as_float(vr[g >> 1][4 * (g & 1) + j]) + S.b3[lbase + 4 * g + j] : -INFINITY;
+          m = fmaxf(m, l[4 * g + j]);
         }
-        if (mx == -INFINITY) continue;
-        if (mx > m) {
-          const float sc = __expf(m - mx);   // m = -inf at the start: exp(-inf) = 0
-          z *= sc;
-          e_best *= sc;
-          m = mx;
-        }
+      }
+      if (m != -INFINITY) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float e = __expf(l[j] - m);   // 0 for masked columns
-          z += e;
-          if (e * q_best > qn[j] * e_best) { e_best = e; q_best = qn[j]; bl = l[j]; bi = nb + j; }
+        for (int j = 0; j < NC; ++j) z += __expf(l[j] - m);
+        if (P.mode == MODE_SAMPLE) {
+          const uint4 rnd = philox4x32(make_uint4((uint32_t)rid, 0x40000000u + (uint32_t)(2 * slice + half),
+                                                  (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                       make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+          const float q = fmaxf(-__logf(u01(rnd.x)), 1e-30f);            // Exp(1)
+          const float target = (rnd.y >> 8) * (1.0f / 16777216.0f) * z;   // uniform in [0, z)
+          float acc = 0.f, last_l = 0.f;
+          int last_j = 0;
+          bool found = false;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            const float e = __expf(l[j] - m);   // the same values, in the same order, as the sum above
+            acc += e;
+            if (e > 0.f) { last_j = j; last_l = l[j]; }
+            if (!found && e > 0.f && acc > target) { found = true; bi = j; bl = l[j]; }
+          }
+          if (!found) { bi = last_j; bl = last_l; }   // target rounded up to z
+          bi += cbase;
+          bs = m + __logf(z) - __logf(q);
+        } else {
+#pragma unroll
+          for (int j = NC - 1; j >= 0; --j)
+            if (l[j] == m) bi = cbase + j;
+          bl = m;
+          bs = m;
         }
       }
     }
-    float bs = bi == 0x7fffffff ? -INFINITY : bl - logf(q_best);
     if (rt == 0) stamp(3);
     S.red[tid] = m; S.red[NT + tid] = z; S.red[2 * NT + tid] = bs; S.red[3 * NT + tid] = bl;
     S.red[4 * NT + tid] = __int_as_float(bi);

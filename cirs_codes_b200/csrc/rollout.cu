@@ -22,6 +22,7 @@
 #include "env_dev.cuh"
 #include "tracker_dev.cuh"
 #include "tracker_cta_dev.cuh"
+#include "tracker_fast_dev.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -56,6 +57,7 @@ struct RolloutArgs {
   int* count;               // [2] length of the compact list of turn t (index t & 1)
   int32_t* list;            // [2, B] environments still running at turn t
   float* h2;                // [B, 64] trunk output of the current state of every environment
+  char* h2_img;             // tensor-core head: the same rows as TF32 (hi, lo) operand-tile images in list order
   const float* w_lo;        // tracker weights (everything but the embedding tables): start and float count
   int w_count;
   int smem_w_off;           // float offset of the staged weights inside dynamic shared memory
@@ -69,6 +71,10 @@ struct RolloutArgs {
   int n_slices;             // ceil(n_action / 80) <= grid
   int tc_keep_off;          // float offset of the launch-lifetime shared-memory region (W3 slice, mbarriers)
   int* tc_timeout;          // set when an mbarrier wait gives up (never expected)
+  // latency form of phase B (tracker_fast_dev.cuh; d = 32): transposed weights staged at smem_w_off, trunk image at
+  // trunk_w_off (rebuilt by every CTA at launch, re-fetched per turn from trunk_img)
+  cirs_tfast::Layout fast;
+  float* trunk_img;         // [TR_FLOATS] global copy of the transposed trunk (written by CTA 0 at launch)
 };
 
 // Trunk + critic of R rows by the whole CTA, in the operation order of actor_trunk_warp / actor_head_body (bias first, k
@@ -79,7 +85,8 @@ __host__ __device__ inline int trunk_w_floats(int S) { return S * HID + HID + HI
 
 __device__ __forceinline__ void trunk_rows(const cirs_policy_weights& W, int R, float* sc, int stride, int state_off,
                                            const int* row_e, float* __restrict__ h2_out, float* __restrict__ value_out,
-                                           const float* ws = nullptr) {
+                                           const float* ws = nullptr, char* h2_img = nullptr,
+                                           const int* row_kn = nullptr) {
   const int S = W.dim_state, tid = threadIdx.x;
   const int H1 = stride - 128, H2 = stride - 64;
   // ws: w1t [S][64] | b1 | w2t [64][64] | b2 | wv | bv in shared memory; otherwise the weights come from global memory
@@ -116,7 +123,11 @@ __device__ __forceinline__ void trunk_rows(const cirs_policy_weights& W, int R, 
     }
     a = fmaxf(a, 0.f);
     sc[(size_t)r * stride + H2 + o] = a;
-    h2_out[(size_t)row_e[r] * HID + o] = a;
+    if (h2_img) {   // position row_kn[r] of the next turn's row list (< 0: the episode ended)
+      if (row_kn[r] >= 0) cirs_actor_tc::h2_image_store(h2_img, row_kn[r], o, a);
+    } else {
+      h2_out[(size_t)row_e[r] * HID + o] = a;
+    }
   }
   __syncthreads();
   if (tid < R && value_out) {
@@ -166,7 +177,8 @@ __device__ __forceinline__ void prefetch_kv(const cirs_tracker_weights& W, int n
 // SMW: the tracker's weights are staged once in shared memory (they are re-read by every warp at every turn; from L2
 // each token is ~55 dependent round trips of ~0.6 us, from shared memory ~20x less)
 // TC: phase A on the tcgen05 tensor cores (3xTF32), each CTA keeping its slice of W3 in shared memory for the launch
-template <bool SMW, bool TC>
+// FAST: phase B in its latency form (tracker_fast_dev.cuh; implies SMW and TC)
+template <bool SMW, bool TC, bool FAST = false>
 __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kernel(const RolloutArgs A) {
   extern __shared__ __align__(128) float smem_dyn[];
   // The two structs that change during the launch (tracker weight pointers rebased into shared memory; the head's
@@ -183,7 +195,12 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
   const int B = A.n_env;
   if (tid == 0) { sT = A.T; sH = A.H; }
   __syncthreads();
-  if (SMW) {
+  if (FAST) {
+    cirs_tfast::stage_tracker(A.T, A.fast, smem_dyn + A.smem_w_off);
+    cirs_tfast::stage_trunk(A.H.W, smem_dyn + A.trunk_w_off);
+    if (blockIdx.x == 0)
+      for (int i = tid; i < cirs_tfast::TR_FLOATS; i += NT) A.trunk_img[i] = smem_dyn[A.trunk_w_off + i];
+  } else if (SMW) {
     float* wsm = smem_dyn + A.smem_w_off;
     for (int i = tid; i < A.w_count / 4; i += NT)
       reinterpret_cast<float4*>(wsm)[i] = __ldg(reinterpret_cast<const float4*>(A.w_lo) + i);
@@ -208,7 +225,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
   }
 
   // ---- reset + user token (position 0); every environment starts in the compact list of turn 0
-  __shared__ int row_e[cirs_tracker::CTA_RB], row_a[cirs_tracker::CTA_RB];
+  __shared__ int row_e[cirs_tracker::CTA_RB], row_a[cirs_tracker::CTA_RB], row_kn[cirs_tracker::CTA_RB];
   __shared__ float row_r[cirs_tracker::CTA_RB];
   constexpr int RB = cirs_tracker::CTA_RB;
   if (blockIdx.x == 0 && tid == 0) {
@@ -227,15 +244,23 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       if (lane == 0) {
         A.ep_len[e] = 0;
         A.list[e] = e;
-        row_e[warp] = e; row_a[warp] = u; row_r[warp] = 0.f;
+        row_e[warp] = e; row_a[warp] = u; row_r[warp] = 0.f; row_kn[warp] = e;
       }
     }
     __syncthreads();
-    const int off = cirs_tracker::tracker_token_cta<SMW>(sT, B, R, 0, row_e, row_a, row_r, A.kcache, A.vcache, smem_dyn,
-                                                         A.row_floats, A.cur_state, A.traj_len, A.traj_obs, A.traj_obs_next,
-                                                         nullptr, nullptr, 0,
-                                                         A.part_off >= 0 ? smem_dyn + A.part_off : nullptr);
-    trunk_rows(A.H.W, R, smem_dyn, A.row_floats, off, row_e, A.h2, A.value);
+    if (FAST) {
+      cirs_tfast::token_and_trunk(sT, A.fast, smem_dyn + A.smem_w_off, smem_dyn + A.trunk_w_off, B, R, 0, row_e, row_a,
+                                  row_r, row_kn, A.kcache, A.vcache, smem_dyn, A.row_floats, A.cur_state, A.traj_len,
+                                  A.traj_obs, A.traj_obs_next, nullptr, 0, A.value, [&](int r, int o, float v) {
+                                    if (row_kn[r] >= 0) cirs_actor_tc::h2_image_store(A.h2_img, row_kn[r], o, v);
+                                  });
+    } else {
+      const int off = cirs_tracker::tracker_token_cta<SMW>(sT, B, R, 0, row_e, row_a, row_r, A.kcache, A.vcache, smem_dyn,
+                                                           A.row_floats, A.cur_state, A.traj_len, A.traj_obs,
+                                                           A.traj_obs_next, nullptr, nullptr, 0,
+                                                           A.part_off >= 0 ? smem_dyn + A.part_off : nullptr);
+      trunk_rows(A.H.W, R, smem_dyn, A.row_floats, off, row_e, A.h2, A.value, nullptr, TC ? A.h2_img : nullptr, row_kn);
+    }
   }
   __threadfence();
   grid.sync();
@@ -257,11 +282,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       sH.gather = A.list + (size_t)(t & 1) * B;
       if (TC) {
         sH.n_split = A.n_slices;
-        // inverse-CDF sampling in phase B (no per-element race in the epilogue) once the head phase walks five or more
-        // 128-row tiles: measured on B200 the epilogue drops from 8.1 to 3.5 us per tile while the per-row split
-        // recompute adds ~7 us to phase B, so it pays from ~5 tiles (configs[2]: 32 tiles per turn, rollout 1.99 ->
-        // 1.70 ms; configs[1] with its 4 tiles keeps the race)
-        sH.icdf = sH.mode == MODE_SAMPLE && (n_act + cirs_actor_tc::ROWS - 1) / cirs_actor_tc::ROWS >= 5;
+        sH.icdf = 0;   // the tensor-core epilogue samples inside the slice (two-level sampler): complete partials
       } else {
         int n_split = gridDim.x / row_tiles;
         n_split = n_split < 1 ? 1 : (n_split > n_col_tiles ? n_col_tiles : n_split);
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
     // ---- phase A: actor head partials over the compact rows
     if (TC) {
       if ((int)blockIdx.x < A.n_slices)
-        cirs_actor_tc::tc_head_turn(H, blockIdx.x, TS, tid, tst, A.tc_timeout,
+        cirs_actor_tc::tc_head_turn(H, A.h2_img, blockIdx.x, TS, tid, tst, A.tc_timeout,
                                     blockIdx.x == 0 ? A.dbg + 1 + 3 * 512 + 32 : nullptr);
     } else {
       const int n_items = row_tiles * H.n_split;
@@ -307,17 +328,18 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
                           (int64_t)R * A.T.nlayers * 2 * p * kv_ld <= (int64_t)A.kv_cap;
       if (warp < R && lane == 0) row_e[warp] = H.gather[blockIdx.x + (j0 + warp) * gridDim.x];
       __syncthreads();
-      if (A.trunk_w_off >= 0 && j0 == 0) prefetch_trunk(A.H.W, smem_dyn + A.trunk_w_off);
+      if (FAST) {
+        if (j0 == 0)
+          for (int i = tid; i < cirs_tfast::TR_FLOATS / 4; i += NT)
+            cp_async16(smem_dyn + A.trunk_w_off + 4 * i, A.trunk_img + 4 * i);
+      } else if (A.trunk_w_off >= 0 && j0 == 0) prefetch_trunk(A.H.W, smem_dyn + A.trunk_w_off);
       if (kv_fit) prefetch_kv(A.T, B, R, row_e, p, A.kcache, A.vcache, smem_dyn + A.kv_off, kv_ld);
       cp_async_commit();
       if (warp < R) {
         const int k = blockIdx.x + (j0 + warp) * gridDim.x;
         const int e = row_e[warp];
         int a;
-        if (!H.icdf) a = actor_combine_warp(H, k, lane, A.act, A.logp);
-        else if (TC) a = actor_combine_icdf_warp<(cirs_actor_tc::SLICE + 31) / 32>(H, k, lane, A.act, A.logp,
-                                                                                   A.h2 + (size_t)e * HID,
-                                                                                   cirs_actor_tc::SLICE, turn_off);
+        if (TC || !H.icdf) a = actor_combine_warp(H, k, lane, A.act, A.logp);
         else a = actor_combine_icdf_warp<8>(H, k, lane, A.act, A.logp, A.h2 + (size_t)e * HID,
                                             H.tiles_per_split * BN, turn_off);
         const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len,
@@ -325,23 +347,35 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
                                                     A.n_active);
         __syncwarp();
         if (lane == 0) {
+          int kn = -1;
           if (!d) {
-            const int kn = atomicAdd(A.count + ((t + 1) & 1), 1);
+            kn = atomicAdd(A.count + ((t + 1) & 1), 1);
             list_next[kn] = e;
           }
-          row_e[warp] = e; row_a[warp] = a; row_r[warp] = A.rew[e];
+          row_e[warp] = e; row_a[warp] = a; row_r[warp] = A.rew[e]; row_kn[warp] = kn;
         }
       }
       cp_async_wait_all();
       __syncthreads();
       if (tq && tid == 0) tq[1] = gtime_ns();
-      const int off = cirs_tracker::tracker_token_cta<SMW>(sT, B, R, p, row_e, row_a, row_r, A.kcache, A.vcache,
-                                                           smem_dyn, A.row_floats, A.cur_state, A.traj_len, A.traj_obs,
-                                                           A.traj_obs_next, tq ? tq + 2 : nullptr,
-                                                           kv_fit ? smem_dyn + A.kv_off : nullptr, kv_ld,
-                                                           A.part_off >= 0 ? smem_dyn + A.part_off : nullptr);
-      trunk_rows(A.H.W, R, smem_dyn, A.row_floats, off, row_e, A.h2, A.value,
-                 A.trunk_w_off >= 0 ? smem_dyn + A.trunk_w_off : nullptr);   // consumed by the next turn's head phase
+      if (FAST) {
+        cirs_tfast::token_and_trunk(sT, A.fast, smem_dyn + A.smem_w_off, smem_dyn + A.trunk_w_off, B, R, p, row_e, row_a,
+                                    row_r, row_kn, A.kcache, A.vcache, smem_dyn, A.row_floats, A.cur_state, A.traj_len,
+                                    A.traj_obs, A.traj_obs_next, kv_fit ? smem_dyn + A.kv_off : nullptr, kv_ld, A.value,
+                                    [&](int r, int o, float v) {
+                                      if (row_kn[r] >= 0) cirs_actor_tc::h2_image_store(A.h2_img, row_kn[r], o, v);
+                                    },
+                                    tq ? tq + 2 : nullptr);
+      } else {
+        const int off = cirs_tracker::tracker_token_cta<SMW>(sT, B, R, p, row_e, row_a, row_r, A.kcache, A.vcache,
+                                                             smem_dyn, A.row_floats, A.cur_state, A.traj_len, A.traj_obs,
+                                                             A.traj_obs_next, tq ? tq + 2 : nullptr,
+                                                             kv_fit ? smem_dyn + A.kv_off : nullptr, kv_ld,
+                                                             A.part_off >= 0 ? smem_dyn + A.part_off : nullptr);
+        trunk_rows(A.H.W, R, smem_dyn, A.row_floats, off, row_e, A.h2, A.value,
+                   A.trunk_w_off >= 0 ? smem_dyn + A.trunk_w_off : nullptr, TC ? A.h2_img : nullptr,
+                   row_kn);   // consumed by the next turn's head phase
+      }
       if (tq && tid == 0) tq[22] = gtime_ns();
     }
     if (blockIdx.x == 0 && tid == 0) {
@@ -378,15 +412,20 @@ static void occupancy_cache_put(int dev, int variant, size_t smem, int v) {
   g_occ[std::make_tuple(dev, variant, smem)] = v;
 }
 
-// workspace: [counters 256 B][phase timers][list 2*B i32][h2 B*64 f32][head partials]
+// workspace: [counters 256 B][phase timers][list 2*B i32][h2 B*64 f32][head partials][h2 tile images]
 constexpr int64_t DBG_BYTES = 8 * (1 + 6 * 512);   // phase timers of up to 512 turns
 static int64_t partial_capacity(int32_t n_env, int32_t n_action) {
   const int64_t ffma = ((int64_t)n_env + 64) * 96 + 64 * 1024;
   const int64_t tc = (int64_t)((n_action + cirs_actor_tc::SLICE - 1) / cirs_actor_tc::SLICE + 1) * ((int64_t)n_env + 128);
   return ffma > tc ? ffma : tc;
 }
+static int64_t h2_image_bytes(int32_t n_env) {
+  return (int64_t)((n_env + cirs_actor_tc::ROWS - 1) / cirs_actor_tc::ROWS) * 2 * cirs_actor_tc::A_BYTES;
+}
 extern "C" int64_t cirs_rollout_workspace_bytes(int32_t n_env, int32_t n_action) {
-  return 256 + DBG_BYTES + (int64_t)sizeof(int32_t) * 2 * n_env + 64 + (int64_t)sizeof(float) * HID * n_env + 64 + (int64_t)sizeof(Partial) * partial_capacity(n_env, n_action);
+  return 256 + DBG_BYTES + (int64_t)sizeof(int32_t) * 2 * n_env + 64 + (int64_t)sizeof(float) * HID * n_env + 64 +
+         (int64_t)sizeof(Partial) * partial_capacity(n_env, n_action) + 128 + h2_image_bytes(n_env) + 128 +
+         (int64_t)sizeof(float) * cirs_tfast::TR_FLOATS;
 }
 
 extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tracker_weights* tw,
@@ -442,8 +481,10 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   for (int l = 0; smw_ok && l < tw->nlayers; ++l)
     smw_ok = tw->layer[l].in_wt >= w_lo && tw->layer[l].n2_b < w_lo + w_count;
   size_t smem = 0;
-  bool smw = false;
+  bool smw = false, fast = false;
   int max_ctas = 0;
+  const bool fast_ok = cirs_tfast::supported(*tw, *pw) && !getenv("CIRS_ROLLOUT_NO_FAST");
+  const cirs_tfast::Layout fast_layout = cirs_tfast::layout(tw->nlayers);
   for (int attempt = 0; attempt < 2; ++attempt) {
     size_t head = tc ? up128(cirs_actor_tc::TURN_BYTES > scratch_bytes ? cirs_actor_tc::TURN_BYTES : scratch_bytes)
                      : up128(SMEM_BYTES > scratch_bytes ? SMEM_BYTES : scratch_bytes);
@@ -455,19 +496,26 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
       return CIRS_ERR_ARG;
     }
     smw = smw_ok && head + (size_t)w_count * sizeof(float) <= SMEM_MAX;
+    fast = tc && fast_ok && head + (size_t)fast_layout.total * sizeof(float) <= SMEM_MAX;
     smem = head;
     A.tc_keep_off = (int)(keep_off / sizeof(float));
     {   // phase-B staging behind the rows' scratch, inside the per-turn region [0, keep_off)
       size_t off = up128(scratch_bytes);
       const size_t part_bytes = (size_t)cirs_tracker::CTA_RB * 128 * sizeof(float);
-      const size_t tw_bytes = up128((size_t)trunk_w_floats(pw->dim_state) * sizeof(float));
+      const size_t tw_bytes = up128((size_t)(fast ? cirs_tfast::TR_FLOATS : trunk_w_floats(pw->dim_state)) * sizeof(float));
       A.part_off = A.trunk_w_off = A.kv_off = -1;
       A.kv_cap = 0;
       if (off + part_bytes <= keep_off) { A.part_off = (int)(off / sizeof(float)); off += part_bytes; }
       if (off + tw_bytes <= keep_off && (pw->dim_state * HID) % 4 == 0) { A.trunk_w_off = (int)(off / sizeof(float)); off += tw_bytes; }
       if (off + 4096 <= keep_off) { A.kv_off = (int)(off / sizeof(float)); A.kv_cap = (int)((keep_off - off) / sizeof(float)); }
+      if (fast && A.trunk_w_off < 0) fast = false;
     }
-    if (smw) {
+    if (fast) {
+      smw = true;   // (the variant index and the occupancy cache treat it as a staged-weights kernel)
+      A.w_lo = nullptr; A.w_count = 0; A.smem_w_off = (int)(smem / sizeof(float));
+      A.fast = fast_layout;
+      smem += (size_t)fast_layout.total * sizeof(float);
+    } else if (smw) {
       A.w_lo = w_lo; A.w_count = (int)w_count; A.smem_w_off = (int)(smem / sizeof(float));
       smem += (size_t)w_count * sizeof(float);
     } else {
@@ -475,14 +523,16 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
     }
     int dev = 0;
     cudaGetDevice(&dev);
-    int mc = occupancy_cache_get(dev, (smw ? 1 : 0) + (tc ? 2 : 0), smem);
+    int mc = occupancy_cache_get(dev, (smw ? 1 : 0) + (tc ? 2 : 0) + (fast ? 4 : 0), smem);
     if (!mc) {
       int per_sm = 0, n_sm = 0;
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      const void* fn = tc ? (smw ? (const void*)rollout_kuaishou_kernel<true, true> : (const void*)rollout_kuaishou_kernel<false, true>)
-                          : (smw ? (const void*)rollout_kuaishou_kernel<true, false> : (const void*)rollout_kuaishou_kernel<false, false>);
+      const void* fn = fast ? (const void*)rollout_kuaishou_kernel<true, true, true>
+                       : tc ? (smw ? (const void*)rollout_kuaishou_kernel<true, true> : (const void*)rollout_kuaishou_kernel<false, true>)
+                            : (smw ? (const void*)rollout_kuaishou_kernel<true, false> : (const void*)rollout_kuaishou_kernel<false, false>);
       cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
-      if (tc && smw) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true, true>, NT, smem);
+      if (fast) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true, true, true>, NT, smem);
+      else if (tc && smw) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true, true>, NT, smem);
       else if (tc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<false, true>, NT, smem);
       else if (smw) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<true, false>, NT, smem);
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kuaishou_kernel<false, false>, NT, smem);
@@ -492,7 +542,7 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
       }
       if (tc && per_sm > 1) per_sm = 1;   // TMEM: 256 columns per CTA, keep one CTA per SM
       mc = per_sm * n_sm;
-      occupancy_cache_put(dev, (smw ? 1 : 0) + (tc ? 2 : 0), smem, mc);
+      occupancy_cache_put(dev, (smw ? 1 : 0) + (tc ? 2 : 0) + (fast ? 4 : 0), smem, mc);
     }
     max_ctas = mc;
     if (tc && n_slices > max_ctas) { tc = false; continue; }   // catalogue too wide for one slice per CTA
@@ -518,6 +568,9 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.h2 = reinterpret_cast<float*>(((uintptr_t)(A.list + 2 * (size_t)env->n_env) + 63) & ~(uintptr_t)63);
   A.H.h2_in = A.h2;
   A.H.part = reinterpret_cast<Partial*>(((uintptr_t)(A.h2 + (size_t)env->n_env * HID) + 63) & ~(uintptr_t)63);
+  A.h2_img = reinterpret_cast<char*>(
+      ((uintptr_t)(A.H.part + partial_capacity(env->n_env, pw->n_action)) + 127) & ~(uintptr_t)127);
+  A.trunk_img = reinterpret_cast<float*>(((uintptr_t)(A.h2_img + h2_image_bytes(env->n_env)) + 127) & ~(uintptr_t)127);
   A.tc_timeout = reinterpret_cast<int*>(wsp + 128);
   if ((int64_t)(grid + 96) * BM > partial_capacity(env->n_env, pw->n_action)) {
     cirs_set_error("cirs_rollout_kuaishou: workspace too small for this grid");
@@ -530,8 +583,9 @@ extern "C" int cirs_rollout_kuaishou(const cirs_kuaishou_env* env, const cirs_tr
   A.row_floats = row_floats;
   void* params[] = {&A};
   const bool prof = cirs_profile_begin("rollout_kuaishou_kernel", (cudaStream_t)stream);
-  void* fn = tc ? (smw ? (void*)rollout_kuaishou_kernel<true, true> : (void*)rollout_kuaishou_kernel<false, true>)
-                : (smw ? (void*)rollout_kuaishou_kernel<true, false> : (void*)rollout_kuaishou_kernel<false, false>);
+  void* fn = fast ? (void*)rollout_kuaishou_kernel<true, true, true>
+             : tc ? (smw ? (void*)rollout_kuaishou_kernel<true, true> : (void*)rollout_kuaishou_kernel<false, true>)
+                  : (smw ? (void*)rollout_kuaishou_kernel<true, false> : (void*)rollout_kuaishou_kernel<false, false>);
   cudaError_t err = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), params, smem, (cudaStream_t)stream);
   cirs_note_launch();
   if (prof) cirs_profile_end((cudaStream_t)stream);

@@ -555,16 +555,17 @@ def pol_split(n, size):
     return split_sizes(n, size)
 
 
-def test_rollout_inverse_cdf_sampler_distribution(H):
-    """The persistent rollout samples by inverse CDF over the catalogue-slice partials (actor_combine_icdf_warp) when a
-    turn has many running environments (>= 5 row tiles; 16384 here): the first actions of many environments that share
-    one user (hence one state) must follow the oracle's softmax probabilities, be reproducible for a fixed seed /
-    counter, and change when the counter advances."""
+@pytest.mark.parametrize("B", [16384, 3000])
+def test_rollout_inverse_cdf_sampler_distribution(H, B):
+    """The persistent rollout's tensor-core head samples with the two-level sampler (actor_tc_dev.cuh: inverse CDF inside
+    a 40-column unit of the catalogue, exponential race across the units) instead of one race draw per item: the first
+    actions of many environments that share one user (hence one state) must follow the oracle's softmax probabilities,
+    be reproducible for a fixed seed / counter, and change when the counter advances.  16384 rows = 128 pipelined row
+    tiles per CTA; 3000 rows = a ragged last tile."""
     import cirs_codes_b200 as cb
     from oracle import nets
     z = G.load("kuaishou_N1")
     c = G.cfg(z)
-    B = 16384
     outs = []
     for rep in range(2):
         env, trk = H.make_env(z, c, B=B), H.make_tracker(z, c, B=B)
