@@ -333,10 +333,26 @@ __device__ __forceinline__ int actor_combine_warp(const HeadArgs& P, int k, int 
   const int id = P.gather ? P.gather[k] : k;
   float m = -INFINITY, z = 0.f, bs = -INFINITY, bl = 0.f;
   int bi = 0x7fffffff;
-  for (int s = lane; s < P.n_split; s += 32) {
-    const Partial p = P.part[(size_t)s * P.n_rows + k];
-    merge_ms(m, z, p.m, p.z);
-    merge_best(bs, bl, bi, p.best_s, p.best_l, p.best_i);
+  if (P.n_split <= 160) {   // all of the lane's partials in flight at once (one L2 round trip instead of five)
+    Partial pp[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int s = lane + 32 * i;
+      if (s < P.n_split) pp[i] = P.part[(size_t)s * P.n_rows + k];
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      if (lane + 32 * i < P.n_split) {
+        merge_ms(m, z, pp[i].m, pp[i].z);
+        merge_best(bs, bl, bi, pp[i].best_s, pp[i].best_l, pp[i].best_i);
+      }
+    }
+  } else {
+    for (int s = lane; s < P.n_split; s += 32) {
+      const Partial p = P.part[(size_t)s * P.n_rows + k];
+      merge_ms(m, z, p.m, p.z);
+      merge_best(bs, bl, bi, p.best_s, p.best_l, p.best_i);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -22,17 +22,42 @@ __device__ __forceinline__ void kuaishou_reset_warp(const cirs_kuaishou_env& E, 
   }
 }
 
+// The part of a transition that does not depend on the action, as loads a caller can issue EARLY (the persistent
+// rollout issues them before it merges the head's partials, so that their L2 round trips overlap that merge): turn,
+// user, the lane's slot of the first 32 history entries with its category mask, the user's alpha, the running return.
+struct StepPre {
+  int t, u, hj;
+  uint32_t mj;
+  float alpha;
+  double cum;
+};
+__device__ __forceinline__ StepPre kuaishou_step_pre(const cirs_kuaishou_env& E, int e, int lane) {
+  StepPre P;
+  P.t = E.turn[e];
+  P.u = E.user[e];
+  P.hj = lane < E.max_turn ? E.hist[(size_t)e * E.max_turn + lane] : 0;   // slots >= t hold 0 (reset) or stale ids: valid indices
+  P.cum = E.cum_rew[e];
+  P.mj = __ldg(E.cat_mask + P.hj);
+  P.alpha = E.alpha_u ? __ldg(E.alpha_u + P.u) : 1.f;
+  return P;
+}
+
 // one transition of environment slot e by one warp (row k of the call's rew / done outputs); action a.
-// Returns true when the episode ended.  n_active (optional) is decremented when it does.
+// Returns true when the episode ended.  n_active (optional) is decremented when it does.  pre (optional): the result of
+// kuaishou_step_pre for this slot, r_out (optional): the reward (lane 0).
 __device__ __forceinline__ bool kuaishou_step_warp(const cirs_kuaishou_env& E, int e, int k, int a, int lane,
                                                    uint8_t* __restrict__ active, float* __restrict__ rew,
                                                    uint8_t* __restrict__ done, int traj_len,
                                                    int32_t* __restrict__ traj_act, float* __restrict__ traj_rew,
                                                    uint8_t* __restrict__ traj_done, int32_t* __restrict__ ep_len,
-                                                   int force_length, int* __restrict__ n_active) {
+                                                   int force_length, int* __restrict__ n_active,
+                                                   const StepPre* pre = nullptr, float* r_out = nullptr) {
   const int T = E.max_turn, N = E.num_leave_compute;
-  const int t = E.turn[e], u = E.user[e];
+  const int t = pre ? pre->t : E.turn[e], u = pre ? pre->u : E.user[e];
+  // everything that depends on the action, issued together (one round trip)
   const uint32_t ma = __ldg(E.cat_mask + a);
+  const float tab = __ldg((E.simulated ? E.normed_mat : E.mat) + (size_t)u * E.n_item + a);
+  const float beta = (E.simulated && E.alpha_u) ? __ldg(E.beta_i + a) : 1.f;
   const int32_t* hist = E.hist + (size_t)e * T;
 
   // window of the exit test: seq[t-N : t] with Python's negative-slice wrap when t < N (kuaishouEnv.py:203)
@@ -48,7 +73,10 @@ __device__ __forceinline__ bool kuaishou_step_warp(const cirs_kuaishou_env& E, i
     const bool valid = j < t;
     int hj = 0;
     uint32_t mj = 0u;
-    if (valid) {
+    if (pre && j0 == 0) {
+      hj = pre->hj;
+      mj = pre->mj;
+    } else if (valid) {
       hj = hist[j];
       mj = __ldg(E.cat_mask + hj);
     }
@@ -74,7 +102,7 @@ __device__ __forceinline__ bool kuaishou_step_warp(const cirs_kuaishou_env& E, i
       for (int j0 = (w_lo & ~31); j0 < t; j0 += 32) {
         const int j = j0 + lane;
         bool hit = false;
-        if (j >= w_lo && j < t) hit = (__ldg(E.cat_mask + hist[j]) >> c) & 1u;
+        if (j >= w_lo && j < t) hit = ((pre && j0 == 0 ? pre->mj : __ldg(E.cat_mask + hist[j])) >> c) & 1u;
         cnt += __popc(__ballot_sync(FULL_MASK, hit));
       }
       if ((float)cnt > E.leave_threshold) leave = true;
@@ -87,21 +115,22 @@ __device__ __forceinline__ bool kuaishou_step_warp(const cirs_kuaishou_env& E, i
   if (lane == 0) {
     float r;
     if (!E.simulated) {
-      r = __ldg(E.mat + (size_t)u * E.n_item + a);  // kuaishouEnv.py:171
+      r = tab;  // kuaishouEnv.py:171
     } else {
       double ex = (t == 0 || E.tau <= 0.f) ? 0.0 : expo;
-      if (E.alpha_u) ex = ex * (double)__ldg(E.alpha_u + u) * (double)__ldg(E.beta_i + a);
+      if (E.alpha_u) ex = ex * (double)(pre ? pre->alpha : __ldg(E.alpha_u + u)) * (double)beta;
       ex *= (double)E.gamma_exposure;
-      const double pr = (double)__ldg(E.normed_mat + (size_t)u * E.n_item + a);
+      const double pr = (double)tab;
       double rr = (E.version == 1) ? pr / (1.0 + ex) : (pr - ex);  // clip0 is an identity, util.py:53-54
       if (E.r_decay != 1.0f) rr *= pow((double)E.r_decay, (double)n_prev);
       r = (float)rr;
     }
     if (t < T) E.hist[(size_t)e * T + t] = a;
     E.turn[e] = t + 1;
-    E.cum_rew[e] += (double)r;
+    E.cum_rew[e] = (pre ? pre->cum : E.cum_rew[e]) + (double)r;
     if (E.seen) E.seen[(size_t)e * ((E.n_item + 31) >> 5) + (a >> 5)] |= (1u << (a & 31));
     rew[k] = r;
+    if (r_out) *r_out = r;
     done[k] = d ? 1 : 0;
     if (traj_act && t < traj_len) {
       traj_act[(size_t)e * traj_len + t] = a;

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
                                   row_r, row_kn, A.kcache, A.vcache, smem_dyn, A.row_floats, A.cur_state, A.traj_len,
                                   A.traj_obs, A.traj_obs_next, nullptr, 0, A.value, [&](int r, int o, float v) {
                                     if (row_kn[r] >= 0) cirs_actor_tc::h2_image_store(A.h2_img, row_kn[r], o, v);
-                                  });
+                                  }, false, [] {});
     } else {
       const int off = cirs_tracker::tracker_token_cta<SMW>(sT, B, R, 0, row_e, row_a, row_r, A.kcache, A.vcache, smem_dyn,
                                                            A.row_floats, A.cur_state, A.traj_len, A.traj_obs,
@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       const int R = min(RB, (left + (int)gridDim.x - 1) / (int)gridDim.x);
       // stage stamps of CTA 0's first pass of the LAST turn played so far: dbg[1 + 3 * 512 ..) = {start, after combine +
       // env, 18 token stamps, after trunk}
-      long long* tq = (timer || (blockIdx.x == 0)) && j0 == 0 ? A.dbg + 1 + 3 * 512 : nullptr;
+      // (turn 0's stamps are kept separately at + 64: the turn with the most rows per CTA)
+      long long* tq = (timer || (blockIdx.x == 0)) && j0 == 0 ? A.dbg + 1 + 3 * 512 + (t == 0 ? 64 : 0) : nullptr;
       if (tq && tid == 0) tq[0] = gtime_ns();
       // this turn's position is t + 1: the cached positions 0 .. t of the rows and the trunk's weights are fetched
       // into shared memory in the background (cp.async) while the rows' warps merge the head partials and step the
@@ -326,33 +327,42 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
       const int kv_ld = A.T.d + 4;
       const bool kv_fit = A.kv_off >= 0 && (A.T.d & 3) == 0 &&
                           (int64_t)R * A.T.nlayers * 2 * p * kv_ld <= (int64_t)A.kv_cap;
-      if (warp < R && lane == 0) row_e[warp] = H.gather[blockIdx.x + (j0 + warp) * gridDim.x];
-      __syncthreads();
       if (FAST) {
         if (j0 == 0)
           for (int i = tid; i < cirs_tfast::TR_FLOATS / 4; i += NT)
             cp_async16(smem_dyn + A.trunk_w_off + 4 * i, A.trunk_img + 4 * i);
       } else if (A.trunk_w_off >= 0 && j0 == 0) prefetch_trunk(A.H.W, smem_dyn + A.trunk_w_off);
+      if (warp < R && lane == 0) row_e[warp] = H.gather[blockIdx.x + (j0 + warp) * gridDim.x];
+      __syncthreads();
       if (kv_fit) prefetch_kv(A.T, B, R, row_e, p, A.kcache, A.vcache, smem_dyn + A.kv_off, kv_ld);
       cp_async_commit();
+      int kn = -1, my_e = -1;   // lane 0 of a row's warp: the row's slot in the next turn's list (published late)
       if (warp < R) {
         const int k = blockIdx.x + (j0 + warp) * gridDim.x;
         const int e = row_e[warp];
+        // the action-independent loads of the environment step go out before the partial merge
+        const cirs_env::StepPre pre = cirs_env::kuaishou_step_pre(A.E, e, lane);
         int a;
         if (TC || !H.icdf) a = actor_combine_warp(H, k, lane, A.act, A.logp);
         else a = actor_combine_icdf_warp<8>(H, k, lane, A.act, A.logp, A.h2 + (size_t)e * HID,
                                             H.tiles_per_split * BN, turn_off);
+        float4 emb = make_float4(0.f, 0.f, 0.f, 0.f);   // FAST: the action's embedding row, in flight behind the env step
+        if (FAST && lane < 8) emb = __ldg(reinterpret_cast<const float4*>(A.T.emb_item + (size_t)a * 32) + lane);
+        float r = 0.f;
         const bool d = cirs_env::kuaishou_step_warp(A.E, e, e, a, lane, A.active, A.rew, A.done, A.traj_len,
                                                     A.traj_act, A.traj_rew, A.traj_done, A.ep_len, A.force_length,
-                                                    A.n_active);
+                                                    A.n_active, &pre, &r);
+        if (FAST && lane < 8)
+          *reinterpret_cast<float4*>(smem_dyn + (size_t)warp * A.row_floats + cirs_tfast::EMB_OFF + 4 * lane) = emb;
         __syncwarp();
         if (lane == 0) {
-          int kn = -1;
-          if (!d) {
-            kn = atomicAdd(A.count + ((t + 1) & 1), 1);
-            list_next[kn] = e;
+          if (!d) kn = atomicAdd(A.count + ((t + 1) & 1), 1);
+          my_e = e;
+          row_a[warp] = a; row_r[warp] = r;
+          if (!FAST) {
+            if (kn >= 0) list_next[kn] = e;
+            row_kn[warp] = kn;
           }
-          row_e[warp] = e; row_a[warp] = a; row_r[warp] = A.rew[e]; row_kn[warp] = kn;
         }
       }
       cp_async_wait_all();
@@ -364,6 +374,13 @@ __global__ void __launch_bounds__(NT, (SMW || TC) ? 1 : 2) rollout_kuaishou_kern
                                     A.traj_obs, A.traj_obs_next, kv_fit ? smem_dyn + A.kv_off : nullptr, kv_ld, A.value,
                                     [&](int r, int o, float v) {
                                       if (row_kn[r] >= 0) cirs_actor_tc::h2_image_store(A.h2_img, row_kn[r], o, v);
+                                    },
+                                    true,
+                                    [&] {   // the list slot's atomic has had the whole token step to return
+                                      if (my_e >= 0) {
+                                        row_kn[warp] = kn;
+                                        if (kn >= 0) list_next[kn] = my_e;
+                                      }
                                     },
                                     tq ? tq + 2 : nullptr);
       } else {

@@ -111,6 +111,8 @@ __device__ __forceinline__ void stage_trunk(const cirs_policy_weights& P, float*
 
 // ep(r, o, b[o] + sum_k W[o][k] x[r][k]) for r < R, o < NO; W [NO][NI] transposed in shared memory, x[r] at
 // xin + r * stride (16-byte aligned, NI floats).  NI, NO multiples of 32.  Ends with a barrier.
+// (Unrolling several passes per trip for instruction-level parallelism was measured SLOWER, 453 vs 429 us per rollout:
+// the token step is bound by the number of instructions on its critical path, not by their latencies.)
 template <int NI, int NO, class Ep>
 __device__ __forceinline__ void mv(const float* W, const float* b, const float* xin, int stride, int R, Ep ep) {
   const int tid = threadIdx.x, ks = tid & 7;
@@ -159,7 +161,10 @@ __device__ __forceinline__ void ln(float* sc, int stride, int out_off, int x_off
 // the last 128 floats of a row = h1 | h2).  ws / L: staged tracker weights; ts: staged trunk image.  kv_s: the rows'
 // cached positions prefetched by the caller (as in tracker_cta_dev.cuh), or NULL.  h2_img: tensor-core head's tile
 // images (actor_tc_dev.cuh); h2_out [n_env][64] otherwise.
-template <class H2Store>
+// emb_ready: the caller already put the ids' embedding rows at sc[r * stride + EMB_OFF .. + 32) (and synchronised).
+// before_trunk(): called by every thread after the decoder stage (the caller's last chance to publish row_kn).
+constexpr int EMB_OFF = 100;   // Y + 4
+template <class H2Store, class Hook>
 __device__ __forceinline__ void token_and_trunk(const cirs_tracker_weights& W, const Layout& L, const float* ws,
                                                 const float* ts, int n_env, int R, int p, const int* row_e,
                                                 const int* row_id, const float* row_rew, const int* row_kn,
@@ -167,7 +172,8 @@ __device__ __forceinline__ void token_and_trunk(const cirs_tracker_weights& W, c
                                                 int stride, float* __restrict__ cur_state, int traj_len,
                                                 float* __restrict__ traj_obs, float* __restrict__ traj_obs_next,
                                                 const float* kv_s, int kv_ld, float* __restrict__ value_out,
-                                                H2Store h2_store, long long* tq = nullptr) {
+                                                H2Store h2_store, bool emb_ready, Hook before_trunk,
+                                                long long* tq = nullptr) {
   int tqi = 0;
   auto stamp = [&]() {
     if (tq && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); tq[tqi] = t_; }
@@ -182,12 +188,15 @@ __device__ __forceinline__ void token_and_trunk(const cirs_tracker_weights& W, c
   const float sq = 5.656854249492380f;   // sqrt(32)
 
   // ---- token input: the id's embedding row -> Y + 4 (16-byte aligned), then the gate / user projection
-  if (tid < R * 8) {
-    const int r = tid >> 3, c4 = tid & 7;
-    const float* src = (p == 0 ? W.emb_user : W.emb_item) + (size_t)row_id[r] * D + 4 * c4;
-    *reinterpret_cast<float4*>(sc + (size_t)r * stride + Y + 4 + 4 * c4) = __ldg(reinterpret_cast<const float4*>(src));
+  static_assert(EMB_OFF == Y + 4, "embedding row offset");
+  if (!emb_ready) {
+    if (tid < R * 8) {
+      const int r = tid >> 3, c4 = tid & 7;
+      const float* src = (p == 0 ? W.emb_user : W.emb_item) + (size_t)row_id[r] * D + 4 * c4;
+      *reinterpret_cast<float4*>(sc + (size_t)r * stride + Y + 4 + 4 * c4) = __ldg(reinterpret_cast<const float4*>(src));
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (p == 0) {
     mv<D, D>(ws + L.user_w, ws + L.user_b, sc + Y + 4, stride, R, [&](int r, int o, float a) {
       sc[(size_t)r * stride + X + o] = a * sq + __ldg(W.pe + o);
@@ -289,6 +298,7 @@ __device__ __forceinline__ void token_and_trunk(const cirs_tracker_weights& W, c
   });
   stamp();
   stamp();
+  before_trunk();
   // ---- policy trunk + critic of the new state (core/policy/ppo.py:122-126: preprocess Net, Critic head)
   mv<32, HIDP>(ts + TR_W1, ts + TR_B1, sc + YB, stride, R,
                [&](int r, int o, float a) { sc[(size_t)r * stride + H1 + o] = fmaxf(a, 0.f); });

@@ -47,11 +47,12 @@ r = col.collect(n_episode=B, users=rng.integers(0, cfg["U"], size=B))
 dbg = col._f["ws_roll"][256:256 + 8 * (1 + 6 * 512)].view(torch.int64).cpu().numpy()
 nt = int(dbg[0]); print("persistent turns", nt, "lens max", r["turns"])
 for t in range(nt): print(f"  turn {t:2d} n_act {dbg[1+3*t]:5d}  phaseA {dbg[2+3*t]/1e3:7.1f} us  phaseB {dbg[3+3*t]/1e3:7.1f} us")
-tq = dbg[1 + 3 * 512: 1 + 3 * 512 + 23]
 names = ["combine+env", "(token entry)", "tok-in"] + [f"L{l}:{n}" for l in range(2) for n in ("inproj", "attn", "outproj", "ln1", "l1", "l2", "ln2")] + ["dec+store", "(dup)"]
-print("phase-B stage times of CTA 0, last turn (us):")
-for i in range(1, 20): print(f"   {names[i-1]}: {(tq[i]-tq[i-1])/1e3:.2f}")
-print(f"   trunk: {(tq[22]-tq[19])/1e3:.2f}   total {(tq[22]-tq[0])/1e3:.2f}")
+for label, base in (("last turn", 1 + 3 * 512), ("turn 0", 1 + 3 * 512 + 64)):
+    tq = dbg[base: base + 23]
+    print(f"phase-B stage times of CTA 0, {label} (us):")
+    print("   " + "  ".join(f"{names[i-1]} {(tq[i]-tq[i-1])/1e3:.2f}" for i in range(1, 20)))
+    print(f"   trunk: {(tq[22]-tq[19])/1e3:.2f}   total {(tq[22]-tq[0])/1e3:.2f}")
 
 ta = dbg[1 + 3 * 512 + 32: 1 + 3 * 512 + 32 + 7]
 print("phase-A stamps of CTA 0, last turn (us): turn start -> entry %.2f, stage h2 tile %.2f, MMA %.2f, epilogue %.2f, merge+partials %.2f, fence+grid.sync %.2f" % (
