@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "tc_dev.cuh"
 #include "head_tc.cuh"
+#include "../../include/cirs_b200.h"
 #include <stdlib.h>
 
 namespace cirs_head_tc {
@@ -62,14 +63,14 @@ __host__ __device__ inline int64_t img_k_off(int64_t n64, int64_t ct) { return n
 __host__ __device__ inline int64_t img_a_off(int64_t n64, int64_t c128) { return 2 * n64 * IMG_B + c128 * IMG_A; }
 __host__ __device__ inline int64_t img_bias_off(int64_t n64) { return 2 * n64 * IMG_B + (n64 / 2) * IMG_A; }   // [ldA] bias, MASKED padding
 
-__global__ void __launch_bounds__(256)
-head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, const float* __restrict__ b3, int nA,
-                    float* __restrict__ img) {
-  __shared__ float s[HID][TN + 1];   // s[k][col]
-  const int ct = blockIdx.x, tid = threadIdx.x, c0 = ct * TN;
+// one 64-column catalogue tile ct by the whole CTA (any block size); s: [HID][TN + 1] floats of shared memory
+__device__ __forceinline__ void pack_w3_tile(int ct, const float* __restrict__ w3t, int64_t ldA,
+                                             const float* __restrict__ b3, int nA, float* __restrict__ img,
+                                             float (*s)[TN + 1]) {
+  const int tid = threadIdx.x, nthr = blockDim.x, c0 = ct * TN;
   const int64_t n64 = ldA / TN;
   if (tid < TN) img[img_bias_off(n64) + c0 + tid] = c0 + tid < nA ? __ldg(b3 + c0 + tid) : MASKED;
-  for (int i = tid; i < HID * TN / 4; i += 256) {
+  for (int i = tid; i < HID * TN / 4; i += nthr) {
     const int k = i / (TN / 4), c4 = i % (TN / 4);
     const float4 v = __ldg(reinterpret_cast<const float4*>(w3t + (size_t)k * ldA + c0) + c4);
     s[k][4 * c4] = v.x; s[k][4 * c4 + 1] = v.y; s[k][4 * c4 + 2] = v.z; s[k][4 * c4 + 3] = v.w;
@@ -85,7 +86,7 @@ head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, const float* __r
     h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
   };
-  for (int i = tid; i < HID * TN / 4; i += 256) {
+  for (int i = tid; i < HID * TN / 4; i += nthr) {
     // 16-byte chunk i of a 64-row tile: chunk column c4 = i / 64, tile row r = i % 64 (tile_chunk_off)
     const int c4 = i / TN, r = i % TN;
     float4 h, l;
@@ -96,6 +97,12 @@ head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, const float* __r
     split4(make_float4(s[r][4 * c4], s[r][4 * c4 + 1], s[r][4 * c4 + 2], s[r][4 * c4 + 3]), h, l);   // row = hidden r
     k_hi[i] = h; k_lo[i] = l;
   }
+}
+__global__ void __launch_bounds__(256)
+head_tc_pack_kernel(const float* __restrict__ w3t, int64_t ldA, const float* __restrict__ b3, int nA,
+                    float* __restrict__ img) {
+  __shared__ float s[HID][TN + 1];   // s[k][col]
+  pack_w3_tile(blockIdx.x, w3t, ldA, b3, nA, img, s);
 }
 
 // h2 [n, 64]: for every 64-row tile t  Hn[t] = { hi, lo } with tile row = row, tile column = hidden (B operand of pass
@@ -135,6 +142,116 @@ head_tc_pack_h2_kernel(const float* __restrict__ h2, int n, float* __restrict__ 
     const int ia = c4 * TM + (t & 1) * TN + r;
     a_hi[ia] = h; a_lo[ia] = l;
     split4(make_float4(s[4 * c4][r], s[4 * c4 + 1][r], s[4 * c4 + 2][r], s[4 * c4 + 3][r]), h, l);   // row = hidden r
+    t_hi[i] = h; t_lo[i] = l;
+  }
+}
+
+// ---- front end of a pass over n rows in ONE launch (replaces trunk_fwd_kernel + head_tc_pack_h2 + head_tc_pack):
+//   CTAs [0, n_pack)   re-split W3 into its operand-tile images (pack_w3_tile) -- concurrently with
+//   CTAs [n_pack, ..)  the policy trunk (Net 2 x Linear + ReLU, Critic head; core/policy/ppo.py:122-126 through
+//                      tianshou Net / Critic) of one 64-row tile each, two 256-thread halves of 32 rows, which then
+//                      write the tile's h2 straight out of shared memory as (hi, lo) operand-tile images.
+// Accumulation order of the trunk (bias first, k ascending, fmaf) is the one of actor_trunk_warp / trunk_fwd_kernel:
+// bit-identical h2.
+constexpr int FRONT_NT = 512;
+constexpr size_t FRONT_SMEM = sizeof(float) * (32 * HID + HID * HID + 2 * 32 * 33 + 2 * HID * 33);
+__global__ void __launch_bounds__(FRONT_NT)
+head_tc_front_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, const float* __restrict__ obs,
+                     float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ value,
+                     float* __restrict__ himg, int n_pack, float* __restrict__ img) {
+  extern __shared__ __align__(16) float fsm[];
+  if ((int)blockIdx.x < n_pack) {
+    pack_w3_tile(blockIdx.x, W.w3t, W.ld_action, W.b3, W.n_action, img, reinterpret_cast<float(*)[TN + 1]>(fsm));
+    return;
+  }
+  constexpr int R = 32;
+  float* s_w1 = fsm;                     // W1t [dim_state <= 32][64]
+  float* s_w2 = s_w1 + 32 * HID;         // W2t [64][64]
+  const int tid = threadIdx.x, half = tid >> 8, t = tid & 255, tile = blockIdx.x - n_pack, S = W.dim_state;
+  float(*s_in)[33] = reinterpret_cast<float(*)[33]>(s_w2 + HID * HID + half * 32 * 33);
+  float(*hT)[R + 1] = reinterpret_cast<float(*)[R + 1]>(s_w2 + HID * HID + 2 * 32 * 33 + half * HID * 33);
+  const int r0 = tile * TN + half * R;
+  for (int i = tid; i < S * HID / 4; i += FRONT_NT) reinterpret_cast<float4*>(s_w1)[i] = __ldg(reinterpret_cast<const float4*>(W.w1t) + i);
+  for (int i = tid; i < HID * HID / 4; i += FRONT_NT) reinterpret_cast<float4*>(s_w2)[i] = __ldg(reinterpret_cast<const float4*>(W.w2t) + i);
+  for (int i = t; i < R * S; i += 256) {
+    const int r = i / S, c = i % S;
+    s_in[r][c] = (r0 + r < n) ? obs[(int64_t)(idx ? idx[r0 + r] : r0 + r) * S + c] : 0.f;
+  }
+  __syncthreads();
+  const int row = t % R, og = t / R;   // og: outputs og*8 .. og*8+7 (uniform per warp)
+  const bool ok = r0 + row < n;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = __ldg(W.b1 + og * 8 + j);
+#pragma unroll 4
+  for (int k = 0; k < S; ++k) {
+    const float x = s_in[row][k];
+    const float4 w0 = *reinterpret_cast<const float4*>(s_w1 + k * HID + og * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(s_w1 + k * HID + og * 8 + 4);
+    acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+    acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] = fmaxf(acc[j], 0.f);
+    hT[og * 8 + j][row] = acc[j];
+  }
+  if (ok && h1) {
+    float4* d = reinterpret_cast<float4*>(h1 + (int64_t)(r0 + row) * HID + og * 8);
+    d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = __ldg(W.b2 + og * 8 + j);
+#pragma unroll 8
+  for (int k = 0; k < HID; ++k) {
+    const float x = hT[k][row];
+    const float4 w0 = *reinterpret_cast<const float4*>(s_w2 + k * HID + og * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(s_w2 + k * HID + og * 8 + 4);
+    acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+    acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] = ok ? fmaxf(acc[j], 0.f) : 0.f;   // rows beyond n are zero in the images
+    hT[og * 8 + j][row] = acc[j];
+  }
+  if (ok) {
+    float4* d = reinterpret_cast<float4*>(h2 + (int64_t)(r0 + row) * HID + og * 8);
+    d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+  if (t < R && r0 + t < n) {
+    float v = __ldg(W.bv);
+    for (int k = 0; k < HID; ++k) v = fmaf(hT[k][t], __ldg(W.wv + k), v);
+    value[r0 + t] = v;
+  }
+  if (!himg) return;
+  // ---- the tile's h2 images (layout of head_tc_pack_h2_kernel); element (row r, hidden k) = hT of half r / 32
+  float(*hA)[R + 1] = reinterpret_cast<float(*)[R + 1]>(s_w2 + HID * HID + 2 * 32 * 33);
+  auto Hrk = [&](int r, int k) { return hA[(r >> 5) * HID + k][r & 31]; };
+  const int64_t n64 = h2_tiles64(n);
+  float4* n_hi = reinterpret_cast<float4*>(himg + himg_n_off(tile));
+  float4* n_lo = n_hi + B_BYTES / 16;
+  float4* t_hi = reinterpret_cast<float4*>(himg + himg_t_off(n64, tile));
+  float4* t_lo = t_hi + B_BYTES / 16;
+  float4* a_hi = reinterpret_cast<float4*>(himg + himg_a_off(n64, tile >> 1));
+  float4* a_lo = a_hi + A_BYTES / 16;
+  auto split4 = [](float4 v, float4& h, float4& l) {
+    h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    l = make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
+  };
+  for (int i = tid; i < TN * HID / 4; i += FRONT_NT) {
+    const int c4 = i / TN, r = i % TN;
+    float4 h, l;
+    split4(make_float4(Hrk(r, 4 * c4), Hrk(r, 4 * c4 + 1), Hrk(r, 4 * c4 + 2), Hrk(r, 4 * c4 + 3)), h, l);   // row = row r
+    n_hi[i] = h; n_lo[i] = l;
+    const int ia = c4 * TM + (tile & 1) * TN + r;
+    a_hi[ia] = h; a_lo[ia] = l;
+    split4(make_float4(Hrk(4 * c4, r), Hrk(4 * c4 + 1, r), Hrk(4 * c4 + 2, r), Hrk(4 * c4 + 3, r)), h, l);   // row = hidden r
     t_hi[i] = h; t_lo[i] = l;
   }
 }
@@ -970,6 +1087,21 @@ int64_t head_tc_h2_image_floats(int64_t n) {
 
 int head_tc_pack_h2(const float* h2, int n, float* himg, cudaStream_t st) {
   CIRS_LAUNCH(head_tc_pack_h2_kernel, (int)h2_tiles64(n), 256, 0, st, h2, n, himg);
+  CIRS_CHECK_LAUNCH();
+  return CIRS_OK;
+}
+
+int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const float* obs, float* h1, float* h2,
+                  float* value, float* himg, float* img, cudaStream_t st) {
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(head_tc_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM);
+    once = true;
+  }
+  const int n_pack = img ? (int)(w->ld_action / TN) : 0;
+  const int tiles = himg ? (int)h2_tiles64(n) : (n + TN - 1) / TN;
+  CIRS_LAUNCH(head_tc_front_kernel, n_pack + tiles, FRONT_NT, FRONT_SMEM, st, *w, n, idx, obs, h1, h2, value, himg,
+              n_pack, img);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }

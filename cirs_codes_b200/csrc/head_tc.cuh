@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/cirs_b200.h"
+
 namespace cirs_head_tc {
 
 constexpr int MAX_SPLIT = 32;   // catalogue splits of passes F / B2 (partials per row)
@@ -37,6 +39,12 @@ int head_tc_pack(const float* w3t, int64_t ldA, const float* b3, int nA, float* 
 // images of the trunk output h2 [n, 64] (rows beyond n are zero); rebuilt once per minibatch after the trunk forward
 int64_t head_tc_h2_image_floats(int64_t n);
 int head_tc_pack_h2(const float* h2, int n, float* himg, cudaStream_t st);
+
+// Front end of a pass in one launch: policy trunk of n gathered observation rows (h1 optional, h2, critic value), the
+// h2 images (himg, optional) written by the same CTAs, and -- concurrently, by further CTAs -- the W3 images (img,
+// optional; pass it whenever the weights changed since they were last packed).
+int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const float* obs, float* h1, float* h2,
+                  float* value, float* himg, float* img, cudaStream_t st);
 
 // number of catalogue splits used for n rows (<= MAX_SPLIT); partial arrays are [n, n_split]
 int plan_split(int n, int nA);

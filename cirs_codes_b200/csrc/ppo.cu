@@ -501,11 +501,20 @@ __global__ void __launch_bounds__(256) colsum32_kernel(int n, const float* __res
 
 // ---- deterministic reduction of the per-row loss terms -> losses[4] = {loss, clip, vf, ent} / n_global
 __global__ void __launch_bounds__(1024)
-loss_reduce_kernel(int n, int n_global, cirs_ppo_config cfg, const float* __restrict__ terms, float* losses) {
+loss_reduce_kernel(int n, int n_global, cirs_ppo_config cfg, const float* __restrict__ terms, float* losses,
+                   const float* __restrict__ ent_part = nullptr, int n_split = 0) {
+  // ent_part (tensor-core path): the rows' entropies still are per-split partials of pass B2, merged here
   __shared__ double sh[3][32];
   double a = 0, b = 0, c = 0;
   for (int r = threadIdx.x; r < n; r += 1024) {
-    a += terms[4 * r]; b += terms[4 * r + 1]; c += terms[4 * r + 2];
+    a += terms[4 * r]; b += terms[4 * r + 1];
+    if (ent_part) {
+      float e = 0.f;
+      for (int s = 0; s < n_split; ++s) e += ent_part[(int64_t)r * n_split + s];
+      c += e;
+    } else {
+      c += terms[4 * r + 2];
+    }
   }
   a = warp_sum_d(a); b = warp_sum_d(b); c = warp_sum_d(c);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -550,9 +559,12 @@ struct DlB {  // B(k = row, n = column): contiguous along n
 
 __global__ void __launch_bounds__(1024)
 adv_stats_kernel(const int32_t* __restrict__ mb_off, const int32_t* __restrict__ idx, const float* __restrict__ adv,
-                 double* __restrict__ stats) {
+                 double* __restrict__ stats, int n_rep_stride = 0) {
+  // blockIdx.y = repeat: its permutation starts n_rep_stride entries further, its statistics 3 * gridDim.x doubles further
   __shared__ double sh[2][32];
   const int j = blockIdx.x, b = mb_off[j], e = mb_off[j + 1];
+  idx += (size_t)blockIdx.y * n_rep_stride;
+  stats += (size_t)blockIdx.y * gridDim.x * 3;
   double s = 0, ss = 0;
   for (int i = b + threadIdx.x; i < e; i += 1024) {
     const double a = adv[idx[i]];
@@ -595,15 +607,12 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
   float *pm = take((int64_t)n * MAX_SPLIT), *ps = take((int64_t)n * MAX_SPLIT), *la = take(n);
   float* himg = take(head_tc_h2_image_floats(n));
   float* img = take(head_tc_image_floats(w->ld_action));
-  CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, row_idx, obs, h1, h2, vtmp);
-  CIRS_CHECK_LAUNCH();
+  // trunk, h2 images and W3 images in one launch (head_tc_front); a value-only evaluation needs the trunk alone
+  int rc = head_tc_front(w, n, row_idx, obs, h1, h2, vtmp, act ? himg : nullptr, act ? img : nullptr, st);
+  if (rc) return rc;
   int n_split = 0;
-  if (act) {   // log-probs of the stored actions; a value-only evaluation needs the trunk alone
+  if (act) {   // log-probs of the stored actions
     n_split = plan_split(n, w->n_action);
-    int rc = head_tc_pack(w->w3t, w->ld_action, w->b3, w->n_action, img, st);
-    if (rc) return rc;
-    rc = head_tc_pack_h2(h2, n, himg, st);
-    if (rc) return rc;
     HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action, img, himg};
     rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
     if (rc) return rc;
@@ -669,8 +678,14 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
   int tc_split = 0;
 
   // ---- forward
-  CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, idx, obs, ws.h1, ws.h2, ws.value);
-  CIRS_CHECK_LAUNCH();
+  const bool tc_path = !gauss && cfg->ent_coef == 0.f && cirs_head_tc::head_tc_enabled(n, nA, ldA);
+  if (tc_path) {   // trunk + h2 images + W3 images (the weights changed in the last Adam step) in one launch
+    int rc = cirs_head_tc::head_tc_front(w, n, idx, obs, ws.h1, ws.h2, ws.value, ws.h2img, ws.w3img, st);
+    if (rc) return rc;
+  } else {
+    CIRS_LAUNCH(trunk_fwd_kernel, (n + 31) / 32, 256, 0, st, *w, n, idx, obs, ws.h1, ws.h2, ws.value);
+    CIRS_CHECK_LAUNCH();
+  }
   if (gauss) {
     float* dz = ws.logits;                      // [n, 32] d loss / d z
     float* dsg = ws.logits + (int64_t)n * 32;   // [n, 32] d loss / d sigma_param, per row
@@ -690,25 +705,19 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
                                StoreEp{ws.dh2, HID, nullptr, 0, nullptr, nullptr, 0}, n, HID, nA, 1, nullptr, st,
                                "gauss_dh2_gemm");
     CIRS_CHECK_LAUNCH();
-  } else if (cfg->ent_coef == 0.f && cirs_head_tc::head_tc_enabled(n, nA, ldA)) {
+  } else if (tc_path) {
     // ---- actor head on the tensor cores: logits are recomputed per pass and never stored (head_tc.cu)
     tc = true;
     tc_split = cirs_head_tc::plan_split(n, nA);
-    int rc = cirs_head_tc::head_tc_pack(w->w3t, ldA, w->b3, nA, ws.w3img, st);   // the weights changed in the last Adam step
-    if (rc) return rc;
-    rc = cirs_head_tc::head_tc_pack_h2(ws.h2, n, ws.h2img, st);
-    if (rc) return rc;
     cirs_head_tc::HeadTc H{ws.h2, n, w->w3t, ldA, w->b3, nA, ws.w3img, ws.h2img};
-    rc = cirs_head_tc::head_tc_stats(H, idx, act, tc_split, ws.pm, ws.ps, ws.la, st);
+    int rc = cirs_head_tc::head_tc_stats(H, idx, act, tc_split, ws.pm, ws.ps, ws.la, st);
     if (rc) return rc;
     CIRS_LAUNCH(row_loss_tc_kernel, (n + 127) / 128, 128, 0, st, n, tc_split, *cfg, n_global, idx, act, adv, returns,
                 v_old, logp_old, adv_stat, ws);
     CIRS_CHECK_LAUNCH();
     rc = cirs_head_tc::head_tc_dh2(H, ws.rowm, ws.rinvz, ws.coef, ws.acta, tc_split, ws.dh2_part, ws.ent_part, st);
     if (rc) return rc;
-    CIRS_LAUNCH(ent_merge_kernel, (n + 255) / 256, 256, 0, st, n, tc_split, ws.ent_part, ws.terms);
-    CIRS_CHECK_LAUNCH();
-    CIRS_LAUNCH(loss_reduce_kernel, 1, 1024, 0, st, n, n_global, *cfg, ws.terms, losses);
+    CIRS_LAUNCH(loss_reduce_kernel, 1, 1024, 0, st, n, n_global, *cfg, ws.terms, losses, ws.ent_part, tc_split);
     CIRS_CHECK_LAUNCH();
     rc = cirs_head_tc::head_tc_dw3(H, ws.rowm, ws.rinvz, ws.coef, ws.acta, grads->w3t, grads->b3, st);
     if (rc) return rc;
@@ -763,9 +772,13 @@ extern "C" int cirs_ppo_learn(const cirs_policy_weights* w, const cirs_policy_we
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t n = mb_off_h[n_mb];
-  for (int r = 0; r < n_repeat; ++r) {
-    int rc = cirs_adv_stats(n_mb, mb_off, slots + (int64_t)r * n, adv, adv_stats + (int64_t)r * n_mb * 3, stream);
-    if (rc) return rc;
+  if (n_mb > 0 && n_repeat > 0) {   // every repeat's minibatch statistics in one launch
+    if (!adv) {
+      cirs_set_error("cirs_ppo_learn: bad argument");
+      return CIRS_ERR_ARG;
+    }
+    CIRS_LAUNCH(adv_stats_kernel, dim3(n_mb, n_repeat), 1024, 0, st, mb_off, slots, adv, adv_stats, n);
+    CIRS_CHECK_LAUNCH();
   }
   if (comm) {
     // n_stats_tail more doubles behind the statistics ride on the same collective (the raw return moments)

@@ -57,7 +57,7 @@ class StateTrackerTransformer:
         self.grad = torch.zeros_like(self.flat)
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
         self.opt_state = torch.zeros(2, dtype=torch.int32, device=self.device)
-        self.opt_scratch = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.opt_scratch = torch.zeros(16, dtype=torch.float64, device=self.device)
         self.lr = float(lr)
         self._w = params.tracker_struct(self.layout, self.flat, self.pe)
         self._g = params.tracker_struct(self.layout, self.grad, None)

@@ -399,7 +399,8 @@ int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_policy_weights* 
  * (the trunk shared by actor and critic, CIRS-RL-kuaishou.py:245-258): they count twice in the
  * norm, are scaled by coef^2, and receive two sequential Adam updates (step counter += 2).
  *   state   int32[2] on the device: {steps taken by ordinary tensors, steps taken by duplicated tensors}
- *   max_grad_norm <= 0 -> no clipping.   scratch: double[8] device scratch (squared norm, per-step bias corrections). */
+ *   max_grad_norm <= 0 -> no clipping.   scratch: double[16] device scratch, ZERO-INITIALISED by the caller once and
+ *   then left to this function (squared norm, per-step bias corrections, the fused kernel's alternating accumulators). */
 int cirs_clip_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t n_dup,
                    const cirs_ppo_config* cfg, int32_t* state, double* scratch, void* stream);
 
