@@ -390,7 +390,7 @@ def gpu_arm(args, cfg):
     n_tr = int(res0["n/st"])
     prng = np.random.default_rng(99 + rank)
     perms_h = [prng.permutation(n_tr).astype(np.int32) for _ in range(cfg["repeat"])]
-    perms_d = [torch.as_tensor(p, device=dev) for p in perms_h]
+    perms_d = torch.as_tensor(np.stack(perms_h), device=dev)   # [repeat, n] int32, resident: one gather launch
 
     def one_step(resident):
         res = col.collect(n_episode=B, users=users_d if resident else users_h)
@@ -563,6 +563,15 @@ def gpu_arm(args, cfg):
                     "env_steps_per_step": steps_e2e / args.steps, "ms_each_step_rank0": per_step_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
         }
+        try:   # the rollout kernel's own per-turn timers of the last collect (rollout.cu dbg block): where a launch goes
+            dbg = col._f["ws_roll"][256:256 + 8 * (1 + 6 * 512)].view(torch.int64).cpu().numpy()
+            nt = int(dbg[0])
+            if 0 < nt <= 512:
+                out["rollout_turns"] = {"turns": nt, "running": [int(dbg[1 + 3 * t]) for t in range(nt)],
+                                        "phase_a_us": [round(float(dbg[2 + 3 * t]) / 1e3, 1) for t in range(nt)],
+                                        "phase_b_us": [round(float(dbg[3 + 3 * t]) / 1e3, 1) for t in range(nt)]}
+        except Exception:
+            pass
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -31,6 +31,52 @@ from .env import KuaishouVectorEnv, TaobaoVectorEnv
 from .state_tracker import StateTrackerTransformer
 
 
+class _LazyResult(dict):
+    """The fused collect's result dict (core/collector.py:345-367 keys).  ``n/ep``, ``n/st`` and ``turns`` are there at
+    once; the completion-ordered ``rews / lens / idxs`` (by turn, then environment id, like the reference's loop) and
+    their means / deviations are filled in at the first access of any other key or of the dict as a whole."""
+    _LAZY = ("rews", "lens", "idxs", "rew", "len", "rew_std", "len_std")
+
+    def __init__(self, rews, lens, B, L):
+        super().__init__({"n/ep": len(lens), "n/st": int(lens.sum()), "turns": int(lens.max()) if len(lens) else 0})
+        self._raw = (rews, lens, B, L)
+
+    def _fill(self):
+        raw, self._raw = self._raw, None
+        if raw is None:
+            return
+        rews, lens, B, L = raw
+        order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
+        full = Collector._result(rews[order], lens[order], (np.arange(B) * L)[order])
+        for k in self._LAZY:
+            dict.__setitem__(self, k, full[k])
+
+    def __getitem__(self, k):
+        if self._raw is not None and k in self._LAZY:
+            self._fill()
+        return dict.__getitem__(self, k)
+
+    def get(self, k, default=None):
+        if self._raw is not None and k in self._LAZY:
+            self._fill()
+        return dict.get(self, k, default)
+
+    def __contains__(self, k):
+        return k in self._LAZY or dict.__contains__(self, k)
+
+    def _all(self):
+        self._fill()
+        return self
+
+    def keys(self): return dict.keys(self._all())          # noqa: E704
+    def items(self): return dict.items(self._all())        # noqa: E704
+    def values(self): return dict.values(self._all())      # noqa: E704
+    def __iter__(self): return dict.__iter__(self._all())  # noqa: E704
+    def __len__(self): return dict.__len__(self._all())    # noqa: E704
+    def __repr__(self): return dict.__repr__(self._all())  # noqa: E704
+    def copy(self): return dict(self._all())               # noqa: E704
+
+
 class Collector:
     def __init__(self, policy, env, buffer=None, preprocess_fn=None, exploration_noise=False,
                  remove_recommended_ids=False, force_length=0, fused=True, use_graph=True, persistent=True):
@@ -190,6 +236,7 @@ class Collector:
                            pin=torch.zeros(2 * T + 8, dtype=torch.int32).pin_memory(),
                            pin_users=torch.zeros(B, dtype=torch.int32).pin_memory(),
                            ev=[torch.cuda.Event() for _ in range(2 * T + 8)])
+            self._f["pin_users_np"] = self._f["pin_users"].numpy()
             self._graph = None
         return self._f
 
@@ -234,13 +281,13 @@ class Collector:
         if torch.is_tensor(users) and users.is_cuda:                # inputs already resident in HBM
             f["d_users"].copy_(users)
         else:
-            users = env.draw_users(B) if users is None else np.asarray(users, dtype=np.int64).reshape(-1)
-            f["pin_users"].copy_(torch.from_numpy(users.astype(np.int32)))
+            users = env.draw_users(B) if users is None else np.asarray(users).reshape(-1)
+            f["pin_users_np"][:] = users                            # pinned staging buffer (numpy view, no torch op)
             f["d_users"].copy_(f["pin_users"], non_blocking=True)   # pinned host -> device
             self.h2d_bytes += 4 * B
         self.data = Batch()
-        buf.reset()
-        trk.build_state(dim_batch=B, reset=True)       # K/V caches sized for THIS collector's environments
+        buf.reset(device_only=True)
+        trk.build_state(dim_batch=B, reset=True, zero_len=not self.persistent)   # K/V caches sized for THIS collector
         if self.persistent:
             # the whole rollout in ONE persistent cooperative kernel (csrc/rollout.cu)
             pol = self.policy
@@ -273,10 +320,9 @@ class Collector:
         lens, rews = self._read_back(buf.d_len, env.cum_rew, flag)  # the collect's D2H read (one synchronisation)
         self.d2h_bytes += 4 * B + 8 * B + 4
         buf.set_from_device(lens)
-        order = np.lexsort((np.arange(B), lens))                    # completion order: by turn, then env id
-        res = self._result(rews[order], lens[order], (np.arange(B) * L)[order])
-        res["turns"] = int(lens.max()) if len(lens) else 0
-        return res
+        # everything else the reference's result dict carries (completion-ordered copies, means / deviations) is
+        # computed when it is first read: it is logging data, and the update that follows must not wait for it
+        return _LazyResult(rews, lens, B, L)
 
     def _read_back(self, d_len, d_rew, d_flag=None):
         """Episode lengths (i32) and cumulative rewards (f64) -> pinned host buffers, asynchronous copies and ONE
@@ -287,15 +333,17 @@ class Collector:
             self._pin_out = (torch.zeros(B, dtype=torch.int32).pin_memory(),
                              torch.zeros(B, dtype=torch.float64).pin_memory(),
                              torch.zeros(1, dtype=torch.int32).pin_memory())
+            self._pin_np = tuple(t.numpy() for t in self._pin_out)
         p_len, p_rew, p_flag = self._pin_out
         p_len.copy_(d_len[:B], non_blocking=True)
         p_rew.copy_(d_rew[:B], non_blocking=True)
         if d_flag is not None:
             p_flag.copy_(d_flag, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        if d_flag is not None and int(p_flag[0]):
+        n_len, n_rew, n_flag = self._pin_np
+        if d_flag is not None and n_flag[0]:
             raise _lib.CirsError("cirs_rollout_kuaishou: a tcgen05 mbarrier wait timed out; the rollout is invalid")
-        return p_len.numpy().astype(np.int64), p_rew.numpy().copy()
+        return n_len.astype(np.int64), n_rew.copy()
 
     # ---- fused path, VirtualTaobao: the whole collect is ONE kernel, one warp per environment (csrc/rollout_taobao.cu)
     def _collect_fused_taobao(self, users):

@@ -1,4 +1,6 @@
 // Error reporting for the C ABI (include/cirs_b200.h): thread-local message + ABI version.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "../../include/cirs_b200.h"
@@ -49,6 +51,18 @@ extern "C" int cirs_profile_report(char* buf, int n) {
   cudaDeviceSynchronize();
   std::lock_guard<std::mutex> lk(g_prof_mu);
   std::map<std::string, std::pair<long long, double>> agg;
+  if (const char* path = getenv("CIRS_PROFILE_TIMELINE")) {   // debugging aid: "name start_us dur_us" per launch, in issue order
+    if (FILE* f = fopen(path, "a")) {
+      for (auto& r : g_prof) {
+        float t0 = 0.f, dt = 0.f;
+        cudaEventElapsedTime(&t0, g_prof.front().a, r.a);
+        cudaEventElapsedTime(&dt, r.a, r.b);
+        fprintf(f, "%s %.2f %.2f\n", r.name, t0 * 1e3, dt * 1e3);
+      }
+      fprintf(f, "--\n");
+      fclose(f);
+    }
+  }
   for (auto& r : g_prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& x = agg[r.name]; x.first++; x.second += ms; }

@@ -212,8 +212,12 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = fmaf(x, s_dz2[r][cq + j], acc[j]);
     }
+    // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the atomic traffic of scalar adds -- every CTA
+    // adds into the same 4096 addresses, so this phase is bound by the L2's atomic throughput
 #pragma unroll
-    for (int j = 0; j < 16; ++j) atomicAdd(G.w2t + (size_t)k * HID + cq + j, acc[j]);
+    for (int j = 0; j < 16; j += 4)
+      atomicAdd(reinterpret_cast<float4*>(G.w2t + (size_t)k * HID + cq + j),
+                make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
   }
   __syncthreads();   // s_t (h2) is consumed
   // dz1[r][k] = (sum_c dz2[r][c] W2t[k][c]) [h1 > 0]:  thread = (row, KPT consecutive k)
@@ -243,12 +247,16 @@ trunk_bwd_kernel(cirs_policy_weights W, cirs_policy_weights G, int n, const int3
     for (int r = 0; r < R; ++r) gb += s_t[r][tid];
     atomicAdd(G.b1 + tid, gb);
   }
-  for (int o = tid; o < S * HID; o += 256) {
-    const int sI = o / HID, c = o % HID;
-    float a = 0.f;
+  for (int o = tid; o < S * HID / 4; o += 256) {
+    const int sI = o / (HID / 4), c = (o % (HID / 4)) * 4;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-    for (int r = 0; r < R; ++r) a = fmaf(s_obs[r][sI], s_t[r][c], a);
-    atomicAdd(G.w1t + (size_t)sI * HID + c, a);
+    for (int r = 0; r < R; ++r) {
+      const float x = s_obs[r][sI];
+      a0 = fmaf(x, s_t[r][c], a0); a1 = fmaf(x, s_t[r][c + 1], a1);
+      a2 = fmaf(x, s_t[r][c + 2], a2); a3 = fmaf(x, s_t[r][c + 3], a3);
+    }
+    atomicAdd(reinterpret_cast<float4*>(G.w1t + (size_t)sI * HID + c), make_float4(a0, a1, a2, a3));
   }
   // d_obs[slot][s] = sum_c dz1[r][c] W1t[s][c]
   if (d_obs) {

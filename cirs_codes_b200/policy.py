@@ -494,7 +494,7 @@ class PPOPolicy:
 
     def update(self, sample_size, buffer, batch_size=None, repeat=1, perms=None, mb_sizes=None, **kwargs):
         """policy/base.py:219-244: sample(0) -> process_fn -> learn.  ``perms`` (one permutation of range(n) per
-        repeat: host arrays, or int32 CUDA tensors already resident in HBM) overrides np.random.permutation for
+        repeat: host arrays, int32 CUDA tensors, or one [repeat, n] int32 CUDA tensor already resident in HBM) overrides np.random.permutation for
         replayable parity runs and for the resident-input benchmark arm.  ``mb_sizes`` (tests only) replaces the
         minibatch sizes Batch.split would produce, so that one process can replay a data-parallel run's plan."""
         if buffer is None or len(buffer) == 0:
@@ -535,26 +535,46 @@ class PPOPolicy:
             sizes, n_glob_plan = plan_from_counts(self._n_all, dist.get_rank(self.group), batch_size)
         else:
             sizes = sharded_sizes(n, batch_size, dist if world > 1 else None, self.group, dev)
-        offs = np.zeros(len(sizes) + 1, dtype=np.int32)
-        offs[1:] = np.cumsum(sizes)
-        d_offs = self._h2d_i32(offs)                 # pinned, asynchronous: no host sync in front of the learn loop
         n_mb = len(sizes)
+        # ---- minibatch offsets and the repeats' permutations travel in ONE pinned staging buffer and ONE asynchronous
+        # copy: [offs (n_mb + 1, padded to 64) | perm_0 (n) | perm_1 (n) | ...]; the previous update's copy has completed
+        # (every update ends with a stream synchronisation for the losses), so the buffer can be rewritten
+        stacked = torch.is_tensor(perms) and perms.is_cuda     # [repeat, n] int32 already resident in HBM
+        host_perms = perms is None or not (stacked or (torch.is_tensor(perms[0]) and perms[0].is_cuda))
+        o_pad = (n_mb + 1 + 63) & ~63
+        need = o_pad + (repeat * n if host_perms else 0)
+        if getattr(self, "_stage_cap", 0) < need:
+            self._stage_cap = max(need, 2 * getattr(self, "_stage_cap", 0), 4096)
+            self._stage_pin = torch.empty(self._stage_cap, dtype=torch.int32).pin_memory()
+            self._stage_np = self._stage_pin.numpy()
+            self._stage_dev = torch.empty(self._stage_cap, dtype=torch.int32, device=dev)
+        sp = self._stage_np
+        sp[0] = 0
+        sp[1:n_mb + 1] = np.cumsum(sizes)
+        offs = sp[:n_mb + 1].copy()                  # host copy for the C loop's bounds
+        if host_perms:
+            for step in range(repeat):               # minibatch order of repeat ``step``: indices[perm]  (batch.py:736)
+                sp[o_pad + step * n:o_pad + (step + 1) * n] = \
+                    np.random.permutation(n) if perms is None else np.asarray(perms[step])
+            self.h2d_bytes += 4 * n * repeat
+        self._stage_dev[:need].copy_(self._stage_pin[:need], non_blocking=True)
+        self.h2d_bytes += 4 * (n_mb + 1)
+        d_offs_ptr = self._stage_dev.data_ptr()
         if getattr(self, "_learn_cap", (0, 0)) < (repeat * buffer.maxsize, repeat * (n_mb + 1)):
             self._learn_cap = (repeat * buffer.maxsize, repeat * (n_mb + 1))
             self._slots = torch.zeros(repeat * buffer.maxsize, dtype=torch.int32, device=dev)
             self._stats = torch.zeros(repeat * (n_mb + 1) * 3 + 3, dtype=torch.float64, device=dev)
             self._losses = torch.zeros(repeat * (n_mb + 1) * 4, dtype=torch.float32, device=dev)
-        d_slots, stats, losses = self._slots[:repeat * n], self._stats[:repeat * n_mb * 3], \
-            self._losses[:repeat * n_mb * 4]
-        for step in range(repeat):                  # minibatch order of repeat ``step``: indices[perm]  (batch.py:736)
-            if perms is not None and torch.is_tensor(perms[step]) and perms[step].is_cuda:
-                d_perm = perms[step]
-            else:
-                perm = np.asarray(perms[step]) if perms is not None else np.random.permutation(n)
-                d_perm = self._h2d_i32(perm)
-                self.h2d_bytes += 4 * n
-            assert d_perm.numel() == n and d_perm.dtype == torch.int32
-            _lib.call("cirs_gather_i32", d_slots.data_ptr() + 4 * n * step, _lib.ptr(indices), _lib.ptr(d_perm), n, st)
+        slots_ptr, stats_ptr, losses_ptr = self._slots.data_ptr(), self._stats.data_ptr(), self._losses.data_ptr()
+        if host_perms:                               # every repeat's slots in one launch
+            _lib.call("cirs_gather_i32", slots_ptr, _lib.ptr(indices), d_offs_ptr + 4 * o_pad, repeat * n, st)
+        elif stacked:
+            assert perms.shape == (repeat, n) and perms.dtype == torch.int32 and perms.is_contiguous()
+            _lib.call("cirs_gather_i32", slots_ptr, _lib.ptr(indices), _lib.ptr(perms), repeat * n, st)
+        else:
+            for step in range(repeat):
+                assert perms[step].numel() == n and perms[step].dtype == torch.int32
+                _lib.call("cirs_gather_i32", slots_ptr + 4 * n * step, _lib.ptr(indices), _lib.ptr(perms[step]), n, st)
 
         # a chunk of Batch.split(merge_last) never exceeds 2 * batch_size - 1 rows: size the workspace once
         ws = self._ppo_ws(max(int(max(sizes)), min(buffer.maxsize, 2 * int(batch_size) - 1)))
@@ -571,10 +591,10 @@ class PPOPolicy:
                     tail = 3
                     self._stats[repeat * n_mb * 3:repeat * n_mb * 3 + 3].copy_(self._moments)
             _lib.call("cirs_ppo_learn", C.byref(self._w), C.byref(self._g), _lib.ptr(self.exp_avg),
-                      _lib.ptr(self.exp_avg_sq), C.byref(self.cfg), repeat, n_mb, offs.ctypes.data, _lib.ptr(d_offs),
-                      _lib.ptr(d_slots), _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act), _lib.ptr(self.adv),
-                      _lib.ptr(self.returns), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(stats),
-                      _lib.ptr(d_obs), d_obs.numel() if d_obs is not None else 0, _lib.ptr(losses),
+                      _lib.ptr(self.exp_avg_sq), C.byref(self.cfg), repeat, n_mb, offs.ctypes.data, d_offs_ptr,
+                      slots_ptr, _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act), _lib.ptr(self.adv),
+                      _lib.ptr(self.returns), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), stats_ptr,
+                      _lib.ptr(d_obs), d_obs.numel() if d_obs is not None else 0, losses_ptr,
                       _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), _lib.ptr(ws), comm,
                       n_glob.ctypes.data if n_glob is not None else None, tail, st)
             if tail:
@@ -585,8 +605,9 @@ class PPOPolicy:
             # CPU-side process group (gloo; tests): per-minibatch entry points with torch.distributed collectives.
             # advantage moments of every minibatch of every repeat (they depend on the permutations only): ONE collective
             for step in range(repeat):
-                _lib.call("cirs_adv_stats", n_mb, _lib.ptr(d_offs), d_slots.data_ptr() + 4 * n * step,
-                          _lib.ptr(self.adv), stats.data_ptr() + 24 * n_mb * step, st)
+                _lib.call("cirs_adv_stats", n_mb, d_offs_ptr, slots_ptr + 4 * n * step,
+                          _lib.ptr(self.adv), stats_ptr + 24 * n_mb * step, st)
+            stats = self._stats[:repeat * n_mb * 3]
             self._allreduce(stats)
             for step in range(repeat):
                 n_glob = n_glob_plan if n_glob_plan is not None else \
@@ -596,14 +617,15 @@ class PPOPolicy:
                 for j in range(n_mb):
                     b, e = int(offs[j]), int(offs[j + 1])
                     _lib.call("cirs_ppo_minibatch", C.byref(self._w), C.byref(self._g), C.byref(self.cfg), e - b,
-                              int(n_glob[j]), d_slots.data_ptr() + 4 * (n * step + b), _lib.ptr(buffer.obs),
+                              int(n_glob[j]), slots_ptr + 4 * (n * step + b), _lib.ptr(buffer.obs),
                               _lib.ptr(buffer.d_act), _lib.ptr(self.adv), _lib.ptr(self.returns), _lib.ptr(self.v_s),
-                              _lib.ptr(self.logp_old), stats.data_ptr() + 24 * (n_mb * step + j), _lib.ptr(d_obs),
-                              losses.data_ptr() + 16 * (n_mb * step + j), _lib.ptr(ws), st)
+                              _lib.ptr(self.logp_old), stats_ptr + 24 * (n_mb * step + j), _lib.ptr(d_obs),
+                              losses_ptr + 16 * (n_mb * step + j), _lib.ptr(ws), st)
                     self._allreduce(self.grad)                                       # ONE collective per minibatch
                     _lib.call("cirs_clip_adam", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
                               _lib.ptr(self.exp_avg_sq), self.layout.total, self.layout.n_trunk, C.byref(self.cfg),
                               _lib.ptr(self.opt_state), _lib.ptr(self.opt_scratch), st)
+        losses = self._losses[:repeat * n_mb * 4]
         if tracker is not None:
             tracker.zero_grad()
             tracker.backward_from_buffer(buffer, self.d_obs, getattr(buffer, "d_users", None), tok_slot=indices,

@@ -157,7 +157,7 @@ class StateTrackerTransformer:
 
     # ------------------------------------------------------------------ rollout (K2)
     def build_state(self, obs=None, env_id=None, obs_next=None, rew=None, done=None, info=None, policy=None,
-                    dim_batch=None, reset=False):
+                    dim_batch=None, reset=False, zero_len=True):
         """state_tracker.py:188-250.  Returns {} / {"obs": s0} / {"obs_next": s_t}; states are float32 CUDA
         tensors [len(env_id), dim_state]."""
         if reset and dim_batch:
@@ -171,7 +171,8 @@ class StateTrackerTransformer:
                     kv[B] = (k, torch.zeros_like(k), torch.zeros(B, dtype=torch.int32, device=self.device))
                 self.n_env = B
                 self.kcache, self.vcache, self.len_data = kv[B]
-            self.len_data.zero_()
+            if zero_len:   # (the persistent rollout kernel keeps its own positions: nothing to clear)
+                self.len_data.zero_()
             return None
         res = {}
         if obs is not None:

@@ -11,3 +11,4 @@ for c in ("configs1","configs2"):
         print(c, round(d["value"]), d["ms_per_step"], round(d["e2e"]["value"]), [(k, round(v["us_per_step"])) for k,v in list(d["kernels"].items())[:4]])
     except Exception as e: print(c, "ERR", e)
 PY
+timeout 300 python scratch/host_trace.py configs1 > gpurun_out/r3_host_trace.txt 2>&1; tail -22 gpurun_out/r3_host_trace.txt
