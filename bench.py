@@ -441,6 +441,12 @@ def gpu_arm(args, cfg):
         one_step(False)
     frozen.restore()
     one_step(True)
+    # settling pass: the per-iteration time needs ~20 iterations to reach its steady state after the first launches
+    # (visible in ms_each_step_rank0 of earlier rounds' lines: 1.33 ms falling to 1.25 ms); they would bias whichever
+    # arm is timed first, so the timed loop itself runs once untimed
+    n_settle = 0 if args.steps < 5 else min(args.steps, 30)
+    if n_settle:
+        timed(n_settle, True)
     l0 = lib.cirs_launch_count()
     ms_res, steps_res, _, _ = timed(args.steps, True)
     per_step_res = list(timed.per_step)
@@ -557,6 +563,8 @@ def gpu_arm(args, cfg):
                        "env_steps_per_step": steps_res / args.steps,
                        "env_steps_per_step_rank0": n_tr,
                        "parallelism": f"env-sharded dp{world}", "l2": "192 MB flush between timed iterations",
+                       "settle": f"{n_settle} untimed iterations of the timed loop between the warm-up steps and the "
+                                 "timed region",
                        "timing": "CUDA events per step, max over ranks", "ms_each_step_rank0": per_step_res},
             "e2e": {"value": steps_e2e / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,

@@ -59,6 +59,7 @@ struct Args {
   const float *rew, *dense_user, *dense_item, *d_obs;
   float* obs_check;
   int ldx, ldb;                       // shared tile strides: [TM][ldx] (width d), [TM][ldb] (width max(3d, dhid, 1+dui))
+  const int32_t* chunk_e0;            // greedy plan (chunk_plan_kernel): chunk c = environments chunk_e0[c] .. chunk_e0[c+1]; [0] = count
   int phase;                          // 3 = forward + backward in one launch, 1 = forward only (activations -> workspace),
                                       // 2 = backward only (after a phase-1 launch on the same workspace)
 };
@@ -521,16 +522,22 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
   }
 
   const float sq = sqrtf((float)d), scale = 1.0f / sqrtf((float)dh);
-  const int n_chunks = (A.M + A.q - 1) / A.q;
+  const int n_chunks = A.chunk_e0 ? A.chunk_e0[0] : (A.M + A.q - 1) / A.q;
   for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    // ---- the chunk's environments: first row in [chunk q, (chunk + 1) q)  (binary search over env_off)
+    // ---- the chunk's environments: the greedy plan's range, or (no plan) those whose first row lies in
+    // [chunk q, (chunk + 1) q)  (binary search over env_off)
     __shared__ int s_e0, s_e1;
     if (tid < 2) {
-      const int target = (chunk + tid) * A.q;
-      int lo = 0, hi = A.n_env;            // first e with env_off[e] >= target
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (A.env_off[mid] < target) lo = mid + 1; else hi = mid;
+      int lo = 0;
+      if (A.chunk_e0) {
+        lo = A.chunk_e0[1 + chunk + tid];
+      } else {
+        const int target = (chunk + tid) * A.q;
+        int hi = A.n_env;            // first e with env_off[e] >= target
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (A.env_off[mid] < target) lo = mid + 1; else hi = mid;
+        }
       }
       // environments with no stored transition own no row: skip them at the lower end
       if (tid == 0) s_e0 = lo; else s_e1 = lo;
@@ -716,6 +723,41 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
         if (rpos[r] == 0) atomicAdd(G.emb_user + (size_t)A.users[renv[r]] * d + c, v);
       });
     __syncthreads();
+  }
+}
+
+// Greedy chunk plan: whole environments are packed in order into chunks of at most `cap` token rows (the optimum for a
+// contiguous partition; the first-row-quantum rule above fills a chunk to ~(cap - longest episode / 2) rows only).
+// plan[0] = number of chunks, plan[1 + c] = first environment of chunk c, plan[1 + n_chunks] = n_env.  One CTA: the
+// offsets are staged through shared memory in tiles, one thread runs the (inherently sequential) scan.
+__global__ void __launch_bounds__(256) chunk_plan_kernel(int n_env, const int32_t* __restrict__ env_off, int cap,
+                                                          int32_t* __restrict__ plan) {
+  constexpr int TILE = 4096;
+  __shared__ int s_off[TILE + 1];
+  __shared__ int s_state[3];   // chunks so far, first row of the open chunk, (unused)
+  if (threadIdx.x == 0) { s_state[0] = 0; s_state[1] = 0; plan[1] = 0; }
+  for (int base = 0; base < n_env; base += TILE) {
+    const int cnt = min(TILE, n_env - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) s_off[i] = env_off[base + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int nc = s_state[0], first = s_state[1];
+      for (int i = 0; i < cnt; ++i) {
+        if (s_off[i + 1] - first > cap) {   // environment base + i does not fit any more: it opens the next chunk
+          ++nc;
+          plan[1 + nc] = base + i;
+          first = s_off[i];
+        }
+      }
+      s_state[0] = nc; s_state[1] = first;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nc = s_state[0] + 1;
+    plan[0] = nc;
+    plan[1 + nc] = n_env;
   }
 }
 

@@ -540,7 +540,7 @@ static bool fused_enabled() {
 extern "C" void cirs_tracker_train_fused_enable(int on) { g_fused_mode = on < 0 ? -1 : (on ? 1 : 0); }
 
 struct FusedPlan { bool ok, res; int TM, ldx, ldb, q; size_t smem; };
-static FusedPlan fused_plan(const cirs_tracker_weights& W, int max_ep_len) {
+static FusedPlan fused_plan(const cirs_tracker_weights& W, int max_ep_len, int M = 0, int B = 0) {
   FusedPlan P{};
   const int d = W.d;
   int wide = 3 * d;
@@ -559,6 +559,15 @@ static FusedPlan fused_plan(const cirs_tracker_weights& W, int max_ep_len) {
     const size_t smem = cirs_k6::chunk_smem_bytes(32, d, W.nhead, P.ldx, P.ldb, cirs_k6::resident_floats(W));
     if (smem <= 224 * 1024 && !getenv("CIRS_K6_STREAM")) {
       P.ok = true; P.res = true; P.TM = 32; P.smem = smem; P.q = 32 - max_ep_len + 1;
+      // 16-row chunks (about half the latency per chunk: the stage products scale with the rows) when the greedy plan
+      // still fits ONE wave of the 148 SMs: a chunk then holds ~16 - (mean episode length) / 2 rows
+      const char* force = getenv("CIRS_K6_TM");
+      const double mean_len = B > 0 ? (double)M / B : max_ep_len;
+      const bool fits16 = max_ep_len <= 16 && M > 0 && (double)M / (16.0 - 0.5 * mean_len) <= 140.0;
+      if ((force ? atoi(force) == 16 && max_ep_len <= 16 : fits16)) {
+        P.TM = 16; P.q = 16 - max_ep_len + 1;
+        P.smem = cirs_k6::chunk_smem_bytes(16, d, W.nhead, P.ldx, P.ldb, cirs_k6::resident_floats(W));
+      }
       return P;
     }
   }
@@ -589,10 +598,17 @@ static int fused_train(const cirs_tracker_weights& W, const cirs_tracker_weights
   A.rew = rew; A.dense_user = dense_user; A.dense_item = dense_item; A.d_obs = d_obs; A.obs_check = obs_check;
   A.ldx = P.ldx; A.ldb = P.ldb;
   A.phase = phase;
-  const int n_chunks = (M + P.q - 1) / P.q;
+  const int n_chunks = (M + P.q - 1) / P.q;   // the quantum rule's count: an upper bound of the greedy plan's
   const int grid = n_chunks < 148 ? n_chunks : 148;
+  if (P.res) {   // greedy chunk plan behind the workspace's activations
+    int32_t* plan = reinterpret_cast<int32_t*>(workspace + A.S.total);
+    CIRS_LAUNCH(chunk_plan_kernel, 1, 256, 0, st, B, env_off, P.TM, plan);
+    CIRS_CHECK_LAUNCH();
+    A.chunk_e0 = plan;
+  }
   static bool attr_set = false;
   if (!attr_set) {
+    cudaFuncSetAttribute(tracker_chunk_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(tracker_chunk_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(tracker_chunk_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(tracker_chunk_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
@@ -600,7 +616,8 @@ static int fused_train(const cirs_tracker_weights& W, const cirs_tracker_weights
   }
   {
     const bool prof = cirs_profile_begin("tracker_chunk_kernel", st);
-    if (P.res) tracker_chunk_kernel<32, true><<<grid, NT, P.smem, st>>>(A);
+    if (P.res && P.TM == 16) tracker_chunk_kernel<16, true><<<grid, NT, P.smem, st>>>(A);
+    else if (P.res) tracker_chunk_kernel<32, true><<<grid, NT, P.smem, st>>>(A);
     else if (P.TM == 64) tracker_chunk_kernel<64, false><<<grid, NT, P.smem, st>>>(A);
     else tracker_chunk_kernel<32, false><<<grid, NT, P.smem, st>>>(A);
     cirs_note_launch();
@@ -653,7 +670,7 @@ extern "C" int64_t cirs_tracker_train_workspace_bytes(const cirs_tracker_weights
   const Bufs b = carve(nullptr, n_env, n_rows, w->d, w->d_hid, w->nlayers, w->d_user_in);
   const cirs_k6::Save s = cirs_k6::carve(nullptr, n_rows, w->d, w->d_hid, w->nlayers, w->d_user_in);
   const int64_t t = b.total > s.total ? b.total : s.total;
-  return t * (int64_t)sizeof(float) + 256;
+  return t * (int64_t)sizeof(float) + 256 + ((int64_t)n_env + 64) * (int64_t)sizeof(int32_t);   // + the greedy chunk plan
 }
 
 extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_tracker_weights* grads, int32_t n_env,
@@ -697,7 +714,7 @@ extern "C" int cirs_tracker_train(const cirs_tracker_weights* w, const cirs_trac
   const int ldd = up32(d), ld3 = up32(3 * d), ldh = up32(dhid), lds = up32(S), dui = w->d_user_in;
   const int nh = w->nhead, dh = d / nh;
   if (tok_slot && fused_enabled()) {
-    const FusedPlan P = fused_plan(*w, max_ep_len > 0 && max_ep_len <= L ? max_ep_len : L);
+    const FusedPlan P = fused_plan(*w, max_ep_len > 0 && max_ep_len <= L ? max_ep_len : L, M, B);
     // one CTA carries a chunk through ~100 dependent stages: a latency design that wins while the chunks fit a few
     // waves of the 148 SMs (Kuaishou: 30-200 chunks); with thousands of chunks (VirtualTaobao at 2048 x 50 tokens) the
     // throughput-oriented layer-by-layer launches are faster (measured 5.0 vs 9.7 ms)

@@ -88,6 +88,15 @@ def test_tracker_train_forward_and_grads_vs_autograd(H, name, compact):
         scale = float(np.abs(ref).max()) + 1e-12
         G.assert_close(mine[k].numpy(), ref, 1e-4, 2e-5 * scale, what=f"grad {k}")
 
+@pytest.mark.parametrize("tm", ["16", "32"])
+@pytest.mark.parametrize("name", G.KUAISHOU_CASES)
+def test_tracker_train_chunk_heights_vs_autograd(H, name, tm, monkeypatch):
+    """The resident-weight chunk kernel with 16-row and with 32-row chunks (greedy chunk plan, chunk_plan_kernel): the
+    same forward states and gradients against autograd.  (The library picks the height from the token count; the
+    golden cases' episodes are short enough for both.)"""
+    monkeypatch.setenv("CIRS_K6_TM", tm)   # (a request: an episode longer than 16 rows keeps 32-row chunks)
+    test_tracker_train_forward_and_grads_vs_autograd(H, name, True)
+
 
 @pytest.mark.parametrize("name", G.KUAISHOU_CASES)
 def test_full_iterations_vs_golden(H, name):
