@@ -42,6 +42,62 @@ __global__ void gae_kernel(int n_env, int L, const int32_t* __restrict__ n_slot,
   }
 }
 
+// the same kernel followed, in the LAST block to finish, by the moments reduction (one launch instead of two)
+__device__ unsigned int g_gae_ticket = 0;
+__global__ void __launch_bounds__(128)
+gae_moments_kernel(int n_env, int L, const int32_t* __restrict__ n_slot, const float* __restrict__ v_s,
+                   const float* __restrict__ v_next, const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                   double gamma, double lam, const double* __restrict__ ret_rms, float* __restrict__ returns,
+                   float* __restrict__ adv, double* __restrict__ part, double* __restrict__ moments) {
+  __shared__ bool last;
+  __shared__ double sh[3][4];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_env) {
+    const int n = n_slot[e];
+    const double scale = ret_rms ? sqrt(ret_rms[1] + 1e-8) : 1.0;
+    double gae = 0.0, s = 0.0, ss = 0.0;
+    for (int t = n - 1; t >= 0; --t) {
+      const size_t i = (size_t)e * L + t;
+      const bool dn = done[i] != 0;
+      const double vs = (double)v_s[i] * scale;
+      const double vn = dn ? 0.0 : (double)v_next[i] * scale;
+      const double delta = (double)rew[i] + vn * gamma - vs;
+      const bool end = dn || (t == n - 1);
+      gae = delta + (end ? 0.0 : gamma * lam) * gae;
+      const double ret = gae + vs;
+      returns[i] = (float)(ret / scale);
+      adv[i] = (float)gae;
+      s += ret;
+      ss += ret * ret;
+    }
+    part[2 * e] = s;
+    part[2 * e + 1] = ss;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&g_gae_ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // the per-environment partials in environment order per thread, then a fixed-order tree: deterministic
+  double s = 0.0, ss = 0.0, cnt = 0.0;
+  for (int i = threadIdx.x; i < n_env; i += blockDim.x) {
+    s += *(volatile double*)(part + 2 * i);
+    ss += *(volatile double*)(part + 2 * i + 1);
+    cnt += (double)n_slot[i];
+  }
+  s = warp_sum_d(s); ss = warp_sum_d(ss); cnt = warp_sum_d(cnt);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s; sh[1][w] = ss; sh[2][w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = ss = cnt = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s += sh[0][i]; ss += sh[1][i]; cnt += sh[2][i]; }
+    moments[0] = s; moments[1] = ss; moments[2] = cnt;
+    g_gae_ticket = 0;
+  }
+}
+
 // raw moments {sum, sumsq, count} of the unnormalised returns of this rank (ranks all-reduce them before merging)
 __global__ void __launch_bounds__(1024) moments_kernel(int n_env, const int32_t* __restrict__ n_slot,
                                                         const double* __restrict__ part, double* moments) {
@@ -91,13 +147,15 @@ extern "C" int cirs_compute_returns(int32_t n_env, int32_t traj_len, const int32
   }
   if (n_env == 0) return CIRS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  CIRS_LAUNCH(gae_kernel, (n_env + 127) / 128, 128, 0, st, n_env, traj_len, n_slot, v_s, v_next, rew, done, gamma,
-                                                  gae_lambda, ret_rms, returns, adv, moments ? scratch : nullptr);
-  CIRS_CHECK_LAUNCH();
   if (moments) {
-    CIRS_LAUNCH(moments_kernel, 1, 1024, 0, st, n_env, n_slot, scratch, moments);
+    CIRS_LAUNCH(gae_moments_kernel, (n_env + 127) / 128, 128, 0, st, n_env, traj_len, n_slot, v_s, v_next, rew, done,
+                gamma, gae_lambda, ret_rms, returns, adv, scratch, moments);
     CIRS_CHECK_LAUNCH();
+    return CIRS_OK;
   }
+  CIRS_LAUNCH(gae_kernel, (n_env + 127) / 128, 128, 0, st, n_env, traj_len, n_slot, v_s, v_next, rew, done, gamma,
+                                                  gae_lambda, ret_rms, returns, adv, nullptr);
+  CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }
 

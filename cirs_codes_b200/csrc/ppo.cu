@@ -383,8 +383,10 @@ row_loss_tc_kernel(int n, int n_split, cirs_ppo_config cfg, int n_global, const 
   const float* pm = ws.pm + (int64_t)r * n_split;
   const float* ps = ws.ps + (int64_t)r * n_split;
   float mx = -INFINITY;
+#pragma unroll 8
   for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, pm[s]);
   float z = 0.f;
+#pragma unroll 8
   for (int s = 0; s < n_split; ++s) z += ps[s] * expf(pm[s] - mx);
   const int slot = idx[r];
   // entropy (terms[4r+2]) and rowG are filled after pass B2 (ent_merge_kernel); rowG is only used when ent_coef != 0
@@ -518,7 +520,14 @@ loss_reduce_kernel(int n, int n_global, cirs_ppo_config cfg, const float* __rest
     a += terms[4 * r]; b += terms[4 * r + 1];
     if (ent_part) {
       float e = 0.f;
-      for (int s = 0; s < n_split; ++s) e += ent_part[(int64_t)r * n_split + s];
+      const float* ep = ent_part + (int64_t)r * n_split;
+      int s = 0;
+      for (; s + 8 <= n_split; s += 8) {   // eight loads in flight; the additions keep their left-to-right order
+        const float v0 = ep[s], v1 = ep[s + 1], v2 = ep[s + 2], v3 = ep[s + 3], v4 = ep[s + 4], v5 = ep[s + 5],
+                    v6 = ep[s + 6], v7 = ep[s + 7];
+        e += v0; e += v1; e += v2; e += v3; e += v4; e += v5; e += v6; e += v7;
+      }
+      for (; s < n_split; ++s) e += ep[s];
       c += e;
     } else {
       c += terms[4 * r + 2];

@@ -728,34 +728,34 @@ __global__ void __launch_bounds__(NT, 1) tracker_chunk_kernel(const Args A) {
 
 // Greedy chunk plan: whole environments are packed in order into chunks of at most `cap` token rows (the optimum for a
 // contiguous partition; the first-row-quantum rule above fills a chunk to ~(cap - longest episode / 2) rows only).
-// plan[0] = number of chunks, plan[1 + c] = first environment of chunk c, plan[1 + n_chunks] = n_env.  One CTA: the
-// offsets are staged through shared memory in tiles, one thread runs the (inherently sequential) scan.
-__global__ void __launch_bounds__(256) chunk_plan_kernel(int n_env, const int32_t* __restrict__ env_off, int cap,
-                                                          int32_t* __restrict__ plan) {
-  constexpr int TILE = 4096;
-  __shared__ int s_off[TILE + 1];
-  __shared__ int s_state[3];   // chunks so far, first row of the open chunk, (unused)
-  if (threadIdx.x == 0) { s_state[0] = 0; s_state[1] = 0; plan[1] = 0; }
-  for (int base = 0; base < n_env; base += TILE) {
-    const int cnt = min(TILE, n_env - base);
-    __syncthreads();
-    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) s_off[i] = env_off[base + i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int nc = s_state[0], first = s_state[1];
-      for (int i = 0; i < cnt; ++i) {
-        if (s_off[i + 1] - first > cap) {   // environment base + i does not fit any more: it opens the next chunk
-          ++nc;
-          plan[1 + nc] = base + i;
-          first = s_off[i];
-        }
-      }
-      s_state[0] = nc; s_state[1] = first;
+// plan[0] = number of chunks, plan[1 + c] = first environment of chunk c, plan[1 + n_chunks] = n_env.  One CTA, offsets
+// in shared memory (n_env <= PLAN_MAX_ENV): every thread finds by binary search where a chunk that STARTS at its
+// environment would end (jump pointer), then one thread follows the pointers from environment 0 -- ~n_chunks dependent
+// shared-memory loads instead of a scan over all environments.
+constexpr int PLAN_MAX_ENV = 6144;   // 36 KB of static shared memory
+__global__ void __launch_bounds__(1024) chunk_plan_kernel(int n_env, const int32_t* __restrict__ env_off, int cap,
+                                                           int32_t* __restrict__ plan) {
+  __shared__ int s_off[PLAN_MAX_ENV + 1];
+  __shared__ uint16_t s_next[PLAN_MAX_ENV];
+  for (int i = threadIdx.x; i <= n_env; i += blockDim.x) s_off[i] = env_off[i];
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_env; e += blockDim.x) {
+    const int limit = s_off[e] + cap;
+    int lo = e + 1, hi = n_env;          // largest j in [e + 1, n_env] with s_off[j] <= limit (j = e + 1 always fits)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= limit) lo = mid; else hi = mid - 1;
     }
+    s_next[e] = (uint16_t)lo;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int nc = s_state[0] + 1;
+    int nc = 0, e = 0;
+    while (e < n_env) {
+      plan[1 + nc] = e;
+      ++nc;
+      e = s_next[e];
+    }
     plan[0] = nc;
     plan[1 + nc] = n_env;
   }

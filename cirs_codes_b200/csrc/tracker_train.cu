@@ -600,9 +600,9 @@ static int fused_train(const cirs_tracker_weights& W, const cirs_tracker_weights
   A.phase = phase;
   const int n_chunks = (M + P.q - 1) / P.q;   // the quantum rule's count: an upper bound of the greedy plan's
   const int grid = n_chunks < 148 ? n_chunks : 148;
-  if (P.res) {   // greedy chunk plan behind the workspace's activations
+  if (P.res && B <= cirs_k6::PLAN_MAX_ENV) {   // greedy chunk plan behind the workspace's activations
     int32_t* plan = reinterpret_cast<int32_t*>(workspace + A.S.total);
-    CIRS_LAUNCH(chunk_plan_kernel, 1, 256, 0, st, B, env_off, P.TM, plan);
+    CIRS_LAUNCH(chunk_plan_kernel, 1, 1024, 0, st, B, env_off, P.TM, plan);
     CIRS_CHECK_LAUNCH();
     A.chunk_e0 = plan;
   }

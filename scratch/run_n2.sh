@@ -1,0 +1,8 @@
+timeout 600 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r3_multi_tests.log 2>&1; tail -3 gpurun_out/r3_multi_tests.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 > gpurun_out/r3_bench_n2.json 2> gpurun_out/r3_bench_n2.err; tail -c 400 gpurun_out/r3_bench_n2.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r3_bench_n2.json").read().strip().splitlines()[-1])
+print(d["n_gpus"], round(d["value"]), d["ms_per_step"], round(d["e2e"]["value"]), d["config"]["env_steps_per_step"])
+print([(k, round(v["us_per_step"])) for k,v in d["kernels"].items() if "nccl" in k or "rollout" in k])
+PY
