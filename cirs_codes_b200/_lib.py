@@ -140,6 +140,7 @@ PROTOTYPES = {
     "cirs_user_model_tc_enable": (None, [i32]),
     "cirs_user_model_timeout": (i32, []),
     "cirs_user_model_debug_phases": (i32, [P(i64)]),
+    "cirs_head_tc_debug_phases": (i32, [i32, P(i64), i32]),
     "cirs_clip_adam": (i32, [fp, fp, fp, fp, i64, i64, P(PPOConfigStruct), fp, fp, fp]),
 }
 

@@ -33,6 +33,30 @@ constexpr int KSTEPS = HID / 8;   // every contraction here has depth 64
 #define LOG_1M_EPS (-1.1920929665620963e-07f)     /* log(1 - CATEGORICAL_EPS) */
 
 __device__ int g_tc_timeout = 0;   // set when an mbarrier wait gives up (never expected; checked by the tests)
+// Phase counters (cycles summed over CTAs) of the ring-fed pass F [0, 16) and the TMA-fed pass B2 [16, 48); filled only
+// by the PH instantiations (cirs_head_tc_debug_phases; scratch/head_phases.py).  One representative worker warp (warp 0)
+// and the issuer warp stamp clock64() around their waits.
+__device__ unsigned long long g_phase[64];
+template <bool PH>
+struct PhaseClock {   // compiled out entirely unless PH (the stamped instantiations are launched while g_phase_host is set)
+  bool on;
+  long long t;
+  __device__ __forceinline__ void start(bool enable) {
+    if constexpr (PH) { on = enable; if (on) t = clock64(); } else { on = false; }
+  }
+  __device__ __forceinline__ void lap(int slot) {
+    if constexpr (PH) {
+      if (on) {
+        const long long n = clock64();
+        atomicAdd(&g_phase[slot], (unsigned long long)(n - t));
+        t = n;
+      }
+    }
+  }
+  __device__ __forceinline__ void count(int slot, int v) {
+    if constexpr (PH) { if (on) atomicAdd(&g_phase[slot], (unsigned long long)v); }
+  }
+};
 
 __device__ __forceinline__ void issue(uint32_t d, const char* a_hi, const char* a_lo, const char* b_hi, const char* b_lo,
                                       bool accumulate) {
@@ -46,6 +70,16 @@ __device__ __forceinline__ void w_issue(uint32_t d, const char* a_hi, const char
 }
 __device__ __forceinline__ void wait_or_flag(uint64_t* bar, uint32_t parity) {
   if (!mbar_wait(bar, parity)) g_tc_timeout = 1;
+}
+// v[k] for a run-time k with v kept in REGISTERS.  The plain forms (v[k], or an unrolled `if (j == k) x = v[j]`) make
+// the compiler index a local-memory copy of v: 8 x STL.128 per thread per tile in the hot loop of every pass-F kernel,
+// which -- with the L1 carved down to nothing beside ~200 KB of shared memory -- went to L2 and paced the epilogue.
+__device__ __forceinline__ float pick32(const float (&v)[32], int k) {
+  float x = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tselp.f32 %0, %3, %0, p;\n\t}" : "+f"(x) : "r"(k), "r"(j), "f"(v[j]));
+  return x;
 }
 
 // ------------------------------------------------------------------------------------------------- pass F
@@ -342,9 +376,7 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
       mt = fmaxf(mt, x);
     }
     if (a >= cb && a < cb + 32) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j == a - cb) lav = v[j];
+      lav = pick32(v, a - cb);
       found = true;
     }
     if (mt > 0.5f * MASKED) {
@@ -464,9 +496,7 @@ head_tc_stats_tma_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_
       __syncwarp();
       if (lane == 0) mbar_arrive(&dfree[b]);
       if (a >= cb && a < cb + 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j == a - cb) lav = v[j];
+        lav = pick32(v, a - cb);
         found = true;
       }
       if (mt > 0.5f * MASKED) {
@@ -494,17 +524,6 @@ head_tc_stats_tma_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
-// ------------------------------------------------------------------------------------------------- passes B2 / B3
-// Software pipeline shared by both backward passes (tile t, buffers b = t & 1):
-//     stage operands of tile t+1 -> MMA1(t+1) into the other logits accumulator   | overlaps
-//     epilogue(t): TMEM logits -> d logits, written BACK TO TMEM as the (hi, lo) A operand  | MMA1(t+1) and MMA2(t-1)
-//     MMA2(t): D2 += d logits[tmem] . B2[smem]
-// d logits never touch shared memory (tcgen05.st), which frees the 64 KB that double-buffer the B operands.
-// TMEM columns (512 allocated): logits accumulators [0,64) [64,128) | D2 [128,192) | d logits hi/lo, two buffers [192,448).
-constexpr uint32_t T_D1 = 0, T_D2 = 128, T_DL = 192;
-__device__ __forceinline__ uint32_t t_dl_hi(int b) { return T_DL + 128u * b; }
-__device__ __forceinline__ uint32_t t_dl_lo(int b) { return T_DL + 128u * b + 64u; }
-
 // D (+)= A[tmem hi/lo] . B[smem hi/lo], 3 TF32 products per k-step of 8
 __device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const char* b_hi, const char* b_lo,
                                          bool accumulate) {
@@ -524,6 +543,328 @@ __device__ __forceinline__ void w_issue_ts(uint32_t d, uint32_t a_hi, uint32_t a
                                            bool accumulate) {
   if (elect_one()) issue_ts(d, a_hi, a_lo, b_hi, b_lo, accumulate);
 }
+
+// ------------------------------------------------------------------------------------------------- pass F, ring-fed
+// One CTA per SM with a RING of three W3 tiles: a 32 KB bulk copy from L2 takes ~1.5 us, and the two-CTAs-per-SM kernel
+// above pays it (plus the MMA's completion) once per tile in its issuer's chain -- 28 us per 1567-row pass for 12 us of
+// MMA work.  Here the copy of tile t + 2 is issued as soon as MMA(t - 1) has released its slot, so three copies are in
+// flight behind the MMAs.  Workers and barriers as above; the bias of tile t sits in slot t & 3 of a ring of four.
+// ATM: the h2 row tile -- the A operand of every MMA of the CTA -- lives in TENSOR MEMORY instead of shared memory: the
+// workers split their rows into (hi, lo) once and tcgen05.st them to TMEM columns [128, 256).  An MMA then reads only
+// its 2 KB B slice from shared memory (the SS form reads 6 KB per M128 N64 K8 MMA and is shared-memory-bandwidth bound:
+// 51-79 cycles per MMA measured against 35 for the TS form), and without the 64 KB A tile two CTAs fit an SM again.
+constexpr int F_RING = 3;
+constexpr size_t FR_SMEM = 2 * A_BYTES + F_RING * 2 * B_BYTES + 4 * 64 * 4 + 2 * NT * 4;
+constexpr size_t FRT_SMEM = F_RING * 2 * B_BYTES + 4 * 64 * 4 + 2 * NT * 4;
+constexpr uint32_t TF_A = 128;   // TMEM columns of the A operand (ATM): hi [128, 192), lo [192, 256)
+
+template <bool ATM, bool PH>
+__global__ void __launch_bounds__(NTF, ATM ? 2 : 1)
+head_tc_stats_ring_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act,
+                          int tiles_per_split, int n_split, float* __restrict__ pm, float* __restrict__ ps,
+                          float* __restrict__ la) {
+  extern __shared__ __align__(1024) char smem[];
+  char* a_hi = smem;                                                       // (SS form only)
+  char* a_lo = a_hi + A_BYTES;
+  char* bring = ATM ? smem : a_lo + A_BYTES;                               // F_RING x { hi, lo }
+  float* sb3 = reinterpret_cast<float*>(bring + F_RING * 2 * B_BYTES);     // 4 x 64
+  float* sm = sb3 + 256;
+  float* ss = sm + NT;
+  __shared__ __align__(8) uint64_t tma_a, tma_b[F_RING], mma[2], dfree[2];   // tma_a (ATM): the workers' A rows are in TMEM
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, half = (tid >> 7) & 1;
+  const bool worker = tid < NT, issuer = __shfl_sync(FULL_MASK, warp, 0) == NT / 32;
+  const int r0 = blockIdx.x * TM, split = blockIdx.y;
+  const int n_tiles = (H.nA + TN - 1) / TN;
+  const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
+  const int64_t n64 = H.ldA / TN;
+  if (warp == 0) tmem_alloc(&tmem_base, ATM ? 256 : 128);
+  if (tid == 0) {
+    mbar_init(&tma_a, ATM ? NT / 32 : 1);
+    for (int i = 0; i < F_RING; ++i) mbar_init(&tma_b[i], 1);
+    mbar_init(&mma[0], 1); mbar_init(&mma[1], 1);
+    mbar_init(&dfree[0], NT / 32); mbar_init(&dfree[1], NT / 32);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base;
+  // PH only: experiment switch g_phase[62] (1: workers skip the epilogue arithmetic, 2: the ring is filled once and never
+  // refilled, 3: both) -- which resource paces the MMAs
+  int dbg = 0;
+  if constexpr (PH) dbg = (int)g_phase[62];
+  if (issuer && T > 0) {
+    auto copy_tile = [&](int t) {   // tile t -> ring slot t % F_RING (phase parity (t / F_RING) & 1), bias -> slot t & 3
+      const int ct = ct0 + t, s = t % F_RING;
+      w_expect_tx(&tma_b[s], 2 * B_BYTES + 64 * 4);
+      w_bulk_g2s(bring + (size_t)s * 2 * B_BYTES, H.img + img_n_off(ct), 2 * B_BYTES, &tma_b[s]);
+      w_bulk_g2s(sb3 + 64 * (t & 3), H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_b[s]);
+    };
+    if (!ATM) {
+      w_expect_tx(&tma_a, 2 * A_BYTES);
+      w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
+    }
+    for (int t = 0; t < F_RING && t < T; ++t) copy_tile(t);
+    wait_or_flag(&tma_a, 0);
+    PhaseClock<PH> pc;
+    pc.start(lane == 0);
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, s = t % F_RING;
+      if (!(dbg & 2) || t < F_RING) wait_or_flag(&tma_b[s], (t / F_RING) & 1);   // tile t and its bias are in shared memory
+      pc.lap(0);
+      if (t >= 2) wait_or_flag(&dfree[b], ((t - 2) >> 1) & 1);        // accumulator b was read by epilogue(t-2)
+      pc.lap(1);
+      fence_after_sync();
+      if (ATM)
+        w_issue_ts(tb + 64u * b, tb + TF_A, tb + TF_A + 64u, bring + (size_t)s * 2 * B_BYTES,
+                   bring + (size_t)s * 2 * B_BYTES + B_BYTES, false);
+      else
+        w_issue(tb + 64u * b, a_hi, a_lo, bring + (size_t)s * 2 * B_BYTES, bring + (size_t)s * 2 * B_BYTES + B_BYTES, false);
+      w_commit(&mma[b]);
+      pc.lap(2);
+      if (t >= 1 && t - 1 + F_RING < T) {
+        wait_or_flag(&mma[b ^ 1], ((t - 1) >> 1) & 1);                // MMA(t-1) released ring slot (t-1) % F_RING; bias
+        if (!(dbg & 2)) copy_tile(t - 1 + F_RING);                    // slot (t+2) & 3 was tile t-2's (dfree above)
+        pc.lap(3);
+      }
+    }
+    pc.count(4, T);
+  }
+  int a = -1;
+  if (worker && act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
+  float m = MASKED, s = 0.f, lav = 0.f;
+  bool found = false;
+  if (worker) {
+    if (ATM && T > 0) {   // this thread's 32 h2 values (row, column half) -> (hi, lo) -> TMEM, split like head_tc_pack_h2
+      const bool okr = r0 + row < H.n;
+      const float4* src = reinterpret_cast<const float4*>(H.h2 + (size_t)(okr ? r0 + row : 0) * HID + half * 32);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 x = okr ? __ldg(src + 4 * q + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[4 * c + e] = tf32_hi(xs[e]);
+            lo[4 * c + e] = tf32_hi(xs[e] - hi[4 * c + e]);
+          }
+        }
+        tmem_st16(tmem_addr(tb + TF_A, (warp & 3) * 32, half * 32 + 16 * q), hi);
+        tmem_st16(tmem_addr(tb + TF_A + 64u, (warp & 3) * 32, half * 32 + 16 * q), lo);
+      }
+      tmem_st_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tma_a);
+    }
+    PhaseClock<PH> pc;
+    pc.start(tid == 0);
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, cb = (ct0 + t) * TN + half * 32;
+      wait_or_flag(&mma[b], (t >> 1) & 1);
+      pc.lap(8);
+      fence_after_sync();
+      float v[32];
+      tmem_ld32(tmem_addr(tb + 64u * b, (warp & 3) * 32, half * 32), v);
+      pc.lap(9);
+      float mt = MASKED;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = v[j] + sb3[64 * (t & 3) + half * 32 + j];   // padding columns carry the MASKED bias
+        v[j] = x;
+        mt = fmaxf(mt, x);
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dfree[b]);
+      pc.lap(10);
+      if (dbg & 1) continue;
+      if (a >= cb && a < cb + 32) {
+        lav = pick32(v, a - cb);
+        found = true;
+      }
+      if (mt > 0.5f * MASKED) {
+        const float mn = fmaxf(m, mt);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += fast_exp(v[j] - mn);
+        s = s * fast_exp(m - mn) + acc;
+        m = mn;
+      }
+      pc.lap(11);
+    }
+    sm[tid] = m;
+    ss[tid] = s;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (worker && half == 0 && r0 + row < H.n) {
+    const float m1 = sm[tid + TM], s1 = ss[tid + TM];
+    const float M = fmaxf(m, m1);
+    const float S = s * fast_exp(m - M) + s1 * fast_exp(m1 - M);   // an empty half has s == 0
+    pm[(size_t)(r0 + row) * n_split + split] = M;
+    ps[(size_t)(r0 + row) * n_split + split] = S;
+  }
+  if (found) la[r0 + row] = lav;
+  if (warp == 0) tmem_dealloc(tmem_base, ATM ? 256 : 128);
+}
+
+// ------------------------------------------------------------------------------------------------- pass F, 128-column tiles
+// Measured on the B200 (cirs_head_tc_debug_phases, scratch/f_experiments.py): an M128 N64 K8 kind::tf32 MMA with both
+// operands in shared memory executes in ~58 cycles, not the tensor pipe's 32 -- it re-reads the 4 KB A slice for 2 KB of
+// B, and shared memory feeds 128 B per clock.  With N = 128 an MMA reads 4 + 4 KB for twice the math.  This variant
+// walks the catalogue in 128-column tiles: the B operand is the 128-row W3 image that pass B3 uses as its A operand
+// (img_a_off), two 64 KB stages in shared memory, two 128-column accumulators in TMEM, and 16 epilogue warps (thread =
+// TMEM lane x 32-column quarter).  One CTA per SM.
+constexpr int WN = 128;
+constexpr uint32_t IDESC_W = idesc_tf32(TM, WN, 0, 0);
+constexpr size_t FW_SMEM = 2 * A_BYTES + 2 * 2 * A_BYTES + 4 * WN * 4 + 2 * NTB * 4;
+
+template <bool PH>
+__global__ void __launch_bounds__(NTB + 32, 1)
+head_tc_stats_wide_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act,
+                          int tiles_per_split, int n_split, float* __restrict__ pm, float* __restrict__ ps,
+                          float* __restrict__ la) {
+  extern __shared__ __align__(1024) char smem[];
+  char* a_hi = smem;
+  char* a_lo = a_hi + A_BYTES;
+  char* bring = a_lo + A_BYTES;                                            // 2 x { hi, lo } of a 128-column W3 tile
+  float* sb3 = reinterpret_cast<float*>(bring + 2 * 2 * A_BYTES);          // ring of 4 x 128 bias values
+  float* sm = sb3 + 4 * WN;
+  float* ss = sm + NTB;
+  __shared__ __align__(8) uint64_t tma_a, tma_b[2], mma[2], dfree[2];
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, q = (tid >> 7) & 3;
+  const bool worker = tid < NTB, issuer = __shfl_sync(FULL_MASK, warp, 0) == NTB / 32;
+  const int r0 = blockIdx.x * TM, split = blockIdx.y;
+  const int n_tiles = (H.nA + WN - 1) / WN;
+  const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
+  const int64_t n64 = H.ldA / TN;
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  if (tid == 0) {
+    mbar_init(&tma_a, 1); mbar_init(&tma_b[0], 1); mbar_init(&tma_b[1], 1);
+    mbar_init(&mma[0], 1); mbar_init(&mma[1], 1);
+    mbar_init(&dfree[0], NTB / 32); mbar_init(&dfree[1], NTB / 32);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (issuer && T > 0) {
+    auto copy_tile = [&](int t) {   // tile t -> stage t & 1 (phase parity (t >> 1) & 1), bias -> ring slot t & 3
+      const int ct = ct0 + t, b = t & 1;
+      w_expect_tx(&tma_b[b], 2 * A_BYTES + WN * 4);
+      w_bulk_g2s(bring + (size_t)b * 2 * A_BYTES, H.img + img_a_off(n64, ct), 2 * A_BYTES, &tma_b[b]);
+      w_bulk_g2s(sb3 + WN * (t & 3), H.img + img_bias_off(n64) + (int64_t)ct * WN, WN * 4, &tma_b[b]);
+    };
+    w_expect_tx(&tma_a, 2 * A_BYTES);
+    w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
+    copy_tile(0);
+    if (T > 1) copy_tile(1);
+    wait_or_flag(&tma_a, 0);
+    PhaseClock<PH> pc;
+    pc.start(lane == 0);
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1;
+      wait_or_flag(&tma_b[b], (t >> 1) & 1);                          // tile t and its bias are in shared memory
+      pc.lap(0);
+      if (t >= 2) wait_or_flag(&dfree[b], ((t - 2) >> 1) & 1);        // accumulator b was read by epilogue(t-2)
+      pc.lap(1);
+      fence_after_sync();
+      if (elect_one())
+        mma_3xtf32(tb + (uint32_t)WN * b, smem_u32(a_hi), smem_u32(a_lo), A_STEP, A_LBO, SBO,
+                   smem_u32(bring + (size_t)b * 2 * A_BYTES), smem_u32(bring + (size_t)b * 2 * A_BYTES + A_BYTES), A_STEP,
+                   A_LBO, SBO, IDESC_W, KSTEPS, false);
+      w_commit(&mma[b]);
+      pc.lap(2);
+      if (t >= 1 && t + 1 < T) {
+        wait_or_flag(&mma[b ^ 1], ((t - 1) >> 1) & 1);                // MMA(t-1) released stage b ^ 1; bias slot (t+1) & 3
+        copy_tile(t + 1);                                             // was tile t-3's
+        pc.lap(3);
+      }
+    }
+    pc.count(4, 2 * T);   // in 64-column units, comparable with the ring kernel's counters
+  }
+  int a = -1;
+  if (worker && act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
+  float m = MASKED, s = 0.f, lav = 0.f;
+  bool found = false;
+  if (worker) {
+    PhaseClock<PH> pc;
+    pc.start(tid == 0);
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, cb = (ct0 + t) * WN + q * 32;
+      wait_or_flag(&mma[b], (t >> 1) & 1);
+      pc.lap(8);
+      fence_after_sync();
+      float v[32];
+      tmem_ld32(tmem_addr(tb + (uint32_t)WN * b, (warp & 3) * 32, q * 32), v);
+      pc.lap(9);
+      float mt = MASKED;
+      const float4* bias = reinterpret_cast<const float4*>(sb3 + WN * (t & 3) + q * 32);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 bb = bias[j4];   // padding columns carry the MASKED bias
+        v[4 * j4] += bb.x; v[4 * j4 + 1] += bb.y; v[4 * j4 + 2] += bb.z; v[4 * j4 + 3] += bb.w;
+      }
+      {   // tree maximum (the serial chain of 32 dependent FMNMX was a third of this epilogue)
+        float m8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m8[j] = fmaxf(fmaxf(v[j], v[j + 8]), fmaxf(v[j + 16], v[j + 24]));
+        mt = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dfree[b]);
+      pc.lap(10);
+      if (a >= cb && a < cb + 32) {
+        lav = pick32(v, a - cb);
+        found = true;
+      }
+      if (mt > 0.5f * MASKED) {
+        const float mn = fmaxf(m, mt);
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc4[j & 3] += fast_exp(v[j] - mn);
+        s = s * fast_exp(m - mn) + ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+        m = mn;
+      }
+      pc.lap(11);
+    }
+    sm[tid] = m;
+    ss[tid] = s;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (worker && q == 0 && r0 + row < H.n) {
+    float M = m;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) M = fmaxf(M, sm[tid + k * TM]);
+    float S = s * fast_exp(m - M);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) S += ss[tid + k * TM] * fast_exp(sm[tid + k * TM] - M);   // an empty quarter has s == 0
+    pm[(size_t)(r0 + row) * n_split + split] = M;
+    ps[(size_t)(r0 + row) * n_split + split] = S;
+  }
+  if (found) la[r0 + row] = lav;
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------- passes B2 / B3
+// Software pipeline shared by both backward passes (tile t, buffers b = t & 1):
+//     stage operands of tile t+1 -> MMA1(t+1) into the other logits accumulator   | overlaps
+//     epilogue(t): TMEM logits -> d logits, written BACK TO TMEM as the (hi, lo) A operand  | MMA1(t+1) and MMA2(t-1)
+//     MMA2(t): D2 += d logits[tmem] . B2[smem]
+// d logits never touch shared memory (tcgen05.st), which frees the 64 KB that double-buffer the B operands.
+// TMEM columns (512 allocated): logits accumulators [0,64) [64,128) | D2 [128,192) | d logits hi/lo, two buffers [192,448).
+constexpr uint32_t T_D1 = 0, T_D2 = 128, T_DL = 192;
+__device__ __forceinline__ uint32_t t_dl_hi(int b) { return T_DL + 128u * b; }
+__device__ __forceinline__ uint32_t t_dl_lo(int b) { return T_DL + 128u * b + 64u; }
+
 // 16 d-logit values of this thread's lane -> TMEM (hi by truncation, lo = x - hi: gradients need ~2^-22, tc_dev.cuh)
 __device__ __forceinline__ void store_dl(uint32_t tb, int b, uint32_t lane_base, int col0, const float (&v)[16]) {
   float hi[16], lo[16];
@@ -807,8 +1148,11 @@ head_tc_dw3_kernel(HeadTc H, const float* __restrict__ rowm, const float* __rest
 //   mma1[b]   logits accumulator b holds tile t                                    workers wait
 //   dlr[b]    (16 arrivals) d logits of tile t are in TMEM buffer b; accumulator b, bias / statistics buffer b consumed
 //   mma2      second MMA of tile t complete (single B buffer free again)           issuer waits; workers at the end
-constexpr size_t B2T_SMEM = 2 * A_BYTES + 6 * B_BYTES + 2 * 64 * 4 + NTB * 4;
+// Both operand streams run TWO tiles ahead of the MMAs (double-buffered B tiles of both MMAs, bias in a ring of four):
+// a 32 KB bulk copy takes ~1.5 us from L2, which the one-tile-ahead version paid twice per tile in the issuer's chain.
+constexpr size_t B2T_SMEM = 2 * A_BYTES + 8 * B_BYTES + 4 * 64 * 4 + NTB * 4;
 
+template <bool PH>
 __global__ void __launch_bounds__(NTB + 32, 1)
 head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
                        const float* __restrict__ coef, const int32_t* __restrict__ acta, int tiles_per_split,
@@ -817,10 +1161,10 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   char* a_hi = smem;                         // h2 tile (hi, lo adjacent)          (A of MMA1)
   char* a_lo = a_hi + A_BYTES;
   char* bn = a_lo + A_BYTES;                 // 2 x { W3 tile r = column, c = hidden: hi, lo }   (B of MMA1)
-  char* bk = bn + 4 * B_BYTES;               // 1 x { W3 tile r = hidden, c = column: hi, lo }   (B of MMA2)
-  float* sb3 = reinterpret_cast<float*>(bk + 2 * B_BYTES);   // 2 x 64
-  float* se = sb3 + 128;
-  __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k, mma1[2], mma2, dlr[2];
+  char* bk = bn + 4 * B_BYTES;               // 2 x { W3 tile r = hidden, c = column: hi, lo }   (B of MMA2)
+  float* sb3 = reinterpret_cast<float*>(bk + 4 * B_BYTES);   // ring of 4 x 64 bias values (tile t in slot t & 3)
+  float* se = sb3 + 256;
+  __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k[2], mma1[2], mma2, dlr[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, qt = (tid >> 7) & 3;
   const bool worker = tid < NTB, issuer = __shfl_sync(FULL_MASK, warp, 0) == NTB / 32;
@@ -830,7 +1174,7 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   const int64_t n64 = H.ldA / TN;
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   if (tid == 0) {
-    mbar_init(&tma_a, 1); mbar_init(&tma_n[0], 1); mbar_init(&tma_n[1], 1); mbar_init(&tma_k, 1);
+    mbar_init(&tma_a, 1); mbar_init(&tma_n[0], 1); mbar_init(&tma_n[1], 1); mbar_init(&tma_k[0], 1); mbar_init(&tma_k[1], 1);
     mbar_init(&mma1[0], 1); mbar_init(&mma1[1], 1); mbar_init(&mma2, 1);
     mbar_init(&dlr[0], NTB / 32); mbar_init(&dlr[1], NTB / 32);
     mbar_fence_init();
@@ -840,48 +1184,65 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   fence_after_sync();
   const uint32_t tb = tmem_base;
   if (issuer && T > 0) {
+    // tile t: logits-MMA B tile in bn[t & 1] (+ bias in ring slot t & 3) on tma_n[t & 1], second-MMA B tile in
+    // bk[t & 1] on tma_k[t & 1]; each barrier's phase for tile t has parity (t >> 1) & 1
     auto copy_n = [&](int t) {
       const int ct = ct0 + t, b = t & 1;
       w_expect_tx(&tma_n[b], 2 * B_BYTES + 64 * 4);
       w_bulk_g2s(bn + 2 * b * B_BYTES, H.img + img_n_off(ct), 2 * B_BYTES, &tma_n[b]);
-      w_bulk_g2s(sb3 + 64 * b, H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_n[b]);
+      w_bulk_g2s(sb3 + 64 * (t & 3), H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_n[b]);
     };
     auto copy_k = [&](int t) {
-      w_expect_tx(&tma_k, 2 * B_BYTES);
-      w_bulk_g2s(bk, H.img + img_k_off(n64, ct0 + t), 2 * B_BYTES, &tma_k);
+      const int b = t & 1;
+      w_expect_tx(&tma_k[b], 2 * B_BYTES);
+      w_bulk_g2s(bk + 2 * b * B_BYTES, H.img + img_k_off(n64, ct0 + t), 2 * B_BYTES, &tma_k[b]);
     };
     w_expect_tx(&tma_a, 2 * A_BYTES);
     w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
     copy_n(0);
+    if (T > 1) copy_n(1);
     copy_k(0);
+    if (T > 1) copy_k(1);
     wait_or_flag(&tma_a, 0);
     wait_or_flag(&tma_n[0], 0);
     fence_after_sync();
     w_issue(tb + T_D1, a_hi, a_lo, bn, bn + B_BYTES, false);
     w_commit(&mma1[0]);
+    PhaseClock<PH> pc;
+    pc.start(lane == 0);
+    pc.lap(16);                                                   // (start-up: first copies + MMA1(0) are not counted)
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, nb = b ^ 1;
       if (t + 1 < T) {
-        if (t >= 1) {
-          wait_or_flag(&mma1[nb], ((t - 1) >> 1) & 1);   // MMA1(t-1) no longer reads bn[nb]
-          wait_or_flag(&dlr[nb], ((t - 1) >> 1) & 1);    // epilogue(t-1) consumed accumulator nb and bias buffer nb
-        }
-        copy_n(t + 1);
-        wait_or_flag(&tma_n[nb], ((t + 1) >> 1) & 1);
+        if (t >= 1) wait_or_flag(&dlr[nb], ((t - 1) >> 1) & 1);   // epilogue(t-1) consumed accumulator nb
+        pc.lap(17);
+        wait_or_flag(&tma_n[nb], ((t + 1) >> 1) & 1);             // copied one tile ago
+        pc.lap(18);
         fence_after_sync();
         w_issue(tb + T_D1 + 64u * nb, a_hi, a_lo, bn + 2 * nb * B_BYTES, bn + (2 * nb + 1) * B_BYTES, false);
         w_commit(&mma1[nb]);
+        pc.lap(19);
       }
-      if (t >= 1) {
-        wait_or_flag(&mma2, (t - 1) & 1);                // MMA2(t-1) no longer reads bk
-        copy_k(t);
+      if (t + 2 < T) {
+        wait_or_flag(&mma1[b], (t >> 1) & 1);                     // MMA1(t) no longer reads bn[b]; bias slot (t+2)&3 was
+        copy_n(t + 2);                                            // tile t-2's, whose epilogue is long over
+        pc.lap(20);
       }
-      wait_or_flag(&dlr[b], (t >> 1) & 1);               // d logits of tile t are in TMEM
-      wait_or_flag(&tma_k, t & 1);
+      if (t >= 1 && t + 1 < T) {
+        wait_or_flag(&mma2, (t - 1) & 1);                         // MMA2(t-1) no longer reads bk[nb]
+        copy_k(t + 1);
+        pc.lap(21);
+      }
+      wait_or_flag(&dlr[b], (t >> 1) & 1);                        // d logits of tile t are in TMEM
+      pc.lap(22);
+      wait_or_flag(&tma_k[b], (t >> 1) & 1);
+      pc.lap(23);
       fence_after_sync();
-      w_issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk, bk + B_BYTES, t > 0);
+      w_issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), bk + 2 * b * B_BYTES, bk + (2 * b + 1) * B_BYTES, t > 0);
       w_commit(&mma2);
+      pc.lap(24);
     }
+    pc.count(25, T);
   }
   const bool live = worker && r0 + row < H.n;
   float ent = 0.f;
@@ -889,28 +1250,35 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
     const float rm = live ? rowm[r0 + row] : 0.f, iz = live ? rinvz[r0 + row] : 0.f, cf = live ? coef[r0 + row] : 0.f;
     const int a = live ? acta[r0 + row] : -1;
     const float log_z = iz > 0.f ? -logf(iz) : 0.f;
+    PhaseClock<PH> pc;
+    pc.start(tid == 0 || tid == NTB - 32);   // first and last worker warp
+    const int ps = tid == 0 ? 32 : 40;
     for (int t = 0; t < T; ++t) {
       const int b = t & 1;
       wait_or_flag(&mma1[b], (t >> 1) & 1);
+      pc.lap(ps);
       fence_after_sync();
       float v[16];
       tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
+      pc.lap(ps + 1);
       const int cb = (ct0 + t) * TN + qt * 16;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float xm = v[j] + sb3[64 * b + qt * 16 + j] - rm;   // logit - max (padding columns: -1e30)
+        const float xm = v[j] + sb3[64 * (t & 3) + qt * 16 + j] - rm;   // logit - max (padding columns: -1e30)
         const float p = fast_exp(xm) * iz;
         const float lg = fminf(fmaxf(xm - log_z, LOG_EPS), LOG_1M_EPS);
         ent = fmaf(-p, lg, ent);
         v[j] = cf * ((cb + j == a ? 1.f : 0.f) - p);
       }
       store_dl(tb, b, (warp & 3) * 32, qt * 16, v);
+      pc.lap(ps + 2);
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dlr[b]);
       // follow every phase of mma2 in order (a parity wait is only unambiguous one phase at a time); MMA2(t-1) was
       // issued a whole epilogue ago, so this does not stall
       if (t >= 1) wait_or_flag(&mma2, (t - 1) & 1);
+      pc.lap(ps + 3);
     }
     if (T > 0) {
       wait_or_flag(&mma2, (T - 1) & 1);
@@ -935,7 +1303,7 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
 
 // pass B3, TMA-fed.  Row statistics of a 64-row tile (max, 1/Z, coef, action: four contiguous 256-byte slices of the
 // per-row arrays, which the caller pads with zeros / -1 up to a multiple of 64 rows) travel with the h2 tile.
-constexpr size_t B3T_SMEM = 2 * A_BYTES + 6 * B_BYTES + 2 * 4 * 64 * 4;
+constexpr size_t B3T_SMEM = 2 * A_BYTES + 8 * B_BYTES + 4 * 4 * 64 * 4;
 
 __global__ void __launch_bounds__(NTB + 32, 1)
 head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
@@ -945,9 +1313,9 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   char* wa_hi = smem;                        // W3 tile, r = column (128), c = hidden (hi, lo adjacent)   (A of MMA1')
   char* wa_lo = wa_hi + A_BYTES;
   char* hb = wa_lo + A_BYTES;                // 2 x { h2 tile r = row (64), c = hidden: hi, lo }   (B of MMA1')
-  char* ht = hb + 4 * B_BYTES;               // 1 x { h2 tile r = hidden, c = row: hi, lo }        (B of MMA3)
-  float* stats = reinterpret_cast<float*>(ht + 2 * B_BYTES);   // 2 x { max[64], 1/Z[64], coef[64], action[64] }
-  __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k, mma1[2], mma2, dlr[2];
+  char* ht = hb + 4 * B_BYTES;               // 2 x { h2 tile r = hidden, c = row: hi, lo }        (B of MMA3)
+  float* stats = reinterpret_cast<float*>(ht + 4 * B_BYTES);   // ring of 4 x { max[64], 1/Z[64], coef[64], action[64] }
+  __shared__ __align__(8) uint64_t tma_a, tma_n[2], tma_k[2], mma1[2], mma2, dlr[2];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cl = tid & 127, qt = (tid >> 7) & 3;
   const bool worker = tid < NTB, issuer = __shfl_sync(FULL_MASK, warp, 0) == NTB / 32;
@@ -957,7 +1325,7 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   const int64_t h64 = h2_tiles64(H.n);
   if (warp == 0) tmem_alloc(&tmem_base, 512);
   if (tid == 0) {
-    mbar_init(&tma_a, 1); mbar_init(&tma_n[0], 1); mbar_init(&tma_n[1], 1); mbar_init(&tma_k, 1);
+    mbar_init(&tma_a, 1); mbar_init(&tma_n[0], 1); mbar_init(&tma_n[1], 1); mbar_init(&tma_k[0], 1); mbar_init(&tma_k[1], 1);
     mbar_init(&mma1[0], 1); mbar_init(&mma1[1], 1); mbar_init(&mma2, 1);
     mbar_init(&dlr[0], NTB / 32); mbar_init(&dlr[1], NTB / 32);
     mbar_fence_init();
@@ -967,9 +1335,10 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   fence_after_sync();
   const uint32_t tb = tmem_base;
   if (issuer && T > 0) {
+    // same two-tiles-ahead operand streams as pass B2 (row statistics in ring slot t & 3)
     auto copy_n = [&](int t) {
       const int r0 = rs0 + t * TN, b = t & 1;
-      float* sp = stats + 256 * b;
+      float* sp = stats + 256 * (t & 3);
       w_expect_tx(&tma_n[b], 2 * B_BYTES + 4 * 64 * 4);
       w_bulk_g2s(hb + 2 * b * B_BYTES, H.himg + himg_n_off(r0 / TN), 2 * B_BYTES, &tma_n[b]);
       w_bulk_g2s(sp, rowm + r0, 64 * 4, &tma_n[b]);
@@ -978,13 +1347,16 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
       w_bulk_g2s(sp + 192, acta + r0, 64 * 4, &tma_n[b]);
     };
     auto copy_k = [&](int t) {
-      w_expect_tx(&tma_k, 2 * B_BYTES);
-      w_bulk_g2s(ht, H.himg + himg_t_off(h64, rs0 / TN + t), 2 * B_BYTES, &tma_k);
+      const int b = t & 1;
+      w_expect_tx(&tma_k[b], 2 * B_BYTES);
+      w_bulk_g2s(ht + 2 * b * B_BYTES, H.himg + himg_t_off(h64, rs0 / TN + t), 2 * B_BYTES, &tma_k[b]);
     };
     w_expect_tx(&tma_a, 2 * A_BYTES);
     w_bulk_g2s(wa_hi, H.img + img_a_off(H.ldA / TN, blockIdx.x), 2 * A_BYTES, &tma_a);
     copy_n(0);
+    if (T > 1) copy_n(1);
     copy_k(0);
+    if (T > 1) copy_k(1);
     wait_or_flag(&tma_a, 0);
     wait_or_flag(&tma_n[0], 0);
     fence_after_sync();
@@ -993,24 +1365,25 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, nb = b ^ 1;
       if (t + 1 < T) {
-        if (t >= 1) {
-          wait_or_flag(&mma1[nb], ((t - 1) >> 1) & 1);
-          wait_or_flag(&dlr[nb], ((t - 1) >> 1) & 1);
-        }
-        copy_n(t + 1);
+        if (t >= 1) wait_or_flag(&dlr[nb], ((t - 1) >> 1) & 1);
         wait_or_flag(&tma_n[nb], ((t + 1) >> 1) & 1);
         fence_after_sync();
         w_issue(tb + T_D1 + 64u * nb, wa_hi, wa_lo, hb + 2 * nb * B_BYTES, hb + (2 * nb + 1) * B_BYTES, false);
         w_commit(&mma1[nb]);
       }
-      if (t >= 1) {
+      if (t + 2 < T) {
+        wait_or_flag(&mma1[b], (t >> 1) & 1);
+        copy_n(t + 2);
+      }
+      if (t >= 1 && t + 1 < T) {
         wait_or_flag(&mma2, (t - 1) & 1);
-        copy_k(t);
+        copy_k(t + 1);
       }
       wait_or_flag(&dlr[b], (t >> 1) & 1);
-      wait_or_flag(&tma_k, t & 1);
+      wait_or_flag(&tma_k[b], (t >> 1) & 1);
       fence_after_sync();
-      w_issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht, ht + B_BYTES, t > 0);   // D3 += d logits^T . h2
+      w_issue_ts(tb + T_D2, tb + t_dl_hi(b), tb + t_dl_lo(b), ht + 2 * b * B_BYTES, ht + (2 * b + 1) * B_BYTES,
+                 t > 0);   // D3 += d logits^T . h2
       w_commit(&mma2);
     }
   }
@@ -1022,7 +1395,7 @@ head_tc_dw3_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
       const int b = t & 1;
       wait_or_flag(&mma1[b], (t >> 1) & 1);
       fence_after_sync();
-      const float* sp = stats + 256 * b;
+      const float* sp = stats + 256 * (t & 3);
       float v[16];
       tmem_ld16(tmem_addr(tb + T_D1 + 64u * b, (warp & 3) * 32, qt * 16), v);
 #pragma unroll
@@ -1106,16 +1479,8 @@ int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const
   return CIRS_OK;
 }
 
-int plan_split(int n, int nA) {
-  const int n_tiles = (nA + TN - 1) / TN, row_tiles = (n + TM - 1) / TM;
-  int want = (2 * 148 + row_tiles - 1) / (row_tiles > 0 ? row_tiles : 1);
-  if (want > MAX_SPLIT) want = MAX_SPLIT;
-  if (want > n_tiles) want = n_tiles;
-  if (want < 1) want = 1;
-  const int per = (n_tiles + want - 1) / want;
-  return (n_tiles + per - 1) / per;
-}
-
+int f_occupancy();
+static bool g_phase_host = false;   // launch the phase-stamped instantiations (cirs_head_tc_debug_phases)
 static int g_tc_mode = -1;   // -1: environment default (CIRS_NO_TC), 0: off, 1: on (TMA-fed kernels), 2: on, register-staged
 static bool tma_on() {
   static int env = -1;
@@ -1125,6 +1490,58 @@ static bool tma_on() {
   }
   return env == 1 && g_tc_mode != 2;
 }
+// Environment switches of the tile pipelines (A/B measurements; defaults are the fast paths)
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+static bool f_ring_on() {
+  static int v = -1;
+  if (v < 0) v = env_int("CIRS_F_RING", 1) ? 1 : 0;
+  return v == 1;
+}
+// Catalogue splits of passes F / B2 (one CTA per SM): the split count that minimises  waves x (tiles per CTA + a fixed
+// per-CTA cost of ~2 tile times: TMEM allocation, pipeline fill, the final partial store).  CIRS_TC_PLAN=0 restores the
+// round-1 rule (about two CTAs per SM's worth of work items).
+static bool f_atm_on() {
+  static int v = -1;
+  if (v < 0) v = env_int("CIRS_F_ATM", 1) ? 1 : 0;
+  return v == 1;
+}
+static bool f_wide_on() {
+  static int v = -1;
+  if (v < 0) v = env_int("CIRS_F_WIDE", 1) ? 1 : 0;
+  return v == 1;
+}
+// tile = columns per tile (64, or 128 for the wide pass F); fixed = per-CTA fixed cost in tile times
+static int plan_split_slots(int n, int nA, int slots, int tile = TN, int fixed = 2) {
+  const int n_tiles = (nA + tile - 1) / tile, row_tiles = (n + TM - 1) / TM;
+  static int plan = -1;
+  if (plan < 0) plan = env_int("CIRS_TC_PLAN", 1);
+  if (plan == 0 || row_tiles <= 0) {
+    int want = (2 * 148 + row_tiles - 1) / (row_tiles > 0 ? row_tiles : 1);
+    if (want > MAX_SPLIT) want = MAX_SPLIT;
+    if (want > n_tiles) want = n_tiles;
+    if (want < 1) want = 1;
+    const int per = (n_tiles + want - 1) / want;
+    return (n_tiles + per - 1) / per;
+  }
+  int best = 1, best_cost = 1 << 30;
+  for (int want = 1; want <= MAX_SPLIT && want <= n_tiles; ++want) {
+    const int per = (n_tiles + want - 1) / want, ns = (n_tiles + per - 1) / per;
+    const int waves = (row_tiles * ns + slots - 1) / slots;
+    const int cost = waves * (per + fixed);
+    if (cost < best_cost || (cost == best_cost && ns > best)) { best_cost = cost; best = ns; }
+  }
+  return best;
+}
+int plan_split(int n, int nA) { return plan_split_slots(n, nA, 148); }
+// pass F has its own split count: its partials (pm, ps) are merged separately from pass B2's (d h2, entropy)
+int plan_split_f(int n, int nA) {
+  if (tma_on() && f_wide_on()) return plan_split_slots(n, nA, 148, WN, 1);
+  return plan_split_slots(n, nA, (!tma_on() || !f_ring_on() || f_atm_on()) ? 296 : 148);
+}
+
 bool head_tc_enabled(int n, int nA, int64_t ldA) {
   if (g_tc_mode < 0) {
     const char* e = getenv("CIRS_NO_TC");
@@ -1139,11 +1556,43 @@ int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n
   if (!once) {
     set_smem(head_tc_stats_kernel, F_SMEM);
     set_smem(head_tc_stats_tma_kernel, FT_SMEM);
+    set_smem(head_tc_stats_wide_kernel<false>, FW_SMEM);
+    set_smem(head_tc_stats_wide_kernel<true>, FW_SMEM);
+    set_smem(head_tc_stats_ring_kernel<false, false>, FR_SMEM);
+    set_smem(head_tc_stats_ring_kernel<false, true>, FR_SMEM);
+    set_smem(head_tc_stats_ring_kernel<true, false>, FRT_SMEM);
+    set_smem(head_tc_stats_ring_kernel<true, true>, FRT_SMEM);
+    // two CTAs of ~100 KB per SM: ask for the largest shared-memory carve-out (the default sizes it for one block)
+    cudaFuncSetAttribute(head_tc_stats_ring_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(head_tc_stats_ring_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(head_tc_stats_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     once = true;
   }
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
+  if (tma_on() && f_wide_on()) {   // 128-column tiles, one CTA per SM (CIRS_F_WIDE=0: the 64-column kernels below)
+    const int n_tiles = (H.nA + WN - 1) / WN, perw = (n_tiles + n_split - 1) / n_split;
+    if (g_phase_host)
+      CIRS_LAUNCH(head_tc_stats_wide_kernel<true>, grid, NTB + 32, FW_SMEM, st, H, idx, act, perw, n_split, pm, ps, la);
+    else
+      CIRS_LAUNCH(head_tc_stats_wide_kernel<false>, grid, NTB + 32, FW_SMEM, st, H, idx, act, perw, n_split, pm, ps, la);
+    CIRS_CHECK_LAUNCH();
+    return CIRS_OK;
+  }
+  if (tma_on() && f_ring_on()) {   // one CTA per SM, ring of three W3 tiles (CIRS_F_RING=0: two CTAs per SM, one tile ahead)
+    // A operand in tensor memory, two CTAs per SM (CIRS_F_ATM=0: A in shared memory, one CTA per SM)
+    if (f_atm_on() && g_phase_host)
+      CIRS_LAUNCH((head_tc_stats_ring_kernel<true, true>), grid, NTF, FRT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
+    else if (f_atm_on())
+      CIRS_LAUNCH((head_tc_stats_ring_kernel<true, false>), grid, NTF, FRT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
+    else if (g_phase_host)
+      CIRS_LAUNCH((head_tc_stats_ring_kernel<false, true>), grid, NTF, FR_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
+    else
+      CIRS_LAUNCH((head_tc_stats_ring_kernel<false, false>), grid, NTF, FR_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
+    CIRS_CHECK_LAUNCH();
+    return CIRS_OK;
+  }
   if (tma_on()) {   // warp-specialised pass F fed by cp.async.bulk (CIRS_NO_TMA=1 selects the register-staged kernel)
     CIRS_LAUNCH(head_tc_stats_tma_kernel, grid, NTF, FT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
     CIRS_CHECK_LAUNCH();
@@ -1159,15 +1608,20 @@ int head_tc_dh2(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   static bool once = false;
   if (!once) {
     set_smem(head_tc_dh2_kernel, B2_SMEM);
-    set_smem(head_tc_dh2_tma_kernel, B2T_SMEM);
+    set_smem(head_tc_dh2_tma_kernel<false>, B2T_SMEM);
+    set_smem(head_tc_dh2_tma_kernel<true>, B2T_SMEM);
     once = true;
   }
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
   if (tma_on()) {
-    CIRS_LAUNCH(head_tc_dh2_tma_kernel, grid, NTB + 32, B2T_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split, dh2_part,
-                ent_part);
+    if (g_phase_host)
+      CIRS_LAUNCH(head_tc_dh2_tma_kernel<true>, grid, NTB + 32, B2T_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split,
+                  dh2_part, ent_part);
+    else
+      CIRS_LAUNCH(head_tc_dh2_tma_kernel<false>, grid, NTB + 32, B2T_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split,
+                  dh2_part, ent_part);
     CIRS_CHECK_LAUNCH();
     return CIRS_OK;
   }
@@ -1203,9 +1657,37 @@ int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   return CIRS_OK;
 }
 
+int f_occupancy() {
+  int n = 0;
+  if (f_atm_on()) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, head_tc_stats_ring_kernel<true, false>, NTF, FRT_SMEM);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, head_tc_stats_ring_kernel<false, false>, NTF, FR_SMEM);
+  return n;
+}
+
 }  // namespace cirs_head_tc
 
 extern "C" void cirs_head_tc_enable(int on) { cirs_head_tc::g_tc_mode = on < 0 ? -1 : (on > 2 ? 1 : on); }
+
+// debug: per-phase cycle counters of the ring-fed pass F and the TMA-fed pass B2 (see g_phase).  enable != 0 switches
+// the stamping on; out (64 values, host memory, may be null) receives the counters accumulated so far; reset != 0 clears
+// them.  Synchronises the device.
+extern "C" int cirs_head_tc_debug_phases(int32_t enable, int64_t* out64_h, int32_t reset) {
+  cudaDeviceSynchronize();
+  if (out64_h) {
+    cudaMemcpyFromSymbol(out64_h, cirs_head_tc::g_phase, 64 * sizeof(unsigned long long));
+    out64_h[63] = cirs_head_tc::f_occupancy();   // resident CTAs per SM of the pass-F kernel in use (runtime's estimate)
+  }
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(cirs_head_tc::g_phase, z, sizeof(z));
+  }
+  cirs_head_tc::g_phase_host = enable != 0;
+  {   // experiment switch of the stamped pass-F kernel (bits 4-5 of enable; see head_tc_stats_ring_kernel)
+    unsigned long long mode = (unsigned long long)((enable >> 4) & 3);
+    cudaMemcpyToSymbol(cirs_head_tc::g_phase, &mode, sizeof(mode), 62 * sizeof(unsigned long long));
+  }
+  return cudaGetLastError() == cudaSuccess ? CIRS_OK : CIRS_ERR_CUDA;
+}
 
 // debug: 1 if any tensor-core kernel gave up waiting on an mbarrier since the last call (synchronises the device)
 extern "C" int cirs_head_tc_timeout(void) {

@@ -48,6 +48,8 @@ int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const
 
 // number of catalogue splits used for n rows (<= MAX_SPLIT); partial arrays are [n, n_split]
 int plan_split(int n, int nA);
+// ... and of pass F alone (its partials pm / ps are merged separately from pass B2's)
+int plan_split_f(int n, int nA);
 
 // pass F.  act_of_row: action of row r = act[idx ? idx[r] : r] (may be NULL: no logit is picked).
 // Outputs: pm, ps [n, n_split] partial (max, sum exp(l - max)); la[n] logit of the taken action.

@@ -629,7 +629,7 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
   if (rc) return rc;
   int n_split = 0;
   if (act) {   // log-probs of the stored actions
-    n_split = plan_split(n, w->n_action);
+    n_split = plan_split_f(n, w->n_action);
     HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action, img, himg};
     rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
     if (rc) return rc;
@@ -727,9 +727,10 @@ extern "C" int cirs_ppo_minibatch(const cirs_policy_weights* w, const cirs_polic
     tc = true;
     tc_split = cirs_head_tc::plan_split(n, nA);
     cirs_head_tc::HeadTc H{ws.h2, n, w->w3t, ldA, w->b3, nA, ws.w3img, ws.h2img};
-    int rc = cirs_head_tc::head_tc_stats(H, idx, act, tc_split, ws.pm, ws.ps, ws.la, st);
+    const int f_split = cirs_head_tc::plan_split_f(n, nA);
+    int rc = cirs_head_tc::head_tc_stats(H, idx, act, f_split, ws.pm, ws.ps, ws.la, st);
     if (rc) return rc;
-    CIRS_LAUNCH(row_loss_tc_kernel, (n + 127) / 128, 128, 0, st, n, tc_split, *cfg, n_global, idx, act, adv, returns,
+    CIRS_LAUNCH(row_loss_tc_kernel, (n + 127) / 128, 128, 0, st, n, f_split, *cfg, n_global, idx, act, adv, returns,
                 v_old, logp_old, adv_stat, ws);
     CIRS_CHECK_LAUNCH();
     rc = cirs_head_tc::head_tc_dh2(H, ws.rowm, ws.rinvz, ws.coef, ws.acta, tc_split, ws.dh2_part, ws.ent_part, st);

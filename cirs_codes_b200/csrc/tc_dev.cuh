@@ -104,15 +104,34 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 // Bounded spin: returns false (instead of hanging the GPU) if the phase does not complete.
+// CIRS_MBAR_MODE (compile time, experiments): 0 = try_wait (may suspend the thread for a system-dependent time), 1 =
+// test_wait (pure polling), 2 = try_wait with a 32 ns suspend-time hint.
+#ifndef CIRS_MBAR_MODE
+#define CIRS_MBAR_MODE 0
+#endif
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
     uint32_t ok;
+#if CIRS_MBAR_MODE == 1
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+#elif CIRS_MBAR_MODE == 2
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity), "r"(32u)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(a), "r"(parity)
         : "memory");
+#endif
     if (ok) return true;
   }
   return false;
