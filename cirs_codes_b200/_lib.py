@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcirs_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_LAYERS = 4
 HIDDEN = 64
 
@@ -105,6 +105,7 @@ PROTOTYPES = {
     "cirs_actor_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp, fp,
                                 fp, fp]),
     "cirs_policy_eval": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp, fp]),
+    "cirs_policy_eval_dev": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp, fp, fp]),
     "cirs_actorprob_sample": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, i64, fp, u64, u64, fp, i32, fp, fp, fp,
                                     fp, fp]),
     "cirs_actorprob_eval": (i32, [P(PolicyWeightsStruct), i32, fp, fp, fp, fp, fp, fp]),

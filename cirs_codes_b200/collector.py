@@ -317,17 +317,21 @@ class Collector:
         if hasattr(self.policy, "post_collect"):
             self.policy.post_collect(buf)                           # multi-GPU: transition counts ride on the read-back
         flag = f["ws_roll"][128:132].view(torch.int32) if self.persistent else None
-        lens, rews = self._read_back(buf.d_len, env.cum_rew, flag)  # the collect's D2H read (one synchronisation)
+        # the collect's D2H read (one synchronisation); the policy may queue the update's front behind the copies
+        lens, rews = self._read_back(buf.d_len, env.cum_rew, flag, getattr(self.policy, "pre_update", None), buf)
         self.d2h_bytes += 4 * B + 8 * B + 4
         buf.set_from_device(lens)
         # everything else the reference's result dict carries (completion-ordered copies, means / deviations) is
         # computed when it is first read: it is logging data, and the update that follows must not wait for it
         return _LazyResult(rews, lens, B, L)
 
-    def _read_back(self, d_len, d_rew, d_flag=None):
+    def _read_back(self, d_len, d_rew, d_flag=None, queue_behind=None, buf=None):
         """Episode lengths (i32) and cumulative rewards (f64) -> pinned host buffers, asynchronous copies and ONE
-        stream synchronisation.  ``d_flag``: the rollout kernel's "an mbarrier wait gave up" word (never expected):
-        a set flag means the head phase computed with incomplete data, so the collect raises instead of returning."""
+        synchronisation (on an event recorded right behind the copies).  ``d_flag``: the rollout kernel's "an mbarrier
+        wait gave up" word (never expected): a set flag means the head phase computed with incomplete data, so the
+        collect raises instead of returning.  ``queue_behind(buf)``: called after the copies are queued and before the
+        host waits -- PPOPolicy.pre_update queues process_fn's kernels there, so the GPU has work while the host wakes
+        up and marshals the update's first launches."""
         B = self.env_num
         if not hasattr(self, "_pin_out"):
             self._pin_out = (torch.zeros(B, dtype=torch.int32).pin_memory(),
@@ -339,7 +343,14 @@ class Collector:
         p_rew.copy_(d_rew[:B], non_blocking=True)
         if d_flag is not None:
             p_flag.copy_(d_flag, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if queue_behind is None:
+            torch.cuda.current_stream().synchronize()
+        else:
+            if not hasattr(self, "_rb_event"):
+                self._rb_event = torch.cuda.Event()
+            self._rb_event.record()
+            queue_behind(buf)
+            self._rb_event.synchronize()
         n_len, n_rew, n_flag = self._pin_np
         if d_flag is not None and n_flag[0]:
             raise _lib.CirsError("cirs_rollout_kuaishou: a tcgen05 mbarrier wait timed out; the rollout is invalid")

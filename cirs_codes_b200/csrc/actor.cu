@@ -14,7 +14,8 @@
 
 namespace cirs_head_tc {
 int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_idx, const float* obs,
-                   const int32_t* act, float* value, float* logp, void* workspace, cudaStream_t st);
+                   const int32_t* act, float* value, float* logp, void* workspace, cudaStream_t st,
+                   const int32_t* n_dev = nullptr);
 }
 
 namespace {
@@ -100,4 +101,22 @@ extern "C" int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, co
   P.state = obs; P.state_stride = w->dim_state; P.noise_q = nullptr; P.mode = MODE_EVAL; P.seen = nullptr;
   P.act_in = act; P.value = value;
   return run_head(P, nullptr, act ? logp : nullptr, workspace, (cudaStream_t)stream);
+}
+
+// cirs_policy_eval with the row count still ON THE DEVICE: n_cap sizes grids / layouts / the workspace, rows >=
+// min(n_cap, *n_dev) are skipped.  Lets the host queue process_fn's evaluations behind the rollout kernel BEFORE it has
+// read the collect's transition count back (PPOPolicy.post_collect), so they run while the host is still waking up.
+// Tensor-core path only (discrete actor, 128-column pass F).
+extern "C" int cirs_policy_eval_dev(const cirs_policy_weights* w, int32_t n_cap, const int32_t* n_dev,
+                                    const int32_t* row_idx, const float* obs, const int32_t* act, float* value,
+                                    float* logp, void* workspace, void* stream) {
+  if (!w || !obs || !workspace || !n_dev || n_cap <= 0 || (act && !logp)) {
+    cirs_set_error("cirs_policy_eval_dev: bad argument");
+    return CIRS_ERR_ARG;
+  }
+  if (!(w->sigma == nullptr && w->dim_state <= 32 && cirs_head_tc::head_tc_enabled(n_cap, w->n_action, w->ld_action))) {
+    cirs_set_error("cirs_policy_eval_dev: needs the tensor-core head (discrete actor, n_action >= 64, CIRS_NO_TC unset)");
+    return CIRS_ERR_ARG;
+  }
+  return cirs_head_tc::policy_eval_tc(w, n_cap, row_idx, obs, act, value, logp, workspace, (cudaStream_t)stream, n_dev);
 }

@@ -192,12 +192,17 @@ constexpr size_t FRONT_SMEM = sizeof(float) * (32 * HID + HID * HID + 2 * 32 * 3
 __global__ void __launch_bounds__(FRONT_NT)
 head_tc_front_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ idx, const float* __restrict__ obs,
                      float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ value,
-                     float* __restrict__ himg, int n_pack, float* __restrict__ img) {
+                     float* __restrict__ himg, int n_pack, float* __restrict__ img,
+                     const int32_t* __restrict__ n_dev) {
   extern __shared__ __align__(16) float fsm[];
   if ((int)blockIdx.x < n_pack) {
     pack_w3_tile(blockIdx.x, W.w3t, W.ld_action, W.b3, W.n_action, img, reinterpret_cast<float(*)[TN + 1]>(fsm));
     return;
   }
+  // n sizes the grid and the image layout; with n_dev the rows that exist are min(n, *n_dev) (count still on the device)
+  const int n_lay = n;
+  if (n_dev) n = min(n, __ldg(n_dev));
+  if ((int)(blockIdx.x - n_pack) * TN >= n) return;
   constexpr int R = 32;
   float* s_w1 = fsm;                     // W1t [dim_state <= 32][64]
   float* s_w2 = s_w1 + 32 * HID;         // W2t [64][64]
@@ -267,7 +272,7 @@ head_tc_front_kernel(cirs_policy_weights W, int n, const int32_t* __restrict__ i
   // ---- the tile's h2 images (layout of head_tc_pack_h2_kernel); element (row r, hidden k) = hT of half r / 32
   float(*hA)[R + 1] = reinterpret_cast<float(*)[R + 1]>(s_w2 + HID * HID + 2 * 32 * 33);
   auto Hrk = [&](int r, int k) { return hA[(r >> 5) * HID + k][r & 31]; };
-  const int64_t n64 = h2_tiles64(n);
+  const int64_t n64 = h2_tiles64(n_lay);
   float4* n_hi = reinterpret_cast<float4*>(himg + himg_n_off(tile));
   float4* n_lo = n_hi + B_BYTES / 16;
   float4* t_hi = reinterpret_cast<float4*>(himg + himg_t_off(n64, tile));
@@ -727,8 +732,11 @@ template <bool PH>
 __global__ void __launch_bounds__(NTB + 32, 1)
 head_tc_stats_wide_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act,
                           int tiles_per_split, int n_split, float* __restrict__ pm, float* __restrict__ ps,
-                          float* __restrict__ la) {
+                          float* __restrict__ la, const int32_t* __restrict__ n_dev) {
   extern __shared__ __align__(1024) char smem[];
+  // H.n sizes the grid and the h2 image layout; with n_dev the rows that exist are min(H.n, *n_dev)
+  const int n_rows = n_dev ? min(H.n, __ldg(n_dev)) : H.n;
+  if ((int)blockIdx.x * TM >= n_rows) return;
   char* a_hi = smem;
   char* a_lo = a_hi + A_BYTES;
   char* bring = a_lo + A_BYTES;                                            // 2 x { hi, lo } of a 128-column W3 tile
@@ -790,7 +798,7 @@ head_tc_stats_wide_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32
     pc.count(4, 2 * T);   // in 64-column units, comparable with the ring kernel's counters
   }
   int a = -1;
-  if (worker && act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
+  if (worker && act != nullptr && r0 + row < n_rows) a = act[idx ? idx[r0 + row] : r0 + row];
   float m = MASKED, s = 0.f, lav = 0.f;
   bool found = false;
   if (worker) {
@@ -840,7 +848,7 @@ head_tc_stats_wide_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32
   }
   fence_before_sync();
   __syncthreads();
-  if (worker && q == 0 && r0 + row < H.n) {
+  if (worker && q == 0 && r0 + row < n_rows) {
     float M = m;
 #pragma unroll
     for (int k = 1; k < 4; ++k) M = fmaxf(M, sm[tid + k * TM]);
@@ -1465,7 +1473,7 @@ int head_tc_pack_h2(const float* h2, int n, float* himg, cudaStream_t st) {
 }
 
 int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const float* obs, float* h1, float* h2,
-                  float* value, float* himg, float* img, cudaStream_t st) {
+                  float* value, float* himg, float* img, cudaStream_t st, const int32_t* n_dev) {
   static bool once = false;
   if (!once) {
     cudaFuncSetAttribute(head_tc_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM);
@@ -1474,7 +1482,7 @@ int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const
   const int n_pack = img ? (int)(w->ld_action / TN) : 0;
   const int tiles = himg ? (int)h2_tiles64(n) : (n + TN - 1) / TN;
   CIRS_LAUNCH(head_tc_front_kernel, n_pack + tiles, FRONT_NT, FRONT_SMEM, st, *w, n, idx, obs, h1, h2, value, himg,
-              n_pack, img);
+              n_pack, img, n_dev);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }
@@ -1551,7 +1559,7 @@ bool head_tc_enabled(int n, int nA, int64_t ldA) {
 }
 
 int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n_split, float* pm, float* ps,
-                  float* la, cudaStream_t st) {
+                  float* la, cudaStream_t st, const int32_t* n_dev) {
   static bool once = false;
   if (!once) {
     set_smem(head_tc_stats_kernel, F_SMEM);
@@ -1574,11 +1582,17 @@ int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n
   if (tma_on() && f_wide_on()) {   // 128-column tiles, one CTA per SM (CIRS_F_WIDE=0: the 64-column kernels below)
     const int n_tiles = (H.nA + WN - 1) / WN, perw = (n_tiles + n_split - 1) / n_split;
     if (g_phase_host)
-      CIRS_LAUNCH(head_tc_stats_wide_kernel<true>, grid, NTB + 32, FW_SMEM, st, H, idx, act, perw, n_split, pm, ps, la);
+      CIRS_LAUNCH(head_tc_stats_wide_kernel<true>, grid, NTB + 32, FW_SMEM, st, H, idx, act, perw, n_split, pm, ps, la,
+                  n_dev);
     else
-      CIRS_LAUNCH(head_tc_stats_wide_kernel<false>, grid, NTB + 32, FW_SMEM, st, H, idx, act, perw, n_split, pm, ps, la);
+      CIRS_LAUNCH(head_tc_stats_wide_kernel<false>, grid, NTB + 32, FW_SMEM, st, H, idx, act, perw, n_split, pm, ps, la,
+                  n_dev);
     CIRS_CHECK_LAUNCH();
     return CIRS_OK;
+  }
+  if (n_dev) {
+    cirs_set_error("head_tc_stats: a device-resident row count needs the 128-column pass F (CIRS_F_WIDE / CIRS_NO_TMA unset)");
+    return CIRS_ERR_ARG;
   }
   if (tma_on() && f_ring_on()) {   // one CTA per SM, ring of three W3 tiles (CIRS_F_RING=0: two CTAs per SM, one tile ahead)
     // A operand in tensor memory, two CTAs per SM (CIRS_F_ATM=0: A in shared memory, one CTA per SM)

@@ -43,8 +43,10 @@ int head_tc_pack_h2(const float* h2, int n, float* himg, cudaStream_t st);
 // Front end of a pass in one launch: policy trunk of n gathered observation rows (h1 optional, h2, critic value), the
 // h2 images (himg, optional) written by the same CTAs, and -- concurrently, by further CTAs -- the W3 images (img,
 // optional; pass it whenever the weights changed since they were last packed).
+// n_dev (optional, DEVICE int32): the true row count when it is not known on the host yet -- n is then a host-side
+// CAPACITY (grid and image layout are sized by n, rows >= min(n, *n_dev) are skipped).
 int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const float* obs, float* h1, float* h2,
-                  float* value, float* himg, float* img, cudaStream_t st);
+                  float* value, float* himg, float* img, cudaStream_t st, const int32_t* n_dev = nullptr);
 
 // number of catalogue splits used for n rows (<= MAX_SPLIT); partial arrays are [n, n_split]
 int plan_split(int n, int nA);
@@ -54,7 +56,7 @@ int plan_split_f(int n, int nA);
 // pass F.  act_of_row: action of row r = act[idx ? idx[r] : r] (may be NULL: no logit is picked).
 // Outputs: pm, ps [n, n_split] partial (max, sum exp(l - max)); la[n] logit of the taken action.
 int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n_split, float* pm, float* ps,
-                  float* la, cudaStream_t st);
+                  float* la, cudaStream_t st, const int32_t* n_dev = nullptr);   // n_dev: as for head_tc_front (wide kernel only)
 
 // pass B2.  rowm / rinvz: softmax max and 1 / sum per row; coef: d loss / d logp per row; acta: taken action per row.
 // Outputs: dh2_part [n_split, n, 64] (sum over splits = d loss / d h2 through the actor head);

@@ -406,8 +406,10 @@ __global__ void ent_merge_kernel(int n, int n_split, const float* __restrict__ e
 // critic value; outputs are indexed by buffer slot like the FFMA path (actor_combine_row, out_by_k = 0)
 __global__ void eval_merge_kernel(int n, int n_split, const int32_t* __restrict__ idx, const float* __restrict__ pm,
                                   const float* __restrict__ ps, const float* __restrict__ la,
-                                  const float* __restrict__ vtmp, float* __restrict__ value, float* __restrict__ logp) {
+                                  const float* __restrict__ vtmp, float* __restrict__ value, float* __restrict__ logp,
+                                  const int32_t* __restrict__ n_dev) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, __ldg(n_dev));
   if (r >= n) return;
   const int o = idx ? idx[r] : r;
   if (value) value[o] = vtmp[r];
@@ -617,7 +619,8 @@ int64_t policy_eval_tc_image_bytes(int64_t ldA) {
   return (int64_t)sizeof(float) * align64(head_tc_image_floats(ldA < 128 ? 128 : ldA));
 }
 int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_idx, const float* obs,
-                   const int32_t* act, float* value, float* logp, void* workspace, cudaStream_t st) {
+                   const int32_t* act, float* value, float* logp, void* workspace, cudaStream_t st,
+                   const int32_t* n_dev) {
   float* p = reinterpret_cast<float*>(workspace);
   auto take = [&](int64_t cnt) { float* r = p; p += align64(cnt); return r; };
   float *h1 = take((int64_t)n * HID), *h2 = take((int64_t)n * HID), *vtmp = take(n);
@@ -625,17 +628,17 @@ int policy_eval_tc(const cirs_policy_weights* w, int32_t n, const int32_t* row_i
   float* himg = take(head_tc_h2_image_floats(n));
   float* img = take(head_tc_image_floats(w->ld_action));
   // trunk, h2 images and W3 images in one launch (head_tc_front); a value-only evaluation needs the trunk alone
-  int rc = head_tc_front(w, n, row_idx, obs, h1, h2, vtmp, act ? himg : nullptr, act ? img : nullptr, st);
+  int rc = head_tc_front(w, n, row_idx, obs, h1, h2, vtmp, act ? himg : nullptr, act ? img : nullptr, st, n_dev);
   if (rc) return rc;
   int n_split = 0;
   if (act) {   // log-probs of the stored actions
     n_split = plan_split_f(n, w->n_action);
     HeadTc H{h2, n, w->w3t, w->ld_action, w->b3, w->n_action, img, himg};
-    rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st);
+    rc = head_tc_stats(H, row_idx, act, n_split, pm, ps, la, st, n_dev);
     if (rc) return rc;
   }
   CIRS_LAUNCH(eval_merge_kernel, (n + 255) / 256, 256, 0, st, n, n_split, row_idx, pm, ps, la, vtmp, value,
-              act ? logp : nullptr);
+              act ? logp : nullptr, n_dev);
   CIRS_CHECK_LAUNCH();
   return CIRS_OK;
 }

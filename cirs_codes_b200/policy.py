@@ -16,6 +16,7 @@ Gradients are summed with ONE all-reduce per minibatch (torch.distributed, NCCL 
 moments of all minibatches of a repeat, the return moments and the losses are reduced once per repeat / update.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -170,6 +171,7 @@ class PPOPolicy:
         a = {k[len("actor."):]: v for k, v in sd.items() if k.startswith("actor.")}
         c = {k[len("critic."):]: v for k, v in sd.items() if k.startswith("critic.")}
         self.flat.copy_(self.layout.pack(params.policy_sd_from_reference(a, c), self.device))
+        self._pre = None   # evaluations queued by post_collect used the previous weights
         if "ret_rms" in sd:   # checkpoints written by round 1 of this package
             self.ret_rms.t.copy_(torch.as_tensor(sd["ret_rms"], dtype=torch.float64))
 
@@ -381,11 +383,6 @@ class PPOPolicy:
             return dist, dist.get_world_size(self.group)
         return None, 1
 
-    def _allreduce(self, t):
-        dist, world = self._world()
-        if world > 1:
-            dist.all_reduce(t, group=self.group)
-
     # ------------------------------------------------------------------ multi-GPU plumbing
     def _comm(self):
         """The C-side communicator of this policy's process group (csrc/comm.cu; NCCL), created on first use: rank 0
@@ -401,6 +398,72 @@ class PPOPolicy:
             from .parallel import create_comm
             self._c_comm = create_comm(dist, self.group, self.device)
         return self._c_comm
+
+    # ---- process_fn's kernels queued BEFORE the collect's read-back
+    pre_eval = True     # set False (or CIRS_NO_PRE_EVAL=1) to queue them from process_fn as the reference's order has it
+
+    def pre_update(self, buffer):
+        """Called by the fused Collector after it has queued its read-back copies and before it waits for them.  The
+        collect ends with a host synchronisation (lengths, rewards, transition count) and the update's first kernel used
+        to be launched ~50 us after it: sync wake-up, bookkeeping, argument marshalling -- with the GPU idle.
+        process_fn's kernels (V(obs) + old log-probs, V(obs'), GAE) only need the transition count to size their grids,
+        so they are queued here, behind the copies, with the count still on the device (cirs_policy_eval_dev; capacity = the previous update's count + 12.5 %, at least 1024 rows) and they
+        run while the host wakes up.  process_fn skips its own launches when the count fits the capacity and repeats
+        them otherwise.  Same kernels on the same inputs: only the catalogue-split count of pass F (planned for the
+        capacity) may differ from the in-order run, i.e. the summation order of the soft-max partials."""
+        self._pre = None
+        n_prev = getattr(self, "_n_prev", 0)
+        if (not self.pre_eval or os.environ.get("CIRS_NO_PRE_EVAL") == "1" or self.continuous or n_prev <= 0
+                or not self._tc_eval_ok()):
+            return
+        n_slots = buffer.maxsize
+        cap = min(n_slots, max(1024, -(-(n_prev + n_prev // 8) // 128) * 128))
+        self._process_kernels(buffer, cap, buffer.d_env_off[buffer.buffer_num:buffer.buffer_num + 1])
+        self._pre = (buffer, cap)
+
+    def _tc_eval_ok(self):
+        if getattr(self, "_tc_ok", None) is None:
+            na = int(self._w.n_action)
+            self._tc_ok = (na >= 64 and int(self._w.dim_state) <= 32 and os.environ.get("CIRS_NO_TC", "0") in ("", "0")
+                           and os.environ.get("CIRS_NO_TMA", "0") in ("", "0")
+                           and os.environ.get("CIRS_F_WIDE", "1") not in ("0",))
+        return self._tc_ok
+
+    def _process_kernels(self, buffer, n, n_dev=None, indices=None):
+        """V(obs) and the old log-probs, V(obs'), then GAE / returns (a2c.py:80-109, ppo.py:96-109): three C calls.
+        ``n_dev`` (device int32[1]): the row count is still on the device and ``n`` is a capacity."""
+        n_slots, dev = buffer.maxsize, self.device
+        B, L = buffer.buffer_num, buffer.sub_size
+        if getattr(self, "_slot_n", 0) != n_slots:
+            self._slot_n = n_slots
+            z = lambda dt=torch.float32: torch.zeros(n_slots, dtype=dt, device=dev)  # noqa: E731
+            self.v_s, self.v_next, self.logp_old, self.returns, self.adv = z(), z(), z(), z(), z()
+            self.d_obs = torch.zeros(n_slots, self.dim_state, dtype=torch.float32, device=dev)
+            self._gae_scratch = torch.zeros(2 * B, dtype=torch.float64, device=dev)
+            self._moments = torch.zeros(3, dtype=torch.float64, device=dev)
+        indices = buffer.d_index if indices is None else indices
+        aws = self._actor_ws(n_slots)   # sized for a full buffer once: no allocation inside later updates
+        st = _lib.stream()
+        if self.continuous:
+            _lib.call("cirs_actorprob_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
+                      _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), st)
+            _lib.call("cirs_actorprob_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
+                      _lib.ptr(self.v_next), None, st)
+        elif n_dev is not None:
+            _lib.call("cirs_policy_eval_dev", C.byref(self._w), n, _lib.ptr(n_dev), _lib.ptr(indices),
+                      _lib.ptr(buffer.obs), _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old),
+                      _lib.ptr(aws), st)
+            _lib.call("cirs_policy_eval_dev", C.byref(self._w), n, _lib.ptr(n_dev), _lib.ptr(indices),
+                      _lib.ptr(buffer.obs_next), None, _lib.ptr(self.v_next), None, _lib.ptr(aws), st)
+        else:
+            _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
+                      _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(aws), st)
+            _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
+                      _lib.ptr(self.v_next), None, _lib.ptr(aws), st)
+        _lib.call("cirs_compute_returns", B, L, _lib.ptr(buffer.d_len), _lib.ptr(self.v_s), _lib.ptr(self.v_next),
+                  _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_done), self._gamma, self._lambda,
+                  _lib.ptr(self.ret_rms.t) if self._rew_norm else None, _lib.ptr(self._gae_scratch),
+                  _lib.ptr(self._moments) if self._rew_norm else None, _lib.ptr(self.returns), _lib.ptr(self.adv), st)
 
     def post_collect(self, buffer):
         """Called by the fused Collector between the rollout kernel and its read-back: every rank's transition count
@@ -439,32 +502,16 @@ class PPOPolicy:
     def process_fn(self, buffer, indices):
         """core/policy/ppo.py:96-109 + a2c.py:80-109: critic values, GAE / returns, old log-probs -- all on the
         device, results stay per buffer slot."""
-        n_slots, dev = buffer.maxsize, self.device
-        B, L = buffer.buffer_num, buffer.sub_size
-        if getattr(self, "_slot_n", 0) != n_slots:
-            self._slot_n = n_slots
-            z = lambda dt=torch.float32: torch.zeros(n_slots, dtype=dt, device=dev)  # noqa: E731
-            self.v_s, self.v_next, self.logp_old, self.returns, self.adv = z(), z(), z(), z(), z()
-            self.d_obs = torch.zeros(n_slots, self.dim_state, dtype=torch.float32, device=dev)
-            self._gae_scratch = torch.zeros(2 * B, dtype=torch.float64, device=dev)
-            self._moments = torch.zeros(3, dtype=torch.float64, device=dev)
         n = indices.numel()
-        aws = self._actor_ws(n_slots)   # sized for a full buffer once: no allocation inside later updates
+        dev = self.device
+        pre, self._pre = getattr(self, "_pre", None), None
+        self._n_prev = n
+        d_index = getattr(buffer, "d_index", None)
+        if not (pre is not None and pre[0] is buffer and n <= pre[1] and d_index is not None
+                and indices.data_ptr() == d_index.data_ptr()):
+            # not queued by post_collect (first update, foreign collector, count above the capacity): in order, here
+            self._process_kernels(buffer, n, indices=indices)
         st = _lib.stream()
-        if self.continuous:
-            _lib.call("cirs_actorprob_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
-                      _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), st)
-            _lib.call("cirs_actorprob_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
-                      _lib.ptr(self.v_next), None, st)
-        else:
-            _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs),
-                      _lib.ptr(buffer.d_act), _lib.ptr(self.v_s), _lib.ptr(self.logp_old), _lib.ptr(aws), st)
-            _lib.call("cirs_policy_eval", C.byref(self._w), n, _lib.ptr(indices), _lib.ptr(buffer.obs_next), None,
-                      _lib.ptr(self.v_next), None, _lib.ptr(aws), st)
-        _lib.call("cirs_compute_returns", B, L, _lib.ptr(buffer.d_len), _lib.ptr(self.v_s), _lib.ptr(self.v_next),
-                  _lib.ptr(buffer.d_rew), _lib.ptr(buffer.d_done), self._gamma, self._lambda,
-                  _lib.ptr(self.ret_rms.t) if self._rew_norm else None, _lib.ptr(self._gae_scratch),
-                  _lib.ptr(self._moments) if self._rew_norm else None, _lib.ptr(self.returns), _lib.ptr(self.adv), st)
         dist, world = self._world()
         self._n_all = None
         pin = getattr(self, "_n_all_pin", None)

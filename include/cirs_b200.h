@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CIRS_ABI_VERSION 8
+#define CIRS_ABI_VERSION 9
 #define CIRS_MAX_LAYERS 4
 #define CIRS_HIDDEN 64 /* tianshou Net hidden_sizes=[64,64], CIRS-RL-kuaishou.py:88 */
 
@@ -293,6 +293,12 @@ int cirs_actor_sample(const cirs_policy_weights* w, int32_t n_rows, const int32_
  * only).  value / logp are indexed like obs (by row_idx[r] when given). */
 int cirs_policy_eval(const cirs_policy_weights* w, int32_t n_rows, const int32_t* row_idx, const float* obs,
                      const int32_t* act, float* value, float* logp, void* workspace, void* stream);
+/* The same with the row count still on the DEVICE (n_dev, i32): n_cap sizes grids / layouts / the workspace and rows
+ * >= min(n_cap, *n_dev) are skipped.  The host can queue process_fn's evaluations behind the rollout before it has read
+ * the collect's transition count back (core/collector.py:147-367 returns before policy.update() starts in the reference;
+ * here the two overlap).  Tensor-core head only; CIRS_ERR_ARG otherwise. */
+int cirs_policy_eval_dev(const cirs_policy_weights* w, int32_t n_cap, const int32_t* n_dev, const int32_t* row_idx,
+                         const float* obs, const int32_t* act, float* value, float* logp, void* workspace, void* stream);
 
 /* policy.forward() for the continuous actor (core/policy/ppo.py:144-156 with dist_fn = Independent(Normal),
  * CIRS-RL-taobao.py:228-232): mu = max_action * tanh(W3 h + b3), std = exp(sigma); act = eps * std + mu

@@ -105,6 +105,19 @@ def main():
     other = mine.clone()
     dist.broadcast(other, src=0)
     assert torch.equal(mine, other), "replicas diverged"
+    # ---- the collect's count exchange (PPOPolicy.post_collect: the counts ride on the collect's read-back)
+    col2.collect(n_episode=B, users=users[rank * B:(rank + 1) * B])
+    assert pol2._n_all_pin is not None
+    counts = [None] * world
+    dist.all_gather_object(counts, int(buf2._lengths.sum()))
+    assert pol2._n_all_pin[0].numpy().tolist() == counts, (pol2._n_all_pin[0].numpy().tolist(), counts)
+    out2 = pol2.update(0, buf2, batch_size=c["batch_size"], repeat=c["repeat"])
+    torch.cuda.synchronize()
+    assert np.isfinite(np.asarray(out2["loss"])).all() and pol2._n_all.tolist() == counts
+    mine = torch.cat([pol2.flat, trk2.flat])
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other), "replicas diverged after the collect-driven update"
     dist.barrier()
     if rank == 0:
         print(f"DIST_OK world={world} n={n} n_all={n_all} minibatches={len(n_glob)} "
