@@ -86,7 +86,7 @@ class PPOPolicy:
         self.c_loop = True       # False: per-minibatch entry points driven from Python (tests; gloo groups)
         # K6's forward half on a side stream beside the PPO minibatches (cirs_tracker_train phase 1 / 2).  Measured on
         # B200 at configs[1]: 1.672 vs 1.654 ms per iteration -- the stream fork / join costs what the overlap hides, so off
-        self.overlap_tracker_forward = False
+        self.overlap_tracker_forward = os.environ.get("CIRS_TRK_OVERLAP") == "1"
         self.h2d_bytes = self.d2h_bytes = 0          # host<->device traffic of the last update()
         # The reference builds ONE Net shared by actor and critic (CIRS-RL-kuaishou.py:245-247) and lists its tensors
         # twice in optim_RL / clip_grad_norm_; this implementation reproduces exactly that structure.

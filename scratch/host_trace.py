@@ -32,6 +32,10 @@ orig_sync = torch.cuda.Stream.synchronize
 def sync(self):
     t0 = time.perf_counter_ns(); r = orig_sync(self); log.append(("SYNC", t0, time.perf_counter_ns())); return r
 torch.cuda.Stream.synchronize = sync
+orig_esync = torch.cuda.Event.synchronize
+def esync(self):
+    t0 = time.perf_counter_ns(); r = orig_esync(self); log.append(("EVENT SYNC", t0, time.perf_counter_ns())); return r
+torch.cuda.Event.synchronize = esync
 for it in range(3):
     fr.restore(); torch.cuda.synchronize()
     log.clear()
