@@ -403,11 +403,16 @@ def gpu_arm(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(K, resident):
-        steps, h2d, d2h, ms = 0, 0, 0, 0.0
-        per_step = []
+    def timed(K, mode):
+        """K timed iterations per arm.  mode "res" / "e2e": one arm; mode "both": the two arms ALTERNATE (resident, end to
+        end, resident, ...) so that slow drifts of the box -- clocks, the other ranks' skew -- hit both alike; every
+        iteration is bracketed by its own pair of CUDA events either way.  Returns {arm: (ms, env-steps, h2d, d2h, launches)}
+        with ms = max over ranks of the arm's summed iteration times."""
+        arms = ("res", "e2e") if mode == "both" else (mode,)
+        acc = {a: dict(steps=0, h2d=0, d2h=0, ms=0.0, launches=0, per_step=[]) for a in arms}
         barrier()
-        for k in range(K):
+        for k in range(K * len(arms)):
+            a = arms[k % len(arms)]
             frozen.restore()
             flush.fill_(float(k))                       # evict L2 between timed iterations (untimed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -415,24 +420,31 @@ def gpu_arm(args, cfg):
             if dist is not None:
                 dist.barrier()                          # ranks enter every timed iteration together
                 torch.cuda.synchronize()
+            l0 = lib.cirs_launch_count()
             e0.record()
-            res = one_step(resident)
+            res = one_step(a == "res")
             e1.record()
             torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
-            per_step.append(round(e0.elapsed_time(e1), 3))
-            steps += res["n/st"]
-            h2d += col.h2d_bytes + pol.h2d_bytes
-            d2h += col.d2h_bytes + pol.d2h_bytes
+            A = acc[a]
+            A["launches"] += lib.cirs_launch_count() - l0
+            A["ms"] += e0.elapsed_time(e1)
+            A["per_step"].append(round(e0.elapsed_time(e1), 3))
+            A["steps"] += res["n/st"]
+            A["h2d"] += col.h2d_bytes + pol.h2d_bytes
+            A["d2h"] += col.d2h_bytes + pol.d2h_bytes
         barrier()
-        t = torch.tensor([ms, float(steps)], dtype=torch.float64, device=dev)
-        if dist is not None:
-            tm = t.clone()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            ms, steps = float(tm[0]), float(t[1])
-        timed.per_step = per_step
-        return ms, steps, h2d / K, d2h / K
+        out = {}
+        for a in arms:
+            A = acc[a]
+            ms, steps = A["ms"], float(A["steps"])
+            t = torch.tensor([ms, steps], dtype=torch.float64, device=dev)
+            if dist is not None:
+                tm = t.clone()
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                ms, steps = float(tm[0]), float(t[1])
+            out[a] = (ms, steps, A["h2d"] / K, A["d2h"] / K, A["launches"], A["per_step"])
+        return out
 
     clocks = Clocks(dev.index or 0)
     clocks.start()                  # sampler runs through warm-up, both timed regions and the profile pass
@@ -446,13 +458,10 @@ def gpu_arm(args, cfg):
     # arm is timed first, so the timed loop itself runs once untimed
     n_settle = 0 if args.steps < 5 else min(args.steps, 30)
     if n_settle:
-        timed(n_settle, True)
-    l0 = lib.cirs_launch_count()
-    ms_res, steps_res, _, _ = timed(args.steps, True)
-    per_step_res = list(timed.per_step)
-    launches = lib.cirs_launch_count() - l0
-    ms_e2e, steps_e2e, h2d, d2h = timed(args.steps, False)
-    per_step_e2e = list(timed.per_step)
+        timed(n_settle, "res")
+    both = timed(args.steps, "both")
+    ms_res, steps_res, _, _, launches, per_step_res = both["res"]
+    ms_e2e, steps_e2e, h2d, d2h, _, per_step_e2e = both["e2e"]
     lens = np.asarray(res0["lens"])
 
     # ---- per-kernel durations, live, CUDA events on the launching stream (separate pass: events perturb the step);
@@ -565,7 +574,8 @@ def gpu_arm(args, cfg):
                        "parallelism": f"env-sharded dp{world}", "l2": "192 MB flush between timed iterations",
                        "settle": f"{n_settle} untimed iterations of the timed loop between the warm-up steps and the "
                                  "timed region",
-                       "timing": "CUDA events per step, max over ranks", "ms_each_step_rank0": per_step_res},
+                       "timing": "CUDA events per iteration, max over ranks; the resident and the end-to-end iterations "
+                                 "alternate inside one loop (K each)", "ms_each_step_rank0": per_step_res},
             "e2e": {"value": steps_e2e / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
                     "env_steps_per_step": steps_e2e / args.steps, "ms_each_step_rank0": per_step_e2e},
