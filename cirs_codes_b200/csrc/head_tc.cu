@@ -8,8 +8,9 @@
 // into tile images in global memory (head_tc_pack) that the passes copy into shared memory; h2 is split while staging;
 // d logits go back to TMEM as the A operand of the second MMA.
 // Thread t owns TMEM lane t % 128 (warp % 4 selects the lane quarter, as tcgen05.ld requires) and the column group
-// t / 128 of each 64-column accumulator: halves with 256 threads (pass F, two CTAs per SM), quarters with 512 threads
-// (passes B2 / B3, one CTA per SM) -- four resident warps per scheduler hide the epilogue's instruction latency.
+// t / 128 of each accumulator: quarters with 512 threads (pass F on 128-column tiles, passes B2 / B3 on 64-column tiles;
+// one CTA per SM) -- four resident warps per scheduler hide the epilogue's instruction latency; halves with 256 threads
+// in the register-staged pass F (two CTAs per SM).
 #include "common.cuh"
 #include "tc_dev.cuh"
 #include "head_tc.cuh"
@@ -33,7 +34,7 @@ constexpr int KSTEPS = HID / 8;   // every contraction here has depth 64
 #define LOG_1M_EPS (-1.1920929665620963e-07f)     /* log(1 - CATEGORICAL_EPS) */
 
 __device__ int g_tc_timeout = 0;   // set when an mbarrier wait gives up (never expected; checked by the tests)
-// Phase counters (cycles summed over CTAs) of the ring-fed pass F [0, 16) and the TMA-fed pass B2 [16, 48); filled only
+// Phase counters (cycles summed over CTAs) of pass F [0, 16) and the bulk-copy fed pass B2 [16, 48); filled only
 // by the PH instantiations (cirs_head_tc_debug_phases; scratch/head_phases.py).  One representative worker warp (warp 0)
 // and the issuer warp stamp clock64() around their waits.
 __device__ unsigned long long g_phase[64];
@@ -409,126 +410,6 @@ head_tc_stats_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* _
   if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
-// ------------------------------------------------------------------------------------------------- pass F, TMA-fed
-// Warp-specialised variant of pass F.  Warps 0-7 (256 threads) only run epilogues; warp 8's lane 0 is the
-// producer + MMA issuer: it moves the pre-split operand images (h2 row tile once, one W3 tile + its bias per catalogue
-// tile) into shared memory with cp.async.bulk (1-D TMA, completion counted in bytes on an mbarrier), issues the
-// 24 MMAs of a tile into one of two TMEM accumulators and re-arms the copy of the next tile as soon as the MMA that
-// read the previous one has completed.  The workers never touch W3 and there is no CTA-wide barrier in the loop:
-//   tma_b     (tx count)   copy of tile t landed            issuer waits
-//   mma[b]    (commit)     accumulator b holds tile t       workers wait
-//   dfree[b]  (8 arrivals) workers have read accumulator b and bias buffer b of tile t into registers   issuer waits
-constexpr int NTF = NT + 32;
-constexpr size_t FT_SMEM = 2 * A_BYTES + 2 * B_BYTES + 2 * 64 * 4 + 2 * NT * 4;
-
-__global__ void __launch_bounds__(NTF, 2)
-head_tc_stats_tma_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act,
-                         int tiles_per_split, int n_split, float* __restrict__ pm, float* __restrict__ ps,
-                         float* __restrict__ la) {
-  extern __shared__ __align__(1024) char smem[];
-  char* a_hi = smem;
-  char* a_lo = a_hi + A_BYTES;
-  char* b_hi = a_lo + A_BYTES;
-  char* b_lo = b_hi + B_BYTES;
-  float* sb3 = reinterpret_cast<float*>(b_lo + B_BYTES);   // 2 x 64
-  float* sm = sb3 + 128;
-  float* ss = sm + NT;
-  __shared__ __align__(8) uint64_t tma_a, tma_b, mma[2], dfree[2];
-  __shared__ uint32_t tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, half = (tid >> 7) & 1;
-  const bool worker = tid < NT, issuer = __shfl_sync(FULL_MASK, warp, 0) == NT / 32;
-  const int r0 = blockIdx.x * TM, split = blockIdx.y;
-  const int n_tiles = (H.nA + TN - 1) / TN;
-  const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
-  const int64_t n64 = H.ldA / TN;
-  if (warp == 0) tmem_alloc(&tmem_base, 128);
-  if (tid == 0) {
-    mbar_init(&tma_a, 1); mbar_init(&tma_b, 1); mbar_init(&mma[0], 1); mbar_init(&mma[1], 1);
-    mbar_init(&dfree[0], NT / 32); mbar_init(&dfree[1], NT / 32);
-    mbar_fence_init();
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tb = tmem_base;
-  if (issuer) {
-    auto copy_tile = [&](int t) {   // W3 image (hi, lo are adjacent: one 32 KB copy) + 64 bias values of tile t
-      const int ct = ct0 + t;
-      w_expect_tx(&tma_b, 2 * B_BYTES + 64 * 4);
-      w_bulk_g2s(b_hi, H.img + img_n_off(ct), 2 * B_BYTES, &tma_b);
-      w_bulk_g2s(sb3 + 64 * (t & 1), H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_b);
-    };
-    if (T > 0) {
-      w_expect_tx(&tma_a, 2 * A_BYTES);
-      w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
-      copy_tile(0);
-      wait_or_flag(&tma_a, 0);
-    }
-    for (int t = 0; t < T; ++t) {
-      const int b = t & 1;
-      wait_or_flag(&tma_b, t & 1);                                  // tile t and its bias are in shared memory
-      if (t >= 2) wait_or_flag(&dfree[b], ((t - 2) >> 1) & 1);      // accumulator b was read by epilogue(t-2)
-      fence_after_sync();
-      w_issue(tb + 64u * b, a_hi, a_lo, b_hi, b_lo, false);
-      w_commit(&mma[b]);
-      if (t + 1 < T) {
-        wait_or_flag(&mma[b], (t >> 1) & 1);                        // MMA(t) no longer reads the B tile
-        if (t >= 1) wait_or_flag(&dfree[b ^ 1], ((t - 1) >> 1) & 1);   // bias buffer (t+1)&1 was read by epilogue(t-1)
-        copy_tile(t + 1);
-      }
-    }
-  }
-  int a = -1;
-  if (worker && act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
-  float m = MASKED, s = 0.f, lav = 0.f;
-  bool found = false;
-  if (worker) {
-    for (int t = 0; t < T; ++t) {
-      const int b = t & 1, cb = (ct0 + t) * TN + half * 32;
-      wait_or_flag(&mma[b], (t >> 1) & 1);
-      fence_after_sync();
-      float v[32];
-      tmem_ld32(tmem_addr(tb + 64u * b, (warp & 3) * 32, half * 32), v);
-      float mt = MASKED;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = v[j] + sb3[64 * b + half * 32 + j];   // padding columns carry the MASKED bias
-        v[j] = x;
-        mt = fmaxf(mt, x);
-      }
-      // accumulator b and bias buffer b are in registers now: hand them back to the issuer (one arrival per warp)
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dfree[b]);
-      if (a >= cb && a < cb + 32) {
-        lav = pick32(v, a - cb);
-        found = true;
-      }
-      if (mt > 0.5f * MASKED) {
-        const float mn = fmaxf(m, mt);
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc += fast_exp(v[j] - mn);
-        s = s * fast_exp(m - mn) + acc;
-        m = mn;
-      }
-    }
-    sm[tid] = m;
-    ss[tid] = s;
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (worker && half == 0 && r0 + row < H.n) {
-    const float m1 = sm[tid + TM], s1 = ss[tid + TM];
-    const float M = fmaxf(m, m1);
-    const float S = s * fast_exp(m - M) + s1 * fast_exp(m1 - M);   // an empty half has s == 0
-    pm[(size_t)(r0 + row) * n_split + split] = M;
-    ps[(size_t)(r0 + row) * n_split + split] = S;
-  }
-  if (found) la[r0 + row] = lav;
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
-}
-
 // D (+)= A[tmem hi/lo] . B[smem hi/lo], 3 TF32 products per k-step of 8
 __device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const char* b_hi, const char* b_lo,
                                          bool accumulate) {
@@ -549,176 +430,8 @@ __device__ __forceinline__ void w_issue_ts(uint32_t d, uint32_t a_hi, uint32_t a
   if (elect_one()) issue_ts(d, a_hi, a_lo, b_hi, b_lo, accumulate);
 }
 
-// ------------------------------------------------------------------------------------------------- pass F, ring-fed
-// One CTA per SM with a RING of three W3 tiles: a 32 KB bulk copy from L2 takes ~1.5 us, and the two-CTAs-per-SM kernel
-// above pays it (plus the MMA's completion) once per tile in its issuer's chain -- 28 us per 1567-row pass for 12 us of
-// MMA work.  Here the copy of tile t + 2 is issued as soon as MMA(t - 1) has released its slot, so three copies are in
-// flight behind the MMAs.  Workers and barriers as above; the bias of tile t sits in slot t & 3 of a ring of four.
-// ATM: the h2 row tile -- the A operand of every MMA of the CTA -- lives in TENSOR MEMORY instead of shared memory: the
-// workers split their rows into (hi, lo) once and tcgen05.st them to TMEM columns [128, 256).  An MMA then reads only
-// its 2 KB B slice from shared memory (the SS form reads 6 KB per M128 N64 K8 MMA and is shared-memory-bandwidth bound:
-// 51-79 cycles per MMA measured against 35 for the TS form), and without the 64 KB A tile two CTAs fit an SM again.
-constexpr int F_RING = 3;
-constexpr size_t FR_SMEM = 2 * A_BYTES + F_RING * 2 * B_BYTES + 4 * 64 * 4 + 2 * NT * 4;
-constexpr size_t FRT_SMEM = F_RING * 2 * B_BYTES + 4 * 64 * 4 + 2 * NT * 4;
-constexpr uint32_t TF_A = 128;   // TMEM columns of the A operand (ATM): hi [128, 192), lo [192, 256)
-
-template <bool ATM, bool PH>
-__global__ void __launch_bounds__(NTF, ATM ? 2 : 1)
-head_tc_stats_ring_kernel(HeadTc H, const int32_t* __restrict__ idx, const int32_t* __restrict__ act,
-                          int tiles_per_split, int n_split, float* __restrict__ pm, float* __restrict__ ps,
-                          float* __restrict__ la) {
-  extern __shared__ __align__(1024) char smem[];
-  char* a_hi = smem;                                                       // (SS form only)
-  char* a_lo = a_hi + A_BYTES;
-  char* bring = ATM ? smem : a_lo + A_BYTES;                               // F_RING x { hi, lo }
-  float* sb3 = reinterpret_cast<float*>(bring + F_RING * 2 * B_BYTES);     // 4 x 64
-  float* sm = sb3 + 256;
-  float* ss = sm + NT;
-  __shared__ __align__(8) uint64_t tma_a, tma_b[F_RING], mma[2], dfree[2];   // tma_a (ATM): the workers' A rows are in TMEM
-  __shared__ uint32_t tmem_base;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, half = (tid >> 7) & 1;
-  const bool worker = tid < NT, issuer = __shfl_sync(FULL_MASK, warp, 0) == NT / 32;
-  const int r0 = blockIdx.x * TM, split = blockIdx.y;
-  const int n_tiles = (H.nA + TN - 1) / TN;
-  const int ct0 = split * tiles_per_split, T = min(n_tiles, ct0 + tiles_per_split) - ct0;
-  const int64_t n64 = H.ldA / TN;
-  if (warp == 0) tmem_alloc(&tmem_base, ATM ? 256 : 128);
-  if (tid == 0) {
-    mbar_init(&tma_a, ATM ? NT / 32 : 1);
-    for (int i = 0; i < F_RING; ++i) mbar_init(&tma_b[i], 1);
-    mbar_init(&mma[0], 1); mbar_init(&mma[1], 1);
-    mbar_init(&dfree[0], NT / 32); mbar_init(&dfree[1], NT / 32);
-    mbar_fence_init();
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tb = tmem_base;
-  // PH only: experiment switch g_phase[62] (1: workers skip the epilogue arithmetic, 2: the ring is filled once and never
-  // refilled, 3: both) -- which resource paces the MMAs
-  int dbg = 0;
-  if constexpr (PH) dbg = (int)g_phase[62];
-  if (issuer && T > 0) {
-    auto copy_tile = [&](int t) {   // tile t -> ring slot t % F_RING (phase parity (t / F_RING) & 1), bias -> slot t & 3
-      const int ct = ct0 + t, s = t % F_RING;
-      w_expect_tx(&tma_b[s], 2 * B_BYTES + 64 * 4);
-      w_bulk_g2s(bring + (size_t)s * 2 * B_BYTES, H.img + img_n_off(ct), 2 * B_BYTES, &tma_b[s]);
-      w_bulk_g2s(sb3 + 64 * (t & 3), H.img + img_bias_off(n64) + (int64_t)ct * TN, 64 * 4, &tma_b[s]);
-    };
-    if (!ATM) {
-      w_expect_tx(&tma_a, 2 * A_BYTES);
-      w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
-    }
-    for (int t = 0; t < F_RING && t < T; ++t) copy_tile(t);
-    wait_or_flag(&tma_a, 0);
-    PhaseClock<PH> pc;
-    pc.start(lane == 0);
-    for (int t = 0; t < T; ++t) {
-      const int b = t & 1, s = t % F_RING;
-      if (!(dbg & 2) || t < F_RING) wait_or_flag(&tma_b[s], (t / F_RING) & 1);   // tile t and its bias are in shared memory
-      pc.lap(0);
-      if (t >= 2) wait_or_flag(&dfree[b], ((t - 2) >> 1) & 1);        // accumulator b was read by epilogue(t-2)
-      pc.lap(1);
-      fence_after_sync();
-      if (ATM)
-        w_issue_ts(tb + 64u * b, tb + TF_A, tb + TF_A + 64u, bring + (size_t)s * 2 * B_BYTES,
-                   bring + (size_t)s * 2 * B_BYTES + B_BYTES, false);
-      else
-        w_issue(tb + 64u * b, a_hi, a_lo, bring + (size_t)s * 2 * B_BYTES, bring + (size_t)s * 2 * B_BYTES + B_BYTES, false);
-      w_commit(&mma[b]);
-      pc.lap(2);
-      if (t >= 1 && t - 1 + F_RING < T) {
-        wait_or_flag(&mma[b ^ 1], ((t - 1) >> 1) & 1);                // MMA(t-1) released ring slot (t-1) % F_RING; bias
-        if (!(dbg & 2)) copy_tile(t - 1 + F_RING);                    // slot (t+2) & 3 was tile t-2's (dfree above)
-        pc.lap(3);
-      }
-    }
-    pc.count(4, T);
-  }
-  int a = -1;
-  if (worker && act != nullptr && r0 + row < H.n) a = act[idx ? idx[r0 + row] : r0 + row];
-  float m = MASKED, s = 0.f, lav = 0.f;
-  bool found = false;
-  if (worker) {
-    if (ATM && T > 0) {   // this thread's 32 h2 values (row, column half) -> (hi, lo) -> TMEM, split like head_tc_pack_h2
-      const bool okr = r0 + row < H.n;
-      const float4* src = reinterpret_cast<const float4*>(H.h2 + (size_t)(okr ? r0 + row : 0) * HID + half * 32);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 x = okr ? __ldg(src + 4 * q + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[4 * c + e] = tf32_hi(xs[e]);
-            lo[4 * c + e] = tf32_hi(xs[e] - hi[4 * c + e]);
-          }
-        }
-        tmem_st16(tmem_addr(tb + TF_A, (warp & 3) * 32, half * 32 + 16 * q), hi);
-        tmem_st16(tmem_addr(tb + TF_A + 64u, (warp & 3) * 32, half * 32 + 16 * q), lo);
-      }
-      tmem_st_wait();
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tma_a);
-    }
-    PhaseClock<PH> pc;
-    pc.start(tid == 0);
-    for (int t = 0; t < T; ++t) {
-      const int b = t & 1, cb = (ct0 + t) * TN + half * 32;
-      wait_or_flag(&mma[b], (t >> 1) & 1);
-      pc.lap(8);
-      fence_after_sync();
-      float v[32];
-      tmem_ld32(tmem_addr(tb + 64u * b, (warp & 3) * 32, half * 32), v);
-      pc.lap(9);
-      float mt = MASKED;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = v[j] + sb3[64 * (t & 3) + half * 32 + j];   // padding columns carry the MASKED bias
-        v[j] = x;
-        mt = fmaxf(mt, x);
-      }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dfree[b]);
-      pc.lap(10);
-      if (dbg & 1) continue;
-      if (a >= cb && a < cb + 32) {
-        lav = pick32(v, a - cb);
-        found = true;
-      }
-      if (mt > 0.5f * MASKED) {
-        const float mn = fmaxf(m, mt);
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc += fast_exp(v[j] - mn);
-        s = s * fast_exp(m - mn) + acc;
-        m = mn;
-      }
-      pc.lap(11);
-    }
-    sm[tid] = m;
-    ss[tid] = s;
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (worker && half == 0 && r0 + row < H.n) {
-    const float m1 = sm[tid + TM], s1 = ss[tid + TM];
-    const float M = fmaxf(m, m1);
-    const float S = s * fast_exp(m - M) + s1 * fast_exp(m1 - M);   // an empty half has s == 0
-    pm[(size_t)(r0 + row) * n_split + split] = M;
-    ps[(size_t)(r0 + row) * n_split + split] = S;
-  }
-  if (found) la[r0 + row] = lav;
-  if (warp == 0) tmem_dealloc(tmem_base, ATM ? 256 : 128);
-}
-
 // ------------------------------------------------------------------------------------------------- pass F, 128-column tiles
-// Measured on the B200 (cirs_head_tc_debug_phases, scratch/f_experiments.py): an M128 N64 K8 kind::tf32 MMA with both
+// Measured on the B200 (cirs_head_tc_debug_phases; profiles/r2c_head_phases.txt): an M128 N64 K8 kind::tf32 MMA with both
 // operands in shared memory executes in ~58 cycles, not the tensor pipe's 32 -- it re-reads the 4 KB A slice for 2 KB of
 // B, and shared memory feeds 128 B per clock.  With N = 128 an MMA reads 4 + 4 KB for twice the math.  This variant
 // walks the catalogue in 128-column tiles: the B operand is the 128-row W3 image that pass B3 uses as its A operand
@@ -1487,7 +1200,6 @@ int head_tc_front(const cirs_policy_weights* w, int n, const int32_t* idx, const
   return CIRS_OK;
 }
 
-int f_occupancy();
 static bool g_phase_host = false;   // launch the phase-stamped instantiations (cirs_head_tc_debug_phases)
 static int g_tc_mode = -1;   // -1: environment default (CIRS_NO_TC), 0: off, 1: on (TMA-fed kernels), 2: on, register-staged
 static bool tma_on() {
@@ -1503,24 +1215,9 @@ static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && e[0]) ? atoi(e) : dflt;
 }
-static bool f_ring_on() {
-  static int v = -1;
-  if (v < 0) v = env_int("CIRS_F_RING", 1) ? 1 : 0;
-  return v == 1;
-}
 // Catalogue splits of passes F / B2 (one CTA per SM): the split count that minimises  waves x (tiles per CTA + a fixed
 // per-CTA cost of ~2 tile times: TMEM allocation, pipeline fill, the final partial store).  CIRS_TC_PLAN=0 restores the
 // round-1 rule (about two CTAs per SM's worth of work items).
-static bool f_atm_on() {
-  static int v = -1;
-  if (v < 0) v = env_int("CIRS_F_ATM", 1) ? 1 : 0;
-  return v == 1;
-}
-static bool f_wide_on() {
-  static int v = -1;
-  if (v < 0) v = env_int("CIRS_F_WIDE", 1) ? 1 : 0;
-  return v == 1;
-}
 // tile = columns per tile (64, or 128 for the wide pass F); fixed = per-CTA fixed cost in tile times
 static int plan_split_slots(int n, int nA, int slots, int tile = TN, int fixed = 2) {
   const int n_tiles = (nA + tile - 1) / tile, row_tiles = (n + TM - 1) / TM;
@@ -1546,8 +1243,8 @@ static int plan_split_slots(int n, int nA, int slots, int tile = TN, int fixed =
 int plan_split(int n, int nA) { return plan_split_slots(n, nA, 148); }
 // pass F has its own split count: its partials (pm, ps) are merged separately from pass B2's (d h2, entropy)
 int plan_split_f(int n, int nA) {
-  if (tma_on() && f_wide_on()) return plan_split_slots(n, nA, 148, WN, 1);
-  return plan_split_slots(n, nA, (!tma_on() || !f_ring_on() || f_atm_on()) ? 296 : 148);
+  if (tma_on()) return plan_split_slots(n, nA, 148, WN, 1);   // 128-column tiles, one CTA per SM
+  return plan_split_slots(n, nA, 296);                        // register-staged kernel: two CTAs per SM
 }
 
 bool head_tc_enabled(int n, int nA, int64_t ldA) {
@@ -1563,23 +1260,14 @@ int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n
   static bool once = false;
   if (!once) {
     set_smem(head_tc_stats_kernel, F_SMEM);
-    set_smem(head_tc_stats_tma_kernel, FT_SMEM);
     set_smem(head_tc_stats_wide_kernel<false>, FW_SMEM);
     set_smem(head_tc_stats_wide_kernel<true>, FW_SMEM);
-    set_smem(head_tc_stats_ring_kernel<false, false>, FR_SMEM);
-    set_smem(head_tc_stats_ring_kernel<false, true>, FR_SMEM);
-    set_smem(head_tc_stats_ring_kernel<true, false>, FRT_SMEM);
-    set_smem(head_tc_stats_ring_kernel<true, true>, FRT_SMEM);
-    // two CTAs of ~100 KB per SM: ask for the largest shared-memory carve-out (the default sizes it for one block)
-    cudaFuncSetAttribute(head_tc_stats_ring_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(head_tc_stats_ring_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(head_tc_stats_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     once = true;
   }
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
-  if (tma_on() && f_wide_on()) {   // 128-column tiles, one CTA per SM (CIRS_F_WIDE=0: the 64-column kernels below)
+  if (tma_on()) {   // 128-column tiles, warp-specialised and bulk-copy fed (CIRS_NO_TMA=1 / mode 2: register-staged kernel)
     const int n_tiles = (H.nA + WN - 1) / WN, perw = (n_tiles + n_split - 1) / n_split;
     if (g_phase_host)
       CIRS_LAUNCH(head_tc_stats_wide_kernel<true>, grid, NTB + 32, FW_SMEM, st, H, idx, act, perw, n_split, pm, ps, la,
@@ -1591,26 +1279,8 @@ int head_tc_stats(const HeadTc& H, const int32_t* idx, const int32_t* act, int n
     return CIRS_OK;
   }
   if (n_dev) {
-    cirs_set_error("head_tc_stats: a device-resident row count needs the 128-column pass F (CIRS_F_WIDE / CIRS_NO_TMA unset)");
+    cirs_set_error("head_tc_stats: a device-resident row count needs the bulk-copy fed pass F (CIRS_NO_TMA unset, mode 1)");
     return CIRS_ERR_ARG;
-  }
-  if (tma_on() && f_ring_on()) {   // one CTA per SM, ring of three W3 tiles (CIRS_F_RING=0: two CTAs per SM, one tile ahead)
-    // A operand in tensor memory, two CTAs per SM (CIRS_F_ATM=0: A in shared memory, one CTA per SM)
-    if (f_atm_on() && g_phase_host)
-      CIRS_LAUNCH((head_tc_stats_ring_kernel<true, true>), grid, NTF, FRT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
-    else if (f_atm_on())
-      CIRS_LAUNCH((head_tc_stats_ring_kernel<true, false>), grid, NTF, FRT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
-    else if (g_phase_host)
-      CIRS_LAUNCH((head_tc_stats_ring_kernel<false, true>), grid, NTF, FR_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
-    else
-      CIRS_LAUNCH((head_tc_stats_ring_kernel<false, false>), grid, NTF, FR_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
-    CIRS_CHECK_LAUNCH();
-    return CIRS_OK;
-  }
-  if (tma_on()) {   // warp-specialised pass F fed by cp.async.bulk (CIRS_NO_TMA=1 selects the register-staged kernel)
-    CIRS_LAUNCH(head_tc_stats_tma_kernel, grid, NTF, FT_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
-    CIRS_CHECK_LAUNCH();
-    return CIRS_OK;
   }
   CIRS_LAUNCH(head_tc_stats_kernel, grid, NT, F_SMEM, st, H, idx, act, per, n_split, pm, ps, la);
   CIRS_CHECK_LAUNCH();
@@ -1671,35 +1341,21 @@ int head_tc_dw3(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   return CIRS_OK;
 }
 
-int f_occupancy() {
-  int n = 0;
-  if (f_atm_on()) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, head_tc_stats_ring_kernel<true, false>, NTF, FRT_SMEM);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, head_tc_stats_ring_kernel<false, false>, NTF, FR_SMEM);
-  return n;
-}
-
 }  // namespace cirs_head_tc
 
 extern "C" void cirs_head_tc_enable(int on) { cirs_head_tc::g_tc_mode = on < 0 ? -1 : (on > 2 ? 1 : on); }
 
-// debug: per-phase cycle counters of the ring-fed pass F and the TMA-fed pass B2 (see g_phase).  enable != 0 switches
-// the stamping on; out (64 values, host memory, may be null) receives the counters accumulated so far; reset != 0 clears
-// them.  Synchronises the device.
+// debug: per-phase cycle counters of pass F (head_tc_stats_wide_kernel) and pass B2 (head_tc_dh2_tma_kernel), see g_phase.
+// enable != 0 makes the launchers pick the stamped instantiations; out (64 values, host memory, may be null) receives
+// the counters accumulated so far; reset != 0 clears them.  Synchronises the device.
 extern "C" int cirs_head_tc_debug_phases(int32_t enable, int64_t* out64_h, int32_t reset) {
   cudaDeviceSynchronize();
-  if (out64_h) {
-    cudaMemcpyFromSymbol(out64_h, cirs_head_tc::g_phase, 64 * sizeof(unsigned long long));
-    out64_h[63] = cirs_head_tc::f_occupancy();   // resident CTAs per SM of the pass-F kernel in use (runtime's estimate)
-  }
+  if (out64_h) cudaMemcpyFromSymbol(out64_h, cirs_head_tc::g_phase, 64 * sizeof(unsigned long long));
   if (reset) {
     unsigned long long z[64] = {0};
     cudaMemcpyToSymbol(cirs_head_tc::g_phase, z, sizeof(z));
   }
   cirs_head_tc::g_phase_host = enable != 0;
-  {   // experiment switch of the stamped pass-F kernel (bits 4-5 of enable; see head_tc_stats_ring_kernel)
-    unsigned long long mode = (unsigned long long)((enable >> 4) & 3);
-    cudaMemcpyToSymbol(cirs_head_tc::g_phase, &mode, sizeof(mode), 62 * sizeof(unsigned long long));
-  }
   return cudaGetLastError() == cudaSuccess ? CIRS_OK : CIRS_ERR_CUDA;
 }
 

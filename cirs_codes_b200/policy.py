@@ -425,8 +425,7 @@ class PPOPolicy:
         if getattr(self, "_tc_ok", None) is None:
             na = int(self._w.n_action)
             self._tc_ok = (na >= 64 and int(self._w.dim_state) <= 32 and os.environ.get("CIRS_NO_TC", "0") in ("", "0")
-                           and os.environ.get("CIRS_NO_TMA", "0") in ("", "0")
-                           and os.environ.get("CIRS_F_WIDE", "1") not in ("0",))
+                           and os.environ.get("CIRS_NO_TMA", "0") in ("", "0"))
         return self._tc_ok
 
     def _process_kernels(self, buffer, n, n_dev=None, indices=None):

@@ -509,7 +509,7 @@ int cirs_user_model_timeout(void);
  * MMA wait, epilogue, barrier, tiles} of the last launch.  Synchronises. */
 int cirs_user_model_debug_phases(int64_t* out8_h);
 /* Profiling aid for the tensor-core head passes (csrc/head_tc.cu): enable != 0 makes the issuer warp and the first / last
- * epilogue warp of every CTA of the ring-fed pass F and the TMA-fed pass B2 accumulate clock64() cycles per phase of
+ * epilogue warp of every CTA of pass F and pass B2 (bulk-copy fed kernels) accumulate clock64() cycles per phase of
  * their tile loops into 64 device counters; out64_h (HOST int64[64], may be NULL) receives the counters accumulated so
  * far, reset != 0 clears them.  Layout: scratch/head_phases.py.  Synchronises. */
 int cirs_head_tc_debug_phases(int32_t enable, int64_t* out64_h, int32_t reset);

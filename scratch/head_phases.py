@@ -1,4 +1,4 @@
-"""Per-phase cycle counters of the tensor-core head passes F (ring-fed) and B2 (TMA-fed) over a few configs[1] updates
+"""Per-phase cycle counters of the tensor-core head passes F (128-column tiles) and B2 (bulk-copy fed) over a few configs[1] updates
 (cirs_head_tc_debug_phases).  Usage: python scratch/head_phases.py [configs1|configs2]"""
 import ctypes, sys
 import numpy as np, torch
@@ -28,7 +28,6 @@ def show(title, names, base, tiles):
     for i, n in enumerate(names):
         if n: print(f"   {n:34s} {c[base + i] / max(tiles, 1):9.0f}"); tot += c[base + i]
     print(f"   {'sum':34s} {tot / max(tiles, 1):9.0f}")
-print("pass F kernel occupancy (CTAs per SM, runtime estimate):", int(c[63]))
 tF = c[4]
 show("pass F issuer", ["wait tma_b", "wait dfree", "issue MMA + commit", "wait mma(t-1) + copy"], 0, tF)
 show("pass F worker warp 0", ["wait mma", "tmem_ld", "bias+max, arrive", "exp-sum"], 8, tF)
