@@ -413,9 +413,9 @@ class PPOPolicy:
         capacity) may differ from the in-order run, i.e. the summation order of the soft-max partials."""
         self._pre = None
         n_prev = getattr(self, "_n_prev", 0)
-        if (not self.pre_eval or os.environ.get("CIRS_NO_PRE_EVAL") == "1" or self.continuous or n_prev <= 0
-                or not self._tc_eval_ok()):
-            return
+        if (not self.pre_eval or not self.training or os.environ.get("CIRS_NO_PRE_EVAL") == "1" or self.continuous
+                or n_prev <= 0 or not self._tc_eval_ok()):
+            return   # (test collectors run under policy.eval(): their buffers are never updated on)
         n_slots = buffer.maxsize
         cap = min(n_slots, max(1024, -(-(n_prev + n_prev // 8) // 128) * 128))
         self._process_kernels(buffer, cap, buffer.d_env_off[buffer.buffer_num:buffer.buffer_num + 1])
