@@ -69,8 +69,14 @@ __device__ __forceinline__ void w_issue(uint32_t d, const char* a_hi, const char
                                         bool accumulate) {
   if (elect_one()) issue(d, a_hi, a_lo, b_hi, b_lo, accumulate);
 }
+// Bounded wait: ~2^28 polls before the first thread gives up and raises the flag; every other waiter then leaves within
+// 2^16 polls (a kernel whose pipeline is wedged ends in seconds instead of one full timeout per remaining wait).
 __device__ __forceinline__ void wait_or_flag(uint64_t* bar, uint32_t parity) {
-  if (!mbar_wait(bar, parity)) g_tc_timeout = 1;
+  for (int c = 0; c < 4096; ++c) {
+    if (mbar_wait_n(bar, parity, 1u << 16)) return;
+    if (*reinterpret_cast<volatile int*>(&g_tc_timeout)) return;
+  }
+  g_tc_timeout = 1;
 }
 // v[k] for a run-time k with v kept in REGISTERS.  The plain forms (v[k], or an unrolled `if (j == k) x = v[j]`) make
 // the compiler index a local-memory copy of v: 8 x STL.128 per thread per tile in the hot loop of every pass-F kernel,
@@ -1022,6 +1028,171 @@ head_tc_dh2_tma_kernel(HeadTc H, const float* __restrict__ rowm, const float* __
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- pass B2 with ONE logits MMA batch per PAIR of 64-column tiles (experimental; CIRS_B2_WIDE=1) ------------------
+// The logits of two neighbouring catalogue tiles come from M128 N128 K8 MMAs against the 128-row W3 image (the operand
+// of pass F): 24 MMAs of ~74 cycles for 128 columns instead of 2 x 24 of ~51.  TMEM has no room for two 128-column
+// logits accumulators AND two (hi, lo) d-logits operands, so the d-logits operand is single-buffered: the epilogue of
+// tile q waits for MMA2(q - 1) right before it stores (the arithmetic in front of the store covers that MMA).  The
+// 128-column B operand (64 KB) is single-staged in shared memory: the copy for pair p + 1 starts when MMA1(p) has
+// completed and lands while the epilogue works on pair p.
+//   TMEM: logits pair accumulators [0, 128) [128, 256) | D2 [256, 320) | d logits hi [320, 384) lo [384, 448)
+//   tma_n     B operand + bias of pair p landed (phase parity p & 1)                  issuer waits
+//   tma_k[s]  second-MMA B tile of tile q landed (s = q & 1, parity (q >> 1) & 1)       issuer waits
+//   mma1[w]   pair accumulator w = p & 1 holds pair p (parity (p >> 1) & 1)            workers wait; issuer (B stage free)
+//   d1r[w]    (16 arrivals) both halves of accumulator w are in registers             issuer waits before MMA1(p + 2)
+//   dlr       (16 arrivals) d logits of tile q are in TMEM (parity q & 1)               issuer waits
+//   mma2      second MMA of tile q complete (parity q & 1)                              workers (operand free), issuer (bk free)
+constexpr uint32_t TW_D1 = 0, TW_D2 = 256, TW_DL = 320;
+constexpr size_t B2W_SMEM = 2 * A_BYTES + 2 * A_BYTES + 4 * B_BYTES + 2 * WN * 4 + NTB * 4;
+
+__global__ void __launch_bounds__(NTB + 32, 1)
+head_tc_dh2_wide_kernel(HeadTc H, const float* __restrict__ rowm, const float* __restrict__ rinvz,
+                        const float* __restrict__ coef, const int32_t* __restrict__ acta, int pairs_per_split,
+                        int n_split, float* __restrict__ dh2_part, float* __restrict__ ent_part) {
+  extern __shared__ __align__(1024) char smem[];
+  char* a_hi = smem;                         // h2 tile (hi, lo adjacent)                          (A of MMA1)
+  char* a_lo = a_hi + A_BYTES;
+  char* bn = a_lo + A_BYTES;                 // W3 pair tile r = column (128), c = hidden: hi, lo  (B of MMA1)
+  char* bk = bn + 2 * A_BYTES;               // 2 x { W3 tile r = hidden, c = column (64): hi, lo } (B of MMA2)
+  float* sb3 = reinterpret_cast<float*>(bk + 4 * B_BYTES);   // 2 x 128 bias values (pair p in slot p & 1)
+  float* se = sb3 + 2 * WN;
+  __shared__ __align__(8) uint64_t tma_a, tma_n, tma_k[2], mma1[2], d1r[2], dlr, mma2;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, row = tid & 127, qt = (tid >> 7) & 3;
+  const bool worker = tid < NTB, issuer = __shfl_sync(FULL_MASK, warp, 0) == NTB / 32;
+  const int r0 = blockIdx.x * TM, split = blockIdx.y;
+  const int n_pairs = (H.nA + WN - 1) / WN;
+  const int cp0 = split * pairs_per_split, P = min(n_pairs, cp0 + pairs_per_split) - cp0, Q = 2 * P;
+  const int64_t n64 = H.ldA / TN;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  if (tid == 0) {
+    mbar_init(&tma_a, 1); mbar_init(&tma_n, 1); mbar_init(&tma_k[0], 1); mbar_init(&tma_k[1], 1);
+    mbar_init(&mma1[0], 1); mbar_init(&mma1[1], 1); mbar_init(&mma2, 1);
+    mbar_init(&d1r[0], NTB / 32); mbar_init(&d1r[1], NTB / 32); mbar_init(&dlr, NTB / 32);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_base;
+  if (issuer && P > 0) {
+    auto copy_n = [&](int p) {   // pair p: 64 KB operand image + 128 bias values
+      w_expect_tx(&tma_n, 2 * A_BYTES + WN * 4);
+      w_bulk_g2s(bn, H.img + img_a_off(n64, cp0 + p), 2 * A_BYTES, &tma_n);
+      w_bulk_g2s(sb3 + WN * (p & 1), H.img + img_bias_off(n64) + (int64_t)(cp0 + p) * WN, WN * 4, &tma_n);
+    };
+    auto copy_k = [&](int q) {   // 64-column tile q of this CTA (catalogue tile 2 cp0 + q)
+      const int s = q & 1;
+      w_expect_tx(&tma_k[s], 2 * B_BYTES);
+      w_bulk_g2s(bk + 2 * s * B_BYTES, H.img + img_k_off(n64, 2 * cp0 + q), 2 * B_BYTES, &tma_k[s]);
+    };
+    auto issue_mma1 = [&](int p) {
+      const int w = p & 1;
+      if (elect_one())
+        mma_3xtf32(tb + TW_D1 + (uint32_t)WN * w, smem_u32(a_hi), smem_u32(a_lo), A_STEP, A_LBO, SBO, smem_u32(bn),
+                   smem_u32(bn + A_BYTES), A_STEP, A_LBO, SBO, IDESC_W, KSTEPS, false);
+      w_commit(&mma1[w]);
+    };
+    w_expect_tx(&tma_a, 2 * A_BYTES);
+    w_bulk_g2s(a_hi, H.himg + himg_a_off(h2_tiles64(H.n), blockIdx.x), 2 * A_BYTES, &tma_a);
+    copy_n(0);
+    copy_k(0);
+    copy_k(1);
+    wait_or_flag(&tma_a, 0);
+    wait_or_flag(&tma_n, 0);
+    fence_after_sync();
+    issue_mma1(0);
+    for (int p = 0; p < P; ++p) {
+      const int w = p & 1;
+      if (p + 1 < P) {
+        wait_or_flag(&mma1[w], (p >> 1) & 1);          // MMA1(p) complete: the B stage is free again (bias slot (p+1) & 1
+        copy_n(p + 1);                                 // was pair p-1's: its last epilogue ended before MMA2(2p - 1))
+      }
+      for (int h = 0; h < 2; ++h) {
+        const int q = 2 * p + h, s = q & 1;
+        if (q >= 1 && q + 1 < Q) {
+          wait_or_flag(&mma2, (q - 1) & 1);            // MMA2(q-1) complete: bk[(q+1) & 1] is free
+          copy_k(q + 1);
+        }
+        wait_or_flag(&dlr, q & 1);                     // d logits of tile q are in TMEM
+        wait_or_flag(&tma_k[s], (q >> 1) & 1);
+        fence_after_sync();
+        w_issue_ts(tb + TW_D2, tb + TW_DL, tb + TW_DL + 64u, bk + 2 * s * B_BYTES, bk + (2 * s + 1) * B_BYTES, q > 0);
+        w_commit(&mma2);
+        if (h == 0 && p + 1 < P) {                     // the next pair's logits, behind this pair's second half
+          wait_or_flag(&tma_n, (p + 1) & 1);
+          if (p >= 1) wait_or_flag(&d1r[w ^ 1], ((p - 1) >> 1) & 1);   // epilogue(p-1) has read accumulator w ^ 1
+          fence_after_sync();
+          issue_mma1(p + 1);
+        }
+      }
+    }
+  }
+  const bool live = worker && r0 + row < H.n;
+  float ent = 0.f;
+  if (worker) {
+    const float rm = live ? rowm[r0 + row] : 0.f, iz = live ? rinvz[r0 + row] : 0.f, cf = live ? coef[r0 + row] : 0.f;
+    const int a = live ? acta[r0 + row] : -1;
+    const float log_z = iz > 0.f ? -logf(iz) : 0.f;
+    for (int q = 0; q < Q; ++q) {
+      const int p = q >> 1, h = q & 1, w = p & 1;
+      if (h == 0) wait_or_flag(&mma1[w], (p >> 1) & 1);
+      fence_after_sync();
+      float v[16];
+      tmem_ld16(tmem_addr(tb + TW_D1 + (uint32_t)WN * w + 64u * h, (warp & 3) * 32, qt * 16), v);
+      if (h == 1) {   // both halves of accumulator w are in registers: the issuer may overwrite it (pair p + 2)
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d1r[w]);
+      }
+      const int cb = (2 * cp0 + q) * TN + qt * 16;
+      const float* bias = sb3 + WN * (p & 1) + 64 * h + qt * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float xm = v[j] + bias[j] - rm;   // logit - max (padding columns: -1e30)
+        const float pr = fast_exp(xm) * iz;
+        const float lg = fminf(fmaxf(xm - log_z, LOG_EPS), LOG_1M_EPS);
+        ent = fmaf(-pr, lg, ent);
+        v[j] = cf * ((cb + j == a ? 1.f : 0.f) - pr);
+      }
+      if (q >= 1) wait_or_flag(&mma2, (q - 1) & 1);   // MMA2(q-1) has read the (single) d-logits operand
+      {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { hi[j] = tf32_trunc(v[j]); lo[j] = v[j] - hi[j]; }
+        tmem_st16(tmem_addr(tb + TW_DL, (warp & 3) * 32, qt * 16), hi);
+        tmem_st16(tmem_addr(tb + TW_DL + 64u, (warp & 3) * 32, qt * 16), lo);
+        tmem_st_wait();
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dlr);
+    }
+    if (Q > 0) {
+      wait_or_flag(&mma2, (Q - 1) & 1);
+      fence_after_sync();
+      float v[16];
+      tmem_ld16(tmem_addr(tb + TW_D2, (warp & 3) * 32, qt * 16), v);
+      if (live) {
+        float* dst = dh2_part + ((size_t)split * H.n + r0 + row) * HID + qt * 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(dst + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      }
+    } else if (live) {   // a split beyond the catalogue's pairs: its partial is zero
+      float* dst = dh2_part + ((size_t)split * H.n + r0 + row) * HID + qt * 16;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(dst + 4 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    se[tid] = ent;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (qt == 0 && live)
+    ent_part[(size_t)(r0 + row) * n_split + split] = (ent + se[tid + TM]) + (se[tid + 2 * TM] + se[tid + 3 * TM]);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 // pass B3, TMA-fed.  Row statistics of a 64-row tile (max, 1/Z, coef, action: four contiguous 256-byte slices of the
 // per-row arrays, which the caller pads with zeros / -1 up to a multiple of 64 rows) travel with the h2 tile.
 constexpr size_t B3T_SMEM = 2 * A_BYTES + 8 * B_BYTES + 4 * 4 * 64 * 4;
@@ -1293,12 +1464,22 @@ int head_tc_dh2(const HeadTc& H, const float* rowm, const float* rinvz, const fl
   if (!once) {
     set_smem(head_tc_dh2_kernel, B2_SMEM);
     set_smem(head_tc_dh2_tma_kernel<false>, B2T_SMEM);
+    set_smem(head_tc_dh2_wide_kernel, B2W_SMEM);
     set_smem(head_tc_dh2_tma_kernel<true>, B2T_SMEM);
     once = true;
   }
   int per;
   tiles_for(H.nA, n_split, &per);
   dim3 grid((H.n + TM - 1) / TM, n_split);
+  static int b2_wide = -1;
+  if (b2_wide < 0) b2_wide = env_int("CIRS_B2_WIDE", 0) ? 1 : 0;
+  if (tma_on() && b2_wide && !g_phase_host) {   // one N = 128 logits MMA batch per pair of tiles (experimental)
+    const int n_pairs = (H.nA + WN - 1) / WN, perp = (n_pairs + n_split - 1) / n_split;
+    CIRS_LAUNCH(head_tc_dh2_wide_kernel, grid, NTB + 32, B2W_SMEM, st, H, rowm, rinvz, coef, acta, perp, n_split, dh2_part,
+                ent_part);
+    CIRS_CHECK_LAUNCH();
+    return CIRS_OK;
+  }
   if (tma_on()) {
     if (g_phase_host)
       CIRS_LAUNCH(head_tc_dh2_tma_kernel<true>, grid, NTB + 32, B2T_SMEM, st, H, rowm, rinvz, coef, acta, per, n_split,

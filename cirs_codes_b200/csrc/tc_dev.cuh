@@ -109,9 +109,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 #ifndef CIRS_MBAR_MODE
 #define CIRS_MBAR_MODE 0
 #endif
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait_n(uint64_t* bar, uint32_t parity, uint32_t max_spins) {
   const uint32_t a = smem_u32(bar);
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+  for (uint32_t spin = 0; spin < max_spins; ++spin) {
     uint32_t ok;
 #if CIRS_MBAR_MODE == 1
     asm volatile(
@@ -136,6 +136,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   return false;
 }
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) { return mbar_wait_n(bar, parity, 1u << 28); }
 
 // ---- TMEM -> registers: warp w reads lanes 32*(w%4).., thread = lane, 32 consecutive FP32 columns ---------------
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
