@@ -137,3 +137,19 @@ def test_tc_policy_eval_matches_ffma(H):
     assert lib.cirs_head_tc_timeout() == 0
     G.assert_close(out[1][0], out[0][0], 1e-6, 1e-7, what="value")
     G.assert_close(out[1][1], out[0][1], 1e-5, what="log-prob")
+
+
+def test_b2_pair_kernel_variant_matches_ffma_and_fp64():
+    """head_tc_dh2_wide_kernel (one N = 128 logits MMA batch per pair of tiles; CIRS_B2_WIDE=1, a switch the library reads
+    once per process): the minibatch tests above -- tensor-core path against the FFMA path and FP64 autograd -- in a
+    child process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CIRS_B2_WIDE") == "1":
+        pytest.skip("this is the child process")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "test_tc_minibatch_matches_ffma_and_fp64"], cwd=root, env=dict(os.environ, CIRS_B2_WIDE="1"),
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-3000:] + "\n" + p.stderr[-2000:]
