@@ -12,7 +12,9 @@ JSON line (rank 0):  value = env-steps/s with the step's inputs (users, minibatc
 HBM, timed with CUDA events; e2e = the same through the public API with HOST inputs (pinned H2D of users and
 permutations, D2H of lengths / rewards / losses inside the timed region); roofline = the dominant kernel of the
 step, its duration measured live with CUDA events on the launching stream (cirs_profile_*); cpu_baseline = the CPU
-oracle port on a bounded sample on this box's host cores.  Multi-GPU: environments are sharded over ranks (weak
+oracle port on a bounded sample on this box's host cores.  Every iteration restores the initial policy / tracker / Adam
+state (frozen workload: env-steps per iteration is a constant of the config); the resident and the end-to-end iterations
+alternate inside one timed loop, each bracketed by its own pair of CUDA events.  Multi-GPU: environments are sharded over ranks (weak
 scaling: --gpus N runs N x B environments), one NCCL all-reduce of the policy gradient per PPO minibatch.
 """
 import argparse
